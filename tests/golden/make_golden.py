@@ -1,0 +1,165 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py
+
+The reference (/root/reference) ships no tests or golden vectors, so these fixtures -- outputs of
+the reference's own NeuralRenderer on seeded synthetic inputs -- are what pins parity:
+tests/test_oracle_golden.py checks oracle/nerf_oracle.py against them on CPU, and the `-m gpu`
+tests check the CUDA path against the same files on the B200 box (where /root/reference is absent).
+
+Cases
+  small_kfd0 / small_kfd4 : tiny dims (S=12, C=16, D=24, hidden 64); every input is stored.
+  full_s32                : BASELINE dims (C=128, D=384, hidden 512, Kc=Kf=64), 32^3 volume;
+                            inputs are regenerated from seeds (synthetic.py / init_params), only
+                            outputs and gradient projections are stored.
+  raygen                  : gen_rays for 60x80 (focal 76.18187) and rows of 128x128 (focal 153).
+"""
+import importlib
+import os
+import sys
+from unittest import mock
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader as L          # noqa: E402
+from oracle import nerf_oracle as O         # noqa: E402
+
+syn = importlib.import_module("real-robot-nerf-actor_b200.synthetic")
+
+
+def load_params_into(renderer, params):
+    sd = renderer.state_dict()
+    for k, v in params.items():
+        sd["nerf_model.mlp_coarse." + k].copy_(v)
+
+
+def run_case(name, S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, focal, store_inputs, seed=0,
+             perturb=True):
+    torch.manual_seed(seed)
+    cfg = L.default_cfg(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H,
+                        n_coarse=Kc, n_fine=Kf, n_fine_depth=Kfd, ray_chunk_size=n_rays,
+                        mlp=dict(d_hidden=hidden), eval_batch_size=1024)
+    bounds = torch.tensor(syn.BOUNDS)
+    ren = L.build_reference_renderer(cfg, bounds)
+    params = O.init_params(d_in=42, d_latent=C, d_hidden=hidden, d_out=4 + D, seed=seed)
+    # non-zero biases so that the bias path is exercised
+    g = torch.Generator().manual_seed(77 + seed)
+    for k in params:
+        if k.endswith(".bias"):
+            params[k] = 0.05 * torch.randn(params[k].shape, generator=g)
+    load_params_into(ren, params)
+    vol = syn.make_volume(SB, C, S, seed=seed).requires_grad_(True)
+    poses = syn.arc_poses(SB)
+    focal_t = torch.tensor(focal, dtype=torch.float32)
+    idx = syn.pick_ray_indices(H * W, n_rays, seed=seed)
+    R = SB * n_rays
+    noise = syn.make_noise(R, Kc, Kf - Kfd, seed=seed, perturb=perturb)
+    gd = torch.Generator().manual_seed(5000 + seed)
+    noise_depth = torch.randn(R, Kfd, generator=gd) if Kfd > 0 else None
+    gt_rgb_img = torch.rand(SB, H, W, 3, generator=gd)
+    gt_embed_img = torch.randn(SB, H, W, D, generator=gd)
+
+    draws = [noise.get("coarse")]
+    if Kf - Kfd > 0:
+        draws += [noise["u"], noise.get("fine")]
+    if Kfd > 0:
+        draws += [noise_depth]
+    ren.train()
+    with L.inject_noise(draws), \
+            mock.patch.object(torch, "randint", lambda *a, **k: idx.clone()):
+        out = ren(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=vol,
+                  voxel_poses=poses, focal=focal_t, gt_rgb=gt_rgb_img, gt_depth=None,
+                  gt_pose=poses, c=None, lang_goal=None, gt_embed=gt_embed_img)
+    out["loss"].backward()
+    grads = {k: p.grad.clone() for k, p in ren.nerf_model.mlp_coarse.named_parameters()}
+    vgrad = vol.grad.clone()
+
+    # second, no-grad pass for the intermediate tensors (same noise)
+    rays_full = ren_rays = None
+    with torch.no_grad():
+        U = sys.modules["_nrf_reference_utils"]
+        rays_full = U.gen_rays(poses, W, H, focal_t, cfg.z_near, cfg.z_far, c=None)
+        rays = rays_full.reshape(SB, H * W, 8)[:, idx]
+        ren.encode(None, None, None, vol.detach(), poses, focal_t, None)
+        with L.inject_noise(list(draws)):
+            o = ren.forward_nerf(rays, want_weights=True)
+        # z samples, by replaying the samplers with the same noise
+        r = rays.reshape(-1, 8)
+        with L.inject_noise([noise.get("coarse")]):
+            z_c = ren.sample_coarse(r)
+
+    fx = {"meta": np.array([S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed]),
+          "focal": np.float32(focal), "idx": idx.numpy(), "rays": rays.numpy(), "z_coarse": z_c.numpy(),
+          "loss": np.float32(out["loss"].item()),
+          "loss_items": np.array([out[k] for k in ("loss_rgb_coarse", "loss_rgb_fine", "loss_embed_coarse",
+                                                   "loss_embed_fine", "psnr")], dtype=np.float32)}
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "weights"):
+            fx[f"{lvl}_{k}"] = o[lvl][k].numpy()
+    if noise_depth is not None:
+        fx["noise_depth"] = noise_depth.numpy()
+    gsign = torch.Generator().manual_seed(99)
+    sign = (torch.randint(0, 2, (C,), generator=gsign) * 2 - 1).float()
+    if store_inputs:
+        fx["vol"] = vol.detach().numpy()
+        fx["vgrad"] = vgrad.numpy()
+        for k, v in params.items():
+            fx["param." + k] = v.numpy()
+        for k, v in grads.items():
+            fx["grad." + k] = v.numpy()
+        for k, v in noise.items():
+            fx["noise_" + k] = v.numpy()
+        fx["gt_rgb_img"] = gt_rgb_img.numpy()
+        fx["gt_embed_img"] = gt_embed_img.numpy()
+        fx["poses"] = poses.numpy()
+    else:
+        fx["vgrad_sum"] = vgrad.sum(1).numpy()
+        fx["vgrad_sign"] = (vgrad * sign.view(1, C, 1, 1, 1)).sum(1).numpy()
+        fx["vgrad_norm"] = np.float32(vgrad.norm().item())
+        for k, v in grads.items():
+            fx["gradnorm." + k] = np.float32(v.norm().item())
+            if v.numel() <= 512 * 42 or k.endswith(".bias"):
+                fx["grad." + k] = v.numpy()
+            else:                      # 64 seeded rows of each big matrix
+                rows = torch.randperm(v.shape[0], generator=torch.Generator().manual_seed(5))[:64]
+                fx["gradrows." + k] = v[rows].numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **fx)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "loss", float(out["loss"]))
+
+
+def run_raygen():
+    L.load_reference()
+    U = sys.modules["_nrf_reference_utils"]
+    poses = syn.arc_poses(3)
+    fx = {"poses": poses.numpy()}
+    r = U.gen_rays(poses, 80, 60, torch.tensor(76.18187, dtype=torch.float32), 1.2, 4.0)
+    fx["rays_60x80"] = r.numpy()
+    r = U.gen_rays(poses[:2], 128, 128, torch.tensor(153.0, dtype=torch.float32), 1.2, 4.0)
+    fx["rays_128_rows"] = r[:, ::16].numpy()
+    c = torch.tensor([70.5, 61.25])
+    r = U.gen_rays(poses[:1], 128, 128, torch.tensor([150.0, 151.0]), 0.5, 3.0, c=c)
+    fx["rays_128_c_rows"] = r[:, ::32].numpy()
+    pe = U.PositionalEncoding(6, 3, 1.5, True)
+    x = torch.rand(257, 3, generator=torch.Generator().manual_seed(3)) * 1.4 - 0.2
+    fx["pe_x"] = x.numpy()
+    fx["pe_out"] = pe(x).numpy()
+    np.savez_compressed(os.path.join(HERE, "raygen_pe.npz"), **fx)
+    print("raygen_pe done")
+
+
+if __name__ == "__main__":
+    run_raygen()
+    run_case("small_kfd0", S=12, C=16, D=24, hidden=64, SB=2, n_rays=48, Kc=16, Kf=16, Kfd=0,
+             H=16, W=16, focal=19.0, store_inputs=True)
+    run_case("small_kfd4", S=12, C=16, D=24, hidden=64, SB=2, n_rays=48, Kc=16, Kf=16, Kfd=4,
+             H=16, W=16, focal=19.0, store_inputs=True, seed=1)
+    run_case("small_noperturb", S=12, C=16, D=24, hidden=64, SB=1, n_rays=40, Kc=16, Kf=8, Kfd=0,
+             H=16, W=16, focal=19.0, store_inputs=True, seed=2, perturb=False)
+    run_case("full_s32", S=32, C=128, D=384, hidden=512, SB=2, n_rays=64, Kc=64, Kf=64, Kfd=0,
+             H=128, W=128, focal=153.0, store_inputs=False, seed=3)
