@@ -1,0 +1,194 @@
+/* nrf_b200.h -- C ABI of the B200-native feature-NeRF render path.
+ *
+ * One shared library (real-robot-nerf-actor_b200/libnrf_b200.so), plain pointers and sizes,
+ * no torch types.  Every entry point
+ *   - takes DEVICE pointers (unless the name says otherwise) and a cudaStream_t passed as void*,
+ *   - enqueues work on that stream and returns immediately,
+ *   - returns 0 on success or a negative NRF_E* code (never throws, keeps no global mutable state
+ *     apart from a read-only driver entry point looked up once),
+ *   - does not allocate: the caller (PyTorch's caching allocator on the Python side) owns all memory.
+ *
+ * The reference has no FFI: its boundary is the Python class NeuralRenderer
+ * (/root/reference/neural_rendering.py:86-711).  Each function below names the reference
+ * lines whose work it replaces; INTEGRATION.md shows the ctypes binding and how
+ * NeuralRenderer.forward_nerf is re-expressed on top of them.
+ *
+ * Layouts
+ *   rays      (R,8) fp32 row-major  [origin xyz, dir xyz, near, far]      (utils.py:504-506)
+ *   z         (R,K) fp32            sample depths along each ray
+ *   volume    channel-first  (SB,C,S0,S1,S2) fp32 as the caller holds it   (models_embed.py:147)
+ *             channels-last  (SB,S0,S1,S2,C) fp32 as the kernels read it
+ *             grid x indexes S2, y indexes S1, z indexes S0 (models_embed.py:275 quirk)
+ *   field in  (N, kin_pad) rows [latent C | PE(xyz) 39 | viewdir 3 | zeros], N = R*K,
+ *             sample n = ray (n / K), depth index (n % K); bf16 (tensor-core mode) or fp32
+ *   field out (N, 4+D) fp32 RAW MLP outputs [rgb(3) | sigma | embed(D)] before sigmoid / relu
+ */
+#ifndef NRF_B200_H
+#define NRF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRF_OK 0
+#define NRF_EINVAL (-1)   /* bad argument (null pointer, size, alignment)   */
+#define NRF_ECUDA (-2)    /* a CUDA runtime / driver call failed            */
+#define NRF_ENOSUP (-3)   /* shape outside what the kernels are built for   */
+
+/* precision of the field MLP */
+#define NRF_PREC_BF16 0   /* bf16 operands, fp32 accumulate, tcgen05 tensor cores */
+#define NRF_PREC_FP32 1   /* fp32 SIMT FFMA: parity-grade mode                    */
+
+const char* nrf_version(void);
+const char* nrf_last_error(void);   /* text of the last failure on this thread */
+
+/* ---- rays (utils.py:444-506 unproj_map + gen_rays) ------------------------------------------
+ * poses (n_img,4,4) cam->world fp32; rays_out (n_img,H,W,8). */
+int nrf_raygen(const float* poses, int n_img, int W, int H, float fx, float fy, float cx, float cy,
+               float z_near, float z_far, float* rays_out, void* stream);
+
+/* ---- stratified sampling (neural_rendering.py:159-176 sample_coarse) ------------------------
+ * base (Kc) = linspace(0, 1-1/Kc, Kc); jitter (R,Kc) in [0,1) or NULL (perturb off). */
+int nrf_sample_coarse(const float* rays, int R, int Kc, const float* base, const float* jitter,
+                      int lindisp, float* z_out, void* stream);
+
+/* ---- importance sampling (neural_rendering.py:179-207 sample_fine) ---------------------------
+ * weights (R,Kc) coarse compositing weights, or cdf (R,Kc+1) when `cdf` is non-NULL (then weights
+ * is ignored); u, jitter (R,Kf) (jitter NULL = 0).  Writes z_out[r*ldz + k], k<Kf, and, when
+ * ind_out != NULL, the bin indices (R,Kf) as fp32 (the reference's `inds`). */
+int nrf_sample_fine(const float* rays, const float* weights, const float* cdf, int R, int Kc,
+                    const float* u, const float* jitter, int Kf, int lindisp, float* z_out, int ldz,
+                    float* ind_out, void* stream);
+
+/* ---- per-ray ascending sort (neural_rendering.py:463 torch.sort) ----------------------------
+ * z (R,K) sorted in place, K <= 1024; perm_out (R,K) int32 source positions or NULL. */
+int nrf_sort_rows(float* z, int R, int K, int32_t* perm_out, void* stream);
+
+/* ---- volume layout ---------------------------------------------------------------------------
+ * (SB,C,V) <-> (SB,V,C), V = S0*S1*S2.  The reference reads the channel-first tensor through
+ * F.grid_sample (models_embed.py:275); the gather kernel wants one contiguous C-vector per corner. */
+int nrf_volume_to_channels_last(const float* src, float* dst, int SB, int C, int64_t V, void* stream);
+int nrf_volume_to_channels_first(const float* src, float* dst, int SB, int C, int64_t V, void* stream);
+
+/* ---- field input: points + canonicalise + trilinear gather + positional encoding -------------
+ * Replaces neural_rendering.py:246-283 (points, viewdirs), models_embed.py:185-203
+ * (world_to_canonical), :259-277 (grid_sample), utils.py:545-557 (PositionalEncoding) and the
+ * concatenations at models_embed.py:366,405.  vol_cl is channels-last.  bounds = 6 floats (HOST).
+ * out: (N, ld_out) bf16 if out_bf16 else fp32; columns >= C+42 are zero-filled up to ld_out.
+ * rays_per_scene = R / SB. points_out (N,3) fp32 optional (debug / parity), may be NULL. */
+int nrf_encode_points(const float* rays, const float* z, int R, int K, int rays_per_scene,
+                      const float* vol_cl, int SB, int C, int S0, int S1, int S2,
+                      const float* bounds_host, int num_freqs, float freq_factor,
+                      void* out, int ld_out, int out_bf16, float* points_out, void* stream);
+
+/* ---- volume gradient: transpose of the trilinear gather (autograd of models_embed.py:275) ----
+ * dlatent (N, ld) fp32; grad_cl channels-last (SB,S0,S1,S2,C), accumulated into (caller zeroes). */
+int nrf_scatter_volume_grad(const float* rays, const float* z, int R, int K, int rays_per_scene,
+                            const float* dlatent, int ld, float* grad_cl, int SB, int C, int S0,
+                            int S1, int S2, const float* bounds_host, void* stream);
+
+/* ---- alpha compositing (neural_rendering.py:239-243,316-359) ---------------------------------
+ * field_out (N, ldo) raw; heads sigmoid(rgb), relu(sigma) (models_embed.py:444-466) applied here.
+ * weights (R,K), rgb (R,3), embed (R,D), depth (R). */
+int nrf_composite_fwd(const float* field_out, int ldo, const float* z, const float* rays, int R, int K,
+                      int D, int white_bkgd, float* weights, float* rgb, float* embed, float* depth,
+                      void* stream);
+
+/* Backward of the above (closed form).  d_weights and d_z may be NULL.
+ * d_field (N, ldg): gradient w.r.t. the RAW MLP outputs, bf16 if out_bf16 else fp32; columns
+ * [4+D, ldg) are zero-filled. */
+int nrf_composite_bwd(const float* field_out, int ldo, const float* z, const float* rays, int R, int K,
+                      int D, int white_bkgd, const float* d_rgb, const float* d_embed,
+                      const float* d_depth, const float* d_weights, void* d_field, int ldg,
+                      int out_bf16, float* d_z, void* stream);
+
+/* ---- GEMM building block of the field MLP ----------------------------------------------------
+ * out = resid + mask( A . B^T + bias ),   A = [A1 | A2] along K,  B (N,K) row-major (nn.Linear)
+ *   A1 (M,K1) lda1, A2 (M,K2) lda2 (K2 may be 0), operand type bf16 (NRF_PREC_BF16) or fp32
+ *   bias (N) fp32 or NULL; mask_src (M,N) operand-typed or NULL: value zeroed where mask_src <= 0
+ *   resid (M,N) fp32 or NULL (may alias out_f32)
+ *   out_f32 (M,n_store) fp32 or NULL; out_act (M,n_store) operand-typed or NULL, relu'd if relu_act
+ * Only columns < n_store are written.  bf16 mode: K1,K2 multiples of 64, N multiple of 128. */
+typedef struct {
+  const void* A1; int K1; int lda1;
+  const void* A2; int K2; int lda2;
+  const void* B;  int ldb;
+  int M; int N; int n_store;
+  const float* bias;
+  const void* mask_src; int ldmask;
+  const float* resid; int ldr;
+  float* out_f32; int ldo;
+  void* out_act; int ldact; int relu_act;
+} NrfGemm;
+int nrf_gemm(const NrfGemm* g, int precision, void* stream);
+
+/* Weight gradient dW (N,K) += G^T . A with G (M,N) ldg, A (M,K) lda operand-typed; dW fp32 ldw.
+ * workspace: fp32, >= nrf_wgrad_workspace_bytes(N,K) (bf16 mode; split-K partials), may be NULL
+ * in fp32 mode.  Only rows < n_valid and columns < k_valid of dW are touched.
+ * dbias (n_valid) += column sums of G when non-NULL. */
+int64_t nrf_wgrad_workspace_bytes(int N, int K);
+int nrf_wgrad(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
+              int k_valid, float* dW, int ldw, float* dbias, void* workspace, int precision,
+              void* stream);
+
+/* ---- the ResnetFC field MLP (resnetfc.py:55-64,146-195) --------------------------------------
+ * Parameters in the reference's own layout (fp32, nn.Linear (out,in) row-major).
+ * lin_z has n_lin_z = min(combine_layer, n_blocks) entries. */
+#define NRF_MAX_BLOCKS 8
+typedef struct {
+  int d_in;        /* 42 = PE(39) + viewdir(3)                     */
+  int d_latent;    /* C                                             */
+  int d_hidden;    /* 512                                           */
+  int d_out;       /* 4 + D                                         */
+  int n_blocks;    /* 5                                             */
+  int n_lin_z;     /* 3                                             */
+  const float* lin_in_w;  const float* lin_in_b;
+  const float* lin_out_w; const float* lin_out_b;
+  const float* fc0_w[NRF_MAX_BLOCKS]; const float* fc0_b[NRF_MAX_BLOCKS];
+  const float* fc1_w[NRF_MAX_BLOCKS]; const float* fc1_b[NRF_MAX_BLOCKS];
+  const float* lin_z_w[NRF_MAX_BLOCKS]; const float* lin_z_b[NRF_MAX_BLOCKS];
+} NrfMlpParams;
+
+/* Same shape as NrfMlpParams, pointing at fp32 gradient buffers that are ACCUMULATED into. */
+typedef struct {
+  float* lin_in_w;  float* lin_in_b;
+  float* lin_out_w; float* lin_out_b;
+  float* fc0_w[NRF_MAX_BLOCKS]; float* fc0_b[NRF_MAX_BLOCKS];
+  float* fc1_w[NRF_MAX_BLOCKS]; float* fc1_b[NRF_MAX_BLOCKS];
+  float* lin_z_w[NRF_MAX_BLOCKS]; float* lin_z_b[NRF_MAX_BLOCKS];
+} NrfMlpGrads;
+
+/* Sizes (bytes) of the caller-provided buffers for a given shape / precision. */
+typedef struct {
+  int kin_pad;            /* row length of the field-input matrix                 */
+  int dout_pad;           /* row length of d_field (gradient of raw outputs)      */
+  int64_t packed_bytes;   /* packed / transposed weight cache                     */
+  int64_t fwd_bytes_per_sample;   /* activations kept by nrf_mlp_fwd              */
+  int64_t bwd_bytes_per_sample;   /* scratch of nrf_mlp_bwd                       */
+  int64_t bwd_fixed_bytes;        /* split-K partials etc.                        */
+} NrfMlpSizes;
+int nrf_mlp_sizes(const NrfMlpParams* p, int precision, NrfMlpSizes* out);
+
+/* Packs the fp32 parameters into the operand layout the GEMMs read ([W_z0 | W_in] etc.). */
+int nrf_mlp_pack(const NrfMlpParams* p, int precision, void* packed, void* stream);
+
+/* Forward over N samples.  field_in (N,kin_pad) operand-typed; acts: fwd_bytes_per_sample*N bytes
+ * (kept for the backward; with keep_acts == 0 only 2 ping-pong layers are needed and the caller
+ * may pass a buffer of nrf_mlp_sizes().fwd_bytes_per_sample*N bytes anyway);
+ * field_out (N,d_out) fp32 raw outputs. */
+int nrf_mlp_fwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                int64_t N, void* acts, float* field_out, void* stream);
+
+/* Backward: d_field (N,dout_pad) operand-typed gradient of the raw outputs (from
+ * nrf_composite_bwd); accumulates parameter gradients into `grads` and writes
+ * dlatent (N,d_latent) fp32.  scratch: bwd_bytes_per_sample*N + bwd_fixed_bytes bytes. */
+int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* grads,
+                float* dlatent, void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRF_B200_H */

@@ -1,0 +1,65 @@
+// C-ABI glue: error text, device query, and the GEMM entry points of include/nrf_b200.h.
+#include <stdarg.h>
+#include "gemm_common.cuh"
+
+namespace nrf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" const char* nrf_version(void) { return "nrf_b200 0.1 (sm_100a; tcgen05/TMEM/TMA)"; }
+extern "C" const char* nrf_last_error(void) { return g_err; }
+
+extern "C" int nrf_gemm(const NrfGemm* g, int precision, void* stream) {
+  NRF_REQUIRE(g && g->A1 && g->B && g->M > 0 && g->N > 0 && g->K1 > 0 && g->K2 >= 0, NRF_EINVAL,
+              "nrf_gemm: bad arguments");
+  NRF_REQUIRE(g->K2 == 0 || g->A2, NRF_EINVAL, "nrf_gemm: K2 > 0 needs A2");
+  NRF_REQUIRE(g->n_store > 0 && g->n_store <= g->N, NRF_EINVAL, "nrf_gemm: n_store out of range");
+  NRF_REQUIRE(g->out_f32 || g->out_act, NRF_EINVAL, "nrf_gemm: no output");
+  if (precision == NRF_PREC_BF16) return gemm_tc_launch(*g, as_stream(stream));
+  if (precision == NRF_PREC_FP32) return gemm_simt_launch(*g, as_stream(stream));
+  set_error("nrf_gemm: unknown precision %d", precision);
+  return NRF_EINVAL;
+}
+
+extern "C" int64_t nrf_wgrad_workspace_bytes(int N, int K) {
+  (void)N; (void)K;
+  return 0;   // partial tiles are reduced with fp32 red.global.add; no workspace needed
+}
+
+extern "C" int nrf_wgrad(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
+                         int k_valid, float* dW, int ldw, float* dbias, void* workspace, int precision,
+                         void* stream) {
+  NRF_REQUIRE(G && A && dW && M > 0 && N > 0 && K > 0, NRF_EINVAL, "nrf_wgrad: bad arguments");
+  NRF_REQUIRE(n_valid > 0 && n_valid <= N && k_valid > 0 && k_valid <= K, NRF_EINVAL,
+              "nrf_wgrad: n_valid/k_valid out of range");
+  if (precision == NRF_PREC_BF16)
+    return wgrad_tc_launch(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace,
+                           as_stream(stream));
+  if (precision == NRF_PREC_FP32)
+    return wgrad_simt_launch(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, as_stream(stream));
+  set_error("nrf_wgrad: unknown precision %d", precision);
+  return NRF_EINVAL;
+}

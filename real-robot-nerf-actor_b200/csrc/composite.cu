@@ -1,0 +1,322 @@
+// Alpha compositing of RGB / depth / D-channel feature along each ray, forward and closed-form
+// backward.  One warp per ray; transmittance is a warp-shuffle product scan.
+//   forward  <- neural_rendering.py:239-243 (deltas), :339-359 (alphas, cumprod, weighted sums),
+//               models_embed.py:444-466 (sigmoid / relu heads, applied here to the raw MLP outputs)
+//   backward <- autograd of the same lines, closed form in SURVEY.md 9.2
+#include "common.cuh"
+
+namespace nrf {
+
+constexpr int kMaxPerLane = 32;   // K <= 1024
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// Computes, for the warp's ray, alpha_k / T_k / w_k for the lane's contiguous chunk of samples.
+// chunk = ceil(K/32); lane owns k in [lane*chunk, min(K,(lane+1)*chunk)).
+struct RayScan {
+  int k0, k1;
+};
+
+// Exclusive product scan across lanes of `local` (the product of a lane's chunk).
+__device__ __forceinline__ float warp_exclusive_prod(float local, int lane) {
+  float incl = local;
+#pragma unroll
+  for (int o = 1; o < kWarp; o <<= 1) {
+    float v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= v;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  return lane == 0 ? 1.0f : excl;
+}
+
+// smem per warp: w[K], aux[K]
+template <bool kBackward>
+__device__ __forceinline__ void ray_weights(const float* __restrict__ field, int ldo,
+                                            const float* __restrict__ zrow, float far, int K, int lane,
+                                            float* __restrict__ s_w, float* __restrict__ s_alpha,
+                                            float* __restrict__ s_T, float* __restrict__ s_delta) {
+  int chunk = (K + kWarp - 1) / kWarp;
+  int k0 = lane * chunk, k1 = min(K, k0 + chunk);
+  float local = 1.0f;
+  for (int k = k0; k < k1; ++k) {
+    float zk = zrow[k];
+    float delta = (k + 1 < K ? zrow[k + 1] : far) - zk;
+    float sigma = fmaxf(field[(int64_t)k * ldo + 3], 0.0f);
+    float alpha = 1.0f - expf(-delta * sigma);
+    s_alpha[k] = alpha;
+    if (kBackward) s_delta[k] = delta;
+    local *= (1.0f - alpha) + 1e-10f;
+  }
+  float T = warp_exclusive_prod(local, lane);
+  for (int k = k0; k < k1; ++k) {
+    float alpha = s_alpha[k];
+    s_w[k] = alpha * T;
+    if (kBackward) s_T[k] = T;
+    T *= (1.0f - alpha) + 1e-10f;
+  }
+  __syncwarp();
+}
+
+// field row = [r g b sigma | embed(D)], D % 4 == 0 and ldo % 4 == 0 -> float4 everywhere.
+__global__ void __launch_bounds__(128) composite_fwd_kernel(
+    const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
+    int R, int K, int D, int white_bkgd, float* __restrict__ weights, float* __restrict__ rgb,
+    float* __restrict__ embed, float* __restrict__ depth) {
+  extern __shared__ float smem[];
+  int warps = blockDim.x / kWarp, wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  int r = blockIdx.x * warps + wid;
+  if (r >= R) return;
+  float* s_w = smem + (size_t)wid * 2 * K;
+  float* s_alpha = s_w + K;
+  const float* f = field + (int64_t)r * K * ldo;
+  const float* zrow = z + (int64_t)r * K;
+  float far = rays[(int64_t)r * 8 + 7];
+  ray_weights<false>(f, ldo, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr);
+
+  const int nvec = (4 + D) / 4;             // float4 per row
+  constexpr int kMaxVec = 8;                // up to (4+D) <= 1024 channels
+  float4 acc[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float dsum = 0.f, wsum = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float w = s_w[k];
+    const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int v = lane + i * kWarp;
+      if (v < nvec) {
+        float4 x = __ldg(row + v);
+        if (v == 0) {
+          x.x = sigmoidf_(x.x); x.y = sigmoidf_(x.y); x.z = sigmoidf_(x.z); x.w = 0.f;
+        }
+        acc[i].x = fmaf(w, x.x, acc[i].x);
+        acc[i].y = fmaf(w, x.y, acc[i].y);
+        acc[i].z = fmaf(w, x.z, acc[i].z);
+        acc[i].w = fmaf(w, x.w, acc[i].w);
+      }
+    }
+    if (lane == 0) {
+      dsum = fmaf(w, zrow[k], dsum);
+      wsum += w;
+    }
+  }
+  for (int k = lane; k < K; k += kWarp) weights[(int64_t)r * K + k] = s_w[k];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    int v = lane + i * kWarp;
+    if (v < nvec) {
+      if (v == 0) {
+        float add = white_bkgd ? 1.0f - wsum : 0.0f;
+        rgb[(int64_t)r * 3 + 0] = acc[i].x + add;
+        rgb[(int64_t)r * 3 + 1] = acc[i].y + add;
+        rgb[(int64_t)r * 3 + 2] = acc[i].z + add;
+        depth[r] = dsum;
+      } else {
+        *reinterpret_cast<float4*>(embed + (int64_t)r * D + (v - 1) * 4) = acc[i];
+      }
+    }
+  }
+}
+
+template <typename T> __device__ __forceinline__ void store_grad4(T* p, float4 v);
+template <> __device__ __forceinline__ void store_grad4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <> __device__ __forceinline__ void store_grad4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// Backward.  With g_k = <d_rgb, rgb_k> + <d_embed, e_k> + d_depth z_k (+ d_w_k):
+//   dL/dsigma_k = 1[raw>0] delta_k (1-alpha_k) ( T_k g_k - S_k / (1-alpha_k+eps) ),  S_k = sum_{j>k} w_j g_j
+//   dL/draw_rgb = w_k d_rgb s(1-s);  dL/de_k = w_k d_embed
+//   white_bkgd adds (-sum_c d_rgb_c) to every g_k.
+//   dL/dz_k (optional) = d_depth w_k + dL/ddelta_{k-1} - dL/ddelta_k,
+//   dL/ddelta_k = relu(sigma_k)(1-alpha_k)(same bracket).
+template <typename T>
+__global__ void __launch_bounds__(128) composite_bwd_kernel(
+    const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
+    int R, int K, int D, int white_bkgd, const float* __restrict__ d_rgb,
+    const float* __restrict__ d_embed, const float* __restrict__ d_depth,
+    const float* __restrict__ d_weights, T* __restrict__ d_field, int ldg, float* __restrict__ d_z) {
+  extern __shared__ float smem[];
+  int warps = blockDim.x / kWarp, wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  int r = blockIdx.x * warps + wid;
+  if (r >= R) return;
+  float* s_w = smem + (size_t)wid * 6 * K;
+  float* s_alpha = s_w + K;
+  float* s_T = s_alpha + K;
+  float* s_delta = s_T + K;
+  float* s_g = s_delta + K;
+  float* s_ds = s_g + K;   // dL/dsigma (pre relu-gate) then reused
+  const float* f = field + (int64_t)r * K * ldo;
+  const float* zrow = z + (int64_t)r * K;
+  float far = rays[(int64_t)r * 8 + 7];
+  ray_weights<true>(f, ldo, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta);
+
+  const int nvec = (4 + D) / 4;
+  constexpr int kMaxVec = 8;
+  // per-lane slice of the output gradients
+  float4 dout[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    int v = lane + i * kWarp;
+    dout[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (v < nvec) {
+      if (v == 0) {
+        dout[i] = make_float4(d_rgb[(int64_t)r * 3 + 0], d_rgb[(int64_t)r * 3 + 1],
+                              d_rgb[(int64_t)r * 3 + 2], 0.f);
+      } else {
+        dout[i] = *reinterpret_cast<const float4*>(d_embed + (int64_t)r * D + (v - 1) * 4);
+      }
+    }
+  }
+  float dd = d_depth ? d_depth[r] : 0.0f;
+  float bk = 0.f;
+  if (white_bkgd) bk = -(d_rgb[(int64_t)r * 3 + 0] + d_rgb[(int64_t)r * 3 + 1] + d_rgb[(int64_t)r * 3 + 2]);
+
+  // pass A: g_k
+  for (int k = 0; k < K; ++k) {
+    const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int v = lane + i * kWarp;
+      if (v < nvec) {
+        float4 x = __ldg(row + v);
+        if (v == 0) {
+          x.x = sigmoidf_(x.x); x.y = sigmoidf_(x.y); x.z = sigmoidf_(x.z); x.w = 0.f;
+        }
+        part += x.x * dout[i].x + x.y * dout[i].y + x.z * dout[i].z + x.w * dout[i].w;
+      }
+    }
+    part = warp_sum(part);
+    if (lane == 0) {
+      float g = part + dd * zrow[k] + bk;
+      if (d_weights) g += d_weights[(int64_t)r * K + k];
+      s_g[k] = g;
+    }
+  }
+  __syncwarp();
+  // suffix sums S_k = sum_{j>k} w_j g_j : lane-chunked reverse scan
+  {
+    int chunk = (K + kWarp - 1) / kWarp;
+    int k0 = lane * chunk, k1 = min(K, k0 + chunk);
+    float local = 0.f;
+    for (int k = k0; k < k1; ++k) local += s_w[k] * s_g[k];
+    // inclusive suffix over lanes
+    float incl = local;
+#pragma unroll
+    for (int o = 1; o < kWarp; o <<= 1) {
+      float v = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < kWarp) incl += v;
+    }
+    float run = incl - local;   // sum over later lanes
+    for (int k = k1 - 1; k >= k0; --k) {
+      float alpha = s_alpha[k];
+      float one_m = 1.0f - alpha;
+      float bracket = s_T[k] * s_g[k] - run / (one_m + 1e-10f);
+      run += s_w[k] * s_g[k];
+      s_ds[k] = one_m * bracket;     // multiply by delta (for dsigma) or relu(sigma) (for ddelta) later
+    }
+  }
+  __syncwarp();
+  // pass B: write d_field rows
+  for (int k = 0; k < K; ++k) {
+    float w = s_w[k];
+    const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
+    T* grow = d_field + ((int64_t)r * K + k) * ldg;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int v = lane + i * kWarp;
+      if (v < nvec) {
+        float4 gq;
+        if (v == 0) {
+          float4 x = __ldg(row);
+          float sr = sigmoidf_(x.x), sg = sigmoidf_(x.y), sb = sigmoidf_(x.z);
+          gq.x = w * dout[i].x * sr * (1.0f - sr);
+          gq.y = w * dout[i].y * sg * (1.0f - sg);
+          gq.z = w * dout[i].z * sb * (1.0f - sb);
+          gq.w = x.w > 0.0f ? s_delta[k] * s_ds[k] : 0.0f;
+        } else {
+          gq = make_float4(w * dout[i].x, w * dout[i].y, w * dout[i].z, w * dout[i].w);
+        }
+        store_grad4<T>(grow + v * 4, gq);
+      }
+    }
+    for (int c = 4 + D + lane; c < ldg; c += kWarp) grow[c] = T(0.0f);
+  }
+  if (d_z) {
+    for (int k = lane; k < K; k += kWarp) {
+      float sig_k = fmaxf(f[(int64_t)k * ldo + 3], 0.0f);
+      float dl_k = sig_k * s_ds[k];
+      float dl_km1 = 0.f;
+      if (k > 0) dl_km1 = fmaxf(f[(int64_t)(k - 1) * ldo + 3], 0.0f) * s_ds[k - 1];
+      d_z[(int64_t)r * K + k] = dd * s_w[k] + dl_km1 - dl_k;
+    }
+  }
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+static int check_composite(const char* who, int R, int K, int D, int ldo) {
+  NRF_REQUIRE(R > 0 && K > 0 && D >= 0, NRF_EINVAL, "%s: bad sizes", who);
+  NRF_REQUIRE(K <= kWarp * kMaxPerLane, NRF_ENOSUP, "%s: K=%d > 1024", who, K);
+  NRF_REQUIRE(D % 4 == 0 && ldo % 4 == 0 && ldo >= 4 + D, NRF_ENOSUP,
+              "%s: D=%d, ldo=%d must be multiples of 4 with ldo >= 4+D", who, D, ldo);
+  NRF_REQUIRE((4 + D) / 4 <= 8 * kWarp, NRF_ENOSUP, "%s: 4+D=%d > 1024", who, 4 + D);
+  return NRF_OK;
+}
+
+extern "C" int nrf_composite_fwd(const float* field_out, int ldo, const float* z, const float* rays,
+                                 int R, int K, int D, int white_bkgd, float* weights, float* rgb,
+                                 float* embed, float* depth, void* stream) {
+  NRF_REQUIRE(field_out && z && rays && weights && rgb && embed && depth, NRF_EINVAL,
+              "nrf_composite_fwd: null pointer");
+  int rc = check_composite("nrf_composite_fwd", R, K, D, ldo);
+  if (rc) return rc;
+  int warps = 4;
+  size_t smem = (size_t)warps * 2 * K * sizeof(float);
+  composite_fwd_kernel<<<(R + warps - 1) / warps, warps * kWarp, smem, as_stream(stream)>>>(
+      field_out, ldo, z, rays, R, K, D, white_bkgd, weights, rgb, embed, depth);
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
+
+extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z, const float* rays,
+                                 int R, int K, int D, int white_bkgd, const float* d_rgb,
+                                 const float* d_embed, const float* d_depth, const float* d_weights,
+                                 void* d_field, int ldg, int out_bf16, float* d_z, void* stream) {
+  NRF_REQUIRE(field_out && z && rays && d_rgb && d_embed && d_field, NRF_EINVAL,
+              "nrf_composite_bwd: null pointer");
+  int rc = check_composite("nrf_composite_bwd", R, K, D, ldo);
+  if (rc) return rc;
+  NRF_REQUIRE(ldg >= 4 + D && ldg % 4 == 0, NRF_EINVAL, "nrf_composite_bwd: ldg=%d", ldg);
+  int warps = 4;
+  size_t smem = (size_t)warps * 6 * K * sizeof(float);
+  NRF_REQUIRE(smem <= 96 * 1024, NRF_ENOSUP, "nrf_composite_bwd: K too large for shared memory");
+  dim3 grid((R + warps - 1) / warps), block(warps * kWarp);
+  if (out_bf16) {
+    if (smem > 48 * 1024)
+      NRF_CUDA_OK(cudaFuncSetAttribute(composite_bwd_kernel<__nv_bfloat16>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    composite_bwd_kernel<__nv_bfloat16><<<grid, block, smem, as_stream(stream)>>>(
+        field_out, ldo, z, rays, R, K, D, white_bkgd, d_rgb, d_embed, d_depth, d_weights,
+        reinterpret_cast<__nv_bfloat16*>(d_field), ldg, d_z);
+  } else {
+    if (smem > 48 * 1024)
+      NRF_CUDA_OK(cudaFuncSetAttribute(composite_bwd_kernel<float>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    composite_bwd_kernel<float><<<grid, block, smem, as_stream(stream)>>>(
+        field_out, ldo, z, rays, R, K, D, white_bkgd, d_rgb, d_embed, d_depth, d_weights,
+        reinterpret_cast<float*>(d_field), ldg, d_z);
+  }
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}

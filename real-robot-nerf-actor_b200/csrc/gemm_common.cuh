@@ -1,0 +1,43 @@
+// Epilogue shared by the tcgen05 (bf16) and SIMT (fp32) GEMMs of the field MLP.
+//   v = acc + bias[n];  v = mask_src[m,n] > 0 ? v : 0;  v += resid[m,n];
+//   out_f32[m,n] = v;   out_act[m,n] = T(relu ? max(v,0) : v)
+// Forward layers use bias/resid/relu (resnetfc.py:57-64,172,183-191); the dgrad chain uses
+// mask_src (ReLU gate of the saved activation) and resid (gradient of the skip connection).
+#pragma once
+#include "common.cuh"
+
+namespace nrf {
+
+template <typename T>
+struct Epilogue {
+  const float* bias;
+  const T* mask_src; int ldmask;
+  const float* resid; int ldr;
+  float* out_f32; int ldo;
+  T* out_act; int ldact; int relu_act;
+  int M, n_store;
+};
+
+template <typename T>
+static inline Epilogue<T> make_epilogue(const NrfGemm& g) {
+  Epilogue<T> e;
+  e.bias = g.bias;
+  e.mask_src = reinterpret_cast<const T*>(g.mask_src); e.ldmask = g.ldmask;
+  e.resid = g.resid; e.ldr = g.ldr;
+  e.out_f32 = g.out_f32; e.ldo = g.ldo;
+  e.out_act = reinterpret_cast<T*>(g.out_act); e.ldact = g.ldact; e.relu_act = g.relu_act;
+  e.M = g.M; e.n_store = g.n_store;
+  return e;
+}
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream);
+int gemm_simt_launch(const NrfGemm& g, cudaStream_t stream);
+int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
+                    int k_valid, float* dW, int ldw, float* dbias, void* workspace, cudaStream_t stream);
+int wgrad_simt_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
+                      int k_valid, float* dW, int ldw, float* dbias, cudaStream_t stream);
+
+}  // namespace nrf

@@ -1,0 +1,590 @@
+// tcgen05 / TMEM / TMA GEMMs of the field MLP (NRF_PREC_BF16): bf16 operands, fp32 accumulate.
+//
+//   gemm_tc_kernel<BN>   out = epilogue([A1|A2] . B^T)        forward layers and the dgrad chain
+//   wgrad_tc_kernel<BK_> dW += G^T . A  (split over samples)  weight gradients
+//
+// Structure (both): persistent CTAs, 8 warps.
+//   warp 0    TMA producer      cp.async.bulk.tensor.2d -> 128B-swizzled smem ring, mbarrier tx counts
+//   warp 1    MMA issuer        one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128),
+//                               tcgen05.commit releases smem stages / publishes the accumulator
+//   warp 2    TMEM allocator    2 accumulator stages so the epilogue of tile i overlaps the MMAs of i+1
+//   warps 4-7 epilogue          tcgen05.ld 32x32b (one TMEM lane = one output row per thread), fused
+//                               bias / ReLU-gate / residual / bf16 re-quantisation, direct global stores
+#include <cuda.h>
+#include <mutex>
+#include "gemm_common.cuh"
+
+namespace nrf {
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------- descriptors
+// Instruction descriptor, kind::f16: D=f32 (bits 4-5 =1), A=B=bf16 (bits 7-9, 10-12 =1),
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at 17, M>>4 at 24.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// Shared-memory matrix descriptor, SWIZZLE_128B (layout type 2 at bits 61-63), version 1 (bit 46).
+//   K-major : rows of 64 bf16 (128 B); 8-row atoms 1024 B apart (SBO); LBO unused (1)
+//   MN-major: rows of 64 MN-elements (128 B) indexed by k; 8-k atoms 1024 B apart (SBO);
+//             64-wide MN slabs `lbo_bytes` apart (LBO)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+constexpr int kTileM = 128;       // UMMA M (cta_group::1)
+constexpr int kTileK = 64;        // 64 bf16 = one 128 B swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++stage == n) { stage = 0; phase ^= 1; }
+  }
+};
+
+// ------------------------------------------------------------------------------- forward / dgrad
+template <int BN>
+struct FwdCfg {
+  static constexpr int kStageA = kTileM * kTileK * 2;          // 16 KB
+  static constexpr int kStageB = BN * kTileK * 2;              // 32 KB (BN=256) / 16 KB (BN=128)
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;                     // 2 accumulator stages
+  static constexpr int kSmem = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, int M, int N, int K1, int K2,
+               Epilogue<__nv_bfloat16> ep) {
+  using Cfg = FwdCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* acc_full = empty + Cfg::kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int m_tiles = (M + kTileM - 1) / kTileM, n_tiles = N / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int kb1 = K1 / kTileK, num_kb = (K1 + K2) / kTileK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    if (K2 > 0) tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState st;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty + st.stage, st.phase ^ 1);
+          uint8_t* sa = smem + st.stage * Cfg::kStage;
+          uint8_t* sb = sa + Cfg::kStageA;
+          mbar_expect_tx(full + st.stage, Cfg::kStage);
+          if (kb < kb1) tma_load_2d(sa, &tmA1, full + st.stage, kb * kTileK, m_blk * kTileM);
+          else          tma_load_2d(sa, &tmA2, full + st.stage, (kb - kb1) * kTileK, m_blk * kTileM);
+          tma_load_2d(sb, &tmB, full + st.stage, kb * kTileK, n_blk * BN);
+          st.advance(Cfg::kStages);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kTileM, BN, 0, 0);
+      PipeState st;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        int as = it & 1;
+        uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(acc_empty + as, aphase ^ 1);
+        tc_fence_after();
+        uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full + st.stage, st.phase);
+          tc_fence_after();
+          uint32_t sa = smem_u32(smem + st.stage * Cfg::kStage);
+          uint32_t sb = sa + Cfg::kStageA;
+          uint64_t adesc = make_sdesc(sa, 16, 1024);
+          uint64_t bdesc = make_sdesc(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kTileK / kUmmaK; ++k) {
+            // +32 B per 16-element K step inside the 128 B swizzle row: +2 in the 16 B address field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty + st.stage);
+          st.advance(Cfg::kStages);
+        }
+        umma_commit(acc_full + as);
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    const int q = warp - kEpiWarp0;            // TMEM lane quarter this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      int as = it & 1;
+      uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(acc_full + as, aphase);
+      tc_fence_after();
+      const int m = m_blk * kTileM + q * 32 + lane;
+      const bool row_ok = m < M;
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= ep.n_store) break;             // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        if (!row_ok) continue;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+          }
+        }
+        const bool full_chunk = n0 + 32 <= ep.n_store;
+        if (full_chunk) {
+          if (ep.mask_src) {
+            const uint4* mp = reinterpret_cast<const uint4*>(ep.mask_src + (int64_t)m * ep.ldmask + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 mk = __ldg(mp + j);
+              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&mk);
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                if (!(__bfloat162float(h[t]) > 0.0f)) x[j * 8 + t] = 0.0f;
+            }
+          }
+          if (ep.resid) {
+            const float4* rp = reinterpret_cast<const float4*>(ep.resid + (int64_t)m * ep.ldr + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 r = rp[j];
+              x[j * 4] += r.x; x[j * 4 + 1] += r.y; x[j * 4 + 2] += r.z; x[j * 4 + 3] += r.w;
+            }
+          }
+          if (ep.out_f32) {
+            float4* op = reinterpret_cast<float4*>(ep.out_f32 + (int64_t)m * ep.ldo + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(x[j * 4], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]);
+          }
+          if (ep.out_act) {
+            uint4* ap = reinterpret_cast<uint4*>(ep.out_act + (int64_t)m * ep.ldact + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float a = x[j * 8 + 2 * t], b = x[j * 8 + 2 * t + 1];
+                if (ep.relu_act) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                w[t] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              ap[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        } else {
+          for (int j = 0; j < 32 && n0 + j < ep.n_store; ++j) {
+            float val = x[j];
+            if (ep.mask_src && !(__bfloat162float(ep.mask_src[(int64_t)m * ep.ldmask + n0 + j]) > 0.0f)) val = 0.0f;
+            if (ep.resid) val += ep.resid[(int64_t)m * ep.ldr + n0 + j];
+            if (ep.out_f32) ep.out_f32[(int64_t)m * ep.ldo + n0 + j] = val;
+            if (ep.out_act)
+              ep.out_act[(int64_t)m * ep.ldact + n0 + j] = __float2bfloat16_rn(ep.relu_act ? fmaxf(val, 0.0f) : val);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------- wgrad
+// dW[n,k] += sum_m G[m,n] A[m,k].  UMMA A-operand = G^T tile (128 n x 64 m), B-operand = A^T tile
+// (BK_ k x 64 m); both MN-major (the sample index m is the slow axis of G and A in memory).
+// grid = (n tiles * k tiles, splits); each CTA reduces its sample range and adds its partial tile
+// into dW with fp32 reductions (red.global.add.f32).
+template <int BK_>
+struct WgCfg {
+  static constexpr int kStageG = kTileM * kTileK * 2;          // 2 slabs of [64 m][64 n]
+  static constexpr int kStageA = BK_ * kTileK * 2;             // BK_/64 slabs of [64 m][64 k]
+  static constexpr int kStage = kStageG + kStageA;
+  static constexpr int kStages = BK_ == 256 ? 4 : 6;
+  static constexpr int kTmemCols = BK_ < 32 ? 32 : BK_;
+  static constexpr int kSmem = kStages * kStage + 1024 + 256;
+};
+
+template <int BK_>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA, int M,
+                int k_tiles, int m_per_split, int n_valid, int k_valid, float* __restrict__ dW, int ldw) {
+  using Cfg = WgCfg<BK_>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* acc_full = empty + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n_blk = blockIdx.x / k_tiles, k_blk = blockIdx.x % k_tiles;
+  const int m_begin = blockIdx.y * m_per_split;
+  const int m_end = min(M, m_begin + m_per_split);
+  const int num_mb = (m_end - m_begin + kTileK - 1) / kTileK;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmA); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState st;
+      for (int mb = 0; mb < num_mb; ++mb) {
+        mbar_wait(empty + st.stage, st.phase ^ 1);
+        uint8_t* sg = smem + st.stage * Cfg::kStage;
+        uint8_t* sa = sg + Cfg::kStageG;
+        mbar_expect_tx(full + st.stage, Cfg::kStage);
+        int m0 = m_begin + mb * kTileK;
+        // rows >= M are zero-filled by TMA; rows in [m_end, M) of the last chunk belong to the next
+        // split, so chunks are aligned: m_per_split is a multiple of 64.
+#pragma unroll
+        for (int s = 0; s < kTileM / 64; ++s)
+          tma_load_2d(sg + s * (kTileK * 128), &tmG, full + st.stage, n_blk * kTileM + s * 64, m0);
+#pragma unroll
+        for (int s = 0; s < BK_ / 64; ++s)
+          tma_load_2d(sa + s * (kTileK * 128), &tmA, full + st.stage, k_blk * BK_ + s * 64, m0);
+        st.advance(Cfg::kStages);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kTileM, BK_, 1, 1);
+      PipeState st;
+      for (int mb = 0; mb < num_mb; ++mb) {
+        mbar_wait(full + st.stage, st.phase);
+        tc_fence_after();
+        uint32_t sg = smem_u32(smem + st.stage * Cfg::kStage);
+        uint32_t sa = sg + Cfg::kStageG;
+        uint64_t gdesc = make_sdesc(sg, kTileK * 128, 1024);
+        uint64_t adesc = make_sdesc(sa, kTileK * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < kTileK / kUmmaK; ++k) {
+          // 16 samples = two 8-row atoms = 2048 B: +128 in the 16 B address field
+          umma_bf16(tmem_base, gdesc + 128 * k, adesc + 128 * k, idesc, (mb | k) != 0);
+        }
+        umma_commit(empty + st.stage);
+        st.advance(Cfg::kStages);
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= kEpiWarp0) {
+    const int q = warp - kEpiWarp0;
+    if (num_mb > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const int n = n_blk * kTileM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BK_ / 32; ++c) {
+        int k0 = k_blk * BK_ + c * 32;
+        if (k0 >= k_valid) break;
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        if (n < n_valid) {
+          float* dst = dW + (int64_t)n * ldw + k0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k0 + j < k_valid) atomicAdd(dst + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// Column sums of a bf16 matrix: dbias[n] += sum_m G[m,n].
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ G, int ldg, int M,
+                                                          int n_valid, float* __restrict__ dbias,
+                                                          int rows_per_block) {
+  int n = blockIdx.x * 64 + (threadIdx.x % 64);
+  int sub = threadIdx.x / 64;   // 4 row phases
+  int m0 = blockIdx.y * rows_per_block;
+  int m1 = min(M, m0 + rows_per_block);
+  float s = 0.f;
+  if (n < n_valid)
+    for (int m = m0 + sub; m < m1; m += 4) s += __bfloat162float(G[(int64_t)m * ldg + n]);
+  __shared__ float red[4][64];
+  red[sub][threadIdx.x % 64] = s;
+  __syncthreads();
+  if (sub == 0 && n < n_valid)
+    atomicAdd(dbias + n, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+// ----------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: `cols` contiguous elements per row, `rows` rows `ld` elements apart;
+// box = box_cols x box_rows, 128 B swizzle, out-of-bounds elements read as zero.
+static int make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
+                    uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  NRF_REQUIRE(fn != nullptr, NRF_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  NRF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, NRF_EINVAL,
+              "TMA operand must be 16 B aligned with a 16 B-multiple row pitch (ld=%llu)",
+              (unsigned long long)ld);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NRF_REQUIRE(r == CUDA_SUCCESS, NRF_ECUDA, "cuTensorMapEncodeTiled failed (%d): cols=%llu rows=%llu ld=%llu",
+              (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld);
+  return NRF_OK;
+}
+
+template <int BN>
+static int launch_fwd(const NrfGemm& g, cudaStream_t stream) {
+  using Cfg = FwdCfg<BN>;
+  CUtensorMap tmA1, tmA2, tmB;
+  int rc = make_map(&tmA1, g.A1, g.K1, g.M, g.lda1, kTileK, kTileM);
+  if (rc) return rc;
+  if (g.K2 > 0) {
+    rc = make_map(&tmA2, g.A2, g.K2, g.M, g.lda2, kTileK, kTileM);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA1;
+  }
+  rc = make_map(&tmB, g.B, g.K1 + g.K2, g.N, g.ldb, kTileK, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr_set = true;
+  }
+  int m_tiles = (g.M + kTileM - 1) / kTileM, n_tiles = g.N / BN;
+  int tiles = m_tiles * n_tiles;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmem, stream>>>(tmA1, tmA2, tmB, g.M, g.N, g.K1, g.K2,
+                                                             make_epilogue<__nv_bfloat16>(g));
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
+
+int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream) {
+  NRF_REQUIRE(g.K1 > 0 && g.K1 % kTileK == 0 && g.K2 % kTileK == 0, NRF_ENOSUP,
+              "gemm_tc: K1=%d, K2=%d must be multiples of 64", g.K1, g.K2);
+  NRF_REQUIRE(g.N % 128 == 0, NRF_ENOSUP, "gemm_tc: N=%d must be a multiple of 128", g.N);
+  NRF_REQUIRE((!g.out_f32 || g.ldo % 4 == 0) && (!g.out_act || g.ldact % 8 == 0) &&
+                  (!g.mask_src || g.ldmask % 8 == 0) && (!g.resid || g.ldr % 4 == 0),
+              NRF_EINVAL, "gemm_tc: epilogue leading dimensions must keep 16 B alignment");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  NRF_REQUIRE(al16(g.bias) && al16(g.mask_src) && al16(g.resid) && al16(g.out_f32) && al16(g.out_act),
+              NRF_EINVAL, "gemm_tc: epilogue pointers must be 16 B aligned");
+  if (g.N % 256 == 0) return launch_fwd<256>(g, stream);
+  return launch_fwd<128>(g, stream);
+}
+
+template <int BK_>
+static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
+                        int k_valid, float* dW, int ldw, cudaStream_t stream) {
+  using Cfg = WgCfg<BK_>;
+  CUtensorMap tmG, tmA;
+  int rc = make_map(&tmG, G, N, M, ldg, 64, kTileK);
+  if (rc) return rc;
+  rc = make_map(&tmA, A, K, M, lda, 64, kTileK);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRF_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr_set = true;
+  }
+  int n_tiles = (n_valid + kTileM - 1) / kTileM;
+  int k_tiles = (k_valid + BK_ - 1) / BK_;
+  int out_tiles = n_tiles * k_tiles;
+  int splits = (sm_count() + out_tiles - 1) / out_tiles;
+  int max_splits = (M + 4 * kTileK - 1) / (4 * kTileK);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int m_per = ((M + splits - 1) / splits + kTileK - 1) / kTileK * kTileK;
+  splits = (M + m_per - 1) / m_per;
+  dim3 grid(out_tiles, splits);
+  wgrad_tc_kernel<BK_><<<grid, kThreads, Cfg::kSmem, stream>>>(tmG, tmA, M, k_tiles, m_per, n_valid, k_valid,
+                                                               dW, ldw);
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
+
+int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
+                    int k_valid, float* dW, int ldw, float* dbias, void* workspace, cudaStream_t stream) {
+  (void)workspace;
+  NRF_REQUIRE(N % 64 == 0 && K % 64 == 0, NRF_ENOSUP, "wgrad_tc: N=%d, K=%d must be multiples of 64", N, K);
+  int rc;
+  if (k_valid > 128) rc = launch_wgrad<256>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, stream);
+  else if (k_valid > 64) rc = launch_wgrad<128>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, stream);
+  else rc = launch_wgrad<64>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, stream);
+  if (rc) return rc;
+  if (dbias) {
+    int rows_per_block = 2048;
+    dim3 grid((n_valid + 63) / 64, (M + rows_per_block - 1) / rows_per_block);
+    colsum_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(G), ldg, M, n_valid,
+                                                 dbias, rows_per_block);
+    NRF_LAUNCH_OK();
+  }
+  return NRF_OK;
+}
+
+}  // namespace nrf

@@ -1,0 +1,349 @@
+// The ResnetFC field MLP (resnetfc.py:55-64,146-195) as a chain of fused-epilogue GEMMs.
+//
+// Algebra (n_lin_z = min(combine_layer, n_blocks), z = latent, p = [PE | viewdir]):
+//   x'_0     = [z | p] . [W_z0 | W_in]^T + (b_in + b_z0)                     one GEMM, K = kin_pad
+//   net_b    = relu(x'_b) . W_fc0[b]^T + b_fc0[b]
+//   x'_{b+1} = x'_b + [relu(net_b) | z] . [W_fc1[b] | W_z,b+1]^T + (b_fc1[b] + b_z,b+1)
+//   out      = relu(x_nb) . W_out^T + b_out
+// i.e. "x = x + lin_z[b](z)" (resnetfc.py:182-188) is folded into the preceding GEMM by
+// concatenating along K; combine_interleaved (utils.py:509-519) is the identity here.
+// Every GEMM writes the next layer's operand (ReLU'd, operand-typed) from its epilogue, so the
+// forward leaves exactly the tensors the backward needs: relu(x'_b) and relu(net_b).
+#include <string.h>
+#include "gemm_common.cuh"
+
+namespace nrf {
+
+static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct MlpLayout {
+  int H, C, Din, Dout, nb, nz;
+  int kin_pad, dout_pad, nout_pad;
+  size_t es;                 // operand element size
+  // byte offsets into the packed buffer
+  int64_t W0, bias0, Wout, bias_out, WoutT;
+  int64_t Wfc0[NRF_MAX_BLOCKS], Wfc1[NRF_MAX_BLOCKS], bias1[NRF_MAX_BLOCKS];
+  int64_t Wfc0T[NRF_MAX_BLOCKS], Wfc1T[NRF_MAX_BLOCKS], WzT[NRF_MAX_BLOCKS];
+  int k1cat[NRF_MAX_BLOCKS];  // K of the concatenated fc_1 weight
+  int64_t total;
+};
+
+static int make_layout(const NrfMlpParams* p, int precision, MlpLayout* L) {
+  NRF_REQUIRE(p, NRF_EINVAL, "mlp: null params");
+  NRF_REQUIRE(p->n_blocks >= 1 && p->n_blocks <= NRF_MAX_BLOCKS && p->n_lin_z >= 0 &&
+                  p->n_lin_z <= p->n_blocks, NRF_EINVAL, "mlp: n_blocks=%d n_lin_z=%d", p->n_blocks, p->n_lin_z);
+  NRF_REQUIRE(p->d_in > 0 && p->d_hidden > 0 && p->d_out > 0 && p->d_latent >= 0, NRF_EINVAL, "mlp: bad dims");
+  NRF_REQUIRE(precision == NRF_PREC_BF16 || precision == NRF_PREC_FP32, NRF_EINVAL, "mlp: precision %d", precision);
+  L->H = p->d_hidden; L->C = p->d_latent; L->Din = p->d_in; L->Dout = p->d_out;
+  L->nb = p->n_blocks; L->nz = p->d_latent > 0 ? p->n_lin_z : 0;
+  L->es = precision == NRF_PREC_BF16 ? 2 : 4;
+  L->kin_pad = (int)round_up(L->C + L->Din, 64);
+  L->dout_pad = (int)round_up(L->Dout, 64);
+  L->nout_pad = (int)round_up(L->Dout, 128);
+  if (precision == NRF_PREC_BF16) {
+    NRF_REQUIRE(L->H % 128 == 0, NRF_ENOSUP, "mlp(bf16): d_hidden=%d must be a multiple of 128", L->H);
+    NRF_REQUIRE(L->C % 64 == 0 && L->C > 0, NRF_ENOSUP,
+                "mlp(bf16): d_latent=%d must be a multiple of 64", L->C);
+    NRF_REQUIRE(L->Dout % 4 == 0, NRF_ENOSUP, "mlp(bf16): d_out=%d must be a multiple of 4", L->Dout);
+  }
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off = round_up(off + bytes, 1024); return o; };
+  L->W0 = take((int64_t)L->H * L->kin_pad * L->es);
+  L->bias0 = take((int64_t)L->H * 4);
+  for (int b = 0; b < L->nb; ++b) {
+    L->k1cat[b] = L->H + ((b + 1 < L->nz) ? L->C : 0);
+    L->Wfc0[b] = take((int64_t)L->H * L->H * L->es);
+    L->Wfc1[b] = take((int64_t)L->H * L->k1cat[b] * L->es);
+    L->bias1[b] = take((int64_t)L->H * 4);
+    L->Wfc0T[b] = take((int64_t)L->H * L->H * L->es);
+    L->Wfc1T[b] = take((int64_t)L->H * L->H * L->es);
+  }
+  for (int b = 0; b < L->nz; ++b) L->WzT[b] = take((int64_t)round_up(L->C, 128) * L->H * L->es);
+  L->Wout = take((int64_t)L->nout_pad * L->H * L->es);
+  L->bias_out = take((int64_t)L->nout_pad * 4);
+  L->WoutT = take((int64_t)L->H * L->dout_pad * L->es);
+  L->total = off;
+  return NRF_OK;
+}
+
+// dst[r*ld_dst + c] = T(src[...]) for r < rows, c < cols;  src element (r,c) is src[r*ld_src + c]
+// or, transposed, src[c*ld_src + r].
+template <typename T>
+__global__ void pack_matrix_kernel(T* __restrict__ dst, int ld_dst, int rows, int cols,
+                                   const float* __restrict__ src, int ld_src, int transpose) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)rows * cols) return;
+  int r = (int)(t / cols), c = (int)(t % cols);
+  float v = transpose ? src[(int64_t)c * ld_src + r] : src[(int64_t)r * ld_src + c];
+  if constexpr (sizeof(T) == 2) dst[(int64_t)r * ld_dst + c] = __float2bfloat16_rn(v);
+  else dst[(int64_t)r * ld_dst + c] = v;
+}
+
+__global__ void add_bias_kernel(float* __restrict__ dst, const float* __restrict__ a,
+                                const float* __restrict__ b, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (a ? a[i] : 0.0f) + (b ? b[i] : 0.0f);
+}
+
+// dst[i] += src[i]
+__global__ void accumulate_vec_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ G, int ldg, int64_t M, int n_valid,
+                                                     float* __restrict__ out, int rows_per_block) {
+  int n = blockIdx.x * 64 + (threadIdx.x % 64);
+  int sub = threadIdx.x / 64;
+  int64_t m0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  float s = 0.f;
+  if (n < n_valid)
+    for (int64_t m = m0 + sub; m < m1; m += 4) s += to_f32(G[m * ldg + n]);
+  __shared__ float red[4][64];
+  red[sub][threadIdx.x % 64] = s;
+  __syncthreads();
+  if (sub == 0 && n < n_valid)
+    atomicAdd(out + n, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+template <typename T>
+static int pack(void* base, int64_t off, int ld_dst, int rows, int cols, const float* src, int ld_src,
+                int transpose, int col0, cudaStream_t s) {
+  if (!src) return NRF_OK;
+  T* dst = reinterpret_cast<T*>(reinterpret_cast<char*>(base) + off) + col0;
+  int64_t n = (int64_t)rows * cols;
+  pack_matrix_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, ld_dst, rows, cols, src, ld_src, transpose);
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
+
+template <typename T>
+static int pack_all(const NrfMlpParams* p, const MlpLayout& L, void* packed, cudaStream_t s) {
+  NRF_CUDA_OK(cudaMemsetAsync(packed, 0, (size_t)L.total, s));
+  char* base = reinterpret_cast<char*>(packed);
+  auto f32 = [&](int64_t off) { return reinterpret_cast<float*>(base + off); };
+  int rc = 0;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  // W0 = [W_z0 | W_in | 0]
+  if (L.nz > 0) TRY(pack<T>(packed, L.W0, L.kin_pad, L.H, L.C, p->lin_z_w[0], L.C, 0, 0, s));
+  TRY(pack<T>(packed, L.W0, L.kin_pad, L.H, L.Din, p->lin_in_w, L.Din, 0, L.C, s));
+  add_bias_kernel<<<(L.H + 255) / 256, 256, 0, s>>>(f32(L.bias0), p->lin_in_b, L.nz > 0 ? p->lin_z_b[0] : nullptr, L.H);
+  NRF_LAUNCH_OK();
+  for (int b = 0; b < L.nb; ++b) {
+    TRY(pack<T>(packed, L.Wfc0[b], L.H, L.H, L.H, p->fc0_w[b], L.H, 0, 0, s));
+    TRY(pack<T>(packed, L.Wfc1[b], L.k1cat[b], L.H, L.H, p->fc1_w[b], L.H, 0, 0, s));
+    bool cat = b + 1 < L.nz;
+    if (cat) TRY(pack<T>(packed, L.Wfc1[b], L.k1cat[b], L.H, L.C, p->lin_z_w[b + 1], L.C, 0, L.H, s));
+    add_bias_kernel<<<(L.H + 255) / 256, 256, 0, s>>>(f32(L.bias1[b]), p->fc1_b[b], cat ? p->lin_z_b[b + 1] : nullptr, L.H);
+    NRF_LAUNCH_OK();
+    TRY(pack<T>(packed, L.Wfc0T[b], L.H, L.H, L.H, p->fc0_w[b], L.H, 1, 0, s));
+    TRY(pack<T>(packed, L.Wfc1T[b], L.H, L.H, L.H, p->fc1_w[b], L.H, 1, 0, s));
+  }
+  for (int b = 0; b < L.nz; ++b) TRY(pack<T>(packed, L.WzT[b], L.H, L.C, L.H, p->lin_z_w[b], L.C, 1, 0, s));
+  TRY(pack<T>(packed, L.Wout, L.H, L.Dout, L.H, p->lin_out_w, L.H, 0, 0, s));
+  add_bias_kernel<<<(L.Dout + 255) / 256, 256, 0, s>>>(f32(L.bias_out), p->lin_out_b, nullptr, L.Dout);
+  NRF_LAUNCH_OK();
+  TRY(pack<T>(packed, L.WoutT, L.dout_pad, L.H, L.Dout, p->lin_out_w, L.H, 1, 0, s));
+#undef TRY
+  return NRF_OK;
+}
+
+static inline NrfGemm gemm_init(int64_t M, int N, int n_store) {
+  NrfGemm g;
+  memset(&g, 0, sizeof(g));
+  g.M = (int)M; g.N = N; g.n_store = n_store;
+  return g;
+}
+
+static int run_gemm(const NrfGemm& g, int precision, cudaStream_t s) {
+  return precision == NRF_PREC_BF16 ? gemm_tc_launch(g, s) : gemm_simt_launch(g, s);
+}
+
+static int run_wgrad(const void* G, int ldg, const void* A, int lda, int64_t M, int N, int K, int n_valid,
+                     int k_valid, float* dW, int ldw, int precision, cudaStream_t s) {
+  if (!dW) return NRF_OK;
+  return precision == NRF_PREC_BF16
+             ? wgrad_tc_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, nullptr, nullptr, s)
+             : wgrad_simt_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, nullptr, s);
+}
+
+// tmp[0..n) = column sums of G, then added to up to two bias gradients.
+static int bias_grads(const void* G, int ldg, int64_t M, int n, float* tmp, float* d1, float* d2, int precision,
+                      cudaStream_t s) {
+  if (!d1 && !d2) return NRF_OK;
+  NRF_CUDA_OK(cudaMemsetAsync(tmp, 0, (size_t)n * 4, s));
+  int rows_per_block = 4096;
+  dim3 grid((n + 63) / 64, (unsigned)((M + rows_per_block - 1) / rows_per_block));
+  if (precision == NRF_PREC_BF16)
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(G), ldg, M, n, tmp, rows_per_block);
+  else
+    colsum_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(G), ldg, M, n, tmp, rows_per_block);
+  NRF_LAUNCH_OK();
+  if (d1) { accumulate_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(d1, tmp, n); NRF_LAUNCH_OK(); }
+  if (d2) { accumulate_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(d2, tmp, n); NRF_LAUNCH_OK(); }
+  return NRF_OK;
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" int nrf_mlp_sizes(const NrfMlpParams* p, int precision, NrfMlpSizes* out) {
+  NRF_REQUIRE(out, NRF_EINVAL, "nrf_mlp_sizes: null out");
+  MlpLayout L;
+  int rc = make_layout(p, precision, &L);
+  if (rc) return rc;
+  out->kin_pad = L.kin_pad;
+  out->dout_pad = L.dout_pad;
+  out->packed_bytes = L.total;
+  out->fwd_bytes_per_sample = (int64_t)(2 * L.nb + 1) * L.H * L.es + (int64_t)L.H * 4;
+  out->bwd_bytes_per_sample = (int64_t)3 * L.H * L.es + (int64_t)L.H * 4;
+  out->bwd_fixed_bytes = (int64_t)round_up((L.H > L.dout_pad ? L.H : L.dout_pad) * 4, 1024);
+  return NRF_OK;
+}
+
+extern "C" int nrf_mlp_pack(const NrfMlpParams* p, int precision, void* packed, void* stream) {
+  NRF_REQUIRE(packed, NRF_EINVAL, "nrf_mlp_pack: null buffer");
+  MlpLayout L;
+  int rc = make_layout(p, precision, &L);
+  if (rc) return rc;
+  return precision == NRF_PREC_BF16 ? pack_all<__nv_bfloat16>(p, L, packed, as_stream(stream))
+                                    : pack_all<float>(p, L, packed, as_stream(stream));
+}
+
+extern "C" int nrf_mlp_fwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                           int64_t N, void* acts, float* field_out, void* stream) {
+  NRF_REQUIRE(packed && field_in && acts && field_out && N > 0, NRF_EINVAL, "nrf_mlp_fwd: bad arguments");
+  NRF_REQUIRE(N < (int64_t)1 << 31, NRF_ENOSUP, "nrf_mlp_fwd: N too large for one call");
+  MlpLayout L;
+  int rc = make_layout(p, precision, &L);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  const char* W = reinterpret_cast<const char*>(packed);
+  char* act = reinterpret_cast<char*>(acts);
+  const int64_t layer = N * L.H * (int64_t)L.es;
+  auto ax = [&](int b) { return act + (int64_t)b * layer; };                 // relu(x'_b), b = 0..nb
+  auto an = [&](int b) { return act + (int64_t)(L.nb + 1 + b) * layer; };    // relu(net_b), b = 0..nb-1
+  float* xres = reinterpret_cast<float*>(act + (int64_t)(2 * L.nb + 1) * layer);
+
+  NrfGemm g = gemm_init(N, L.H, L.H);
+  g.A1 = field_in; g.K1 = L.kin_pad; g.lda1 = L.kin_pad;
+  g.B = W + L.W0; g.ldb = L.kin_pad;
+  g.bias = reinterpret_cast<const float*>(W + L.bias0);
+  g.out_f32 = xres; g.ldo = L.H;
+  g.out_act = ax(0); g.ldact = L.H; g.relu_act = 1;
+  rc = run_gemm(g, precision, s);
+  if (rc) return rc;
+  for (int b = 0; b < L.nb; ++b) {
+    g = gemm_init(N, L.H, L.H);
+    g.A1 = ax(b); g.K1 = L.H; g.lda1 = L.H;
+    g.B = W + L.Wfc0[b]; g.ldb = L.H;
+    g.bias = p->fc0_b[b];
+    g.out_act = an(b); g.ldact = L.H; g.relu_act = 1;
+    rc = run_gemm(g, precision, s);
+    if (rc) return rc;
+    g = gemm_init(N, L.H, L.H);
+    g.A1 = an(b); g.K1 = L.H; g.lda1 = L.H;
+    if (b + 1 < L.nz) { g.A2 = field_in; g.K2 = L.C; g.lda2 = L.kin_pad; }
+    g.B = W + L.Wfc1[b]; g.ldb = L.k1cat[b];
+    g.bias = reinterpret_cast<const float*>(W + L.bias1[b]);
+    g.resid = xres; g.ldr = L.H;
+    if (b + 1 < L.nb) { g.out_f32 = xres; g.ldo = L.H; }
+    g.out_act = ax(b + 1); g.ldact = L.H; g.relu_act = 1;
+    rc = run_gemm(g, precision, s);
+    if (rc) return rc;
+  }
+  g = gemm_init(N, L.nout_pad, L.Dout);
+  g.A1 = ax(L.nb); g.K1 = L.H; g.lda1 = L.H;
+  g.B = W + L.Wout; g.ldb = L.H;
+  g.bias = reinterpret_cast<const float*>(W + L.bias_out);
+  g.out_f32 = field_out; g.ldo = L.Dout;
+  return run_gemm(g, precision, s);
+}
+
+extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                           int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* gr,
+                           float* dlatent, void* scratch, void* stream) {
+  NRF_REQUIRE(packed && field_in && acts && d_field && gr && scratch && N > 0, NRF_EINVAL,
+              "nrf_mlp_bwd: bad arguments");
+  NRF_REQUIRE(N < (int64_t)1 << 31, NRF_ENOSUP, "nrf_mlp_bwd: N too large for one call");
+  MlpLayout L;
+  int rc = make_layout(p, precision, &L);
+  if (rc) return rc;
+  NRF_REQUIRE(L.nz == 0 || dlatent, NRF_EINVAL, "nrf_mlp_bwd: dlatent is required when d_latent > 0");
+  cudaStream_t s = as_stream(stream);
+  const char* W = reinterpret_cast<const char*>(packed);
+  const char* act = reinterpret_cast<const char*>(acts);
+  const char* fin = reinterpret_cast<const char*>(field_in);
+  const int64_t layer = N * L.H * (int64_t)L.es;
+  auto ax = [&](int b) { return act + (int64_t)b * layer; };
+  auto an = [&](int b) { return act + (int64_t)(L.nb + 1 + b) * layer; };
+  char* sc = reinterpret_cast<char*>(scratch);
+  float* tmp = reinterpret_cast<float*>(sc);
+  int64_t fixed = round_up((L.H > L.dout_pad ? L.H : L.dout_pad) * 4, 1024);
+  float* gx = reinterpret_cast<float*>(sc + fixed);
+  char* gxa[2] = {sc + fixed + N * L.H * 4, sc + fixed + N * L.H * 4 + layer};
+  char* dnet = sc + fixed + N * L.H * 4 + 2 * layer;
+  int cur = 0;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+
+  // lin_out: parameter gradients, then the gradient of x_nb (ReLU-gated by relu(x_nb) > 0)
+  TRY(run_wgrad(d_field, L.dout_pad, ax(L.nb), L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H, precision, s));
+  TRY(bias_grads(d_field, L.dout_pad, N, L.Dout, tmp, gr->lin_out_b, nullptr, precision, s));
+  NrfGemm g = gemm_init(N, L.H, L.H);
+  g.A1 = d_field; g.K1 = L.dout_pad; g.lda1 = L.dout_pad;
+  g.B = W + L.WoutT; g.ldb = L.dout_pad;
+  g.mask_src = ax(L.nb); g.ldmask = L.H;
+  g.out_f32 = gx; g.ldo = L.H;
+  g.out_act = gxa[cur]; g.ldact = L.H;
+  TRY(run_gemm(g, precision, s));
+
+  for (int b = L.nb - 1; b >= 0; --b) {
+    const char* gcur = gxa[cur];             // dL/dx_{b+1}
+    bool cat = b + 1 < L.nz;
+    TRY(run_wgrad(gcur, L.H, an(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc1_w[b], L.H, precision, s));
+    if (cat)
+      TRY(run_wgrad(gcur, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[b + 1], L.C, precision, s));
+    TRY(bias_grads(gcur, L.H, N, L.H, tmp, gr->fc1_b[b], cat ? gr->lin_z_b[b + 1] : nullptr, precision, s));
+    // dnet_b = (g . W_fc1[b]) gated by relu(net_b) > 0
+    g = gemm_init(N, L.H, L.H);
+    g.A1 = gcur; g.K1 = L.H; g.lda1 = L.H;
+    g.B = W + L.Wfc1T[b]; g.ldb = L.H;
+    g.mask_src = an(b); g.ldmask = L.H;
+    g.out_act = dnet; g.ldact = L.H;
+    TRY(run_gemm(g, precision, s));
+    TRY(run_wgrad(dnet, L.H, ax(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc0_w[b], L.H, precision, s));
+    TRY(bias_grads(dnet, L.H, N, L.H, tmp, gr->fc0_b[b], nullptr, precision, s));
+    // dL/dx'_b = dL/dx_{b+1} + (dnet_b . W_fc0[b]) gated by relu(x'_b) > 0
+    g = gemm_init(N, L.H, L.H);
+    g.A1 = dnet; g.K1 = L.H; g.lda1 = L.H;
+    g.B = W + L.Wfc0T[b]; g.ldb = L.H;
+    g.mask_src = ax(b); g.ldmask = L.H;
+    g.resid = gx; g.ldr = L.H;
+    g.out_f32 = gx; g.ldo = L.H;
+    g.out_act = gxa[cur ^ 1]; g.ldact = L.H;
+    TRY(run_gemm(g, precision, s));
+    cur ^= 1;
+    if (b < L.nz) {
+      // dL/dz += dL/dx'_b . W_z[b]
+      int cpad = (int)round_up(L.C, 128);
+      g = gemm_init(N, precision == NRF_PREC_BF16 ? cpad : L.C, L.C);
+      g.A1 = gxa[cur]; g.K1 = L.H; g.lda1 = L.H;
+      g.B = W + L.WzT[b]; g.ldb = L.H;
+      if (b != L.nz - 1) { g.resid = dlatent; g.ldr = L.C; }
+      g.out_f32 = dlatent; g.ldo = L.C;
+      TRY(run_gemm(g, precision, s));
+    }
+  }
+  // first layer: x'_0 = [z | p] . [W_z0 | W_in]^T
+  const char* g0 = gxa[cur];
+  if (L.nz > 0)
+    TRY(run_wgrad(g0, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[0], L.C, precision, s));
+  TRY(run_wgrad(g0, L.H, fin + (int64_t)L.C * L.es, L.kin_pad, N, L.H, L.kin_pad - L.C, L.H, L.Din, gr->lin_in_w,
+                L.Din, precision, s));
+  TRY(bias_grads(g0, L.H, N, L.H, tmp, gr->lin_in_b, L.nz > 0 ? gr->lin_z_b[0] : nullptr, precision, s));
+#undef TRY
+  return NRF_OK;
+}

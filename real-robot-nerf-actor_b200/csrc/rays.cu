@@ -1,0 +1,214 @@
+// Ray generation and per-ray sampling kernels (bit-exact restatements of eager-PyTorch op chains).
+//   nrf_raygen        <- utils.py:444-506   unproj_map + gen_rays
+//   nrf_sample_coarse <- neural_rendering.py:159-176
+//   nrf_sample_fine   <- neural_rendering.py:179-207
+//   nrf_sort_rows     <- neural_rendering.py:463 (torch.sort along the sample axis)
+// Every operation the reference rounds separately is rounded separately here (__f*_rn).
+#include "common.cuh"
+
+namespace nrf {
+
+// One thread per pixel.  CPU-ATen bit pattern: norm = sqrt(fma(z,z,fma(y,y,x*x))),
+// direction = (r0*x + r1*y) + r2*z with separately rounded products and sums.
+__global__ void raygen_kernel(const float* __restrict__ poses, int n_img, int W, int H, float fx,
+                              float fy, float cx, float cy, float z_near, float z_far,
+                              float* __restrict__ rays) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)n_img * H * W;
+  if (t >= total) return;
+  int j = (int)(t % W);
+  int i = (int)((t / W) % H);
+  int b = (int)(t / ((int64_t)W * H));
+  const float* P = poses + (int64_t)b * 16;
+  float x = __fdiv_rn(__fsub_rn((float)j, cx), fx);
+  float y = -__fdiv_rn(__fsub_rn((float)i, cy), fy);
+  float zc = -1.0f;
+  float nrm = __fsqrt_rn(__fmaf_rn(zc, zc, __fmaf_rn(y, y, __fmul_rn(x, x))));
+  x = __fdiv_rn(x, nrm);
+  y = __fdiv_rn(y, nrm);
+  zc = __fdiv_rn(zc, nrm);
+  float4 lo, hi;
+  lo.x = P[3];
+  lo.y = P[7];
+  lo.z = P[11];
+  float d[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    d[r] = __fadd_rn(__fadd_rn(__fmul_rn(P[r * 4 + 0], x), __fmul_rn(P[r * 4 + 1], y)),
+                     __fmul_rn(P[r * 4 + 2], zc));
+  lo.w = d[0];
+  hi.x = d[1];
+  hi.y = d[2];
+  hi.z = z_near;
+  hi.w = z_far;
+  float4* o = reinterpret_cast<float4*>(rays + t * 8);
+  o[0] = lo;
+  o[1] = hi;
+}
+
+__device__ __forceinline__ float lerp_depth(float near, float far, float zs, int lindisp) {
+  if (!lindisp) return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, zs)), __fmul_rn(far, zs));
+  float a = __fmul_rn(__fdiv_rn(1.0f, near), __fsub_rn(1.0f, zs));
+  float b = __fmul_rn(__fdiv_rn(1.0f, far), zs);
+  return __fdiv_rn(1.0f, __fadd_rn(a, b));
+}
+
+__global__ void sample_coarse_kernel(const float* __restrict__ rays, int R, int Kc,
+                                     const float* __restrict__ base, const float* __restrict__ jitter,
+                                     int lindisp, float* __restrict__ z) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)R * Kc) return;
+  int r = (int)(t / Kc), k = (int)(t % Kc);
+  float step = (float)(1.0 / (double)Kc);
+  float zs = base[k];
+  if (jitter) zs = __fadd_rn(zs, __fmul_rn(jitter[t], step));
+  z[t] = lerp_depth(rays[(int64_t)r * 8 + 6], rays[(int64_t)r * 8 + 7], zs, lindisp);
+}
+
+// One warp per ray.  cdf is either given (bit-exact path: identical (cdf,u,jitter) -> identical
+// (ind,z)) or built here from the weights: pdf = (w+1e-5)/sum, cdf = cumsum(pdf) accumulated in
+// double and rounded to fp32 per entry (the CPU-ATen cumsum bit pattern).
+__global__ void sample_fine_kernel(const float* __restrict__ rays, const float* __restrict__ weights,
+                                   const float* __restrict__ cdf_in, int R, int Kc,
+                                   const float* __restrict__ u, const float* __restrict__ jitter,
+                                   int Kf, int lindisp, float* __restrict__ z_out, int ldz,
+                                   float* __restrict__ ind_out) {
+  extern __shared__ float smem[];
+  int warps = blockDim.x / kWarp;
+  int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  int r = blockIdx.x * warps + wid;
+  float* cdf = smem + (size_t)wid * (Kc + 1);
+  if (r >= R) return;
+  if (cdf_in) {
+    for (int k = lane; k <= Kc; k += kWarp) cdf[k] = cdf_in[(int64_t)r * (Kc + 1) + k];
+  } else {
+    const float* w = weights + (int64_t)r * Kc;
+    // sum of (w + 1e-5) in fp32 element order-independent double accumulation
+    double s = 0.0;
+    for (int k = lane; k < Kc; k += kWarp) s += (double)__fadd_rn(w[k], 1e-5f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    float total = (float)s;
+    // inclusive double prefix sums of pdf, chunked per lane
+    int per = (Kc + kWarp - 1) / kWarp;
+    int k0 = lane * per;
+    double local = 0.0;
+    for (int k = k0; k < min(k0 + per, Kc); ++k)
+      local += (double)__fdiv_rn(__fadd_rn(w[k], 1e-5f), total);
+    double pre = local;
+#pragma unroll
+    for (int o = 1; o < kWarp; o <<= 1) {
+      double v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    double run = pre - local;
+    if (lane == 0) cdf[0] = 0.0f;
+    for (int k = k0; k < min(k0 + per, Kc); ++k) {
+      run += (double)__fdiv_rn(__fadd_rn(w[k], 1e-5f), total);
+      cdf[k + 1] = (float)run;
+    }
+  }
+  __syncwarp();
+  float near = rays[(int64_t)r * 8 + 6], far = rays[(int64_t)r * 8 + 7];
+  for (int k = lane; k < Kf; k += kWarp) {
+    float uu = u[(int64_t)r * Kf + k];
+    // searchsorted(cdf, u, right=True): number of entries <= u  (cdf is non-decreasing)
+    int lo = 0, hi = Kc + 1;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+    }
+    float ind = fmaxf((float)lo - 1.0f, 0.0f);
+    float jit = jitter ? jitter[(int64_t)r * Kf + k] : 0.0f;
+    float zs = __fdiv_rn(__fadd_rn(ind, jit), (float)Kc);
+    z_out[(int64_t)r * ldz + k] = lerp_depth(near, far, zs, lindisp);
+    if (ind_out) ind_out[(int64_t)r * Kf + k] = ind;
+  }
+}
+
+// One CTA per ray: bitonic sort of up to 1024 keys in shared memory, stable w.r.t. the original
+// position (ties broken by index, as torch.sort(stable=False) happens to do for small rows is not
+// guaranteed -- only the sorted VALUES are compared bit-for-bit; perm is used for the backward).
+__global__ void sort_rows_kernel(float* __restrict__ z, int R, int K, int P, int32_t* __restrict__ perm) {
+  extern __shared__ unsigned char raw[];
+  float* key = reinterpret_cast<float*>(raw);
+  int* idx = reinterpret_cast<int*>(key + P);
+  int r = blockIdx.x;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    key[i] = i < K ? z[(int64_t)r * K + i] : __int_as_float(0x7f800000);
+    idx[i] = i;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+        int lo = 2 * t - (t & (stride - 1));
+        int hi = lo + stride;
+        bool up = ((lo & size) == 0);
+        float a = key[lo], b = key[hi];
+        int ia = idx[lo], ib = idx[hi];
+        bool gt = (a > b) || (a == b && ia > ib);
+        if (gt == up) {
+          key[lo] = b; key[hi] = a;
+          idx[lo] = ib; idx[hi] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    z[(int64_t)r * K + i] = key[i];
+    if (perm) perm[(int64_t)r * K + i] = idx[i];
+  }
+}
+
+}  // namespace nrf
+
+using namespace nrf;
+
+extern "C" int nrf_raygen(const float* poses, int n_img, int W, int H, float fx, float fy, float cx,
+                          float cy, float z_near, float z_far, float* rays_out, void* stream) {
+  NRF_REQUIRE(poses && rays_out && n_img > 0 && W > 0 && H > 0, NRF_EINVAL, "nrf_raygen: bad args");
+  int64_t total = (int64_t)n_img * H * W;
+  int threads = 256;
+  raygen_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
+      poses, n_img, W, H, fx, fy, cx, cy, z_near, z_far, rays_out);
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
+
+extern "C" int nrf_sample_coarse(const float* rays, int R, int Kc, const float* base,
+                                 const float* jitter, int lindisp, float* z_out, void* stream) {
+  NRF_REQUIRE(rays && base && z_out && R > 0 && Kc > 0, NRF_EINVAL, "nrf_sample_coarse: bad args");
+  int64_t total = (int64_t)R * Kc;
+  int threads = 256;
+  sample_coarse_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
+      rays, R, Kc, base, jitter, lindisp, z_out);
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
+
+extern "C" int nrf_sample_fine(const float* rays, const float* weights, const float* cdf, int R,
+                               int Kc, const float* u, const float* jitter, int Kf, int lindisp,
+                               float* z_out, int ldz, float* ind_out, void* stream) {
+  NRF_REQUIRE(rays && (weights || cdf) && u && z_out && R > 0 && Kc > 0 && Kf > 0 && ldz >= Kf,
+              NRF_EINVAL, "nrf_sample_fine: bad args");
+  NRF_REQUIRE(Kc <= 4096, NRF_ENOSUP, "nrf_sample_fine: Kc > 4096");
+  int warps = 4;
+  size_t smem = (size_t)warps * (Kc + 1) * sizeof(float);
+  sample_fine_kernel<<<(R + warps - 1) / warps, warps * kWarp, smem, as_stream(stream)>>>(
+      rays, weights, cdf, R, Kc, u, jitter, Kf, lindisp, z_out, ldz, ind_out);
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
+
+extern "C" int nrf_sort_rows(float* z, int R, int K, int32_t* perm_out, void* stream) {
+  NRF_REQUIRE(z && R > 0 && K > 0, NRF_EINVAL, "nrf_sort_rows: bad args");
+  NRF_REQUIRE(K <= 1024, NRF_ENOSUP, "nrf_sort_rows: K > 1024");
+  int P = 2;
+  while (P < K) P <<= 1;
+  int threads = P / 2 < 32 ? 32 : (P / 2 > 512 ? 512 : P / 2);
+  sort_rows_kernel<<<R, threads, (size_t)P * 8, as_stream(stream)>>>(z, R, K, P, perm_out);
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}

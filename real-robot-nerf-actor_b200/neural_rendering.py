@@ -1,0 +1,605 @@
+"""Drop-in `NeuralRenderer` for the reference's neural_rendering.py:86-711, on the sm_100a C ABI.
+
+Same constructor, methods, config keys, state_dict keys and loss dictionary as the reference class;
+every stage of `forward_nerf` (sampling, points + trilinear gather + positional encoding, the ResnetFC
+field MLP, alpha compositing, and the whole backward) runs in the hand-written CUDA kernels behind
+include/nrf_b200.h.  There is no PyTorch/CPU fallback: CPU tensors raise.
+
+Differences from the reference, all opt-in or invisible to its callers:
+  * `precision` ("bf16" tensor-core mode, default; "fp32" parity mode) and `perturb` (default True:
+    the reference always draws sampling noise, neural_rendering.py:172,194,200,218) attributes;
+  * `forward_nerf(rays, want_weights=False, noise=None)`: `noise` injects pre-drawn tensors
+    (keys coarse / u / fine / depth), used by the parity tests;
+  * branches that are off in nerfact.conf (multi-scale voxels, depth-supervision volume, coord /
+    attention heads, ret_last_feat, softplus, spade, noise_std) raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .utils import AttrDict, PositionalEncoding, gen_rays
+
+__all__ = ["NeuralRenderer", "PixelNeRFEmbedNet", "ResnetFC", "ResnetBlockFC", "PSNR_torch"]
+
+
+def _cfg_get(cfg, key, default=None):
+    try:
+        return cfg[key]
+    except (KeyError, TypeError, AttributeError):
+        return getattr(cfg, key, default)
+
+
+def PSNR_torch(img1, img2, max_val=1):
+    """neural_rendering.py:78-83."""
+    mse = torch.mean((img1 - img2) ** 2)
+    if mse == 0:
+        return 100
+    return 20 * torch.log10(max_val / torch.sqrt(mse))
+
+
+# ------------------------------------------------------------------ parameter containers
+class ResnetBlockFC(nn.Module):
+    """Parameters of resnetfc.py:12-64 (size_in == size_out == size_h; ReLU)."""
+
+    def __init__(self, size):
+        super().__init__()
+        self.fc_0 = nn.Linear(size, size)
+        self.fc_1 = nn.Linear(size, size)
+        nn.init.constant_(self.fc_0.bias, 0.0)
+        nn.init.kaiming_normal_(self.fc_0.weight, a=0, mode="fan_in")
+        nn.init.constant_(self.fc_1.bias, 0.0)
+        nn.init.zeros_(self.fc_1.weight)
+
+
+class ResnetFC(nn.Module):
+    """Parameters of resnetfc.py:67-209 with the reference's initialisation and state_dict keys.
+
+    The arithmetic lives in the fused GEMM chain of csrc/mlp.cu; `forward(zx)` evaluates it
+    (differentiable w.r.t. the latent part of zx and all parameters).
+    """
+
+    def __init__(self, d_in, d_out=4, n_blocks=5, d_latent=0, d_lang=0, d_hidden=128, beta=0.0,
+                 combine_layer=1000, combine_type="average", use_spade=False, use_language=False):
+        super().__init__()
+        if beta > 0:
+            raise NotImplementedError("softplus activation (beta > 0) is not built; nerfact.conf uses ReLU")
+        if use_spade:
+            raise NotImplementedError("use_spade is off in nerfact.conf and not built")
+        self.lin_in = nn.Linear(d_in, d_hidden)
+        nn.init.constant_(self.lin_in.bias, 0.0)
+        nn.init.kaiming_normal_(self.lin_in.weight, a=0, mode="fan_in")
+        self.lin_out = nn.Linear(d_hidden, d_out)
+        nn.init.constant_(self.lin_out.bias, 0.0)
+        nn.init.kaiming_normal_(self.lin_out.weight, a=0, mode="fan_in")
+        self.n_blocks, self.d_latent, self.d_lang = n_blocks, d_latent, d_lang
+        self.d_in, self.d_out, self.d_hidden = d_in, d_out, d_hidden
+        self.combine_layer, self.combine_type, self.use_spade = combine_layer, combine_type, use_spade
+        self.use_language = False            # resnetfc.py:115 hard-wires this off
+        self.blocks = nn.ModuleList([ResnetBlockFC(d_hidden) for _ in range(n_blocks)])
+        if d_latent != 0:
+            n_lin_z = min(combine_layer, n_blocks)
+            self.lin_z = nn.ModuleList([nn.Linear(d_latent, d_hidden) for _ in range(n_lin_z)])
+            for i in range(n_lin_z):
+                nn.init.constant_(self.lin_z[i].bias, 0.0)
+                nn.init.kaiming_normal_(self.lin_z[i].weight, a=0, mode="fan_in")
+        self._handles = {}
+
+    @property
+    def n_lin_z(self):
+        return len(self.lin_z) if self.d_latent != 0 else 0
+
+    def handle(self, precision) -> ops.FieldMLP:
+        """C-ABI handle for the given precision; rebuilt if parameters moved (e.g. after .to())."""
+        params = dict(self.named_parameters())
+        key = (precision, tuple(p.data_ptr() for p in params.values()))
+        h = self._handles.get(precision)
+        if h is None or h[0] != key:
+            h = (key, ops.FieldMLP(params, self.d_in, self.d_latent, self.d_hidden, self.d_out,
+                                   self.n_blocks, self.n_lin_z, precision))
+            self._handles[precision] = h
+        return h[1]
+
+    def forward(self, zx, precision="bf16", **_ignored):
+        """zx (..., d_latent + d_in) -> (out (..., d_out), None).  See `_MlpFn`."""
+        prec = ops.PRECISIONS[precision] if isinstance(precision, str) else precision
+        h = self.handle(prec)
+        lead = zx.shape[:-1]
+        flat = zx.reshape(-1, zx.shape[-1])
+        names = h.names()
+        out = _MlpFn.apply(h, flat, *[dict(self.named_parameters())[n] for n in names])
+        return out.reshape(*lead, self.d_out), None
+
+
+class _MlpFn(torch.autograd.Function):
+    """The field MLP alone: rows [latent | pe | dir] (fp32) -> raw outputs.  Test / API hook."""
+
+    @staticmethod
+    def forward(ctx, h: ops.FieldMLP, zx, *params):
+        N, width = zx.shape
+        kin = h.sizes.kin_pad
+        fin = torch.zeros(N, kin, device=zx.device, dtype=ops.act_dtype(h.precision))
+        fin[:, :width] = zx.detach().to(fin.dtype)
+        out, acts = h.forward(fin)
+        ctx.h, ctx.fin, ctx.acts, ctx.width = h, fin, acts, width
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        h = ctx.h
+        N = ctx.fin.shape[0]
+        dpad = h.sizes.dout_pad
+        dfield = torch.zeros(N, dpad, device=d_out.device, dtype=ops.act_dtype(h.precision))
+        dfield[:, :d_out.shape[1]] = d_out.to(dfield.dtype)
+        names = h.names()
+        grads = {n: torch.zeros_like(h.params[n]) for n in names}
+        dlat = h.backward(ctx.fin, ctx.acts, dfield, grads)
+        dzx = torch.zeros(N, ctx.width, device=d_out.device, dtype=torch.float32)
+        dzx[:, :dlat.shape[1]] = dlat
+        return (None, dzx, *[grads[n] for n in names])
+
+
+class PixelNeRFEmbedNet(nn.Module):
+    """Parameter / config container mirroring models_embed.py:16-134 (default branch only)."""
+
+    def __init__(self, conf, coordinate_bounds, stop_encoder_grad=False):
+        super().__init__()
+        self.conf = conf
+        self.coordinate_bounds = coordinate_bounds
+        g = lambda k, d=None: _cfg_get(conf, k, d)
+        unsupported = dict(use_multi_scale_voxel=g("use_multi_scale_voxel", False),
+                           use_depth_supervision=g("use_depth_supervision", False),
+                           regress_coord=g("regress_coord", False),
+                           regress_attention=g("regress_attention", False),
+                           use_code_viewdirs=g("use_code_viewdirs", False),
+                           use_freenerf=g("use_freenerf", False), normalize_z=g("normalize_z", False))
+        for k, v in unsupported.items():
+            if v:
+                raise NotImplementedError(f"config option {k}=True is off in nerfact.conf and not built "
+                                          "(SURVEY.md section 8f, 'next')")
+        if not g("use_viewdirs", True):
+            raise NotImplementedError("use_viewdirs=False (neural_rendering.py:294-295 raises too)")
+        if not g("use_xyz", True) or not g("use_code", True):
+            raise NotImplementedError("use_xyz / use_code must be True (nerfact.conf:69-71)")
+        self._voxel_shape = g("voxel_shape")
+        self.image_shape = (g("image_height"), g("image_width"))
+        self.normalize_z = False
+        self.canon_xyz = True
+        self.stop_encoder_grad = stop_encoder_grad
+        self.use_code, self.use_code_viewdirs, self.use_viewdirs, self.use_xyz = True, False, True, True
+        self.use_freenerf = False
+        self.regress_coord = self.regress_attention = False
+        self.use_multi_scale_voxel = self.use_depth_supervision = False
+        self.d_latent = d_latent = g("d_latent")
+        self.d_lang = g("d_lang", 0)
+        self.code = PositionalEncoding.from_conf(conf["code"], d_in=3)
+        d_in = self.code.d_out + 3
+        d_out = 4 + conf["d_embed"]
+        self.share_mlp = g("share_mlp", True)
+        mlp = conf["mlp"] if not hasattr(conf, "mlp") else conf.mlp
+        mk = lambda: ResnetFC(d_in=d_in, d_latent=d_latent, d_lang=self.d_lang, d_out=d_out,
+                              d_hidden=_cfg_get(mlp, "d_hidden"), n_blocks=_cfg_get(mlp, "n_blocks"),
+                              combine_layer=_cfg_get(mlp, "combine_layer"), beta=_cfg_get(mlp, "beta", 0.0),
+                              use_spade=_cfg_get(mlp, "use_spade", False),
+                              use_language=_cfg_get(mlp, "use_language", False))
+        self.mlp_coarse = mk()
+        self.mlp_fine = self.mlp_coarse if self.share_mlp else mk()
+        self.register_buffer("poses", torch.empty(1, 3, 4), persistent=False)
+        self.register_buffer("focal", torch.empty(1, 2), persistent=False)
+        self.register_buffer("c", torch.empty(1, 2), persistent=False)
+        self.d_in, self.d_out, self.d_embed = d_in, d_out, conf["d_embed"]
+        self.num_objs, self.num_views_per_obj = 0, 1
+        self.voxel_feat = None
+
+    def encode(self, voxel_feat, lang, multi_scale_voxel_list, voxel_density, poses, focal, c=None):
+        """models_embed.py:136-183: stores a reference to the volume; focal / c bookkeeping only."""
+        self.voxel_feat = voxel_feat
+        self.multi_scale_voxel_list = None
+        self.voxel_density = None
+        self.language = lang
+        if focal is not None:
+            focal = torch.as_tensor(focal)
+            if focal.dim() == 0:
+                focal = focal[None, None].repeat((1, 2))
+            elif focal.dim() == 1:
+                focal = focal.unsqueeze(-1).repeat((1, 2))
+            else:
+                focal = focal.clone()
+            self.focal = focal.float()
+            self.focal[..., 1] *= -1.0
+        if c is not None:
+            c = torch.as_tensor(c)
+            if c.dim() == 0:
+                c = c[None, None].repeat((1, 2))
+            elif c.dim() == 1:
+                c = c.unsqueeze(-1).repeat((1, 2))
+        self.c = c
+
+
+# -------------------------------------------------------------------------- render passes
+class _PassState:
+    __slots__ = ("rays", "z", "field_in", "acts", "field_out", "rps", "mlp", "perm")
+
+
+def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps):
+    """One composite pass (neural_rendering.py:224-395) over all samples of `z`."""
+    st = _PassState()
+    st.rays, st.z, st.rps, st.mlp, st.perm = rays, z, rps, mlp, None
+    st.field_in = ops.encode_points(rays, z, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
+                                    ld_out=mlp.sizes.kin_pad, precision=mlp.precision)
+    st.field_out, st.acts = mlp.forward(st.field_in)
+    outs = ops.composite_fwd(st.field_out, z, rays, ren._d_embed, ren.white_bkgd)
+    return st, outs
+
+
+def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, want_dz=False):
+    res = ops.composite_bwd(st.field_out, st.z, st.rays, ren._d_embed, d_rgb, d_embed, d_depth, d_weights,
+                            ldg=st.mlp.sizes.dout_pad, precision=st.mlp.precision,
+                            white_bkgd=ren.white_bkgd, want_dz=want_dz)
+    d_field, d_z = res if want_dz else (res, None)
+    dlat = st.mlp.backward(st.field_in, st.acts, d_field, grads)
+    ops.scatter_volume_grad(st.rays, st.z, st.rps, dlat, grad_cl, ren._bounds)
+    return d_z
+
+
+def _zeros_like_or(t, ref_shape, device):
+    return t.contiguous() if t is not None else torch.zeros(ref_shape, device=device, dtype=torch.float32)
+
+
+class _ForwardNerfFn(torch.autograd.Function):
+    """forward_nerf (neural_rendering.py:435-471) as one autograd node.
+
+    inputs : ren, voxel_feat (SB,C,S,S,S), rays (R,8), sb, noise dict, n_param_coarse, *params
+    outputs: z_coarse, cw, crgb, cemb, cdep[, z_fine, fw, frgb, femb, fdep]
+    """
+
+    @staticmethod
+    def forward(ctx, ren, voxel_feat, rays, sb, noise, n_pc, *params):
+        R = rays.shape[0]
+        rps = R // sb
+        mlp_c = ren.nerf_model.mlp_coarse.handle(ren._prec)
+        mlp_f = ren.nerf_model.mlp_fine.handle(ren._prec)
+        vol_cl = ops.volume_to_channels_last(voxel_feat)
+        Kc, Kf, Kfd = ren.n_coarse, ren.n_fine, ren.n_fine_depth
+        z_c = ops.sample_coarse(rays, Kc, noise.get("coarse"), ren.lindisp)
+        st_c, (cw, crgb, cemb, cdep) = _pass_forward(ren, mlp_c, vol_cl, rays, z_c, rps)
+        outs = [z_c, cw, crgb, cemb, cdep]
+        st_f = None
+        depth_mask = None
+        if ren.using_fine:
+            K = Kc + Kf
+            z_all = torch.empty(R, K, device=rays.device, dtype=torch.float32)
+            z_all[:, :Kc] = z_c
+            kf = Kf - Kfd
+            if kf > 0:
+                zf = ops.sample_fine(rays, cw, Kc, noise["u"], noise.get("fine"), ren.lindisp)
+                z_all[:, Kc:Kc + kf] = zf
+            if Kfd > 0:
+                # neural_rendering.py:210-221 (tiny; plain torch ops, incl. the clamp mask for backward)
+                z0 = cdep.unsqueeze(1).repeat(1, Kfd)
+                nz = noise.get("depth")
+                if nz is not None:
+                    z0 = z0 + nz * ren.depth_std
+                near, far = rays[:, 6:7], rays[:, 7:8]
+                depth_mask = ((z0 <= far) & (z0 >= near)).to(torch.float32)
+                z_all[:, Kc + kf:] = torch.max(torch.min(z0, far), near)
+            z_all, perm = ops.sort_rows(z_all, want_perm=True)
+            st_f, (fw, frgb, femb, fdep) = _pass_forward(ren, mlp_f, vol_cl, rays, z_all, rps)
+            st_f.perm = perm
+            outs += [z_all, fw, frgb, femb, fdep]
+        ctx.ren, ctx.st_c, ctx.st_f, ctx.sb, ctx.n_pc = ren, st_c, st_f, sb, n_pc
+        ctx.vol_shape = tuple(vol_cl.shape)
+        ctx.depth_mask = depth_mask
+        ctx.n_params = len(params)
+        ctx.mark_non_differentiable(z_c)
+        if st_f is not None:
+            ctx.mark_non_differentiable(outs[5])
+        if not any(ctx.needs_input_grad):
+            st_c.acts = None
+            if st_f is not None:
+                st_f.acts = None
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g):
+        ren, st_c, st_f = ctx.ren, ctx.st_c, ctx.st_f
+        dev = st_c.rays.device
+        R = st_c.rays.shape[0]
+        D = ren._d_embed
+        shared = ren.nerf_model.mlp_fine is ren.nerf_model.mlp_coarse
+        names_c = st_c.mlp.names()
+        grads_c = {n: torch.zeros_like(st_c.mlp.params[n]) for n in names_c}
+        grads_f = grads_c if shared or st_f is None else {n: torch.zeros_like(st_f.mlp.params[n])
+                                                          for n in st_f.mlp.names()}
+        grad_cl = torch.zeros(ctx.vol_shape, device=dev, dtype=torch.float32)
+        _, d_cw, d_crgb, d_cemb, d_cdep = g[:5]
+        d_cdep = _zeros_like_or(d_cdep, (R,), dev)
+        if st_f is not None:
+            _, d_fw, d_frgb, d_femb, d_fdep = g[5:10]
+            Kfd = ren.n_fine_depth
+            d_z = _pass_backward(ren, st_f, _zeros_like_or(d_frgb, (R, 3), dev),
+                                 _zeros_like_or(d_femb, (R, D), dev), d_fdep, d_fw, grads_f, grad_cl,
+                                 want_dz=Kfd > 0)
+            if Kfd > 0:
+                # route dL/dz of the depth-guided samples back through sort and clamp to coarse depth
+                K = st_f.z.shape[1]
+                d_cat = torch.zeros(R, K, device=dev, dtype=torch.float32)
+                d_cat.scatter_(1, st_f.perm.long(), d_z)
+                d_cdep = d_cdep + (d_cat[:, K - Kfd:] * ctx.depth_mask).sum(-1)
+        _pass_backward(ren, st_c, _zeros_like_or(d_crgb, (R, 3), dev), _zeros_like_or(d_cemb, (R, D), dev),
+                       d_cdep, d_cw, grads_c, grad_cl)
+        d_vol = ops.volume_to_channels_first(grad_cl) if ctx.needs_input_grad[1] else None
+        pg = [grads_c[n] for n in names_c]
+        if not shared and st_f is not None:
+            pg += [grads_f[n] for n in st_f.mlp.names()]
+        return (None, d_vol, None, None, None, None, *pg)
+
+
+# ------------------------------------------------------------------------------ the renderer
+class NeuralRenderer(nn.Module):
+    """take a voxel, camera pose, and camera intrinsics as input, and output a rendered image
+    (neural_rendering.py:86-711)."""
+
+    def __init__(self, cfg, coordinate_bounds, precision="bf16", feature_extractor=None):
+        super().__init__()
+        self.cfg = cfg
+        self.coordinate_bounds = coordinate_bounds
+        g = lambda k, d=None: _cfg_get(cfg, k, d)
+        self.W, self.H = g("image_width"), g("image_height")
+        self.z_near, self.z_far = g("z_near"), g("z_far")
+        self.regress_coord, self.regress_attention = g("regress_coord", False), g("regress_attention", False)
+        self.n_coarse, self.n_fine, self.n_fine_depth = g("n_coarse"), g("n_fine"), g("n_fine_depth", 0)
+        self.lindisp = g("lindisp", False)
+        self.using_fine = self.n_fine > 0
+        self.eval_batch_size = g("eval_batch_size", 4096)
+        self.ret_last_feat = g("ret_last_feat", False)
+        self.noise_std, self.white_bkgd, self.depth_std = g("noise_std", 0.0), g("white_bkgd", False), g("depth_std", 0.001)
+        if self.ret_last_feat:
+            raise NotImplementedError("ret_last_feat=True is off in nerfact.conf and not built")
+        if self.noise_std and self.noise_std > 0.0:
+            raise NotImplementedError("noise_std > 0 is off in nerfact.conf and not built")
+        self.nerf_model = PixelNeRFEmbedNet(cfg, coordinate_bounds)
+        self.model_name = g("foundation_model_name", None)
+        if self.model_name not in ("odise", "diffusion", "dinov2", "deepfloyd", None):
+            raise NotImplementedError(f"foundation model {self.model_name} is not implemented")
+        # target-feature extractors are outside the render path: pass `gt_embed`,
+        # or supply `feature_extractor(gt_rgb, lang_goal) -> (B,D,H,W)`.
+        self.feature_extractor = feature_extractor
+        self.lambda_embed = g("lambda_embed", 0.01)
+        self.lambda_depth = g("lambda_depth", 0.0)
+        self.threshold_depth_supervision = g("threshold_depth_supervision", 0.8)
+        self.precision = precision
+        self.perturb = True
+        self.render_chunk_rays = 4096          # neural_rendering.py:482
+        self._num_freqs = self.nerf_model.code.num_freqs
+        self._freq_factor = float(self.nerf_model.code.freq_factor)
+        self._d_embed = self.nerf_model.d_embed
+        if not self.nerf_model.code.include_input:
+            raise NotImplementedError("code.include_input=False is not built")
+
+    # ---- internals
+    @property
+    def _prec(self):
+        return ops.PRECISIONS[self.precision]
+
+    @property
+    def _bounds(self):
+        return torch.as_tensor(self.coordinate_bounds, dtype=torch.float32).reshape(-1).cpu()
+
+    def _draw_noise(self, R, device):
+        """Noise in the reference's draw order (SURVEY 8b 'RNG'); zeros / a fixed grid if not perturb."""
+        Kc, kf, Kfd = self.n_coarse, self.n_fine - self.n_fine_depth, self.n_fine_depth
+        n = {}
+        if self.perturb:
+            n["coarse"] = torch.rand(R, Kc, device=device)
+            if self.using_fine and kf > 0:
+                n["u"] = torch.rand(R, kf, dtype=torch.float32, device=device)
+                n["fine"] = torch.rand(R, kf, device=device)
+            if self.using_fine and Kfd > 0:
+                n["depth"] = torch.randn(R, Kfd, device=device)
+        elif self.using_fine and kf > 0:
+            n["u"] = ((torch.arange(kf, device=device, dtype=torch.float32) + 0.5) / kf).repeat(R, 1)
+        return n
+
+    def _params_flat(self):
+        m = self.nerf_model
+        pc = dict(m.mlp_coarse.named_parameters())
+        names = m.mlp_coarse.handle(self._prec).names()
+        ps = [pc[n] for n in names]
+        n_pc = len(ps)
+        if m.mlp_fine is not m.mlp_coarse:
+            pf = dict(m.mlp_fine.named_parameters())
+            ps += [pf[n] for n in m.mlp_fine.handle(self._prec).names()]
+        return n_pc, ps
+
+    # ---- reference API
+    def sample_coarse(self, rays, jitter="draw"):
+        """neural_rendering.py:159-176."""
+        if isinstance(jitter, str):
+            jitter = torch.rand(rays.shape[0], self.n_coarse, device=rays.device) if self.perturb else None
+        return ops.sample_coarse(rays, self.n_coarse, jitter, self.lindisp)
+
+    def sample_fine(self, rays, weights, u=None, jitter="draw"):
+        """neural_rendering.py:179-207."""
+        R, kf = rays.shape[0], self.n_fine - self.n_fine_depth
+        if u is None:
+            u = torch.rand(R, kf, dtype=torch.float32, device=rays.device)
+        if isinstance(jitter, str):
+            jitter = torch.rand(R, kf, device=rays.device) if self.perturb else None
+        return ops.sample_fine(rays, weights.detach(), self.n_coarse, u, jitter, self.lindisp)
+
+    def sample_fine_depth(self, rays, depth, noise="draw"):
+        """neural_rendering.py:210-221 (plain torch: R*Kfd elements)."""
+        z = depth.unsqueeze(1).repeat((1, self.n_fine_depth))
+        if isinstance(noise, str):
+            noise = torch.randn_like(z) if self.perturb else None
+        if noise is not None:
+            z = z + noise * self.depth_std
+        return torch.max(torch.min(z, rays[:, -1:]), rays[:, -2:-1])
+
+    def encode(self, multi_scale_voxel_list, voxel_density, lang, voxel_feat, poses, focal, c=None):
+        """neural_rendering.py:428-432."""
+        self.nerf_model.encode(multi_scale_voxel_list=multi_scale_voxel_list, voxel_density=voxel_density,
+                               lang=lang, voxel_feat=voxel_feat, poses=poses, focal=focal, c=c)
+
+    def composite(self, model, rays, z_samp, coarse=True, sb=0):
+        """neural_rendering.py:224-395 for externally supplied samples -> weights, rgb, embed, depth."""
+        model = model if model is not None else self.nerf_model
+        sb = max(int(sb), 1)
+        mlp = (model.mlp_coarse if coarse or model.mlp_fine is None else model.mlp_fine)
+        h = mlp.handle(self._prec)
+        names = h.names()
+        ps = [dict(mlp.named_parameters())[n] for n in names]
+        return _CompositeFn.apply(self, h, model.voxel_feat, rays.contiguous(), z_samp.contiguous(), sb, *ps)
+
+    def _format_outputs(self, rendered_outputs, superbatch_size, want_weights=False):
+        """neural_rendering.py:398-426."""
+        weights, rgb, embed, depth = rendered_outputs
+        if superbatch_size > 0:
+            rgb = rgb.reshape(superbatch_size, -1, 3)
+            embed = embed.reshape(superbatch_size, -1, embed.shape[-1])
+            depth = depth.reshape(superbatch_size, -1)
+            weights = weights.reshape(superbatch_size, -1, weights.shape[-1])
+        ret = AttrDict(rgb=rgb, embed=embed, depth=depth)
+        if want_weights:
+            ret.weights = weights
+        return ret
+
+    def forward_nerf(self, rays, want_weights=False, noise=None):
+        """neural_rendering.py:435-471.  rays (SB,B,8) -> AttrDict(coarse=..., fine=...)."""
+        assert len(rays.shape) == 3
+        sb = rays.shape[0]
+        vol = self.nerf_model.voxel_feat
+        if vol is None:
+            raise RuntimeError("call encode() before forward_nerf()")
+        if vol.shape[0] != sb:
+            raise RuntimeError("grid_sampler(): expected grid and input to have same batch size, "
+                               f"but got input with sizes {list(vol.shape)} and {sb} ray batches")
+        flat = rays.reshape(-1, 8).contiguous()
+        if noise is None:
+            noise = self._draw_noise(flat.shape[0], flat.device)
+        n_pc, ps = self._params_flat()
+        outs = _ForwardNerfFn.apply(self, vol, flat, sb, noise, n_pc, *ps)
+        outputs = AttrDict(coarse=self._format_outputs(outs[1:5], sb, want_weights))
+        outputs.coarse.z = outs[0]
+        if self.using_fine:
+            outputs.fine = self._format_outputs(outs[6:10], sb, want_weights)
+            outputs.fine.z = outs[5]
+        return outputs
+
+    @torch.no_grad()
+    def rendering(self, voxel_feat, language, multi_scale_voxel_list, voxel_density, voxel_pose, focal,
+                  tgt_pose, c=None):
+        """neural_rendering.py:474-502: full images, fine outputs, SB forced to 1."""
+        rays = gen_rays(tgt_pose, self.W, self.H, focal, self.z_near, self.z_far, c=c)
+        self.encode(multi_scale_voxel_list=multi_scale_voxel_list, voxel_density=voxel_density, lang=language,
+                    voxel_feat=voxel_feat, poses=voxel_pose, focal=focal, c=c)
+        B, H, W, _ = rays.shape
+        rays = rays.reshape(B * H * W, 8)
+        rgbs, embeds, depths = [], [], []
+        for i in range(0, rays.shape[0], self.render_chunk_rays):
+            out = self.forward_nerf(rays[i:i + self.render_chunk_rays].unsqueeze(0))
+            fine = out.fine
+            rgbs.append(fine.rgb.squeeze(0))
+            embeds.append(fine.embed.squeeze(0))
+            depths.append(fine.depth.squeeze(0))
+        rgbs = torch.cat(rgbs, dim=0).reshape(B, H, W, 3)
+        embeds = torch.cat(embeds, dim=0).reshape(B, H, W, -1)
+        depths = torch.cat(depths, dim=0).reshape(B, H, W)
+        return rgbs, embeds, depths
+
+    def extract_foundation_model_feature(self, gt_rgb, lang_goal):
+        """neural_rendering.py:505-592 is target preprocessing, outside the render path."""
+        if self.feature_extractor is None:
+            raise NotImplementedError(
+                "target-feature extraction (odise / diffusion / dinov2 / deepfloyd) is outside the render "
+                "hot path: pass gt_embed=..., or construct NeuralRenderer(..., feature_extractor=fn)")
+        feat = self.feature_extractor(gt_rgb, lang_goal)
+        return F.interpolate(feat, size=(self.H, self.W), mode="bilinear", align_corners=False)
+
+    def compute_rendering_loss(self, multi_scale_voxel_list, voxel_density, language, voxel_feat, voxel_poses,
+                               focal, gt_rgb, gt_depth, gt_pose, c=None, lang_goal=None, gt_embed=None):
+        """neural_rendering.py:595-707."""
+        rays = gen_rays(gt_pose, self.W, self.H, focal, self.z_near, self.z_far, c=c)
+        self.encode(multi_scale_voxel_list=multi_scale_voxel_list, voxel_density=voxel_density, lang=language,
+                    voxel_feat=voxel_feat, poses=voxel_poses, focal=focal, c=c)
+        B, H, W, DimRay = rays.shape
+        rays = rays.reshape(B, H * W, DimRay)
+        chunk_size = _cfg_get(self.cfg, "ray_chunk_size")
+        idx = torch.randint(H * W, (chunk_size,), device=rays.device)      # shared across scenes (:608)
+        sampled_rays = rays[:, idx, :]
+        outputs = self.forward_nerf(sampled_rays)
+        if gt_embed is None:
+            with torch.no_grad():
+                gt_embed = self.extract_foundation_model_feature(gt_rgb, lang_goal)
+                embed_dim = _cfg_get(self.cfg, "d_embed")
+                if embed_dim < 512 and gt_embed.shape[1] != embed_dim:
+                    from sklearn.decomposition import PCA        # neural_rendering.py:640-646
+                    Bq, Dq, Hq, Wq = gt_embed.shape
+                    flat = gt_embed.permute(0, 2, 3, 1).reshape(Bq * Hq * Wq, Dq).cpu().numpy()
+                    flat = PCA(n_components=embed_dim).fit_transform(flat)
+                    gt_embed = torch.from_numpy(flat).reshape(Bq, Hq, Wq, embed_dim).permute(0, 3, 1, 2)
+                    gt_embed = gt_embed.to(gt_rgb.device)
+                gt_embed = gt_embed.permute(0, 2, 3, 1)
+        gt_rgb = gt_rgb.reshape(B, H * W, 3)[:, idx, :]
+        loss_rgb_coarse = F.mse_loss(outputs.coarse.rgb, gt_rgb)
+        loss_rgb_fine = F.mse_loss(outputs.fine.rgb, gt_rgb)
+        loss = loss_rgb_coarse + loss_rgb_fine
+        psnr = PSNR_torch(outputs.fine.rgb, gt_rgb)
+        gt_embed = gt_embed.reshape(B, H * W, -1)[:, idx, :]
+        loss_embed_coarse = self.lambda_embed * F.mse_loss(outputs.coarse.embed, gt_embed)
+        loss_embed_fine = self.lambda_embed * F.mse_loss(outputs.fine.embed, gt_embed)
+        loss = loss + loss_embed_coarse + loss_embed_fine
+        if gt_depth is not None:
+            gt_depth = gt_depth.reshape(B, H * W)[:, idx]
+            far_mask = gt_depth < self.z_far
+            loss_depth_coarse = self.lambda_depth * F.mse_loss(gt_depth[far_mask], outputs.coarse.depth[far_mask])
+            loss_depth_fine = self.lambda_depth * F.mse_loss(gt_depth[far_mask], outputs.fine.depth[far_mask])
+            loss = loss + loss_depth_coarse + loss_depth_fine
+        else:
+            loss_depth_coarse = torch.zeros((), device=loss.device)
+            loss_depth_fine = torch.zeros((), device=loss.device)
+        # one host sync instead of the reference's 13 .item() calls
+        psnr_t = psnr if torch.is_tensor(psnr) else torch.tensor(float(psnr), device=loss.device)
+        vals = torch.stack([v.detach().float().reshape(()) for v in
+                            (loss_rgb_coarse, loss_rgb_fine, loss_embed_coarse, loss_embed_fine,
+                             loss_depth_coarse, loss_depth_fine, psnr_t)]).tolist()
+        return {"loss": loss,
+                "loss_rgb_coarse": vals[0], "loss_rgb_fine": vals[1], "loss_rgb": vals[0] + vals[1],
+                "loss_embed_coarse": vals[2], "loss_embed_fine": vals[3], "loss_embed": vals[2] + vals[3],
+                "loss_depth_coarse": vals[4], "loss_depth_fine": vals[5], "loss_depth": vals[4] + vals[5],
+                "psnr": vals[6]}
+
+    def forward(self, multi_scale_voxel_list, voxel_density, language, voxel_feat, voxel_poses, focal, gt_rgb,
+                gt_depth, gt_pose, c=None, lang_goal=None, gt_embed=None):
+        """neural_rendering.py:710-711."""
+        return self.compute_rendering_loss(multi_scale_voxel_list, voxel_density, language, voxel_feat,
+                                           voxel_poses, focal, gt_rgb, gt_depth, gt_pose, c, lang_goal, gt_embed)
+
+
+class _CompositeFn(torch.autograd.Function):
+    """A single composite pass with caller-supplied samples (public `NeuralRenderer.composite`)."""
+
+    @staticmethod
+    def forward(ctx, ren, h, voxel_feat, rays, z, sb, *params):
+        vol_cl = ops.volume_to_channels_last(voxel_feat)
+        st, outs = _pass_forward(ren, h, vol_cl, rays, z, rays.shape[0] // sb)
+        ctx.ren, ctx.st, ctx.vol_shape = ren, st, tuple(vol_cl.shape)
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_w, d_rgb, d_emb, d_dep):
+        ren, st = ctx.ren, ctx.st
+        dev = st.rays.device
+        R, D = st.rays.shape[0], ren._d_embed
+        names = st.mlp.names()
+        grads = {n: torch.zeros_like(st.mlp.params[n]) for n in names}
+        grad_cl = torch.zeros(ctx.vol_shape, device=dev, dtype=torch.float32)
+        d_z = _pass_backward(ren, st, _zeros_like_or(d_rgb, (R, 3), dev), _zeros_like_or(d_emb, (R, D), dev),
+                             d_dep, d_w, grads, grad_cl, want_dz=ctx.needs_input_grad[4])
+        d_vol = ops.volume_to_channels_first(grad_cl) if ctx.needs_input_grad[2] else None
+        return (None, None, d_vol, None, d_z, None, *[grads[n] for n in names])

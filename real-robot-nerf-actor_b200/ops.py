@@ -1,0 +1,325 @@
+"""Tensor-level wrappers over the C ABI (include/nrf_b200.h).  CUDA tensors in, CUDA tensors out.
+
+Each function validates device / dtype / contiguity, allocates outputs through PyTorch's caching
+allocator, and enqueues one C-ABI call on the current CUDA stream.  No CPU path exists: a CPU tensor
+is an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import NRF_PREC_BF16, NRF_PREC_FP32, check, ptr, stream_ptr
+
+PRECISIONS = {"bf16": NRF_PREC_BF16, "fp32": NRF_PREC_FP32}
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.NrfError(f"{name}: expected a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise _lib.NrfError(f"{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def act_dtype(precision: int):
+    return torch.bfloat16 if precision == NRF_PREC_BF16 else torch.float32
+
+
+# ------------------------------------------------------------------------------------- rays
+def raygen(poses, width, height, focal, z_near, z_far, c=None):
+    """utils.py:477-506 gen_rays.  poses (B,4,4) -> rays (B,H,W,8)."""
+    poses = _f32(poses, "poses")
+    f = torch.as_tensor(focal, dtype=torch.float32).reshape(-1).cpu()
+    fx, fy = (float(f[0]), float(f[0])) if f.numel() == 1 else (float(f[0]), float(f[1]))
+    if c is None:
+        cx, cy = width * 0.5, height * 0.5
+    else:
+        cc = torch.as_tensor(c, dtype=torch.float32).reshape(-1).cpu()
+        cx, cy = float(cc[0]), float(cc[1])
+    B = poses.shape[0]
+    rays = torch.empty(B, height, width, 8, device=poses.device, dtype=torch.float32)
+    check(_lib.load().nrf_raygen(ptr(poses), B, width, height, fx, fy, cx, cy, float(z_near),
+                                 float(z_far), ptr(rays), stream_ptr()), "nrf_raygen")
+    return rays
+
+
+def sample_coarse(rays, n_coarse, jitter=None, lindisp=False):
+    """neural_rendering.py:159-176.  rays (R,8) -> z (R,Kc)."""
+    rays = _f32(rays, "rays")
+    R = rays.shape[0]
+    step = 1.0 / n_coarse
+    base = torch.linspace(0, 1 - step, n_coarse, device=rays.device)     # the reference's own op
+    if jitter is not None:
+        jitter = _f32(jitter, "jitter")
+        assert jitter.shape == (R, n_coarse)
+    z = torch.empty(R, n_coarse, device=rays.device, dtype=torch.float32)
+    check(_lib.load().nrf_sample_coarse(ptr(rays), R, n_coarse, ptr(base), ptr(jitter), int(lindisp),
+                                        ptr(z), stream_ptr()), "nrf_sample_coarse")
+    return z
+
+
+def sample_fine(rays, weights, n_coarse, u, jitter=None, lindisp=False, cdf=None, out=None,
+                want_ind=False):
+    """neural_rendering.py:179-207.  Returns z (R,Kf) (written into out[:, :Kf] when given)."""
+    rays = _f32(rays, "rays")
+    u = _f32(u, "u")
+    R, Kf = u.shape
+    weights = _f32(weights, "weights") if weights is not None else None
+    cdf = _f32(cdf, "cdf") if cdf is not None else None
+    jitter = _f32(jitter, "jitter") if jitter is not None else None
+    if out is None:
+        out = torch.empty(R, Kf, device=rays.device, dtype=torch.float32)
+    assert out.is_contiguous() and out.shape[0] == R and out.shape[1] >= Kf
+    ind = torch.empty(R, Kf, device=rays.device, dtype=torch.float32) if want_ind else None
+    check(_lib.load().nrf_sample_fine(ptr(rays), ptr(weights), ptr(cdf), R, n_coarse, ptr(u), ptr(jitter),
+                                      Kf, int(lindisp), ptr(out), out.shape[1], ptr(ind), stream_ptr()),
+          "nrf_sample_fine")
+    return (out, ind) if want_ind else out
+
+
+def sort_rows(z, want_perm=False):
+    """neural_rendering.py:463.  In-place ascending sort of each row; optional int32 permutation."""
+    assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous()
+    R, K = z.shape
+    perm = torch.empty(R, K, device=z.device, dtype=torch.int32) if want_perm else None
+    check(_lib.load().nrf_sort_rows(ptr(z), R, K, ptr(perm), stream_ptr()), "nrf_sort_rows")
+    return (z, perm) if want_perm else z
+
+
+# ----------------------------------------------------------------------------------- volume
+def volume_to_channels_last(vol):
+    """(SB,C,S0,S1,S2) -> (SB,S0,S1,S2,C)."""
+    vol = _f32(vol, "voxel_feat")
+    SB, Cc, S0, S1, S2 = vol.shape
+    out = torch.empty(SB, S0, S1, S2, Cc, device=vol.device, dtype=torch.float32)
+    check(_lib.load().nrf_volume_to_channels_last(ptr(vol), ptr(out), SB, Cc, S0 * S1 * S2, stream_ptr()),
+          "nrf_volume_to_channels_last")
+    return out
+
+
+def volume_to_channels_first(vol_cl):
+    """(SB,S0,S1,S2,C) -> (SB,C,S0,S1,S2)."""
+    vol_cl = _f32(vol_cl, "volume")
+    SB, S0, S1, S2, Cc = vol_cl.shape
+    out = torch.empty(SB, Cc, S0, S1, S2, device=vol_cl.device, dtype=torch.float32)
+    check(_lib.load().nrf_volume_to_channels_first(ptr(vol_cl), ptr(out), SB, Cc, S0 * S1 * S2, stream_ptr()),
+          "nrf_volume_to_channels_first")
+    return out
+
+
+def _bounds_host(bounds):
+    b = torch.as_tensor(bounds, dtype=torch.float32).reshape(-1).cpu()
+    assert b.numel() == 6
+    return (C.c_float * 6)(*[float(v) for v in b])
+
+
+def encode_points(rays, z, rays_per_scene, vol_cl, bounds, num_freqs=6, freq_factor=1.5, ld_out=None,
+                  precision=NRF_PREC_BF16, want_points=False, out=None):
+    """Field-input rows [latent | PE | viewdir | 0] for every sample (see nrf_encode_points)."""
+    rays = _f32(rays, "rays")
+    z = _f32(z, "z")
+    vol_cl = _f32(vol_cl, "volume")
+    R, K = z.shape
+    SB, S0, S1, S2, Cc = vol_cl.shape
+    need = Cc + 6 + 6 * num_freqs
+    if ld_out is None:
+        ld_out = (need + 63) // 64 * 64
+    if out is None:
+        out = torch.empty(R * K, ld_out, device=rays.device, dtype=act_dtype(precision))
+    pts = torch.empty(R * K, 3, device=rays.device, dtype=torch.float32) if want_points else None
+    bh = _bounds_host(bounds)
+    check(_lib.load().nrf_encode_points(ptr(rays), ptr(z), R, K, rays_per_scene, ptr(vol_cl), SB, Cc, S0, S1,
+                                        S2, C.cast(bh, C.c_void_p), num_freqs, float(freq_factor), ptr(out),
+                                        ld_out, int(precision == NRF_PREC_BF16), ptr(pts), stream_ptr()),
+          "nrf_encode_points")
+    return (out, pts) if want_points else out
+
+
+def scatter_volume_grad(rays, z, rays_per_scene, dlatent, grad_cl, bounds):
+    """grad_cl (SB,S0,S1,S2,C) += transpose-of-gather(dlatent (N,C))."""
+    rays = _f32(rays, "rays")
+    z = _f32(z, "z")
+    dlatent = _f32(dlatent, "dlatent")
+    assert grad_cl.is_cuda and grad_cl.dtype == torch.float32 and grad_cl.is_contiguous()
+    R, K = z.shape
+    SB, S0, S1, S2, Cc = grad_cl.shape
+    bh = _bounds_host(bounds)
+    check(_lib.load().nrf_scatter_volume_grad(ptr(rays), ptr(z), R, K, rays_per_scene, ptr(dlatent),
+                                              dlatent.shape[1], ptr(grad_cl), SB, Cc, S0, S1, S2,
+                                              C.cast(bh, C.c_void_p), stream_ptr()),
+          "nrf_scatter_volume_grad")
+    return grad_cl
+
+
+# ------------------------------------------------------------------------------- compositing
+def composite_fwd(field_out, z, rays, D, white_bkgd=False):
+    """neural_rendering.py:339-359 on RAW MLP outputs (N, 4+D).  -> weights, rgb, embed, depth."""
+    field_out = _f32(field_out, "field_out")
+    z = _f32(z, "z")
+    rays = _f32(rays, "rays")
+    R, K = z.shape
+    dev = z.device
+    w = torch.empty(R, K, device=dev, dtype=torch.float32)
+    rgb = torch.empty(R, 3, device=dev, dtype=torch.float32)
+    emb = torch.empty(R, D, device=dev, dtype=torch.float32)
+    dep = torch.empty(R, device=dev, dtype=torch.float32)
+    check(_lib.load().nrf_composite_fwd(ptr(field_out), field_out.shape[1], ptr(z), ptr(rays), R, K, D,
+                                        int(white_bkgd), ptr(w), ptr(rgb), ptr(emb), ptr(dep), stream_ptr()),
+          "nrf_composite_fwd")
+    return w, rgb, emb, dep
+
+
+def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights=None, ldg=None,
+                  precision=NRF_PREC_BF16, white_bkgd=False, want_dz=False, out=None):
+    """Closed-form backward; returns d_field (N, ldg) (operand-typed) and optionally d_z (R,K)."""
+    field_out = _f32(field_out, "field_out")
+    z = _f32(z, "z")
+    rays = _f32(rays, "rays")
+    d_rgb = _f32(d_rgb, "d_rgb")
+    d_embed = _f32(d_embed, "d_embed")
+    d_depth = _f32(d_depth, "d_depth") if d_depth is not None else None
+    d_weights = _f32(d_weights, "d_weights") if d_weights is not None else None
+    R, K = z.shape
+    if ldg is None:
+        ldg = (4 + D + 63) // 64 * 64
+    if out is None:
+        out = torch.empty(R * K, ldg, device=z.device, dtype=act_dtype(precision))
+    dz = torch.empty(R, K, device=z.device, dtype=torch.float32) if want_dz else None
+    check(_lib.load().nrf_composite_bwd(ptr(field_out), field_out.shape[1], ptr(z), ptr(rays), R, K, D,
+                                        int(white_bkgd), ptr(d_rgb), ptr(d_embed), ptr(d_depth),
+                                        ptr(d_weights), ptr(out), ldg, int(precision == NRF_PREC_BF16),
+                                        ptr(dz), stream_ptr()), "nrf_composite_bwd")
+    return (out, dz) if want_dz else out
+
+
+# ------------------------------------------------------------------------------------- GEMMs
+def gemm(A1, B, *, A2=None, bias=None, mask_src=None, resid=None, out_f32=None, out_act=None,
+         relu_act=False, n_store=None, precision=NRF_PREC_BF16):
+    """out = resid + mask(A.B^T + bias); thin test hook over nrf_gemm."""
+    g = _lib.NrfGemm()
+    g.A1, g.K1, g.lda1 = ptr(A1), A1.shape[1], A1.stride(0)
+    if A2 is not None:
+        g.A2, g.K2, g.lda2 = ptr(A2), A2.shape[1], A2.stride(0)
+    g.B, g.ldb = ptr(B), B.stride(0)
+    g.M, g.N = A1.shape[0], B.shape[0]
+    g.n_store = n_store if n_store is not None else g.N
+    g.bias = ptr(bias)
+    if mask_src is not None:
+        g.mask_src, g.ldmask = ptr(mask_src), mask_src.stride(0)
+    if resid is not None:
+        g.resid, g.ldr = ptr(resid), resid.stride(0)
+    if out_f32 is not None:
+        g.out_f32, g.ldo = ptr(out_f32), out_f32.stride(0)
+    if out_act is not None:
+        g.out_act, g.ldact, g.relu_act = ptr(out_act), out_act.stride(0), int(relu_act)
+    check(_lib.load().nrf_gemm(C.byref(g), precision, stream_ptr()), "nrf_gemm")
+
+
+def wgrad(G, A, dW, dbias=None, n_valid=None, k_valid=None, precision=NRF_PREC_BF16):
+    """dW (n_valid,k_valid) += G^T.A ; dbias += colsum(G)."""
+    M, N = G.shape
+    K = A.shape[1]
+    check(_lib.load().nrf_wgrad(ptr(G), G.stride(0), ptr(A), A.stride(0), M, N, K,
+                                n_valid if n_valid is not None else N, k_valid if k_valid is not None else K,
+                                ptr(dW), dW.stride(0), ptr(dbias), None, precision, stream_ptr()), "nrf_wgrad")
+
+
+# --------------------------------------------------------------------------------------- MLP
+PARAM_ORDER_DOC = "lin_in.{weight,bias}, lin_out.*, blocks.b.fc_0.*, blocks.b.fc_1.*, lin_z.b.*"
+
+
+class FieldMLP:
+    """Host-side handle of the ResnetFC field MLP: parameter pointers, packed operand cache, sizes.
+
+    `params` maps the reference's state_dict suffixes ('lin_in.weight', 'blocks.0.fc_1.bias',
+    'lin_z.2.weight', ...) to fp32 CUDA tensors.  The packed (bf16 / transposed) copies are derived
+    caches, refreshed by `pack()` whenever a parameter's version counter changes.
+    """
+
+    def __init__(self, params: dict, d_in: int, d_latent: int, d_hidden: int, d_out: int, n_blocks: int,
+                 n_lin_z: int, precision: int = NRF_PREC_BF16):
+        self.params = params
+        self.dims = (d_in, d_latent, d_hidden, d_out, n_blocks, n_lin_z)
+        self.precision = precision
+        self._packed = None
+        self._packed_key = None
+        self.sizes = _lib.NrfMlpSizes()
+        check(_lib.load().nrf_mlp_sizes(C.byref(self._cparams()), precision, C.byref(self.sizes)),
+              "nrf_mlp_sizes")
+
+    # names in a fixed order (used for flat gradient buffers too)
+    def names(self):
+        d_in, d_latent, d_hidden, d_out, nb, nz = self.dims
+        out = ["lin_in.weight", "lin_in.bias", "lin_out.weight", "lin_out.bias"]
+        for b in range(nb):
+            out += [f"blocks.{b}.fc_0.weight", f"blocks.{b}.fc_0.bias",
+                    f"blocks.{b}.fc_1.weight", f"blocks.{b}.fc_1.bias"]
+        for b in range(nz):
+            out += [f"lin_z.{b}.weight", f"lin_z.{b}.bias"]
+        return out
+
+    def _fill(self, st, get):
+        d_in, d_latent, d_hidden, d_out, nb, nz = self.dims
+        st.lin_in_w, st.lin_in_b = get("lin_in.weight"), get("lin_in.bias")
+        st.lin_out_w, st.lin_out_b = get("lin_out.weight"), get("lin_out.bias")
+        for b in range(nb):
+            st.fc0_w[b], st.fc0_b[b] = get(f"blocks.{b}.fc_0.weight"), get(f"blocks.{b}.fc_0.bias")
+            st.fc1_w[b], st.fc1_b[b] = get(f"blocks.{b}.fc_1.weight"), get(f"blocks.{b}.fc_1.bias")
+        for b in range(nz):
+            st.lin_z_w[b], st.lin_z_b[b] = get(f"lin_z.{b}.weight"), get(f"lin_z.{b}.bias")
+        return st
+
+    def _cparams(self):
+        d_in, d_latent, d_hidden, d_out, nb, nz = self.dims
+        st = _lib.NrfMlpParams()
+        st.d_in, st.d_latent, st.d_hidden, st.d_out, st.n_blocks, st.n_lin_z = self.dims
+
+        def get(name):
+            t = self.params[name]
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise _lib.NrfError(f"MLP parameter {name} must be a contiguous fp32 CUDA tensor")
+            return t.data_ptr()
+        return self._fill(st, get)
+
+    def pack(self):
+        key = tuple((self.params[n].data_ptr(), self.params[n]._version) for n in self.names())
+        if self._packed is None or key != self._packed_key:
+            dev = self.params["lin_in.weight"].device
+            if self._packed is None or self._packed.device != dev:
+                self._packed = torch.empty(self.sizes.packed_bytes, device=dev, dtype=torch.uint8)
+            check(_lib.load().nrf_mlp_pack(C.byref(self._cparams()), self.precision, ptr(self._packed),
+                                           stream_ptr()), "nrf_mlp_pack")
+            self._packed_key = key
+        return self._packed
+
+    def forward(self, field_in, acts=None):
+        """field_in (N,kin_pad) -> (field_out (N,d_out) fp32 raw, acts buffer)."""
+        N = field_in.shape[0]
+        dev = field_in.device
+        packed = self.pack()
+        if acts is None:
+            acts = torch.empty(self.sizes.fwd_bytes_per_sample * N, device=dev, dtype=torch.uint8)
+        out = torch.empty(N, self.dims[3], device=dev, dtype=torch.float32)
+        check(_lib.load().nrf_mlp_fwd(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
+                                      ptr(acts), ptr(out), stream_ptr()), "nrf_mlp_fwd")
+        return out, acts
+
+    def backward(self, field_in, acts, d_field, grads: dict, scratch=None):
+        """Accumulates parameter grads into `grads` (same keys as params); returns dlatent (N,C)."""
+        N = field_in.shape[0]
+        dev = field_in.device
+        d_latent = self.dims[1]
+        packed = self.pack()
+        need = self.sizes.bwd_bytes_per_sample * N + self.sizes.bwd_fixed_bytes
+        if scratch is None or scratch.numel() < need:
+            scratch = torch.empty(need, device=dev, dtype=torch.uint8)
+        dlatent = torch.empty(N, d_latent, device=dev, dtype=torch.float32)
+        g = self._fill(_lib.NrfMlpGrads(), lambda n: grads[n].data_ptr() if grads.get(n) is not None else None)
+        check(_lib.load().nrf_mlp_bwd(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
+                                      ptr(acts), ptr(d_field), C.byref(g), ptr(dlatent), ptr(scratch),
+                                      stream_ptr()), "nrf_mlp_bwd")
+        return dlatent

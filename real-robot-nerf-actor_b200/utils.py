@@ -1,0 +1,123 @@
+"""Ray / encoding helpers with the reference's names (utils.py:434-567), on the C ABI where it matters."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+class AttrDict(dict):
+    """Attribute-access dict: the role dotmap.DotMap plays for forward_nerf's outputs
+    (neural_rendering.py:419,447)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def toDict(self):
+        return {k: (v.toDict() if isinstance(v, AttrDict) else v) for k, v in self.items()}
+
+
+class ConfigDict(dict):
+    """Config object supporting both cfg.key and cfg["key"], like pyhocon's ConfigTree
+    (nerfact.conf is read that way: neural_rendering.py:93-154, models_embed.py:26-120)."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in {**(d or {}), **kw}.items():
+            self[k] = ConfigDict(v) if isinstance(v, dict) and not isinstance(v, ConfigDict) else v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def default_config(**over) -> ConfigDict:
+    """The `neural_renderer{}` block of nerfact.conf:14-104, at the BASELINE dims (C=128, D=384)."""
+    d = dict(
+        foundation_model_name="diffusion", d_embed=384, d_latent=128,
+        use_multi_scale_voxel=False, d_multi_scale_latent=266, use_depth_supervision=False,
+        lambda_embed=0.01, lambda_depth=0.0, threshold_depth_supervision=0.8,
+        ray_chunk_size=512, d_lang=128, voxel_shape=100, share_mlp=True,
+        image_width=128, image_height=128, z_near=1.2, z_far=4.0,
+        regress_coord=False, regress_attention=False, ret_last_feat=False,
+        use_code=True, use_code_viewdirs=False, use_freenerf=False, use_xyz=True,
+        n_coarse=64, n_fine=64, n_fine_depth=0, white_bkgd=False, lindisp=False,
+        normalize_z=False, canon_xyz=True, use_viewdirs=True, eval_batch_size=4096,
+        noise_std=0.0, depth_std=0.001,
+        mlp=dict(n_blocks=5, d_hidden=512, combine_layer=3, combine_type="average",
+                 beta=0.0, use_spade=False, use_language=False),
+        code=dict(num_freqs=6, freq_factor=1.5, include_input=True),
+    )
+    for k, v in over.items():
+        if isinstance(v, dict) and isinstance(d.get(k), dict):
+            d[k] = {**d[k], **v}
+        else:
+            d[k] = v
+    return ConfigDict(d)
+
+
+def repeat_interleave(input, repeats, dim=0):
+    """utils.py:434-441."""
+    output = input.unsqueeze(1).expand(-1, repeats, *input.shape[1:])
+    return output.reshape(-1, *input.shape[1:])
+
+
+def combine_interleaved(t, inner_dims=(1,), agg_type="average"):
+    """utils.py:509-519."""
+    if len(inner_dims) == 1 and inner_dims[0] == 1:
+        return t
+    t = t.reshape(-1, *inner_dims, *t.shape[1:])
+    if agg_type == "average":
+        return torch.mean(t, dim=1)
+    if agg_type == "max":
+        return torch.max(t, dim=1)[0]
+    raise NotImplementedError("Unsupported combine type " + agg_type)
+
+
+def gen_rays(poses, width, height, focal, z_near, z_far, c=None):
+    """utils.py:477-506 -> (B,H,W,8), computed by nrf_raygen."""
+    f = focal.squeeze() if torch.is_tensor(focal) else focal
+    return ops.raygen(poses, width, height, f, z_near, z_far, c=c)
+
+
+def unproj_map(width, height, f, c=None, device="cuda"):
+    """utils.py:444-474 -> (H,W,3): the direction part of gen_rays for an identity pose."""
+    eye = torch.eye(4, device=device, dtype=torch.float32).unsqueeze(0)
+    return ops.raygen(eye, width, height, f, 0.0, 0.0, c=c)[0, :, :, 3:6].contiguous()
+
+
+class PositionalEncoding(torch.nn.Module):
+    """utils.py:521-567: carries the reference's persistent buffers `_freqs` / `_phases` (state_dict
+    compatibility); the encoding itself is fused into nrf_encode_points."""
+
+    def __init__(self, num_freqs=6, d_in=3, freq_factor=np.pi, include_input=True):
+        super().__init__()
+        self.num_freqs = num_freqs
+        self.d_in = d_in
+        self.freq_factor = freq_factor
+        self.freqs = freq_factor * 2.0 ** torch.arange(0, num_freqs)
+        self.d_out = self.num_freqs * 2 * d_in
+        self.include_input = include_input
+        if include_input:
+            self.d_out += d_in
+        self.register_buffer("_freqs", torch.repeat_interleave(self.freqs, 2).view(1, -1, 1))
+        _phases = torch.zeros(2 * self.num_freqs)
+        _phases[1::2] = np.pi * 0.5
+        self.register_buffer("_phases", _phases.view(1, -1, 1))
+
+    @classmethod
+    def from_conf(cls, conf, d_in=3):
+        g = lambda k: conf[k] if isinstance(conf, dict) else getattr(conf, k)
+        return cls(g("num_freqs"), d_in, g("freq_factor"), g("include_input"))

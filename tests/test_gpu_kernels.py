@@ -1,0 +1,317 @@
+"""Per-kernel parity tests: every C-ABI entry point against the oracle (oracle/nerf_oracle.py, torch
+CPU fp32) on the same seeded inputs.  Run on the B200 box: `pytest -m gpu`."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from tests.conftest import golden, load_pkg
+
+pytestmark = pytest.mark.gpu
+
+syn = load_pkg("synthetic")
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return load_pkg("ops")
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bits_equal_frac(a, b):
+    a, b = a.cpu().contiguous(), b.cpu().contiguous()
+    return float((a.view(torch.int32) == b.view(torch.int32)).float().mean())
+
+
+# ------------------------------------------------------------------------------------ rays
+def test_raygen_matches_reference(ops):
+    fx = golden("raygen_pe")
+    poses = T(fx["poses"]).cuda()
+    r = ops.raygen(poses, 80, 60, 76.18187, 1.2, 4.0).cpu()
+    ref = T(fx["rays_60x80"])
+    assert torch.equal(r[..., :3], ref[..., :3]) and torch.equal(r[..., 6:], ref[..., 6:])
+    frac = bits_equal_frac(r, ref)
+    print(f"raygen 60x80: bit-identical fraction vs CPU reference = {frac:.6f}")
+    assert (r - ref).abs().max() <= 2.5e-7
+    r = ops.raygen(poses[:2], 128, 128, torch.tensor(153.0), 1.2, 4.0).cpu()
+    assert (r[:, ::16] - T(fx["rays_128_rows"])).abs().max() <= 2.5e-7
+    r = ops.raygen(poses[:1], 128, 128, torch.tensor([150.0, 151.0]), 0.5, 3.0,
+                   c=torch.tensor([70.5, 61.25])).cpu()
+    assert (r[:, ::32] - T(fx["rays_128_c_rows"])).abs().max() <= 2.5e-7
+    assert frac > 0.99
+
+
+@pytest.mark.parametrize("Kc,lindisp,jit", [(64, False, False), (64, False, True), (128, False, True),
+                                            (96, False, True), (64, True, True), (17, False, True)])
+def test_sample_coarse_bit_exact(ops, Kc, lindisp, jit):
+    g = torch.Generator().manual_seed(Kc)
+    R = 333
+    rays = torch.rand(R, 8, generator=g)
+    rays[:, 6] = 0.5 + rays[:, 6]
+    rays[:, 7] = 3.0 + rays[:, 7]
+    jitter = torch.rand(R, Kc, generator=g) if jit else None
+    ref = O.sample_coarse(rays, Kc, jitter, lindisp)
+    out = ops.sample_coarse(rays.cuda(), Kc, jitter.cuda() if jit else None, lindisp).cpu()
+    if Kc in (64, 128):
+        assert torch.equal(out, ref)          # linspace == i/Kc exactly
+    else:                                     # linspace bits may differ between CPU and CUDA ATen
+        assert (out - ref).abs().max() <= 5e-7
+
+
+@pytest.mark.parametrize("Kc,Kf,lindisp", [(64, 64, False), (64, 32, False), (128, 128, False), (16, 12, True)])
+def test_sample_fine_bit_exact_given_cdf(ops, Kc, Kf, lindisp):
+    g = torch.Generator().manual_seed(Kc + Kf)
+    R = 257
+    rays = torch.rand(R, 8, generator=g)
+    rays[:, 6], rays[:, 7] = 1.2, 4.0
+    w = torch.rand(R, Kc, generator=g) ** 4
+    w[::7] = 0.0                                               # degenerate rays: uniform pdf
+    u = torch.rand(R, Kf, generator=g)
+    u[0, 0], u[1, 0] = 0.0, 0.99999994                          # edge draws (no upper clamp)
+    jitter = torch.rand(R, Kf, generator=g)
+    cdf = O.fine_cdf(w)
+    ind_ref, z_ref = O.sample_fine_from_cdf(rays, cdf, Kc, u, jitter, lindisp)
+    z, ind = ops.sample_fine(rays.cuda(), None, Kc, u.cuda(), jitter.cuda(), lindisp, cdf=cdf.cuda(),
+                             want_ind=True)
+    assert torch.equal(ind.cpu(), ind_ref)
+    assert torch.equal(z.cpu(), z_ref)
+    # cdf built in-kernel from the weights: identical up to rare ulp flips at bin edges
+    z2, ind2 = ops.sample_fine(rays.cuda(), w.cuda(), Kc, u.cuda(), jitter.cuda(), lindisp, want_ind=True)
+    mism = float((ind2.cpu() != ind_ref).float().mean())
+    print(f"sample_fine Kc={Kc}: bin mismatches with in-kernel cdf = {mism:.2e}")
+    assert mism < 2e-3
+    same = ind2.cpu() == ind_ref
+    assert torch.equal(z2.cpu()[same], z_ref[same])
+
+
+@pytest.mark.parametrize("K", [128, 96, 112, 256, 33])
+def test_sort_rows(ops, K):
+    g = torch.Generator().manual_seed(K)
+    z = torch.rand(301, K, generator=g)
+    z[:, 5] = z[:, 3]                                          # ties
+    ref, _ = torch.sort(z, dim=-1)
+    out, perm = ops.sort_rows(z.cuda().clone(), want_perm=True)
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(torch.gather(z, 1, perm.cpu().long()), ref)
+    assert torch.equal(torch.sort(perm.cpu().long(), dim=1)[0], torch.arange(K).expand(301, K))
+
+
+# ---------------------------------------------------------------------------------- volume
+def test_volume_transpose_roundtrip(ops):
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(2, 20, 7, 9, 11, generator=g).cuda()
+    cl = ops.volume_to_channels_last(v)
+    assert torch.equal(cl, v.permute(0, 2, 3, 4, 1).contiguous())
+    assert torch.equal(ops.volume_to_channels_first(cl), v)
+
+
+def _scene_inputs(SB, C, S, R_per, K, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    vol = syn.make_volume(SB, C, S, seed=seed)
+    poses = syn.arc_poses(SB)
+    rays = O.gen_rays(poses, 32, 32, torch.tensor(38.0), 1.2, 4.0).reshape(SB, -1, 8)
+    idx = torch.randint(32 * 32, (R_per,), generator=g)
+    rays = rays[:, idx].reshape(-1, 8).contiguous()
+    z = O.sample_coarse(rays, K, torch.rand(SB * R_per, K, generator=g))
+    return vol, rays, z
+
+
+@pytest.mark.parametrize("C,S", [(128, 24), (16, 12), (64, 17)])
+def test_encode_points_fp32_matches_oracle(ops, C, S):
+    SB, R_per, K = 2, 50, 24
+    vol, rays, z = _scene_inputs(SB, C, S, R_per, K, seed=C)
+    pts = rays[:, None, :3] + z.unsqueeze(2) * rays[:, None, 3:6]
+    dirs = rays[:, None, 3:6].expand(-1, K, -1)
+    ref = O.field(None, vol, pts.reshape(SB, -1, 3), dirs.reshape(SB, -1, 3), syn.BOUNDS,
+                  return_mlp_input=True)
+    vol_cl = ops.volume_to_channels_last(vol.cuda())
+    out, p = ops.encode_points(rays.cuda(), z.cuda(), R_per, vol_cl, syn.BOUNDS,
+                               precision=ops.NRF_PREC_FP32, want_points=True)
+    out, p = out.cpu(), p.cpu()
+    assert torch.equal(p, pts.reshape(-1, 3)), "sample positions must be bit-exact"
+    lat_frac = bits_equal_frac(out[:, :C], ref[:, :C])
+    print(f"encode C={C}: latent bit-identical fraction = {lat_frac:.6f}")
+    assert (out[:, :C] - ref[:, :C]).abs().max() <= 1e-6
+    assert lat_frac > 0.999
+    assert torch.equal(out[:, C:C + 3], ref[:, C:C + 3])                 # canonical xyz: bit-exact
+    assert (out[:, C + 3:C + 39] - ref[:, C + 3:C + 39]).abs().max() <= 2e-6   # sin(): ulp-level
+    assert torch.equal(out[:, C + 39:C + 42], ref[:, C + 39:C + 42])     # view direction
+    assert (out[:, C + 42:] == 0).all()
+    # bf16 operand mode is the fp32 row rounded to nearest-even
+    out16 = ops.encode_points(rays.cuda(), z.cuda(), R_per, vol_cl, syn.BOUNDS, precision=ops.NRF_PREC_BF16)
+    assert torch.equal(out16.cpu(), out.to(torch.bfloat16))
+
+
+def test_encode_points_outside_box_and_edges(ops):
+    """Zero padding outside the grid, exact hits on the faces, far-away points."""
+    C, S = 8, 5
+    g = torch.Generator().manual_seed(1)
+    vol = torch.randn(1, C, S, S, S, generator=g)
+    b = torch.tensor(syn.BOUNDS)
+    canon = torch.tensor([[0., 0., 0.], [1., 1., 1.], [0.5, 0.5, 0.5], [-0.01, 0.5, 0.5], [1.2, 0.3, 0.1],
+                          [0.25, 0.5, 0.75], [50., -50., 3.], [1.0, 0.0, 0.5]])
+    world = canon * (b[3:] - b[:3]) + b[:3]
+    n = world.shape[0]
+    rays = torch.zeros(n, 8)
+    rays[:, :3] = world
+    rays[:, 3:6] = torch.tensor([0., 0., 1.])
+    rays[:, 6], rays[:, 7] = 0.0, 1.0
+    z = torch.zeros(n, 1)
+    ref = O.field(None, vol, world.reshape(1, n, 3), rays[:, 3:6].reshape(1, n, 3), syn.BOUNDS,
+                  return_mlp_input=True)
+    out = ops.encode_points(rays.cuda(), z.cuda(), n, ops.volume_to_channels_last(vol.cuda()), syn.BOUNDS,
+                            precision=ops.NRF_PREC_FP32).cpu()
+    assert (out[:, :C] - ref[:, :C]).abs().max() <= 1e-6
+    assert (out[6, :C] == 0).all() and (out[4, :C] == 0).all()
+
+
+def test_scatter_volume_grad_matches_autograd(ops):
+    SB, C, S, R_per, K = 2, 32, 10, 40, 16
+    vol, rays, z = _scene_inputs(SB, C, S, R_per, K, seed=5)
+    vol.requires_grad_(True)
+    pts = (rays[:, None, :3] + z.unsqueeze(2) * rays[:, None, 3:6]).reshape(SB, -1, 3)
+    lat = O.trilinear_gather(vol, O.world_to_canonical(pts, syn.BOUNDS))
+    g = torch.Generator().manual_seed(9)
+    dl = torch.randn(lat.shape, generator=g)
+    lat.backward(dl)
+    grad_cl = torch.zeros(SB, S, S, S, C, device="cuda")
+    ops.scatter_volume_grad(rays.cuda(), z.cuda(), R_per, dl.reshape(-1, C).cuda(), grad_cl, syn.BOUNDS)
+    got = ops.volume_to_channels_first(grad_cl).cpu()
+    assert rel(got, vol.grad) < 1e-6
+
+
+# ------------------------------------------------------------------------------ compositing
+@pytest.mark.parametrize("K,D,white", [(64, 384, False), (128, 384, False), (96, 24, True), (40, 8, False)])
+def test_composite_fwd_bwd_matches_oracle(ops, K, D, white):
+    g = torch.Generator().manual_seed(K + D)
+    R = 37
+    raw = torch.randn(R, K, 4 + D, generator=g)
+    raw[..., 3] = raw[..., 3] * 3.0                      # sigma: mix of <0 (gated) and large values
+    raw.requires_grad_(True)
+    rays = torch.rand(R, 8, generator=g)
+    rays[:, 6], rays[:, 7] = 1.2, 4.0
+    z = O.sample_coarse(rays, K, torch.rand(R, K, generator=g)).requires_grad_(True)
+    act = torch.cat([torch.sigmoid(raw[..., :3]), torch.relu(raw[..., 3:4]), raw[..., 4:]], -1)
+    w, rgb, emb, dep = O.composite_from_field(act, z, rays[:, -1:], white_bkgd=white)
+    d_rgb, d_emb = torch.randn(R, 3, generator=g), torch.randn(R, D, generator=g)
+    d_dep, d_w = torch.randn(R, generator=g), torch.randn(R, K, generator=g) * 0.1
+    (rgb * d_rgb).sum().add((emb * d_emb).sum()).add((dep * d_dep).sum()).add((w * d_w).sum()).backward()
+
+    raw_c = raw.detach().reshape(R * K, 4 + D).cuda()
+    w2, rgb2, emb2, dep2 = ops.composite_fwd(raw_c, z.detach().cuda(), rays.cuda(), D, white)
+    assert rel(w2, w.detach()) < 2e-6 and rel(rgb2, rgb.detach()) < 2e-6
+    assert rel(emb2, emb.detach()) < 2e-6 and rel(dep2, dep.detach()) < 2e-6
+    dfield, dz = ops.composite_bwd(raw_c, z.detach().cuda(), rays.cuda(), D, d_rgb.cuda(), d_emb.cuda(),
+                                   d_dep.cuda(), d_w.cuda(), precision=ops.NRF_PREC_FP32, white_bkgd=white,
+                                   want_dz=True)
+    ldg = dfield.shape[1]
+    assert ldg % 64 == 0 and (dfield[:, 4 + D:] == 0).all()
+    assert rel(dfield[:, :4 + D].reshape(R, K, -1), raw.grad) < 1e-5
+    assert rel(dz, z.grad) < 1e-5
+    df16 = ops.composite_bwd(raw_c, z.detach().cuda(), rays.cuda(), D, d_rgb.cuda(), d_emb.cuda(),
+                             d_dep.cuda(), d_w.cuda(), precision=ops.NRF_PREC_BF16, white_bkgd=white)
+    assert torch.equal(df16.cpu(), dfield.cpu().to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------ GEMMs
+def _bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K1,K2", [(128, 256, 64, 0), (300, 512, 512, 0), (1000, 512, 512, 128),
+                                       (257, 128, 512, 0), (4096 + 77, 512, 192, 0), (130, 512, 448, 0)])
+def test_gemm_tc_against_fp32_matmul_of_bf16_operands(ops, M, N, K1, K2):
+    g = torch.Generator().manual_seed(M + N + K1 + K2)
+    A1 = torch.randn(M, K1, generator=g).to(torch.bfloat16)
+    A2 = torch.randn(M, K2, generator=g).to(torch.bfloat16) if K2 else None
+    B = (torch.randn(N, K1 + K2, generator=g) / math.sqrt(K1 + K2)).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    resid = torch.randn(M, N, generator=g)
+    mask = torch.randn(M, N, generator=g).relu().to(torch.bfloat16)
+    A = A1.float() if A2 is None else torch.cat([A1.float(), A2.float()], 1)
+    acc = A @ B.float().t()
+
+    # plain
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(A1.cuda(), B.cuda(), A2=None if A2 is None else A2.cuda(), out_f32=out)
+    assert rel(out, acc) < 2e-6, "accumulation must be fp32-grade"
+    # forward-style epilogue: bias + residual (in place) + relu'd bf16 copy
+    xres = resid.clone().cuda()
+    act = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A1.cuda(), B.cuda(), A2=None if A2 is None else A2.cuda(), bias=bias.cuda(), resid=xres,
+             out_f32=xres, out_act=act, relu_act=True)
+    want = acc + bias + resid
+    assert rel(xres, want) < 2e-6
+    assert torch.equal(act.cpu(), xres.cpu().relu().to(torch.bfloat16))
+    # dgrad-style epilogue: ReLU gate from a saved activation + residual, bf16 copy without relu
+    out2 = torch.empty(M, N, device="cuda")
+    act2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A1.cuda(), B.cuda(), A2=None if A2 is None else A2.cuda(), mask_src=mask.cuda(),
+             resid=resid.cuda(), out_f32=out2, out_act=act2)
+    want2 = torch.where(mask.float() > 0, acc, torch.zeros_like(acc)) + resid
+    assert rel(out2, want2) < 2e-6
+    assert torch.equal(act2.cpu(), out2.cpu().to(torch.bfloat16))
+
+
+def test_gemm_tc_partial_store(ops):
+    """lin_out: N padded to 512, only 388 columns stored into a 388-wide fp32 matrix."""
+    g = torch.Generator().manual_seed(3)
+    M, K, N, ns = 333, 512, 512, 388
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    B = torch.zeros(N, K)
+    B[:ns] = torch.randn(ns, K, generator=g) / math.sqrt(K)
+    B = B.to(torch.bfloat16)
+    bias = torch.zeros(N)
+    bias[:ns] = torch.randn(ns, generator=g)
+    out = torch.full((M, ns), 7.0, device="cuda")
+    ops.gemm(A.cuda(), B.cuda(), bias=bias.cuda(), out_f32=out, n_store=ns)
+    assert rel(out, A.float() @ B.float().t()[:, :ns] + bias[:ns]) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K,nv,kv", [(64, 128, 64, 128, 64), (1000, 512, 512, 512, 512),
+                                         (5000, 448, 512, 388, 512), (777, 512, 128, 512, 128),
+                                         (20000, 512, 64, 512, 42), (4099, 512, 256, 512, 256)])
+def test_wgrad_tc(ops, M, N, K, nv, kv):
+    g = torch.Generator().manual_seed(M + N + K)
+    G = torch.randn(M, N, generator=g).to(torch.bfloat16)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    dW = torch.ones(nv, kv, device="cuda")
+    db = torch.ones(nv, device="cuda")
+    ops.wgrad(G.cuda(), A.cuda(), dW, db, n_valid=nv, k_valid=kv)
+    want = (G.float().t() @ A.float())[:nv, :kv] + 1.0
+    assert rel(dW, want) < 5e-6
+    assert rel(db, G.float().sum(0)[:nv] + 1.0) < 5e-6
+
+
+@pytest.mark.parametrize("M,N,K1,K2", [(100, 64, 58, 0), (513, 388, 512, 0), (300, 512, 512, 128), (65, 70, 33, 16)])
+def test_gemm_simt_fp32(ops, M, N, K1, K2):
+    g = torch.Generator().manual_seed(M + N)
+    A1 = torch.randn(M, K1, generator=g)
+    A2 = torch.randn(M, K2, generator=g) if K2 else None
+    B = torch.randn(N, K1 + K2, generator=g) / math.sqrt(K1 + K2)
+    bias, resid = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    mask = torch.randn(M, N, generator=g).relu()
+    A = A1 if A2 is None else torch.cat([A1, A2], 1)
+    acc = (A.double() @ B.double().t()).float()
+    out = torch.empty(M, N, device="cuda")
+    act = torch.empty(M, N, device="cuda")
+    ops.gemm(A1.cuda(), B.cuda(), A2=None if A2 is None else A2.cuda(), bias=bias.cuda(), mask_src=mask.cuda(),
+             resid=resid.cuda(), out_f32=out, out_act=act, relu_act=True, precision=ops.NRF_PREC_FP32)
+    want = torch.where(mask > 0, acc + bias, torch.zeros_like(acc)) + resid
+    assert rel(out, want) < 1e-6
+    assert rel(act, want.relu()) < 1e-6
+    dW = torch.zeros(N, K1, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    G = torch.randn(M, N, generator=g)
+    ops.wgrad(G.cuda(), A1.cuda(), dW, db, precision=ops.NRF_PREC_FP32)
+    assert rel(dW, (G.double().t() @ A1.double()).float()) < 1e-6
+    assert rel(db, G.sum(0)) < 1e-6

@@ -1,0 +1,227 @@
+"""End-to-end parity of the CUDA render path: the field MLP and NeuralRenderer against the oracle and
+against the golden outputs of the unmodified reference (tests/golden, see make_golden.py).
+
+Tolerances: the fp32 precision mode must match the fp32 reference at 1e-4
+relative-L2 on every output and gradient; the bf16 tensor-core mode is compared with (a) the fp32
+reference, reported and loosely bounded, and (b) a bf16-operand emulation of the oracle."""
+from unittest import mock
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from tests.conftest import golden, load_pkg
+from tests.test_oracle_golden import syn_case_inputs, _case_inputs
+
+pytestmark = pytest.mark.gpu
+
+syn = load_pkg("synthetic")
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return load_pkg("ops")
+
+
+@pytest.fixture(scope="module")
+def NR():
+    return load_pkg("neural_rendering")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def cosine(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def make_renderer(NR, meta, params, precision):
+    U = load_pkg("utils")
+    S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
+    cfg = U.default_config(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H, n_coarse=Kc,
+                           n_fine=Kf, n_fine_depth=Kfd, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden))
+    ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS), precision=precision)
+    sd = ren.state_dict()
+    for k, v in params.items():
+        sd["nerf_model.mlp_coarse." + k].copy_(v)
+    return ren.cuda()
+
+
+# --------------------------------------------------------------------------------- field MLP
+@pytest.mark.parametrize("precision,C,H,D,N", [("fp32", 16, 64, 24, 300), ("fp32", 128, 512, 384, 700),
+                                               ("bf16", 128, 512, 384, 1500), ("bf16", 64, 256, 60, 517)])
+def test_field_mlp_forward_backward(ops, NR, precision, C, H, D, N):
+    g = torch.Generator().manual_seed(N)
+    p = O.init_params(d_in=42, d_latent=C, d_hidden=H, d_out=4 + D, seed=1)
+    for k in p:
+        if k.endswith(".bias"):
+            p[k] = 0.05 * torch.randn(p[k].shape, generator=g)
+    mlp = NR.ResnetFC(d_in=42, d_out=4 + D, n_blocks=5, d_latent=C, d_hidden=H, combine_layer=3)
+    mlp.load_state_dict(p)
+    mlp = mlp.cuda()
+    zx = torch.randn(N, C + 42, generator=g)
+    zx[:, :C] *= 0.1
+    d_out = torch.randn(N, 4 + D, generator=g)
+    if precision == "bf16":
+        zx = zx.to(torch.bfloat16).float()
+        d_out = d_out.to(torch.bfloat16).float()
+    # oracle (fp32, and bf16-operand emulation for the tensor-core mode)
+    def run_oracle(operand_dtype):
+        pp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        x = zx.clone().requires_grad_(True)
+        out = O.resnetfc(pp, x, C, operand_dtype=operand_dtype)
+        (out * d_out).sum().backward()
+        return out.detach(), x.grad[:, :C], {k: v.grad for k, v in pp.items()}
+    out32, dz32, gp32 = run_oracle(None)
+    x = zx.cuda().requires_grad_(True)
+    out, _ = mlp(x, precision=precision)
+    (out * d_out.cuda()).sum().backward()
+    got = {k: v.grad for k, v in mlp.named_parameters()}
+    if precision == "fp32":
+        assert rel(out, out32) < 2e-5
+        assert rel(x.grad[:, :C], dz32) < 5e-5
+        assert float(x.grad[:, C:].abs().max()) == 0.0          # no gradient reaches PE / viewdirs
+        for k in gp32:
+            assert rel(got[k], gp32[k]) < 5e-5, k
+    else:
+        out16, dz16, gp16 = run_oracle(torch.bfloat16)
+        e_out, e_dz = rel(out, out16), rel(x.grad[:, :C], dz16)
+        print(f"bf16 MLP vs bf16-emulated oracle: out {e_out:.2e}  dlatent {e_dz:.2e}; "
+              f"vs fp32 oracle: out {rel(out, out32):.2e}  dlatent {rel(x.grad[:, :C], dz32):.2e}")
+        assert e_out < 5e-3
+        assert e_dz < 3e-2 and cosine(x.grad[:, :C], dz16) > 0.999
+        for k in gp16:
+            assert rel(got[k], gp16[k]) < 3e-2 and cosine(got[k], gp16[k]) > 0.999, k
+        assert rel(out, out32) < 3e-2
+
+
+# ------------------------------------------------------------------------ NeuralRenderer e2e
+def _run_cuda(ren, vol, rays, noise, gt_rgb, gt_embed):
+    vol = vol.clone().cuda().requires_grad_(True)
+    ren.encode(None, None, None, vol, None, None, None)
+    out = ren.forward_nerf(rays.cuda(), want_weights=True, noise={k: v.cuda() for k, v in noise.items()})
+    loss = O.rendering_loss({lvl: {k: out[lvl][k] for k in ("rgb", "embed", "depth")} for lvl in ("coarse", "fine")},
+                            gt_rgb.cuda(), gt_embed.cuda())["loss"]
+    loss.backward()
+    grads = {k[len("nerf_model.mlp_coarse."):]: v.grad for k, v in ren.named_parameters()
+             if k.startswith("nerf_model.mlp_coarse.")}
+    return out, loss, vol.grad, grads
+
+
+@pytest.mark.parametrize("name", ["small_kfd0", "small_noperturb", "small_kfd4"])
+def test_small_golden_fp32(ops, NR, name):
+    """Tiny-dims cases against the reference's own outputs and gradients (fp32 parity mode)."""
+    fx = golden(name)
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    ren = make_renderer(NR, meta, ci["params"], "fp32")
+    rays = T(fx["rays"])
+    idx = T(fx["idx"])
+    gt_rgb = T(fx["gt_rgb_img"]).reshape(ci["SB"], -1, 3)[:, idx]
+    gt_emb = T(fx["gt_embed_img"]).reshape(ci["SB"], -1, ci["D"])[:, idx]
+    out, loss, vgrad, grads = _run_cuda(ren, T(fx["vol"]), rays, ci["noise"], gt_rgb, gt_emb)
+    assert torch.equal(out.coarse.z.cpu(), T(fx["z_coarse"])), "coarse sample depths must be bit-exact"
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "weights"):
+            e = rel(out[lvl][k], T(fx[f"{lvl}_{k}"]))
+            assert e < 1e-4, (lvl, k, e)
+    assert abs(float(loss) - float(fx["loss"])) < 1e-5
+    assert rel(vgrad, T(fx["vgrad"])) < 2e-4
+    for k, gk in grads.items():
+        assert rel(gk, T(fx["grad." + k])) < 2e-4, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_dims_golden(ops, NR, precision):
+    """BASELINE dims (C=128, D=384, hidden 512, 64+64 samples) against the reference's outputs."""
+    fx = golden("full_s32")
+    meta = [int(v) for v in fx["meta"]]
+    S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
+    inp = syn_case_inputs(fx)
+    ren = make_renderer(NR, meta, inp["params"], precision)
+    out, loss, vgrad, grads = _run_cuda(ren, inp["vol"], inp["rays"], inp["noise"], inp["gt_rgb"], inp["gt_embed"])
+    assert torch.equal(out.coarse.z.cpu(), T(fx["z_coarse"]))
+    errs = {(lvl, k): rel(out[lvl][k], T(fx[f"{lvl}_{k}"])) for lvl in ("coarse", "fine")
+            for k in ("rgb", "embed", "depth", "weights")}
+    sign = inp["sign"].cuda()
+    e_vsum = rel(vgrad.sum(1), T(fx["vgrad_sum"]))
+    e_vsign = rel((vgrad * sign.view(1, C, 1, 1, 1)).sum(1), T(fx["vgrad_sign"]))
+    e_par = {}
+    for k, gk in grads.items():
+        if "grad." + k in fx.files:
+            e_par[k] = rel(gk, T(fx["grad." + k]))
+        else:
+            rows = torch.randperm(gk.shape[0], generator=torch.Generator().manual_seed(5))[:64]
+            e_par[k] = rel(gk[rows.cuda()], T(fx["gradrows." + k]))
+    worst_par = max(e_par.values())
+    print(f"[{precision}] outputs: " + ", ".join(f"{a}.{b}={v:.1e}" for (a, b), v in errs.items()))
+    print(f"[{precision}] loss {float(loss):.6f} vs {float(fx['loss']):.6f}; dvoxel {e_vsum:.1e}/{e_vsign:.1e}; "
+          f"worst dparam {worst_par:.1e}")
+    if precision == "fp32":
+        assert max(errs.values()) < 1e-4
+        assert abs(float(loss) - float(fx["loss"])) < 1e-5
+        assert e_vsum < 3e-4 and e_vsign < 3e-4 and worst_par < 3e-4
+    else:
+        # bf16 operands vs the fp32 reference: SURVEY section 10 measured 4-8e-3 forward, ~1e-1 gradients
+        assert errs[("coarse", "rgb")] < 3e-2 and errs[("coarse", "embed")] < 3e-2
+        assert errs[("fine", "rgb")] < 5e-2 and errs[("fine", "embed")] < 5e-2
+        assert errs[("coarse", "depth")] < 1e-2
+        assert abs(float(loss) - float(fx["loss"])) < 5e-3
+        assert e_vsum < 0.3 and worst_par < 0.3
+
+
+def test_forward_loss_dict_and_rendering(ops, NR):
+    """forward() returns the reference's keys/values; rendering() returns full images."""
+    fx = golden("small_kfd0")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    ren = make_renderer(NR, meta, ci["params"], "fp32")
+    vol = T(fx["vol"]).cuda().requires_grad_(True)
+    poses = T(fx["poses"]).cuda()
+    focal = torch.tensor(float(fx["focal"])).cuda()
+    idx = T(fx["idx"]).cuda()
+    R = ci["SB"] * ci["n_rays"]
+    noise = {k: v.cuda() for k, v in ci["noise"].items()}
+    with mock.patch.object(torch, "randint", lambda *a, **k: idx.clone()), \
+            mock.patch.object(ren, "_draw_noise", lambda R_, dev: noise):
+        out = ren(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=vol,
+                  voxel_poses=poses, focal=focal, gt_rgb=T(fx["gt_rgb_img"]).cuda(), gt_depth=None,
+                  gt_pose=poses, c=None, lang_goal=None, gt_embed=T(fx["gt_embed_img"]).cuda())
+    assert list(out.keys()) == ["loss", "loss_rgb_coarse", "loss_rgb_fine", "loss_rgb", "loss_embed_coarse",
+                                "loss_embed_fine", "loss_embed", "loss_depth_coarse", "loss_depth_fine",
+                                "loss_depth", "psnr"]
+    assert torch.is_tensor(out["loss"]) and all(isinstance(out[k], float) for k in list(out)[1:])
+    assert abs(float(out["loss"]) - float(fx["loss"])) < 1e-5
+    got = [out[k] for k in ("loss_rgb_coarse", "loss_rgb_fine", "loss_embed_coarse", "loss_embed_fine", "psnr")]
+    assert np.allclose(got, fx["loss_items"], rtol=2e-4)
+    out["loss"].backward()
+    assert rel(vol.grad, T(fx["vgrad"])) < 2e-4
+    # rendering(): SB forced to 1 (neural_rendering.py:487) -> use scene 0's volume for both cameras
+    ren.perturb = False
+    rgb, emb, dep = ren.rendering(voxel_feat=vol.detach()[:1], language=None, multi_scale_voxel_list=None,
+                                  voxel_density=None, voxel_pose=None, focal=focal, tgt_pose=poses, c=None)
+    H, W, D = ci["H"], ci["W"], ci["D"]
+    assert rgb.shape == (2, H, W, 3) and emb.shape == (2, H, W, D) and dep.shape == (2, H, W)
+    rays = O.gen_rays(poses.cpu(), W, H, focal.cpu(), 1.2, 4.0).reshape(1, -1, 8)
+    kf = ci["Kf"] - ci["Kfd"]
+    u = ((torch.arange(kf, dtype=torch.float32) + 0.5) / kf).repeat(rays.shape[1], 1)
+    ref = O.forward_nerf(ci["params"], T(fx["vol"])[:1], rays, syn.BOUNDS, ci["Kc"], ci["Kf"], ci["Kfd"],
+                         noise={"u": u})
+    assert rel(rgb.reshape(1, -1, 3), ref["fine"]["rgb"]) < 1e-4
+    assert rel(emb.reshape(1, -1, D), ref["fine"]["embed"]) < 1e-4
+    assert rel(dep.reshape(1, -1), ref["fine"]["depth"]) < 1e-4
+    with pytest.raises(RuntimeError):
+        ren.rendering(voxel_feat=vol.detach(), language=None, multi_scale_voxel_list=None, voxel_density=None,
+                      voxel_pose=None, focal=focal, tgt_pose=poses, c=None)
+
+
+def test_cpu_tensors_are_rejected(ops):
+    with pytest.raises(Exception):
+        ops.sample_coarse(torch.rand(4, 8), 8)
