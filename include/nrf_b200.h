@@ -188,6 +188,27 @@ int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precision, const 
                 int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* grads,
                 float* dlatent, void* scratch, void* stream);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------
+ * nrf_launch_count: number of kernels this library has launched in this process (monotonic).
+ * nrf_timing_begin: from now on bracket every kernel launch with a CUDA event pair on its own stream.
+ * nrf_timing_end:   synchronise, sum the durations per category into ms[cat] / launches[cat]
+ *                   (arrays of NRF_TIMING_CATEGORIES), stop recording. */
+#define NRF_CAT_GEMM 0        /* tcgen05 forward / dgrad GEMMs (gemm_tc_kernel)   */
+#define NRF_CAT_WGRAD 1       /* tcgen05 weight-gradient GEMMs (wgrad_tc_kernel)  */
+#define NRF_CAT_ENCODE 2      /* points + trilinear gather + positional encoding  */
+#define NRF_CAT_COMPOSITE_FWD 3
+#define NRF_CAT_COMPOSITE_BWD 4
+#define NRF_CAT_SCATTER 5     /* volume-gradient scatter                          */
+#define NRF_CAT_TRANSPOSE 6   /* volume re-layout                                 */
+#define NRF_CAT_COLSUM 7      /* bias gradients                                   */
+#define NRF_CAT_SAMPLING 8    /* raygen, coarse / fine sampling, sort             */
+#define NRF_CAT_SIMT 9        /* fp32 parity-mode GEMMs                           */
+#define NRF_CAT_MISC 10       /* weight packing, small vector kernels             */
+#define NRF_TIMING_CATEGORIES 11
+int64_t nrf_launch_count(void);
+int nrf_timing_begin(void);
+int nrf_timing_end(double* ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

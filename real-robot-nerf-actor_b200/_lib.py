@@ -73,7 +73,12 @@ _SIGNATURES = {
     "nrf_mlp_fwd": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, _p],
     "nrf_mlp_bwd": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, C.POINTER(NrfMlpGrads), _p, _p, _p],
 }
-EXPORTS = sorted(list(_SIGNATURES) + ["nrf_version", "nrf_last_error", "nrf_wgrad_workspace_bytes"])
+_SIGNATURES["nrf_timing_begin"] = []
+_SIGNATURES["nrf_timing_end"] = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+EXPORTS = sorted(list(_SIGNATURES) + ["nrf_version", "nrf_last_error", "nrf_wgrad_workspace_bytes",
+                                      "nrf_launch_count"])
+TIMING_CATEGORIES = ["gemm_tc", "wgrad_tc", "encode", "composite_fwd", "composite_bwd", "scatter", "transpose",
+                     "colsum", "sampling", "simt", "misc"]
 
 _lib = None
 
@@ -99,6 +104,8 @@ def load():
     lib.nrf_last_error.restype = C.c_char_p
     lib.nrf_wgrad_workspace_bytes.argtypes = [_i, _i]
     lib.nrf_wgrad_workspace_bytes.restype = C.c_int64
+    lib.nrf_launch_count.argtypes = []
+    lib.nrf_launch_count.restype = C.c_int64
     _lib = lib
     return lib
 
@@ -117,3 +124,20 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load().nrf_launch_count())
+
+
+def timing_begin():
+    check(load().nrf_timing_begin(), "nrf_timing_begin")
+
+
+def timing_end():
+    """-> {category: (milliseconds, launches)} for every kernel launched since timing_begin()."""
+    n = len(TIMING_CATEGORIES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(load().nrf_timing_end(ms, cnt), "nrf_timing_end")
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(TIMING_CATEGORIES)}

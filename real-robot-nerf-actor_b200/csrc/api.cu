@@ -1,5 +1,8 @@
 // C-ABI glue: error text, device query, and the GEMM entry points of include/nrf_b200.h.
 #include <stdarg.h>
+#include <atomic>
+#include <mutex>
+#include <vector>
 #include "gemm_common.cuh"
 
 namespace nrf {
@@ -25,9 +28,62 @@ int sm_count() {
   return cached[dev];
 }
 
+struct TimedLaunch { int cat; cudaEvent_t a, b; };
+static std::atomic<int64_t> g_launches{0};
+static std::atomic<bool> g_timing{false};
+static std::mutex g_timing_mu;
+static std::vector<TimedLaunch> g_timed;
+
+LaunchScope::LaunchScope(int category, cudaStream_t s) : idx(-1), stream(s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_timing.load(std::memory_order_relaxed)) return;
+  TimedLaunch t;
+  t.cat = category;
+  if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
+  cudaEventRecord(t.a, s);
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timed.push_back(t);
+  idx = (int)g_timed.size() - 1;
+}
+
+LaunchScope::~LaunchScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if (idx < (int)g_timed.size()) cudaEventRecord(g_timed[idx].b, stream);
+}
+
 }  // namespace nrf
 
 using namespace nrf;
+
+extern "C" int64_t nrf_launch_count(void) { return g_launches.load(); }
+
+extern "C" int nrf_timing_begin(void) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (auto& t : g_timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  g_timed.clear();
+  g_timing.store(true);
+  return NRF_OK;
+}
+
+extern "C" int nrf_timing_end(double* ms, int64_t* launches) {
+  NRF_REQUIRE(ms && launches, NRF_EINVAL, "nrf_timing_end: null output");
+  g_timing.store(false);
+  NRF_CUDA_OK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (int c = 0; c < NRF_TIMING_CATEGORIES; ++c) { ms[c] = 0.0; launches[c] = 0; }
+  for (auto& t : g_timed) {
+    float dt = 0.f;
+    if (cudaEventElapsedTime(&dt, t.a, t.b) == cudaSuccess && t.cat >= 0 && t.cat < NRF_TIMING_CATEGORIES) {
+      ms[t.cat] += dt;
+      launches[t.cat] += 1;
+    }
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  g_timed.clear();
+  return NRF_OK;
+}
 
 extern "C" const char* nrf_version(void) { return "nrf_b200 0.1 (sm_100a; tcgen05/TMEM/TMA)"; }
 extern "C" const char* nrf_last_error(void) { return g_err; }

@@ -34,6 +34,14 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 int sm_count();
 
+// Counts every kernel launch and, while nrf_timing_begin() is active, brackets it with an event pair.
+struct LaunchScope {
+  LaunchScope(int category, cudaStream_t stream);
+  ~LaunchScope();
+  int idx;
+  cudaStream_t stream;
+};
+
 constexpr int kWarp = 32;
 
 __device__ __forceinline__ float warp_sum(float v) {

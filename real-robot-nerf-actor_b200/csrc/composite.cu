@@ -283,8 +283,10 @@ extern "C" int nrf_composite_fwd(const float* field_out, int ldo, const float* z
   if (rc) return rc;
   int warps = 4;
   size_t smem = (size_t)warps * 2 * K * sizeof(float);
+  { LaunchScope ls_(NRF_CAT_COMPOSITE_FWD, as_stream(stream));
   composite_fwd_kernel<<<(R + warps - 1) / warps, warps * kWarp, smem, as_stream(stream)>>>(
       field_out, ldo, z, rays, R, K, D, white_bkgd, weights, rgb, embed, depth);
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
@@ -306,16 +308,20 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
     if (smem > 48 * 1024)
       NRF_CUDA_OK(cudaFuncSetAttribute(composite_bwd_kernel<__nv_bfloat16>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { LaunchScope ls_(NRF_CAT_COMPOSITE_BWD, as_stream(stream));
     composite_bwd_kernel<__nv_bfloat16><<<grid, block, smem, as_stream(stream)>>>(
         field_out, ldo, z, rays, R, K, D, white_bkgd, d_rgb, d_embed, d_depth, d_weights,
         reinterpret_cast<__nv_bfloat16*>(d_field), ldg, d_z);
+    }
   } else {
     if (smem > 48 * 1024)
       NRF_CUDA_OK(cudaFuncSetAttribute(composite_bwd_kernel<float>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { LaunchScope ls_(NRF_CAT_COMPOSITE_BWD, as_stream(stream));
     composite_bwd_kernel<float><<<grid, block, smem, as_stream(stream)>>>(
         field_out, ldo, z, rays, R, K, D, white_bkgd, d_rgb, d_embed, d_depth, d_weights,
         reinterpret_cast<float*>(d_field), ldg, d_z);
+    }
   }
   NRF_LAUNCH_OK();
   return NRF_OK;

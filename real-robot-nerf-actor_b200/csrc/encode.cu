@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) encode_points_kernel(EncodeArgs a) {
         int f = q / 6, w = q % 6;
         float freq = a.freq_factor * (float)(1 << f);
         float phase = (w >= 3) ? 1.57079637050628662109375f : 0.0f;   // fp32(pi/2), utils.py:542
-        val = sinf(__fadd_rn(phase, __fmul_rn(cxyz[w % 3], freq)));
+        val = sinf(__fmaf_rn(cxyz[w % 3], freq, phase));   // addcmul contracts to an FMA in ATen
       } else if (e < n_pe + 3) {
         val = ray[3 + (e - n_pe)];
       }
@@ -205,9 +205,13 @@ static int volume_transpose(const float* src, float* dst, int SB, int C, int64_t
   dim3 block(32, 8);
   dim3 grid((unsigned)((V + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)SB);
   if (to_last)
+    { LaunchScope ls_(NRF_CAT_TRANSPOSE, as_stream(stream));
     volume_transpose_kernel<true><<<grid, block, 0, as_stream(stream)>>>(src, dst, C, V);
+    }
   else
+    { LaunchScope ls_(NRF_CAT_TRANSPOSE, as_stream(stream));
     volume_transpose_kernel<false><<<grid, block, 0, as_stream(stream)>>>(src, dst, C, V);
+    }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
@@ -243,9 +247,13 @@ extern "C" int nrf_encode_points(const float* rays, const float* z, int R, int K
   int max_blocks = sm_count() * 16;
   int blocks = (int)(want < max_blocks ? want : max_blocks);
   if (out_bf16)
+    { LaunchScope ls_(NRF_CAT_ENCODE, as_stream(stream));
     encode_points_kernel<__nv_bfloat16><<<blocks, threads, 0, as_stream(stream)>>>(a);
+    }
   else
+    { LaunchScope ls_(NRF_CAT_ENCODE, as_stream(stream));
     encode_points_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(a);
+    }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
@@ -269,7 +277,9 @@ extern "C" int nrf_scatter_volume_grad(const float* rays, const float* z, int R,
   int64_t want = (N + 7) / 8;
   int max_blocks = sm_count() * 16;
   int blocks = (int)(want < max_blocks ? want : max_blocks);
+  { LaunchScope ls_(NRF_CAT_SCATTER, as_stream(stream));
   scatter_volume_grad_kernel<<<blocks, threads, 0, as_stream(stream)>>>(a);
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }

@@ -140,8 +140,10 @@ int gemm_simt_launch(const NrfGemm& g, cudaStream_t stream) {
     const float* A1 = reinterpret_cast<const float*>(g.A1) + m_off * g.lda1;
     const float* A2 = g.A2 ? reinterpret_cast<const float*>(g.A2) + m_off * g.lda2 : nullptr;
     dim3 gr((g.N + BN - 1) / BN, (unsigned)((rows + BM - 1) / BM));
+    { LaunchScope ls_(NRF_CAT_SIMT, stream);
     gemm_simt_kernel<<<gr, 256, 0, stream>>>(A1, g.K1, g.lda1, A2, g.K2, g.lda2,
                                               reinterpret_cast<const float*>(g.B), g.ldb, g.N, e);
+    }
     NRF_LAUNCH_OK();
   }
   return NRF_OK;
@@ -158,9 +160,11 @@ int wgrad_simt_launch(const void* G, int ldg, const void* A, int lda, int M, int
   int m_per = ((M + splits - 1) / splits + BK - 1) / BK * BK;
   splits = (M + m_per - 1) / m_per;
   dim3 grid(k_tiles, n_tiles, splits);
+  { LaunchScope ls_(NRF_CAT_SIMT, stream);
   wgrad_simt_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(G), ldg,
                                                reinterpret_cast<const float*>(A), lda, M, n_valid, k_valid,
                                                dW, ldw, dbias, m_per);
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }

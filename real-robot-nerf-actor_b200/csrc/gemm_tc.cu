@@ -518,8 +518,10 @@ static int launch_fwd(const NrfGemm& g, cudaStream_t stream) {
   int m_tiles = (g.M + kTileM - 1) / kTileM, n_tiles = g.N / BN;
   int tiles = m_tiles * n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
+  { LaunchScope ls_(NRF_CAT_GEMM, stream);
   gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmem, stream>>>(tmA1, tmA2, tmB, g.M, g.N, g.K1, g.K2,
                                                              make_epilogue<__nv_bfloat16>(g));
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
@@ -562,8 +564,10 @@ static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, i
   int m_per = ((M + splits - 1) / splits + kTileK - 1) / kTileK * kTileK;
   splits = (M + m_per - 1) / m_per;
   dim3 grid(out_tiles, splits);
+  { LaunchScope ls_(NRF_CAT_WGRAD, stream);
   wgrad_tc_kernel<BK_><<<grid, kThreads, Cfg::kSmem, stream>>>(tmG, tmA, M, k_tiles, m_per, n_valid, k_valid,
                                                                dW, ldw);
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
@@ -580,8 +584,10 @@ int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N
   if (dbias) {
     int rows_per_block = 2048;
     dim3 grid((n_valid + 63) / 64, (M + rows_per_block - 1) / rows_per_block);
+    { LaunchScope ls_(NRF_CAT_COLSUM, stream);
     colsum_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(G), ldg, M, n_valid,
                                                  dbias, rows_per_block);
+    }
     NRF_LAUNCH_OK();
   }
   return NRF_OK;

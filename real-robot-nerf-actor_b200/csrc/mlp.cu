@@ -114,7 +114,9 @@ static int pack(void* base, int64_t off, int ld_dst, int rows, int cols, const f
   if (!src) return NRF_OK;
   T* dst = reinterpret_cast<T*>(reinterpret_cast<char*>(base) + off) + col0;
   int64_t n = (int64_t)rows * cols;
+  { LaunchScope ls_(NRF_CAT_MISC, s);
   pack_matrix_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, ld_dst, rows, cols, src, ld_src, transpose);
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
@@ -129,21 +131,27 @@ static int pack_all(const NrfMlpParams* p, const MlpLayout& L, void* packed, cud
   // W0 = [W_z0 | W_in | 0]
   if (L.nz > 0) TRY(pack<T>(packed, L.W0, L.kin_pad, L.H, L.C, p->lin_z_w[0], L.C, 0, 0, s));
   TRY(pack<T>(packed, L.W0, L.kin_pad, L.H, L.Din, p->lin_in_w, L.Din, 0, L.C, s));
+  { LaunchScope ls_(NRF_CAT_MISC, s);
   add_bias_kernel<<<(L.H + 255) / 256, 256, 0, s>>>(f32(L.bias0), p->lin_in_b, L.nz > 0 ? p->lin_z_b[0] : nullptr, L.H);
+  }
   NRF_LAUNCH_OK();
   for (int b = 0; b < L.nb; ++b) {
     TRY(pack<T>(packed, L.Wfc0[b], L.H, L.H, L.H, p->fc0_w[b], L.H, 0, 0, s));
     TRY(pack<T>(packed, L.Wfc1[b], L.k1cat[b], L.H, L.H, p->fc1_w[b], L.H, 0, 0, s));
     bool cat = b + 1 < L.nz;
     if (cat) TRY(pack<T>(packed, L.Wfc1[b], L.k1cat[b], L.H, L.C, p->lin_z_w[b + 1], L.C, 0, L.H, s));
+    { LaunchScope ls_(NRF_CAT_MISC, s);
     add_bias_kernel<<<(L.H + 255) / 256, 256, 0, s>>>(f32(L.bias1[b]), p->fc1_b[b], cat ? p->lin_z_b[b + 1] : nullptr, L.H);
+    }
     NRF_LAUNCH_OK();
     TRY(pack<T>(packed, L.Wfc0T[b], L.H, L.H, L.H, p->fc0_w[b], L.H, 1, 0, s));
     TRY(pack<T>(packed, L.Wfc1T[b], L.H, L.H, L.H, p->fc1_w[b], L.H, 1, 0, s));
   }
   for (int b = 0; b < L.nz; ++b) TRY(pack<T>(packed, L.WzT[b], L.H, L.C, L.H, p->lin_z_w[b], L.C, 1, 0, s));
   TRY(pack<T>(packed, L.Wout, L.H, L.Dout, L.H, p->lin_out_w, L.H, 0, 0, s));
+  { LaunchScope ls_(NRF_CAT_MISC, s);
   add_bias_kernel<<<(L.Dout + 255) / 256, 256, 0, s>>>(f32(L.bias_out), p->lin_out_b, nullptr, L.Dout);
+  }
   NRF_LAUNCH_OK();
   TRY(pack<T>(packed, L.WoutT, L.dout_pad, L.H, L.Dout, p->lin_out_w, L.H, 1, 0, s));
 #undef TRY
@@ -177,12 +185,24 @@ static int bias_grads(const void* G, int ldg, int64_t M, int n, float* tmp, floa
   int rows_per_block = 4096;
   dim3 grid((n + 63) / 64, (unsigned)((M + rows_per_block - 1) / rows_per_block));
   if (precision == NRF_PREC_BF16)
+    { LaunchScope ls_(NRF_CAT_COLSUM, s);
     colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(G), ldg, M, n, tmp, rows_per_block);
+    }
   else
+    { LaunchScope ls_(NRF_CAT_COLSUM, s);
     colsum_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(G), ldg, M, n, tmp, rows_per_block);
+    }
   NRF_LAUNCH_OK();
-  if (d1) { accumulate_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(d1, tmp, n); NRF_LAUNCH_OK(); }
-  if (d2) { accumulate_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(d2, tmp, n); NRF_LAUNCH_OK(); }
+  if (d1) {
+    { LaunchScope ls_(NRF_CAT_MISC, s);
+      accumulate_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(d1, tmp, n); }
+    NRF_LAUNCH_OK();
+  }
+  if (d2) {
+    { LaunchScope ls_(NRF_CAT_MISC, s);
+      accumulate_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(d2, tmp, n); }
+    NRF_LAUNCH_OK();
+  }
   return NRF_OK;
 }
 

@@ -171,8 +171,10 @@ extern "C" int nrf_raygen(const float* poses, int n_img, int W, int H, float fx,
   NRF_REQUIRE(poses && rays_out && n_img > 0 && W > 0 && H > 0, NRF_EINVAL, "nrf_raygen: bad args");
   int64_t total = (int64_t)n_img * H * W;
   int threads = 256;
+  { LaunchScope ls_(NRF_CAT_SAMPLING, as_stream(stream));
   raygen_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
       poses, n_img, W, H, fx, fy, cx, cy, z_near, z_far, rays_out);
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
@@ -182,8 +184,10 @@ extern "C" int nrf_sample_coarse(const float* rays, int R, int Kc, const float* 
   NRF_REQUIRE(rays && base && z_out && R > 0 && Kc > 0, NRF_EINVAL, "nrf_sample_coarse: bad args");
   int64_t total = (int64_t)R * Kc;
   int threads = 256;
+  { LaunchScope ls_(NRF_CAT_SAMPLING, as_stream(stream));
   sample_coarse_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
       rays, R, Kc, base, jitter, lindisp, z_out);
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
@@ -196,8 +200,10 @@ extern "C" int nrf_sample_fine(const float* rays, const float* weights, const fl
   NRF_REQUIRE(Kc <= 4096, NRF_ENOSUP, "nrf_sample_fine: Kc > 4096");
   int warps = 4;
   size_t smem = (size_t)warps * (Kc + 1) * sizeof(float);
+  { LaunchScope ls_(NRF_CAT_SAMPLING, as_stream(stream));
   sample_fine_kernel<<<(R + warps - 1) / warps, warps * kWarp, smem, as_stream(stream)>>>(
       rays, weights, cdf, R, Kc, u, jitter, Kf, lindisp, z_out, ldz, ind_out);
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
@@ -208,7 +214,9 @@ extern "C" int nrf_sort_rows(float* z, int R, int K, int32_t* perm_out, void* st
   int P = 2;
   while (P < K) P <<= 1;
   int threads = P / 2 < 32 ? 32 : (P / 2 > 512 ? 512 : P / 2);
+  { LaunchScope ls_(NRF_CAT_SAMPLING, as_stream(stream));
   sort_rows_kernel<<<R, threads, (size_t)P * 8, as_stream(stream)>>>(z, R, K, P, perm_out);
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }

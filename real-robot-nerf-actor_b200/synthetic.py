@@ -103,3 +103,18 @@ def make_noise(R, n_coarse, n_fine, seed=0, perturb=True):
 def pick_ray_indices(n_pixels, n, seed=0):
     g = torch.Generator().manual_seed(4000 + seed)
     return torch.randint(n_pixels, (n,), generator=g)
+
+
+def init_mlp_(mlp, seed=0):
+    """Reference init (resnetfc.py:38-41,92-98,126-128) from a seeded CPU generator, with
+    fc_1.weight ~ N(0, 2/d_hidden) instead of zeros so the residual blocks are not identities
+    (SURVEY.md 9.8).  In-place on a ResnetFC parameter container; returns it."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in mlp.named_parameters():
+            if name.endswith(".bias"):
+                p.zero_()
+            else:
+                fan_in = p.shape[1]
+                p.copy_((torch.randn(p.shape, generator=g) * math.sqrt(2.0 / fan_in)).to(p.device))
+    return mlp

@@ -143,7 +143,7 @@ def test_encode_points_fp32_matches_oracle(ops, C, S):
     assert (out[:, :C] - ref[:, :C]).abs().max() <= 1e-6
     assert lat_frac > 0.999
     assert torch.equal(out[:, C:C + 3], ref[:, C:C + 3])                 # canonical xyz: bit-exact
-    assert (out[:, C + 3:C + 39] - ref[:, C + 3:C + 39]).abs().max() <= 2e-6   # sin(): ulp-level
+    assert (out[:, C + 3:C + 39] - ref[:, C + 3:C + 39]).abs().max() <= 5e-7   # sin(): ulp-level
     assert torch.equal(out[:, C + 39:C + 42], ref[:, C + 39:C + 42])     # view direction
     assert (out[:, C + 42:] == 0).all()
     # bf16 operand mode is the fp32 row rounded to nearest-even
@@ -157,7 +157,7 @@ def test_encode_points_outside_box_and_edges(ops):
     g = torch.Generator().manual_seed(1)
     vol = torch.randn(1, C, S, S, S, generator=g)
     b = torch.tensor(syn.BOUNDS)
-    canon = torch.tensor([[0., 0., 0.], [1., 1., 1.], [0.5, 0.5, 0.5], [-0.01, 0.5, 0.5], [1.2, 0.3, 0.1],
+    canon = torch.tensor([[0., 0., 0.], [1., 1., 1.], [0.5, 0.5, 0.5], [-0.01, 0.5, 0.5], [1.3, 0.3, 0.1],
                           [0.25, 0.5, 0.75], [50., -50., 3.], [1.0, 0.0, 0.5]])
     world = canon * (b[3:] - b[:3]) + b[:3]
     n = world.shape[0]
