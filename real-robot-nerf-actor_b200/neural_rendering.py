@@ -295,9 +295,9 @@ class _ForwardNerfFn(torch.autograd.Function):
         ctx.vol_shape = tuple(vol_cl.shape)
         ctx.depth_mask = depth_mask
         ctx.n_params = len(params)
-        ctx.mark_non_differentiable(z_c)
-        if st_f is not None:
-            ctx.mark_non_differentiable(outs[5])
+        # one call only: a second mark_non_differentiable() would replace the first, give z_c a grad_fn
+        # pointing at this node while st_c.z holds it, and leak every activation through that cycle
+        ctx.mark_non_differentiable(*([z_c] + ([outs[5]] if st_f is not None else [])))
         if not any(ctx.needs_input_grad):
             st_c.acts = None
             if st_f is not None:
