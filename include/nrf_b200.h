@@ -105,22 +105,26 @@ int nrf_composite_bwd(const float* field_out, int ldo, const float* z, const flo
                       int out_bf16, float* d_z, void* stream);
 
 /* ---- GEMM building block of the field MLP ----------------------------------------------------
- * out = resid + mask( A . B^T + bias ),   A = [A1 | A2] along K,  B (N,K) row-major (nn.Linear)
- *   A1 (M,K1) lda1, A2 (M,K2) lda2 (K2 may be 0), operand type bf16 (NRF_PREC_BF16) or fp32
- *   bias (N) fp32 or NULL; mask_src (M,N) operand-typed or NULL: value zeroed where mask_src <= 0
- *   resid (M,N) fp32 or NULL (may alias out_f32)
- *   out_f32 (M,n_store) fp32 or NULL; out_act (M,n_store) operand-typed or NULL, relu'd if relu_act
- * Only columns < n_store are written.  bf16 mode: K1,K2 multiples of 64, N multiple of 128. */
+ * v = resid + mask( [A0 | A1 | A2] . B^T + bias ),   B (N,K) row-major (nn.Linear layout)
+ *   A[i] (M,K[i]) lda[i]: up to three operand matrices concatenated along K (K[i] = 0: unused)
+ *   operand type: bf16 (NRF_PREC_BF16) or fp32 (NRF_PREC_FP32); applies to A, B, mask_src, resid,
+ *   out_act and out_act2
+ *   bias (N) fp32 or NULL; mask_src (M,N) or NULL: v is zeroed where mask_src <= 0 (ReLU gate)
+ *   resid (M,N) or NULL (may alias out_act: the update is element-wise in place)
+ *   out_act / out_act2 (M,n_store) or NULL: v, ReLU'd when the matching relu flag is set
+ *   out_f32 (M,n_store) fp32 or NULL: v.  bf16 mode: out_f32 excludes mask/resid/out_act*.
+ * Only columns < n_store are written.  bf16 mode: every K[i] a multiple of 64, N a multiple of 128,
+ * all pointers 16 B aligned with 16 B-multiple row pitches. */
 typedef struct {
-  const void* A1; int K1; int lda1;
-  const void* A2; int K2; int lda2;
+  const void* A[3]; int K[3]; int lda[3];
   const void* B;  int ldb;
   int M; int N; int n_store;
   const float* bias;
   const void* mask_src; int ldmask;
-  const float* resid; int ldr;
-  float* out_f32; int ldo;
+  const void* resid; int ldr;
   void* out_act; int ldact; int relu_act;
+  void* out_act2; int ldact2; int relu_act2;
+  float* out_f32; int ldo;
 } NrfGemm;
 int nrf_gemm(const NrfGemm* g, int precision, void* stream);
 

@@ -19,15 +19,15 @@ c_ptr = C.c_void_p
 
 
 class NrfGemm(C.Structure):
-    _fields_ = [("A1", c_ptr), ("K1", C.c_int), ("lda1", C.c_int),
-                ("A2", c_ptr), ("K2", C.c_int), ("lda2", C.c_int),
+    _fields_ = [("A", c_ptr * 3), ("K", C.c_int * 3), ("lda", C.c_int * 3),
                 ("B", c_ptr), ("ldb", C.c_int),
                 ("M", C.c_int), ("N", C.c_int), ("n_store", C.c_int),
                 ("bias", c_ptr),
                 ("mask_src", c_ptr), ("ldmask", C.c_int),
                 ("resid", c_ptr), ("ldr", C.c_int),
-                ("out_f32", c_ptr), ("ldo", C.c_int),
-                ("out_act", c_ptr), ("ldact", C.c_int), ("relu_act", C.c_int)]
+                ("out_act", c_ptr), ("ldact", C.c_int), ("relu_act", C.c_int),
+                ("out_act2", c_ptr), ("ldact2", C.c_int), ("relu_act2", C.c_int),
+                ("out_f32", c_ptr), ("ldo", C.c_int)]
 
 
 _PA = c_ptr * NRF_MAX_BLOCKS

@@ -89,9 +89,9 @@ extern "C" const char* nrf_version(void) { return "nrf_b200 0.1 (sm_100a; tcgen0
 extern "C" const char* nrf_last_error(void) { return g_err; }
 
 extern "C" int nrf_gemm(const NrfGemm* g, int precision, void* stream) {
-  NRF_REQUIRE(g && g->A1 && g->B && g->M > 0 && g->N > 0 && g->K1 > 0 && g->K2 >= 0, NRF_EINVAL,
-              "nrf_gemm: bad arguments");
-  NRF_REQUIRE(g->K2 == 0 || g->A2, NRF_EINVAL, "nrf_gemm: K2 > 0 needs A2");
+  NRF_REQUIRE(g && g->A[0] && g->B && g->M > 0 && g->N > 0 && g->K[0] > 0 && g->K[1] >= 0 && g->K[2] >= 0,
+              NRF_EINVAL, "nrf_gemm: bad arguments");
+  NRF_REQUIRE((g->K[1] == 0 || g->A[1]) && (g->K[2] == 0 || g->A[2]), NRF_EINVAL, "nrf_gemm: K[i] > 0 needs A[i]");
   NRF_REQUIRE(g->n_store > 0 && g->n_store <= g->N, NRF_EINVAL, "nrf_gemm: n_store out of range");
   NRF_REQUIRE(g->out_f32 || g->out_act, NRF_EINVAL, "nrf_gemm: no output");
   if (precision == NRF_PREC_BF16) return gemm_tc_launch(*g, as_stream(stream));

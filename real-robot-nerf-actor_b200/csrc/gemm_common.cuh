@@ -1,6 +1,6 @@
 // Epilogue shared by the tcgen05 (bf16) and SIMT (fp32) GEMMs of the field MLP.
 //   v = acc + bias[n];  v = mask_src[m,n] > 0 ? v : 0;  v += resid[m,n];
-//   out_f32[m,n] = v;   out_act[m,n] = T(relu ? max(v,0) : v)
+//   out_act[m,n] = T(relu ? max(v,0) : v);  out_act2 likewise;  out_f32[m,n] = v
 // Forward layers use bias/resid/relu (resnetfc.py:57-64,172,183-191); the dgrad chain uses
 // mask_src (ReLU gate of the saved activation) and resid (gradient of the skip connection).
 #pragma once
@@ -12,9 +12,10 @@ template <typename T>
 struct Epilogue {
   const float* bias;
   const T* mask_src; int ldmask;
-  const float* resid; int ldr;
-  float* out_f32; int ldo;
+  const T* resid; int ldr;
   T* out_act; int ldact; int relu_act;
+  T* out_act2; int ldact2; int relu_act2;
+  float* out_f32; int ldo;
   int M, n_store;
 };
 
@@ -23,9 +24,10 @@ static inline Epilogue<T> make_epilogue(const NrfGemm& g) {
   Epilogue<T> e;
   e.bias = g.bias;
   e.mask_src = reinterpret_cast<const T*>(g.mask_src); e.ldmask = g.ldmask;
-  e.resid = g.resid; e.ldr = g.ldr;
-  e.out_f32 = g.out_f32; e.ldo = g.ldo;
+  e.resid = reinterpret_cast<const T*>(g.resid); e.ldr = g.ldr;
   e.out_act = reinterpret_cast<T*>(g.out_act); e.ldact = g.ldact; e.relu_act = g.relu_act;
+  e.out_act2 = reinterpret_cast<T*>(g.out_act2); e.ldact2 = g.ldact2; e.relu_act2 = g.relu_act2;
+  e.out_f32 = g.out_f32; e.ldo = g.ldo;
   e.M = g.M; e.n_store = g.n_store;
   return e;
 }

@@ -7,14 +7,18 @@ namespace nrf {
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
-// C = epilogue([A1|A2] . B^T).  256 threads, each a 4x4 micro-tile.
-__global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict__ A1, int K1, int lda1,
-                                                        const float* __restrict__ A2, int K2, int lda2,
-                                                        const float* __restrict__ B, int ldb, int N,
+struct SimtA {
+  const float* A[3];
+  int K[3];
+  int lda[3];
+};
+
+// C = epilogue([A0|A1|A2] . B^T).  256 threads, each a 4x4 micro-tile.
+__global__ void __launch_bounds__(256) gemm_simt_kernel(SimtA sa, const float* __restrict__ B, int ldb, int N,
                                                         Epilogue<float> ep) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
-  const int M = ep.M, K = K1 + K2;
+  const int M = ep.M, K01 = sa.K[0] + sa.K[1], K = K01 + sa.K[2];
   int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   int tid = threadIdx.x;
   int tx = tid % 16, ty = tid / 16;
@@ -28,7 +32,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
       int k = k0 + kk;
       float av = 0.f, bv = 0.f;
       int m = m0 + row;
-      if (m < M && k < K) av = k < K1 ? A1[(int64_t)m * lda1 + k] : A2[(int64_t)m * lda2 + (k - K1)];
+      if (m < M && k < K) {
+        if (k < sa.K[0]) av = sa.A[0][(int64_t)m * sa.lda[0] + k];
+        else if (k < K01) av = sa.A[1][(int64_t)m * sa.lda[1] + (k - sa.K[0])];
+        else av = sa.A[2][(int64_t)m * sa.lda[2] + (k - K01)];
+      }
       int n = n0 + row;
       if (n < N && k < K) bv = B[(int64_t)n * ldb + k];
       As[kk][row] = av;
@@ -61,8 +69,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
       if (ep.bias) v += ep.bias[n];
       if (ep.mask_src && !(ep.mask_src[(int64_t)m * ep.ldmask + n] > 0.0f)) v = 0.0f;
       if (ep.resid) v += ep.resid[(int64_t)m * ep.ldr + n];
-      if (ep.out_f32) ep.out_f32[(int64_t)m * ep.ldo + n] = v;
       if (ep.out_act) ep.out_act[(int64_t)m * ep.ldact + n] = ep.relu_act ? fmaxf(v, 0.0f) : v;
+      if (ep.out_act2) ep.out_act2[(int64_t)m * ep.ldact2 + n] = ep.relu_act2 ? fmaxf(v, 0.0f) : v;
+      if (ep.out_f32) ep.out_f32[(int64_t)m * ep.ldo + n] = v;
     }
   }
 }
@@ -137,12 +146,16 @@ int gemm_simt_launch(const NrfGemm& g, cudaStream_t stream) {
     if (e.resid) e.resid += m_off * e.ldr;
     if (e.out_f32) e.out_f32 += m_off * e.ldo;
     if (e.out_act) e.out_act += m_off * e.ldact;
-    const float* A1 = reinterpret_cast<const float*>(g.A1) + m_off * g.lda1;
-    const float* A2 = g.A2 ? reinterpret_cast<const float*>(g.A2) + m_off * g.lda2 : nullptr;
+    if (e.out_act2) e.out_act2 += m_off * e.ldact2;
+    SimtA sa;
+    for (int i = 0; i < 3; ++i) {
+      sa.K[i] = g.K[i];
+      sa.lda[i] = g.lda[i];
+      sa.A[i] = g.K[i] > 0 ? reinterpret_cast<const float*>(g.A[i]) + m_off * g.lda[i] : nullptr;
+    }
     dim3 gr((g.N + BN - 1) / BN, (unsigned)((rows + BM - 1) / BM));
     { LaunchScope ls_(NRF_CAT_SIMT, stream);
-    gemm_simt_kernel<<<gr, 256, 0, stream>>>(A1, g.K1, g.lda1, A2, g.K2, g.lda2,
-                                              reinterpret_cast<const float*>(g.B), g.ldb, g.N, e);
+    gemm_simt_kernel<<<gr, 256, 0, stream>>>(sa, reinterpret_cast<const float*>(g.B), g.ldb, g.N, e);
     }
     NRF_LAUNCH_OK();
   }

@@ -137,43 +137,81 @@ struct PipeState {
 };
 
 // ------------------------------------------------------------------------------- forward / dgrad
+// Epilogue I/O goes through TMA as well: the ReLU-gate and residual tiles are prefetched three
+// 32-column chunks ahead into 64B-swizzled shared-memory buffers, results are written to swizzled
+// staging buffers and leave through cp.async.bulk.tensor stores (coalesced, asynchronous, clipped to
+// the tensor bounds, so there are no row/column predicates anywhere in the kernel).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int BN>
 struct FwdCfg {
   static constexpr int kStageA = kTileM * kTileK * 2;          // 16 KB
   static constexpr int kStageB = BN * kTileK * 2;              // 32 KB (BN=256) / 16 KB (BN=128)
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kStages = BN == 256 ? 3 : 4;
+  static constexpr int kEpiBuf = kTileM * 64;                  // 128 rows x 64 B (32 bf16 columns)
+  static constexpr int kEpiBufs = 10;                          // outA[2] outB[2] mask[3] resid[3]
+  static constexpr int kInSlots = 3;
   static constexpr int kTmemCols = 2 * BN;                     // 2 accumulator stages
-  static constexpr int kSmem = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmem = kStages * kStage + kEpiBufs * kEpiBuf + 1024 /*align*/ + 512 /*barriers*/;
+};
+
+struct FwdArgs {
+  int M, N, n_store;
+  int kb[3];                 // 64-wide k-blocks per A source
+  const float* bias;
+  int has_mask, has_resid, has_outA, relu_a, has_outB, relu_b, f32_out;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, int M, int N, int K1, int K2,
-               Epilogue<__nv_bfloat16> ep) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmMask, const __grid_constant__ CUtensorMap tmResid,
+               const __grid_constant__ CUtensorMap tmOutA, const __grid_constant__ CUtensorMap tmOutB,
+               const __grid_constant__ CUtensorMap tmOutF, const FwdArgs a) {
   using Cfg = FwdCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
+  uint8_t* epi = smem + Cfg::kStages * Cfg::kStage;
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi + Cfg::kEpiBufs * Cfg::kEpiBuf);
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* acc_full = empty + Cfg::kStages;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* in_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + Cfg::kInSlots);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int m_tiles = (M + kTileM - 1) / kTileM, n_tiles = N / BN;
+  const int m_tiles = (a.M + kTileM - 1) / kTileM, n_tiles = a.N / BN;
   const int tiles = m_tiles * n_tiles;
-  const int kb1 = K1 / kTileK, num_kb = (K1 + K2) / kTileK;
+  const int kb01 = a.kb[0] + a.kb[1];
+  const int num_kb = kb01 + a.kb[2];
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA1);
-    if (K2 > 0) tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
+    if (a.kb[1] > 0) tma_prefetch_desc(&tmA1);
+    if (a.kb[2] > 0) tma_prefetch_desc(&tmA2);
+    if (a.has_mask) tma_prefetch_desc(&tmMask);
+    if (a.has_resid) tma_prefetch_desc(&tmResid);
+    if (a.has_outA) tma_prefetch_desc(&tmOutA);
+    if (a.has_outB) tma_prefetch_desc(&tmOutB);
+    if (a.f32_out) tma_prefetch_desc(&tmOutF);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+    for (int s = 0; s < Cfg::kInSlots; ++s) mbar_init(in_full + s, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -192,8 +230,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint8_t* sa = smem + st.stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
           mbar_expect_tx(full + st.stage, Cfg::kStage);
-          if (kb < kb1) tma_load_2d(sa, &tmA1, full + st.stage, kb * kTileK, m_blk * kTileM);
-          else          tma_load_2d(sa, &tmA2, full + st.stage, (kb - kb1) * kTileK, m_blk * kTileM);
+          if (kb < a.kb[0])    tma_load_2d(sa, &tmA0, full + st.stage, kb * kTileK, m_blk * kTileM);
+          else if (kb < kb01)  tma_load_2d(sa, &tmA1, full + st.stage, (kb - a.kb[0]) * kTileK, m_blk * kTileM);
+          else                 tma_load_2d(sa, &tmA2, full + st.stage, (kb - kb01) * kTileK, m_blk * kTileM);
           tma_load_2d(sb, &tmB, full + st.stage, kb * kTileK, n_blk * BN);
           st.advance(Cfg::kStages);
         }
@@ -229,90 +268,150 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     }
   } else if (warp >= kEpiWarp0) {
-    const int q = warp - kEpiWarp0;            // TMEM lane quarter this warp may read
+    const int q4 = warp - kEpiWarp0;                 // TMEM lane quarter this warp may read
+    const int row = q4 * 32 + lane;                  // row of the tile == TMEM lane
+    const bool leader = (row == 0);
+    const bool has_in = a.has_mask || a.has_resid;
+    const uint32_t in_bytes = (uint32_t)(a.has_mask + a.has_resid) * Cfg::kEpiBuf;
+    uint8_t* bufOutA = epi;                          // 2 x 8 KB (bf16) -- or 2 x 16 KB fp32 over outA+outB
+    uint8_t* bufOutB = epi + 2 * Cfg::kEpiBuf;
+    uint8_t* bufMask = epi + 4 * Cfg::kEpiBuf;       // 3 slots
+    uint8_t* bufResid = epi + 7 * Cfg::kEpiBuf;      // 3 slots
+    auto chunks_of = [&](int tile) {
+      int n_blk = tile % n_tiles;
+      int left = a.n_store - n_blk * BN;
+      int c = (left + 31) / 32;
+      return c < 0 ? 0 : (c > BN / 32 ? BN / 32 : c);
+    };
+    // prefetch cursor (leader only): runs kInSlots chunks ahead of the consumer
+    int pf_tile = blockIdx.x, pf_c = 0;
+    uint32_t pf_q = 0;
+    auto prefetch_one = [&]() {
+      while (pf_tile < tiles && pf_c >= chunks_of(pf_tile)) { pf_tile += gridDim.x; pf_c = 0; }
+      if (pf_tile >= tiles) return;
+      int slot = pf_q % Cfg::kInSlots;
+      int m0 = (pf_tile / n_tiles) * kTileM, n0 = (pf_tile % n_tiles) * BN + pf_c * 32;
+      mbar_expect_tx(in_full + slot, in_bytes);
+      if (a.has_mask) tma_load_2d(bufMask + slot * Cfg::kEpiBuf, &tmMask, in_full + slot, n0, m0);
+      if (a.has_resid) tma_load_2d(bufResid + slot * Cfg::kEpiBuf, &tmResid, in_full + slot, n0, m0);
+      ++pf_q;
+      ++pf_c;
+    };
+    if (leader && has_in)
+      for (int i = 0; i < Cfg::kInSlots; ++i) prefetch_one();
+
+    uint32_t q = 0;                                  // running chunk counter (all epilogue threads)
     int it = 0;
+    const uint32_t sw64 = (uint32_t)((row >> 1) & 3);   // 64B swizzle: 16 B chunk index ^= (row/2)%4
+    const uint32_t sw128 = (uint32_t)(row & 7);         // 128B swizzle: 16 B chunk index ^= row%8
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      int as = it & 1;
-      uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * kTileM, n_base = (tile % n_tiles) * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int nch = chunks_of(tile);
       mbar_wait(acc_full + as, aphase);
       tc_fence_after();
-      const int m = m_blk * kTileM + q * 32 + lane;
-      const bool row_ok = m < M;
-      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q4 * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= ep.n_store) break;             // warp-uniform
+      for (int c = 0; c < nch; ++c, ++q) {
+        const int n0 = n_base + c * 32;
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
-        if (!row_ok) continue;
+        if (c == nch - 1) {                          // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + as);
+        }
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-        if (ep.bias) {
+        if (a.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+            float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + j));
             x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
           }
         }
-        const bool full_chunk = n0 + 32 <= ep.n_store;
-        if (full_chunk) {
-          if (ep.mask_src) {
-            const uint4* mp = reinterpret_cast<const uint4*>(ep.mask_src + (int64_t)m * ep.ldmask + n0);
+        if (has_in) {
+          const int slot = q % Cfg::kInSlots;
+          mbar_wait(in_full + slot, (q / Cfg::kInSlots) & 1);
+          if (a.has_mask) {
+            const uint8_t* mrow = bufMask + slot * Cfg::kEpiBuf + row * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 mk = __ldg(mp + j);
+              uint4 mk = *reinterpret_cast<const uint4*>(mrow + ((j ^ sw64) << 4));
               const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&mk);
 #pragma unroll
               for (int t = 0; t < 8; ++t)
                 if (!(__bfloat162float(h[t]) > 0.0f)) x[j * 8 + t] = 0.0f;
             }
           }
-          if (ep.resid) {
-            const float4* rp = reinterpret_cast<const float4*>(ep.resid + (int64_t)m * ep.ldr + n0);
+          if (a.has_resid) {
+            const uint8_t* rrow = bufResid + slot * Cfg::kEpiBuf + row * 64;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 r = rp[j];
-              x[j * 4] += r.x; x[j * 4 + 1] += r.y; x[j * 4 + 2] += r.z; x[j * 4 + 3] += r.w;
+            for (int j = 0; j < 4; ++j) {
+              uint4 rk = *reinterpret_cast<const uint4*>(rrow + ((j ^ sw64) << 4));
+              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&rk);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) x[j * 8 + t] += __bfloat162float(h[t]);
             }
           }
-          if (ep.out_f32) {
-            float4* op = reinterpret_cast<float4*>(ep.out_f32 + (int64_t)m * ep.ldo + n0);
+        }
+        const int ob = q & 1;
+        if (a.f32_out) {
+          uint8_t* orow = epi + ob * (2 * Cfg::kEpiBuf) + row * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(x[j * 4], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]);
-          }
-          if (ep.out_act) {
-            uint4* ap = reinterpret_cast<uint4*>(ep.out_act + (int64_t)m * ep.ldact + n0);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(orow + ((j ^ sw128) << 4)) =
+                make_float4(x[j * 4], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]);
+        } else {
+          if (a.has_outA) {
+            uint8_t* orow = bufOutA + ob * Cfg::kEpiBuf + row * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t w[4];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                float a = x[j * 8 + 2 * t], b = x[j * 8 + 2 * t + 1];
-                if (ep.relu_act) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-                __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                float p = x[j * 8 + 2 * t], r = x[j * 8 + 2 * t + 1];
+                if (a.relu_a) { p = fmaxf(p, 0.0f); r = fmaxf(r, 0.0f); }
+                __nv_bfloat162 h = __floats2bfloat162_rn(p, r);
                 w[t] = *reinterpret_cast<uint32_t*>(&h);
               }
-              ap[j] = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(orow + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
-        } else {
-          for (int j = 0; j < 32 && n0 + j < ep.n_store; ++j) {
-            float val = x[j];
-            if (ep.mask_src && !(__bfloat162float(ep.mask_src[(int64_t)m * ep.ldmask + n0 + j]) > 0.0f)) val = 0.0f;
-            if (ep.resid) val += ep.resid[(int64_t)m * ep.ldr + n0 + j];
-            if (ep.out_f32) ep.out_f32[(int64_t)m * ep.ldo + n0 + j] = val;
-            if (ep.out_act)
-              ep.out_act[(int64_t)m * ep.ldact + n0 + j] = __float2bfloat16_rn(ep.relu_act ? fmaxf(val, 0.0f) : val);
+          if (a.has_outB) {
+            uint8_t* orow = bufOutB + ob * Cfg::kEpiBuf + row * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float p = x[j * 8 + 2 * t], r = x[j * 8 + 2 * t + 1];
+                if (a.relu_b) { p = fmaxf(p, 0.0f); r = fmaxf(r, 0.0f); }
+                __nv_bfloat162 h = __floats2bfloat162_rn(p, r);
+                w[t] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(orow + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
           }
         }
+        fence_proxy_async();                 // staging writes -> visible to the TMA (async proxy)
+        if (leader) bulk_wait_read0();       // stores of the previous chunk have drained the other buffer
+        epi_barrier();
+        if (leader) {
+          if (a.f32_out) {
+            tma_store_2d(&tmOutF, epi + ob * (2 * Cfg::kEpiBuf), n0, m0);
+          } else {
+            if (a.has_outA) tma_store_2d(&tmOutA, bufOutA + ob * Cfg::kEpiBuf, n0, m0);
+            if (a.has_outB) tma_store_2d(&tmOutB, bufOutB + ob * Cfg::kEpiBuf, n0, m0);
+          }
+          bulk_commit();
+          if (has_in) prefetch_one();        // every thread is past its reads of slot q % kInSlots
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + as);
     }
+    if (leader) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -321,6 +420,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
+
 
 // ------------------------------------------------------------------------------------- wgrad
 // dW[n,k] += sum_m G[m,n] A[m,k].  UMMA A-operand = G^T tile (128 n x 64 m), B-operand = A^T tile
@@ -475,41 +575,72 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: `cols` contiguous elements per row, `rows` rows `ld` elements apart;
-// box = box_cols x box_rows, 128 B swizzle, out-of-bounds elements read as zero.
-static int make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
-                    uint32_t box_cols, uint32_t box_rows) {
+// 2-D tensor map: `cols` contiguous elements per row, `rows` rows `ld` elements apart; box =
+// box_cols x box_rows; out-of-bounds elements read as zero / are not written.
+static int make_map_ex(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
+                       uint32_t box_cols, uint32_t box_rows, CUtensorMapDataType dt, int esize,
+                       CUtensorMapSwizzle sw) {
   EncodeTiledFn fn = encode_tiled_fn();
   NRF_REQUIRE(fn != nullptr, NRF_ECUDA, "cuTensorMapEncodeTiled entry point not found");
-  NRF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, NRF_EINVAL,
+  NRF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * esize) % 16 == 0, NRF_EINVAL,
               "TMA operand must be 16 B aligned with a 16 B-multiple row pitch (ld=%llu)",
               (unsigned long long)ld);
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
+  cuuint64_t gstride[1] = {ld * (uint64_t)esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NRF_REQUIRE(r == CUDA_SUCCESS, NRF_ECUDA, "cuTensorMapEncodeTiled failed (%d): cols=%llu rows=%llu ld=%llu",
               (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld);
   return NRF_OK;
 }
 
+// bf16 operand tile map, 128 B swizzle (the UMMA canonical layouts).
+static int make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
+                    uint32_t box_cols, uint32_t box_rows) {
+  return make_map_ex(map, base, cols, rows, ld, box_cols, box_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 template <int BN>
 static int launch_fwd(const NrfGemm& g, cudaStream_t stream) {
   using Cfg = FwdCfg<BN>;
-  CUtensorMap tmA1, tmA2, tmB;
-  int rc = make_map(&tmA1, g.A1, g.K1, g.M, g.lda1, kTileK, kTileM);
-  if (rc) return rc;
-  if (g.K2 > 0) {
-    rc = make_map(&tmA2, g.A2, g.K2, g.M, g.lda2, kTileK, kTileM);
-    if (rc) return rc;
-  } else {
-    tmA2 = tmA1;
+  CUtensorMap tmA[3], tmB, tmMask, tmResid, tmOutA, tmOutB, tmOutF;
+  int rc = 0;
+  int ktot = 0;
+  for (int i = 0; i < 3; ++i) {
+    if (g.K[i] > 0) {
+      rc = make_map(&tmA[i], g.A[i], g.K[i], g.M, g.lda[i], kTileK, kTileM);
+      if (rc) return rc;
+    } else {
+      tmA[i] = tmA[0];
+    }
+    ktot += g.K[i];
   }
-  rc = make_map(&tmB, g.B, g.K1 + g.K2, g.N, g.ldb, kTileK, BN);
+  rc = make_map(&tmB, g.B, ktot, g.N, g.ldb, kTileK, BN);
   if (rc) return rc;
+  // epilogue tiles: 32 bf16 columns (64 B rows, 64 B swizzle) or 32 fp32 columns (128 B rows, 128 B swizzle)
+  auto epi_map = [&](CUtensorMap* m, const void* ptr, int ld) {
+    return make_map_ex(m, ptr, g.n_store, g.M, ld, 32, kTileM, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                       CU_TENSOR_MAP_SWIZZLE_64B);
+  };
+  tmMask = tmResid = tmOutA = tmOutB = tmOutF = tmB;
+  if (g.mask_src && (rc = epi_map(&tmMask, g.mask_src, g.ldmask))) return rc;
+  if (g.resid && (rc = epi_map(&tmResid, g.resid, g.ldr))) return rc;
+  if (g.out_act && (rc = epi_map(&tmOutA, g.out_act, g.ldact))) return rc;
+  if (g.out_act2 && (rc = epi_map(&tmOutB, g.out_act2, g.ldact2))) return rc;
+  if (g.out_f32 && (rc = make_map_ex(&tmOutF, g.out_f32, g.n_store, g.M, g.ldo, 32, kTileM,
+                                     CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  FwdArgs a;
+  a.M = g.M; a.N = g.N; a.n_store = g.n_store;
+  for (int i = 0; i < 3; ++i) a.kb[i] = g.K[i] / kTileK;
+  a.bias = g.bias;
+  a.has_mask = g.mask_src != nullptr; a.has_resid = g.resid != nullptr;
+  a.has_outA = g.out_act != nullptr; a.relu_a = g.relu_act;
+  a.has_outB = g.out_act2 != nullptr; a.relu_b = g.relu_act2;
+  a.f32_out = g.out_f32 != nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     NRF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
@@ -519,24 +650,25 @@ static int launch_fwd(const NrfGemm& g, cudaStream_t stream) {
   int tiles = m_tiles * n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
   { LaunchScope ls_(NRF_CAT_GEMM, stream);
-  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmem, stream>>>(tmA1, tmA2, tmB, g.M, g.N, g.K1, g.K2,
-                                                             make_epilogue<__nv_bfloat16>(g));
+  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmem, stream>>>(tmA[0], tmA[1], tmA[2], tmB, tmMask, tmResid, tmOutA,
+                                                             tmOutB, tmOutF, a);
   }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
 
 int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream) {
-  NRF_REQUIRE(g.K1 > 0 && g.K1 % kTileK == 0 && g.K2 % kTileK == 0, NRF_ENOSUP,
-              "gemm_tc: K1=%d, K2=%d must be multiples of 64", g.K1, g.K2);
+  NRF_REQUIRE(g.K[0] > 0 && g.K[0] % kTileK == 0 && g.K[1] % kTileK == 0 && g.K[2] % kTileK == 0, NRF_ENOSUP,
+              "gemm_tc: K = %d,%d,%d must be multiples of 64", g.K[0], g.K[1], g.K[2]);
+  NRF_REQUIRE(g.K[2] == 0 || g.K[1] > 0, NRF_EINVAL, "gemm_tc: A[2] needs A[1]");
   NRF_REQUIRE(g.N % 128 == 0, NRF_ENOSUP, "gemm_tc: N=%d must be a multiple of 128", g.N);
-  NRF_REQUIRE((!g.out_f32 || g.ldo % 4 == 0) && (!g.out_act || g.ldact % 8 == 0) &&
-                  (!g.mask_src || g.ldmask % 8 == 0) && (!g.resid || g.ldr % 4 == 0),
-              NRF_EINVAL, "gemm_tc: epilogue leading dimensions must keep 16 B alignment");
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  NRF_REQUIRE(al16(g.bias) && al16(g.mask_src) && al16(g.resid) && al16(g.out_f32) && al16(g.out_act),
-              NRF_EINVAL, "gemm_tc: epilogue pointers must be 16 B aligned");
-  if (g.N % 256 == 0) return launch_fwd<256>(g, stream);
+  NRF_REQUIRE(!g.out_f32 || (!g.mask_src && !g.resid && !g.out_act && !g.out_act2), NRF_ENOSUP,
+              "gemm_tc: out_f32 excludes mask_src / resid / out_act* in bf16 mode");
+  NRF_REQUIRE(g.out_act || !g.out_act2, NRF_EINVAL, "gemm_tc: out_act2 without out_act");
+  NRF_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, NRF_EINVAL, "gemm_tc: bias must be 16 B aligned");
+  const int BN = g.N % 256 == 0 ? 256 : 128;
+  NRF_REQUIRE(g.N - g.n_store < BN, NRF_EINVAL, "gemm_tc: N=%d over-padded for n_store=%d", g.N, g.n_store);
+  if (BN == 256) return launch_fwd<256>(g, stream);
   return launch_fwd<128>(g, stream);
 }
 

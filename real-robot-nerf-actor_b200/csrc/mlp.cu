@@ -8,7 +8,13 @@
 // i.e. "x = x + lin_z[b](z)" (resnetfc.py:182-188) is folded into the preceding GEMM by
 // concatenating along K; combine_interleaved (utils.py:509-519) is the identity here.
 // Every GEMM writes the next layer's operand (ReLU'd, operand-typed) from its epilogue, so the
-// forward leaves exactly the tensors the backward needs: relu(x'_b) and relu(net_b).
+// forward leaves exactly the tensors the backward needs: relu(x'_b) and relu(net_b).  The residual
+// stream x' itself lives in ONE operand-typed buffer updated in place (bf16 in the tensor-core mode:
+// SURVEY.md section 10 measured no error on top of bf16 operands; fp32 in the parity mode).
+// Backward, per block (g = dL/dx_{b+1}, one buffer updated in place):
+//   dW_fc1 += g^T relu(net_b);  dnet = (g . W_fc1) gated by net_b > 0;  dW_fc0 += dnet^T relu(x'_b)
+//   g <- g + (dnet . W_fc0) gated by x'_b > 0        (kept per block b < n_lin_z for dL/dz)
+//   dL/dz = [g'_0 | g'_1 | g'_2] . [W_z0 ; W_z1 ; W_z2]                       one GEMM, K = 3 H
 #include <string.h>
 #include "gemm_common.cuh"
 
@@ -23,7 +29,7 @@ struct MlpLayout {
   // byte offsets into the packed buffer
   int64_t W0, bias0, Wout, bias_out, WoutT;
   int64_t Wfc0[NRF_MAX_BLOCKS], Wfc1[NRF_MAX_BLOCKS], bias1[NRF_MAX_BLOCKS];
-  int64_t Wfc0T[NRF_MAX_BLOCKS], Wfc1T[NRF_MAX_BLOCKS], WzT[NRF_MAX_BLOCKS];
+  int64_t Wfc0T[NRF_MAX_BLOCKS], Wfc1T[NRF_MAX_BLOCKS], WzcatT;
   int k1cat[NRF_MAX_BLOCKS];  // K of the concatenated fc_1 weight
   int64_t total;
 };
@@ -45,6 +51,7 @@ static int make_layout(const NrfMlpParams* p, int precision, MlpLayout* L) {
     NRF_REQUIRE(L->C % 64 == 0 && L->C > 0, NRF_ENOSUP,
                 "mlp(bf16): d_latent=%d must be a multiple of 64", L->C);
     NRF_REQUIRE(L->Dout % 4 == 0, NRF_ENOSUP, "mlp(bf16): d_out=%d must be a multiple of 4", L->Dout);
+    NRF_REQUIRE(L->nz <= 3, NRF_ENOSUP, "mlp(bf16): n_lin_z=%d > 3", L->nz);
   }
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t o = off; off = round_up(off + bytes, 1024); return o; };
@@ -58,7 +65,7 @@ static int make_layout(const NrfMlpParams* p, int precision, MlpLayout* L) {
     L->Wfc0T[b] = take((int64_t)L->H * L->H * L->es);
     L->Wfc1T[b] = take((int64_t)L->H * L->H * L->es);
   }
-  for (int b = 0; b < L->nz; ++b) L->WzT[b] = take((int64_t)round_up(L->C, 128) * L->H * L->es);
+  L->WzcatT = take((int64_t)round_up(L->C > 0 ? L->C : 1, 128) * (L->nz > 0 ? L->nz : 1) * L->H * L->es);
   L->Wout = take((int64_t)L->nout_pad * L->H * L->es);
   L->bias_out = take((int64_t)L->nout_pad * 4);
   L->WoutT = take((int64_t)L->H * L->dout_pad * L->es);
@@ -147,7 +154,7 @@ static int pack_all(const NrfMlpParams* p, const MlpLayout& L, void* packed, cud
     TRY(pack<T>(packed, L.Wfc0T[b], L.H, L.H, L.H, p->fc0_w[b], L.H, 1, 0, s));
     TRY(pack<T>(packed, L.Wfc1T[b], L.H, L.H, L.H, p->fc1_w[b], L.H, 1, 0, s));
   }
-  for (int b = 0; b < L.nz; ++b) TRY(pack<T>(packed, L.WzT[b], L.H, L.C, L.H, p->lin_z_w[b], L.C, 1, 0, s));
+  for (int b = 0; b < L.nz; ++b) TRY(pack<T>(packed, L.WzcatT, L.nz * L.H, L.C, L.H, p->lin_z_w[b], L.C, 1, b * L.H, s));
   TRY(pack<T>(packed, L.Wout, L.H, L.Dout, L.H, p->lin_out_w, L.H, 0, 0, s));
   { LaunchScope ls_(NRF_CAT_MISC, s);
   add_bias_kernel<<<(L.Dout + 255) / 256, 256, 0, s>>>(f32(L.bias_out), p->lin_out_b, nullptr, L.Dout);
@@ -163,6 +170,9 @@ static inline NrfGemm gemm_init(int64_t M, int N, int n_store) {
   memset(&g, 0, sizeof(g));
   g.M = (int)M; g.N = N; g.n_store = n_store;
   return g;
+}
+static inline void set_a(NrfGemm& g, int i, const void* A, int K, int lda) {
+  g.A[i] = A; g.K[i] = K; g.lda[i] = lda;
 }
 
 static int run_gemm(const NrfGemm& g, int precision, cudaStream_t s) {
@@ -218,8 +228,8 @@ extern "C" int nrf_mlp_sizes(const NrfMlpParams* p, int precision, NrfMlpSizes* 
   out->kin_pad = L.kin_pad;
   out->dout_pad = L.dout_pad;
   out->packed_bytes = L.total;
-  out->fwd_bytes_per_sample = (int64_t)(2 * L.nb + 1) * L.H * L.es + (int64_t)L.H * 4;
-  out->bwd_bytes_per_sample = (int64_t)3 * L.H * L.es + (int64_t)L.H * 4;
+  out->fwd_bytes_per_sample = (int64_t)(2 * L.nb + 2) * L.H * L.es;
+  out->bwd_bytes_per_sample = (int64_t)(2 + L.nz) * L.H * L.es;
   out->bwd_fixed_bytes = (int64_t)round_up((L.H > L.dout_pad ? L.H : L.dout_pad) * 4, 1024);
   return NRF_OK;
 }
@@ -246,37 +256,41 @@ extern "C" int nrf_mlp_fwd(const NrfMlpParams* p, const void* packed, int precis
   const int64_t layer = N * L.H * (int64_t)L.es;
   auto ax = [&](int b) { return act + (int64_t)b * layer; };                 // relu(x'_b), b = 0..nb
   auto an = [&](int b) { return act + (int64_t)(L.nb + 1 + b) * layer; };    // relu(net_b), b = 0..nb-1
-  float* xres = reinterpret_cast<float*>(act + (int64_t)(2 * L.nb + 1) * layer);
+  char* xcur = act + (int64_t)(2 * L.nb + 1) * layer;                        // residual stream x'
 
   NrfGemm g = gemm_init(N, L.H, L.H);
-  g.A1 = field_in; g.K1 = L.kin_pad; g.lda1 = L.kin_pad;
+  set_a(g, 0, field_in, L.kin_pad, L.kin_pad);
   g.B = W + L.W0; g.ldb = L.kin_pad;
   g.bias = reinterpret_cast<const float*>(W + L.bias0);
-  g.out_f32 = xres; g.ldo = L.H;
-  g.out_act = ax(0); g.ldact = L.H; g.relu_act = 1;
+  g.out_act = xcur; g.ldact = L.H;
+  g.out_act2 = ax(0); g.ldact2 = L.H; g.relu_act2 = 1;
   rc = run_gemm(g, precision, s);
   if (rc) return rc;
   for (int b = 0; b < L.nb; ++b) {
     g = gemm_init(N, L.H, L.H);
-    g.A1 = ax(b); g.K1 = L.H; g.lda1 = L.H;
+    set_a(g, 0, ax(b), L.H, L.H);
     g.B = W + L.Wfc0[b]; g.ldb = L.H;
     g.bias = p->fc0_b[b];
     g.out_act = an(b); g.ldact = L.H; g.relu_act = 1;
     rc = run_gemm(g, precision, s);
     if (rc) return rc;
     g = gemm_init(N, L.H, L.H);
-    g.A1 = an(b); g.K1 = L.H; g.lda1 = L.H;
-    if (b + 1 < L.nz) { g.A2 = field_in; g.K2 = L.C; g.lda2 = L.kin_pad; }
+    set_a(g, 0, an(b), L.H, L.H);
+    if (b + 1 < L.nz) set_a(g, 1, field_in, L.C, L.kin_pad);
     g.B = W + L.Wfc1[b]; g.ldb = L.k1cat[b];
     g.bias = reinterpret_cast<const float*>(W + L.bias1[b]);
-    g.resid = xres; g.ldr = L.H;
-    if (b + 1 < L.nb) { g.out_f32 = xres; g.ldo = L.H; }
-    g.out_act = ax(b + 1); g.ldact = L.H; g.relu_act = 1;
+    g.resid = xcur; g.ldr = L.H;
+    if (b + 1 < L.nb) {
+      g.out_act = xcur; g.ldact = L.H;                       // x' updated in place
+      g.out_act2 = ax(b + 1); g.ldact2 = L.H; g.relu_act2 = 1;
+    } else {
+      g.out_act = ax(b + 1); g.ldact = L.H; g.relu_act = 1;  // only relu(x_nb) is needed after the last block
+    }
     rc = run_gemm(g, precision, s);
     if (rc) return rc;
   }
   g = gemm_init(N, L.nout_pad, L.Dout);
-  g.A1 = ax(L.nb); g.K1 = L.H; g.lda1 = L.H;
+  set_a(g, 0, ax(L.nb), L.H, L.H);
   g.B = W + L.Wout; g.ldb = L.H;
   g.bias = reinterpret_cast<const float*>(W + L.bias_out);
   g.out_f32 = field_out; g.ldo = L.Dout;
@@ -303,25 +317,23 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
   char* sc = reinterpret_cast<char*>(scratch);
   float* tmp = reinterpret_cast<float*>(sc);
   int64_t fixed = round_up((L.H > L.dout_pad ? L.H : L.dout_pad) * 4, 1024);
-  float* gx = reinterpret_cast<float*>(sc + fixed);
-  char* gxa[2] = {sc + fixed + N * L.H * 4, sc + fixed + N * L.H * 4 + layer};
-  char* dnet = sc + fixed + N * L.H * 4 + 2 * layer;
-  int cur = 0;
+  char* gbuf = sc + fixed;                    // dL/dx, updated in place while b >= n_lin_z
+  char* dnet = gbuf + layer;
+  auto gz = [&](int b) { return dnet + (int64_t)(1 + b) * layer; };   // dL/dx'_b kept for dL/dz, b < n_lin_z
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
 
   // lin_out: parameter gradients, then the gradient of x_nb (ReLU-gated by relu(x_nb) > 0)
   TRY(run_wgrad(d_field, L.dout_pad, ax(L.nb), L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H, precision, s));
   TRY(bias_grads(d_field, L.dout_pad, N, L.Dout, tmp, gr->lin_out_b, nullptr, precision, s));
   NrfGemm g = gemm_init(N, L.H, L.H);
-  g.A1 = d_field; g.K1 = L.dout_pad; g.lda1 = L.dout_pad;
+  set_a(g, 0, d_field, L.dout_pad, L.dout_pad);
   g.B = W + L.WoutT; g.ldb = L.dout_pad;
   g.mask_src = ax(L.nb); g.ldmask = L.H;
-  g.out_f32 = gx; g.ldo = L.H;
-  g.out_act = gxa[cur]; g.ldact = L.H;
+  g.out_act = gbuf; g.ldact = L.H;
   TRY(run_gemm(g, precision, s));
 
+  const char* gcur = gbuf;                    // dL/dx_{b+1}
   for (int b = L.nb - 1; b >= 0; --b) {
-    const char* gcur = gxa[cur];             // dL/dx_{b+1}
     bool cat = b + 1 < L.nz;
     TRY(run_wgrad(gcur, L.H, an(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc1_w[b], L.H, precision, s));
     if (cat)
@@ -329,7 +341,7 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
     TRY(bias_grads(gcur, L.H, N, L.H, tmp, gr->fc1_b[b], cat ? gr->lin_z_b[b + 1] : nullptr, precision, s));
     // dnet_b = (g . W_fc1[b]) gated by relu(net_b) > 0
     g = gemm_init(N, L.H, L.H);
-    g.A1 = gcur; g.K1 = L.H; g.lda1 = L.H;
+    set_a(g, 0, gcur, L.H, L.H);
     g.B = W + L.Wfc1T[b]; g.ldb = L.H;
     g.mask_src = an(b); g.ldmask = L.H;
     g.out_act = dnet; g.ldact = L.H;
@@ -337,33 +349,36 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
     TRY(run_wgrad(dnet, L.H, ax(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc0_w[b], L.H, precision, s));
     TRY(bias_grads(dnet, L.H, N, L.H, tmp, gr->fc0_b[b], nullptr, precision, s));
     // dL/dx'_b = dL/dx_{b+1} + (dnet_b . W_fc0[b]) gated by relu(x'_b) > 0
+    char* target = b < L.nz ? gz(b) : gbuf;
     g = gemm_init(N, L.H, L.H);
-    g.A1 = dnet; g.K1 = L.H; g.lda1 = L.H;
+    set_a(g, 0, dnet, L.H, L.H);
     g.B = W + L.Wfc0T[b]; g.ldb = L.H;
     g.mask_src = ax(b); g.ldmask = L.H;
-    g.resid = gx; g.ldr = L.H;
-    g.out_f32 = gx; g.ldo = L.H;
-    g.out_act = gxa[cur ^ 1]; g.ldact = L.H;
+    g.resid = gcur; g.ldr = L.H;
+    g.out_act = target; g.ldact = L.H;
     TRY(run_gemm(g, precision, s));
-    cur ^= 1;
-    if (b < L.nz) {
-      // dL/dz += dL/dx'_b . W_z[b]
-      int cpad = (int)round_up(L.C, 128);
+    gcur = target;
+  }
+  // dL/dz = [g'_0 | g'_1 | ...] . [W_z0 ; W_z1 ; ...]
+  if (L.nz > 0) {
+    int cpad = (int)round_up(L.C, 128);
+    if (precision == NRF_PREC_BF16 || L.nz <= 3) {
       g = gemm_init(N, precision == NRF_PREC_BF16 ? cpad : L.C, L.C);
-      g.A1 = gxa[cur]; g.K1 = L.H; g.lda1 = L.H;
-      g.B = W + L.WzT[b]; g.ldb = L.H;
-      if (b != L.nz - 1) { g.resid = dlatent; g.ldr = L.C; }
+      for (int b = 0; b < L.nz; ++b) set_a(g, b, gz(b), L.H, L.H);
+      g.B = W + L.WzcatT; g.ldb = L.nz * L.H;
       g.out_f32 = dlatent; g.ldo = L.C;
       TRY(run_gemm(g, precision, s));
+    } else {
+      set_error("nrf_mlp_bwd: n_lin_z=%d > 3 is not supported", L.nz);
+      return NRF_ENOSUP;
     }
   }
-  // first layer: x'_0 = [z | p] . [W_z0 | W_in]^T
-  const char* g0 = gxa[cur];
+  // first layer: x'_0 = [z | p] . [W_z0 | W_in]^T ; gcur = dL/dx'_0
   if (L.nz > 0)
-    TRY(run_wgrad(g0, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[0], L.C, precision, s));
-  TRY(run_wgrad(g0, L.H, fin + (int64_t)L.C * L.es, L.kin_pad, N, L.H, L.kin_pad - L.C, L.H, L.Din, gr->lin_in_w,
+    TRY(run_wgrad(gcur, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[0], L.C, precision, s));
+  TRY(run_wgrad(gcur, L.H, fin + (int64_t)L.C * L.es, L.kin_pad, N, L.H, L.kin_pad - L.C, L.H, L.Din, gr->lin_in_w,
                 L.Din, precision, s));
-  TRY(bias_grads(g0, L.H, N, L.H, tmp, gr->lin_in_b, L.nz > 0 ? gr->lin_z_b[0] : nullptr, precision, s));
+  TRY(bias_grads(gcur, L.H, N, L.H, tmp, gr->lin_in_b, L.nz > 0 ? gr->lin_z_b[0] : nullptr, precision, s));
 #undef TRY
   return NRF_OK;
 }

@@ -197,13 +197,13 @@ def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights
 
 
 # ------------------------------------------------------------------------------------- GEMMs
-def gemm(A1, B, *, A2=None, bias=None, mask_src=None, resid=None, out_f32=None, out_act=None,
-         relu_act=False, n_store=None, precision=NRF_PREC_BF16):
-    """out = resid + mask(A.B^T + bias); thin test hook over nrf_gemm."""
+def gemm(A1, B, *, A2=None, A3=None, bias=None, mask_src=None, resid=None, out_f32=None, out_act=None,
+         relu_act=False, out_act2=None, relu_act2=False, n_store=None, precision=NRF_PREC_BF16):
+    """v = resid + mask([A1|A2|A3].B^T + bias) -> out_act / out_act2 / out_f32; test hook over nrf_gemm."""
     g = _lib.NrfGemm()
-    g.A1, g.K1, g.lda1 = ptr(A1), A1.shape[1], A1.stride(0)
-    if A2 is not None:
-        g.A2, g.K2, g.lda2 = ptr(A2), A2.shape[1], A2.stride(0)
+    for i, A in enumerate((A1, A2, A3)):
+        if A is not None:
+            g.A[i], g.K[i], g.lda[i] = A.data_ptr(), A.shape[1], A.stride(0)
     g.B, g.ldb = ptr(B), B.stride(0)
     g.M, g.N = A1.shape[0], B.shape[0]
     g.n_store = n_store if n_store is not None else g.N
@@ -216,6 +216,8 @@ def gemm(A1, B, *, A2=None, bias=None, mask_src=None, resid=None, out_f32=None, 
         g.out_f32, g.ldo = ptr(out_f32), out_f32.stride(0)
     if out_act is not None:
         g.out_act, g.ldact, g.relu_act = ptr(out_act), out_act.stride(0), int(relu_act)
+    if out_act2 is not None:
+        g.out_act2, g.ldact2, g.relu_act2 = ptr(out_act2), out_act2.stride(0), int(relu_act2)
     check(_lib.load().nrf_gemm(C.byref(g), precision, stream_ptr()), "nrf_gemm")
 
 

@@ -27,8 +27,11 @@ def bench(name, fn, flops, bytes_):
     ms = a.elapsed_time(b) / 10
     print(f"{name:28s} {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TFLOP/s  {bytes_/ms/1e6:7.1f} GB/s", flush=True)
 
+xb = xres.to(torch.bfloat16)
+gb = torch.empty_like(xb)
 F = 2.0 * M * 512 * 512
 bench("fc_0 (bias, relu act out)", lambda: ops.gemm(A, W, bias=bias, out_act=act, relu_act=True), F, M * 2048)
 bench("plain f32 out", lambda: ops.gemm(A, W, out_f32=xres), F, M * 3072)
-bench("fc_1 (K=640, resid, 2 outs)", lambda: ops.gemm(A, Wc, A2=Z[:, :128], bias=bias, resid=xres, out_f32=xres, out_act=act, relu_act=True), F * 1.25, M * (1024 + 256 + 2048 + 2048 + 1024))
-bench("dgrad (mask, act out)", lambda: ops.gemm(A, W, mask_src=mask, out_act=act), F, M * 3072)
+bench("fc_1 (K=640, resid, 2 outs)", lambda: ops.gemm(A, Wc, A2=Z[:, :128], bias=bias, resid=xb, out_act=xb, out_act2=act, relu_act2=True), F * 1.25, M * (1024 + 256 + 1024 + 1024 + 1024))
+bench("dnet (mask, act out)", lambda: ops.gemm(A, W, mask_src=mask, out_act=act), F, M * 3072)
+bench("gx (mask, resid, act out)", lambda: ops.gemm(A, W, mask_src=mask, resid=xb, out_act=gb), F, M * 4096)

@@ -227,39 +227,45 @@ def _bf16r(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-@pytest.mark.parametrize("M,N,K1,K2", [(128, 256, 64, 0), (300, 512, 512, 0), (1000, 512, 512, 128),
-                                       (257, 128, 512, 0), (4096 + 77, 512, 192, 0), (130, 512, 448, 0)])
-def test_gemm_tc_against_fp32_matmul_of_bf16_operands(ops, M, N, K1, K2):
+@pytest.mark.parametrize("M,N,K1,K2,K3", [(128, 256, 64, 0, 0), (300, 512, 512, 0, 0), (1000, 512, 512, 128, 0),
+                                          (257, 128, 512, 512, 512), (4096 + 77, 512, 192, 0, 0),
+                                          (130, 512, 448, 0, 0), (148 * 128 * 3 + 5, 512, 512, 0, 0)])
+def test_gemm_tc_against_fp32_matmul_of_bf16_operands(ops, M, N, K1, K2, K3):
     g = torch.Generator().manual_seed(M + N + K1 + K2)
-    A1 = torch.randn(M, K1, generator=g).to(torch.bfloat16)
-    A2 = torch.randn(M, K2, generator=g).to(torch.bfloat16) if K2 else None
-    B = (torch.randn(N, K1 + K2, generator=g) / math.sqrt(K1 + K2)).to(torch.bfloat16)
+    K = K1 + K2 + K3
+    As = [torch.randn(M, k, generator=g).to(torch.bfloat16) for k in (K1, K2, K3) if k]
+    B = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
     bias = torch.randn(N, generator=g)
-    resid = torch.randn(M, N, generator=g)
+    resid = torch.randn(M, N, generator=g).to(torch.bfloat16)
     mask = torch.randn(M, N, generator=g).relu().to(torch.bfloat16)
-    A = A1.float() if A2 is None else torch.cat([A1.float(), A2.float()], 1)
-    acc = A @ B.float().t()
+    acc = torch.cat([a.float() for a in As], 1) @ B.float().t()
+    Ac = [a.cuda() for a in As] + [None, None]
+    kw = dict(A2=Ac[1], A3=Ac[2])
 
-    # plain
+    # plain fp32 output (the lin_out / dL/dz form)
     out = torch.empty(M, N, device="cuda")
-    ops.gemm(A1.cuda(), B.cuda(), A2=None if A2 is None else A2.cuda(), out_f32=out)
+    ops.gemm(Ac[0], B.cuda(), out_f32=out, **kw)
     assert rel(out, acc) < 2e-6, "accumulation must be fp32-grade"
-    # forward-style epilogue: bias + residual (in place) + relu'd bf16 copy
+    # forward-style epilogue: bias + residual updated in place + relu'd second copy
     xres = resid.clone().cuda()
     act = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(A1.cuda(), B.cuda(), A2=None if A2 is None else A2.cuda(), bias=bias.cuda(), resid=xres,
-             out_f32=xres, out_act=act, relu_act=True)
-    want = acc + bias + resid
-    assert rel(xres, want) < 2e-6
-    assert torch.equal(act.cpu(), xres.cpu().relu().to(torch.bfloat16))
-    # dgrad-style epilogue: ReLU gate from a saved activation + residual, bf16 copy without relu
-    out2 = torch.empty(M, N, device="cuda")
+    ops.gemm(Ac[0], B.cuda(), bias=bias.cuda(), resid=xres, out_act=xres, out_act2=act, relu_act2=True, **kw)
+    want = acc + bias + resid.float()
+    assert rel(xres.float(), want) < 3e-3                      # one bf16 rounding of the result
+    assert torch.equal(act.cpu(), xres.cpu().float().relu().to(torch.bfloat16)) or \
+        rel(act.float(), want.relu()) < 3e-3
+    assert (xres.cpu().float() - want).abs().max() <= want.abs().max() * 2 ** -8
+    # dgrad-style epilogue: ReLU gate from a saved activation + residual
     act2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(A1.cuda(), B.cuda(), A2=None if A2 is None else A2.cuda(), mask_src=mask.cuda(),
-             resid=resid.cuda(), out_f32=out2, out_act=act2)
-    want2 = torch.where(mask.float() > 0, acc, torch.zeros_like(acc)) + resid
-    assert rel(out2, want2) < 2e-6
-    assert torch.equal(act2.cpu(), out2.cpu().to(torch.bfloat16))
+    ops.gemm(Ac[0], B.cuda(), mask_src=mask.cuda(), resid=resid.cuda(), out_act=act2, **kw)
+    want2 = torch.where(mask.float() > 0, acc, torch.zeros_like(acc)) + resid.float()
+    assert rel(act2.float(), want2) < 3e-3
+    gated = (mask.float() <= 0)
+    assert torch.equal(act2.cpu()[gated], resid[gated])        # gated entries pass the residual through exactly
+    # relu'd single output (fc_0 form)
+    act3 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(Ac[0], B.cuda(), bias=bias.cuda(), out_act=act3, relu_act=True, **kw)
+    assert rel(act3.float(), (acc + bias).relu()) < 3e-3
 
 
 def test_gemm_tc_partial_store(ops):
@@ -304,11 +310,13 @@ def test_gemm_simt_fp32(ops, M, N, K1, K2):
     acc = (A.double() @ B.double().t()).float()
     out = torch.empty(M, N, device="cuda")
     act = torch.empty(M, N, device="cuda")
+    act2 = torch.empty(M, N, device="cuda")
     ops.gemm(A1.cuda(), B.cuda(), A2=None if A2 is None else A2.cuda(), bias=bias.cuda(), mask_src=mask.cuda(),
-             resid=resid.cuda(), out_f32=out, out_act=act, relu_act=True, precision=ops.NRF_PREC_FP32)
+             resid=resid.cuda(), out_f32=out, out_act=act, out_act2=act2, relu_act2=True,
+             precision=ops.NRF_PREC_FP32)
     want = torch.where(mask > 0, acc + bias, torch.zeros_like(acc)) + resid
-    assert rel(out, want) < 1e-6
-    assert rel(act, want.relu()) < 1e-6
+    assert rel(out, want) < 1e-6 and rel(act, want) < 1e-6
+    assert rel(act2, want.relu()) < 1e-6
     dW = torch.zeros(N, K1, device="cuda")
     db = torch.zeros(N, device="cuda")
     G = torch.randn(M, N, generator=g)
