@@ -9,7 +9,8 @@
 //                               tcgen05.commit releases smem stages / publishes the accumulator
 //   warp 2    TMEM allocator    2 accumulator stages so the epilogue of tile i overlaps the MMAs of i+1
 //   warps 4-7 epilogue          tcgen05.ld 32x32b (one TMEM lane = one output row per thread), fused
-//                               bias / ReLU-gate / residual / bf16 re-quantisation, direct global stores
+//                               bias / ReLU-gate / residual / bf16 re-quantisation; ReLU-gate and residual
+//                               tiles arrive by TMA (prefetched 3 chunks ahead), results leave by TMA store
 #include <cuda.h>
 #include <mutex>
 #include "gemm_common.cuh"
@@ -440,7 +441,8 @@ struct WgCfg {
 template <int BK_>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA, int M,
-                int k_tiles, int m_per_split, int n_valid, int k_valid, float* __restrict__ dW, int ldw) {
+                int k_tiles, int m_per_split, int n_valid, int k_valid, float* __restrict__ dW, int ldw,
+                float* __restrict__ dbias) {
   using Cfg = WgCfg<BK_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -454,10 +456,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   const int m_begin = blockIdx.y * m_per_split;
   const int m_end = min(M, m_begin + m_per_split);
   const int num_mb = (m_end - m_begin + kTileK - 1) / kTileK;
+  // bias gradient = column sums of G: the CTAs of the first k tile add them up from the G tiles that
+  // pass through shared memory anyway (the epilogue warps are idle during the main loop)
+  const bool do_bias = dbias != nullptr && k_blk == 0;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmA); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, do_bias ? 5 : 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -510,6 +515,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
     }
   } else if (warp >= kEpiWarp0) {
     const int q = warp - kEpiWarp0;
+    if (do_bias) {
+      const int col = q * 32 + lane;                       // column of the 128-wide G tile
+      const uint32_t slab = (uint32_t)(col >> 6) * (kTileK * 128);
+      const uint32_t cc = (uint32_t)(col & 63);
+      float bsum = 0.f;
+      PipeState st;
+      for (int mb = 0; mb < num_mb; ++mb) {
+        mbar_wait(full + st.stage, st.phase);
+        const uint8_t* sg = smem + st.stage * Cfg::kStage + slab;
+#pragma unroll 8
+        for (int m = 0; m < kTileK; ++m) {
+          uint32_t off = (uint32_t)m * 128 + ((((cc >> 3) ^ (uint32_t)(m & 7))) << 4) + (cc & 7) * 2;
+          bsum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sg + off));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st.stage);
+        st.advance(Cfg::kStages);
+      }
+      const int n = n_blk * kTileM + col;
+      if (n < n_valid && num_mb > 0) atomicAdd(dbias + n, bsum);
+    }
     if (num_mb > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -536,24 +562,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
-}
-
-// Column sums of a bf16 matrix: dbias[n] += sum_m G[m,n].
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ G, int ldg, int M,
-                                                          int n_valid, float* __restrict__ dbias,
-                                                          int rows_per_block) {
-  int n = blockIdx.x * 64 + (threadIdx.x % 64);
-  int sub = threadIdx.x / 64;   // 4 row phases
-  int m0 = blockIdx.y * rows_per_block;
-  int m1 = min(M, m0 + rows_per_block);
-  float s = 0.f;
-  if (n < n_valid)
-    for (int m = m0 + sub; m < m1; m += 4) s += __bfloat162float(G[(int64_t)m * ldg + n]);
-  __shared__ float red[4][64];
-  red[sub][threadIdx.x % 64] = s;
-  __syncthreads();
-  if (sub == 0 && n < n_valid)
-    atomicAdd(dbias + n, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
 
 // ----------------------------------------------------------------------------------- host side
@@ -674,7 +682,7 @@ int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream) {
 
 template <int BK_>
 static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
-                        int k_valid, float* dW, int ldw, cudaStream_t stream) {
+                        int k_valid, float* dW, int ldw, float* dbias, cudaStream_t stream) {
   using Cfg = WgCfg<BK_>;
   CUtensorMap tmG, tmA;
   int rc = make_map(&tmG, G, N, M, ldg, 64, kTileK);
@@ -698,7 +706,7 @@ static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, i
   dim3 grid(out_tiles, splits);
   { LaunchScope ls_(NRF_CAT_WGRAD, stream);
   wgrad_tc_kernel<BK_><<<grid, kThreads, Cfg::kSmem, stream>>>(tmG, tmA, M, k_tiles, m_per, n_valid, k_valid,
-                                                               dW, ldw);
+                                                               dW, ldw, dbias);
   }
   NRF_LAUNCH_OK();
   return NRF_OK;
@@ -709,20 +717,10 @@ int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N
   (void)workspace;
   NRF_REQUIRE(N % 64 == 0 && K % 64 == 0, NRF_ENOSUP, "wgrad_tc: N=%d, K=%d must be multiples of 64", N, K);
   int rc;
-  if (k_valid > 128) rc = launch_wgrad<256>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, stream);
-  else if (k_valid > 64) rc = launch_wgrad<128>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, stream);
-  else rc = launch_wgrad<64>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, stream);
-  if (rc) return rc;
-  if (dbias) {
-    int rows_per_block = 2048;
-    dim3 grid((n_valid + 63) / 64, (M + rows_per_block - 1) / rows_per_block);
-    { LaunchScope ls_(NRF_CAT_COLSUM, stream);
-    colsum_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(G), ldg, M, n_valid,
-                                                 dbias, rows_per_block);
-    }
-    NRF_LAUNCH_OK();
-  }
-  return NRF_OK;
+  if (k_valid > 128) rc = launch_wgrad<256>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, stream);
+  else if (k_valid > 64) rc = launch_wgrad<128>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, stream);
+  else rc = launch_wgrad<64>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, stream);
+  return rc;
 }
 
 }  // namespace nrf

@@ -92,29 +92,6 @@ __global__ void add_bias_kernel(float* __restrict__ dst, const float* __restrict
   if (i < n) dst[i] = (a ? a[i] : 0.0f) + (b ? b[i] : 0.0f);
 }
 
-// dst[i] += src[i]
-__global__ void accumulate_vec_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] += src[i];
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ G, int ldg, int64_t M, int n_valid,
-                                                     float* __restrict__ out, int rows_per_block) {
-  int n = blockIdx.x * 64 + (threadIdx.x % 64);
-  int sub = threadIdx.x / 64;
-  int64_t m0 = (int64_t)blockIdx.y * rows_per_block;
-  int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
-  float s = 0.f;
-  if (n < n_valid)
-    for (int64_t m = m0 + sub; m < m1; m += 4) s += to_f32(G[m * ldg + n]);
-  __shared__ float red[4][64];
-  red[sub][threadIdx.x % 64] = s;
-  __syncthreads();
-  if (sub == 0 && n < n_valid)
-    atomicAdd(out + n, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
-}
-
 template <typename T>
 static int pack(void* base, int64_t off, int ld_dst, int rows, int cols, const float* src, int ld_src,
                 int transpose, int col0, cudaStream_t s) {
@@ -179,41 +156,13 @@ static int run_gemm(const NrfGemm& g, int precision, cudaStream_t s) {
   return precision == NRF_PREC_BF16 ? gemm_tc_launch(g, s) : gemm_simt_launch(g, s);
 }
 
+// dW += G^T A and (fused, from the same G tiles) dbias += column sums of G.
 static int run_wgrad(const void* G, int ldg, const void* A, int lda, int64_t M, int N, int K, int n_valid,
-                     int k_valid, float* dW, int ldw, int precision, cudaStream_t s) {
+                     int k_valid, float* dW, int ldw, float* dbias, int precision, cudaStream_t s) {
   if (!dW) return NRF_OK;
   return precision == NRF_PREC_BF16
-             ? wgrad_tc_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, nullptr, nullptr, s)
-             : wgrad_simt_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, nullptr, s);
-}
-
-// tmp[0..n) = column sums of G, then added to up to two bias gradients.
-static int bias_grads(const void* G, int ldg, int64_t M, int n, float* tmp, float* d1, float* d2, int precision,
-                      cudaStream_t s) {
-  if (!d1 && !d2) return NRF_OK;
-  NRF_CUDA_OK(cudaMemsetAsync(tmp, 0, (size_t)n * 4, s));
-  int rows_per_block = 4096;
-  dim3 grid((n + 63) / 64, (unsigned)((M + rows_per_block - 1) / rows_per_block));
-  if (precision == NRF_PREC_BF16)
-    { LaunchScope ls_(NRF_CAT_COLSUM, s);
-    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(G), ldg, M, n, tmp, rows_per_block);
-    }
-  else
-    { LaunchScope ls_(NRF_CAT_COLSUM, s);
-    colsum_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(G), ldg, M, n, tmp, rows_per_block);
-    }
-  NRF_LAUNCH_OK();
-  if (d1) {
-    { LaunchScope ls_(NRF_CAT_MISC, s);
-      accumulate_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(d1, tmp, n); }
-    NRF_LAUNCH_OK();
-  }
-  if (d2) {
-    { LaunchScope ls_(NRF_CAT_MISC, s);
-      accumulate_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(d2, tmp, n); }
-    NRF_LAUNCH_OK();
-  }
-  return NRF_OK;
+             ? wgrad_tc_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, dbias, nullptr, s)
+             : wgrad_simt_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, dbias, s);
 }
 
 }  // namespace nrf
@@ -315,7 +264,6 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
   auto ax = [&](int b) { return act + (int64_t)b * layer; };
   auto an = [&](int b) { return act + (int64_t)(L.nb + 1 + b) * layer; };
   char* sc = reinterpret_cast<char*>(scratch);
-  float* tmp = reinterpret_cast<float*>(sc);
   int64_t fixed = round_up((L.H > L.dout_pad ? L.H : L.dout_pad) * 4, 1024);
   char* gbuf = sc + fixed;                    // dL/dx, updated in place while b >= n_lin_z
   char* dnet = gbuf + layer;
@@ -323,8 +271,8 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
 
   // lin_out: parameter gradients, then the gradient of x_nb (ReLU-gated by relu(x_nb) > 0)
-  TRY(run_wgrad(d_field, L.dout_pad, ax(L.nb), L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H, precision, s));
-  TRY(bias_grads(d_field, L.dout_pad, N, L.Dout, tmp, gr->lin_out_b, nullptr, precision, s));
+  TRY(run_wgrad(d_field, L.dout_pad, ax(L.nb), L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H,
+                gr->lin_out_b, precision, s));
   NrfGemm g = gemm_init(N, L.H, L.H);
   set_a(g, 0, d_field, L.dout_pad, L.dout_pad);
   g.B = W + L.WoutT; g.ldb = L.dout_pad;
@@ -335,10 +283,10 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
   const char* gcur = gbuf;                    // dL/dx_{b+1}
   for (int b = L.nb - 1; b >= 0; --b) {
     bool cat = b + 1 < L.nz;
-    TRY(run_wgrad(gcur, L.H, an(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc1_w[b], L.H, precision, s));
+    TRY(run_wgrad(gcur, L.H, an(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc1_w[b], L.H, gr->fc1_b[b], precision, s));
     if (cat)
-      TRY(run_wgrad(gcur, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[b + 1], L.C, precision, s));
-    TRY(bias_grads(gcur, L.H, N, L.H, tmp, gr->fc1_b[b], cat ? gr->lin_z_b[b + 1] : nullptr, precision, s));
+      TRY(run_wgrad(gcur, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[b + 1], L.C,
+                    gr->lin_z_b[b + 1], precision, s));
     // dnet_b = (g . W_fc1[b]) gated by relu(net_b) > 0
     g = gemm_init(N, L.H, L.H);
     set_a(g, 0, gcur, L.H, L.H);
@@ -346,8 +294,7 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
     g.mask_src = an(b); g.ldmask = L.H;
     g.out_act = dnet; g.ldact = L.H;
     TRY(run_gemm(g, precision, s));
-    TRY(run_wgrad(dnet, L.H, ax(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc0_w[b], L.H, precision, s));
-    TRY(bias_grads(dnet, L.H, N, L.H, tmp, gr->fc0_b[b], nullptr, precision, s));
+    TRY(run_wgrad(dnet, L.H, ax(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc0_w[b], L.H, gr->fc0_b[b], precision, s));
     // dL/dx'_b = dL/dx_{b+1} + (dnet_b . W_fc0[b]) gated by relu(x'_b) > 0
     char* target = b < L.nz ? gz(b) : gbuf;
     g = gemm_init(N, L.H, L.H);
@@ -375,10 +322,10 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
   }
   // first layer: x'_0 = [z | p] . [W_z0 | W_in]^T ; gcur = dL/dx'_0
   if (L.nz > 0)
-    TRY(run_wgrad(gcur, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[0], L.C, precision, s));
+    TRY(run_wgrad(gcur, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[0], L.C,
+                  gr->lin_z_b[0], precision, s));
   TRY(run_wgrad(gcur, L.H, fin + (int64_t)L.C * L.es, L.kin_pad, N, L.H, L.kin_pad - L.C, L.H, L.Din, gr->lin_in_w,
-                L.Din, precision, s));
-  TRY(bias_grads(gcur, L.H, N, L.H, tmp, gr->lin_in_b, L.nz > 0 ? gr->lin_z_b[0] : nullptr, precision, s));
+                L.Din, gr->lin_in_b, precision, s));
 #undef TRY
   return NRF_OK;
 }
