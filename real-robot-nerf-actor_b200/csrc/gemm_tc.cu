@@ -516,25 +516,40 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   } else if (warp >= kEpiWarp0) {
     const int q = warp - kEpiWarp0;
     if (do_bias) {
-      const int col = q * 32 + lane;                       // column of the 128-wide G tile
-      const uint32_t slab = (uint32_t)(col >> 6) * (kTileK * 128);
-      const uint32_t cc = (uint32_t)(col & 63);
-      float bsum = 0.f;
+      // thread -> one 16 B column group (8 columns) and one row phase: 8 x LDS.128 per 64-sample stage
+      const int et = q * 32 + lane;
+      const uint32_t cg = (uint32_t)(et & 15), rp = (uint32_t)(et >> 4);   // column group 0..15, row phase 0..7
+      const uint32_t base = (cg >> 3) * (kTileK * 128) + rp * 128 + (((cg & 7) ^ rp) << 4);
+      float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       PipeState st;
       for (int mb = 0; mb < num_mb; ++mb) {
         mbar_wait(full + st.stage, st.phase);
-        const uint8_t* sg = smem + st.stage * Cfg::kStage + slab;
-#pragma unroll 8
-        for (int m = 0; m < kTileK; ++m) {
-          uint32_t off = (uint32_t)m * 128 + ((((cc >> 3) ^ (uint32_t)(m & 7))) << 4) + (cc & 7) * 2;
-          bsum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sg + off));
+        const uint8_t* sg = smem + st.stage * Cfg::kStage + base;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                                        // rows rp, rp+8, ..., rp+56
+          uint4 v = *reinterpret_cast<const uint4*>(sg + i * 1024);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float2 f = __bfloat1622float2(h[t]);
+            bs[2 * t] += f.x;
+            bs[2 * t + 1] += f.y;
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + st.stage);
         st.advance(Cfg::kStages);
       }
-      const int n = n_blk * kTileM + col;
-      if (n < n_valid && num_mb > 0) atomicAdd(dbias + n, bsum);
+      // the two row phases of a warp meet by shuffle; the four warps add their partials atomically
+#pragma unroll
+      for (int t = 0; t < 8; ++t) bs[t] += __shfl_xor_sync(0xffffffffu, bs[t], 16);
+      if (lane < 16 && num_mb > 0) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          int n = n_blk * kTileM + (int)cg * 8 + t;
+          if (n < n_valid) atomicAdd(dbias + n, bs[t]);
+        }
+      }
     }
     if (num_mb > 0) {
       mbar_wait(acc_full, 0);

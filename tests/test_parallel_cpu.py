@@ -1,0 +1,121 @@
+"""Host-side logic of the multi-GPU path on CPU: ray sharding and the gradient all-reduce with
+world_size 2 over gloo.  Also checks that the C-ABI library loads and exports every declared symbol."""
+import os
+import re
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.conftest import ROOT, load_pkg
+
+par = load_pkg("parallel")
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 4096, 81920, 81921):
+        for w in (1, 2, 3, 4, 8):
+            spans = [par.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    rays = torch.arange(10 * 8, dtype=torch.float32).reshape(10, 8)
+    assert torch.equal(torch.cat([par.shard_rays(rays, 3, r) for r in range(3)]), rays)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(5, 3)
+        shared = torch.nn.Linear(3, 3)
+        model = torch.nn.ModuleDict({"a": lin, "coarse": shared, "fine": shared, "nograd": torch.nn.Linear(2, 2)})
+        x = torch.full((4, 5), float(rank + 1))
+        (shared(lin(x)).sum() * (rank + 1)).backward()          # 'nograd' never receives a gradient
+        local = [p.grad.clone() for p in (lin.weight, lin.bias, shared.weight, shared.bias)]
+        nbytes = par.allreduce_mlp_grads(model)
+        n_unique = sum(p.numel() for p in model.parameters())
+        assert nbytes == 4 * n_unique                            # aliased module counted once
+        gathered = [[torch.zeros_like(g) for _ in range(world)] for g in local]
+        for g, dst in zip(local, gathered):
+            dist.all_gather(dst, g)
+        for p, parts in zip((lin.weight, lin.bias, shared.weight, shared.bias), gathered):
+            assert torch.allclose(p.grad, sum(parts))
+        assert torch.equal(model["nograd"].weight.grad, torch.zeros(2, 2))
+        vol = torch.full((2, 3), float(rank + 1))
+        par.allreduce_volume_grad(vol)
+        assert torch.equal(vol, torch.full((2, 3), float(sum(range(1, world + 1)))))
+        out.put((rank, "ok"))
+    except Exception as e:                                        # pragma: no cover
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(out.get() for _ in range(2))
+    assert res == {0: "ok", 1: "ok"}, res
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """include/nrf_b200.h <-> libnrf_b200.so <-> the ctypes binding agree (no compute calls: no GPU here)."""
+    lib_mod = load_pkg("_lib")
+    if not os.path.exists(lib_mod.LIB_PATH):
+        load_pkg("_build").build()
+    lib = lib_mod.load()
+    header = open(os.path.join(ROOT, "include", "nrf_b200.h")).read()
+    declared = set(re.findall(r"\b(nrf_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(lib_mod.EXPORTS), declared ^ set(lib_mod.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.nrf_version()
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    lib_mod = load_pkg("_lib")
+    monkeypatch.setattr(lib_mod, "_lib", None)
+    monkeypatch.setattr(lib_mod, "LIB_PATH", "/nonexistent/libnrf_b200.so")
+    with pytest.raises(lib_mod.NrfError):
+        lib_mod.load()
+
+
+def test_renderer_keeps_reference_surface():
+    """Constructor / config / state_dict surface of the drop-in (no GPU needed)."""
+    NR = load_pkg("neural_rendering")
+    U = load_pkg("utils")
+    ren = NR.NeuralRenderer(U.default_config(), torch.tensor([-0.1, -0.3, -0.2, 0.8, 0.7, 0.7]))
+    sd = ren.state_dict()
+    assert len(sd) == 62 and sum(p.numel() for p in ren.parameters()) == 3_045_764
+    assert ren.nerf_model.mlp_fine is ren.nerf_model.mlp_coarse
+    assert "nerf_model.code._freqs" in sd and "nerf_model.mlp_fine.lin_z.2.bias" in sd
+    assert float(ren.nerf_model.mlp_coarse.blocks[0].fc_1.weight.abs().max()) == 0.0     # resnetfc.py:41
+    for name in ("forward", "rendering", "encode", "forward_nerf", "sample_coarse", "sample_fine",
+                 "sample_fine_depth", "composite", "compute_rendering_loss"):
+        assert callable(getattr(ren, name))
+    for key, bad in (("use_multi_scale_voxel", True), ("regress_coord", True), ("ret_last_feat", True)):
+        with pytest.raises(NotImplementedError):
+            NR.NeuralRenderer(U.default_config(**{key: bad}), torch.zeros(6))
+    with pytest.raises(NotImplementedError):
+        NR.NeuralRenderer(U.default_config(foundation_model_name="nope"), torch.zeros(6))
+    with pytest.raises(Exception):                # CPU tensors are rejected: there is no CPU fallback
+        ren.encode(None, None, None, torch.zeros(1, 128, 4, 4, 4), None, None)
+        ren.forward_nerf(torch.zeros(1, 4, 8))
