@@ -12,6 +12,8 @@
 //                               bias / ReLU-gate / residual / bf16 re-quantisation; ReLU-gate and residual
 //                               tiles arrive by TMA (prefetched 3 chunks ahead), results leave by TMA store
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include "gemm_common.cuh"
 
@@ -58,6 +60,28 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> the pair's leader
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -92,7 +116,25 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {     // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -104,7 +146,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  tmem_ld32_nowait(taddr, v);
+  tmem_ld_wait();
 }
 
 // ---------------------------------------------------------------------------------- descriptors
@@ -126,7 +172,8 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
 constexpr int kTileM = 128;       // UMMA M (cta_group::1)
 constexpr int kTileK = 64;        // 64 bf16 = one 128 B swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;          // wgrad kernel: 4 service warps + 4 epilogue warps
+constexpr int kFwdThreads = 384;       // forward/dgrad kernel: 4 service warps + 2 x 4 epilogue warps
 constexpr int kEpiWarp0 = 4;
 
 struct PipeState {
@@ -152,19 +199,19 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN>
+template <int BN, int CG>
 struct FwdCfg {
-  static constexpr int kStageA = kTileM * kTileK * 2;          // 16 KB
-  static constexpr int kStageB = BN * kTileK * 2;              // 32 KB (BN=256) / 16 KB (BN=128)
+  static constexpr int kStageA = kTileM * kTileK * 2;          // 16 KB: this CTA's 128 rows of A
+  static constexpr int kStageB = BN * kTileK * 2 / CG;         // B tile; a CTA pair (CG = 2) holds half each
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = BN == 256 ? 3 : 4;
+  static constexpr int kStages = (CG == 2 || BN == 128) ? 4 : 2;   // 32 KB stages x 4 (BN=256 single CTA: 48 KB x 2)
   static constexpr int kEpiBuf = kTileM * 64;                  // 128 rows x 64 B (32 bf16 columns)
-  static constexpr int kEpiBufs = 10;                          // outA[2] outB[2] mask[3] resid[3]
-  static constexpr int kInSlots = 3;
+  static constexpr int kEpiBufs = 12;                          // per epilogue group: 2 slots of outA | outB or mask | resid
+  static constexpr int kInSlots = 2;
   static constexpr int kTmemCols = 2 * BN;                     // 2 accumulator stages
-  static constexpr int kSmem = kStages * kStage + kEpiBufs * kEpiBuf + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kSmem = kStages * kStage + kEpiBufs * kEpiBuf + 1024 /*align*/ + 512 /*barriers*/ +
+                               BN * 4 /*bias slice*/;
 };
 
 struct FwdArgs {
@@ -172,16 +219,23 @@ struct FwdArgs {
   int kb[3];                 // 64-wide k-blocks per A source
   const float* bias;
   int has_mask, has_resid, has_outA, relu_a, has_outB, relu_b, f32_out;
+  int dbg;                   // NRF_DBG experiments: 1 = no TMA stores, 2 = no epilogue at all (timing only!)
 };
+// compile-time epilogue kinds (EPI < 0: decided at run time from FwdArgs)
+constexpr int kEpiMask = 1, kEpiResid = 2, kEpiOutB = 4, kEpiF32 = 8;
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+// CG = 2: the two CTAs of a cluster (one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA holds its
+// own 128 rows of A and HALF of the B tile, the leader CTA issues the MMAs for both, each CTA's TMEM receives
+// the accumulator of its own rows.  Per MMA every SM ingests 32 KB per k-block instead of 48 KB, which is what
+// bounded the single-CTA kernel (profiles/r01_gemm_v2_ncu.md).
+template <int BN, int CG, int EPI>
+__global__ void __launch_bounds__(kFwdThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmMask, const __grid_constant__ CUtensorMap tmResid,
                const __grid_constant__ CUtensorMap tmOutA, const __grid_constant__ CUtensorMap tmOutB,
                const __grid_constant__ CUtensorMap tmOutF, const FwdArgs a) {
-  using Cfg = FwdCfg<BN>;
+  using Cfg = FwdCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi = smem + Cfg::kStages * Cfg::kStage;
@@ -190,14 +244,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* acc_full = empty + Cfg::kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* in_full = acc_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + Cfg::kInSlots);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 2 * Cfg::kInSlots);
+  float* sbias = reinterpret_cast<float*>(epi + Cfg::kEpiBufs * Cfg::kEpiBuf + 512);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m_tiles = (a.M + kTileM - 1) / kTileM, n_tiles = a.N / BN;
   const int tiles = m_tiles * n_tiles;
   const int kb01 = a.kb[0] + a.kb[1];
   const int num_kb = kb01 + a.kb[2];
-
+  // tile sequence of this CTA: iteration `it` -> (m_blk, n_blk).  A pair walks (row pair, n block) tiles.
+  uint32_t crank = 0;
+  if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const bool cta_leader = crank == 0;
+  const int unit = CG == 2 ? blockIdx.x / 2 : blockIdx.x, n_units = CG == 2 ? gridDim.x / 2 : gridDim.x;
+  const int work = (CG == 2 ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+  const int n_iter = unit < work ? (work - unit + n_units - 1) / n_units : 0;
+  auto tile_of = [&](int it, int& m_blk, int& n_blk) {
+    int t = unit + it * n_units;
+    m_blk = CG == 2 ? 2 * (t / n_tiles) + (int)crank : t / n_tiles;
+    n_blk = t % n_tiles;
+  };
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
@@ -210,41 +276,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (a.f32_out) tma_prefetch_desc(&tmOutF);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
-    for (int s = 0; s < Cfg::kInSlots; ++s) mbar_init(in_full + s, 1);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, CG); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 8 * CG); }
+    for (int s = 0; s < 2 * Cfg::kInSlots; ++s) mbar_init(in_full + s, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 2) { if (CG == 2) tmem_alloc2(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols); }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();   // both CTAs' barriers exist before the peer signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       PipeState st;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      for (int it = 0; it < n_iter; ++it) {
+        int m_blk, n_blk;
+        tile_of(it, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty + st.stage, st.phase ^ 1);
           uint8_t* sa = smem + st.stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
-          mbar_expect_tx(full + st.stage, Cfg::kStage);
-          if (kb < a.kb[0])    tma_load_2d(sa, &tmA0, full + st.stage, kb * kTileK, m_blk * kTileM);
-          else if (kb < kb01)  tma_load_2d(sa, &tmA1, full + st.stage, (kb - a.kb[0]) * kTileK, m_blk * kTileM);
-          else                 tma_load_2d(sa, &tmA2, full + st.stage, (kb - kb01) * kTileK, m_blk * kTileM);
-          tma_load_2d(sb, &tmB, full + st.stage, kb * kTileK, n_blk * BN);
+          const CUtensorMap* mapA = kb < a.kb[0] ? &tmA0 : (kb < kb01 ? &tmA1 : &tmA2);
+          const int kcol = (kb < a.kb[0] ? kb : (kb < kb01 ? kb - a.kb[0] : kb - kb01)) * kTileK;
+          if (CG == 2) {
+            // both CTAs' loads complete on the LEADER's barrier (it issues the MMAs for the pair)
+            if (cta_leader) mbar_expect_tx(full + st.stage, 2 * Cfg::kStage);
+            else mbar_arrive_leader(full + st.stage);
+            tma_load_2d_pair(sa, mapA, full + st.stage, kcol, m_blk * kTileM);
+            tma_load_2d_pair(sb, &tmB, full + st.stage, kb * kTileK, n_blk * BN + (int)crank * (BN / 2));
+          } else {
+            mbar_expect_tx(full + st.stage, Cfg::kStage);
+            tma_load_2d(sa, mapA, full + st.stage, kcol, m_blk * kTileM);
+            tma_load_2d(sb, &tmB, full + st.stage, kb * kTileK, n_blk * BN);
+          }
           st.advance(Cfg::kStages);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kTileM, BN, 0, 0);
+    if (lane == 0 && cta_leader) {
+      constexpr uint32_t idesc = make_idesc(kTileM * CG, BN, 0, 0);
       PipeState st;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      for (int it = 0; it < n_iter; ++it) {
         int as = it & 1;
         uint32_t aphase = (it >> 1) & 1;
         mbar_wait(acc_empty + as, aphase ^ 1);
@@ -260,68 +335,105 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < kTileK / kUmmaK; ++k) {
             // +32 B per 16-element K step inside the 128 B swizzle row: +2 in the 16 B address field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (CG == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(empty + st.stage);
+          if (CG == 2) umma_commit_pair(empty + st.stage);      // frees the stage in both CTAs
+          else umma_commit(empty + st.stage);
           st.advance(Cfg::kStages);
         }
-        umma_commit(acc_full + as);
+        if (CG == 2) umma_commit_pair(acc_full + as);           // both CTAs' epilogues
+        else umma_commit(acc_full + as);
       }
     }
   } else if (warp >= kEpiWarp0) {
-    const int q4 = warp - kEpiWarp0;                 // TMEM lane quarter this warp may read
+    // ---- epilogue: two groups of 4 warps; group g owns the 32-column chunks c with c % 2 == g.  Every warp
+    // reads its own TMEM lane quarter (warp % 4).  Each group has its own leader thread, named barrier,
+    // staging slots and TMA prefetch cursor.
+    const int eg = (warp - kEpiWarp0) >> 2;          // group 0 / 1
+    const int q4 = warp & 3;                         // TMEM lane quarter this warp may read
     const int row = q4 * 32 + lane;                  // row of the tile == TMEM lane
     const bool leader = (row == 0);
-    const bool has_in = a.has_mask || a.has_resid;
-    const uint32_t in_bytes = (uint32_t)(a.has_mask + a.has_resid) * Cfg::kEpiBuf;
-    uint8_t* bufOutA = epi;                          // 2 x 8 KB (bf16) -- or 2 x 16 KB fp32 over outA+outB
-    uint8_t* bufOutB = epi + 2 * Cfg::kEpiBuf;
-    uint8_t* bufMask = epi + 4 * Cfg::kEpiBuf;       // 3 slots
-    uint8_t* bufResid = epi + 7 * Cfg::kEpiBuf;      // 3 slots
-    auto chunks_of = [&](int tile) {
-      int n_blk = tile % n_tiles;
+    const bool has_mask = EPI < 0 ? a.has_mask != 0 : (EPI & kEpiMask) != 0;
+    const bool has_resid = EPI < 0 ? a.has_resid != 0 : (EPI & kEpiResid) != 0;
+    const bool has_outB = EPI < 0 ? a.has_outB != 0 : (EPI & kEpiOutB) != 0;
+    const bool f32_out = EPI < 0 ? a.f32_out != 0 : (EPI & kEpiF32) != 0;
+    const bool has_in = has_mask || has_resid;
+    const uint32_t in_bytes = (uint32_t)((has_mask ? 1 : 0) + (has_resid ? 1 : 0)) * Cfg::kEpiBuf;
+    // per group: [outA x2 | outB-or-mask x2 | resid x2] 8 KB buffers; an fp32 output chunk (16 KB) uses the
+    // first four.  A second output and a ReLU-gate input never occur in the same GEMM.
+    uint8_t* gbase = epi + eg * (Cfg::kEpiBufs / 2) * Cfg::kEpiBuf;
+    uint8_t* bufOutA = gbase;
+    uint8_t* bufOutB = gbase + 2 * Cfg::kEpiBuf;
+    uint8_t* bufMask = gbase + 2 * Cfg::kEpiBuf;
+    uint8_t* bufResid = gbase + 4 * Cfg::kEpiBuf;
+    uint64_t* my_in_full = in_full + eg * Cfg::kInSlots;
+    auto group_barrier = [&]() {
+      if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
+    auto chunks_of = [&](int it) {                   // chunks of tile `it` (both groups together)
+      int m_blk, n_blk;
+      tile_of(it, m_blk, n_blk);
       int left = a.n_store - n_blk * BN;
       int c = (left + 31) / 32;
       return c < 0 ? 0 : (c > BN / 32 ? BN / 32 : c);
     };
-    // prefetch cursor (leader only): runs kInSlots chunks ahead of the consumer
-    int pf_tile = blockIdx.x, pf_c = 0;
+    // prefetch cursor (leader only): runs kInSlots of this group's chunks ahead of the consumer
+    int pf_it = 0, pf_c = eg;
     uint32_t pf_q = 0;
     auto prefetch_one = [&]() {
-      while (pf_tile < tiles && pf_c >= chunks_of(pf_tile)) { pf_tile += gridDim.x; pf_c = 0; }
-      if (pf_tile >= tiles) return;
+      while (pf_it < n_iter && pf_c >= chunks_of(pf_it)) { ++pf_it; pf_c = eg; }
+      if (pf_it >= n_iter) return;
       int slot = pf_q % Cfg::kInSlots;
-      int m0 = (pf_tile / n_tiles) * kTileM, n0 = (pf_tile % n_tiles) * BN + pf_c * 32;
-      mbar_expect_tx(in_full + slot, in_bytes);
-      if (a.has_mask) tma_load_2d(bufMask + slot * Cfg::kEpiBuf, &tmMask, in_full + slot, n0, m0);
-      if (a.has_resid) tma_load_2d(bufResid + slot * Cfg::kEpiBuf, &tmResid, in_full + slot, n0, m0);
+      int pm, pn;
+      tile_of(pf_it, pm, pn);
+      int m0 = pm * kTileM, n0 = pn * BN + pf_c * 32;
+      mbar_expect_tx(my_in_full + slot, in_bytes);
+      if (has_mask) tma_load_2d(bufMask + slot * Cfg::kEpiBuf, &tmMask, my_in_full + slot, n0, m0);
+      if (has_resid) tma_load_2d(bufResid + slot * Cfg::kEpiBuf, &tmResid, my_in_full + slot, n0, m0);
       ++pf_q;
-      ++pf_c;
+      pf_c += 2;
     };
     if (leader && has_in)
       for (int i = 0; i < Cfg::kInSlots; ++i) prefetch_one();
 
-    uint32_t q = 0;                                  // running chunk counter (all epilogue threads)
-    int it = 0;
+    uint32_t q = 0;                                  // running chunk counter of this group
     const uint32_t sw64 = (uint32_t)((row >> 1) & 3);   // 64B swizzle: 16 B chunk index ^= (row/2)%4
     const uint32_t sw128 = (uint32_t)(row & 7);         // 128B swizzle: 16 B chunk index ^= row%8
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / n_tiles) * kTileM, n_base = (tile % n_tiles) * BN;
+    int bias_blk = -1;                               // n block whose bias slice sits in sbias
+    for (int it = 0; it < n_iter; ++it) {
+      int tm, tn;
+      tile_of(it, tm, tn);
+      const int m0 = tm * kTileM, n_base = tn * BN;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int nch = chunks_of(tile);
+      const int nch = chunks_of(it);
+      if (a.bias && bias_blk != tn) {                // once per CTA when the CTA keeps its n block
+        asm volatile("bar.sync 3, 256;" ::: "memory");            // nobody still reads the previous slice
+        for (int i = (eg * 128 + row); i < BN; i += 256) sbias[i] = __ldg(a.bias + n_base + i);
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        bias_blk = tn;
+      }
       mbar_wait(acc_full + as, aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q4 * 32) << 16);
+      const int last_c = nch - 1 - (((nch - 1) & 1) != eg ? 1 : 0);   // this group's last chunk (may be < eg: none)
+      if ((a.dbg & 2) || last_c < eg) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CG == 2) mbar_arrive_leader(acc_empty + as); else mbar_arrive(acc_empty + as); }
+        continue;
+      }
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c, ++q) {
+      for (int c = eg; c < nch; c += 2, ++q) {
         const int n0 = n_base + c * 32;
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
-        if (c == nch - 1) {                          // accumulator fully read: hand it back to the MMA warp
+        if (c == last_c) {                           // this warp is done with the accumulator stage
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty + as);
+          if (lane == 0) { if (CG == 2) mbar_arrive_leader(acc_empty + as); else mbar_arrive(acc_empty + as); }
         }
         float x[32];
 #pragma unroll
@@ -329,14 +441,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (a.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + j));
+            float4 b = *reinterpret_cast<const float4*>(sbias + c * 32 + j);
             x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
           }
         }
         if (has_in) {
           const int slot = q % Cfg::kInSlots;
-          mbar_wait(in_full + slot, (q / Cfg::kInSlots) & 1);
-          if (a.has_mask) {
+          mbar_wait(my_in_full + slot, (q / Cfg::kInSlots) & 1);
+          if (has_mask) {
             const uint8_t* mrow = bufMask + slot * Cfg::kEpiBuf + row * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -347,7 +459,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (!(__bfloat162float(h[t]) > 0.0f)) x[j * 8 + t] = 0.0f;
             }
           }
-          if (a.has_resid) {
+          if (has_resid) {
             const uint8_t* rrow = bufResid + slot * Cfg::kEpiBuf + row * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -359,14 +471,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
         const int ob = q & 1;
-        if (a.f32_out) {
-          uint8_t* orow = epi + ob * (2 * Cfg::kEpiBuf) + row * 128;
+        if (f32_out) {
+          uint8_t* orow = gbase + ob * (2 * Cfg::kEpiBuf) + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(orow + ((j ^ sw128) << 4)) =
                 make_float4(x[j * 4], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]);
         } else {
-          if (a.has_outA) {
+          {
             uint8_t* orow = bufOutA + ob * Cfg::kEpiBuf + row * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -381,7 +493,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               *reinterpret_cast<uint4*>(orow + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
-          if (a.has_outB) {
+          if (has_outB) {
             uint8_t* orow = bufOutB + ob * Cfg::kEpiBuf + row * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -398,17 +510,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
         fence_proxy_async();                 // staging writes -> visible to the TMA (async proxy)
-        if (leader) bulk_wait_read0();       // stores of the previous chunk have drained the other buffer
-        epi_barrier();
+        if (leader) bulk_wait_read0();       // the other slot (chunk q-1 of this group) has been drained
+        group_barrier();
         if (leader) {
-          if (a.f32_out) {
-            tma_store_2d(&tmOutF, epi + ob * (2 * Cfg::kEpiBuf), n0, m0);
+          if (a.dbg & 1) {
+          } else if (f32_out) {
+            tma_store_2d(&tmOutF, gbase + ob * (2 * Cfg::kEpiBuf), n0, m0);
           } else {
-            if (a.has_outA) tma_store_2d(&tmOutA, bufOutA + ob * Cfg::kEpiBuf, n0, m0);
-            if (a.has_outB) tma_store_2d(&tmOutB, bufOutB + ob * Cfg::kEpiBuf, n0, m0);
+            tma_store_2d(&tmOutA, bufOutA + ob * Cfg::kEpiBuf, n0, m0);
+            if (has_outB) tma_store_2d(&tmOutB, bufOutB + ob * Cfg::kEpiBuf, n0, m0);
           }
           bulk_commit();
-          if (has_in) prefetch_one();        // every thread is past its reads of slot q % kInSlots
+          if (has_in) prefetch_one();        // every thread of the group is past its reads of slot q % kInSlots
         }
       }
     }
@@ -416,9 +529,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();   // neither CTA leaves while the pair's MMAs / barrier traffic may still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) tmem_dealloc2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -626,22 +740,23 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t 
                      CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN>
+template <int BN, int CG, int EPI>
 static int launch_fwd(const NrfGemm& g, cudaStream_t stream) {
-  using Cfg = FwdCfg<BN>;
+  using Cfg = FwdCfg<BN, CG>;
+  const int a_rows = kTileM, b_rows = BN / CG;   // TMA box heights
   CUtensorMap tmA[3], tmB, tmMask, tmResid, tmOutA, tmOutB, tmOutF;
   int rc = 0;
   int ktot = 0;
   for (int i = 0; i < 3; ++i) {
     if (g.K[i] > 0) {
-      rc = make_map(&tmA[i], g.A[i], g.K[i], g.M, g.lda[i], kTileK, kTileM);
+      rc = make_map(&tmA[i], g.A[i], g.K[i], g.M, g.lda[i], kTileK, a_rows);
       if (rc) return rc;
     } else {
       tmA[i] = tmA[0];
     }
     ktot += g.K[i];
   }
-  rc = make_map(&tmB, g.B, ktot, g.N, g.ldb, kTileK, BN);
+  rc = make_map(&tmB, g.B, ktot, g.N, g.ldb, kTileK, b_rows);
   if (rc) return rc;
   // epilogue tiles: 32 bf16 columns (64 B rows, 64 B swizzle) or 32 fp32 columns (128 B rows, 128 B swizzle)
   auto epi_map = [&](CUtensorMap* m, const void* ptr, int ld) {
@@ -664,17 +779,30 @@ static int launch_fwd(const NrfGemm& g, cudaStream_t stream) {
   a.has_outA = g.out_act != nullptr; a.relu_a = g.relu_act;
   a.has_outB = g.out_act2 != nullptr; a.relu_b = g.relu_act2;
   a.f32_out = g.out_f32 != nullptr;
+  { const char* e = getenv("NRF_DBG"); a.dbg = e ? atoi(e) : 0; }
   static bool attr_set = false;
   if (!attr_set) {
-    NRF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    NRF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;
   }
   int m_tiles = (g.M + kTileM - 1) / kTileM, n_tiles = g.N / BN;
   int tiles = m_tiles * n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  if (CG == 2) {
+    grid = sm_count() / 2 * 2;                       // whole CTA pairs; a pair walks (row pair, n block) tiles
+    int work = (m_tiles + 1) / 2 * n_tiles;
+    if (grid > work * 2) grid = work * 2;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kFwdThreads); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = stream;
   { LaunchScope ls_(NRF_CAT_GEMM, stream);
-  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmem, stream>>>(tmA[0], tmA[1], tmA[2], tmB, tmMask, tmResid, tmOutA,
-                                                             tmOutB, tmOutF, a);
+  NRF_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, EPI>, tmA[0], tmA[1], tmA[2], tmB, tmMask, tmResid, tmOutA,
+                                 tmOutB, tmOutF, a));
   }
   NRF_LAUNCH_OK();
   return NRF_OK;
@@ -688,11 +816,29 @@ int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream) {
   NRF_REQUIRE(!g.out_f32 || (!g.mask_src && !g.resid && !g.out_act && !g.out_act2), NRF_ENOSUP,
               "gemm_tc: out_f32 excludes mask_src / resid / out_act* in bf16 mode");
   NRF_REQUIRE(g.out_act || !g.out_act2, NRF_EINVAL, "gemm_tc: out_act2 without out_act");
+  NRF_REQUIRE(!(g.out_act2 && g.mask_src), NRF_ENOSUP, "gemm_tc: out_act2 and mask_src share staging buffers");
   NRF_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, NRF_EINVAL, "gemm_tc: bias must be 16 B aligned");
   const int BN = g.N % 256 == 0 ? 256 : 128;
   NRF_REQUIRE(g.N - g.n_store < BN, NRF_EINVAL, "gemm_tc: N=%d over-padded for n_store=%d", g.N, g.n_store);
-  if (BN == 256) return launch_fwd<256>(g, stream);
-  return launch_fwd<128>(g, stream);
+  // 256-wide tiles: CTA pairs with tcgen05.mma.cta_group::2 (NRF_GEMM_1CTA=1 keeps the single-CTA kernel);
+  // the pair kernel is specialised on the epilogue kind (less code in the hot loop: it is i-cache sensitive)
+  static const bool one_cta = getenv("NRF_GEMM_1CTA") != nullptr;
+  if (BN == 256 && g.M > kTileM && !one_cta) {
+    int epi = (g.mask_src ? kEpiMask : 0) | (g.resid ? kEpiResid : 0) | (g.out_act2 ? kEpiOutB : 0) |
+              (g.out_f32 ? kEpiF32 : 0);
+    switch (epi) {
+      case 0: return launch_fwd<256, 2, 0>(g, stream);
+      case kEpiOutB: return launch_fwd<256, 2, kEpiOutB>(g, stream);
+      case kEpiResid: return launch_fwd<256, 2, kEpiResid>(g, stream);
+      case kEpiResid | kEpiOutB: return launch_fwd<256, 2, kEpiResid | kEpiOutB>(g, stream);
+      case kEpiMask: return launch_fwd<256, 2, kEpiMask>(g, stream);
+      case kEpiMask | kEpiResid: return launch_fwd<256, 2, kEpiMask | kEpiResid>(g, stream);
+      case kEpiF32: return launch_fwd<256, 2, kEpiF32>(g, stream);
+      default: return launch_fwd<256, 2, -1>(g, stream);
+    }
+  }
+  if (BN == 256) return launch_fwd<256, 1, -1>(g, stream);
+  return launch_fwd<128, 1, -1>(g, stream);
 }
 
 template <int BK_>
@@ -712,7 +858,7 @@ static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, i
   int n_tiles = (n_valid + kTileM - 1) / kTileM;
   int k_tiles = (k_valid + BK_ - 1) / BK_;
   int out_tiles = n_tiles * k_tiles;
-  int splits = (sm_count() + out_tiles - 1) / out_tiles;
+  int splits = sm_count() / out_tiles;      // one wave: (output tiles) x (sample splits) <= #SMs
   int max_splits = (M + 4 * kTileK - 1) / (4 * kTileK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
