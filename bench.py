@@ -169,9 +169,13 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3)
     launches0 = lib.launch_count()
-    lib.timing_begin()
-    ms_total = timed(args.steps, False)
+    ms_total = timed(args.steps, False)                 # the timed region behind `value`
     launches = lib.launch_count() - launches0
+    # same K steps again with a CUDA-event pair around every kernel launch (recorded by the library on the
+    # launching stream): per-kernel durations for the roofline; kept out of `value` because ~500 event
+    # records per step add launch gaps
+    lib.timing_begin()
+    ms_total_ev = timed(args.steps, False)
     kern = lib.timing_end()
     clocks = sampler.stop() if sampler else None
     # end-to-end: host (pinned) inputs copied in, loss read back, every step
@@ -209,7 +213,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 * 8,
                     "note": "poses, focal, gt_rgb, gt_embed copied from pinned host memory each step; loss dict read "
                             "back; the voxel volume is device-resident as in the reference (PerAct encoder output)"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_ms_per_step": kernel_ms}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_ms_per_step": kernel_ms,
+            "ms_per_step_with_kernel_events": round(ms_total_ev / args.steps, 3)}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(rays=args.cpu_rays, reps=1)

@@ -58,20 +58,24 @@ __device__ __forceinline__ void ray_weights(const float* __restrict__ field, int
 }
 
 // field row = [r g b sigma | embed(D)], D % 4 == 0 and ldo % 4 == 0 -> float4 everywhere.
+// One CTA of 4 warps per ray: warp 0 runs the transmittance scan, then warp w accumulates the samples
+// k = w, w+4, ... and the four partial sums meet in shared memory.
+constexpr int kRayWarps = 4;
 __global__ void __launch_bounds__(128) composite_fwd_kernel(
     const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
     int R, int K, int D, int white_bkgd, float* __restrict__ weights, float* __restrict__ rgb,
     float* __restrict__ embed, float* __restrict__ depth) {
   extern __shared__ float smem[];
-  int warps = blockDim.x / kWarp, wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-  int r = blockIdx.x * warps + wid;
-  if (r >= R) return;
-  float* s_w = smem + (size_t)wid * 2 * K;
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int r = blockIdx.x;
+  float* s_w = smem;
   float* s_alpha = s_w + K;
+  float* s_part = smem + ((2 * K + 3) & ~3);   // kRayWarps x (4 + D + 4) partial sums, 16 B aligned
   const float* f = field + (int64_t)r * K * ldo;
   const float* zrow = z + (int64_t)r * K;
   float far = rays[(int64_t)r * 8 + 7];
-  ray_weights<false>(f, ldo, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr);
+  if (wid == 0) ray_weights<false>(f, ldo, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr);
+  __syncthreads();
 
   const int nvec = (4 + D) / 4;             // float4 per row
   constexpr int kMaxVec = 8;                // up to (4+D) <= 1024 channels
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float dsum = 0.f, wsum = 0.f;
-  for (int k = 0; k < K; ++k) {
+  for (int k = wid; k < K; k += kRayWarps) {
     float w = s_w[k];
     const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
 #pragma unroll
@@ -101,20 +105,30 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(
       wsum += w;
     }
   }
-  for (int k = lane; k < K; k += kWarp) weights[(int64_t)r * K + k] = s_w[k];
+  const int pstride = 4 + D + 4;
+  float* mine = s_part + wid * pstride;
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
     int v = lane + i * kWarp;
-    if (v < nvec) {
-      if (v == 0) {
-        float add = white_bkgd ? 1.0f - wsum : 0.0f;
-        rgb[(int64_t)r * 3 + 0] = acc[i].x + add;
-        rgb[(int64_t)r * 3 + 1] = acc[i].y + add;
-        rgb[(int64_t)r * 3 + 2] = acc[i].z + add;
-        depth[r] = dsum;
-      } else {
-        *reinterpret_cast<float4*>(embed + (int64_t)r * D + (v - 1) * 4) = acc[i];
-      }
+    if (v < nvec) *reinterpret_cast<float4*>(mine + v * 4) = acc[i];
+  }
+  if (lane == 0) { mine[4 + D] = dsum; mine[4 + D + 1] = wsum; }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) weights[(int64_t)r * K + k] = s_w[k];
+  for (int c = threadIdx.x; c < 4 + D + 2; c += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRayWarps; ++w) v += s_part[w * pstride + c];
+    if (c < 3) {
+      float ws = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRayWarps; ++w) ws += s_part[w * pstride + 4 + D + 1];
+      rgb[(int64_t)r * 3 + c] = v + (white_bkgd ? 1.0f - ws : 0.0f);
+    } else if (c == 3) {
+    } else if (c < 4 + D) {
+      embed[(int64_t)r * D + (c - 4)] = v;
+    } else if (c == 4 + D) {
+      depth[r] = v;
     }
   }
 }
@@ -143,11 +157,11 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
     int R, int K, int D, int white_bkgd, const float* __restrict__ d_rgb,
     const float* __restrict__ d_embed, const float* __restrict__ d_depth,
     const float* __restrict__ d_weights, T* __restrict__ d_field, int ldg, float* __restrict__ d_z) {
+  // One CTA of 4 warps per ray: scans on warp 0, the per-sample row work split over the 4 warps.
   extern __shared__ float smem[];
-  int warps = blockDim.x / kWarp, wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-  int r = blockIdx.x * warps + wid;
-  if (r >= R) return;
-  float* s_w = smem + (size_t)wid * 6 * K;
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int r = blockIdx.x;
+  float* s_w = smem;
   float* s_alpha = s_w + K;
   float* s_T = s_alpha + K;
   float* s_delta = s_T + K;
@@ -156,7 +170,8 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
   const float* f = field + (int64_t)r * K * ldo;
   const float* zrow = z + (int64_t)r * K;
   float far = rays[(int64_t)r * 8 + 7];
-  ray_weights<true>(f, ldo, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta);
+  if (wid == 0) ray_weights<true>(f, ldo, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta);
+  __syncthreads();
 
   const int nvec = (4 + D) / 4;
   constexpr int kMaxVec = 8;
@@ -180,7 +195,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
   if (white_bkgd) bk = -(d_rgb[(int64_t)r * 3 + 0] + d_rgb[(int64_t)r * 3 + 1] + d_rgb[(int64_t)r * 3 + 2]);
 
   // pass A: g_k
-  for (int k = 0; k < K; ++k) {
+  for (int k = wid; k < K; k += kRayWarps) {
     const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
     float part = 0.f;
 #pragma unroll
@@ -201,9 +216,9 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
       s_g[k] = g;
     }
   }
-  __syncwarp();
-  // suffix sums S_k = sum_{j>k} w_j g_j : lane-chunked reverse scan
-  {
+  __syncthreads();
+  // suffix sums S_k = sum_{j>k} w_j g_j : lane-chunked reverse scan (warp 0)
+  if (wid == 0) {
     int chunk = (K + kWarp - 1) / kWarp;
     int k0 = lane * chunk, k1 = min(K, k0 + chunk);
     float local = 0.f;
@@ -224,9 +239,9 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
       s_ds[k] = one_m * bracket;     // multiply by delta (for dsigma) or relu(sigma) (for ddelta) later
     }
   }
-  __syncwarp();
+  __syncthreads();
   // pass B: write d_field rows
-  for (int k = 0; k < K; ++k) {
+  for (int k = wid; k < K; k += kRayWarps) {
     float w = s_w[k];
     const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
     T* grow = d_field + ((int64_t)r * K + k) * ldg;
@@ -251,7 +266,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
     for (int c = 4 + D + lane; c < ldg; c += kWarp) grow[c] = T(0.0f);
   }
   if (d_z) {
-    for (int k = lane; k < K; k += kWarp) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
       float sig_k = fmaxf(f[(int64_t)k * ldo + 3], 0.0f);
       float dl_k = sig_k * s_ds[k];
       float dl_km1 = 0.f;
@@ -281,10 +296,9 @@ extern "C" int nrf_composite_fwd(const float* field_out, int ldo, const float* z
               "nrf_composite_fwd: null pointer");
   int rc = check_composite("nrf_composite_fwd", R, K, D, ldo);
   if (rc) return rc;
-  int warps = 4;
-  size_t smem = (size_t)warps * 2 * K * sizeof(float);
+  size_t smem = ((size_t)((2 * K + 3) & ~3) + (size_t)kRayWarps * (4 + D + 4)) * sizeof(float);
   { LaunchScope ls_(NRF_CAT_COMPOSITE_FWD, as_stream(stream));
-  composite_fwd_kernel<<<(R + warps - 1) / warps, warps * kWarp, smem, as_stream(stream)>>>(
+  composite_fwd_kernel<<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
       field_out, ldo, z, rays, R, K, D, white_bkgd, weights, rgb, embed, depth);
   }
   NRF_LAUNCH_OK();
@@ -300,10 +314,8 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
   int rc = check_composite("nrf_composite_bwd", R, K, D, ldo);
   if (rc) return rc;
   NRF_REQUIRE(ldg >= 4 + D && ldg % 4 == 0, NRF_EINVAL, "nrf_composite_bwd: ldg=%d", ldg);
-  int warps = 4;
-  size_t smem = (size_t)warps * 6 * K * sizeof(float);
-  NRF_REQUIRE(smem <= 96 * 1024, NRF_ENOSUP, "nrf_composite_bwd: K too large for shared memory");
-  dim3 grid((R + warps - 1) / warps), block(warps * kWarp);
+  size_t smem = (size_t)6 * K * sizeof(float);
+  dim3 grid(R), block(kRayWarps * kWarp);
   if (out_bf16) {
     if (smem > 48 * 1024)
       NRF_CUDA_OK(cudaFuncSetAttribute(composite_bwd_kernel<__nv_bfloat16>,

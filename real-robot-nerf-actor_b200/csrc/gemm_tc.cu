@@ -249,7 +249,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m_tiles = (a.M + kTileM - 1) / kTileM, n_tiles = a.N / BN;
-  const int tiles = m_tiles * n_tiles;
   const int kb01 = a.kb[0] + a.kb[1];
   const int num_kb = kb01 + a.kb[2];
   // tile sequence of this CTA: iteration `it` -> (m_blk, n_blk).  A pair walks (row pair, n block) tiles.

@@ -136,7 +136,7 @@ class _MlpFn(torch.autograd.Function):
         dfield = torch.zeros(N, dpad, device=d_out.device, dtype=ops.act_dtype(h.precision))
         dfield[:, :d_out.shape[1]] = d_out.to(dfield.dtype)
         names = h.names()
-        grads = {n: torch.zeros_like(h.params[n]) for n in names}
+        grads = _zero_grads(h)
         dlat = h.backward(ctx.fin, ctx.acts, dfield, grads)
         dzx = torch.zeros(N, ctx.width, device=d_out.device, dtype=torch.float32)
         dzx[:, :dlat.shape[1]] = dlat
@@ -246,6 +246,19 @@ def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, 
     return d_z
 
 
+def _zero_grads(mlp: ops.FieldMLP):
+    """Zeroed gradient buffers for every MLP parameter: ONE flat allocation / fill, views per parameter."""
+    names = mlp.names()
+    sizes = [mlp.params[n].numel() for n in names]
+    dev = mlp.params[names[0]].device
+    flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+    out, off = {}, 0
+    for n, sz in zip(names, sizes):
+        out[n] = flat[off:off + sz].view_as(mlp.params[n])
+        off += sz
+    return out
+
+
 def _zeros_like_or(t, ref_shape, device):
     return t.contiguous() if t is not None else torch.zeros(ref_shape, device=device, dtype=torch.float32)
 
@@ -312,9 +325,8 @@ class _ForwardNerfFn(torch.autograd.Function):
         D = ren._d_embed
         shared = ren.nerf_model.mlp_fine is ren.nerf_model.mlp_coarse
         names_c = st_c.mlp.names()
-        grads_c = {n: torch.zeros_like(st_c.mlp.params[n]) for n in names_c}
-        grads_f = grads_c if shared or st_f is None else {n: torch.zeros_like(st_f.mlp.params[n])
-                                                          for n in st_f.mlp.names()}
+        grads_c = _zero_grads(st_c.mlp)
+        grads_f = grads_c if shared or st_f is None else _zero_grads(st_f.mlp)
         grad_cl = torch.zeros(ctx.vol_shape, device=dev, dtype=torch.float32)
         _, d_cw, d_crgb, d_cemb, d_cdep = g[:5]
         d_cdep = _zeros_like_or(d_cdep, (R,), dev)
@@ -597,7 +609,7 @@ class _CompositeFn(torch.autograd.Function):
         dev = st.rays.device
         R, D = st.rays.shape[0], ren._d_embed
         names = st.mlp.names()
-        grads = {n: torch.zeros_like(st.mlp.params[n]) for n in names}
+        grads = _zero_grads(st.mlp)
         grad_cl = torch.zeros(ctx.vol_shape, device=dev, dtype=torch.float32)
         d_z = _pass_backward(ren, st, _zeros_like_or(d_rgb, (R, 3), dev), _zeros_like_or(d_emb, (R, D), dev),
                              d_dep, d_w, grads, grad_cl, want_dz=ctx.needs_input_grad[4])
