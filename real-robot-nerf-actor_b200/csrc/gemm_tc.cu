@@ -547,8 +547,9 @@ struct WgCfg {
   static constexpr int kStageA = BK_ * kTileK * 2;             // BK_/64 slabs of [64 m][64 k]
   static constexpr int kStage = kStageG + kStageA;
   static constexpr int kStages = BK_ == 256 ? 4 : 6;
-  static constexpr int kTmemCols = BK_ < 32 ? 32 : BK_;
-  static constexpr int kSmem = kStages * kStage + 1024 + 256;
+  static constexpr int kTmemCols = BK_ == 256 ? 512 : 2 * BK_;  // accumulator + 32 columns for the bias sums
+  static constexpr int kOnes = 2048;                           // 16 x 64 bf16 ones: B operand of the bias MMA
+  static constexpr int kSmem = kStages * kStage + kOnes + 1024 + 256;
 };
 
 template <int BK_>
@@ -559,7 +560,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   using Cfg = WgCfg<BK_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
+  uint8_t* ones = smem + Cfg::kStages * Cfg::kStage;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ones + Cfg::kOnes);
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* acc_full = empty + Cfg::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -569,13 +571,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   const int m_begin = blockIdx.y * m_per_split;
   const int m_end = min(M, m_begin + m_per_split);
   const int num_mb = (m_end - m_begin + kTileK - 1) / kTileK;
-  // bias gradient = column sums of G: the CTAs of the first k tile add them up from the G tiles that
-  // pass through shared memory anyway (the epilogue warps are idle during the main loop)
+  // bias gradient = column sums of G = G^T . 1: the CTAs of the first k tile issue one extra N=16 MMA per
+  // k-step against a constant tile of ones (+6 % tensor time, no extra memory traffic, no extra barriers)
   const bool do_bias = dbias != nullptr && k_blk == 0;
+  if (warp >= kEpiWarp0) {
+    for (int i = threadIdx.x - kEpiWarp0 * 32; i < Cfg::kOnes / 4; i += 128)
+      reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;      // two bf16 1.0
+    fence_proxy_async();
+  }
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmA); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, do_bias ? 5 : 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -608,6 +615,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kTileM, BK_, 1, 1);
+      constexpr uint32_t idesc_bias = make_idesc(kTileM, 16, 1, 1);
+      const uint64_t odesc = make_sdesc(smem_u32(ones), kTileK * 128, 1024);
       PipeState st;
       for (int mb = 0; mb < num_mb; ++mb) {
         mbar_wait(full + st.stage, st.phase);
@@ -620,6 +629,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
         for (int k = 0; k < kTileK / kUmmaK; ++k) {
           // 16 samples = two 8-row atoms = 2048 B: +128 in the 16 B address field
           umma_bf16(tmem_base, gdesc + 128 * k, adesc + 128 * k, idesc, (mb | k) != 0);
+          if (do_bias) umma_bf16(tmem_base + BK_, gdesc + 128 * k, odesc, idesc_bias, (mb | k) != 0);
         }
         umma_commit(empty + st.stage);
         st.advance(Cfg::kStages);
@@ -628,42 +638,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
     }
   } else if (warp >= kEpiWarp0) {
     const int q = warp - kEpiWarp0;
-    if (do_bias) {
-      // thread -> one 16 B column group (8 columns) and one row phase: 8 x LDS.128 per 64-sample stage
-      const int et = q * 32 + lane;
-      const uint32_t cg = (uint32_t)(et & 15), rp = (uint32_t)(et >> 4);   // column group 0..15, row phase 0..7
-      const uint32_t base = (cg >> 3) * (kTileK * 128) + rp * 128 + (((cg & 7) ^ rp) << 4);
-      float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      PipeState st;
-      for (int mb = 0; mb < num_mb; ++mb) {
-        mbar_wait(full + st.stage, st.phase);
-        const uint8_t* sg = smem + st.stage * Cfg::kStage + base;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {                                        // rows rp, rp+8, ..., rp+56
-          uint4 v = *reinterpret_cast<const uint4*>(sg + i * 1024);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float2 f = __bfloat1622float2(h[t]);
-            bs[2 * t] += f.x;
-            bs[2 * t + 1] += f.y;
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + st.stage);
-        st.advance(Cfg::kStages);
-      }
-      // the two row phases of a warp meet by shuffle; the four warps add their partials atomically
-#pragma unroll
-      for (int t = 0; t < 8; ++t) bs[t] += __shfl_xor_sync(0xffffffffu, bs[t], 16);
-      if (lane < 16 && num_mb > 0) {
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          int n = n_blk * kTileM + (int)cg * 8 + t;
-          if (n < n_valid) atomicAdd(dbias + n, bs[t]);
-        }
-      }
-    }
     if (num_mb > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -681,6 +655,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
           for (int j = 0; j < 32; ++j)
             if (k0 + j < k_valid) atomicAdd(dst + j, __uint_as_float(v[j]));
         }
+      }
+      if (do_bias) {                              // column BK_ of the accumulator: sum over the samples of G[:, n]
+        uint32_t v[32];
+        tmem_ld32(taddr + BK_, v);
+        if (n < n_valid) atomicAdd(dbias + n, __uint_as_float(v[0]));
       }
     }
   }

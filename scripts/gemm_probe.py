@@ -35,3 +35,9 @@ bench("plain f32 out", lambda: ops.gemm(A, W, out_f32=xres), F, M * 3072)
 bench("fc_1 (K=640, resid, 2 outs)", lambda: ops.gemm(A, Wc, A2=Z[:, :128], bias=bias, resid=xb, out_act=xb, out_act2=act, relu_act2=True), F * 1.25, M * (1024 + 256 + 1024 + 1024 + 1024))
 bench("dnet (mask, act out)", lambda: ops.gemm(A, W, mask_src=mask, out_act=act), F, M * 3072)
 bench("gx (mask, resid, act out)", lambda: ops.gemm(A, W, mask_src=mask, resid=xb, out_act=gb), F, M * 4096)
+G = torch.randn(M, 512, device=dev, generator=g).to(torch.bfloat16)
+dW = torch.zeros(512, 512, device=dev)
+db = torch.zeros(512, device=dev)
+bench("wgrad 512x512 (no bias)", lambda: ops.wgrad(G, A, dW), F, M * 2048)
+bench("wgrad 512x512 (+bias)", lambda: ops.wgrad(G, A, dW, db), F, M * 2048)
+bench("wgrad 512x128 (+bias)", lambda: ops.wgrad(G, Z[:, :128], torch.zeros(512, 128, device=dev), db), F / 4, M * 1280)
