@@ -89,6 +89,16 @@ int nrf_scatter_volume_grad(const float* rays, const float* z, int R, int K, int
                             const float* dlatent, int ld, float* grad_cl, int SB, int C, int S0,
                             int S1, int S2, const float* bounds_host, void* stream);
 
+/* Atomics-free, bit-reproducible variant: counting sort of the (sample, corner) entries by voxel, then one
+ * warp per voxel sums its entries in a fixed order and writes the row once.  accumulate == 0: every voxel
+ * row of grad_cl is written (zeros where untouched, no prior memset needed); accumulate != 0: touched rows
+ * are read-modify-written.  workspace: nrf_scatter_sorted_workspace_bytes(N = R*K, SB, V = S0*S1*S2). */
+int64_t nrf_scatter_sorted_workspace_bytes(int64_t N, int SB, int64_t V);
+int nrf_scatter_volume_grad_sorted(const float* rays, const float* z, int R, int K, int rays_per_scene,
+                                   const float* dlatent, int ld, float* grad_cl, int SB, int C, int S0,
+                                   int S1, int S2, const float* bounds_host, int accumulate,
+                                   void* workspace, void* stream);
+
 /* ---- alpha compositing (neural_rendering.py:239-243,316-359) ---------------------------------
  * field_out (N, ldo) raw; heads sigmoid(rgb), relu(sigma) (models_embed.py:444-466) applied here.
  * weights (R,K), rgb (R,3), embed (R,D), depth (R). */

@@ -73,10 +73,11 @@ _SIGNATURES = {
     "nrf_mlp_fwd": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, _p],
     "nrf_mlp_bwd": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, C.POINTER(NrfMlpGrads), _p, _p, _p],
 }
+_SIGNATURES["nrf_scatter_volume_grad_sorted"] = [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p]
 _SIGNATURES["nrf_timing_begin"] = []
 _SIGNATURES["nrf_timing_end"] = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
 EXPORTS = sorted(list(_SIGNATURES) + ["nrf_version", "nrf_last_error", "nrf_wgrad_workspace_bytes",
-                                      "nrf_launch_count"])
+                                      "nrf_launch_count", "nrf_scatter_sorted_workspace_bytes"])
 TIMING_CATEGORIES = ["gemm_tc", "wgrad_tc", "encode", "composite_fwd", "composite_bwd", "scatter", "transpose",
                      "colsum", "sampling", "simt", "misc"]
 
@@ -104,6 +105,8 @@ def load():
     lib.nrf_last_error.restype = C.c_char_p
     lib.nrf_wgrad_workspace_bytes.argtypes = [_i, _i]
     lib.nrf_wgrad_workspace_bytes.restype = C.c_int64
+    lib.nrf_scatter_sorted_workspace_bytes.argtypes = [_i64, _i, _i64]
+    lib.nrf_scatter_sorted_workspace_bytes.restype = C.c_int64
     lib.nrf_launch_count.argtypes = []
     lib.nrf_launch_count.restype = C.c_int64
     _lib = lib

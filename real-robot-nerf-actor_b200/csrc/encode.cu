@@ -283,3 +283,225 @@ extern "C" int nrf_scatter_volume_grad(const float* rays, const float* z, int R,
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Atomics-free, deterministic volume-gradient scatter (counting sort by voxel + segmented reduce).
+//   1. scatter_count : per (sample, corner) entry e = 8n + c: key[e] = scene*V + voxel (or -1), w[e] = corner
+//                      weight, count[key]++            (integer atomics only: their result is order-free)
+//   2. exclusive scan of count -> offset               (three small kernels)
+//   3. scatter_fill  : list[offset[key] + cursor[key]++] = e
+//   4. scatter_reduce: one warp per voxel: its entries are visited in ascending e (selection by warp-min, the
+//                      lists are short), grad[voxel,:] (+)= sum_e w[e] * dlatent[e/8,:] -- every voxel row is
+//                      written by exactly one warp, in a fixed order: no float atomics, bit-reproducible.
+namespace nrf {
+
+__global__ void __launch_bounds__(256) scatter_count_kernel(ScatterArgs a, int64_t V, int32_t* __restrict__ key,
+                                                            float* __restrict__ wts, int32_t* __restrict__ count) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t N = (int64_t)a.R * a.K;
+  if (n >= N) return;
+  int r = (int)(n / a.K);
+  int scene = r / a.rays_per_scene;
+  SampleGeom g = sample_geometry(a.rays + (int64_t)r * 8, a.z[n], a.bmin, a.bext);
+  Corner8 c8;
+  trilinear_corners(g.cx, g.cy, g.cz, a.S0, a.S1, a.S2, 1, c8);      // C = 1: off = voxel index
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int32_t kk = -1;
+    if (c8.off[k] >= 0) {
+      kk = (int32_t)((int64_t)scene * V + c8.off[k]);
+      atomicAdd(count + kk, 1);
+    }
+    key[n * 8 + k] = kk;
+    wts[n * 8 + k] = c8.w[k];
+  }
+}
+
+// exclusive scan, 1024 elements per block
+__global__ void __launch_bounds__(256) scan_block_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                         int32_t* __restrict__ block_sums, int64_t T) {
+  __shared__ int32_t warp_tot[8];
+  int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x * 4;
+  int32_t v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = base + i < T ? in[base + i] : 0;
+  int32_t tsum = v[0] + v[1] + v[2] + v[3];
+  int lane = threadIdx.x % 32, wid = threadIdx.x / 32;
+  int32_t incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  int32_t woff = 0;
+  for (int w = 0; w < wid; ++w) woff += warp_tot[w];
+  int32_t excl = woff + incl - tsum;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (base + i < T) out[base + i] = excl;
+    excl += v[i];
+  }
+  if (threadIdx.x == 255) block_sums[blockIdx.x] = woff + incl;
+}
+
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int32_t* __restrict__ block_sums, int nb,
+                                                         int32_t* __restrict__ total) {
+  // single block: serial over chunks of 1024 with a running carry
+  __shared__ int32_t s[1024];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nb; b0 += 1024) {
+    int i = b0 + threadIdx.x;
+    int32_t v = i < nb ? block_sums[i] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int32_t t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    int32_t c = carry;
+    if (i < nb) block_sums[i] = c + s[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + s[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void __launch_bounds__(256) scan_add_kernel(int32_t* __restrict__ out, const int32_t* __restrict__ block_sums,
+                                                       int64_t T) {
+  int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x * 4;
+  int32_t add = block_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (base + i < T) out[base + i] += add;
+}
+
+__global__ void __launch_bounds__(256) scatter_fill_kernel(const int32_t* __restrict__ key, int64_t E,
+                                                           const int32_t* __restrict__ offset,
+                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ list) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int32_t k = key[e];
+  if (k < 0) return;
+  int32_t pos = offset[k] + atomicAdd(cursor + k, 1);
+  list[pos] = (int32_t)e;
+}
+
+__global__ void __launch_bounds__(256) scatter_reduce_kernel(const int32_t* __restrict__ offset,
+                                                             const int32_t* __restrict__ count,
+                                                             const int32_t* __restrict__ list,
+                                                             const float* __restrict__ wts,
+                                                             const float* __restrict__ dlatent, int ld,
+                                                             float* __restrict__ grad, int C, int64_t T, int accumulate) {
+  int lane = threadIdx.x % kWarp;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) / kWarp;
+  for (int64_t v = warp; v < T; v += nwarps) {
+    int cnt = count[v];
+    float* grow = grad + v * C;
+    if (cnt == 0) {
+      if (!accumulate)
+        for (int c0 = lane * 4; c0 < C; c0 += kWarp * 4) *reinterpret_cast<float4*>(grow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const int32_t* lst = list + offset[v];
+    // 128 channels (one float4 per lane) per walk of the list; wider volumes walk it again per slab
+    for (int cb = 0; cb < C; cb += kWarp * 4) {
+      const int c0 = cb + lane * 4;
+      const bool active = c0 < C;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int32_t last = -1;
+      for (int step = 0; step < cnt; ++step) {
+        // next entry in ascending order: smallest id > last (warp-wide selection; the lists are short)
+        int32_t best = 0x7fffffff;
+        for (int i = lane; i < cnt; i += kWarp) {
+          int32_t e = lst[i];
+          if (e > last && e < best) best = e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        last = best;
+        if (active) {
+          float w = wts[best];
+          float4 d = *reinterpret_cast<const float4*>(dlatent + (int64_t)(best >> 3) * ld + c0);
+          acc.x = fmaf(w, d.x, acc.x); acc.y = fmaf(w, d.y, acc.y);
+          acc.z = fmaf(w, d.z, acc.z); acc.w = fmaf(w, d.w, acc.w);
+        }
+      }
+      if (active) {
+        float4* dst = reinterpret_cast<float4*>(grow + c0);
+        if (accumulate) {
+          float4 o = *dst;
+          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        *dst = acc;
+      }
+    }
+  }
+}
+
+}  // namespace nrf
+
+extern "C" int64_t nrf_scatter_sorted_workspace_bytes(int64_t N, int SB, int64_t V) {
+  int64_t T = (int64_t)SB * V, E = N * 8;
+  int64_t nb = (T + 1023) / 1024;
+  // count[T] cursor[T] offset[T] block_sums[nb+1] key[E] list[E] wts[E]
+  return (3 * T + nb + 1 + 2 * E) * 4 + E * 4 + 1024;
+}
+
+extern "C" int nrf_scatter_volume_grad_sorted(const float* rays, const float* z, int R, int K, int rays_per_scene,
+                                              const float* dlatent, int ld, float* grad_cl, int SB, int C, int S0,
+                                              int S1, int S2, const float* bounds_host, int accumulate,
+                                              void* workspace, void* stream) {
+  NRF_REQUIRE(rays && z && dlatent && grad_cl && bounds_host && workspace, NRF_EINVAL,
+              "nrf_scatter_volume_grad_sorted: null pointer");
+  NRF_REQUIRE(R > 0 && K > 0 && R == SB * rays_per_scene, NRF_EINVAL,
+              "nrf_scatter_volume_grad_sorted: R != SB*rays_per_scene");
+  NRF_REQUIRE(C % 4 == 0 && ld % 4 == 0 && ld >= C, NRF_ENOSUP, "nrf_scatter_volume_grad_sorted: C/ld alignment");
+  int64_t V = (int64_t)S0 * S1 * S2, T = (int64_t)SB * V, N = (int64_t)R * K, E = N * 8;
+  NRF_REQUIRE(T < ((int64_t)1 << 31) && E < ((int64_t)1 << 31), NRF_ENOSUP,
+              "nrf_scatter_volume_grad_sorted: more than 2^31 voxels or entries");
+  cudaStream_t s = as_stream(stream);
+  int64_t nb = (T + 1023) / 1024;
+  int32_t* count = reinterpret_cast<int32_t*>(workspace);
+  int32_t* cursor = count + T;
+  int32_t* offset = cursor + T;
+  int32_t* block_sums = offset + T;
+  int32_t* key = block_sums + nb + 1;
+  int32_t* list = key + E;
+  float* wts = reinterpret_cast<float*>(list + E);
+  NRF_CUDA_OK(cudaMemsetAsync(count, 0, (size_t)(2 * T) * 4, s));       // count and cursor
+  ScatterArgs a;
+  a.rays = rays; a.z = z; a.R = R; a.K = K; a.rays_per_scene = rays_per_scene;
+  a.dlatent = dlatent; a.ld = ld; a.grad = grad_cl;
+  a.SB = SB; a.C = C; a.S0 = S0; a.S1 = S1; a.S2 = S2;
+  fill_bounds(bounds_host, a.bmin, a.bext);
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scatter_count_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(a, V, key, wts, count); }
+  NRF_LAUNCH_OK();
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scan_block_kernel<<<(unsigned)nb, 256, 0, s>>>(count, offset, block_sums, T); }
+  NRF_LAUNCH_OK();
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scan_sums_kernel<<<1, 1024, 0, s>>>(block_sums, (int)nb, nullptr); }
+  NRF_LAUNCH_OK();
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scan_add_kernel<<<(unsigned)nb, 256, 0, s>>>(offset, block_sums, T); }
+  NRF_LAUNCH_OK();
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scatter_fill_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(key, E, offset, cursor, list); }
+  NRF_LAUNCH_OK();
+  int64_t want = (T + 7) / 8;
+  int max_blocks = sm_count() * 32;
+  int blocks = (int)(want < max_blocks ? want : max_blocks);
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scatter_reduce_kernel<<<blocks, 256, 0, s>>>(offset, count, list, wts, dlatent, ld, grad_cl, C, T, accumulate); }
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}

@@ -6,8 +6,9 @@ field MLP, alpha compositing, and the whole backward) runs in the hand-written C
 include/nrf_b200.h.  There is no PyTorch/CPU fallback: CPU tensors raise.
 
 Differences from the reference, all opt-in or invisible to its callers:
-  * `precision` ("bf16" tensor-core mode, default; "fp32" parity mode) and `perturb` (default True:
-    the reference always draws sampling noise, neural_rendering.py:172,194,200,218) attributes;
+  * `precision` ("bf16" tensor-core mode, default; "fp32" parity mode), `perturb` (default True: the
+    reference always draws sampling noise, neural_rendering.py:172,194,200,218) and `scatter` ("atomic" |
+    "sorted": atomics-free, bit-reproducible volume gradient) attributes;
   * `forward_nerf(rays, want_weights=False, noise=None)`: `noise` injects pre-drawn tensors
     (keys coarse / u / fine / depth), used by the parity tests;
   * branches that are off in nerfact.conf (multi-scale voxels, depth-supervision volume, coord /
@@ -236,13 +237,16 @@ def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps):
     return st, outs
 
 
-def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, want_dz=False):
+def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, want_dz=False, first=True):
     res = ops.composite_bwd(st.field_out, st.z, st.rays, ren._d_embed, d_rgb, d_embed, d_depth, d_weights,
                             ldg=st.mlp.sizes.dout_pad, precision=st.mlp.precision,
                             white_bkgd=ren.white_bkgd, want_dz=want_dz)
     d_field, d_z = res if want_dz else (res, None)
     dlat = st.mlp.backward(st.field_in, st.acts, d_field, grads)
-    ops.scatter_volume_grad(st.rays, st.z, st.rps, dlat, grad_cl, ren._bounds)
+    if ren.scatter == "sorted":       # atomics-free, bit-reproducible; the first pass writes every voxel row
+        ops.scatter_volume_grad_sorted(st.rays, st.z, st.rps, dlat, grad_cl, ren._bounds, accumulate=not first)
+    else:                             # fp32 vector reductions into a zeroed volume
+        ops.scatter_volume_grad(st.rays, st.z, st.rps, dlat, grad_cl, ren._bounds)
     return d_z
 
 
@@ -327,7 +331,8 @@ class _ForwardNerfFn(torch.autograd.Function):
         names_c = st_c.mlp.names()
         grads_c = _zero_grads(st_c.mlp)
         grads_f = grads_c if shared or st_f is None else _zero_grads(st_f.mlp)
-        grad_cl = torch.zeros(ctx.vol_shape, device=dev, dtype=torch.float32)
+        alloc = torch.empty if ren.scatter == "sorted" else torch.zeros
+        grad_cl = alloc(ctx.vol_shape, device=dev, dtype=torch.float32)
         _, d_cw, d_crgb, d_cemb, d_cdep = g[:5]
         d_cdep = _zeros_like_or(d_cdep, (R,), dev)
         if st_f is not None:
@@ -343,7 +348,7 @@ class _ForwardNerfFn(torch.autograd.Function):
                 d_cat.scatter_(1, st_f.perm.long(), d_z)
                 d_cdep = d_cdep + (d_cat[:, K - Kfd:] * ctx.depth_mask).sum(-1)
         _pass_backward(ren, st_c, _zeros_like_or(d_crgb, (R, 3), dev), _zeros_like_or(d_cemb, (R, D), dev),
-                       d_cdep, d_cw, grads_c, grad_cl)
+                       d_cdep, d_cw, grads_c, grad_cl, first=st_f is None)
         d_vol = ops.volume_to_channels_first(grad_cl) if ctx.needs_input_grad[1] else None
         pg = [grads_c[n] for n in names_c]
         if not shared and st_f is not None:
@@ -385,6 +390,7 @@ class NeuralRenderer(nn.Module):
         self.lambda_depth = g("lambda_depth", 0.0)
         self.threshold_depth_supervision = g("threshold_depth_supervision", 0.8)
         self.precision = precision
+        self.scatter = "atomic"                # volume-gradient scatter: "atomic" (fast) | "sorted" (atomics-free)
         self.perturb = True
         self.render_chunk_rays = 4096          # neural_rendering.py:482
         self._num_freqs = self.nerf_model.code.num_freqs
@@ -610,7 +616,8 @@ class _CompositeFn(torch.autograd.Function):
         R, D = st.rays.shape[0], ren._d_embed
         names = st.mlp.names()
         grads = _zero_grads(st.mlp)
-        grad_cl = torch.zeros(ctx.vol_shape, device=dev, dtype=torch.float32)
+        alloc = torch.empty if ren.scatter == "sorted" else torch.zeros
+        grad_cl = alloc(ctx.vol_shape, device=dev, dtype=torch.float32)
         d_z = _pass_backward(ren, st, _zeros_like_or(d_rgb, (R, 3), dev), _zeros_like_or(d_emb, (R, D), dev),
                              d_dep, d_w, grads, grad_cl, want_dz=ctx.needs_input_grad[4])
         d_vol = ops.volume_to_channels_first(grad_cl) if ctx.needs_input_grad[2] else None

@@ -155,6 +155,25 @@ def scatter_volume_grad(rays, z, rays_per_scene, dlatent, grad_cl, bounds):
     return grad_cl
 
 
+def scatter_volume_grad_sorted(rays, z, rays_per_scene, dlatent, grad_cl, bounds, accumulate=False):
+    """Atomics-free, bit-reproducible scatter (counting sort by voxel + one warp per voxel)."""
+    rays = _f32(rays, "rays")
+    z = _f32(z, "z")
+    dlatent = _f32(dlatent, "dlatent")
+    assert grad_cl.is_cuda and grad_cl.dtype == torch.float32 and grad_cl.is_contiguous()
+    R, K = z.shape
+    SB, S0, S1, S2, Cc = grad_cl.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.nrf_scatter_sorted_workspace_bytes(R * K, SB, S0 * S1 * S2), device=z.device,
+                     dtype=torch.uint8)
+    bh = _bounds_host(bounds)
+    check(lib.nrf_scatter_volume_grad_sorted(ptr(rays), ptr(z), R, K, rays_per_scene, ptr(dlatent),
+                                             dlatent.shape[1], ptr(grad_cl), SB, Cc, S0, S1, S2,
+                                             C.cast(bh, C.c_void_p), int(accumulate), ptr(ws), stream_ptr()),
+          "nrf_scatter_volume_grad_sorted")
+    return grad_cl
+
+
 # ------------------------------------------------------------------------------- compositing
 def composite_fwd(field_out, z, rays, D, white_bkgd=False):
     """neural_rendering.py:339-359 on RAW MLP outputs (N, 4+D).  -> weights, rgb, embed, depth."""

@@ -323,3 +323,29 @@ def test_gemm_simt_fp32(ops, M, N, K1, K2):
     ops.wgrad(G.cuda(), A1.cuda(), dW, db, precision=ops.NRF_PREC_FP32)
     assert rel(dW, (G.double().t() @ A1.double()).float()) < 1e-6
     assert rel(db, G.sum(0)) < 1e-6
+
+
+def test_scatter_sorted_is_atomics_free_and_reproducible(ops):
+    """Counting-sort scatter: equals the autograd of the gather, bit-identical run to run, accumulate mode."""
+    SB, C, S, R_per, K = 2, 128, 12, 300, 48          # many samples per voxel: long lists, ties, both scenes
+    vol, rays, z = _scene_inputs(SB, C, S, R_per, K, seed=11)
+    vol.requires_grad_(True)
+    pts = (rays[:, None, :3] + z.unsqueeze(2) * rays[:, None, 3:6]).reshape(SB, -1, 3)
+    lat = O.trilinear_gather(vol, O.world_to_canonical(pts, syn.BOUNDS))
+    dl = torch.randn(lat.shape, generator=torch.Generator().manual_seed(9))
+    lat.backward(dl)
+    dlc = dl.reshape(-1, C).cuda()
+    outs = []
+    for _ in range(3):
+        g = torch.full((SB, S, S, S, C), 7.0, device="cuda")         # garbage: every row must be rewritten
+        ops.scatter_volume_grad_sorted(rays.cuda(), z.cuda(), R_per, dlc, g, syn.BOUNDS)
+        outs.append(g)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "must be bit-reproducible"
+    got = ops.volume_to_channels_first(outs[0]).cpu()
+    assert rel(got, vol.grad) < 1e-6
+    g2 = outs[0].clone()
+    ops.scatter_volume_grad_sorted(rays.cuda(), z.cuda(), R_per, dlc, g2, syn.BOUNDS, accumulate=True)
+    assert rel(g2, 2 * outs[0]) < 1e-6
+    ga = torch.zeros(SB, S, S, S, C, device="cuda")
+    ops.scatter_volume_grad(rays.cuda(), z.cuda(), R_per, dlc, ga, syn.BOUNDS)
+    assert rel(ga, outs[0]) < 1e-6

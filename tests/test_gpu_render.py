@@ -228,6 +228,71 @@ def test_forward_loss_dict_and_rendering(ops, NR):
                       voxel_pose=None, focal=focal, tgt_pose=poses, c=None)
 
 
+def test_sorted_scatter_end_to_end_and_separate_fine_mlp(ops, NR):
+    """scatter="sorted" gives the same volume gradient (bit-reproducible run to run); share_mlp=False trains
+    two MLPs (models_embed.py:115-120)."""
+    fx = golden("small_kfd0")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    rays, idx = T(fx["rays"]), T(fx["idx"])
+    gt_rgb = T(fx["gt_rgb_img"]).reshape(ci["SB"], -1, 3)[:, idx]
+    gt_emb = T(fx["gt_embed_img"]).reshape(ci["SB"], -1, ci["D"])[:, idx]
+    ren = make_renderer(NR, meta, ci["params"], "fp32")
+    ren.scatter = "sorted"
+    _, loss, vg1, _ = _run_cuda(ren, T(fx["vol"]), rays, ci["noise"], gt_rgb, gt_emb)
+    for p in ren.parameters():
+        p.grad = None
+    _, _, vg2, _ = _run_cuda(ren, T(fx["vol"]), rays, ci["noise"], gt_rgb, gt_emb)
+    assert rel(vg1, T(fx["vgrad"])) < 2e-4
+    # the volume scatter itself is order-fixed; the MLP weight-gradient reduction still uses fp32 atomics, which
+    # does not feed the volume gradient, so dL/dvoxel is bit-identical run to run
+    assert torch.equal(vg1, vg2)
+    # separate fine MLP with the same weights -> same outputs, gradients split between the two MLPs
+    U = load_pkg("utils")
+    S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
+    cfg = U.default_config(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H, n_coarse=Kc,
+                           n_fine=Kf, n_fine_depth=Kfd, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden),
+                           share_mlp=False)
+    ren2 = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS), precision="fp32")
+    sd = ren2.state_dict()
+    for k, v in ci["params"].items():
+        sd["nerf_model.mlp_coarse." + k].copy_(v)
+        sd["nerf_model.mlp_fine." + k].copy_(v)
+    ren2 = ren2.cuda()
+    assert len(ren2.state_dict()) == 62 and ren2.nerf_model.mlp_fine is not ren2.nerf_model.mlp_coarse
+    out2, loss2, vg3, gc = _run_cuda(ren2, T(fx["vol"]), rays, ci["noise"], gt_rgb, gt_emb)
+    assert abs(float(loss2) - float(fx["loss"])) < 1e-5 and rel(vg3, T(fx["vgrad"])) < 2e-4
+    gf = {k[len("nerf_model.mlp_fine."):]: v.grad for k, v in ren2.named_parameters()
+          if k.startswith("nerf_model.mlp_fine.")}
+    for k in gc:
+        assert rel(gc[k] + gf[k], T(fx["grad." + k])) < 2e-4, k
+
+
+def test_public_composite_with_external_samples(ops, NR):
+    """NeuralRenderer.composite(model, rays, z, coarse, sb) (neural_rendering.py:224) incl. dL/dz."""
+    fx = golden("small_kfd0")
+    ci = _case_inputs(fx)
+    ren = make_renderer(NR, [int(v) for v in fx["meta"]], ci["params"], "fp32")
+    vol = T(fx["vol"])
+    rays = T(fx["rays"]).reshape(-1, 8)
+    zc = T(fx["z_coarse"])
+    volc = vol.clone().cuda().requires_grad_(True)
+    zg = zc.clone().cuda().requires_grad_(True)
+    ren.encode(None, None, None, volc, None, None, None)
+    w, rgb, emb, dep = ren.composite(ren.nerf_model, rays.cuda(), zg, coarse=True, sb=ci["SB"])
+    assert rel(w.reshape(ci["SB"], -1, w.shape[-1]), T(fx["coarse_weights"])) < 1e-4
+    assert rel(rgb.reshape(ci["SB"], -1, 3), T(fx["coarse_rgb"])) < 1e-4
+    (rgb.sum() + emb.sum() * 0.01 + dep.sum()).backward()
+    pv = {k: v.clone().requires_grad_(True) for k, v in ci["params"].items()}
+    vo = vol.clone().requires_grad_(True)
+    zo = zc.clone().requires_grad_(True)
+    wo, ro, eo, do = O.composite(pv, vo, rays, zo, ci["SB"], syn.BOUNDS)
+    (ro.sum() + eo.sum() * 0.01 + do.sum()).backward()
+    assert rel(volc.grad, vo.grad) < 2e-4
+    # dL/dz through deltas and depth only (no gradient reaches the field through the positions, models_embed.py:185)
+    assert rel(zg.grad, zo.grad) < 2e-4
+
+
 def test_cpu_tensors_are_rejected(ops):
     with pytest.raises(Exception):
         ops.sample_coarse(torch.rand(4, 8), 8)
