@@ -116,6 +116,7 @@ def run_ours(args):
     ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS), precision=args.precision)
     syn.init_mlp_(ren.nerf_model.mlp_coarse, seed=0)
     ren = ren.to(dev).train()
+    ren.scatter = args.scatter
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     vol = (torch.randn(SB, wl.C, wl.S, wl.S, wl.S, device=dev, generator=g) * 0.1).requires_grad_(True)
     # host-side inputs of a training step (what the data loader hands over), pinned
@@ -206,7 +207,7 @@ def run_ours(args):
             "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
             "config": {"workload": f"{wl.name}: per GPU {SB} scenes x {n_rays} rays, {wl.n_coarse}+{wl.n_fine} samples, "
                                    f"{wl.S}^3 x {wl.C}ch volume, ResnetFC 512x5, RGB+{wl.D}d heads, fwd+bwd",
-                       "evals_per_step": evals_step, "precision": args.precision,
+                       "evals_per_step": evals_step, "precision": args.precision, "scatter": args.scatter,
                        "l2": "working set (1 GiB volume + ~20 GiB activations per step) >> 126 MB L2; no flush needed",
                        "parallelism": f"dp{world} over scenes; NCCL all-reduce of MLP grads" if world > 1 else "single GPU"},
             "e2e": {"value": round(e2e_value, 1), "unit": "ray-samples/s", "ms_per_step": round(ms_e2e / args.steps, 3),
@@ -300,6 +301,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=128, dest="cpu_rays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scatter", default="sorted", choices=["atomic", "sorted"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -390,7 +390,7 @@ class NeuralRenderer(nn.Module):
         self.lambda_depth = g("lambda_depth", 0.0)
         self.threshold_depth_supervision = g("threshold_depth_supervision", 0.8)
         self.precision = precision
-        self.scatter = "atomic"                # volume-gradient scatter: "atomic" (fast) | "sorted" (atomics-free)
+        self.scatter = "sorted"                # volume-gradient scatter: "sorted" (atomics-free, default) | "atomic"
         self.perturb = True
         self.render_chunk_rays = 4096          # neural_rendering.py:482
         self._num_freqs = self.nerf_model.code.num_freqs
