@@ -102,7 +102,8 @@ extern "C" int nrf_gemm(const NrfGemm* g, int precision, void* stream) {
 
 extern "C" int64_t nrf_wgrad_workspace_bytes(int N, int K) {
   (void)N; (void)K;
-  return 0;   // partial tiles are reduced with fp32 red.global.add; no workspace needed
+  // (output tiles) x (sample splits) <= #SMs; a split's partial tile is 128 x (256 + 1 bias column) fp32
+  return (int64_t)sm_count() * 128 * (256 + 8) * 4 + 4096;
 }
 
 extern "C" int nrf_wgrad(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,

@@ -556,7 +556,7 @@ template <int BK_>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA, int M,
                 int k_tiles, int m_per_split, int n_valid, int k_valid, float* __restrict__ dW, int ldw,
-                float* __restrict__ dbias) {
+                float* __restrict__ dbias, float* __restrict__ ws, int n_pad, int k_pad) {
   using Cfg = WgCfg<BK_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -649,7 +649,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
         if (k0 >= k_valid) break;
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
-        if (n < n_valid) {
+        if (ws) {
+          // deterministic mode: this split's partial tile goes to the workspace; wgrad_reduce_kernel adds the
+          // splits up in a fixed order
+          float4* dst = reinterpret_cast<float4*>(ws + ((int64_t)blockIdx.y * n_pad + n) * k_pad + k0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        } else if (n < n_valid) {
           float* dst = dW + (int64_t)n * ldw + k0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -659,7 +667,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
       if (do_bias) {                              // column BK_ of the accumulator: sum over the samples of G[:, n]
         uint32_t v[32];
         tmem_ld32(taddr + BK_, v);
-        if (n < n_valid) atomicAdd(dbias + n, __uint_as_float(v[0]));
+        if (ws) ws[(int64_t)gridDim.y * n_pad * k_pad + (int64_t)blockIdx.y * n_pad + n] = __uint_as_float(v[0]);
+        else if (n < n_valid) atomicAdd(dbias + n, __uint_as_float(v[0]));
       }
     }
   }
@@ -668,6 +677,35 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// dW[n,k] += sum over splits (ascending) of the partial tiles; dbias likewise.  One thread per 4 columns.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int n_pad,
+                                                           int k_pad, int n_valid, int k_valid,
+                                                           float* __restrict__ dW, int ldw, float* __restrict__ dbias) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int kq = (k_valid + 3) / 4;
+  if (t < (int64_t)n_valid * kq) {
+    int n = (int)(t / kq), k = (int)(t % kq) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      float4 p = *reinterpret_cast<const float4*>(ws + ((int64_t)s * n_pad + n) * k_pad + k);
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    float* dst = dW + (int64_t)n * ldw + k;
+    dst[0] += acc.x;
+    if (k + 1 < k_valid) dst[1] += acc.y;
+    if (k + 2 < k_valid) dst[2] += acc.z;
+    if (k + 3 < k_valid) dst[3] += acc.w;
+  } else if (dbias) {
+    int64_t n = t - (int64_t)n_valid * kq;
+    if (n < n_valid) {
+      const float* wb = ws + (int64_t)splits * n_pad * k_pad;
+      float acc = 0.f;
+      for (int s = 0; s < splits; ++s) acc += wb[(int64_t)s * n_pad + n];
+      dbias[n] += acc;
+    }
   }
 }
 
@@ -821,7 +859,7 @@ int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream) {
 
 template <int BK_>
 static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
-                        int k_valid, float* dW, int ldw, float* dbias, cudaStream_t stream) {
+                        int k_valid, float* dW, int ldw, float* dbias, void* workspace, cudaStream_t stream) {
   using Cfg = WgCfg<BK_>;
   CUtensorMap tmG, tmA;
   int rc = make_map(&tmG, G, N, M, ldg, 64, kTileK);
@@ -843,22 +881,31 @@ static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, i
   int m_per = ((M + splits - 1) / splits + kTileK - 1) / kTileK * kTileK;
   splits = (M + m_per - 1) / m_per;
   dim3 grid(out_tiles, splits);
+  const int n_pad = n_tiles * kTileM, k_pad = k_tiles * BK_;
+  float* ws = reinterpret_cast<float*>(workspace);
   { LaunchScope ls_(NRF_CAT_WGRAD, stream);
   wgrad_tc_kernel<BK_><<<grid, kThreads, Cfg::kSmem, stream>>>(tmG, tmA, M, k_tiles, m_per, n_valid, k_valid,
-                                                               dW, ldw, dbias);
+                                                               dW, ldw, dbias, ws, n_pad, k_pad);
   }
   NRF_LAUNCH_OK();
+  if (ws) {
+    int64_t work = (int64_t)n_valid * ((k_valid + 3) / 4) + (dbias ? n_valid : 0);
+    { LaunchScope ls_(NRF_CAT_WGRAD, stream);
+    wgrad_reduce_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(ws, splits, n_pad, k_pad, n_valid, k_valid,
+                                                                           dW, ldw, dbias);
+    }
+    NRF_LAUNCH_OK();
+  }
   return NRF_OK;
 }
 
 int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
                     int k_valid, float* dW, int ldw, float* dbias, void* workspace, cudaStream_t stream) {
-  (void)workspace;
   NRF_REQUIRE(N % 64 == 0 && K % 64 == 0, NRF_ENOSUP, "wgrad_tc: N=%d, K=%d must be multiples of 64", N, K);
   int rc;
-  if (k_valid > 128) rc = launch_wgrad<256>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, stream);
-  else if (k_valid > 64) rc = launch_wgrad<128>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, stream);
-  else rc = launch_wgrad<64>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, stream);
+  if (k_valid > 128) rc = launch_wgrad<256>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
+  else if (k_valid > 64) rc = launch_wgrad<128>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
+  else rc = launch_wgrad<64>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
   return rc;
 }
 

@@ -157,11 +157,12 @@ static int run_gemm(const NrfGemm& g, int precision, cudaStream_t s) {
 }
 
 // dW += G^T A and (fused, from the same G tiles) dbias += column sums of G.
+// `ws`: split-reduction workspace (deterministic mode of the tensor-core kernel), may be NULL.
 static int run_wgrad(const void* G, int ldg, const void* A, int lda, int64_t M, int N, int K, int n_valid,
-                     int k_valid, float* dW, int ldw, float* dbias, int precision, cudaStream_t s) {
+                     int k_valid, float* dW, int ldw, float* dbias, void* ws, int precision, cudaStream_t s) {
   if (!dW) return NRF_OK;
   return precision == NRF_PREC_BF16
-             ? wgrad_tc_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, dbias, nullptr, s)
+             ? wgrad_tc_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, dbias, ws, s)
              : wgrad_simt_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, dbias, s);
 }
 
@@ -179,7 +180,7 @@ extern "C" int nrf_mlp_sizes(const NrfMlpParams* p, int precision, NrfMlpSizes* 
   out->packed_bytes = L.total;
   out->fwd_bytes_per_sample = (int64_t)(2 * L.nb + 2) * L.H * L.es;
   out->bwd_bytes_per_sample = (int64_t)(2 + L.nz) * L.H * L.es;
-  out->bwd_fixed_bytes = (int64_t)round_up((L.H > L.dout_pad ? L.H : L.dout_pad) * 4, 1024);
+  out->bwd_fixed_bytes = (int64_t)round_up(nrf_wgrad_workspace_bytes(L.H, L.H), 1024);
   return NRF_OK;
 }
 
@@ -264,7 +265,8 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
   auto ax = [&](int b) { return act + (int64_t)b * layer; };
   auto an = [&](int b) { return act + (int64_t)(L.nb + 1 + b) * layer; };
   char* sc = reinterpret_cast<char*>(scratch);
-  int64_t fixed = round_up((L.H > L.dout_pad ? L.H : L.dout_pad) * 4, 1024);
+  int64_t fixed = round_up(nrf_wgrad_workspace_bytes(L.H, L.H), 1024);
+  void* wws = sc;                             // per-split partial tiles of the weight gradients (ordered reduce)
   char* gbuf = sc + fixed;                    // dL/dx, updated in place while b >= n_lin_z
   char* dnet = gbuf + layer;
   auto gz = [&](int b) { return dnet + (int64_t)(1 + b) * layer; };   // dL/dx'_b kept for dL/dz, b < n_lin_z
@@ -272,7 +274,7 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
 
   // lin_out: parameter gradients, then the gradient of x_nb (ReLU-gated by relu(x_nb) > 0)
   TRY(run_wgrad(d_field, L.dout_pad, ax(L.nb), L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H,
-                gr->lin_out_b, precision, s));
+                gr->lin_out_b, wws, precision, s));
   NrfGemm g = gemm_init(N, L.H, L.H);
   set_a(g, 0, d_field, L.dout_pad, L.dout_pad);
   g.B = W + L.WoutT; g.ldb = L.dout_pad;
@@ -283,10 +285,10 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
   const char* gcur = gbuf;                    // dL/dx_{b+1}
   for (int b = L.nb - 1; b >= 0; --b) {
     bool cat = b + 1 < L.nz;
-    TRY(run_wgrad(gcur, L.H, an(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc1_w[b], L.H, gr->fc1_b[b], precision, s));
+    TRY(run_wgrad(gcur, L.H, an(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc1_w[b], L.H, gr->fc1_b[b], wws, precision, s));
     if (cat)
       TRY(run_wgrad(gcur, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[b + 1], L.C,
-                    gr->lin_z_b[b + 1], precision, s));
+                    gr->lin_z_b[b + 1], wws, precision, s));
     // dnet_b = (g . W_fc1[b]) gated by relu(net_b) > 0
     g = gemm_init(N, L.H, L.H);
     set_a(g, 0, gcur, L.H, L.H);
@@ -294,7 +296,7 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
     g.mask_src = an(b); g.ldmask = L.H;
     g.out_act = dnet; g.ldact = L.H;
     TRY(run_gemm(g, precision, s));
-    TRY(run_wgrad(dnet, L.H, ax(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc0_w[b], L.H, gr->fc0_b[b], precision, s));
+    TRY(run_wgrad(dnet, L.H, ax(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc0_w[b], L.H, gr->fc0_b[b], wws, precision, s));
     // dL/dx'_b = dL/dx_{b+1} + (dnet_b . W_fc0[b]) gated by relu(x'_b) > 0
     char* target = b < L.nz ? gz(b) : gbuf;
     g = gemm_init(N, L.H, L.H);
@@ -323,9 +325,9 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
   // first layer: x'_0 = [z | p] . [W_z0 | W_in]^T ; gcur = dL/dx'_0
   if (L.nz > 0)
     TRY(run_wgrad(gcur, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[0], L.C,
-                  gr->lin_z_b[0], precision, s));
+                  gr->lin_z_b[0], wws, precision, s));
   TRY(run_wgrad(gcur, L.H, fin + (int64_t)L.C * L.es, L.kin_pad, N, L.H, L.kin_pad - L.C, L.H, L.Din, gr->lin_in_w,
-                L.Din, gr->lin_in_b, precision, s));
+                L.Din, gr->lin_in_b, wws, precision, s));
 #undef TRY
   return NRF_OK;
 }

@@ -240,13 +240,18 @@ def gemm(A1, B, *, A2=None, A3=None, bias=None, mask_src=None, resid=None, out_f
     check(_lib.load().nrf_gemm(C.byref(g), precision, stream_ptr()), "nrf_gemm")
 
 
-def wgrad(G, A, dW, dbias=None, n_valid=None, k_valid=None, precision=NRF_PREC_BF16):
-    """dW (n_valid,k_valid) += G^T.A ; dbias += colsum(G)."""
+def wgrad(G, A, dW, dbias=None, n_valid=None, k_valid=None, precision=NRF_PREC_BF16, deterministic=False):
+    """dW (n_valid,k_valid) += G^T.A ; dbias += colsum(G).  deterministic: ordered reduction of the sample splits
+    through a workspace instead of fp32 atomics."""
     M, N = G.shape
     K = A.shape[1]
-    check(_lib.load().nrf_wgrad(ptr(G), G.stride(0), ptr(A), A.stride(0), M, N, K,
-                                n_valid if n_valid is not None else N, k_valid if k_valid is not None else K,
-                                ptr(dW), dW.stride(0), ptr(dbias), None, precision, stream_ptr()), "nrf_wgrad")
+    lib = _lib.load()
+    ws = None
+    if deterministic:
+        ws = torch.empty(lib.nrf_wgrad_workspace_bytes(N, K), device=G.device, dtype=torch.uint8)
+    check(lib.nrf_wgrad(ptr(G), G.stride(0), ptr(A), A.stride(0), M, N, K,
+                        n_valid if n_valid is not None else N, k_valid if k_valid is not None else K,
+                        ptr(dW), dW.stride(0), ptr(dbias), ptr(ws), precision, stream_ptr()), "nrf_wgrad")
 
 
 # --------------------------------------------------------------------------------------- MLP

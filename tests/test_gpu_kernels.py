@@ -296,6 +296,15 @@ def test_wgrad_tc(ops, M, N, K, nv, kv):
     want = (G.float().t() @ A.float())[:nv, :kv] + 1.0
     assert rel(dW, want) < 5e-6
     assert rel(db, G.float().sum(0)[:nv] + 1.0) < 5e-6
+    # deterministic mode: ordered reduction of the sample splits, bit-identical run to run
+    outs = []
+    for _ in range(2):
+        dW2 = torch.ones(nv, kv, device="cuda")
+        db2 = torch.ones(nv, device="cuda")
+        ops.wgrad(G.cuda(), A.cuda(), dW2, db2, n_valid=nv, k_valid=kv, deterministic=True)
+        outs.append((dW2, db2))
+    assert rel(outs[0][0], want) < 5e-6 and rel(outs[0][1], G.float().sum(0)[:nv] + 1.0) < 5e-6
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
 @pytest.mark.parametrize("M,N,K1,K2", [(100, 64, 58, 0), (513, 388, 512, 0), (300, 512, 512, 128), (65, 70, 33, 16)])
