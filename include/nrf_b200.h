@@ -188,12 +188,18 @@ int nrf_mlp_sizes(const NrfMlpParams* p, int precision, NrfMlpSizes* out);
 /* Packs the fp32 parameters into the operand layout the GEMMs read ([W_z0 | W_in] etc.). */
 int nrf_mlp_pack(const NrfMlpParams* p, int precision, void* packed, void* stream);
 
-/* Forward over N samples.  field_in (N,kin_pad) operand-typed; acts: fwd_bytes_per_sample*N bytes
- * (kept for the backward; with keep_acts == 0 only 2 ping-pong layers are needed and the caller
- * may pass a buffer of nrf_mlp_sizes().fwd_bytes_per_sample*N bytes anyway);
- * field_out (N,d_out) fp32 raw outputs. */
+/* Forward over N samples.  field_in (N,kin_pad) operand-typed; field_out (N,d_out) fp32 raw outputs.
+ * acts: fwd_bytes_per_sample*N bytes, the operands kept for the backward: relu(x'_b) (b = 0..n_blocks), then
+ * relu(net_b) (b < n_blocks), each (N,d_hidden) operand-typed, then one layer of scratch.
+ * bf16 mode, when nrf_mlp_fused_supported(): ONE persistent tcgen05 kernel runs all layers per 256-sample tile
+ * (csrc/mlp_fused.cu: activations never leave the SM; `acts` is written as a side effect and may be NULL for
+ * inference, in which case nothing but field_out is written).  Otherwise a chain of fused-epilogue GEMMs, one
+ * per layer (acts required).  nrf_mlp_fwd_layered always runs the chain (A/B timing, parity tests). */
+int nrf_mlp_fused_supported(const NrfMlpParams* p, int precision);
 int nrf_mlp_fwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
                 int64_t N, void* acts, float* field_out, void* stream);
+int nrf_mlp_fwd_layered(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                        int64_t N, void* acts, float* field_out, void* stream);
 
 /* Backward: d_field (N,dout_pad) operand-typed gradient of the raw outputs (from
  * nrf_composite_bwd); accumulates parameter gradients into `grads` and writes
@@ -218,7 +224,9 @@ int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precision, const 
 #define NRF_CAT_SAMPLING 8    /* raygen, coarse / fine sampling, sort             */
 #define NRF_CAT_SIMT 9        /* fp32 parity-mode GEMMs                           */
 #define NRF_CAT_MISC 10       /* weight packing, small vector kernels             */
-#define NRF_TIMING_CATEGORIES 11
+#define NRF_CAT_FUSED_FWD 11  /* whole-MLP fused forward kernel (mlp_fused_fwd_kernel) */
+#define NRF_CAT_FUSED_BWD 12  /* whole-MLP fused dgrad kernel                           */
+#define NRF_TIMING_CATEGORIES 13
 int64_t nrf_launch_count(void);
 int nrf_timing_begin(void);
 int nrf_timing_end(double* ms, int64_t* launches);

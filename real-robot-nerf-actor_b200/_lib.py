@@ -71,6 +71,8 @@ _SIGNATURES = {
     "nrf_mlp_sizes": [C.POINTER(NrfMlpParams), _i, C.POINTER(NrfMlpSizes)],
     "nrf_mlp_pack": [C.POINTER(NrfMlpParams), _i, _p, _p],
     "nrf_mlp_fwd": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, _p],
+    "nrf_mlp_fwd_layered": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, _p],
+    "nrf_mlp_fused_supported": [C.POINTER(NrfMlpParams), _i],
     "nrf_mlp_bwd": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, C.POINTER(NrfMlpGrads), _p, _p, _p],
 }
 _SIGNATURES["nrf_scatter_volume_grad_sorted"] = [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p]
@@ -79,7 +81,7 @@ _SIGNATURES["nrf_timing_end"] = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
 EXPORTS = sorted(list(_SIGNATURES) + ["nrf_version", "nrf_last_error", "nrf_wgrad_workspace_bytes",
                                       "nrf_launch_count", "nrf_scatter_sorted_workspace_bytes"])
 TIMING_CATEGORIES = ["gemm_tc", "wgrad_tc", "encode", "composite_fwd", "composite_bwd", "scatter", "transpose",
-                     "colsum", "sampling", "simt", "misc"]
+                     "colsum", "sampling", "simt", "misc", "fused_fwd", "fused_bwd"]
 
 _lib = None
 

@@ -35,6 +35,28 @@ static inline Epilogue<T> make_epilogue(const NrfGemm& g) {
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+// ---- whole-MLP fused kernel (mlp_fused.cu): layer program built by mlp.cu
+constexpr int kFusedMaxLayers = 2 * NRF_MAX_BLOCKS + 2;
+struct FusedLayerDesc {
+  const void* W;       // (512, ldw) bf16 row-major, K = 64 * (kb_main + kb_z) columns used
+  int ldw;
+  int kb_main, kb_z;   // 64-wide k-blocks of the main operand / of the trailing latent part
+  int kind;            // 0: residual-stream layer (lin_in, fc_1)   1: fc_0   2: lin_out
+  int a_src;           // 0: field-input tile   1: relu(x') in TMEM   2: relu(net) in shared memory
+  int first;           // residual-stream layer that starts the stream (no residual added)
+  int act_slot;        // slot of the saved operand in `acts` (training), -1: nothing to save
+  const float* bias;
+};
+struct FusedFwdDesc {
+  int n_layers;
+  FusedLayerDesc L[kFusedMaxLayers];
+  const void* field_in; int kin_pad; int kb_lat;
+  int64_t N;
+  void* acts; int n_slots;     // acts: n_slots x (N, 512) bf16, NULL = inference (nothing kept)
+  float* out; int d_out; int ldo;
+};
+int mlp_fused_fwd_launch(const FusedFwdDesc& d, cudaStream_t stream);
+
 int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream);
 int gemm_simt_launch(const NrfGemm& g, cudaStream_t stream);
 int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,

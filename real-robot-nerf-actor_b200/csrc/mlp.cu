@@ -15,6 +15,7 @@
 //   dW_fc1 += g^T relu(net_b);  dnet = (g . W_fc1) gated by net_b > 0;  dW_fc0 += dnet^T relu(x'_b)
 //   g <- g + (dnet . W_fc0) gated by x'_b > 0        (kept per block b < n_lin_z for dL/dz)
 //   dL/dz = [g'_0 | g'_1 | g'_2] . [W_z0 ; W_z1 ; W_z2]                       one GEMM, K = 3 H
+#include <stdlib.h>
 #include <string.h>
 #include "gemm_common.cuh"
 
@@ -193,15 +194,60 @@ extern "C" int nrf_mlp_pack(const NrfMlpParams* p, int precision, void* packed, 
                                     : pack_all<float>(p, L, packed, as_stream(stream));
 }
 
-extern "C" int nrf_mlp_fwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
-                           int64_t N, void* acts, float* field_out, void* stream) {
-  NRF_REQUIRE(packed && field_in && acts && field_out && N > 0, NRF_EINVAL, "nrf_mlp_fwd: bad arguments");
+// The fused kernel is built for the reference's field MLP: 512 hidden units, a latent of 64 or 128 channels that
+// fills whole k-blocks, PE + viewdir in one k-block.  Anything else runs the layer-by-layer chain below.
+static bool fused_supported(const MlpLayout& L) {
+  return L.H == 512 && L.es == 2 && (L.C == 64 || L.C == 128) && L.kin_pad == L.C + 64 && L.nz >= 1 &&
+         L.nout_pad <= 512 && 2 * L.nb + 2 <= kFusedMaxLayers;
+}
+
+static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* W, const void* field_in, int64_t N,
+                         void* acts, float* field_out, cudaStream_t s) {
+  FusedFwdDesc d;
+  memset(&d, 0, sizeof(d));
+  const int kbH = L.H / 64, kbC = L.C / 64;
+  int l = 0;
+  auto add = [&](const void* Wl, int ldw, int kb_main, int kb_z, int kind, int a_src, int first, int slot,
+                 const float* bias) {
+    FusedLayerDesc& f = d.L[l++];
+    f.W = Wl; f.ldw = ldw; f.kb_main = kb_main; f.kb_z = kb_z; f.kind = kind; f.a_src = a_src; f.first = first;
+    f.act_slot = slot; f.bias = bias;
+  };
+  // slots of `acts`: relu(x'_b) at b, relu(net_b) at nb + 1 + b (the layout nrf_mlp_bwd reads)
+  add(W + L.W0, L.kin_pad, kbC + 1, 0, 0, 0, 1, 0, reinterpret_cast<const float*>(W + L.bias0));
+  for (int b = 0; b < L.nb; ++b) {
+    add(W + L.Wfc0[b], L.H, kbH, 0, 1, 1, 0, L.nb + 1 + b, p->fc0_b[b]);
+    add(W + L.Wfc1[b], L.k1cat[b], kbH, (b + 1 < L.nz) ? kbC : 0, 0, 2, 0, b + 1,
+        reinterpret_cast<const float*>(W + L.bias1[b]));
+  }
+  add(W + L.Wout, L.H, kbH, 0, 2, 1, 0, -1, reinterpret_cast<const float*>(W + L.bias_out));
+  d.n_layers = l;
+  d.field_in = field_in; d.kin_pad = L.kin_pad; d.kb_lat = kbC;
+  d.N = N;
+  d.acts = acts; d.n_slots = 2 * L.nb + 1;
+  d.out = field_out; d.d_out = L.Dout; d.ldo = L.Dout;
+  return mlp_fused_fwd_launch(d, s);
+}
+
+extern "C" int nrf_mlp_fused_supported(const NrfMlpParams* p, int precision) {
+  MlpLayout L;
+  if (make_layout(p, precision, &L)) return 0;
+  return precision == NRF_PREC_BF16 && fused_supported(L) ? 1 : 0;
+}
+
+static int mlp_fwd_impl(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                        int64_t N, void* acts, float* field_out, void* stream, bool allow_fused) {
+  NRF_REQUIRE(packed && field_in && field_out && N > 0, NRF_EINVAL, "nrf_mlp_fwd: bad arguments");
   NRF_REQUIRE(N < (int64_t)1 << 31, NRF_ENOSUP, "nrf_mlp_fwd: N too large for one call");
   MlpLayout L;
   int rc = make_layout(p, precision, &L);
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
   const char* W = reinterpret_cast<const char*>(packed);
+  static const bool layered = getenv("NRF_MLP_LAYERED") != nullptr;
+  if (allow_fused && precision == NRF_PREC_BF16 && fused_supported(L) && !layered)
+    return mlp_fwd_fused(p, L, W, field_in, N, acts, field_out, s);
+  NRF_REQUIRE(acts, NRF_EINVAL, "nrf_mlp_fwd: the layer-by-layer chain needs the activation buffer");
   char* act = reinterpret_cast<char*>(acts);
   const int64_t layer = N * L.H * (int64_t)L.es;
   auto ax = [&](int b) { return act + (int64_t)b * layer; };                 // relu(x'_b), b = 0..nb
@@ -245,6 +291,16 @@ extern "C" int nrf_mlp_fwd(const NrfMlpParams* p, const void* packed, int precis
   g.bias = reinterpret_cast<const float*>(W + L.bias_out);
   g.out_f32 = field_out; g.ldo = L.Dout;
   return run_gemm(g, precision, s);
+}
+
+extern "C" int nrf_mlp_fwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                           int64_t N, void* acts, float* field_out, void* stream) {
+  return mlp_fwd_impl(p, packed, precision, field_in, N, acts, field_out, stream, true);
+}
+
+extern "C" int nrf_mlp_fwd_layered(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                                   int64_t N, void* acts, float* field_out, void* stream) {
+  return mlp_fwd_impl(p, packed, precision, field_in, N, acts, field_out, stream, false);
 }
 
 extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,

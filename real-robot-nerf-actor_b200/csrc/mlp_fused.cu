@@ -1,0 +1,516 @@
+// The whole ResnetFC field MLP (resnetfc.py:55-64,146-195) as ONE persistent tcgen05 kernel per sample tile.
+//
+// A CTA pair (cluster of 2, one TPC) owns 256 samples (128 per CTA) and walks them through every layer without
+// touching HBM in between: only the field-input rows come in, the raw field outputs go out and - in training -
+// the bf16 operands the backward needs (relu(x'_b), relu(net_b)) are streamed out by TMA stores as a side effect.
+//
+// Where everything lives (per CTA; the MMAs are tcgen05.mma.cta_group::2, M = 256, N = 128, K = 16):
+//   weights        stream from L2 through a TMA ring of 8 KB stages (this CTA's 64 of the 128 weight rows x 64 k);
+//                  the pair shares every weight byte, so the L2 -> SM weight traffic is 32 B/clk/SM at full rate
+//   accumulators   TMEM columns [0,256): two 128-column buffers; the epilogue of chunk i overlaps the MMAs of i+1
+//   relu(x')       TMEM columns [256,512) as packed bf16 pairs: the A operand of fc_0 and lin_out comes straight
+//                  from tensor memory (tcgen05.mma with A in TMEM), written by the epilogue with tcgen05.st
+//   relu(net)      shared memory "P": 8 k-panels of 128 rows x 64 bf16 (128B-swizzled UMMA layout), the A operand
+//                  of fc_1, written by the epilogue with st.shared; in training the same panels are the source of
+//                  the TMA stores of relu(net_b)
+//   latent z       shared memory "Z": the first kb_lat k-panels of the field-input tile; read three times
+//                  (lin_in|lin_z[0], and the lin_z[b+1] tails of fc_1); the PE|viewdir panel borrows P panel 0
+//   residual x'    REGISTERS of the epilogue threads: thread (row, warpgroup g) keeps its 256 elements of the bf16
+//                  residual stream as 128 packed registers for the whole tile (setmaxnreg gives the epilogue
+//                  warpgroups 232 registers, the service warps 40)
+// Ping-ponging the operand between TMEM and shared memory removes every write-after-read hazard between a layer's
+// MMAs and its own epilogue, so the next layer's MMAs start on k-block kb as soon as the epilogue has published it
+// (a_ready[kb]) and the tensor pipe never drains between layers.
+//
+// Warp roles: 0 weight TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator | 3 field-input loader |
+// 4-7, 8-11 two epilogue warpgroups (warpgroup g owns columns [64g, 64g+64) of every 128-column chunk = k-block 2c+g
+// of the next layer).
+#include "tc_ptx.cuh"
+
+namespace nrf {
+
+namespace {
+
+constexpr int kFThreads = 384;
+constexpr int kFPanel = 128 * 64 * 2;        // 16 KB: 128 rows x 64 bf16, 128B swizzle
+constexpr int kFBoxB = 64 * 64 * 2;          // 8 KB: this CTA's 64 weight rows x 64 k
+constexpr int kFStageB = 2 * kFBoxB;         // a ring stage carries two k-blocks (8 MMAs per barrier round trip)
+constexpr int kFChunks = 4;                  // 512 / 128 accumulator chunks per layer
+constexpr int kFSmemP = 8 * kFPanel;         // 128 KB
+constexpr int kFSmemZ = 2 * kFPanel;         // 32 KB
+constexpr int kFSlot = 32 * 64;              // 2 KB: 32 rows x 32 bf16 (64B swizzle), one per epilogue warp
+constexpr int kFSmemBar = 256;
+constexpr int kFSmemBias = 8 * 256;          // per epilogue warp: the 64 bias values of its current chunk
+constexpr int kFAlignSlack = 768;            // dynamic shared memory starts 1024-aligned in practice (checked)
+template <bool kTrain>
+struct FCfg {
+  static constexpr int kStages = kTrain ? 3 : 4;     // training gives one stage up for the relu(x') staging slots
+  static constexpr int kRing = kStages * kFStageB;
+  static constexpr int kStaging = kTrain ? 8 * kFSlot : 0;
+  static constexpr int kSmem = kFSmemP + kFSmemZ + kRing + kStaging + kFSmemBar + kFSmemBias + kFAlignSlack;
+  static_assert(kSmem <= 232448, "fused MLP kernel exceeds the 227 KB shared-memory limit");
+};
+constexpr uint32_t kFColQ = 256;             // first TMEM column of the packed relu(x') operand
+
+enum { kLayerX = 0, kLayerNet = 1, kLayerOut = 2 };
+enum { kSrcIn = 0, kSrcQ = 1, kSrcP = 2 };
+
+struct FLayer {
+  int kind, a_src, kb_main, kb_z, first, act_slot;
+  const float* bias;
+};
+struct FArgs {
+  int n_layers, n_tiles, kb_lat, train;
+  int N, d_out, ldo;
+  int dbg;      // NRF_DBG timing experiments (wrong results!): 1 no weight TMA, 2 epilogue protocol only, 4 no MMAs,
+                // 8 MMA issuer ignores acc_empty / a_ready
+  float* out;
+  FLayer L[kFusedMaxLayers];
+};
+struct FMaps {
+  CUtensorMap w[kFusedMaxLayers];
+  CUtensorMap in;
+  CUtensorMap acts;      // (512, N, slots) bf16, box 64 x 32 x 1, 128B swizzle: relu(net_b) straight from the P panels
+  CUtensorMap acts32;    // same tensor, box 32 x 32 x 1, 64B swizzle: relu(x'_b) from the per-warp staging slots
+};
+
+__device__ __forceinline__ void umma_bf16_pair_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Long waits (a whole tile): let the hardware park the warp instead of re-polling every few hundred cycles.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(100000u)
+        : "memory");
+    if (spin > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// packed fp32 pairs (sm_100 add.f32x2: two IEEE rn additions per instruction) and packed bf16 ReLU
+__device__ __forceinline__ uint64_t pair_u32(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pair_f32(float lo, float hi) {
+  return pair_u32(__float_as_uint(lo), __float_as_uint(hi));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t x, uint64_t y) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {     // {lo, hi} fp32 -> packed bf16 (lo in bits 0-15)
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t w) {    // bf16(relu(x)) == relu(bf16(x))
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(w), "r"(0u));
+  return r;
+}
+
+template <bool kTrain>
+__global__ void __launch_bounds__(kFThreads, 1)
+mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FArgs a) {
+  using Cfg = FCfg<kTrain>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sP = smem;
+  uint8_t* sZ = sP + kFSmemP;
+  uint8_t* sRing = sZ + kFSmemZ;
+  uint8_t* sStage = sRing + Cfg::kRing;
+  float* sBias = reinterpret_cast<float*>(sStage + Cfg::kStaging);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sStage + Cfg::kStaging + kFSmemBias);
+  if (smem - smem_raw > kFAlignSlack) __trap();
+  uint64_t* empty = full + kStages;
+  uint64_t* acc_full = empty + kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* a_ready = acc_empty + 2;           // 8: k-block kb of the next layer's A operand is in place
+  uint64_t* in_full = a_ready + 8;
+  uint64_t* in_free = in_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_free + 1);
+
+  const int warp = uniform_warp_idx();
+  int lane;                                      // volatile: kept in a register, never re-read with S2R in the loops
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const bool cta_leader = crank == 0;
+  const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
+  const int n_iter = pair < a.n_tiles ? (a.n_tiles - pair + n_pairs - 1) / n_pairs : 0;
+  const int nl = a.n_layers;
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < nl; ++l) tma_prefetch_desc(&maps.w[l]);
+    tma_prefetch_desc(&maps.in);
+    if (kTrain) { tma_prefetch_desc(&maps.acts); tma_prefetch_desc(&maps.acts32); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 2); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 16); }
+    for (int s = 0; s < 8; ++s) mbar_init(a_ready + s, 8);
+    mbar_init(in_full, 2);
+    mbar_init(in_free, 5);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ---- weight producer: runs ahead of the MMAs by the depth of the ring, across layers and tiles
+      PipeState st;
+      for (int it = 0; it < n_iter; ++it)
+        for (int l = 0; l < nl; ++l) {
+          const int kb_tot = a.L[l].kb_main + a.L[l].kb_z;
+          for (int c = 0; c < kFChunks; ++c)
+            for (int kb = 0; kb < kb_tot; kb += 2) {
+              if (a.dbg & 1) continue;
+              const int nk = kb_tot - kb < 2 ? 1 : 2;
+              mbar_wait(empty + st.stage, st.phase ^ 1);
+              if (elect_one()) {
+                if (cta_leader) mbar_expect_tx(full + st.stage, 2 * nk * kFBoxB);
+                else mbar_arrive_leader(full + st.stage);
+                uint8_t* dst = sRing + st.stage * kFStageB;
+                const int wrow = c * 128 + (int)crank * 64;
+                tma_load_2d_pair(dst, &maps.w[l], full + st.stage, kb * 64, wrow);
+                if (nk == 2) tma_load_2d_pair(dst + kFBoxB, &maps.w[l], full + st.stage, kb * 64 + 64, wrow);
+              }
+              __syncwarp();
+              st.advance(kStages);
+            }
+        }
+    } else if (warp == 3 && lane == 0) {
+      // ---- field-input loader: latent panels -> Z, PE|viewdir panel -> P panel 0 (dead until fc_0's epilogue)
+      for (int it = 0; it < n_iter; ++it) {
+        if (it > 0) mbar_wait_parked(in_free, (it - 1) & 1);
+        const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
+        if (cta_leader) mbar_expect_tx(in_full, 2 * (a.kb_lat + 1) * kFPanel);
+        else mbar_arrive_leader(in_full);
+        for (int kb = 0; kb < a.kb_lat; ++kb) tma_load_2d_pair(sZ + kb * kFPanel, &maps.in, in_full, kb * 64, row0);
+        tma_load_2d_pair(sP, &maps.in, in_full, a.kb_lat * 64, row0);
+      }
+    } else if (warp == 1 && cta_leader) {
+      // ---- MMA issuer for the pair: the whole warp runs the loop (uniform control flow), one elected lane issues
+      constexpr uint32_t idesc = make_idesc(256, 128, 0, 0);
+      const uint32_t sP_u = smem_u32(sP), sZ_u = smem_u32(sZ), sRing_u = smem_u32(sRing);
+      PipeState st;
+      uint32_t n = 0;                              // running chunk counter -> accumulator buffer / phase
+      for (int it = 0; it < n_iter; ++it) {
+        mbar_wait(in_full, it & 1);
+        for (int l = 0; l < nl; ++l) {
+          const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
+          const int a_src = a.L[l].a_src;
+          const uint32_t a_par = (uint32_t)(it * (nl - 1) + l - 1) & 1;   // phase of the epilogue that produced A
+          for (int c = 0; c < kFChunks; ++c, ++n) {
+            const uint32_t buf = n & 1;
+            if (!(a.dbg & 8)) mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1);
+            const uint32_t tmem_d = tmem_base + buf * 128;
+            for (int kb0 = 0; kb0 < kb_tot; kb0 += 2) {
+              const int nk = kb_tot - kb0 < 2 ? 1 : 2;
+              if (c == 0 && l > 0 && !(a.dbg & 8)) {
+                if (kb0 < kb_main) mbar_wait(a_ready + kb0, a_par);
+                if (nk == 2 && kb0 + 1 < kb_main) mbar_wait(a_ready + kb0 + 1, a_par);
+              }
+              if (!(a.dbg & 1)) mbar_wait(full + st.stage, st.phase);
+              tc_fence_after();
+              const uint32_t sb = sRing_u + st.stage * kFStageB;
+              if (elect_one()) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  if (h < nk && !(a.dbg & 4)) {
+                    const int kb = kb0 + h;
+                    const uint64_t bdesc = make_sdesc(sb + h * kFBoxB, 16, 1024);
+                    if (a_src == kSrcQ && kb < kb_main) {
+                      const uint32_t ta = tmem_base + kFColQ + kb * 32;
+#pragma unroll
+                      for (int k = 0; k < 4; ++k)
+                        umma_bf16_pair_ts(tmem_d, ta + k * 8, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    } else {
+                      uint32_t pa;                                                     // smem A panel
+                      if (kb >= kb_main) pa = sZ_u + (kb - kb_main) * kFPanel;         // latent tail of fc_1
+                      else if (a_src == kSrcP) pa = sP_u + kb * kFPanel;
+                      else pa = kb < a.kb_lat ? sZ_u + kb * kFPanel : sP_u;            // field input
+                      const uint64_t adesc = make_sdesc(pa, 16, 1024);
+#pragma unroll
+                      for (int k = 0; k < 4; ++k)
+                        umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                  }
+                }
+                if (!(a.dbg & 1)) umma_commit_pair(empty + st.stage);
+              }
+              __syncwarp();
+              st.advance(kStages);
+            }
+            if (elect_one()) {
+              umma_commit_pair(acc_full + buf);
+              if (l == nl - 2 && c == kFChunks - 1) umma_commit_pair(in_free);   // P and Z are dead: next input may land
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ---- epilogue: 8 warps that never synchronise with each other.  Warp (g, q4) owns rows [32 q4, 32 q4 + 32)
+    // x columns [64g, 64g+64) of every chunk; it stages and TMA-stores its own 32-row boxes, keeps its own copy of
+    // the chunk's bias values in shared memory and signals the MMA issuer on its own.
+    const int ew = warp - 4;
+    const int g = ew >> 2;                           // column half of every chunk
+    const int q4 = warp & 3;                         // TMEM lane quarter
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const uint32_t sw128 = (uint32_t)(row & 7);
+    const uint32_t sw64 = (uint32_t)((row >> 1) & 3);
+    uint8_t* slot = sStage + ew * kFSlot;            // this warp's staging slot (training)
+    float* wbias = sBias + ew * 64;                  // this warp's bias values of the current chunk
+    uint32_t xres[kFChunks][32];                     // this thread's slice of the bf16 residual stream x'
+    uint32_t n = 0;
+    // bias of the first chunk
+    wbias[lane] = __ldg(a.L[0].bias + g * 64 + lane);
+    wbias[lane + 32] = __ldg(a.L[0].bias + g * 64 + lane + 32);
+    __syncwarp();
+    for (int it = 0; it < n_iter; ++it) {
+      const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
+      for (int l = 0; l < nl; ++l) {
+        const FLayer& L = a.L[l];
+        const int kind = L.kind;
+        const bool first = L.first != 0;
+        const bool save = kTrain && L.act_slot >= 0;
+        const float* bias_next_layer = a.L[l + 1 < nl ? l + 1 : 0].bias;
+        if (l == nl - 2 && g == 0 && lane == 0) {    // this warp's TMA stores that read P panel 0 have drained
+          if (kTrain) bulk_wait_read0();
+          mbar_arrive(in_free);
+        }
+#pragma unroll
+        for (int c = 0; c < kFChunks; ++c, ++n) {
+          const uint32_t buf = n & 1;
+          const int col0 = c * 128 + g * 64;         // first feature this thread handles in this chunk
+          // prefetch the next chunk's bias (2 values per lane), parked in registers until this chunk is done
+          const float* bnext = (c + 1 < kFChunks ? L.bias + (c + 1) * 128 : bias_next_layer) + g * 64;
+          const float bn0 = __ldg(bnext + lane), bn1 = __ldg(bnext + lane + 32);
+          mbar_wait(acc_full + buf, (n >> 1) & 1);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + buf * 128 + g * 64 + lane_off;
+          uint8_t* prow = sP + (2 * c + g) * kFPanel + row * 128;
+          if (a.dbg & 2) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_leader(acc_empty + buf);
+              if (kind != kLayerOut) mbar_arrive_leader(a_ready + 2 * c + g);
+            }
+            continue;
+          }
+          uint32_t v[64];
+          tmem_ld32_nowait(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld32_nowait(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+          tc_fence_before();                         // the accumulator buffer is free again
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(acc_empty + buf);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            uint64_t x2[16];                         // acc + bias, as fp32 pairs
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(wbias + s * 32 + 4 * j);
+              x2[2 * j] = add2(pair_u32(v[s * 32 + 4 * j], v[s * 32 + 4 * j + 1]), pair_f32(b.x, b.y));
+              x2[2 * j + 1] = add2(pair_u32(v[s * 32 + 4 * j + 2], v[s * 32 + 4 * j + 3]), pair_f32(b.z, b.w));
+            }
+            if (kind == kLayerOut) {
+              // raw field outputs, fp32, written row-wise (128 B per thread per sub-chunk)
+              if (row0 + row < a.N) {
+                float* dst = a.out + (int64_t)(row0 + row) * a.ldo + col0 + s * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (col0 + s * 32 + 4 * j < a.d_out)
+                    *reinterpret_cast<uint4*>(dst + 4 * j) =
+                        make_uint4((uint32_t)x2[2 * j], (uint32_t)(x2[2 * j] >> 32), (uint32_t)x2[2 * j + 1],
+                                   (uint32_t)(x2[2 * j + 1] >> 32));
+              }
+            } else {
+              uint32_t w[16];
+              if (kind == kLayerX) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  uint64_t t = x2[j];
+                  if (!first) {
+                    const uint32_t r = xres[c][s * 16 + j];
+                    t = add2(t, pair_u32(r << 16, r & 0xffff0000u));
+                  }
+                  const uint32_t xb = cvt_bf16x2(t);
+                  xres[c][s * 16 + j] = xb;
+                  w[j] = relu_bf16x2(xb);
+                }
+                tmem_st16(tmem_base + kFColQ + lane_off + (uint32_t)(col0 / 2 + s * 16), w);
+                if (save) {
+                  if (lane == 0) bulk_wait_read0();  // the slot's previous TMA store has read it
+                  __syncwarp();
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(slot + lane * 64 + (((uint32_t)j ^ sw64) << 4)) =
+                        make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                  fence_proxy_async();
+                  __syncwarp();
+                  if (lane == 0) {
+                    tma_store_3d(&maps.acts32, slot, col0 + s * 32, row0 + q4 * 32, L.act_slot);
+                    bulk_commit();
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j] = relu_bf16x2(cvt_bf16x2(x2[j]));
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(prow + (((uint32_t)(s * 4 + j) ^ sw128) << 4)) =
+                      make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+              }
+            }
+          }
+          if (kind != kLayerOut) {
+            // publish this warp's rows of k-block 2c+g of the next layer's A operand to the MMA issuer
+            if (kind == kLayerX) tmem_st_wait();
+            else fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_leader(a_ready + 2 * c + g);
+              if (save && kind == kLayerNet) {
+                tma_store_3d(&maps.acts, sP + (2 * c + g) * kFPanel + q4 * 32 * 128, col0, row0 + q4 * 32, L.act_slot);
+                bulk_commit();
+              }
+            }
+          } else {
+            __syncwarp();
+          }
+          wbias[lane] = bn0;                         // every lane is past its reads of this chunk's bias
+          wbias[lane + 32] = bn1;
+          __syncwarp();
+        }
+      }
+    }
+    if (kTrain && lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+static int make_acts_map(CUtensorMap* map, void* acts, int64_t N, int n_slots, int box_cols, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  NRF_REQUIRE(fn != nullptr, NRF_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[3] = {512, (cuuint64_t)N, (cuuint64_t)n_slots};
+  cuuint64_t gstride[2] = {512 * 2, (cuuint64_t)N * 512 * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, acts, gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NRF_REQUIRE(r == CUDA_SUCCESS, NRF_ECUDA, "cuTensorMapEncodeTiled(acts) failed (%d)", (int)r);
+  return NRF_OK;
+}
+
+}  // namespace
+
+int mlp_fused_fwd_launch(const FusedFwdDesc& d, cudaStream_t stream) {
+  NRF_REQUIRE(d.n_layers >= 2 && d.n_layers <= kFusedMaxLayers, NRF_EINVAL, "mlp_fused: %d layers", d.n_layers);
+  NRF_REQUIRE(d.kb_lat >= 0 && d.kb_lat <= 2 && d.kin_pad == (d.kb_lat + 1) * 64, NRF_ENOSUP,
+              "mlp_fused: kin_pad=%d, latent k-blocks=%d", d.kin_pad, d.kb_lat);
+  FMaps maps;
+  FArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const FusedLayerDesc& L = d.L[l];
+    const int ktot = (L.kb_main + L.kb_z) * 64;
+    if ((rc = make_map(&maps.w[l], L.W, ktot, 512, L.ldw, 64, 64))) return rc;   // box = one k-block of a CTA's 64 rows
+    NRF_REQUIRE((reinterpret_cast<uintptr_t>(L.bias) & 15) == 0 && L.bias, NRF_EINVAL, "mlp_fused: bias alignment");
+    a.L[l].kind = L.kind; a.L[l].a_src = L.a_src; a.L[l].kb_main = L.kb_main; a.L[l].kb_z = L.kb_z;
+    a.L[l].first = L.first; a.L[l].act_slot = L.act_slot; a.L[l].bias = L.bias;
+  }
+  for (int l = d.n_layers; l < kFusedMaxLayers; ++l) maps.w[l] = maps.w[0];
+  if ((rc = make_map(&maps.in, d.field_in, d.kin_pad, d.N, d.kin_pad, 64, 128))) return rc;
+  const bool train = d.acts != nullptr;
+  if (train) {
+    if ((rc = make_acts_map(&maps.acts, d.acts, d.N, d.n_slots, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_acts_map(&maps.acts32, d.acts, d.N, d.n_slots, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  } else {
+    maps.acts = maps.acts32 = maps.in;
+  }
+  a.n_layers = d.n_layers;
+  a.n_tiles = (int)((d.N + 255) / 256);
+  a.kb_lat = d.kb_lat;
+  a.train = train;
+  a.N = (int)d.N; a.d_out = d.d_out; a.ldo = d.ldo; a.out = d.out;
+  { const char* e = getenv("NRF_DBG"); a.dbg = e ? atoi(e) : 0; }
+  int grid = sm_count() / 2 * 2;
+  if (grid > 2 * a.n_tiles) grid = 2 * a.n_tiles;
+  auto kern = train ? mlp_fused_fwd_kernel<true> : mlp_fused_fwd_kernel<false>;
+  const int smem_bytes = train ? FCfg<true>::kSmem : FCfg<false>::kSmem;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[train]) {
+    NRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set[train] = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kFThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+  { LaunchScope ls_(NRF_CAT_FUSED_FWD, stream);
+  NRF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, a));
+  }
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
+
+}  // namespace nrf

@@ -322,16 +322,26 @@ class FieldMLP:
             self._packed_key = key
         return self._packed
 
-    def forward(self, field_in, acts=None):
-        """field_in (N,kin_pad) -> (field_out (N,d_out) fp32 raw, acts buffer)."""
+    @property
+    def fused(self) -> bool:
+        """True when nrf_mlp_fwd runs the whole MLP as one persistent tcgen05 kernel (csrc/mlp_fused.cu)."""
+        return bool(_lib.load().nrf_mlp_fused_supported(C.byref(self._cparams()), self.precision))
+
+    def forward(self, field_in, acts=None, keep_acts=True, layered=False):
+        """field_in (N,kin_pad) -> (field_out (N,d_out) fp32 raw, acts buffer).
+
+        keep_acts=False (inference): the fused kernel keeps nothing (acts is None); the layer-by-layer chain
+        still needs its buffer.  layered=True forces the chain (A/B timing, parity tests)."""
         N = field_in.shape[0]
         dev = field_in.device
         packed = self.pack()
-        if acts is None:
+        lib = _lib.load()
+        if acts is None and (keep_acts or layered or not self.fused):
             acts = torch.empty(self.sizes.fwd_bytes_per_sample * N, device=dev, dtype=torch.uint8)
         out = torch.empty(N, self.dims[3], device=dev, dtype=torch.float32)
-        check(_lib.load().nrf_mlp_fwd(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
-                                      ptr(acts), ptr(out), stream_ptr()), "nrf_mlp_fwd")
+        fn = lib.nrf_mlp_fwd_layered if layered else lib.nrf_mlp_fwd
+        check(fn(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
+                 ptr(acts), ptr(out), stream_ptr()), "nrf_mlp_fwd")
         return out, acts
 
     def backward(self, field_in, acts, d_field, grads: dict, scratch=None):
