@@ -111,12 +111,6 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
     if (spin > (1u << 22)) __trap();
   }
 }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
 // packed fp32 pairs (sm_100 add.f32x2: two IEEE rn additions per instruction) and packed bf16 ReLU
 __device__ __forceinline__ uint64_t pair_u32(uint32_t lo, uint32_t hi) {
   uint64_t r;
@@ -141,6 +135,162 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t w) {    // bf16(relu(x)
   uint32_t r;
   asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(w), "r"(0u));
   return r;
+}
+
+// explicit shared-space accesses with 32-bit addresses (the aligned dynamic-smem base is a generic pointer to the
+// compiler, which would otherwise emit generic LD/ST with 64-bit address arithmetic in the epilogue's hot loop)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_arrive_leader_u32(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(addr & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_u32(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+struct EpiCtx {            // per-thread constants of the epilogue
+  uint32_t tmem_base, lane_off;
+  uint32_t sP, slot, wbias;            // shared-space addresses: P, this warp's staging slot, this warp's bias values
+  uint32_t acc_full, acc_empty, a_ready;
+  int lane, g, q4, row;
+  uint32_t sw128, sw64;
+};
+
+// One 128-column accumulator chunk of one layer, this thread's 64 columns.  KIND is the layer kind; xr is the thread's
+// slice of the residual stream for this chunk (used by kLayerX only).
+template <int KIND, bool kTrain>
+__device__ __forceinline__ void epi_chunk(const EpiCtx& e, const FMaps& maps, const FArgs& a, const FLayer& L, int c,
+                                          uint32_t n, int row0, bool first, bool save, uint32_t (&xr)[32],
+                                          const float* bnext) {
+  const uint32_t buf = n & 1;
+  const int col0 = c * 128 + e.g * 64;         // first feature this thread handles in this chunk
+  // prefetch the next chunk's bias (2 values per lane), parked in registers until this chunk is done
+  const float bn0 = __ldg(bnext + e.lane), bn1 = __ldg(bnext + e.lane + 32);
+  mbar_wait_u32(e.acc_full + buf * 8, (n >> 1) & 1);
+  tc_fence_after();
+  const uint32_t taddr = e.tmem_base + buf * 128 + e.g * 64 + e.lane_off;
+  if (a.dbg & 2) {
+    tc_fence_before();
+    __syncwarp();
+    if (e.lane == 0) {
+      mbar_arrive_leader_u32(e.acc_empty + buf * 8);
+      if (KIND != kLayerOut) mbar_arrive_leader_u32(e.a_ready + (2 * c + e.g) * 8);
+    }
+    return;
+  }
+  uint32_t v[64];
+  tmem_ld32_nowait(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+  tmem_ld32_nowait(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+  tmem_ld_wait();
+  tc_fence_before();                           // the accumulator buffer is free again
+  __syncwarp();
+  if (e.lane == 0) mbar_arrive_leader_u32(e.acc_empty + buf * 8);
+  const uint32_t prow = e.sP + (2 * c + e.g) * kFPanel + e.row * 128;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    uint64_t x2[16];                           // acc + bias, as fp32 pairs
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = lds128f(e.wbias + (s * 32 + 4 * j) * 4);
+      x2[2 * j] = add2(pair_u32(v[s * 32 + 4 * j], v[s * 32 + 4 * j + 1]), pair_f32(b.x, b.y));
+      x2[2 * j + 1] = add2(pair_u32(v[s * 32 + 4 * j + 2], v[s * 32 + 4 * j + 3]), pair_f32(b.z, b.w));
+    }
+    if (KIND == kLayerOut) {
+      // raw field outputs, fp32, written row-wise (128 B per thread per sub-chunk)
+      if (row0 + e.row < a.N) {
+        float* dst = a.out + (int64_t)(row0 + e.row) * a.ldo + col0 + s * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (col0 + s * 32 + 4 * j < a.d_out)
+            *reinterpret_cast<uint4*>(dst + 4 * j) =
+                make_uint4((uint32_t)x2[2 * j], (uint32_t)(x2[2 * j] >> 32), (uint32_t)x2[2 * j + 1],
+                           (uint32_t)(x2[2 * j + 1] >> 32));
+      }
+    } else {
+      uint32_t w[16];
+      if (KIND == kLayerX) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          uint64_t t = x2[j];
+          if (!first) {
+            const uint32_t r = xr[s * 16 + j];
+            t = add2(t, pair_u32(r << 16, r & 0xffff0000u));
+          }
+          const uint32_t xb = cvt_bf16x2(t);
+          xr[s * 16 + j] = xb;
+          w[j] = relu_bf16x2(xb);
+        }
+        tmem_st16(e.tmem_base + kFColQ + e.lane_off + (uint32_t)(col0 / 2 + s * 16), w);
+        if (kTrain && save) {
+          if (e.lane == 0) bulk_wait_read0();  // the slot's previous TMA store has read it
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(e.slot + e.lane * 64 + (((uint32_t)j ^ e.sw64) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2],
+                   w[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (e.lane == 0) {
+            tma_store_3d_u32(&maps.acts32, e.slot, col0 + s * 32, row0 + e.q4 * 32, L.act_slot);
+            bulk_commit();
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = relu_bf16x2(cvt_bf16x2(x2[j]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128(prow + (((uint32_t)(s * 4 + j) ^ e.sw128) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      }
+    }
+  }
+  if (KIND != kLayerOut) {
+    // publish this warp's rows of k-block 2c+g of the next layer's A operand to the MMA issuer
+    if (KIND == kLayerX) tmem_st_wait();
+    else fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (e.lane == 0) {
+      mbar_arrive_leader_u32(e.a_ready + (2 * c + e.g) * 8);
+      if (kTrain && save && KIND == kLayerNet) {
+        tma_store_3d_u32(&maps.acts, e.sP + (2 * c + e.g) * kFPanel + e.q4 * 32 * 128, col0, row0 + e.q4 * 32,
+                         L.act_slot);
+        bulk_commit();
+      }
+    }
+  } else {
+    __syncwarp();
+  }
+  sts32f(e.wbias + e.lane * 4, bn0);           // every lane is past its reads of this chunk's bias
+  sts32f(e.wbias + (e.lane + 32) * 4, bn1);
+  __syncwarp();
 }
 
 template <bool kTrain>
@@ -298,19 +448,27 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
     // x columns [64g, 64g+64) of every chunk; it stages and TMA-stores its own 32-row boxes, keeps its own copy of
     // the chunk's bias values in shared memory and signals the MMA issuer on its own.
     const int ew = warp - 4;
-    const int g = ew >> 2;                           // column half of every chunk
-    const int q4 = warp & 3;                         // TMEM lane quarter
-    const int row = q4 * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-    const uint32_t sw128 = (uint32_t)(row & 7);
-    const uint32_t sw64 = (uint32_t)((row >> 1) & 3);
-    uint8_t* slot = sStage + ew * kFSlot;            // this warp's staging slot (training)
-    float* wbias = sBias + ew * 64;                  // this warp's bias values of the current chunk
+    EpiCtx e;
+    e.tmem_base = tmem_base;
+    e.g = ew >> 2;                                   // column half of every chunk
+    e.q4 = warp & 3;                                 // TMEM lane quarter
+    e.lane = lane;
+    e.row = e.q4 * 32 + lane;
+    e.lane_off = (uint32_t)(e.q4 * 32) << 16;
+    e.sw128 = (uint32_t)(e.row & 7);
+    e.sw64 = (uint32_t)((e.row >> 1) & 3);
+    e.sP = smem_u32(sP);
+    e.slot = smem_u32(sStage) + ew * kFSlot;         // this warp's staging slot (training)
+    e.wbias = smem_u32(sBias) + ew * 256;            // this warp's bias values of the current chunk
+    e.acc_full = smem_u32(acc_full);
+    e.acc_empty = smem_u32(acc_empty);
+    e.a_ready = smem_u32(a_ready);
+    const int g = e.g;
     uint32_t xres[kFChunks][32];                     // this thread's slice of the bf16 residual stream x'
     uint32_t n = 0;
     // bias of the first chunk
-    wbias[lane] = __ldg(a.L[0].bias + g * 64 + lane);
-    wbias[lane + 32] = __ldg(a.L[0].bias + g * 64 + lane + 32);
+    sts32f(e.wbias + lane * 4, __ldg(a.L[0].bias + g * 64 + lane));
+    sts32f(e.wbias + (lane + 32) * 4, __ldg(a.L[0].bias + g * 64 + lane + 32));
     __syncwarp();
     for (int it = 0; it < n_iter; ++it) {
       const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
@@ -319,116 +477,27 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
         const int kind = L.kind;
         const bool first = L.first != 0;
         const bool save = kTrain && L.act_slot >= 0;
-        const float* bias_next_layer = a.L[l + 1 < nl ? l + 1 : 0].bias;
+        const float* bias_next_layer = a.L[l + 1 < nl ? l + 1 : 0].bias + g * 64;
+        const float* bias_l = L.bias + g * 64;
         if (l == nl - 2 && g == 0 && lane == 0) {    // this warp's TMA stores that read P panel 0 have drained
           if (kTrain) bulk_wait_read0();
           mbar_arrive(in_free);
         }
+        if (kind == kLayerX) {
 #pragma unroll
-        for (int c = 0; c < kFChunks; ++c, ++n) {
-          const uint32_t buf = n & 1;
-          const int col0 = c * 128 + g * 64;         // first feature this thread handles in this chunk
-          // prefetch the next chunk's bias (2 values per lane), parked in registers until this chunk is done
-          const float* bnext = (c + 1 < kFChunks ? L.bias + (c + 1) * 128 : bias_next_layer) + g * 64;
-          const float bn0 = __ldg(bnext + lane), bn1 = __ldg(bnext + lane + 32);
-          mbar_wait(acc_full + buf, (n >> 1) & 1);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + buf * 128 + g * 64 + lane_off;
-          uint8_t* prow = sP + (2 * c + g) * kFPanel + row * 128;
-          if (a.dbg & 2) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              mbar_arrive_leader(acc_empty + buf);
-              if (kind != kLayerOut) mbar_arrive_leader(a_ready + 2 * c + g);
-            }
-            continue;
-          }
-          uint32_t v[64];
-          tmem_ld32_nowait(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld32_nowait(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          tmem_ld_wait();
-          tc_fence_before();                         // the accumulator buffer is free again
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(acc_empty + buf);
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            uint64_t x2[16];                         // acc + bias, as fp32 pairs
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = *reinterpret_cast<const float4*>(wbias + s * 32 + 4 * j);
-              x2[2 * j] = add2(pair_u32(v[s * 32 + 4 * j], v[s * 32 + 4 * j + 1]), pair_f32(b.x, b.y));
-              x2[2 * j + 1] = add2(pair_u32(v[s * 32 + 4 * j + 2], v[s * 32 + 4 * j + 3]), pair_f32(b.z, b.w));
-            }
-            if (kind == kLayerOut) {
-              // raw field outputs, fp32, written row-wise (128 B per thread per sub-chunk)
-              if (row0 + row < a.N) {
-                float* dst = a.out + (int64_t)(row0 + row) * a.ldo + col0 + s * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (col0 + s * 32 + 4 * j < a.d_out)
-                    *reinterpret_cast<uint4*>(dst + 4 * j) =
-                        make_uint4((uint32_t)x2[2 * j], (uint32_t)(x2[2 * j] >> 32), (uint32_t)x2[2 * j + 1],
-                                   (uint32_t)(x2[2 * j + 1] >> 32));
-              }
-            } else {
-              uint32_t w[16];
-              if (kind == kLayerX) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  uint64_t t = x2[j];
-                  if (!first) {
-                    const uint32_t r = xres[c][s * 16 + j];
-                    t = add2(t, pair_u32(r << 16, r & 0xffff0000u));
-                  }
-                  const uint32_t xb = cvt_bf16x2(t);
-                  xres[c][s * 16 + j] = xb;
-                  w[j] = relu_bf16x2(xb);
-                }
-                tmem_st16(tmem_base + kFColQ + lane_off + (uint32_t)(col0 / 2 + s * 16), w);
-                if (save) {
-                  if (lane == 0) bulk_wait_read0();  // the slot's previous TMA store has read it
-                  __syncwarp();
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint4*>(slot + lane * 64 + (((uint32_t)j ^ sw64) << 4)) =
-                        make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-                  fence_proxy_async();
-                  __syncwarp();
-                  if (lane == 0) {
-                    tma_store_3d(&maps.acts32, slot, col0 + s * 32, row0 + q4 * 32, L.act_slot);
-                    bulk_commit();
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) w[j] = relu_bf16x2(cvt_bf16x2(x2[j]));
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  *reinterpret_cast<uint4*>(prow + (((uint32_t)(s * 4 + j) ^ sw128) << 4)) =
-                      make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-              }
-            }
-          }
-          if (kind != kLayerOut) {
-            // publish this warp's rows of k-block 2c+g of the next layer's A operand to the MMA issuer
-            if (kind == kLayerX) tmem_st_wait();
-            else fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              mbar_arrive_leader(a_ready + 2 * c + g);
-              if (save && kind == kLayerNet) {
-                tma_store_3d(&maps.acts, sP + (2 * c + g) * kFPanel + q4 * 32 * 128, col0, row0 + q4 * 32, L.act_slot);
-                bulk_commit();
-              }
-            }
-          } else {
-            __syncwarp();
-          }
-          wbias[lane] = bn0;                         // every lane is past its reads of this chunk's bias
-          wbias[lane + 32] = bn1;
-          __syncwarp();
+          for (int c = 0; c < kFChunks; ++c, ++n)
+            epi_chunk<kLayerX, kTrain>(e, maps, a, L, c, n, row0, first, save, xres[c],
+                                       c + 1 < kFChunks ? bias_l + (c + 1) * 128 : bias_next_layer);
+        } else if (kind == kLayerNet) {
+#pragma unroll 1
+          for (int c = 0; c < kFChunks; ++c, ++n)
+            epi_chunk<kLayerNet, kTrain>(e, maps, a, L, c, n, row0, false, save, xres[0],
+                                         c + 1 < kFChunks ? bias_l + (c + 1) * 128 : bias_next_layer);
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < kFChunks; ++c, ++n)
+            epi_chunk<kLayerOut, kTrain>(e, maps, a, L, c, n, row0, false, false, xres[0],
+                                         c + 1 < kFChunks ? bias_l + (c + 1) * 128 : bias_next_layer);
         }
       }
     }
