@@ -172,6 +172,8 @@ typedef struct {
   float* fc0_w[NRF_MAX_BLOCKS]; float* fc0_b[NRF_MAX_BLOCKS];
   float* fc1_w[NRF_MAX_BLOCKS]; float* fc1_b[NRF_MAX_BLOCKS];
   float* lin_z_w[NRF_MAX_BLOCKS]; float* lin_z_b[NRF_MAX_BLOCKS];
+  int deterministic;   /* bf16 mode: reduce the sample splits of every weight gradient in a fixed order through the
+                          scratch workspace (bit-reproducible, ~10 % slower wgrads) instead of fp32 atomics */
 } NrfMlpGrads;
 
 /* Sizes (bytes) of the caller-provided buffers for a given shape / precision. */

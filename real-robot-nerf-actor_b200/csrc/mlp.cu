@@ -322,7 +322,7 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
   auto an = [&](int b) { return act + (int64_t)(L.nb + 1 + b) * layer; };
   char* sc = reinterpret_cast<char*>(scratch);
   int64_t fixed = round_up(nrf_wgrad_workspace_bytes(L.H, L.H), 1024);
-  void* wws = sc;                             // per-split partial tiles of the weight gradients (ordered reduce)
+  void* wws = gr->deterministic ? sc : nullptr;   // per-split partial tiles of the weight gradients (ordered reduce)
   char* gbuf = sc + fixed;                    // dL/dx, updated in place while b >= n_lin_z
   char* dnet = gbuf + layer;
   auto gz = [&](int b) { return dnet + (int64_t)(1 + b) * layer; };   // dL/dx'_b kept for dL/dz, b < n_lin_z

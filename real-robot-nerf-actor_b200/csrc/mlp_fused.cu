@@ -5,26 +5,27 @@
 // the bf16 operands the backward needs (relu(x'_b), relu(net_b)) are streamed out by TMA stores as a side effect.
 //
 // Where everything lives (per CTA; the MMAs are tcgen05.mma.cta_group::2, M = 256, N = 128, K = 16):
-//   weights        stream from L2 through a TMA ring of 8 KB stages (this CTA's 64 of the 128 weight rows x 64 k);
+//   weights        stream from L2 through a TMA ring of 16 KB stages (this CTA's 64 of the 128 weight rows x 128 k);
 //                  the pair shares every weight byte, so the L2 -> SM weight traffic is 32 B/clk/SM at full rate
+//   field input    the [latent | PE | viewdir] k-panels (lin_in|lin_z[0], and the lin_z[b+1] tails of fc_1) come
+//                  through the same ring, one 16 KB stage per 128-row k-panel
 //   accumulators   TMEM columns [0,256): two 128-column buffers; the epilogue of chunk i overlaps the MMAs of i+1
 //   relu(x')       TMEM columns [256,512) as packed bf16 pairs: the A operand of fc_0 and lin_out comes straight
 //                  from tensor memory (tcgen05.mma with A in TMEM), written by the epilogue with tcgen05.st
 //   relu(net)      shared memory "P": 8 k-panels of 128 rows x 64 bf16 (128B-swizzled UMMA layout), the A operand
 //                  of fc_1, written by the epilogue with st.shared; in training the same panels are the source of
 //                  the TMA stores of relu(net_b)
-//   latent z       shared memory "Z": the first kb_lat k-panels of the field-input tile; read three times
-//                  (lin_in|lin_z[0], and the lin_z[b+1] tails of fc_1); the PE|viewdir panel borrows P panel 0
-//   residual x'    REGISTERS of the epilogue threads: thread (row, warpgroup g) keeps its 256 elements of the bf16
+//   residual x'    REGISTERS of the epilogue threads: thread (row, column half g) keeps its 256 elements of the bf16
 //                  residual stream as 128 packed registers for the whole tile (setmaxnreg gives the epilogue
 //                  warpgroups 232 registers, the service warps 40)
 // Ping-ponging the operand between TMEM and shared memory removes every write-after-read hazard between a layer's
 // MMAs and its own epilogue, so the next layer's MMAs start on k-block kb as soon as the epilogue has published it
-// (a_ready[kb]) and the tensor pipe never drains between layers.
+// (a_ready[kb]) and the tensor pipe never drains between layers - or between tiles: nothing but ring slots and
+// accumulator buffers is shared from one tile to the next.
 //
-// Warp roles: 0 weight TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator | 3 field-input loader |
-// 4-7, 8-11 two epilogue warpgroups (warpgroup g owns columns [64g, 64g+64) of every 128-column chunk = k-block 2c+g
-// of the next layer).
+// Warp roles: 0 TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator | 4-11 epilogue: warp (g, q4) owns
+// rows [32 q4, 32 q4 + 32) x columns [64g, 64g+64) of every 128-column chunk (= its rows of k-block 2c+g of the next
+// layer); the eight epilogue warps never synchronise with each other.
 #include "tc_ptx.cuh"
 
 namespace nrf {
@@ -37,17 +38,16 @@ constexpr int kFBoxB = 64 * 64 * 2;          // 8 KB: this CTA's 64 weight rows 
 constexpr int kFStageB = 2 * kFBoxB;         // a ring stage carries two k-blocks (8 MMAs per barrier round trip)
 constexpr int kFChunks = 4;                  // 512 / 128 accumulator chunks per layer
 constexpr int kFSmemP = 8 * kFPanel;         // 128 KB
-constexpr int kFSmemZ = 2 * kFPanel;         // 32 KB
-constexpr int kFSlot = 32 * 64;              // 2 KB: 32 rows x 32 bf16 (64B swizzle), one per epilogue warp
+constexpr int kFSlot = 32 * 128;             // 4 KB: 32 rows x 64 bf16 (128B swizzle), one per epilogue warp
 constexpr int kFSmemBar = 256;
 constexpr int kFSmemBias = 8 * 256;          // per epilogue warp: the 64 bias values of its current chunk
 constexpr int kFAlignSlack = 768;            // dynamic shared memory starts 1024-aligned in practice (checked)
 template <bool kTrain>
 struct FCfg {
-  static constexpr int kStages = kTrain ? 3 : 4;     // training gives one stage up for the relu(x') staging slots
+  static constexpr int kStages = kTrain ? 4 : 6;     // training gives 32 KB up for the relu(x') staging slots
   static constexpr int kRing = kStages * kFStageB;
   static constexpr int kStaging = kTrain ? 8 * kFSlot : 0;
-  static constexpr int kSmem = kFSmemP + kFSmemZ + kRing + kStaging + kFSmemBar + kFSmemBias + kFAlignSlack;
+  static constexpr int kSmem = kFSmemP + kRing + kStaging + kFSmemBar + kFSmemBias + kFAlignSlack;
   static_assert(kSmem <= 232448, "fused MLP kernel exceeds the 227 KB shared-memory limit");
 };
 constexpr uint32_t kFColQ = 256;             // first TMEM column of the packed relu(x') operand
@@ -60,7 +60,7 @@ struct FLayer {
   const float* bias;
 };
 struct FArgs {
-  int n_layers, n_tiles, kb_lat, train;
+  int n_layers, n_tiles, train;
   int N, d_out, ldo;
   int dbg;      // NRF_DBG timing experiments (wrong results!): 1 no weight TMA, 2 epilogue protocol only, 4 no MMAs,
                 // 8 MMA issuer ignores acc_empty / a_ready
@@ -70,8 +70,8 @@ struct FArgs {
 struct FMaps {
   CUtensorMap w[kFusedMaxLayers];
   CUtensorMap in;
-  CUtensorMap acts;      // (512, N, slots) bf16, box 64 x 32 x 1, 128B swizzle: relu(net_b) straight from the P panels
-  CUtensorMap acts32;    // same tensor, box 32 x 32 x 1, 64B swizzle: relu(x'_b) from the per-warp staging slots
+  CUtensorMap acts;      // (512, N, slots) bf16, box 64 x 32 x 1, 128B swizzle: a warp's 32 rows of one k-panel, from
+                         // the P panels (relu(net_b)) or from the warp's staging slot (relu(x'_b))
 };
 
 __device__ __forceinline__ void umma_bf16_pair_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -94,23 +94,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// Long waits (a whole tile): let the hardware park the warp instead of re-polling every few hundred cycles.
-__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(100000u)
-        : "memory");
-    if (spin > (1u << 22)) __trap();
-  }
-}
 // packed fp32 pairs (sm_100 add.f32x2: two IEEE rn additions per instruction) and packed bf16 ReLU
 __device__ __forceinline__ uint64_t pair_u32(uint32_t lo, uint32_t hi) {
   uint64_t r;
@@ -168,11 +151,24 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive_leader_u32(uint32_t addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(addr & kPeerBitMask) : "memory");
 }
+// L2 cache-policy descriptors (the values CUTLASS passes as TMA cache hints): the saved operands are written once and
+// read much later (evict first), the weights are re-read by every CTA for every tile (evict last).
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
 __device__ __forceinline__ void tma_store_3d_u32(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
+          reinterpret_cast<uint64_t>(map)),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "l"(kL2EvictFirst)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                      uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
 }
 
 struct EpiCtx {            // per-thread constants of the epilogue
@@ -249,18 +245,14 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& e, const FMaps& maps, co
         }
         tmem_st16(e.tmem_base + kFColQ + e.lane_off + (uint32_t)(col0 / 2 + s * 16), w);
         if (kTrain && save) {
-          if (e.lane == 0) bulk_wait_read0();  // the slot's previous TMA store has read it
-          __syncwarp();
+          if (s == 0) {                        // the slot's previous TMA store (a whole chunk ago) has read it
+            if (e.lane == 0) bulk_wait_read0();
+            __syncwarp();
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            sts128(e.slot + e.lane * 64 + (((uint32_t)j ^ e.sw64) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2],
-                   w[4 * j + 3]);
-          fence_proxy_async();
-          __syncwarp();
-          if (e.lane == 0) {
-            tma_store_3d_u32(&maps.acts32, e.slot, col0 + s * 32, row0 + e.q4 * 32, L.act_slot);
-            bulk_commit();
-          }
+            sts128(e.slot + e.lane * 128 + (((uint32_t)(s * 4 + j) ^ e.sw128) << 4), w[4 * j], w[4 * j + 1],
+                   w[4 * j + 2], w[4 * j + 3]);
         }
       } else {
 #pragma unroll
@@ -274,14 +266,14 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& e, const FMaps& maps, co
   if (KIND != kLayerOut) {
     // publish this warp's rows of k-block 2c+g of the next layer's A operand to the MMA issuer
     if (KIND == kLayerX) tmem_st_wait();
-    else fence_proxy_async();
+    if (KIND == kLayerNet || (kTrain && save)) fence_proxy_async();
     tc_fence_before();
     __syncwarp();
     if (e.lane == 0) {
       mbar_arrive_leader_u32(e.a_ready + (2 * c + e.g) * 8);
-      if (kTrain && save && KIND == kLayerNet) {
-        tma_store_3d_u32(&maps.acts, e.sP + (2 * c + e.g) * kFPanel + e.q4 * 32 * 128, col0, row0 + e.q4 * 32,
-                         L.act_slot);
+      if (kTrain && save && !(a.dbg & (KIND == kLayerNet ? 64 : 32))) {
+        tma_store_3d_u32(&maps.acts, KIND == kLayerNet ? e.sP + (2 * c + e.g) * kFPanel + e.q4 * 32 * 128 : e.slot,
+                         col0, row0 + e.q4 * 32, L.act_slot);
         bulk_commit();
       }
     }
@@ -301,8 +293,7 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sP = smem;
-  uint8_t* sZ = sP + kFSmemP;
-  uint8_t* sRing = sZ + kFSmemZ;
+  uint8_t* sRing = sP + kFSmemP;
   uint8_t* sStage = sRing + Cfg::kRing;
   float* sBias = reinterpret_cast<float*>(sStage + Cfg::kStaging);
   uint64_t* full = reinterpret_cast<uint64_t*>(sStage + Cfg::kStaging + kFSmemBias);
@@ -311,9 +302,7 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
   uint64_t* acc_full = empty + kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* a_ready = acc_empty + 2;           // 8: k-block kb of the next layer's A operand is in place
-  uint64_t* in_full = a_ready + 8;
-  uint64_t* in_free = in_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_free + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 8);
 
   const int warp = uniform_warp_idx();
   int lane;                                      // volatile: kept in a register, never re-read with S2R in the loops
@@ -328,14 +317,12 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < nl; ++l) tma_prefetch_desc(&maps.w[l]);
     tma_prefetch_desc(&maps.in);
-    if (kTrain) { tma_prefetch_desc(&maps.acts); tma_prefetch_desc(&maps.acts32); }
+    if (kTrain) tma_prefetch_desc(&maps.acts);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 2); mbar_init(empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 16); }
     for (int s = 0; s < 8; ++s) mbar_init(a_ready + s, 8);
-    mbar_init(in_full, 2);
-    mbar_init(in_free, 5);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc2(tmem_slot, 512);
@@ -347,47 +334,56 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    // A "unit" is a pair of k-blocks (the last one of a layer may be single).  Units whose A operand is the field
+    // input (layer 0; the latent tail of fc_1) take one ring stage per A k-panel followed by the weight stage; all
+    // other units take the weight stage only.  Producer and issuer walk the same sequence.
     if (warp == 0) {
-      // ---- weight producer: runs ahead of the MMAs by the depth of the ring, across layers and tiles
+      // ---- TMA producer: runs ahead of the MMAs by the depth of the ring, across layers and tiles
       PipeState st;
-      for (int it = 0; it < n_iter; ++it)
+      for (int it = 0; it < n_iter; ++it) {
+        const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
         for (int l = 0; l < nl; ++l) {
-          const int kb_tot = a.L[l].kb_main + a.L[l].kb_z;
+          const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
+          const bool in_main = a.L[l].a_src == kSrcIn;
           for (int c = 0; c < kFChunks; ++c)
             for (int kb = 0; kb < kb_tot; kb += 2) {
               if (a.dbg & 1) continue;
               const int nk = kb_tot - kb < 2 ? 1 : 2;
+              if (in_main || kb >= kb_main) {          // this CTA's 128 rows of the field-input k-panels
+                for (int h = 0; h < nk; ++h) {
+                  mbar_wait(empty + st.stage, st.phase ^ 1);
+                  if (elect_one()) {
+                    if (cta_leader) mbar_expect_tx(full + st.stage, 2 * kFPanel);
+                    else mbar_arrive_leader(full + st.stage);
+                    tma_load_2d_pair(sRing + st.stage * kFStageB, &maps.in, full + st.stage,
+                                     (in_main ? kb + h : kb + h - kb_main) * 64, row0);
+                  }
+                  __syncwarp();
+                  st.advance(kStages);
+                }
+              }
               mbar_wait(empty + st.stage, st.phase ^ 1);
               if (elect_one()) {
                 if (cta_leader) mbar_expect_tx(full + st.stage, 2 * nk * kFBoxB);
                 else mbar_arrive_leader(full + st.stage);
                 uint8_t* dst = sRing + st.stage * kFStageB;
                 const int wrow = c * 128 + (int)crank * 64;
-                tma_load_2d_pair(dst, &maps.w[l], full + st.stage, kb * 64, wrow);
-                if (nk == 2) tma_load_2d_pair(dst + kFBoxB, &maps.w[l], full + st.stage, kb * 64 + 64, wrow);
+                tma_load_2d_pair_hint(dst, &maps.w[l], full + st.stage, kb * 64, wrow, kL2EvictLast);
+                if (nk == 2)
+                  tma_load_2d_pair_hint(dst + kFBoxB, &maps.w[l], full + st.stage, kb * 64 + 64, wrow, kL2EvictLast);
               }
               __syncwarp();
               st.advance(kStages);
             }
         }
-    } else if (warp == 3 && lane == 0) {
-      // ---- field-input loader: latent panels -> Z, PE|viewdir panel -> P panel 0 (dead until fc_0's epilogue)
-      for (int it = 0; it < n_iter; ++it) {
-        if (it > 0) mbar_wait_parked(in_free, (it - 1) & 1);
-        const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
-        if (cta_leader) mbar_expect_tx(in_full, 2 * (a.kb_lat + 1) * kFPanel);
-        else mbar_arrive_leader(in_full);
-        for (int kb = 0; kb < a.kb_lat; ++kb) tma_load_2d_pair(sZ + kb * kFPanel, &maps.in, in_full, kb * 64, row0);
-        tma_load_2d_pair(sP, &maps.in, in_full, a.kb_lat * 64, row0);
       }
     } else if (warp == 1 && cta_leader) {
       // ---- MMA issuer for the pair: the whole warp runs the loop (uniform control flow), one elected lane issues
       constexpr uint32_t idesc = make_idesc(256, 128, 0, 0);
-      const uint32_t sP_u = smem_u32(sP), sZ_u = smem_u32(sZ), sRing_u = smem_u32(sRing);
+      const uint32_t sP_u = smem_u32(sP), sRing_u = smem_u32(sRing);
       PipeState st;
       uint32_t n = 0;                              // running chunk counter -> accumulator buffer / phase
       for (int it = 0; it < n_iter; ++it) {
-        mbar_wait(in_full, it & 1);
         for (int l = 0; l < nl; ++l) {
           const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
           const int a_src = a.L[l].a_src;
@@ -398,9 +394,27 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
             const uint32_t tmem_d = tmem_base + buf * 128;
             for (int kb0 = 0; kb0 < kb_tot; kb0 += 2) {
               const int nk = kb_tot - kb0 < 2 ? 1 : 2;
-              if (c == 0 && l > 0 && !(a.dbg & 8)) {
-                if (kb0 < kb_main) mbar_wait(a_ready + kb0, a_par);
-                if (nk == 2 && kb0 + 1 < kb_main) mbar_wait(a_ready + kb0 + 1, a_par);
+              const bool ext = a_src == kSrcIn || kb0 >= kb_main;          // A k-panels arrive through the ring
+              uint32_t pa0 = 0, pa1 = 0;                                    // smem A panels of the unit's k-blocks
+              int sa0 = 0, sa1 = 0;
+              if (ext) {
+                sa0 = st.stage;
+                pa0 = sRing_u + st.stage * kFStageB;
+                if (!(a.dbg & 1)) mbar_wait(full + st.stage, st.phase);
+                st.advance(kStages);
+                if (nk == 2) {
+                  sa1 = st.stage;
+                  pa1 = sRing_u + st.stage * kFStageB;
+                  if (!(a.dbg & 1)) mbar_wait(full + st.stage, st.phase);
+                  st.advance(kStages);
+                }
+              } else if (a_src == kSrcP) {
+                pa0 = sP_u + kb0 * kFPanel;
+                pa1 = pa0 + kFPanel;
+              }
+              if (!ext && c == 0 && !(a.dbg & 8)) {     // produced by the previous layer's epilogue
+                mbar_wait(a_ready + kb0, a_par);
+                if (nk == 2) mbar_wait(a_ready + kb0 + 1, a_par);
               }
               if (!(a.dbg & 1)) mbar_wait(full + st.stage, st.phase);
               tc_fence_after();
@@ -411,32 +425,31 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
                   if (h < nk && !(a.dbg & 4)) {
                     const int kb = kb0 + h;
                     const uint64_t bdesc = make_sdesc(sb + h * kFBoxB, 16, 1024);
-                    if (a_src == kSrcQ && kb < kb_main) {
+                    if (!ext && a_src == kSrcQ) {
                       const uint32_t ta = tmem_base + kFColQ + kb * 32;
 #pragma unroll
                       for (int k = 0; k < 4; ++k)
                         umma_bf16_pair_ts(tmem_d, ta + k * 8, bdesc + 2 * k, idesc, (kb | k) != 0);
                     } else {
-                      uint32_t pa;                                                     // smem A panel
-                      if (kb >= kb_main) pa = sZ_u + (kb - kb_main) * kFPanel;         // latent tail of fc_1
-                      else if (a_src == kSrcP) pa = sP_u + kb * kFPanel;
-                      else pa = kb < a.kb_lat ? sZ_u + kb * kFPanel : sP_u;            // field input
-                      const uint64_t adesc = make_sdesc(pa, 16, 1024);
+                      const uint64_t adesc = make_sdesc(h == 0 ? pa0 : pa1, 16, 1024);
 #pragma unroll
                       for (int k = 0; k < 4; ++k)
                         umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
                   }
                 }
-                if (!(a.dbg & 1)) umma_commit_pair(empty + st.stage);
+                if (!(a.dbg & 1)) {
+                  if (ext) {
+                    umma_commit_pair(empty + sa0);
+                    if (nk == 2) umma_commit_pair(empty + sa1);
+                  }
+                  umma_commit_pair(empty + st.stage);
+                }
               }
               __syncwarp();
               st.advance(kStages);
             }
-            if (elect_one()) {
-              umma_commit_pair(acc_full + buf);
-              if (l == nl - 2 && c == kFChunks - 1) umma_commit_pair(in_free);   // P and Z are dead: next input may land
-            }
+            if (elect_one()) umma_commit_pair(acc_full + buf);
             __syncwarp();
           }
         }
@@ -479,10 +492,6 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
         const bool save = kTrain && L.act_slot >= 0;
         const float* bias_next_layer = a.L[l + 1 < nl ? l + 1 : 0].bias + g * 64;
         const float* bias_l = L.bias + g * 64;
-        if (l == nl - 2 && g == 0 && lane == 0) {    // this warp's TMA stores that read P panel 0 have drained
-          if (kTrain) bulk_wait_read0();
-          mbar_arrive(in_free);
-        }
         if (kind == kLayerX) {
 #pragma unroll
           for (int c = 0; c < kFChunks; ++c, ++n)
@@ -530,8 +539,7 @@ static int make_acts_map(CUtensorMap* map, void* acts, int64_t N, int n_slots, i
 
 int mlp_fused_fwd_launch(const FusedFwdDesc& d, cudaStream_t stream) {
   NRF_REQUIRE(d.n_layers >= 2 && d.n_layers <= kFusedMaxLayers, NRF_EINVAL, "mlp_fused: %d layers", d.n_layers);
-  NRF_REQUIRE(d.kb_lat >= 0 && d.kb_lat <= 2 && d.kin_pad == (d.kb_lat + 1) * 64, NRF_ENOSUP,
-              "mlp_fused: kin_pad=%d, latent k-blocks=%d", d.kin_pad, d.kb_lat);
+  NRF_REQUIRE(d.kin_pad % 64 == 0 && d.kin_pad >= 64, NRF_ENOSUP, "mlp_fused: kin_pad=%d", d.kin_pad);
   FMaps maps;
   FArgs a;
   memset(&a, 0, sizeof(a));
@@ -549,13 +557,11 @@ int mlp_fused_fwd_launch(const FusedFwdDesc& d, cudaStream_t stream) {
   const bool train = d.acts != nullptr;
   if (train) {
     if ((rc = make_acts_map(&maps.acts, d.acts, d.N, d.n_slots, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_acts_map(&maps.acts32, d.acts, d.N, d.n_slots, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   } else {
-    maps.acts = maps.acts32 = maps.in;
+    maps.acts = maps.in;
   }
   a.n_layers = d.n_layers;
   a.n_tiles = (int)((d.N + 255) / 256);
-  a.kb_lat = d.kb_lat;
   a.train = train;
   a.N = (int)d.N; a.d_out = d.d_out; a.ldo = d.ldo; a.out = d.out;
   { const char* e = getenv("NRF_DBG"); a.dbg = e ? atoi(e) : 0; }

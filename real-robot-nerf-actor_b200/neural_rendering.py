@@ -7,8 +7,9 @@ include/nrf_b200.h.  There is no PyTorch/CPU fallback: CPU tensors raise.
 
 Differences from the reference, all opt-in or invisible to its callers:
   * `precision` ("bf16" tensor-core mode, default; "fp32" parity mode), `perturb` (default True: the
-    reference always draws sampling noise, neural_rendering.py:172,194,200,218) and `scatter` ("atomic" |
-    "sorted": atomics-free, bit-reproducible volume gradient) attributes;
+    reference always draws sampling noise, neural_rendering.py:172,194,200,218), `scatter` ("atomic" |
+    "sorted": atomics-free, bit-reproducible volume gradient) and `deterministic` (bit-reproducible MLP weight
+    gradients too: ordered reduction instead of fp32 atomics) attributes;
   * `forward_nerf(rays, want_weights=False, noise=None)`: `noise` injects pre-drawn tensors
     (keys coarse / u / fine / depth), used by the parity tests;
   * branches that are off in nerfact.conf (multi-scale voxels, depth-supervision volume, coord /
@@ -242,7 +243,7 @@ def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, 
                             ldg=st.mlp.sizes.dout_pad, precision=st.mlp.precision,
                             white_bkgd=ren.white_bkgd, want_dz=want_dz)
     d_field, d_z = res if want_dz else (res, None)
-    dlat = st.mlp.backward(st.field_in, st.acts, d_field, grads)
+    dlat = st.mlp.backward(st.field_in, st.acts, d_field, grads, deterministic=ren.deterministic)
     if ren.scatter == "sorted":       # atomics-free, bit-reproducible; the first pass writes every voxel row
         ops.scatter_volume_grad_sorted(st.rays, st.z, st.rps, dlat, grad_cl, ren._bounds, accumulate=not first)
     else:                             # fp32 vector reductions into a zeroed volume
@@ -391,6 +392,7 @@ class NeuralRenderer(nn.Module):
         self.threshold_depth_supervision = g("threshold_depth_supervision", 0.8)
         self.precision = precision
         self.scatter = "sorted"                # volume-gradient scatter: "sorted" (atomics-free, default) | "atomic"
+        self.deterministic = False             # True: ordered split reduction of the MLP weight gradients as well
         self.perturb = True
         self.render_chunk_rays = 4096          # neural_rendering.py:482
         self._num_freqs = self.nerf_model.code.num_freqs

@@ -358,3 +358,42 @@ def test_scatter_sorted_is_atomics_free_and_reproducible(ops):
     ga = torch.zeros(SB, S, S, S, C, device="cuda")
     ops.scatter_volume_grad(rays.cuda(), z.cuda(), R_per, dlc, ga, syn.BOUNDS)
     assert rel(ga, outs[0]) < 1e-6
+
+
+# ------------------------------------------------------------------ whole-MLP fused forward kernel
+def _bf16_mlp(C=128, D=384, seed=0):
+    NR = load_pkg("neural_rendering")
+    mlp = NR.ResnetFC(d_in=42, d_out=4 + D, n_blocks=5, d_latent=C, d_hidden=512, combine_layer=3)
+    syn.init_mlp_(mlp, seed=seed)
+    g = torch.Generator().manual_seed(5 + seed)
+    with torch.no_grad():
+        for n, p in mlp.named_parameters():          # non-zero biases: the bias path must be exercised
+            if n.endswith(".bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    return mlp.cuda()
+
+
+@pytest.mark.parametrize("C,N", [(128, 256), (128, 1000), (128, 40000), (64, 777), (128, 1)])
+def test_fused_mlp_forward_is_bit_identical_to_the_layered_chain(ops, C, N):
+    """csrc/mlp_fused.cu (one persistent tcgen05 kernel, activations on chip) against the layer-by-layer GEMM chain
+    on the same packed weights: raw outputs and every operand saved for the backward, ragged N included; the
+    inference variant (nothing saved) gives the same outputs."""
+    mlp = _bf16_mlp(C=C)
+    h = mlp.handle(ops.NRF_PREC_BF16)
+    assert h.fused, "the BASELINE shape must take the fused kernel"
+    g = torch.Generator().manual_seed(N)
+    fin = torch.zeros(N, h.sizes.kin_pad, dtype=torch.bfloat16)
+    fin[:, :C + 42] = (torch.randn(N, C + 42, generator=g) * 0.5).to(torch.bfloat16)
+    fin = fin.cuda()
+    out_l, acts_l = h.forward(fin, layered=True)
+    out_f, acts_f = h.forward(fin)
+    out_i, acts_i = h.forward(fin, keep_acts=False)
+    assert acts_i is None
+    assert torch.equal(out_f, out_l) and torch.equal(out_i, out_l)
+    n = 11 * N * 512
+    assert torch.equal(acts_f.view(torch.bfloat16)[:n], acts_l.view(torch.bfloat16)[:n])
+    # and against fp32 math on the bf16-rounded operands (independent of both CUDA paths)
+    p = {k: v.detach().float().cpu() for k, v in mlp.named_parameters()}
+    ref = O.resnetfc(p, fin[:, :C + 42].float().cpu(), d_latent=C, operand_dtype=torch.bfloat16)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    assert rel(out_f, ref) < 3e-2
