@@ -35,27 +35,32 @@ static inline Epilogue<T> make_epilogue(const NrfGemm& g) {
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// ---- whole-MLP fused kernel (mlp_fused.cu): layer program built by mlp.cu
+// ---- whole-MLP fused kernel (mlp_fused.cu): layer programs built by mlp.cu, forward and backward
 constexpr int kFusedMaxLayers = 2 * NRF_MAX_BLOCKS + 2;
 struct FusedLayerDesc {
   const void* W;       // (512, ldw) bf16 row-major, K = 64 * (kb_main + kb_z) columns used
   int ldw;
-  int kb_main, kb_z;   // 64-wide k-blocks of the main operand / of the trailing latent part
-  int kind;            // 0: residual-stream layer (lin_in, fc_1)   1: fc_0   2: lin_out
-  int a_src;           // 0: field-input tile   1: relu(x') in TMEM   2: relu(net) in shared memory
-  int first;           // residual-stream layer that starts the stream (no residual added)
-  int act_slot;        // slot of the saved operand in `acts` (training), -1: nothing to save
-  const float* bias;
+  int kb_main, kb_z;   // 64-wide k-blocks of the main operand / of the trailing part read from `in`
+  int kind;            // 0: residual-stream layer (fwd: lin_in, fc_1; bwd: lin_out^T, fc_0^T)  1: fc_0 / fc_1^T
+                       // 2: lin_out (forward only, last)
+  int a_src;           // 0: rows of `in`   1: previous output in TMEM   2: previous output in shared memory
+  int first;           // residual-stream layer that starts the stream (nothing added)
+  int act_slot;        // slot of `saves` this layer's output operand is written to, -1: none
+  int mask_slot;       // backward: slot of `gates` whose sign gates this layer's output
+  const float* bias;   // forward
 };
-struct FusedFwdDesc {
+struct FusedDesc {
   int n_layers;
   FusedLayerDesc L[kFusedMaxLayers];
-  const void* field_in; int kin_pad; int kb_lat;
+  int backward;
+  const void* in; int in_cols;       // forward: field input (N, kin_pad); backward: d_field (N, dout_pad); bf16
   int64_t N;
-  void* acts; int n_slots;     // acts: n_slots x (N, 512) bf16, NULL = inference (nothing kept)
-  float* out; int d_out; int ldo;
+  void* saves; int n_slots;          // n_slots x (N, 512) bf16 written by the epilogues (forward: NULL = inference)
+  const void* gates;                 // backward: the forward's saves
+  float* out; int d_out; int ldo;    // forward: raw field outputs
+  void* prof;                        // optional: 32 int64 cycle counters per CTA (diagnostics), NULL otherwise
 };
-int mlp_fused_fwd_launch(const FusedFwdDesc& d, cudaStream_t stream);
+int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream);
 
 int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream);
 int gemm_simt_launch(const NrfGemm& g, cudaStream_t stream);

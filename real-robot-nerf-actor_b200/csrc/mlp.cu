@@ -180,7 +180,8 @@ extern "C" int nrf_mlp_sizes(const NrfMlpParams* p, int precision, NrfMlpSizes* 
   out->dout_pad = L.dout_pad;
   out->packed_bytes = L.total;
   out->fwd_bytes_per_sample = (int64_t)(2 * L.nb + 2) * L.H * L.es;
-  out->bwd_bytes_per_sample = (int64_t)(2 + L.nz) * L.H * L.es;
+  // layer-by-layer chain: dL/dx, dL/dnet and the n_lin_z kept gradients; fused chain: every dL/dx'_b and dL/dnet_b
+  out->bwd_bytes_per_sample = (int64_t)(2 * L.nb + 1 > 2 + L.nz ? 2 * L.nb + 1 : 2 + L.nz) * L.H * L.es;
   out->bwd_fixed_bytes = (int64_t)round_up(nrf_wgrad_workspace_bytes(L.H, L.H), 1024);
   return NRF_OK;
 }
@@ -201,9 +202,13 @@ static bool fused_supported(const MlpLayout& L) {
          L.nout_pad <= 512 && 2 * L.nb + 2 <= kFusedMaxLayers;
 }
 
+// diagnostics: device buffer (148 x 32 int64) that the next fused launches fill with per-role cycle counters
+static void* g_fused_prof = nullptr;
+extern "C" void nrf_debug_set_fused_profile(void* device_buffer) { g_fused_prof = device_buffer; }
+
 static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* W, const void* field_in, int64_t N,
                          void* acts, float* field_out, cudaStream_t s) {
-  FusedFwdDesc d;
+  FusedDesc d;
   memset(&d, 0, sizeof(d));
   const int kbH = L.H / 64, kbC = L.C / 64;
   int l = 0;
@@ -211,7 +216,7 @@ static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* 
                  const float* bias) {
     FusedLayerDesc& f = d.L[l++];
     f.W = Wl; f.ldw = ldw; f.kb_main = kb_main; f.kb_z = kb_z; f.kind = kind; f.a_src = a_src; f.first = first;
-    f.act_slot = slot; f.bias = bias;
+    f.act_slot = slot; f.mask_slot = -1; f.bias = bias;
   };
   // slots of `acts`: relu(x'_b) at b, relu(net_b) at nb + 1 + b (the layout nrf_mlp_bwd reads)
   add(W + L.W0, L.kin_pad, kbC + 1, 0, 0, 0, 1, 0, reinterpret_cast<const float*>(W + L.bias0));
@@ -222,11 +227,44 @@ static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* 
   }
   add(W + L.Wout, L.H, kbH, 0, 2, 1, 0, -1, reinterpret_cast<const float*>(W + L.bias_out));
   d.n_layers = l;
-  d.field_in = field_in; d.kin_pad = L.kin_pad; d.kb_lat = kbC;
+  d.in = field_in; d.in_cols = L.kin_pad;
   d.N = N;
-  d.acts = acts; d.n_slots = 2 * L.nb + 1;
+  d.saves = acts; d.n_slots = 2 * L.nb + 1;
   d.out = field_out; d.d_out = L.Dout; d.ldo = L.Dout;
-  return mlp_fused_fwd_launch(d, s);
+  d.prof = g_fused_prof;
+  return mlp_fused_launch(d, s);
+}
+
+// Backward data-gradient chain in the fused kernel.  G (slots x (N,H) bf16) receives dL/dx'_b at slot b and
+// dL/dnet_b at slot nb + 1 + b: the same slot numbering as the forward's `acts`, so that every weight gradient is
+// G[slot]^T . acts[slot'] (see nrf_mlp_bwd).
+static int mlp_bwd_fused(const MlpLayout& L, const char* W, const void* d_field, int64_t N, const void* acts,
+                         void* G, cudaStream_t s) {
+  FusedDesc d;
+  memset(&d, 0, sizeof(d));
+  const int kbH = L.H / 64;
+  int l = 0;
+  auto add = [&](const void* Wl, int ldw, int kb_main, int kind, int a_src, int first, int slot, int mask_slot) {
+    FusedLayerDesc& f = d.L[l++];
+    f.W = Wl; f.ldw = ldw; f.kb_main = kb_main; f.kb_z = 0; f.kind = kind; f.a_src = a_src; f.first = first;
+    f.act_slot = slot; f.mask_slot = mask_slot; f.bias = nullptr;
+  };
+  // dL/dx_nb = (d_field . W_out) gated by relu(x_nb) > 0
+  add(W + L.WoutT, L.dout_pad, L.dout_pad / 64, 0, 0, 1, L.nb, L.nb);
+  for (int b = L.nb - 1; b >= 0; --b) {
+    // dL/dnet_b = (dL/dx_{b+1} . W_fc1[b]) gated by relu(net_b) > 0
+    add(W + L.Wfc1T[b], L.H, kbH, 1, 1, 0, L.nb + 1 + b, L.nb + 1 + b);
+    // dL/dx'_b = dL/dx_{b+1} + (dL/dnet_b . W_fc0[b]) gated by relu(x'_b) > 0
+    add(W + L.Wfc0T[b], L.H, kbH, 0, 2, 0, b, b);
+  }
+  d.n_layers = l;
+  d.backward = 1;
+  d.in = d_field; d.in_cols = L.dout_pad;
+  d.N = N;
+  d.saves = G; d.n_slots = 2 * L.nb + 1;
+  d.gates = acts;
+  d.prof = g_fused_prof;
+  return mlp_fused_launch(d, s);
 }
 
 extern "C" int nrf_mlp_fused_supported(const NrfMlpParams* p, int precision) {
@@ -303,9 +341,9 @@ extern "C" int nrf_mlp_fwd_layered(const NrfMlpParams* p, const void* packed, in
   return mlp_fwd_impl(p, packed, precision, field_in, N, acts, field_out, stream, false);
 }
 
-extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
-                           int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* gr,
-                           float* dlatent, void* scratch, void* stream) {
+static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                        int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* gr,
+                        float* dlatent, void* scratch, void* stream, bool force_layered) {
   NRF_REQUIRE(packed && field_in && acts && d_field && gr && scratch && N > 0, NRF_EINVAL,
               "nrf_mlp_bwd: bad arguments");
   NRF_REQUIRE(N < (int64_t)1 << 31, NRF_ENOSUP, "nrf_mlp_bwd: N too large for one call");
@@ -327,6 +365,35 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
   char* dnet = gbuf + layer;
   auto gz = [&](int b) { return dnet + (int64_t)(1 + b) * layer; };   // dL/dx'_b kept for dL/dz, b < n_lin_z
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+
+  static const bool layered = getenv("NRF_MLP_LAYERED") != nullptr;
+  if (precision == NRF_PREC_BF16 && fused_supported(L) && !layered && !force_layered) {
+    // one fused kernel for the whole data-gradient chain, then the weight gradients and dL/dz from its outputs
+    char* G = sc + fixed;
+    auto gx = [&](int b) { return G + (int64_t)b * layer; };                 // dL/dx'_b, b = 0..nb
+    auto gn = [&](int b) { return G + (int64_t)(L.nb + 1 + b) * layer; };    // dL/dnet_b
+    TRY(mlp_bwd_fused(L, W, d_field, N, acts, G, s));
+    TRY(run_wgrad(d_field, L.dout_pad, ax(L.nb), L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H,
+                  gr->lin_out_b, wws, precision, s));
+    for (int b = L.nb - 1; b >= 0; --b) {
+      TRY(run_wgrad(gx(b + 1), L.H, an(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc1_w[b], L.H, gr->fc1_b[b], wws,
+                    precision, s));
+      if (b + 1 < L.nz)
+        TRY(run_wgrad(gx(b + 1), L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[b + 1],
+                      L.C, gr->lin_z_b[b + 1], wws, precision, s));
+      TRY(run_wgrad(gn(b), L.H, ax(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc0_w[b], L.H, gr->fc0_b[b], wws, precision, s));
+    }
+    NrfGemm g = gemm_init(N, (int)round_up(L.C, 128), L.C);
+    for (int b = 0; b < L.nz; ++b) set_a(g, b, gx(b), L.H, L.H);
+    g.B = W + L.WzcatT; g.ldb = L.nz * L.H;
+    g.out_f32 = dlatent; g.ldo = L.C;
+    TRY(run_gemm(g, precision, s));
+    TRY(run_wgrad(gx(0), L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[0], L.C,
+                  gr->lin_z_b[0], wws, precision, s));
+    TRY(run_wgrad(gx(0), L.H, fin + (int64_t)L.C * L.es, L.kin_pad, N, L.H, L.kin_pad - L.C, L.H, L.Din, gr->lin_in_w,
+                  L.Din, gr->lin_in_b, wws, precision, s));
+    return NRF_OK;
+  }
 
   // lin_out: parameter gradients, then the gradient of x_nb (ReLU-gated by relu(x_nb) > 0)
   TRY(run_wgrad(d_field, L.dout_pad, ax(L.nb), L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H,
@@ -386,4 +453,16 @@ extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precis
                 L.Din, gr->lin_in_b, wws, precision, s));
 #undef TRY
   return NRF_OK;
+}
+
+extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                           int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* gr,
+                           float* dlatent, void* scratch, void* stream) {
+  return mlp_bwd_impl(p, packed, precision, field_in, N, acts, d_field, gr, dlatent, scratch, stream, false);
+}
+
+extern "C" int nrf_mlp_bwd_layered(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                                   int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* gr,
+                                   float* dlatent, void* scratch, void* stream) {
+  return mlp_bwd_impl(p, packed, precision, field_in, N, acts, d_field, gr, dlatent, scratch, stream, true);
 }

@@ -23,6 +23,11 @@
 // (a_ready[kb]) and the tensor pipe never drains between layers - or between tiles: nothing but ring slots and
 // accumulator buffers is shared from one tile to the next.
 //
+// The same kernel runs the BACKWARD data-gradient chain (kBwd): lin_out^T, then per block fc_1^T and fc_0^T with the
+// ReLU gates read from the operands the forward saved, the gradient of the residual stream in the epilogue
+// registers, and every intermediate gradient (dL/dx'_b, dL/dnet_b: the G operands of the weight-gradient GEMMs)
+// streamed out by TMA stores.  Forward and backward are two "layer programs" for one executor.
+//
 // Warp roles: 0 TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator | 4-11 epilogue: warp (g, q4) owns
 // rows [32 q4, 32 q4 + 32) x columns [64g, 64g+64) of every 128-column chunk (= its rows of k-block 2c+g of the next
 // layer); the eight epilogue warps never synchronise with each other.
@@ -42,11 +47,11 @@ constexpr int kFSlot = 32 * 128;             // 4 KB: 32 rows x 64 bf16 (128B sw
 constexpr int kFSmemBar = 256;
 constexpr int kFSmemBias = 8 * 256;          // per epilogue warp: the 64 bias values of its current chunk
 constexpr int kFAlignSlack = 768;            // dynamic shared memory starts 1024-aligned in practice (checked)
-template <bool kTrain>
+template <bool kSave>
 struct FCfg {
-  static constexpr int kStages = kTrain ? 4 : 6;     // training gives 32 KB up for the relu(x') staging slots
+  static constexpr int kStages = kSave ? 4 : 6;      // saving gives 32 KB up for the staging slots
   static constexpr int kRing = kStages * kFStageB;
-  static constexpr int kStaging = kTrain ? 8 * kFSlot : 0;
+  static constexpr int kStaging = kSave ? 8 * kFSlot : 0;
   static constexpr int kSmem = kFSmemP + kRing + kStaging + kFSmemBar + kFSmemBias + kFAlignSlack;
   static_assert(kSmem <= 232448, "fused MLP kernel exceeds the 227 KB shared-memory limit");
 };
@@ -57,21 +62,25 @@ enum { kSrcIn = 0, kSrcQ = 1, kSrcP = 2 };
 
 struct FLayer {
   int kind, a_src, kb_main, kb_z, first, act_slot;
-  const float* bias;
+  int mask_slot;           // backward: slot of the forward's saved operand whose sign gates this layer's output
+  int publish;             // the epilogue hands its output to the next layer's MMAs (a_ready)
+  const float* bias;       // forward only
 };
 struct FArgs {
-  int n_layers, n_tiles, train;
+  int n_layers, n_tiles, n_prod;   // n_prod: layers per tile whose epilogue publishes an A operand
   int N, d_out, ldo;
   int dbg;      // NRF_DBG timing experiments (wrong results!): 1 no weight TMA, 2 epilogue protocol only, 4 no MMAs,
                 // 8 MMA issuer ignores acc_empty / a_ready
   float* out;
+  const __nv_bfloat16* mask_base;  // backward: the forward's `acts` (slots x (N,512) bf16)
+  long long* prof;                 // NRF_FUSED_PROF=1: per-CTA cycle counters of the warp roles (see mlp_fused_launch)
   FLayer L[kFusedMaxLayers];
 };
 struct FMaps {
   CUtensorMap w[kFusedMaxLayers];
-  CUtensorMap in;
+  CUtensorMap in;        // forward: field input (N, kin_pad); backward: d_field (N, dout_pad)
   CUtensorMap acts;      // (512, N, slots) bf16, box 64 x 32 x 1, 128B swizzle: a warp's 32 rows of one k-panel, from
-                         // the P panels (relu(net_b)) or from the warp's staging slot (relu(x'_b))
+                         // the P panels or from the warp's staging slot
 };
 
 __device__ __forceinline__ void umma_bf16_pair_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -118,6 +127,13 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t w) {    // bf16(relu(x)
   uint32_t r;
   asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(w), "r"(0u));
   return r;
+}
+
+// per-half 0xffff where the packed bf16 operand is non-zero (a ReLU output: non-zero <=> the gate is open)
+__device__ __forceinline__ uint32_t gate_mask_bf16x2(uint32_t r) {
+  uint32_t m;
+  asm("set.ne.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(r), "r"(0u));
+  return m;
 }
 
 // explicit shared-space accesses with 32-bit addresses (the aligned dynamic-smem base is a generic pointer to the
@@ -171,25 +187,48 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorM
       : "memory");
 }
 
+// cycle accounting of the waits (only when a.prof != NULL; one predictable branch per wait otherwise)
+#define FUSED_TIMED(acc, stmt)                         \
+  do {                                                 \
+    if (a.prof) {                                      \
+      const long long t0__ = clock64();                \
+      stmt;                                            \
+      acc += clock64() - t0__;                         \
+    } else {                                           \
+      stmt;                                            \
+    }                                                  \
+  } while (0)
+
 struct EpiCtx {            // per-thread constants of the epilogue
   uint32_t tmem_base, lane_off;
   uint32_t sP, slot, wbias;            // shared-space addresses: P, this warp's staging slot, this warp's bias values
   uint32_t acc_full, acc_empty, a_ready;
   int lane, g, q4, row;
-  uint32_t sw128, sw64;
+  uint32_t sw128;
+  long long t_wait;                    // cycles spent waiting for accumulators (profiling)
 };
 
 // One 128-column accumulator chunk of one layer, this thread's 64 columns.  KIND is the layer kind; xr is the thread's
-// slice of the residual stream for this chunk (used by kLayerX only).
-template <int KIND, bool kTrain>
-__device__ __forceinline__ void epi_chunk(const EpiCtx& e, const FMaps& maps, const FArgs& a, const FLayer& L, int c,
-                                          uint32_t n, int row0, bool first, bool save, uint32_t (&xr)[32],
-                                          const float* bnext) {
+// slice of the residual stream for this chunk (kLayerX only).
+//   forward : v = acc + bias (+ x' for kLayerX);  operand for the next layer = bf16(relu(v))
+//   backward: v = gate(acc) (+ g for kLayerX), gate = sign of the forward's saved operand; next operand = bf16(v)
+// `nxt` points at the next chunk's bias values (forward) or gate row (backward); both are prefetched here and parked
+// (bias: in the warp's smem slot; gates: in mk) until the next call.
+template <int KIND, bool kSave, bool kBwd>
+__device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FArgs& a, const FLayer& L, int c,
+                                          uint32_t n, int row0, bool first, uint32_t (&xr)[32], uint32_t (&mk)[32],
+                                          const void* nxt, const void* nxt2) {
   const uint32_t buf = n & 1;
   const int col0 = c * 128 + e.g * 64;         // first feature this thread handles in this chunk
-  // prefetch the next chunk's bias (2 values per lane), parked in registers until this chunk is done
-  const float bn0 = __ldg(bnext + e.lane), bn1 = __ldg(bnext + e.lane + 32);
-  mbar_wait_u32(e.acc_full + buf * 8, (n >> 1) & 1);
+  const bool save = kSave && L.act_slot >= 0;
+  float bn0 = 0.f, bn1 = 0.f;
+  if (!kBwd) {                                 // next chunk's bias: 2 values per lane, parked in registers
+    bn0 = __ldg(reinterpret_cast<const float*>(nxt) + e.lane);
+    bn1 = __ldg(reinterpret_cast<const float*>(nxt) + e.lane + 32);
+  } else {                                     // the gate row after next: pull its 128 B line into L2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt2));
+  }
+  FUSED_TIMED(e.t_wait, mbar_wait_u32(e.acc_full + buf * 8, (n >> 1) & 1));
   tc_fence_after();
   const uint32_t taddr = e.tmem_base + buf * 128 + e.g * 64 + e.lane_off;
   if (a.dbg & 2) {
@@ -197,7 +236,7 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& e, const FMaps& maps, co
     __syncwarp();
     if (e.lane == 0) {
       mbar_arrive_leader_u32(e.acc_empty + buf * 8);
-      if (KIND != kLayerOut) mbar_arrive_leader_u32(e.a_ready + (2 * c + e.g) * 8);
+      if (L.publish) mbar_arrive_leader_u32(e.a_ready + (2 * c + e.g) * 8);
     }
     return;
   }
@@ -211,12 +250,17 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& e, const FMaps& maps, co
   const uint32_t prow = e.sP + (2 * c + e.g) * kFPanel + e.row * 128;
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    uint64_t x2[16];                           // acc + bias, as fp32 pairs
+    uint64_t x2[16];                           // fp32 pairs
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 b = lds128f(e.wbias + (s * 32 + 4 * j) * 4);
-      x2[2 * j] = add2(pair_u32(v[s * 32 + 4 * j], v[s * 32 + 4 * j + 1]), pair_f32(b.x, b.y));
-      x2[2 * j + 1] = add2(pair_u32(v[s * 32 + 4 * j + 2], v[s * 32 + 4 * j + 3]), pair_f32(b.z, b.w));
+      if (!kBwd) {                             // acc + bias
+        const float4 b = lds128f(e.wbias + (s * 32 + 4 * j) * 4);
+        x2[2 * j] = add2(pair_u32(v[s * 32 + 4 * j], v[s * 32 + 4 * j + 1]), pair_f32(b.x, b.y));
+        x2[2 * j + 1] = add2(pair_u32(v[s * 32 + 4 * j + 2], v[s * 32 + 4 * j + 3]), pair_f32(b.z, b.w));
+      } else {
+        x2[2 * j] = pair_u32(v[s * 32 + 4 * j], v[s * 32 + 4 * j + 1]);
+        x2[2 * j + 1] = pair_u32(v[s * 32 + 4 * j + 2], v[s * 32 + 4 * j + 3]);
+      }
     }
     if (KIND == kLayerOut) {
       // raw field outputs, fp32, written row-wise (128 B per thread per sub-chunk)
@@ -235,16 +279,18 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& e, const FMaps& maps, co
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           uint64_t t = x2[j];
-          if (!first) {
-            const uint32_t r = xr[s * 16 + j];
-            t = add2(t, pair_u32(r << 16, r & 0xffff0000u));
+          const uint32_t r = xr[s * 16 + j];
+          if (!first) t = add2(t, pair_u32(r << 16, r & 0xffff0000u));
+          uint32_t xb = cvt_bf16x2(t);
+          if (kBwd) {                          // ReLU gate: closed -> the residual gradient passes unchanged
+            const uint32_t m = gate_mask_bf16x2(mk[s * 16 + j]);
+            xb = first ? (xb & m) : ((xb & m) | (r & ~m));
           }
-          const uint32_t xb = cvt_bf16x2(t);
           xr[s * 16 + j] = xb;
-          w[j] = relu_bf16x2(xb);
+          w[j] = kBwd ? xb : relu_bf16x2(xb);
         }
-        tmem_st16(e.tmem_base + kFColQ + e.lane_off + (uint32_t)(col0 / 2 + s * 16), w);
-        if (kTrain && save) {
+        if (L.publish) tmem_st16(e.tmem_base + kFColQ + e.lane_off + (uint32_t)(col0 / 2 + s * 16), w);
+        if (save) {
           if (s == 0) {                        // the slot's previous TMA store (a whole chunk ago) has read it
             if (e.lane == 0) bulk_wait_read0();
             __syncwarp();
@@ -256,7 +302,8 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& e, const FMaps& maps, co
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = relu_bf16x2(cvt_bf16x2(x2[j]));
+        for (int j = 0; j < 16; ++j)
+          w[j] = kBwd ? (cvt_bf16x2(x2[j]) & gate_mask_bf16x2(mk[s * 16 + j])) : relu_bf16x2(cvt_bf16x2(x2[j]));
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           sts128(prow + (((uint32_t)(s * 4 + j) ^ e.sw128) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
@@ -265,13 +312,13 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& e, const FMaps& maps, co
   }
   if (KIND != kLayerOut) {
     // publish this warp's rows of k-block 2c+g of the next layer's A operand to the MMA issuer
-    if (KIND == kLayerX) tmem_st_wait();
-    if (KIND == kLayerNet || (kTrain && save)) fence_proxy_async();
+    if (KIND == kLayerX && L.publish) tmem_st_wait();
+    if (KIND == kLayerNet || save) fence_proxy_async();
     tc_fence_before();
     __syncwarp();
     if (e.lane == 0) {
-      mbar_arrive_leader_u32(e.a_ready + (2 * c + e.g) * 8);
-      if (kTrain && save && !(a.dbg & (KIND == kLayerNet ? 64 : 32))) {
+      if (L.publish) mbar_arrive_leader_u32(e.a_ready + (2 * c + e.g) * 8);
+      if (save) {
         tma_store_3d_u32(&maps.acts, KIND == kLayerNet ? e.sP + (2 * c + e.g) * kFPanel + e.q4 * 32 * 128 : e.slot,
                          col0, row0 + e.q4 * 32, L.act_slot);
         bulk_commit();
@@ -280,15 +327,24 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& e, const FMaps& maps, co
   } else {
     __syncwarp();
   }
-  sts32f(e.wbias + e.lane * 4, bn0);           // every lane is past its reads of this chunk's bias
-  sts32f(e.wbias + (e.lane + 32) * 4, bn1);
-  __syncwarp();
+  if (!kBwd) {
+    sts32f(e.wbias + e.lane * 4, bn0);         // every lane is past its reads of this chunk's bias
+    sts32f(e.wbias + (e.lane + 32) * 4, bn1);
+    __syncwarp();
+  } else {                                     // next chunk's gate row: 128 B of the forward's saved operand
+    const uint4* m = reinterpret_cast<const uint4*>(nxt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 t = __ldg(m + j);
+      mk[4 * j] = t.x; mk[4 * j + 1] = t.y; mk[4 * j + 2] = t.z; mk[4 * j + 3] = t.w;
+    }
+  }
 }
 
-template <bool kTrain>
+template <bool kSave, bool kBwd>
 __global__ void __launch_bounds__(kFThreads, 1)
-mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FArgs a) {
-  using Cfg = FCfg<kTrain>;
+mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FArgs a) {
+  using Cfg = FCfg<kSave>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -317,7 +373,7 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < nl; ++l) tma_prefetch_desc(&maps.w[l]);
     tma_prefetch_desc(&maps.in);
-    if (kTrain) tma_prefetch_desc(&maps.acts);
+    if (kSave) tma_prefetch_desc(&maps.acts);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 2); mbar_init(empty + s, 1); }
@@ -334,12 +390,15 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    // A "unit" is a pair of k-blocks (the last one of a layer may be single).  Units whose A operand is the field
-    // input (layer 0; the latent tail of fc_1) take one ring stage per A k-panel followed by the weight stage; all
-    // other units take the weight stage only.  Producer and issuer walk the same sequence.
+    // A "unit" is a pair of k-blocks (the last one of a layer may be single).  Units whose A operand comes from
+    // global memory (forward: the field input of layer 0 and the latent tail of fc_1; backward: d_field) take one
+    // ring stage per A k-panel followed by the weight stage; all other units take the weight stage only.  Producer
+    // and issuer walk the same sequence.
     if (warp == 0) {
       // ---- TMA producer: runs ahead of the MMAs by the depth of the ring, across layers and tiles
       PipeState st;
+      long long t_empty = 0;
+      const long long t_begin = clock64();
       for (int it = 0; it < n_iter; ++it) {
         const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
         for (int l = 0; l < nl; ++l) {
@@ -349,9 +408,9 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
             for (int kb = 0; kb < kb_tot; kb += 2) {
               if (a.dbg & 1) continue;
               const int nk = kb_tot - kb < 2 ? 1 : 2;
-              if (in_main || kb >= kb_main) {          // this CTA's 128 rows of the field-input k-panels
+              if (in_main || kb >= kb_main) {          // this CTA's 128 rows of the global A k-panels
                 for (int h = 0; h < nk; ++h) {
-                  mbar_wait(empty + st.stage, st.phase ^ 1);
+                  FUSED_TIMED(t_empty, mbar_wait(empty + st.stage, st.phase ^ 1));
                   if (elect_one()) {
                     if (cta_leader) mbar_expect_tx(full + st.stage, 2 * kFPanel);
                     else mbar_arrive_leader(full + st.stage);
@@ -362,7 +421,7 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
                   st.advance(kStages);
                 }
               }
-              mbar_wait(empty + st.stage, st.phase ^ 1);
+              FUSED_TIMED(t_empty, mbar_wait(empty + st.stage, st.phase ^ 1));
               if (elect_one()) {
                 if (cta_leader) mbar_expect_tx(full + st.stage, 2 * nk * kFBoxB);
                 else mbar_arrive_leader(full + st.stage);
@@ -377,20 +436,26 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
             }
         }
       }
+      if (a.prof && lane == 0) {
+        a.prof[blockIdx.x * 32 + 0] = clock64() - t_begin;
+        a.prof[blockIdx.x * 32 + 1] = t_empty;
+      }
     } else if (warp == 1 && cta_leader) {
       // ---- MMA issuer for the pair: the whole warp runs the loop (uniform control flow), one elected lane issues
       constexpr uint32_t idesc = make_idesc(256, 128, 0, 0);
       const uint32_t sP_u = smem_u32(sP), sRing_u = smem_u32(sRing);
       PipeState st;
       uint32_t n = 0;                              // running chunk counter -> accumulator buffer / phase
+      long long t_acc = 0, t_ready = 0, t_full = 0;
+      const long long t_begin = clock64();
       for (int it = 0; it < n_iter; ++it) {
         for (int l = 0; l < nl; ++l) {
           const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
           const int a_src = a.L[l].a_src;
-          const uint32_t a_par = (uint32_t)(it * (nl - 1) + l - 1) & 1;   // phase of the epilogue that produced A
+          const uint32_t a_par = (uint32_t)(it * a.n_prod + l - 1) & 1;   // phase of the epilogue that produced A
           for (int c = 0; c < kFChunks; ++c, ++n) {
             const uint32_t buf = n & 1;
-            if (!(a.dbg & 8)) mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1);
+            if (!(a.dbg & 8)) FUSED_TIMED(t_acc, mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1));
             const uint32_t tmem_d = tmem_base + buf * 128;
             for (int kb0 = 0; kb0 < kb_tot; kb0 += 2) {
               const int nk = kb_tot - kb0 < 2 ? 1 : 2;
@@ -400,12 +465,12 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
               if (ext) {
                 sa0 = st.stage;
                 pa0 = sRing_u + st.stage * kFStageB;
-                if (!(a.dbg & 1)) mbar_wait(full + st.stage, st.phase);
+                if (!(a.dbg & 1)) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
                 st.advance(kStages);
                 if (nk == 2) {
                   sa1 = st.stage;
                   pa1 = sRing_u + st.stage * kFStageB;
-                  if (!(a.dbg & 1)) mbar_wait(full + st.stage, st.phase);
+                  if (!(a.dbg & 1)) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
                   st.advance(kStages);
                 }
               } else if (a_src == kSrcP) {
@@ -413,10 +478,10 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
                 pa1 = pa0 + kFPanel;
               }
               if (!ext && c == 0 && !(a.dbg & 8)) {     // produced by the previous layer's epilogue
-                mbar_wait(a_ready + kb0, a_par);
-                if (nk == 2) mbar_wait(a_ready + kb0 + 1, a_par);
+                FUSED_TIMED(t_ready, mbar_wait(a_ready + kb0, a_par));
+                if (nk == 2) FUSED_TIMED(t_ready, mbar_wait(a_ready + kb0 + 1, a_par));
               }
-              if (!(a.dbg & 1)) mbar_wait(full + st.stage, st.phase);
+              if (!(a.dbg & 1)) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
               tc_fence_after();
               const uint32_t sb = sRing_u + st.stage * kFStageB;
               if (elect_one()) {
@@ -454,6 +519,12 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
           }
         }
       }
+      if (a.prof && lane == 0) {
+        a.prof[blockIdx.x * 32 + 2] = clock64() - t_begin;
+        a.prof[blockIdx.x * 32 + 3] = t_acc;
+        a.prof[blockIdx.x * 32 + 4] = t_ready;
+        a.prof[blockIdx.x * 32 + 5] = t_full;
+      }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
@@ -469,48 +540,66 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
     e.row = e.q4 * 32 + lane;
     e.lane_off = (uint32_t)(e.q4 * 32) << 16;
     e.sw128 = (uint32_t)(e.row & 7);
-    e.sw64 = (uint32_t)((e.row >> 1) & 3);
     e.sP = smem_u32(sP);
-    e.slot = smem_u32(sStage) + ew * kFSlot;         // this warp's staging slot (training)
+    e.slot = smem_u32(sStage) + ew * kFSlot;         // this warp's staging slot
     e.wbias = smem_u32(sBias) + ew * 256;            // this warp's bias values of the current chunk
     e.acc_full = smem_u32(acc_full);
     e.acc_empty = smem_u32(acc_empty);
     e.a_ready = smem_u32(a_ready);
+    e.t_wait = 0;
+    const long long t_begin = clock64();
     const int g = e.g;
-    uint32_t xres[kFChunks][32];                     // this thread's slice of the bf16 residual stream x'
+    uint32_t xres[kFChunks][32];                     // this thread's slice of the bf16 residual stream (x' or dL/dx')
+    uint32_t mk[32];                                 // backward: this thread's gate row of the current chunk
     uint32_t n = 0;
-    // bias of the first chunk
-    sts32f(e.wbias + lane * 4, __ldg(a.L[0].bias + g * 64 + lane));
-    sts32f(e.wbias + (lane + 32) * 4, __ldg(a.L[0].bias + g * 64 + lane + 32));
-    __syncwarp();
+    // what the next chunk (c of layer l of this CTA's tile `it`) needs prefetched: its bias values / its gate row
+    auto pre = [&](int it, int l, int c) -> const void* {
+      if (c >= kFChunks) { c -= kFChunks; ++l; }
+      if (l == nl) { l = 0; ++it; }
+      if (!kBwd) return a.L[l].bias + c * 128 + g * 64;
+      int64_t r = (int64_t)((pair + it * n_pairs) * 2 + (int)crank) * 128 + e.row;
+      if (r > a.N - 1) r = a.N - 1;                  // ragged tail / past the last tile: any valid row will do
+      return a.mask_base + ((int64_t)a.L[l].mask_slot * a.N + r) * 512 + c * 128 + g * 64;
+    };
+    if (!kBwd) {
+      const float* b0 = reinterpret_cast<const float*>(pre(0, 0, 0));
+      sts32f(e.wbias + lane * 4, __ldg(b0 + lane));
+      sts32f(e.wbias + (lane + 32) * 4, __ldg(b0 + lane + 32));
+      __syncwarp();
+    } else {
+      const uint4* m = reinterpret_cast<const uint4*>(pre(0, 0, 0));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 t = __ldg(m + j);
+        mk[4 * j] = t.x; mk[4 * j + 1] = t.y; mk[4 * j + 2] = t.z; mk[4 * j + 3] = t.w;
+      }
+    }
     for (int it = 0; it < n_iter; ++it) {
       const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
       for (int l = 0; l < nl; ++l) {
         const FLayer& L = a.L[l];
         const int kind = L.kind;
         const bool first = L.first != 0;
-        const bool save = kTrain && L.act_slot >= 0;
-        const float* bias_next_layer = a.L[l + 1 < nl ? l + 1 : 0].bias + g * 64;
-        const float* bias_l = L.bias + g * 64;
         if (kind == kLayerX) {
 #pragma unroll
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerX, kTrain>(e, maps, a, L, c, n, row0, first, save, xres[c],
-                                       c + 1 < kFChunks ? bias_l + (c + 1) * 128 : bias_next_layer);
+            epi_chunk<kLayerX, kSave, kBwd>(e, maps, a, L, c, n, row0, first, xres[c], mk, pre(it, l, c + 1), pre(it, l, c + 2));
         } else if (kind == kLayerNet) {
 #pragma unroll 1
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerNet, kTrain>(e, maps, a, L, c, n, row0, false, save, xres[0],
-                                         c + 1 < kFChunks ? bias_l + (c + 1) * 128 : bias_next_layer);
-        } else {
+            epi_chunk<kLayerNet, kSave, kBwd>(e, maps, a, L, c, n, row0, false, xres[0], mk, pre(it, l, c + 1), pre(it, l, c + 2));
+        } else if (!kBwd) {
 #pragma unroll 1
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerOut, kTrain>(e, maps, a, L, c, n, row0, false, false, xres[0],
-                                         c + 1 < kFChunks ? bias_l + (c + 1) * 128 : bias_next_layer);
+            epi_chunk<kLayerOut, kSave, kBwd>(e, maps, a, L, c, n, row0, false, xres[0], mk, pre(it, l, c + 1), pre(it, l, c + 2));
         }
       }
     }
-    if (kTrain && lane == 0) bulk_wait_all();
+    if (a.prof && lane == 0) {
+      a.prof[blockIdx.x * 32 + 8 + 2 * ew] = clock64() - t_begin;
+      a.prof[blockIdx.x * 32 + 9 + 2 * ew] = e.t_wait;
+    }
+    if (kSave && lane == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -521,15 +610,15 @@ mlp_fused_fwd_kernel(const __grid_constant__ FMaps maps, const __grid_constant__
   }
 }
 
-static int make_acts_map(CUtensorMap* map, void* acts, int64_t N, int n_slots, int box_cols, CUtensorMapSwizzle sw) {
+static int make_acts_map(CUtensorMap* map, void* acts, int64_t N, int n_slots) {
   EncodeTiledFn fn = encode_tiled_fn();
   NRF_REQUIRE(fn != nullptr, NRF_ECUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t gdim[3] = {512, (cuuint64_t)N, (cuuint64_t)n_slots};
   cuuint64_t gstride[2] = {512 * 2, (cuuint64_t)N * 512 * 2};
-  cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1};
+  cuuint32_t box[3] = {64, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, acts, gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NRF_REQUIRE(r == CUDA_SUCCESS, NRF_ECUDA, "cuTensorMapEncodeTiled(acts) failed (%d)", (int)r);
   return NRF_OK;
@@ -537,42 +626,52 @@ static int make_acts_map(CUtensorMap* map, void* acts, int64_t N, int n_slots, i
 
 }  // namespace
 
-int mlp_fused_fwd_launch(const FusedFwdDesc& d, cudaStream_t stream) {
+int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
   NRF_REQUIRE(d.n_layers >= 2 && d.n_layers <= kFusedMaxLayers, NRF_EINVAL, "mlp_fused: %d layers", d.n_layers);
-  NRF_REQUIRE(d.kin_pad % 64 == 0 && d.kin_pad >= 64, NRF_ENOSUP, "mlp_fused: kin_pad=%d", d.kin_pad);
+  NRF_REQUIRE(d.in_cols % 64 == 0 && d.in_cols >= 64, NRF_ENOSUP, "mlp_fused: %d input columns", d.in_cols);
+  NRF_REQUIRE(!d.backward || (d.saves && d.gates), NRF_EINVAL, "mlp_fused: the backward needs saves and gates");
   FMaps maps;
   FArgs a;
   memset(&a, 0, sizeof(a));
   int rc;
+  int n_prod = 0;
   for (int l = 0; l < d.n_layers; ++l) {
     const FusedLayerDesc& L = d.L[l];
     const int ktot = (L.kb_main + L.kb_z) * 64;
     if ((rc = make_map(&maps.w[l], L.W, ktot, 512, L.ldw, 64, 64))) return rc;   // box = one k-block of a CTA's 64 rows
-    NRF_REQUIRE((reinterpret_cast<uintptr_t>(L.bias) & 15) == 0 && L.bias, NRF_EINVAL, "mlp_fused: bias alignment");
+    NRF_REQUIRE(d.backward || ((reinterpret_cast<uintptr_t>(L.bias) & 15) == 0 && L.bias), NRF_EINVAL,
+                "mlp_fused: bias alignment");
     a.L[l].kind = L.kind; a.L[l].a_src = L.a_src; a.L[l].kb_main = L.kb_main; a.L[l].kb_z = L.kb_z;
-    a.L[l].first = L.first; a.L[l].act_slot = L.act_slot; a.L[l].bias = L.bias;
+    a.L[l].first = L.first; a.L[l].act_slot = d.saves ? L.act_slot : -1; a.L[l].bias = L.bias;
+    a.L[l].mask_slot = L.mask_slot;
+    a.L[l].publish = l + 1 < d.n_layers && L.kind != 2;
+    n_prod += a.L[l].publish;
   }
   for (int l = d.n_layers; l < kFusedMaxLayers; ++l) maps.w[l] = maps.w[0];
-  if ((rc = make_map(&maps.in, d.field_in, d.kin_pad, d.N, d.kin_pad, 64, 128))) return rc;
-  const bool train = d.acts != nullptr;
-  if (train) {
-    if ((rc = make_acts_map(&maps.acts, d.acts, d.N, d.n_slots, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&maps.in, d.in, d.in_cols, d.N, d.in_cols, 64, 128))) return rc;
+  const bool save = d.saves != nullptr;
+  if (save) {
+    if ((rc = make_acts_map(&maps.acts, d.saves, d.N, d.n_slots))) return rc;
   } else {
     maps.acts = maps.in;
   }
   a.n_layers = d.n_layers;
   a.n_tiles = (int)((d.N + 255) / 256);
-  a.train = train;
+  a.n_prod = n_prod;
+  NRF_REQUIRE(n_prod == d.n_layers - 1, NRF_EINVAL, "mlp_fused: every layer but the last must feed the next");
   a.N = (int)d.N; a.d_out = d.d_out; a.ldo = d.ldo; a.out = d.out;
+  a.mask_base = reinterpret_cast<const __nv_bfloat16*>(d.gates);
   { const char* e = getenv("NRF_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.prof = reinterpret_cast<long long*>(d.prof);
   int grid = sm_count() / 2 * 2;
   if (grid > 2 * a.n_tiles) grid = 2 * a.n_tiles;
-  auto kern = train ? mlp_fused_fwd_kernel<true> : mlp_fused_fwd_kernel<false>;
-  const int smem_bytes = train ? FCfg<true>::kSmem : FCfg<false>::kSmem;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[train]) {
+  auto kern = d.backward ? mlp_fused_kernel<true, true> : (save ? mlp_fused_kernel<true, false> : mlp_fused_kernel<false, false>);
+  const int which = d.backward ? 2 : (save ? 1 : 0);
+  const int smem_bytes = save ? FCfg<true>::kSmem : FCfg<false>::kSmem;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[which]) {
     NRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set[train] = true;
+    attr_set[which] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -581,7 +680,7 @@ int mlp_fused_fwd_launch(const FusedFwdDesc& d, cudaStream_t stream) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kFThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
-  { LaunchScope ls_(NRF_CAT_FUSED_FWD, stream);
+  { LaunchScope ls_(d.backward ? NRF_CAT_FUSED_BWD : NRF_CAT_FUSED_FWD, stream);
   NRF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, a));
   }
   NRF_LAUNCH_OK();

@@ -344,7 +344,7 @@ class FieldMLP:
                  ptr(acts), ptr(out), stream_ptr()), "nrf_mlp_fwd")
         return out, acts
 
-    def backward(self, field_in, acts, d_field, grads: dict, scratch=None, deterministic=False):
+    def backward(self, field_in, acts, d_field, grads: dict, scratch=None, deterministic=False, layered=False):
         """Accumulates parameter grads into `grads` (same keys as params); returns dlatent (N,C).
         deterministic: ordered (bit-reproducible) reduction of the weight-gradient sample splits."""
         N = field_in.shape[0]
@@ -357,7 +357,9 @@ class FieldMLP:
         dlatent = torch.empty(N, d_latent, device=dev, dtype=torch.float32)
         g = self._fill(_lib.NrfMlpGrads(), lambda n: grads[n].data_ptr() if grads.get(n) is not None else None)
         g.deterministic = int(bool(deterministic))
-        check(_lib.load().nrf_mlp_bwd(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
-                                      ptr(acts), ptr(d_field), C.byref(g), ptr(dlatent), ptr(scratch),
-                                      stream_ptr()), "nrf_mlp_bwd")
+        lib = _lib.load()
+        fn = lib.nrf_mlp_bwd_layered if layered else lib.nrf_mlp_bwd
+        check(fn(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
+                 ptr(acts), ptr(d_field), C.byref(g), ptr(dlatent), ptr(scratch),
+                 stream_ptr()), "nrf_mlp_bwd")
         return dlatent
