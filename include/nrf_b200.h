@@ -212,7 +212,9 @@ int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precision, const 
 /* bf16 mode, when nrf_mlp_fused_supported(): nrf_mlp_bwd runs the whole data-gradient chain (lin_out^T, fc_1^T,
  * fc_0^T per block, ReLU gates from `acts`, residual gradient in registers) as ONE persistent tcgen05 kernel that
  * streams every dL/dx'_b and dL/dnet_b into `scratch`, followed by the weight-gradient GEMMs and one GEMM for
- * dL/dlatent.  nrf_mlp_bwd_layered always runs the per-layer chain. */
+ * dL/dlatent.  It reads the ReLU gates bit-packed (64 B per sample and saved operand) from the last layer of
+ * `acts`, where only the fused nrf_mlp_fwd writes them: pair nrf_mlp_fwd with nrf_mlp_bwd and nrf_mlp_fwd_layered
+ * with nrf_mlp_bwd_layered (which always runs the per-layer chain). */
 int nrf_mlp_bwd_layered(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
                         int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* grads,
                         float* dlatent, void* scratch, void* stream);

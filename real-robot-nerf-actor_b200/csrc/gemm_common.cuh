@@ -46,7 +46,7 @@ struct FusedLayerDesc {
   int a_src;           // 0: rows of `in`   1: previous output in TMEM   2: previous output in shared memory
   int first;           // residual-stream layer that starts the stream (nothing added)
   int act_slot;        // slot of `saves` this layer's output operand is written to, -1: none
-  int mask_slot;       // backward: slot of `gates` whose sign gates this layer's output
+  int mask_slot;       // backward: slot of the forward's saved operand whose ReLU gate applies to this layer's output
   const float* bias;   // forward
 };
 struct FusedDesc {
@@ -56,7 +56,8 @@ struct FusedDesc {
   const void* in; int in_cols;       // forward: field input (N, kin_pad); backward: d_field (N, dout_pad); bf16
   int64_t N;
   void* saves; int n_slots;          // n_slots x (N, 512) bf16 written by the epilogues (forward: NULL = inference)
-  const void* gates;                 // backward: the forward's saves
+  void* gate_bits;                   // slots x (N, 64 B) bit-packed ReLU gates: written by the saving forward, read
+                                     // by the backward (same slot numbering as `saves` of the forward)
   float* out; int d_out; int ldo;    // forward: raw field outputs
   void* prof;                        // optional: 32 int64 cycle counters per CTA (diagnostics), NULL otherwise
 };

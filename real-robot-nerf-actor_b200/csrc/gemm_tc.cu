@@ -68,7 +68,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 2 * Cfg::kInSlots);
   float* sbias = reinterpret_cast<float*>(epi + Cfg::kEpiBufs * Cfg::kEpiBuf + 512);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   const int m_tiles = (a.M + kTileM - 1) / kTileM, n_tiles = a.N / BN;
   const int kb01 = a.kb[0] + a.kb[1];
   const int num_kb = kb01 + a.kb[2];
@@ -109,17 +109,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      PipeState st;
-      for (int it = 0; it < n_iter; ++it) {
-        int m_blk, n_blk;
-        tile_of(it, m_blk, n_blk);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty + st.stage, st.phase ^ 1);
-          uint8_t* sa = smem + st.stage * Cfg::kStage;
-          uint8_t* sb = sa + Cfg::kStageA;
-          const CUtensorMap* mapA = kb < a.kb[0] ? &tmA0 : (kb < kb01 ? &tmA1 : &tmA2);
-          const int kcol = (kb < a.kb[0] ? kb : (kb < kb01 ? kb - a.kb[0] : kb - kb01)) * kTileK;
+    // whole warp runs the loop (uniform control flow: addresses stay in uniform registers), one elected lane issues
+    PipeState st;
+    for (int it = 0; it < n_iter; ++it) {
+      int m_blk, n_blk;
+      tile_of(it, m_blk, n_blk);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty + st.stage, st.phase ^ 1);
+        uint8_t* sa = smem + st.stage * Cfg::kStage;
+        uint8_t* sb = sa + Cfg::kStageA;
+        const CUtensorMap* mapA = kb < a.kb[0] ? &tmA0 : (kb < kb01 ? &tmA1 : &tmA2);
+        const int kcol = (kb < a.kb[0] ? kb : (kb < kb01 ? kb - a.kb[0] : kb - kb01)) * kTileK;
+        if (elect_one()) {
           if (CG == 2) {
             // both CTAs' loads complete on the LEADER's barrier (it issues the MMAs for the pair)
             if (cta_leader) mbar_expect_tx(full + st.stage, 2 * Cfg::kStage);
@@ -131,19 +132,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tma_load_2d(sa, mapA, full + st.stage, kcol, m_blk * kTileM);
             tma_load_2d(sb, &tmB, full + st.stage, kb * kTileK, n_blk * BN);
           }
-          st.advance(Cfg::kStages);
         }
+        __syncwarp();
+        st.advance(Cfg::kStages);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && cta_leader) {
+    if (cta_leader) {
       constexpr uint32_t idesc = make_idesc(kTileM * CG, BN, 0, 0);
       PipeState st;
       for (int it = 0; it < n_iter; ++it) {
         int as = it & 1;
         uint32_t aphase = (it >> 1) & 1;
         mbar_wait(acc_empty + as, aphase ^ 1);
-        tc_fence_after();
         uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full + st.stage, st.phase);
@@ -152,18 +153,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           uint32_t sb = sa + Cfg::kStageA;
           uint64_t adesc = make_sdesc(sa, 16, 1024);
           uint64_t bdesc = make_sdesc(sb, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kTileK / kUmmaK; ++k) {
-            // +32 B per 16-element K step inside the 128 B swizzle row: +2 in the 16 B address field
-            if (CG == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kTileK / kUmmaK; ++k) {
+              // +32 B per 16-element K step inside the 128 B swizzle row: +2 in the 16 B address field
+              if (CG == 2) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
+            if (CG == 2) umma_commit_pair(empty + st.stage);      // frees the stage in both CTAs
+            else umma_commit(empty + st.stage);
           }
-          if (CG == 2) umma_commit_pair(empty + st.stage);      // frees the stage in both CTAs
-          else umma_commit(empty + st.stage);
+          __syncwarp();
           st.advance(Cfg::kStages);
         }
-        if (CG == 2) umma_commit_pair(acc_full + as);           // both CTAs' epilogues
-        else umma_commit(acc_full + as);
+        if (elect_one()) {
+          if (CG == 2) umma_commit_pair(acc_full + as);           // both CTAs' epilogues
+          else umma_commit(acc_full + as);
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -387,7 +394,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   uint64_t* acc_full = empty + Cfg::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   const int n_blk = blockIdx.x / k_tiles, k_blk = blockIdx.x % k_tiles;
   const int m_begin = blockIdx.y * m_per_split;
   const int m_end = min(M, m_begin + m_per_split);
@@ -414,14 +421,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      PipeState st;
-      for (int mb = 0; mb < num_mb; ++mb) {
-        mbar_wait(empty + st.stage, st.phase ^ 1);
-        uint8_t* sg = smem + st.stage * Cfg::kStage;
-        uint8_t* sa = sg + Cfg::kStageG;
+    PipeState st;
+    for (int mb = 0; mb < num_mb; ++mb) {
+      mbar_wait(empty + st.stage, st.phase ^ 1);
+      uint8_t* sg = smem + st.stage * Cfg::kStage;
+      uint8_t* sa = sg + Cfg::kStageG;
+      int m0 = m_begin + mb * kTileK;
+      if (elect_one()) {
         mbar_expect_tx(full + st.stage, Cfg::kStage);
-        int m0 = m_begin + mb * kTileK;
         // rows >= M are zero-filled by TMA; rows in [m_end, M) of the last chunk belong to the next
         // split, so chunks are aligned: m_per_split is a multiple of 64.
 #pragma unroll
@@ -430,22 +437,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
 #pragma unroll
         for (int s = 0; s < BK_ / 64; ++s)
           tma_load_2d(sa + s * (kTileK * 128), &tmA, full + st.stage, k_blk * BK_ + s * 64, m0);
-        st.advance(Cfg::kStages);
       }
+      __syncwarp();
+      st.advance(Cfg::kStages);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kTileM, BK_, 1, 1);
-      constexpr uint32_t idesc_bias = make_idesc(kTileM, 16, 1, 1);
-      const uint64_t odesc = make_sdesc(smem_u32(ones), kTileK * 128, 1024);
-      PipeState st;
-      for (int mb = 0; mb < num_mb; ++mb) {
-        mbar_wait(full + st.stage, st.phase);
-        tc_fence_after();
-        uint32_t sg = smem_u32(smem + st.stage * Cfg::kStage);
-        uint32_t sa = sg + Cfg::kStageG;
-        uint64_t gdesc = make_sdesc(sg, kTileK * 128, 1024);
-        uint64_t adesc = make_sdesc(sa, kTileK * 128, 1024);
+    constexpr uint32_t idesc = make_idesc(kTileM, BK_, 1, 1);
+    constexpr uint32_t idesc_bias = make_idesc(kTileM, 16, 1, 1);
+    const uint64_t odesc = make_sdesc(smem_u32(ones), kTileK * 128, 1024);
+    PipeState st;
+    for (int mb = 0; mb < num_mb; ++mb) {
+      mbar_wait(full + st.stage, st.phase);
+      tc_fence_after();
+      uint32_t sg = smem_u32(smem + st.stage * Cfg::kStage);
+      uint32_t sa = sg + Cfg::kStageG;
+      uint64_t gdesc = make_sdesc(sg, kTileK * 128, 1024);
+      uint64_t adesc = make_sdesc(sa, kTileK * 128, 1024);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kTileK / kUmmaK; ++k) {
           // 16 samples = two 8-row atoms = 2048 B: +128 in the 16 B address field
@@ -453,10 +461,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
           if (do_bias) umma_bf16(tmem_base + BK_, gdesc + 128 * k, odesc, idesc_bias, (mb | k) != 0);
         }
         umma_commit(empty + st.stage);
-        st.advance(Cfg::kStages);
       }
-      umma_commit(acc_full);
+      __syncwarp();
+      st.advance(Cfg::kStages);
     }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
   } else if (warp >= kEpiWarp0) {
     const int q = warp - kEpiWarp0;
     if (num_mb > 0) {

@@ -198,7 +198,8 @@ extern "C" int nrf_mlp_pack(const NrfMlpParams* p, int precision, void* packed, 
 // The fused kernel is built for the reference's field MLP: 512 hidden units, a latent of 64 or 128 channels that
 // fills whole k-blocks, PE + viewdir in one k-block.  Anything else runs the layer-by-layer chain below.
 static bool fused_supported(const MlpLayout& L) {
-  return L.H == 512 && L.es == 2 && (L.C == 64 || L.C == 128) && L.kin_pad == L.C + 64 && L.nz >= 1 &&
+  // (2 nb + 1) slots x 64 B of gate bits per sample must fit the spare activation layer (H * es bytes per sample)
+  return (2 * L.nb + 1) * 64 <= L.H * (int)L.es && L.H == 512 && L.es == 2 && (L.C == 64 || L.C == 128) && L.kin_pad == L.C + 64 && L.nz >= 1 &&
          L.nout_pad <= 512 && 2 * L.nb + 2 <= kFusedMaxLayers;
 }
 
@@ -230,6 +231,8 @@ static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* 
   d.in = field_in; d.in_cols = L.kin_pad;
   d.N = N;
   d.saves = acts; d.n_slots = 2 * L.nb + 1;
+  // the layer-by-layer chain keeps the residual stream in the last layer of `acts`; here it holds the gate bits
+  d.gate_bits = acts ? reinterpret_cast<char*>(acts) + (int64_t)(2 * L.nb + 1) * N * L.H * (int64_t)L.es : nullptr;
   d.out = field_out; d.d_out = L.Dout; d.ldo = L.Dout;
   d.prof = g_fused_prof;
   return mlp_fused_launch(d, s);
@@ -262,7 +265,7 @@ static int mlp_bwd_fused(const MlpLayout& L, const char* W, const void* d_field,
   d.in = d_field; d.in_cols = L.dout_pad;
   d.N = N;
   d.saves = G; d.n_slots = 2 * L.nb + 1;
-  d.gates = acts;
+  d.gate_bits = const_cast<char*>(reinterpret_cast<const char*>(acts)) + (int64_t)(2 * L.nb + 1) * N * L.H * (int64_t)L.es;
   d.prof = g_fused_prof;
   return mlp_fused_launch(d, s);
 }

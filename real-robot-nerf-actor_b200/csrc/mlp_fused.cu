@@ -72,7 +72,8 @@ struct FArgs {
   int dbg;      // NRF_DBG timing experiments (wrong results!): 1 no weight TMA, 2 epilogue protocol only, 4 no MMAs,
                 // 8 MMA issuer ignores acc_empty / a_ready
   float* out;
-  const __nv_bfloat16* mask_base;  // backward: the forward's `acts` (slots x (N,512) bf16)
+  uint2* gate_bits;                // slots x (N, 8) x 64 bits: bit-packed ReLU gates, written by the training forward
+                                   // (one bit per saved operand element: non-zero) and read by the backward
   long long* prof;                 // NRF_FUSED_PROF=1: per-CTA cycle counters of the warp roles (see mlp_fused_launch)
   FLayer L[kFusedMaxLayers];
 };
@@ -129,10 +130,18 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t w) {    // bf16(relu(x)
   return r;
 }
 
-// per-half 0xffff where the packed bf16 operand is non-zero (a ReLU output: non-zero <=> the gate is open)
-__device__ __forceinline__ uint32_t gate_mask_bf16x2(uint32_t r) {
-  uint32_t m;
-  asm("set.ne.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(r), "r"(0u));
+// Bit-packed ReLU gates.  A gate word covers one 32-column sub-chunk of one row: bit j / bit 16+j = element 2j /
+// 2j+1 of the saved (ReLU'd, packed bf16) operand is non-zero.
+//   forward : 16 x gate_push(G, w_j)   (w + 0x7fff7fff carries "non-zero" into bits 15 / 31 of a non-negative pair)
+//   backward: gate_mask(G, j) = per-half 0xffff / 0 for pair j  (shift the two flags to the byte MSBs, PRMT
+//             replicates them over the halves)
+__device__ __forceinline__ uint32_t gate_push(uint32_t G, uint32_t w) {
+  const uint32_t t = w + 0x7fff7fffu;
+  return ((G >> 1) & 0x7fff7fffu) | (t & 0x80008000u);
+}
+__device__ __forceinline__ uint32_t gate_mask(uint32_t G, int j) {
+  uint32_t m;                                  // selector nibble 8+k: the MSB of byte k replicated over the byte
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(G << (15 - j)), "r"(0u), "r"(0xBB99u));
   return m;
 }
 
@@ -212,12 +221,12 @@ struct EpiCtx {            // per-thread constants of the epilogue
 // slice of the residual stream for this chunk (kLayerX only).
 //   forward : v = acc + bias (+ x' for kLayerX);  operand for the next layer = bf16(relu(v))
 //   backward: v = gate(acc) (+ g for kLayerX), gate = sign of the forward's saved operand; next operand = bf16(v)
-// `nxt` points at the next chunk's bias values (forward) or gate row (backward); both are prefetched here and parked
-// (bias: in the warp's smem slot; gates: in mk) until the next call.
+// Prefetched here and parked until needed: the next chunk's bias values (`nxt`, forward: into the warp's smem slot) or
+// the gate row of the chunk after next (`nxt2`, backward: into mk, which the caller double-buffers by chunk parity).
 template <int KIND, bool kSave, bool kBwd>
 __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FArgs& a, const FLayer& L, int c,
-                                          uint32_t n, int row0, bool first, uint32_t (&xr)[32], uint32_t (&mk)[32],
-                                          const void* nxt, const void* nxt2) {
+                                          uint32_t n, int row0, bool first, uint32_t (&xr)[32], uint2& gate,
+                                          const void* nxt, const uint2* gate2) {
   const uint32_t buf = n & 1;
   const int col0 = c * 128 + e.g * 64;         // first feature this thread handles in this chunk
   const bool save = kSave && L.act_slot >= 0;
@@ -225,8 +234,6 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
   if (!kBwd) {                                 // next chunk's bias: 2 values per lane, parked in registers
     bn0 = __ldg(reinterpret_cast<const float*>(nxt) + e.lane);
     bn1 = __ldg(reinterpret_cast<const float*>(nxt) + e.lane + 32);
-  } else {                                     // the gate row after next: pull its 128 B line into L2
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt2));
   }
   FUSED_TIMED(e.t_wait, mbar_wait_u32(e.acc_full + buf * 8, (n >> 1) & 1));
   tc_fence_after();
@@ -247,9 +254,11 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
   tc_fence_before();                           // the accumulator buffer is free again
   __syncwarp();
   if (e.lane == 0) mbar_arrive_leader_u32(e.acc_empty + buf * 8);
+  uint32_t gout[2] = {0u, 0u};                 // forward (training): the gate words of this thread's 64 outputs
   const uint32_t prow = e.sP + (2 * c + e.g) * kFPanel + e.row * 128;
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
+    const uint32_t gw = s == 0 ? gate.x : gate.y;    // backward: gate word of this sub-chunk
     uint64_t x2[16];                           // fp32 pairs
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -283,11 +292,12 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
           if (!first) t = add2(t, pair_u32(r << 16, r & 0xffff0000u));
           uint32_t xb = cvt_bf16x2(t);
           if (kBwd) {                          // ReLU gate: closed -> the residual gradient passes unchanged
-            const uint32_t m = gate_mask_bf16x2(mk[s * 16 + j]);
+            const uint32_t m = gate_mask(gw, j);
             xb = first ? (xb & m) : ((xb & m) | (r & ~m));
           }
           xr[s * 16 + j] = xb;
           w[j] = kBwd ? xb : relu_bf16x2(xb);
+          if (kSave && !kBwd) gout[s] = gate_push(gout[s], w[j]);
         }
         if (L.publish) tmem_st16(e.tmem_base + kFColQ + e.lane_off + (uint32_t)(col0 / 2 + s * 16), w);
         if (save) {
@@ -302,8 +312,10 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          w[j] = kBwd ? (cvt_bf16x2(x2[j]) & gate_mask_bf16x2(mk[s * 16 + j])) : relu_bf16x2(cvt_bf16x2(x2[j]));
+        for (int j = 0; j < 16; ++j) {
+          w[j] = kBwd ? (cvt_bf16x2(x2[j]) & gate_mask(gw, j)) : relu_bf16x2(cvt_bf16x2(x2[j]));
+          if (kSave && !kBwd) gout[s] = gate_push(gout[s], w[j]);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           sts128(prow + (((uint32_t)(s * 4 + j) ^ e.sw128) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
@@ -331,13 +343,10 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
     sts32f(e.wbias + e.lane * 4, bn0);         // every lane is past its reads of this chunk's bias
     sts32f(e.wbias + (e.lane + 32) * 4, bn1);
     __syncwarp();
-  } else {                                     // next chunk's gate row: 128 B of the forward's saved operand
-    const uint4* m = reinterpret_cast<const uint4*>(nxt);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint4 t = __ldg(m + j);
-      mk[4 * j] = t.x; mk[4 * j + 1] = t.y; mk[4 * j + 2] = t.z; mk[4 * j + 3] = t.w;
-    }
+    if (kSave && KIND != kLayerOut && save && row0 + e.row < a.N)
+      a.gate_bits[((int64_t)L.act_slot * a.N + row0 + e.row) * 8 + c * 2 + e.g] = make_uint2(gout[0], gout[1]);
+  } else {
+    gate = __ldg(gate2);                       // gate words of the chunk after next (the caller double-buffers)
   }
 }
 
@@ -550,29 +559,33 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
     const long long t_begin = clock64();
     const int g = e.g;
     uint32_t xres[kFChunks][32];                     // this thread's slice of the bf16 residual stream (x' or dL/dx')
-    uint32_t mk[32];                                 // backward: this thread's gate row of the current chunk
+    uint2 gate[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};   // backward: gate words of this chunk and the next
     uint32_t n = 0;
     // what the next chunk (c of layer l of this CTA's tile `it`) needs prefetched: its bias values / its gate row
-    auto pre = [&](int it, int l, int c) -> const void* {
+    // what a later chunk (c of layer l of this CTA's tile `it`; c may run past the layer) needs prefetched
+    auto norm = [&](int& it, int& l, int& c) {
       if (c >= kFChunks) { c -= kFChunks; ++l; }
       if (l == nl) { l = 0; ++it; }
-      if (!kBwd) return a.L[l].bias + c * 128 + g * 64;
+    };
+    auto pre_bias = [&](int it, int l, int c) -> const void* {
+      norm(it, l, c);
+      return kBwd ? nullptr : a.L[l].bias + c * 128 + g * 64;
+    };
+    auto pre_gate = [&](int it, int l, int c) -> const uint2* {
+      if (!kBwd) return nullptr;
+      norm(it, l, c);
       int64_t r = (int64_t)((pair + it * n_pairs) * 2 + (int)crank) * 128 + e.row;
       if (r > a.N - 1) r = a.N - 1;                  // ragged tail / past the last tile: any valid row will do
-      return a.mask_base + ((int64_t)a.L[l].mask_slot * a.N + r) * 512 + c * 128 + g * 64;
+      return a.gate_bits + ((int64_t)a.L[l].mask_slot * a.N + r) * 8 + c * 2 + g;
     };
     if (!kBwd) {
-      const float* b0 = reinterpret_cast<const float*>(pre(0, 0, 0));
+      const float* b0 = reinterpret_cast<const float*>(pre_bias(0, 0, 0));
       sts32f(e.wbias + lane * 4, __ldg(b0 + lane));
       sts32f(e.wbias + (lane + 32) * 4, __ldg(b0 + lane + 32));
       __syncwarp();
     } else {
-      const uint4* m = reinterpret_cast<const uint4*>(pre(0, 0, 0));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint4 t = __ldg(m + j);
-        mk[4 * j] = t.x; mk[4 * j + 1] = t.y; mk[4 * j + 2] = t.z; mk[4 * j + 3] = t.w;
-      }
+      gate[0] = __ldg(pre_gate(0, 0, 0));
+      gate[1] = __ldg(pre_gate(0, 0, 1));
     }
     for (int it = 0; it < n_iter; ++it) {
       const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
@@ -583,15 +596,18 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
         if (kind == kLayerX) {
 #pragma unroll
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerX, kSave, kBwd>(e, maps, a, L, c, n, row0, first, xres[c], mk, pre(it, l, c + 1), pre(it, l, c + 2));
+            epi_chunk<kLayerX, kSave, kBwd>(e, maps, a, L, c, n, row0, first, xres[c], gate[c & 1],
+                                            pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         } else if (kind == kLayerNet) {
-#pragma unroll 1
+#pragma unroll 2
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerNet, kSave, kBwd>(e, maps, a, L, c, n, row0, false, xres[0], mk, pre(it, l, c + 1), pre(it, l, c + 2));
+            epi_chunk<kLayerNet, kSave, kBwd>(e, maps, a, L, c, n, row0, false, xres[0], gate[c & 1],
+                                              pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         } else if (!kBwd) {
 #pragma unroll 1
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerOut, kSave, kBwd>(e, maps, a, L, c, n, row0, false, xres[0], mk, pre(it, l, c + 1), pre(it, l, c + 2));
+            epi_chunk<kLayerOut, kSave, kBwd>(e, maps, a, L, c, n, row0, false, xres[0], gate[0],
+                                              pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         }
       }
     }
@@ -629,7 +645,7 @@ static int make_acts_map(CUtensorMap* map, void* acts, int64_t N, int n_slots) {
 int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
   NRF_REQUIRE(d.n_layers >= 2 && d.n_layers <= kFusedMaxLayers, NRF_EINVAL, "mlp_fused: %d layers", d.n_layers);
   NRF_REQUIRE(d.in_cols % 64 == 0 && d.in_cols >= 64, NRF_ENOSUP, "mlp_fused: %d input columns", d.in_cols);
-  NRF_REQUIRE(!d.backward || (d.saves && d.gates), NRF_EINVAL, "mlp_fused: the backward needs saves and gates");
+  NRF_REQUIRE(!d.backward || d.saves, NRF_EINVAL, "mlp_fused: the backward needs its output buffer");
   FMaps maps;
   FArgs a;
   memset(&a, 0, sizeof(a));
@@ -660,7 +676,8 @@ int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
   a.n_prod = n_prod;
   NRF_REQUIRE(n_prod == d.n_layers - 1, NRF_EINVAL, "mlp_fused: every layer but the last must feed the next");
   a.N = (int)d.N; a.d_out = d.d_out; a.ldo = d.ldo; a.out = d.out;
-  a.mask_base = reinterpret_cast<const __nv_bfloat16*>(d.gates);
+  a.gate_bits = reinterpret_cast<uint2*>(d.gate_bits);
+  NRF_REQUIRE(!d.saves || d.gate_bits, NRF_EINVAL, "mlp_fused: saving needs the gate-bit buffer");
   { const char* e = getenv("NRF_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.prof = reinterpret_cast<long long*>(d.prof);
   int grid = sm_count() / 2 * 2;

@@ -342,6 +342,9 @@ class FieldMLP:
         fn = lib.nrf_mlp_fwd_layered if layered else lib.nrf_mlp_fwd
         check(fn(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
                  ptr(acts), ptr(out), stream_ptr()), "nrf_mlp_fwd")
+        if acts is not None:
+            # the fused backward reads the bit-packed ReLU gates only the fused forward writes
+            acts._nrf_layered = bool(layered or not self.fused)
         return out, acts
 
     def backward(self, field_in, acts, d_field, grads: dict, scratch=None, deterministic=False, layered=False):
@@ -358,6 +361,7 @@ class FieldMLP:
         g = self._fill(_lib.NrfMlpGrads(), lambda n: grads[n].data_ptr() if grads.get(n) is not None else None)
         g.deterministic = int(bool(deterministic))
         lib = _lib.load()
+        layered = layered or getattr(acts, "_nrf_layered", False)
         fn = lib.nrf_mlp_bwd_layered if layered else lib.nrf_mlp_bwd
         check(fn(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
                  ptr(acts), ptr(d_field), C.byref(g), ptr(dlatent), ptr(scratch),
