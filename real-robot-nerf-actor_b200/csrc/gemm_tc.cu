@@ -369,23 +369,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // (BK_ k x 64 m); both MN-major (the sample index m is the slow axis of G and A in memory).
 // grid = (n tiles * k tiles, splits); each CTA reduces its sample range and adds its partial tile
 // into dW with fp32 reductions (red.global.add.f32).
-template <int BK_>
+template <int BK_, int CG>
 struct WgCfg {
-  static constexpr int kStageG = kTileM * kTileK * 2;          // 2 slabs of [64 m][64 n]
-  static constexpr int kStageA = BK_ * kTileK * 2;             // BK_/64 slabs of [64 m][64 k]
+  static constexpr int kStageG = kTileM * kTileK * 2;          // 2 slabs of [64 m][64 n]: this CTA's 128 n
+  static constexpr int kStageA = BK_ * kTileK * 2 / CG;        // slabs of [64 m][64 k]; a CTA pair holds half each
   static constexpr int kStage = kStageG + kStageA;
-  static constexpr int kStages = BK_ == 256 ? 4 : 6;
+  static constexpr int kStages = CG == 2 ? 6 : (BK_ == 256 ? 4 : 6);
   static constexpr int kTmemCols = BK_ == 256 ? 512 : 2 * BK_;  // accumulator + 32 columns for the bias sums
   static constexpr int kOnes = 2048;                           // 16 x 64 bf16 ones: B operand of the bias MMA
   static constexpr int kSmem = kStages * kStage + kOnes + 1024 + 256;
 };
 
-template <int BK_>
+// CG = 2: the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 of M = 256: a pair covers 256 n x BK_ k of dW;
+// each CTA loads the G^T slabs of its own 128 n and HALF of the A^T slabs (the tensor cores of both SMs read both
+// halves), so every SM ingests 32 KB instead of 48 KB per 64 samples at BK_ = 256: the single-CTA kernel was bound
+// by that L2 -> SM traffic (96 B/clk at full MMA rate).
+template <int BK_, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA, int M,
                 int k_tiles, int m_per_split, int n_valid, int k_valid, float* __restrict__ dW, int ldw,
                 float* __restrict__ dbias, float* __restrict__ ws, int n_pad, int k_pad) {
-  using Cfg = WgCfg<BK_>;
+  using Cfg = WgCfg<BK_, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem + Cfg::kStages * Cfg::kStage;
@@ -395,7 +399,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
-  const int n_blk = blockIdx.x / k_tiles, k_blk = blockIdx.x % k_tiles;
+  uint32_t crank = 0;
+  if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const bool cta_leader = crank == 0;
+  const int unit = blockIdx.x / CG;                     // (n tile [pair], k tile)
+  const int n_blk = (unit / k_tiles) * CG + (int)crank, k_blk = unit % k_tiles;
   const int m_begin = blockIdx.y * m_per_split;
   const int m_end = min(M, m_begin + m_per_split);
   const int num_mb = (m_end - m_begin + kTileK - 1) / kTileK;
@@ -410,13 +418,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmA); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, CG); mbar_init(empty + s, 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 2) { if (CG == 2) tmem_alloc2(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols); }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();   // both CTAs' barriers and ones tiles exist before the peer signals / reads them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -428,45 +437,64 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
       uint8_t* sa = sg + Cfg::kStageG;
       int m0 = m_begin + mb * kTileK;
       if (elect_one()) {
-        mbar_expect_tx(full + st.stage, Cfg::kStage);
         // rows >= M are zero-filled by TMA; rows in [m_end, M) of the last chunk belong to the next
         // split, so chunks are aligned: m_per_split is a multiple of 64.
+        if (CG == 2) {
+          if (cta_leader) mbar_expect_tx(full + st.stage, 2 * Cfg::kStage);
+          else mbar_arrive_leader(full + st.stage);
 #pragma unroll
-        for (int s = 0; s < kTileM / 64; ++s)
-          tma_load_2d(sg + s * (kTileK * 128), &tmG, full + st.stage, n_blk * kTileM + s * 64, m0);
+          for (int s = 0; s < kTileM / 64; ++s)
+            tma_load_2d_pair(sg + s * (kTileK * 128), &tmG, full + st.stage, n_blk * kTileM + s * 64, m0);
 #pragma unroll
-        for (int s = 0; s < BK_ / 64; ++s)
-          tma_load_2d(sa + s * (kTileK * 128), &tmA, full + st.stage, k_blk * BK_ + s * 64, m0);
+          for (int s = 0; s < BK_ / 128; ++s)
+            tma_load_2d_pair(sa + s * (kTileK * 128), &tmA, full + st.stage,
+                             k_blk * BK_ + (int)crank * (BK_ / 2) + s * 64, m0);
+        } else {
+          mbar_expect_tx(full + st.stage, Cfg::kStage);
+#pragma unroll
+          for (int s = 0; s < kTileM / 64; ++s)
+            tma_load_2d(sg + s * (kTileK * 128), &tmG, full + st.stage, n_blk * kTileM + s * 64, m0);
+#pragma unroll
+          for (int s = 0; s < BK_ / 64; ++s)
+            tma_load_2d(sa + s * (kTileK * 128), &tmA, full + st.stage, k_blk * BK_ + s * 64, m0);
+        }
       }
       __syncwarp();
       st.advance(Cfg::kStages);
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc(kTileM, BK_, 1, 1);
-    constexpr uint32_t idesc_bias = make_idesc(kTileM, 16, 1, 1);
-    const uint64_t odesc = make_sdesc(smem_u32(ones), kTileK * 128, 1024);
-    PipeState st;
-    for (int mb = 0; mb < num_mb; ++mb) {
-      mbar_wait(full + st.stage, st.phase);
-      tc_fence_after();
-      uint32_t sg = smem_u32(smem + st.stage * Cfg::kStage);
-      uint32_t sa = sg + Cfg::kStageG;
-      uint64_t gdesc = make_sdesc(sg, kTileK * 128, 1024);
-      uint64_t adesc = make_sdesc(sa, kTileK * 128, 1024);
-      if (elect_one()) {
+    if (cta_leader) {
+      constexpr uint32_t idesc = make_idesc(kTileM * CG, BK_, 1, 1);
+      constexpr uint32_t idesc_bias = make_idesc(kTileM * CG, 16, 1, 1);
+      const uint64_t odesc = make_sdesc(smem_u32(ones), kTileK * 128, 1024);
+      PipeState st;
+      for (int mb = 0; mb < num_mb; ++mb) {
+        mbar_wait(full + st.stage, st.phase);
+        tc_fence_after();
+        uint32_t sg = smem_u32(smem + st.stage * Cfg::kStage);
+        uint32_t sa = sg + Cfg::kStageG;
+        uint64_t gdesc = make_sdesc(sg, kTileK * 128, 1024);
+        uint64_t adesc = make_sdesc(sa, kTileK * 128, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kTileK / kUmmaK; ++k) {
-          // 16 samples = two 8-row atoms = 2048 B: +128 in the 16 B address field
-          umma_bf16(tmem_base, gdesc + 128 * k, adesc + 128 * k, idesc, (mb | k) != 0);
-          if (do_bias) umma_bf16(tmem_base + BK_, gdesc + 128 * k, odesc, idesc_bias, (mb | k) != 0);
+          for (int k = 0; k < kTileK / kUmmaK; ++k) {
+            // 16 samples = two 8-row atoms = 2048 B: +128 in the 16 B address field
+            if (CG == 2) {
+              umma_bf16_pair(tmem_base, gdesc + 128 * k, adesc + 128 * k, idesc, (mb | k) != 0);
+              if (do_bias) umma_bf16_pair(tmem_base + BK_, gdesc + 128 * k, odesc, idesc_bias, (mb | k) != 0);
+            } else {
+              umma_bf16(tmem_base, gdesc + 128 * k, adesc + 128 * k, idesc, (mb | k) != 0);
+              if (do_bias) umma_bf16(tmem_base + BK_, gdesc + 128 * k, odesc, idesc_bias, (mb | k) != 0);
+            }
+          }
+          if (CG == 2) umma_commit_pair(empty + st.stage); else umma_commit(empty + st.stage);
         }
-        umma_commit(empty + st.stage);
+        __syncwarp();
+        st.advance(Cfg::kStages);
       }
+      if (elect_one()) { if (CG == 2) umma_commit_pair(acc_full); else umma_commit(acc_full); }
       __syncwarp();
-      st.advance(Cfg::kStages);
     }
-    if (elect_one()) umma_commit(acc_full);
-    __syncwarp();
   } else if (warp >= kEpiWarp0) {
     const int q = warp - kEpiWarp0;
     if (num_mb > 0) {
@@ -505,9 +533,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();   // neither CTA leaves while the pair's MMAs / barrier traffic may still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) tmem_dealloc2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -642,10 +671,10 @@ int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream) {
   return launch_fwd<128, 1, -1>(g, stream);
 }
 
-template <int BK_>
+template <int BK_, int CG>
 static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
                         int k_valid, float* dW, int ldw, float* dbias, void* workspace, cudaStream_t stream) {
-  using Cfg = WgCfg<BK_>;
+  using Cfg = WgCfg<BK_, CG>;
   CUtensorMap tmG, tmA;
   int rc = make_map(&tmG, G, N, M, ldg, 64, kTileK);
   if (rc) return rc;
@@ -653,10 +682,11 @@ static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, i
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    NRF_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    NRF_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<BK_, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;
   }
   int n_tiles = (n_valid + kTileM - 1) / kTileM;
+  if (CG == 2) n_tiles = (n_tiles + 1) / 2 * 2;      // whole CTA pairs
   int k_tiles = (k_valid + BK_ - 1) / BK_;
   int out_tiles = n_tiles * k_tiles;
   int splits = sm_count() / out_tiles;      // one wave: (output tiles) x (sample splits) <= #SMs
@@ -665,12 +695,21 @@ static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, i
   if (splits < 1) splits = 1;
   int m_per = ((M + splits - 1) / splits + kTileK - 1) / kTileK * kTileK;
   splits = (M + m_per - 1) / m_per;
-  dim3 grid(out_tiles, splits);
   const int n_pad = n_tiles * kTileM, k_pad = k_tiles * BK_;
   float* ws = reinterpret_cast<float*>(workspace);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  if (CG == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  cfg.gridDim = dim3(out_tiles, splits); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmem;
+  cfg.stream = stream;
   { LaunchScope ls_(NRF_CAT_WGRAD, stream);
-  wgrad_tc_kernel<BK_><<<grid, kThreads, Cfg::kSmem, stream>>>(tmG, tmA, M, k_tiles, m_per, n_valid, k_valid,
-                                                               dW, ldw, dbias, ws, n_pad, k_pad);
+  NRF_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<BK_, CG>, tmG, tmA, M, k_tiles, m_per, n_valid, k_valid, dW, ldw,
+                                 dbias, ws, n_pad, k_pad));
   }
   NRF_LAUNCH_OK();
   if (ws) {
@@ -688,9 +727,12 @@ int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N
                     int k_valid, float* dW, int ldw, float* dbias, void* workspace, cudaStream_t stream) {
   NRF_REQUIRE(N % 64 == 0 && K % 64 == 0, NRF_ENOSUP, "wgrad_tc: N=%d, K=%d must be multiples of 64", N, K);
   int rc;
-  if (k_valid > 128) rc = launch_wgrad<256>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
-  else if (k_valid > 64) rc = launch_wgrad<128>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
-  else rc = launch_wgrad<64>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
+  static const bool one_cta = getenv("NRF_WGRAD_1CTA") != nullptr;
+  if (k_valid > 128 && n_valid > kTileM && !one_cta)
+    rc = launch_wgrad<256, 2>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
+  else if (k_valid > 128) rc = launch_wgrad<256, 1>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
+  else if (k_valid > 64) rc = launch_wgrad<128, 1>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
+  else rc = launch_wgrad<64, 1>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
   return rc;
 }
 

@@ -26,7 +26,7 @@ import torch.nn.functional as F
 from . import ops
 from .utils import AttrDict, PositionalEncoding, gen_rays
 
-__all__ = ["NeuralRenderer", "PixelNeRFEmbedNet", "ResnetFC", "ResnetBlockFC", "PSNR_torch"]
+__all__ = ["NeuralRenderer", "PixelNeRFEmbedNet", "ResnetFC", "ResnetBlockFC", "PSNR_torch", "LossDict"]
 
 
 def _cfg_get(cfg, key, default=None):
@@ -42,6 +42,83 @@ def PSNR_torch(img1, img2, max_val=1):
     if mse == 0:
         return 100
     return 20 * torch.log10(max_val / torch.sqrt(mse))
+
+
+class LossDict(dict):
+    """What compute_rendering_loss returns (neural_rendering.py:697-707): 'loss' is the tensor to back-propagate, the
+    other ten entries are Python floats.  The reference produces them with 13 `.item()` calls - host syncs between the
+    forward and the backward of every step.  Here the seven scalars behind them are copied to pinned host memory
+    asynchronously and become floats the first time any of them is read (or the dict is iterated / printed), so a
+    loop that calls `out['loss'].backward()` before it logs never stalls the GPU."""
+
+    _KEYS = ("loss_rgb_coarse", "loss_rgb_fine", "loss_rgb", "loss_embed_coarse", "loss_embed_fine", "loss_embed",
+             "loss_depth_coarse", "loss_depth_fine", "loss_depth", "psnr")
+    _ring, _owners, _next = [], [], 0          # pinned staging buffers, reused round-robin
+
+    def __init__(self, loss, scalars):
+        super().__init__(loss=loss)
+        for k in self._KEYS:
+            dict.__setitem__(self, k, None)
+        cls = LossDict
+        if not cls._ring:
+            cls._ring = [torch.empty(7, dtype=torch.float32).pin_memory() for _ in range(8)]
+            cls._owners = [None] * 8
+        i = cls._next
+        cls._next = (i + 1) % len(cls._ring)
+        prev = cls._owners[i]() if cls._owners[i] is not None else None
+        if prev is not None:
+            prev._resolve()                    # its values leave the staging buffer before it is reused
+        self._host = cls._ring[i]
+        self._host.copy_(scalars, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+        import weakref
+        cls._owners[i] = weakref.ref(self)
+
+    def _resolve(self):
+        if getattr(self, "_host", None) is None:
+            return
+        self._event.synchronize()
+        v = self._host.tolist()
+        self._host = None
+        for k, x in zip(self._KEYS, (v[0], v[1], v[0] + v[1], v[2], v[3], v[2] + v[3], v[4], v[5], v[4] + v[5], v[6])):
+            dict.__setitem__(self, k, x)
+
+    def __getitem__(self, k):
+        if k != "loss":
+            self._resolve()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        if k != "loss":
+            self._resolve()
+        return dict.get(self, k, default)
+
+    def items(self):
+        self._resolve()
+        return dict.items(self)
+
+    def values(self):
+        self._resolve()
+        return dict.values(self)
+
+    def copy(self):
+        self._resolve()
+        return dict(self)
+
+    def __repr__(self):
+        self._resolve()
+        return dict.__repr__(self)
+
+    def __eq__(self, other):
+        self._resolve()
+        return dict.__eq__(self, other)
+
+    __hash__ = None
+
+    def __reduce__(self):
+        self._resolve()
+        return (dict, (dict(self),))
 
 
 # ------------------------------------------------------------------ parameter containers
@@ -227,13 +304,14 @@ class _PassState:
     __slots__ = ("rays", "z", "field_in", "acts", "field_out", "rps", "mlp", "perm")
 
 
-def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps):
-    """One composite pass (neural_rendering.py:224-395) over all samples of `z`."""
+def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps, keep_acts=True):
+    """One composite pass (neural_rendering.py:224-395) over all samples of `z`.  keep_acts=False (no gradient
+    will be asked for): the fused MLP kernel keeps nothing but the raw field outputs."""
     st = _PassState()
     st.rays, st.z, st.rps, st.mlp, st.perm = rays, z, rps, mlp, None
     st.field_in = ops.encode_points(rays, z, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
                                     ld_out=mlp.sizes.kin_pad, precision=mlp.precision)
-    st.field_out, st.acts = mlp.forward(st.field_in)
+    st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts)
     outs = ops.composite_fwd(st.field_out, z, rays, ren._d_embed, ren.white_bkgd)
     return st, outs
 
@@ -281,10 +359,12 @@ class _ForwardNerfFn(torch.autograd.Function):
         rps = R // sb
         mlp_c = ren.nerf_model.mlp_coarse.handle(ren._prec)
         mlp_f = ren.nerf_model.mlp_fine.handle(ren._prec)
-        vol_cl = ops.volume_to_channels_last(voxel_feat)
+        held = getattr(ren, "_vol_cl_held", None)          # rendering(): one re-layout for all ray chunks
+        vol_cl = held[1] if held is not None and held[0] is voxel_feat else ops.volume_to_channels_last(voxel_feat)
         Kc, Kf, Kfd = ren.n_coarse, ren.n_fine, ren.n_fine_depth
         z_c = ops.sample_coarse(rays, Kc, noise.get("coarse"), ren.lindisp)
-        st_c, (cw, crgb, cemb, cdep) = _pass_forward(ren, mlp_c, vol_cl, rays, z_c, rps)
+        keep = any(ctx.needs_input_grad)
+        st_c, (cw, crgb, cemb, cdep) = _pass_forward(ren, mlp_c, vol_cl, rays, z_c, rps, keep)
         outs = [z_c, cw, crgb, cemb, cdep]
         st_f = None
         depth_mask = None
@@ -306,7 +386,7 @@ class _ForwardNerfFn(torch.autograd.Function):
                 depth_mask = ((z0 <= far) & (z0 >= near)).to(torch.float32)
                 z_all[:, Kc + kf:] = torch.max(torch.min(z0, far), near)
             z_all, perm = ops.sort_rows(z_all, want_perm=True)
-            st_f, (fw, frgb, femb, fdep) = _pass_forward(ren, mlp_f, vol_cl, rays, z_all, rps)
+            st_f, (fw, frgb, femb, fdep) = _pass_forward(ren, mlp_f, vol_cl, rays, z_all, rps, keep)
             st_f.perm = perm
             outs += [z_all, fw, frgb, femb, fdep]
         ctx.ren, ctx.st_c, ctx.st_f, ctx.sb, ctx.n_pc = ren, st_c, st_f, sb, n_pc
@@ -316,10 +396,10 @@ class _ForwardNerfFn(torch.autograd.Function):
         # one call only: a second mark_non_differentiable() would replace the first, give z_c a grad_fn
         # pointing at this node while st_c.z holds it, and leak every activation through that cycle
         ctx.mark_non_differentiable(*([z_c] + ([outs[5]] if st_f is not None else [])))
-        if not any(ctx.needs_input_grad):
-            st_c.acts = None
+        if not keep:                           # nothing to back-propagate: drop what a backward would have used
+            st_c.acts = st_c.field_in = st_c.field_out = None
             if st_f is not None:
-                st_f.acts = None
+                st_f.acts = st_f.field_in = st_f.field_out = None
         return tuple(outs)
 
     @staticmethod
@@ -521,12 +601,17 @@ class NeuralRenderer(nn.Module):
         B, H, W, _ = rays.shape
         rays = rays.reshape(B * H * W, 8)
         rgbs, embeds, depths = [], [], []
-        for i in range(0, rays.shape[0], self.render_chunk_rays):
-            out = self.forward_nerf(rays[i:i + self.render_chunk_rays].unsqueeze(0))
-            fine = out.fine
-            rgbs.append(fine.rgb.squeeze(0))
-            embeds.append(fine.embed.squeeze(0))
-            depths.append(fine.depth.squeeze(0))
+        # the volume is re-laid out channels-last once for all ray chunks (the tensor is held, so identity is safe)
+        self._vol_cl_held = (voxel_feat, ops.volume_to_channels_last(voxel_feat))
+        try:
+            for i in range(0, rays.shape[0], self.render_chunk_rays):
+                out = self.forward_nerf(rays[i:i + self.render_chunk_rays].unsqueeze(0))
+                fine = out.fine
+                rgbs.append(fine.rgb.squeeze(0))
+                embeds.append(fine.embed.squeeze(0))
+                depths.append(fine.depth.squeeze(0))
+        finally:
+            self._vol_cl_held = None
         rgbs = torch.cat(rgbs, dim=0).reshape(B, H, W, 3)
         embeds = torch.cat(embeds, dim=0).reshape(B, H, W, -1)
         depths = torch.cat(depths, dim=0).reshape(B, H, W)
@@ -569,7 +654,9 @@ class NeuralRenderer(nn.Module):
         loss_rgb_coarse = F.mse_loss(outputs.coarse.rgb, gt_rgb)
         loss_rgb_fine = F.mse_loss(outputs.fine.rgb, gt_rgb)
         loss = loss_rgb_coarse + loss_rgb_fine
-        psnr = PSNR_torch(outputs.fine.rgb, gt_rgb)
+        mse_fine = torch.mean((outputs.fine.rgb.detach() - gt_rgb) ** 2)       # PSNR_torch without its host-side branch
+        psnr = torch.where(mse_fine == 0, torch.full_like(mse_fine, 100.0),
+                           20 * torch.log10(1.0 / torch.sqrt(mse_fine.clamp_min(1e-45))))
         gt_embed = gt_embed.reshape(B, H * W, -1)[:, idx, :]
         loss_embed_coarse = self.lambda_embed * F.mse_loss(outputs.coarse.embed, gt_embed)
         loss_embed_fine = self.lambda_embed * F.mse_loss(outputs.fine.embed, gt_embed)
@@ -583,16 +670,12 @@ class NeuralRenderer(nn.Module):
         else:
             loss_depth_coarse = torch.zeros((), device=loss.device)
             loss_depth_fine = torch.zeros((), device=loss.device)
-        # one host sync instead of the reference's 13 .item() calls
+        # no host sync here (the reference has 13 .item() calls): see LossDict
         psnr_t = psnr if torch.is_tensor(psnr) else torch.tensor(float(psnr), device=loss.device)
-        vals = torch.stack([v.detach().float().reshape(()) for v in
-                            (loss_rgb_coarse, loss_rgb_fine, loss_embed_coarse, loss_embed_fine,
-                             loss_depth_coarse, loss_depth_fine, psnr_t)]).tolist()
-        return {"loss": loss,
-                "loss_rgb_coarse": vals[0], "loss_rgb_fine": vals[1], "loss_rgb": vals[0] + vals[1],
-                "loss_embed_coarse": vals[2], "loss_embed_fine": vals[3], "loss_embed": vals[2] + vals[3],
-                "loss_depth_coarse": vals[4], "loss_depth_fine": vals[5], "loss_depth": vals[4] + vals[5],
-                "psnr": vals[6]}
+        scalars = torch.stack([v.detach().float().reshape(()) for v in
+                               (loss_rgb_coarse, loss_rgb_fine, loss_embed_coarse, loss_embed_fine,
+                                loss_depth_coarse, loss_depth_fine, psnr_t)])
+        return LossDict(loss, scalars)
 
     def forward(self, multi_scale_voxel_list, voxel_density, language, voxel_feat, voxel_poses, focal, gt_rgb,
                 gt_depth, gt_pose, c=None, lang_goal=None, gt_embed=None):
