@@ -349,12 +349,12 @@ def _zeros_like_or(t, ref_shape, device):
 class _ForwardNerfFn(torch.autograd.Function):
     """forward_nerf (neural_rendering.py:435-471) as one autograd node.
 
-    inputs : ren, voxel_feat (SB,C,S,S,S), rays (R,8), sb, noise dict, n_param_coarse, *params
+    inputs : ren, voxel_feat (SB,C,S,S,S), rays (R,8), sb, noise dict, n_param_coarse, keep (activations), *params
     outputs: z_coarse, cw, crgb, cemb, cdep[, z_fine, fw, frgb, femb, fdep]
     """
 
     @staticmethod
-    def forward(ctx, ren, voxel_feat, rays, sb, noise, n_pc, *params):
+    def forward(ctx, ren, voxel_feat, rays, sb, noise, n_pc, keep, *params):
         R = rays.shape[0]
         rps = R // sb
         mlp_c = ren.nerf_model.mlp_coarse.handle(ren._prec)
@@ -363,7 +363,6 @@ class _ForwardNerfFn(torch.autograd.Function):
         vol_cl = held[1] if held is not None and held[0] is voxel_feat else ops.volume_to_channels_last(voxel_feat)
         Kc, Kf, Kfd = ren.n_coarse, ren.n_fine, ren.n_fine_depth
         z_c = ops.sample_coarse(rays, Kc, noise.get("coarse"), ren.lindisp)
-        keep = any(ctx.needs_input_grad)
         st_c, (cw, crgb, cemb, cdep) = _pass_forward(ren, mlp_c, vol_cl, rays, z_c, rps, keep)
         outs = [z_c, cw, crgb, cemb, cdep]
         st_f = None
@@ -434,7 +433,7 @@ class _ForwardNerfFn(torch.autograd.Function):
         pg = [grads_c[n] for n in names_c]
         if not shared and st_f is not None:
             pg += [grads_f[n] for n in st_f.mlp.names()]
-        return (None, d_vol, None, None, None, None, *pg)
+        return (None, d_vol, None, None, None, None, None, *pg)
 
 
 # ------------------------------------------------------------------------------ the renderer
@@ -583,7 +582,9 @@ class NeuralRenderer(nn.Module):
         if noise is None:
             noise = self._draw_noise(flat.shape[0], flat.device)
         n_pc, ps = self._params_flat()
-        outs = _ForwardNerfFn.apply(self, vol, flat, sb, noise, n_pc, *ps)
+        # decided here: inside Function.forward grad mode is always off and needs_input_grad ignores no_grad()
+        keep = torch.is_grad_enabled() and (vol.requires_grad or any(p.requires_grad for p in ps))
+        outs = _ForwardNerfFn.apply(self, vol, flat, sb, noise, n_pc, keep, *ps)
         outputs = AttrDict(coarse=self._format_outputs(outs[1:5], sb, want_weights))
         outputs.coarse.z = outs[0]
         if self.using_fine:

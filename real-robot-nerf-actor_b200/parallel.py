@@ -84,9 +84,14 @@ def render_sharded(renderer, voxel_feat, focal, tgt_pose, c=None, group=None, ga
     lo, hi = shard_bounds(flat.shape[0], world, rank)
     renderer.encode(None, None, None, voxel_feat, None, focal, c)
     rgbs, embs, deps = [], [], []
-    for i in range(lo, hi, renderer.render_chunk_rays):
-        out = renderer.forward_nerf(flat[i:min(i + renderer.render_chunk_rays, hi)].unsqueeze(0)).fine
-        rgbs.append(out.rgb.squeeze(0)); embs.append(out.embed.squeeze(0)); deps.append(out.depth.squeeze(0))
+    from . import ops
+    renderer._vol_cl_held = (voxel_feat, ops.volume_to_channels_last(voxel_feat))   # one re-layout for all chunks
+    try:
+        for i in range(lo, hi, renderer.render_chunk_rays):
+            out = renderer.forward_nerf(flat[i:min(i + renderer.render_chunk_rays, hi)].unsqueeze(0)).fine
+            rgbs.append(out.rgb.squeeze(0)); embs.append(out.embed.squeeze(0)); deps.append(out.depth.squeeze(0))
+    finally:
+        renderer._vol_cl_held = None
     rgb, emb, dep = torch.cat(rgbs), torch.cat(embs), torch.cat(deps)
     if not gather or world == 1:
         if world == 1:
