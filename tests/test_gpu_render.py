@@ -296,3 +296,56 @@ def test_public_composite_with_external_samples(ops, NR):
 def test_cpu_tensors_are_rejected(ops):
     with pytest.raises(Exception):
         ops.sample_coarse(torch.rand(4, 8), 8)
+
+
+def test_loss_dict_is_lazy_and_matches_the_reference_keys(ops, NR):
+    """forward() returns the reference's eleven keys; the float entries resolve on first read without having forced a
+    host sync before (LossDict), and are consistent with the loss tensor."""
+    fx = golden("small_kfd0")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
+    ren = make_renderer(NR, meta, ci["params"], "fp32")
+    vol = T(fx["vol"]).cuda().requires_grad_(True)
+    gt_rgb, gt_emb = T(fx["gt_rgb_img"]).cuda(), T(fx["gt_embed_img"]).cuda()
+    poses = syn.arc_poses(SB).cuda()
+    torch.manual_seed(0)
+    out = ren(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=vol, voxel_poses=poses,
+              focal=torch.tensor(float(fx["focal"])).cuda(), gt_rgb=gt_rgb, gt_depth=None, gt_pose=poses, c=None,
+              lang_goal=None, gt_embed=gt_emb)
+    assert isinstance(out, dict) and isinstance(out, NR.LossDict)
+    assert set(out.keys()) == {"loss", "loss_rgb_coarse", "loss_rgb_fine", "loss_rgb", "loss_embed_coarse",
+                               "loss_embed_fine", "loss_embed", "loss_depth_coarse", "loss_depth_fine", "loss_depth",
+                               "psnr"}
+    assert out._host is not None                       # nothing has been read yet
+    out["loss"].backward()                             # the tensor entry does not resolve the floats
+    assert out._host is not None and vol.grad is not None
+    total = float(out["loss"])
+    assert out._host is not None
+    vals = dict(out.items())                           # resolves
+    assert out._host is None and all(isinstance(vals[k], float) for k in vals if k != "loss")
+    parts = vals["loss_rgb"] + vals["loss_embed"] + vals["loss_depth"]
+    assert abs(parts - total) < 1e-5 * max(1.0, abs(total))
+    assert abs(vals["loss_rgb"] - (vals["loss_rgb_coarse"] + vals["loss_rgb_fine"])) < 1e-7
+    assert 0.0 < vals["psnr"] < 100.0
+    assert out["psnr"] == vals["psnr"] and out.get("loss_depth") == 0.0
+
+
+def test_bf16_training_step_is_reproducible_when_asked(ops, NR):
+    """scatter="sorted" + deterministic=True: volume gradient AND every MLP parameter gradient are bit-identical run
+    to run in the tensor-core mode (fused forward / backward kernels, ordered wgrad reduction)."""
+    fx = golden("full_s32")
+    meta = [int(v) for v in fx["meta"]]
+    inp = syn_case_inputs(fx)
+    ren = make_renderer(NR, meta, inp["params"], "bf16")
+    assert ren.nerf_model.mlp_coarse.handle(ops.NRF_PREC_BF16).fused
+    ren.deterministic = True
+    runs = []
+    for _ in range(2):
+        for p in ren.parameters():
+            p.grad = None
+        _, _, vg, pg = _run_cuda(ren, inp["vol"], inp["rays"], inp["noise"], inp["gt_rgb"], inp["gt_embed"])
+        runs.append((vg.clone(), {k: v.clone() for k, v in pg.items()}))
+    assert torch.equal(runs[0][0], runs[1][0])
+    for k in runs[0][1]:
+        assert torch.equal(runs[0][1][k], runs[1][1][k]), k
