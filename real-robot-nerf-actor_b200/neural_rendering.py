@@ -472,6 +472,8 @@ class NeuralRenderer(nn.Module):
         self.precision = precision
         self.scatter = "sorted"                # volume-gradient scatter: "sorted" (atomics-free, default) | "atomic"
         self.deterministic = False             # True: ordered split reduction of the MLP weight gradients as well
+        self.target_ready_event = None         # optional torch.cuda.Event: gt_rgb / gt_embed were copied on a side
+                                               # stream; awaited right before the losses read them
         self.perturb = True
         self.render_chunk_rays = 4096          # neural_rendering.py:482
         self._num_freqs = self.nerf_model.code.num_freqs
@@ -639,6 +641,9 @@ class NeuralRenderer(nn.Module):
         idx = torch.randint(H * W, (chunk_size,), device=rays.device)      # shared across scenes (:608)
         sampled_rays = rays[:, idx, :]
         outputs = self.forward_nerf(sampled_rays)
+        if self.target_ready_event is not None:            # targets prefetched on a side stream (see bench.py)
+            torch.cuda.current_stream(rays.device).wait_event(self.target_ready_event)
+            self.target_ready_event = None
         if gt_embed is None:
             with torch.no_grad():
                 gt_embed = self.extract_foundation_model_feature(gt_rgb, lang_goal)
