@@ -518,9 +518,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         } else if (n < n_valid) {
           float* dst = dW + (int64_t)n * ldw + k0;
+          if ((ldw & 3) == 0 && k0 + 32 <= k_valid) {      // 16 B aligned rows: vector reductions (red.global.add.v4.f32)
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (k0 + j < k_valid) atomicAdd(dst + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4)
+              atomicAdd(reinterpret_cast<float4*>(dst + j),
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                    __uint_as_float(v[j + 3])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (k0 + j < k_valid) atomicAdd(dst + j, __uint_as_float(v[j]));
+          }
         }
       }
       if (do_bias) {                              // column BK_ of the accumulator: sum over the samples of G[:, n]
