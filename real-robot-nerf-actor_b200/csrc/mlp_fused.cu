@@ -7,8 +7,9 @@
 // Where everything lives (per CTA; the MMAs are tcgen05.mma.cta_group::2, M = 256, N = 128, K = 16):
 //   weights        stream from L2 through a TMA ring of 16 KB stages (this CTA's 64 of the 128 weight rows x 128 k);
 //                  the pair shares every weight byte, so the L2 -> SM weight traffic is 32 B/clk/SM at full rate
-//   field input    the [latent | PE | viewdir] k-panels (lin_in|lin_z[0], and the lin_z[b+1] tails of fc_1) come
-//                  through the same ring, one 16 KB stage per 128-row k-panel
+//   field input    the first layer's A operand ([latent | PE | viewdir]; backward: d_field) is loaded once per tile
+//                  into P, which is dead at that point; the latent k-panels of the lin_z[b+1] tails of fc_1 come
+//                  through the weight ring, one 16 KB stage per 128-row k-panel
 //   accumulators   TMEM columns [0,256): two 128-column buffers; the epilogue of chunk i overlaps the MMAs of i+1
 //   relu(x')       TMEM columns [256,512) as packed bf16 pairs: the A operand of fc_0 and lin_out comes straight
 //                  from tensor memory (tcgen05.mma with A in TMEM), written by the epilogue with tcgen05.st
@@ -20,15 +21,15 @@
 //                  warpgroups 232 registers, the service warps 40)
 // Ping-ponging the operand between TMEM and shared memory removes every write-after-read hazard between a layer's
 // MMAs and its own epilogue, so the next layer's MMAs start on k-block kb as soon as the epilogue has published it
-// (a_ready[kb]) and the tensor pipe never drains between layers - or between tiles: nothing but ring slots and
-// accumulator buffers is shared from one tile to the next.
+// (a_ready[kb]) and the tensor pipe never drains between layers.
 //
 // The same kernel runs the BACKWARD data-gradient chain (kBwd): lin_out^T, then per block fc_1^T and fc_0^T with the
 // ReLU gates read from the operands the forward saved, the gradient of the residual stream in the epilogue
 // registers, and every intermediate gradient (dL/dx'_b, dL/dnet_b: the G operands of the weight-gradient GEMMs)
 // streamed out by TMA stores.  Forward and backward are two "layer programs" for one executor.
 //
-// Warp roles: 0 TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator | 4-11 epilogue: warp (g, q4) owns
+// Warp roles: 0 TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator | 3 first-layer input loader |
+// 4-11 epilogue: warp (g, q4) owns
 // rows [32 q4, 32 q4 + 32) x columns [64g, 64g+64) of every 128-column chunk (= its rows of k-block 2c+g of the next
 // layer); the eight epilogue warps never synchronise with each other.
 #include "tc_ptx.cuh"
@@ -44,9 +45,10 @@ constexpr int kFStageB = 2 * kFBoxB;         // a ring stage carries two k-block
 constexpr int kFChunks = 4;                  // 512 / 128 accumulator chunks per layer
 constexpr int kFSmemP = 8 * kFPanel;         // 128 KB
 constexpr int kFSlot = 32 * 128;             // 4 KB: 32 rows x 64 bf16 (128B swizzle), one per epilogue warp
-constexpr int kFSmemBar = 256;
+constexpr int kFSmemBar = 320;
+constexpr int kFMaxIn = 7;                   // k-panels of the first layer's global A operand (they live in P)
 constexpr int kFSmemBias = 8 * 256;          // per epilogue warp: the 64 bias values of its current chunk
-constexpr int kFAlignSlack = 768;            // dynamic shared memory starts 1024-aligned in practice (checked)
+constexpr int kFAlignSlack = 704;            // dynamic shared memory starts 1024-aligned in practice (checked)
 template <bool kSave>
 struct FCfg {
   static constexpr int kStages = kSave ? 4 : 6;      // saving gives 32 KB up for the staging slots
@@ -68,6 +70,7 @@ struct FLayer {
 };
 struct FArgs {
   int n_layers, n_tiles, n_prod;   // n_prod: layers per tile whose epilogue publishes an A operand
+  int l_p_free;                    // last layer of a tile whose MMAs read P: after it the next tile's input may land
   int N, d_out, ldo;
   int dbg;      // NRF_DBG timing experiments (wrong results!): 1 no weight TMA, 2 epilogue protocol only, 4 no MMAs,
                 // 8 MMA issuer ignores acc_empty / a_ready
@@ -367,7 +370,9 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
   uint64_t* acc_full = empty + kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* a_ready = acc_empty + 2;           // 8: k-block kb of the next layer's A operand is in place
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 8);
+  uint64_t* in_full = a_ready + 8;             // kFMaxIn: k-panel kb of this tile's first-layer A operand is in P
+  uint64_t* in_free = in_full + kFMaxIn;       // P may receive the next tile's input
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_free + 1);
 
   const int warp = uniform_warp_idx();
   int lane;                                      // volatile: kept in a register, never re-read with S2R in the loops
@@ -388,6 +393,8 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
     for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 2); mbar_init(empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 16); }
     for (int s = 0; s < 8; ++s) mbar_init(a_ready + s, 8);
+    for (int s = 0; s < kFMaxIn; ++s) mbar_init(in_full + s, 2);
+    mbar_init(in_free, 9);                     // the issuer's commit + the 8 epilogue warps (their P stores drained)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc2(tmem_slot, 512);
@@ -399,10 +406,9 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    // A "unit" is a pair of k-blocks (the last one of a layer may be single).  Units whose A operand comes from
-    // global memory (forward: the field input of layer 0 and the latent tail of fc_1; backward: d_field) take one
-    // ring stage per A k-panel followed by the weight stage; all other units take the weight stage only.  Producer
-    // and issuer walk the same sequence.
+    // A "unit" is a pair of k-blocks (the last one of a layer may be single).  Units of the latent tail of fc_1
+    // (their A operand is the latent part of the field input) take one ring stage per A k-panel followed by the
+    // weight stage; all other units take the weight stage only.  Producer and issuer walk the same sequence.
     if (warp == 0) {
       // ---- TMA producer: runs ahead of the MMAs by the depth of the ring, across layers and tiles
       PipeState st;
@@ -412,19 +418,18 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
         const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
         for (int l = 0; l < nl; ++l) {
           const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
-          const bool in_main = a.L[l].a_src == kSrcIn;
           for (int c = 0; c < kFChunks; ++c)
             for (int kb = 0; kb < kb_tot; kb += 2) {
               if (a.dbg & 1) continue;
               const int nk = kb_tot - kb < 2 ? 1 : 2;
-              if (in_main || kb >= kb_main) {          // this CTA's 128 rows of the global A k-panels
+              if (kb >= kb_main) {                     // this CTA's 128 rows of the trailing global A k-panels
                 for (int h = 0; h < nk; ++h) {
                   FUSED_TIMED(t_empty, mbar_wait(empty + st.stage, st.phase ^ 1));
                   if (elect_one()) {
                     if (cta_leader) mbar_expect_tx(full + st.stage, 2 * kFPanel);
                     else mbar_arrive_leader(full + st.stage);
                     tma_load_2d_pair(sRing + st.stage * kFStageB, &maps.in, full + st.stage,
-                                     (in_main ? kb + h : kb + h - kb_main) * 64, row0);
+                                     (kb + h - kb_main) * 64, row0);
                   }
                   __syncwarp();
                   st.advance(kStages);
@@ -449,6 +454,22 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
         a.prof[blockIdx.x * 32 + 0] = clock64() - t_begin;
         a.prof[blockIdx.x * 32 + 1] = t_empty;
       }
+    } else if (warp == 3) {
+      // ---- first-layer A operand (field input / d_field): k-panels straight into P, which is dead between the
+      // last layer that reads it and the second layer's epilogue.  One barrier per panel: the MMAs start on panel 0.
+      const int kb_in = a.L[0].kb_main;
+      for (int it = 0; it < n_iter; ++it) {
+        if (it > 0) mbar_wait(in_free, (it - 1) & 1);
+        const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
+        if (elect_one()) {
+          for (int kb = 0; kb < kb_in; ++kb) {
+            if (cta_leader) mbar_expect_tx(in_full + kb, 2 * kFPanel);
+            else mbar_arrive_leader(in_full + kb);
+            tma_load_2d_pair(sP + kb * kFPanel, &maps.in, in_full + kb, kb * 64, row0);
+          }
+        }
+        __syncwarp();
+      }
     } else if (warp == 1 && cta_leader) {
       // ---- MMA issuer for the pair: the whole warp runs the loop (uniform control flow), one elected lane issues
       constexpr uint32_t idesc = make_idesc(256, 128, 0, 0);
@@ -468,7 +489,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
             const uint32_t tmem_d = tmem_base + buf * 128;
             for (int kb0 = 0; kb0 < kb_tot; kb0 += 2) {
               const int nk = kb_tot - kb0 < 2 ? 1 : 2;
-              const bool ext = a_src == kSrcIn || kb0 >= kb_main;          // A k-panels arrive through the ring
+              const bool ext = kb0 >= kb_main;                             // A k-panels arrive through the ring
               uint32_t pa0 = 0, pa1 = 0;                                    // smem A panels of the unit's k-blocks
               int sa0 = 0, sa1 = 0;
               if (ext) {
@@ -482,13 +503,18 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
                   if (!(a.dbg & 1)) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
                   st.advance(kStages);
                 }
-              } else if (a_src == kSrcP) {
+              } else if (a_src != kSrcQ) {
                 pa0 = sP_u + kb0 * kFPanel;
                 pa1 = pa0 + kFPanel;
               }
-              if (!ext && c == 0 && !(a.dbg & 8)) {     // produced by the previous layer's epilogue
-                FUSED_TIMED(t_ready, mbar_wait(a_ready + kb0, a_par));
-                if (nk == 2) FUSED_TIMED(t_ready, mbar_wait(a_ready + kb0 + 1, a_par));
+              if (!ext && c == 0 && !(a.dbg & 8)) {
+                if (a_src == kSrcIn) {                  // loaded by warp 3
+                  FUSED_TIMED(t_ready, mbar_wait(in_full + kb0, it & 1));
+                  if (nk == 2) FUSED_TIMED(t_ready, mbar_wait(in_full + kb0 + 1, it & 1));
+                } else {                                // produced by the previous layer's epilogue
+                  FUSED_TIMED(t_ready, mbar_wait(a_ready + kb0, a_par));
+                  if (nk == 2) FUSED_TIMED(t_ready, mbar_wait(a_ready + kb0 + 1, a_par));
+                }
               }
               if (!(a.dbg & 1)) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
               tc_fence_after();
@@ -523,7 +549,10 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
               __syncwarp();
               st.advance(kStages);
             }
-            if (elect_one()) umma_commit_pair(acc_full + buf);
+            if (elect_one()) {
+              umma_commit_pair(acc_full + buf);
+              if (l == a.l_p_free && c == kFChunks - 1) umma_commit_pair(in_free);
+            }
             __syncwarp();
           }
         }
@@ -593,6 +622,10 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
         const FLayer& L = a.L[l];
         const int kind = L.kind;
         const bool first = L.first != 0;
+        if (l == nl - 1 && lane == 0) {              // this warp's TMA stores that read P panels have drained
+          if (kSave) bulk_wait_read0();
+          mbar_arrive(in_free);
+        }
         if (kind == kLayerX) {
 #pragma unroll
           for (int c = 0; c < kFChunks; ++c, ++n)
@@ -674,6 +707,13 @@ int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
   a.n_layers = d.n_layers;
   a.n_tiles = (int)((d.N + 255) / 256);
   a.n_prod = n_prod;
+  NRF_REQUIRE(d.L[0].a_src == 0 && d.L[0].kb_z == 0 && d.L[0].kb_main <= kFMaxIn && d.L[0].kb_main * 64 == d.in_cols,
+              NRF_ENOSUP, "mlp_fused: the first layer reads all %d input columns from P (at most %d k-panels)",
+              d.in_cols, kFMaxIn);
+  a.l_p_free = 0;
+  for (int l = 0; l < d.n_layers; ++l)
+    if (d.L[l].a_src == 2 || (l == 0)) a.l_p_free = l;
+  NRF_REQUIRE(a.l_p_free < d.n_layers - 1 || d.backward, NRF_EINVAL, "mlp_fused: forward programs end on lin_out");
   NRF_REQUIRE(n_prod == d.n_layers - 1, NRF_EINVAL, "mlp_fused: every layer but the last must feed the next");
   a.N = (int)d.N; a.d_out = d.d_out; a.ldo = d.ldo; a.out = d.out;
   a.gate_bits = reinterpret_cast<uint2*>(d.gate_bits);
