@@ -257,8 +257,8 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
   tc_fence_before();                           // the accumulator buffer is free again
   __syncwarp();
   if (e.lane == 0) mbar_arrive_leader_u32(e.acc_empty + buf * 8);
-  uint32_t gout[2] = {0u, 0u};                 // forward (training): the gate words of this thread's 64 outputs
   const uint32_t prow = e.sP + (2 * c + e.g) * kFPanel + e.row * 128;
+  uint32_t w[32];                              // this thread's 64 outputs of the chunk as packed bf16 operand values
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const uint32_t gw = s == 0 ? gate.x : gate.y;    // backward: gate word of this sub-chunk
@@ -285,69 +285,79 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
                 make_uint4((uint32_t)x2[2 * j], (uint32_t)(x2[2 * j] >> 32), (uint32_t)x2[2 * j + 1],
                            (uint32_t)(x2[2 * j + 1] >> 32));
       }
-    } else {
-      uint32_t w[16];
-      if (KIND == kLayerX) {
+    } else if (KIND == kLayerX) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          uint64_t t = x2[j];
-          const uint32_t r = xr[s * 16 + j];
-          if (!first) t = add2(t, pair_u32(r << 16, r & 0xffff0000u));
-          uint32_t xb = cvt_bf16x2(t);
-          if (kBwd) {                          // ReLU gate: closed -> the residual gradient passes unchanged
-            const uint32_t m = gate_mask(gw, j);
-            xb = first ? (xb & m) : ((xb & m) | (r & ~m));
-          }
-          xr[s * 16 + j] = xb;
-          w[j] = kBwd ? xb : relu_bf16x2(xb);
-          if (kSave && !kBwd) gout[s] = gate_push(gout[s], w[j]);
+      for (int j = 0; j < 16; ++j) {
+        uint64_t t = x2[j];
+        const uint32_t r = xr[s * 16 + j];
+        if (!first) t = add2(t, pair_u32(r << 16, r & 0xffff0000u));
+        uint32_t xb = cvt_bf16x2(t);
+        if (kBwd) {                            // ReLU gate: closed -> the residual gradient passes unchanged
+          const uint32_t m = gate_mask(gw, j);
+          xb = first ? (xb & m) : ((xb & m) | (r & ~m));
         }
-        if (L.publish) tmem_st16(e.tmem_base + kFColQ + e.lane_off + (uint32_t)(col0 / 2 + s * 16), w);
-        if (save) {
-          if (s == 0) {                        // the slot's previous TMA store (a whole chunk ago) has read it
-            if (e.lane == 0) bulk_wait_read0();
-            __syncwarp();
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            sts128(e.slot + e.lane * 128 + (((uint32_t)(s * 4 + j) ^ e.sw128) << 4), w[4 * j], w[4 * j + 1],
-                   w[4 * j + 2], w[4 * j + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          w[j] = kBwd ? (cvt_bf16x2(x2[j]) & gate_mask(gw, j)) : relu_bf16x2(cvt_bf16x2(x2[j]));
-          if (kSave && !kBwd) gout[s] = gate_push(gout[s], w[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          sts128(prow + (((uint32_t)(s * 4 + j) ^ e.sw128) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        xr[s * 16 + j] = xb;
+        w[s * 16 + j] = kBwd ? xb : relu_bf16x2(xb);
       }
+      if (L.publish)
+        tmem_st16(e.tmem_base + kFColQ + e.lane_off + (uint32_t)(col0 / 2 + s * 16),
+                  *reinterpret_cast<uint32_t(*)[16]>(&w[s * 16]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        w[s * 16 + j] = kBwd ? (cvt_bf16x2(x2[j]) & gate_mask(gw, j)) : relu_bf16x2(cvt_bf16x2(x2[j]));
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(prow + (((uint32_t)(s * 4 + j) ^ e.sw128) << 4), w[s * 16 + 4 * j], w[s * 16 + 4 * j + 1],
+               w[s * 16 + 4 * j + 2], w[s * 16 + 4 * j + 3]);
     }
   }
   if (KIND != kLayerOut) {
-    // publish this warp's rows of k-block 2c+g of the next layer's A operand to the MMA issuer
-    if (KIND == kLayerX && L.publish) tmem_st_wait();
-    if (KIND == kLayerNet || save) fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (e.lane == 0) {
-      if (L.publish) mbar_arrive_leader_u32(e.a_ready + (2 * c + e.g) * 8);
-      if (save) {
+    // 1. publish this warp's rows of k-block 2c+g of the next layer's A operand to the MMA issuer: this is what the
+    //    tensor pipe may be waiting for, so nothing that only serves the saved copies comes before it
+    if (L.publish) {
+      if (KIND == kLayerX) tmem_st_wait();
+      else fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (e.lane == 0) mbar_arrive_leader_u32(e.a_ready + (2 * c + e.g) * 8);
+    }
+    // 2. the copies kept for the other pass: operand values by TMA store, ReLU gates bit-packed
+    if (save) {
+      if (KIND == kLayerX) {
+        if (e.lane == 0) bulk_wait_read0();    // the slot's previous TMA store (a whole chunk ago) has read it
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(e.slot + e.lane * 128 + (((uint32_t)j ^ e.sw128) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2],
+                 w[4 * j + 3]);
+        fence_proxy_async();
+        __syncwarp();
+      } else if (!L.publish) {
+        fence_proxy_async();
+        __syncwarp();
+      }
+      if (e.lane == 0) {
         tma_store_3d_u32(&maps.acts, KIND == kLayerNet ? e.sP + (2 * c + e.g) * kFPanel + e.q4 * 32 * 128 : e.slot,
                          col0, row0 + e.q4 * 32, L.act_slot);
         bulk_commit();
       }
+      if (!kBwd && row0 + e.row < a.N) {
+        uint32_t g0 = 0u, g1 = 0u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          g0 = gate_push(g0, w[j]);
+          g1 = gate_push(g1, w[16 + j]);
+        }
+        a.gate_bits[((int64_t)L.act_slot * a.N + row0 + e.row) * 8 + c * 2 + e.g] = make_uint2(g0, g1);
+      }
     }
-  } else {
-    __syncwarp();
   }
   if (!kBwd) {
+    __syncwarp();
     sts32f(e.wbias + e.lane * 4, bn0);         // every lane is past its reads of this chunk's bias
     sts32f(e.wbias + (e.lane + 32) * 4, bn1);
     __syncwarp();
-    if (kSave && KIND != kLayerOut && save && row0 + e.row < a.N)
-      a.gate_bits[((int64_t)L.act_slot * a.N + row0 + e.row) * 8 + c * 2 + e.g] = make_uint2(gout[0], gout[1]);
   } else {
     gate = __ldg(gate2);                       // gate words of the chunk after next (the caller double-buffers)
   }
