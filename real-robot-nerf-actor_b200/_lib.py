@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnrf_b200.so")
+LIB_PATH = os.environ.get("NRF_LIB_PATH") or os.path.join(HERE, "libnrf_b200.so")   # override: A/B builds
 
 NRF_PREC_BF16 = 0
 NRF_PREC_FP32 = 1

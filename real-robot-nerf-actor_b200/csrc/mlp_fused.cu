@@ -72,8 +72,9 @@ struct FArgs {
   int n_layers, n_tiles, n_prod;   // n_prod: layers per tile whose epilogue publishes an A operand
   int l_p_free;                    // last layer of a tile whose MMAs read P: after it the next tile's input may land
   int N, d_out, ldo;
-  int dbg;      // NRF_DBG timing experiments (wrong results!): 1 no weight TMA, 2 epilogue protocol only, 4 no MMAs,
-                // 8 MMA issuer ignores acc_empty / a_ready
+  int dbg;      // NRF_DBG timing experiments (wrong results!; only in the profiling instantiations, i.e. with a
+                // profile buffer set): 1 no weight TMA, 2 epilogue protocol only, 4 no MMAs, 8 MMA issuer ignores
+                // acc_empty / a_ready
   float* out;
   uint2* gate_bits;                // slots x (N, 8) x 64 bits: bit-packed ReLU gates, written by the training forward
                                    // (one bit per saved operand element: non-zero) and read by the backward
@@ -199,10 +200,11 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorM
       : "memory");
 }
 
-// cycle accounting of the waits (only when a.prof != NULL; one predictable branch per wait otherwise)
+// cycle accounting of the waits: compiled in only for the kProf instantiations (even a dormant run-time branch
+// per wait cost 5-7 % of the kernel)
 #define FUSED_TIMED(acc, stmt)                         \
   do {                                                 \
-    if (a.prof) {                                      \
+    if (kProf) {                                       \
       const long long t0__ = clock64();                \
       stmt;                                            \
       acc += clock64() - t0__;                         \
@@ -226,7 +228,7 @@ struct EpiCtx {            // per-thread constants of the epilogue
 //   backward: v = gate(acc) (+ g for kLayerX), gate = sign of the forward's saved operand; next operand = bf16(v)
 // Prefetched here and parked until needed: the next chunk's bias values (`nxt`, forward: into the warp's smem slot) or
 // the gate row of the chunk after next (`nxt2`, backward: into mk, which the caller double-buffers by chunk parity).
-template <int KIND, bool kSave, bool kBwd>
+template <int KIND, bool kSave, bool kBwd, bool kProf>
 __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FArgs& a, const FLayer& L, int c,
                                           uint32_t n, int row0, bool first, uint32_t (&xr)[32], uint2& gate,
                                           const void* nxt, const uint2* gate2) {
@@ -241,7 +243,7 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
   FUSED_TIMED(e.t_wait, mbar_wait_u32(e.acc_full + buf * 8, (n >> 1) & 1));
   tc_fence_after();
   const uint32_t taddr = e.tmem_base + buf * 128 + e.g * 64 + e.lane_off;
-  if (a.dbg & 2) {
+  if (kProf && (a.dbg & 2)) {
     tc_fence_before();
     __syncwarp();
     if (e.lane == 0) {
@@ -363,7 +365,7 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
   }
 }
 
-template <bool kSave, bool kBwd>
+template <bool kSave, bool kBwd, bool kProf>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FArgs a) {
   using Cfg = FCfg<kSave>;
@@ -430,7 +432,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
           const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
           for (int c = 0; c < kFChunks; ++c)
             for (int kb = 0; kb < kb_tot; kb += 2) {
-              if (a.dbg & 1) continue;
+              if (kProf && (a.dbg & 1)) continue;
               const int nk = kb_tot - kb < 2 ? 1 : 2;
               if (kb >= kb_main) {                     // this CTA's 128 rows of the trailing global A k-panels
                 for (int h = 0; h < nk; ++h) {
@@ -460,7 +462,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
             }
         }
       }
-      if (a.prof && lane == 0) {
+      if (kProf && lane == 0) {
         a.prof[blockIdx.x * 32 + 0] = clock64() - t_begin;
         a.prof[blockIdx.x * 32 + 1] = t_empty;
       }
@@ -495,7 +497,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
           const uint32_t a_par = (uint32_t)(it * a.n_prod + l - 1) & 1;   // phase of the epilogue that produced A
           for (int c = 0; c < kFChunks; ++c, ++n) {
             const uint32_t buf = n & 1;
-            if (!(a.dbg & 8)) FUSED_TIMED(t_acc, mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1));
+            if (!(kProf && (a.dbg & 8))) FUSED_TIMED(t_acc, mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1));
             const uint32_t tmem_d = tmem_base + buf * 128;
             for (int kb0 = 0; kb0 < kb_tot; kb0 += 2) {
               const int nk = kb_tot - kb0 < 2 ? 1 : 2;
@@ -505,19 +507,19 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
               if (ext) {
                 sa0 = st.stage;
                 pa0 = sRing_u + st.stage * kFStageB;
-                if (!(a.dbg & 1)) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
+                if (!(kProf && (a.dbg & 1))) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
                 st.advance(kStages);
                 if (nk == 2) {
                   sa1 = st.stage;
                   pa1 = sRing_u + st.stage * kFStageB;
-                  if (!(a.dbg & 1)) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
+                  if (!(kProf && (a.dbg & 1))) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
                   st.advance(kStages);
                 }
               } else if (a_src != kSrcQ) {
                 pa0 = sP_u + kb0 * kFPanel;
                 pa1 = pa0 + kFPanel;
               }
-              if (!ext && c == 0 && !(a.dbg & 8)) {
+              if (!ext && c == 0 && !(kProf && (a.dbg & 8))) {
                 if (a_src == kSrcIn) {                  // loaded by warp 3
                   FUSED_TIMED(t_ready, mbar_wait(in_full + kb0, it & 1));
                   if (nk == 2) FUSED_TIMED(t_ready, mbar_wait(in_full + kb0 + 1, it & 1));
@@ -526,13 +528,13 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
                   if (nk == 2) FUSED_TIMED(t_ready, mbar_wait(a_ready + kb0 + 1, a_par));
                 }
               }
-              if (!(a.dbg & 1)) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
+              if (!(kProf && (a.dbg & 1))) FUSED_TIMED(t_full, mbar_wait(full + st.stage, st.phase));
               tc_fence_after();
               const uint32_t sb = sRing_u + st.stage * kFStageB;
               if (elect_one()) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                  if (h < nk && !(a.dbg & 4)) {
+                  if (h < nk && !(kProf && (a.dbg & 4))) {
                     const int kb = kb0 + h;
                     const uint64_t bdesc = make_sdesc(sb + h * kFBoxB, 16, 1024);
                     if (!ext && a_src == kSrcQ) {
@@ -548,7 +550,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
                     }
                   }
                 }
-                if (!(a.dbg & 1)) {
+                if (!(kProf && (a.dbg & 1))) {
                   if (ext) {
                     umma_commit_pair(empty + sa0);
                     if (nk == 2) umma_commit_pair(empty + sa1);
@@ -567,7 +569,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
           }
         }
       }
-      if (a.prof && lane == 0) {
+      if (kProf && lane == 0) {
         a.prof[blockIdx.x * 32 + 2] = clock64() - t_begin;
         a.prof[blockIdx.x * 32 + 3] = t_acc;
         a.prof[blockIdx.x * 32 + 4] = t_ready;
@@ -639,22 +641,22 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
         if (kind == kLayerX) {
 #pragma unroll
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerX, kSave, kBwd>(e, maps, a, L, c, n, row0, first, xres[c], gate[c & 1],
+            epi_chunk<kLayerX, kSave, kBwd, kProf>(e, maps, a, L, c, n, row0, first, xres[c], gate[c & 1],
                                             pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         } else if (kind == kLayerNet) {
 #pragma unroll 2
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerNet, kSave, kBwd>(e, maps, a, L, c, n, row0, false, xres[0], gate[c & 1],
+            epi_chunk<kLayerNet, kSave, kBwd, kProf>(e, maps, a, L, c, n, row0, false, xres[0], gate[c & 1],
                                               pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         } else if (!kBwd) {
 #pragma unroll 1
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerOut, kSave, kBwd>(e, maps, a, L, c, n, row0, false, xres[0], gate[0],
+            epi_chunk<kLayerOut, kSave, kBwd, kProf>(e, maps, a, L, c, n, row0, false, xres[0], gate[0],
                                               pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         }
       }
     }
-    if (a.prof && lane == 0) {
+    if (kProf && lane == 0) {
       a.prof[blockIdx.x * 32 + 8 + 2 * ew] = clock64() - t_begin;
       a.prof[blockIdx.x * 32 + 9 + 2 * ew] = e.t_wait;
     }
@@ -732,10 +734,13 @@ int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
   a.prof = reinterpret_cast<long long*>(d.prof);
   int grid = sm_count() / 2 * 2;
   if (grid > 2 * a.n_tiles) grid = 2 * a.n_tiles;
-  auto kern = d.backward ? mlp_fused_kernel<true, true> : (save ? mlp_fused_kernel<true, false> : mlp_fused_kernel<false, false>);
-  const int which = d.backward ? 2 : (save ? 1 : 0);
+  const bool prof = a.prof != nullptr;
+  auto kern = d.backward ? (prof ? mlp_fused_kernel<true, true, true> : mlp_fused_kernel<true, true, false>)
+              : save     ? (prof ? mlp_fused_kernel<true, false, true> : mlp_fused_kernel<true, false, false>)
+                         : (prof ? mlp_fused_kernel<false, false, true> : mlp_fused_kernel<false, false, false>);
+  const int which = (d.backward ? 2 : (save ? 1 : 0)) + (prof ? 3 : 0);
   const int smem_bytes = save ? FCfg<true>::kSmem : FCfg<false>::kSmem;
-  static bool attr_set[3] = {false, false, false};
+  static bool attr_set[6] = {false, false, false, false, false, false};
   if (!attr_set[which]) {
     NRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set[which] = true;
