@@ -407,9 +407,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   const int m_begin = blockIdx.y * m_per_split;
   const int m_end = min(M, m_begin + m_per_split);
   const int num_mb = (m_end - m_begin + kTileK - 1) / kTileK;
-  // bias gradient = column sums of G = G^T . 1: the CTAs of the first k tile issue one extra N=16 MMA per
-  // k-step against a constant tile of ones (+6 % tensor time, no extra memory traffic, no extra barriers)
-  const bool do_bias = dbias != nullptr && k_blk == 0;
+  // bias gradient = column sums of G = G^T . 1: one extra N=16 MMA per k-step against a constant tile of ones (no
+  // extra memory traffic, no extra barriers).  It re-reads the 4 KB G^T operand from shared memory, a quarter of a
+  // main MMA's time, so the k-steps are dealt round-robin over the CTAs that share this G tile (the k tiles): every
+  // CTA sums its share of the samples and the launch finishes together.
+  const bool do_bias = dbias != nullptr;
+  // k-step i belongs to k tile (i & bias_mask); a k-tile count that is not a power of two leaves all of it to tile 0
+  const int bias_mask = (k_tiles & (k_tiles - 1)) == 0 ? k_tiles - 1 : 0;
   if (warp >= kEpiWarp0) {
     for (int i = threadIdx.x - kEpiWarp0 * 32; i < Cfg::kOnes / 4; i += 128)
       reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;      // two bf16 1.0
@@ -468,6 +472,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
       constexpr uint32_t idesc_bias = make_idesc(kTileM * CG, 16, 1, 1);
       const uint64_t odesc = make_sdesc(smem_u32(ones), kTileK * 128, 1024);
       PipeState st;
+      uint32_t bias_acc = 0;                       // the first bias MMA of this CTA overwrites its accumulator columns
       for (int mb = 0; mb < num_mb; ++mb) {
         mbar_wait(full + st.stage, st.phase);
         tc_fence_after();
@@ -479,13 +484,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < kTileK / kUmmaK; ++k) {
             // 16 samples = two 8-row atoms = 2048 B: +128 in the 16 B address field
+            const bool bias_step = do_bias && ((mb * (kTileK / kUmmaK) + k) & bias_mask) == k_blk;
             if (CG == 2) {
               umma_bf16_pair(tmem_base, gdesc + 128 * k, adesc + 128 * k, idesc, (mb | k) != 0);
-              if (do_bias) umma_bf16_pair(tmem_base + BK_, gdesc + 128 * k, odesc, idesc_bias, (mb | k) != 0);
+              if (bias_step) umma_bf16_pair(tmem_base + BK_, gdesc + 128 * k, odesc, idesc_bias, bias_acc);
             } else {
               umma_bf16(tmem_base, gdesc + 128 * k, adesc + 128 * k, idesc, (mb | k) != 0);
-              if (do_bias) umma_bf16(tmem_base + BK_, gdesc + 128 * k, odesc, idesc_bias, (mb | k) != 0);
+              if (bias_step) umma_bf16(tmem_base + BK_, gdesc + 128 * k, odesc, idesc_bias, bias_acc);
             }
+            if (bias_step) bias_acc = 1;
           }
           if (CG == 2) umma_commit_pair(empty + st.stage); else umma_commit(empty + st.stage);
         }
@@ -531,11 +538,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
           }
         }
       }
-      if (do_bias) {                              // column BK_ of the accumulator: sum over the samples of G[:, n]
+      // column BK_ of the accumulator: this CTA's share of the sum over the samples of G[:, n] (nothing if its share
+      // of the k-steps was empty: a split shorter than k_tiles k-steps)
+      if (do_bias && (bias_mask ? num_mb * (kTileK / kUmmaK) > k_blk : k_blk == 0)) {
         uint32_t v[32];
         tmem_ld32(taddr + BK_, v);
-        if (ws) ws[(int64_t)gridDim.y * n_pad * k_pad + (int64_t)blockIdx.y * n_pad + n] = __uint_as_float(v[0]);
+        if (ws) ws[(int64_t)gridDim.y * n_pad * k_pad + ((int64_t)k_blk * gridDim.y + blockIdx.y) * n_pad + n] = __uint_as_float(v[0]);
         else if (n < n_valid) atomicAdd(dbias + n, __uint_as_float(v[0]));
+      } else if (do_bias && ws) {
+        ws[(int64_t)gridDim.y * n_pad * k_pad + ((int64_t)k_blk * gridDim.y + blockIdx.y) * n_pad + n] = 0.0f;
       }
     }
   }
@@ -551,7 +562,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
 // dW[n,k] += sum over splits (ascending) of the partial tiles; dbias likewise.  One thread per 4 columns.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int n_pad,
                                                            int k_pad, int n_valid, int k_valid,
-                                                           float* __restrict__ dW, int ldw, float* __restrict__ dbias) {
+                                                           float* __restrict__ dW, int ldw, float* __restrict__ dbias,
+                                                           int bias_parts) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int kq = (k_valid + 3) / 4;
   if (t < (int64_t)n_valid * kq) {
@@ -571,7 +583,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     if (n < n_valid) {
       const float* wb = ws + (int64_t)splits * n_pad * k_pad;
       float acc = 0.f;
-      for (int s = 0; s < splits; ++s) acc += wb[(int64_t)s * n_pad + n];
+      for (int s = 0; s < splits * bias_parts; ++s) acc += wb[(int64_t)s * n_pad + n];
       dbias[n] += acc;
     }
   }
@@ -724,7 +736,7 @@ static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, i
     int64_t work = (int64_t)n_valid * ((k_valid + 3) / 4) + (dbias ? n_valid : 0);
     { LaunchScope ls_(NRF_CAT_WGRAD, stream);
     wgrad_reduce_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(ws, splits, n_pad, k_pad, n_valid, k_valid,
-                                                                           dW, ldw, dbias);
+                                                                           dW, ldw, dbias, k_tiles);
     }
     NRF_LAUNCH_OK();
   }
