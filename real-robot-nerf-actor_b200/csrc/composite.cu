@@ -276,6 +276,183 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast paths for D = 128 * DV (384 at the BASELINE dims, 512 in nerfact.conf): the D feature channels are exactly DV
+// float4 per lane, the [r g b sigma] head is handled by lane 0 outside the vector loop, nothing is predicated.
+// The generic kernels above spend ~380 warp instructions per sample on predicates for the ragged 97-float4 row;
+// these need ~70 and read every field row exactly once.
+template <int DV>
+__global__ void __launch_bounds__(128) composite_fwd_fast_kernel(
+    const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
+    int K, int white_bkgd, float* __restrict__ weights, float* __restrict__ rgb, float* __restrict__ embed,
+    float* __restrict__ depth) {
+  constexpr int D = 128 * DV;
+  extern __shared__ float smem[];
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int r = blockIdx.x;
+  float* s_w = smem;
+  float* s_alpha = s_w + K;
+  float* s_part = smem + ((2 * K + 3) & ~3);   // kRayWarps x (D + 8): embed sums, then rgb(3), depth, wsum
+  const float* f = field + (int64_t)r * K * ldo;
+  const float* zrow = z + (int64_t)r * K;
+  const float far = rays[(int64_t)r * 8 + 7];
+  if (wid == 0) ray_weights<false>(f, ldo, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr);
+  __syncthreads();
+  float4 acc[DV];
+#pragma unroll
+  for (int i = 0; i < DV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float hr = 0.f, hg = 0.f, hb = 0.f, dsum = 0.f, wsum = 0.f;
+#pragma unroll 2
+  for (int k = wid; k < K; k += kRayWarps) {
+    const float w = s_w[k];
+    const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
+    float4 x[DV];
+#pragma unroll
+    for (int i = 0; i < DV; ++i) x[i] = __ldg(row + 1 + lane + i * kWarp);
+    if (lane == 0) {
+      const float4 h = __ldg(row);
+      hr = fmaf(w, sigmoidf_(h.x), hr);
+      hg = fmaf(w, sigmoidf_(h.y), hg);
+      hb = fmaf(w, sigmoidf_(h.z), hb);
+      dsum = fmaf(w, zrow[k], dsum);
+      wsum += w;
+    }
+#pragma unroll
+    for (int i = 0; i < DV; ++i) {
+      acc[i].x = fmaf(w, x[i].x, acc[i].x);
+      acc[i].y = fmaf(w, x[i].y, acc[i].y);
+      acc[i].z = fmaf(w, x[i].z, acc[i].z);
+      acc[i].w = fmaf(w, x[i].w, acc[i].w);
+    }
+  }
+  constexpr int pstride = D + 8;
+  float* mine = s_part + wid * pstride;
+#pragma unroll
+  for (int i = 0; i < DV; ++i) *reinterpret_cast<float4*>(mine + (lane + i * kWarp) * 4) = acc[i];
+  if (lane == 0) { mine[D] = hr; mine[D + 1] = hg; mine[D + 2] = hb; mine[D + 3] = dsum; mine[D + 4] = wsum; }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) weights[(int64_t)r * K + k] = s_w[k];
+  for (int c = threadIdx.x; c < D + 4; c += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRayWarps; ++w) v += s_part[w * pstride + c];
+    if (c < D) {
+      embed[(int64_t)r * D + c] = v;
+    } else if (c < D + 3) {
+      float ws = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRayWarps; ++w) ws += s_part[w * pstride + D + 4];
+      rgb[(int64_t)r * 3 + (c - D)] = v + (white_bkgd ? 1.0f - ws : 0.0f);
+    } else {
+      depth[r] = v;
+    }
+  }
+}
+
+template <int DV, typename T>
+__global__ void __launch_bounds__(128) composite_bwd_fast_kernel(
+    const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
+    int K, int white_bkgd, const float* __restrict__ d_rgb, const float* __restrict__ d_embed,
+    const float* __restrict__ d_depth, const float* __restrict__ d_weights, T* __restrict__ d_field, int ldg,
+    float* __restrict__ d_z) {
+  constexpr int D = 128 * DV;
+  extern __shared__ float smem[];
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int r = blockIdx.x;
+  float* s_w = smem;
+  float* s_alpha = s_w + K;
+  float* s_T = s_alpha + K;
+  float* s_delta = s_T + K;
+  float* s_g = s_delta + K;
+  float* s_ds = s_g + K;       // (1 - alpha) * bracket
+  float* s_sig = s_ds + K;     // relu(sigma_k) (0 where the raw output is <= 0)
+  float* s_h = s_sig + K;      // 3 per sample: d_rgb_c * s(1-s), the sigmoid-head factors
+  const float* f = field + (int64_t)r * K * ldo;
+  const float* zrow = z + (int64_t)r * K;
+  const float far = rays[(int64_t)r * 8 + 7];
+  if (wid == 0) ray_weights<true>(f, ldo, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta);
+  // this lane's slice of dL/d(embed of the ray) and the ray's scalar upstream gradients
+  float4 de[DV];
+#pragma unroll
+  for (int i = 0; i < DV; ++i) de[i] = __ldg(reinterpret_cast<const float4*>(d_embed + (int64_t)r * D) + lane + i * kWarp);
+  const float dr = d_rgb[(int64_t)r * 3 + 0], dg = d_rgb[(int64_t)r * 3 + 1], db = d_rgb[(int64_t)r * 3 + 2];
+  const float dd = d_depth ? d_depth[r] : 0.0f;
+  const float bk = white_bkgd ? -(dr + dg + db) : 0.0f;
+  __syncthreads();
+
+  // pass A: g_k = <d_rgb, rgb_k> + <d_embed, e_k> + d_depth z_k (+ d_w_k); every field row is read here, once
+#pragma unroll 2
+  for (int k = wid; k < K; k += kRayWarps) {
+    const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
+    float4 x[DV];
+#pragma unroll
+    for (int i = 0; i < DV; ++i) x[i] = __ldg(row + 1 + lane + i * kWarp);
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < DV; ++i) part += x[i].x * de[i].x + x[i].y * de[i].y + x[i].z * de[i].z + x[i].w * de[i].w;
+    part = warp_sum(part);
+    if (lane == 0) {
+      const float4 h = __ldg(row);
+      const float sr = sigmoidf_(h.x), sg = sigmoidf_(h.y), sb = sigmoidf_(h.z);
+      float g = part + sr * dr + sg * dg + sb * db + dd * zrow[k] + bk;
+      if (d_weights) g += d_weights[(int64_t)r * K + k];
+      s_g[k] = g;
+      s_sig[k] = fmaxf(h.w, 0.0f);
+      s_h[3 * k + 0] = dr * sr * (1.0f - sr);
+      s_h[3 * k + 1] = dg * sg * (1.0f - sg);
+      s_h[3 * k + 2] = db * sb * (1.0f - sb);
+    }
+  }
+  __syncthreads();
+  // suffix sums S_k = sum_{j>k} w_j g_j : lane-chunked reverse scan (warp 0)
+  if (wid == 0) {
+    int chunk = (K + kWarp - 1) / kWarp;
+    int k0 = lane * chunk, k1 = min(K, k0 + chunk);
+    float local = 0.f;
+    for (int k = k0; k < k1; ++k) local += s_w[k] * s_g[k];
+    float incl = local;
+#pragma unroll
+    for (int o = 1; o < kWarp; o <<= 1) {
+      float v = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < kWarp) incl += v;
+    }
+    float run = incl - local;   // sum over later lanes
+    for (int k = k1 - 1; k >= k0; --k) {
+      float alpha = s_alpha[k];
+      float one_m = 1.0f - alpha;
+      float bracket = s_T[k] * s_g[k] - run / (one_m + 1e-10f);
+      run += s_w[k] * s_g[k];
+      s_ds[k] = one_m * bracket;
+    }
+  }
+  __syncthreads();
+  // pass B: the gradient rows, from shared memory and registers only
+  const int pad4 = (ldg - (4 + D)) / 4;            // zero-filled float4 groups behind the last channel
+#pragma unroll 2
+  for (int k = wid; k < K; k += kRayWarps) {
+    const float w = s_w[k];
+    T* grow = d_field + ((int64_t)r * K + k) * ldg;
+#pragma unroll
+    for (int i = 0; i < DV; ++i)
+      store_grad4<T>(grow + 4 + (lane + i * kWarp) * 4, make_float4(w * de[i].x, w * de[i].y, w * de[i].z, w * de[i].w));
+    if (lane == 0) {
+      const float sig = s_sig[k];
+      store_grad4<T>(grow, make_float4(w * s_h[3 * k], w * s_h[3 * k + 1], w * s_h[3 * k + 2],
+                                       sig > 0.0f ? s_delta[k] * s_ds[k] : 0.0f));
+    } else if (lane <= pad4) {
+      store_grad4<T>(grow + 4 + D + (lane - 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+  if (d_z) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float dl_k = s_sig[k] * s_ds[k];
+      float dl_km1 = k > 0 ? s_sig[k - 1] * s_ds[k - 1] : 0.f;
+      d_z[(int64_t)r * K + k] = dd * s_w[k] + dl_km1 - dl_k;
+    }
+  }
+}
+
 }  // namespace nrf
 
 using namespace nrf;
@@ -297,9 +474,17 @@ extern "C" int nrf_composite_fwd(const float* field_out, int ldo, const float* z
   int rc = check_composite("nrf_composite_fwd", R, K, D, ldo);
   if (rc) return rc;
   size_t smem = ((size_t)((2 * K + 3) & ~3) + (size_t)kRayWarps * (4 + D + 4)) * sizeof(float);
+  const bool aligned = (reinterpret_cast<uintptr_t>(field_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(embed) & 15) == 0;
   { LaunchScope ls_(NRF_CAT_COMPOSITE_FWD, as_stream(stream));
-  composite_fwd_kernel<<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
-      field_out, ldo, z, rays, R, K, D, white_bkgd, weights, rgb, embed, depth);
+  if (D == 384 && aligned && smem <= 48 * 1024)
+    composite_fwd_fast_kernel<3><<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
+        field_out, ldo, z, rays, K, white_bkgd, weights, rgb, embed, depth);
+  else if (D == 512 && aligned && smem <= 48 * 1024)
+    composite_fwd_fast_kernel<4><<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
+        field_out, ldo, z, rays, K, white_bkgd, weights, rgb, embed, depth);
+  else
+    composite_fwd_kernel<<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
+        field_out, ldo, z, rays, R, K, D, white_bkgd, weights, rgb, embed, depth);
   }
   NRF_LAUNCH_OK();
   return NRF_OK;
@@ -316,7 +501,21 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
   NRF_REQUIRE(ldg >= 4 + D && ldg % 4 == 0, NRF_EINVAL, "nrf_composite_bwd: ldg=%d", ldg);
   size_t smem = (size_t)6 * K * sizeof(float);
   dim3 grid(R), block(kRayWarps * kWarp);
-  if (out_bf16) {
+  // fast path (D = 384 / 512): every field row read once, nothing predicated
+  const size_t smem_fast = (size_t)10 * K * sizeof(float);
+  const bool aligned = (reinterpret_cast<uintptr_t>(field_out) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(d_embed) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_field) & 15) == 0;
+  const int pad4 = (ldg - (4 + D)) / 4;
+  if ((D == 384 || D == 512) && aligned && smem_fast <= 48 * 1024 && pad4 < kWarp) {
+    LaunchScope ls_(NRF_CAT_COMPOSITE_BWD, as_stream(stream));
+#define NRF_CBWD_FAST(DV, T)                                                                                   \
+    composite_bwd_fast_kernel<DV, T><<<grid, block, smem_fast, as_stream(stream)>>>(                          \
+        field_out, ldo, z, rays, K, white_bkgd, d_rgb, d_embed, d_depth, d_weights, reinterpret_cast<T*>(d_field), \
+        ldg, d_z)
+    if (D == 384) { if (out_bf16) NRF_CBWD_FAST(3, __nv_bfloat16); else NRF_CBWD_FAST(3, float); }
+    else { if (out_bf16) NRF_CBWD_FAST(4, __nv_bfloat16); else NRF_CBWD_FAST(4, float); }
+#undef NRF_CBWD_FAST
+  } else if (out_bf16) {
     if (smem > 48 * 1024)
       NRF_CUDA_OK(cudaFuncSetAttribute(composite_bwd_kernel<__nv_bfloat16>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

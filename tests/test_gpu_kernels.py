@@ -190,7 +190,8 @@ def test_scatter_volume_grad_matches_autograd(ops):
 
 
 # ------------------------------------------------------------------------------ compositing
-@pytest.mark.parametrize("K,D,white", [(64, 384, False), (128, 384, False), (96, 24, True), (40, 8, False)])
+@pytest.mark.parametrize("K,D,white", [(64, 384, False), (128, 384, False), (96, 24, True), (40, 8, False),
+                                       (128, 384, True), (80, 512, False), (256, 384, False)])
 def test_composite_fwd_bwd_matches_oracle(ops, K, D, white):
     g = torch.Generator().manual_seed(K + D)
     R = 37
