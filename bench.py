@@ -121,7 +121,10 @@ def run_ours(args):
     ren = ren.to(dev).train()
     ren.scatter = args.scatter
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    vol = (torch.randn(SB, wl.C, wl.S, wl.S, wl.S, device=dev, generator=g) * 0.1).requires_grad_(True)
+    vol = torch.randn(SB, wl.C, wl.S, wl.S, wl.S, device=dev, generator=g) * 0.1
+    if args.volume_layout == "channels_last_3d":       # what a conv3d producer run in that memory format hands over
+        vol = vol.contiguous(memory_format=torch.channels_last_3d)
+    vol.requires_grad_(True)
     # host-side inputs of a training step (what the data loader hands over), pinned
     poses_h = syn.arc_poses(SB).pin_memory()
     focal_h = torch.tensor(wl.focal, dtype=torch.float32).pin_memory()
@@ -243,7 +246,7 @@ def run_ours(args):
             "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
             "config": {"workload": f"{wl.name}: per GPU {SB} scenes x {n_rays} rays, {wl.n_coarse}+{wl.n_fine} samples, "
                                    f"{wl.S}^3 x {wl.C}ch volume, ResnetFC 512x5, RGB+{wl.D}d heads, fwd+bwd",
-                       "evals_per_step": evals_step, "precision": args.precision, "scatter": args.scatter,
+                       "evals_per_step": evals_step, "precision": args.precision, "scatter": args.scatter, "volume_layout": args.volume_layout,
                        "l2": "working set (1 GiB volume + ~20 GiB activations per step) >> 126 MB L2; no flush needed",
                        "parallelism": f"dp{world} over scenes; NCCL all-reduce of MLP grads" if world > 1 else "single GPU"},
             "e2e": {"value": round(e2e_value, 1), "unit": "ray-samples/s", "ms_per_step": round(ms_e2e / args.steps, 3),
@@ -339,6 +342,9 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=128, dest="cpu_rays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scatter", default="sorted", choices=["atomic", "sorted"])
+    ap.add_argument("--volume-layout", default="contiguous", choices=["contiguous", "channels_last_3d"],
+                    dest="volume_layout", help="memory format of the voxel volume handed to the renderer (default: "
+                    "the reference's contiguous (SB,C,S,S,S); channels_last_3d skips both re-layout passes)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

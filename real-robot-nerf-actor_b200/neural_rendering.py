@@ -329,6 +329,13 @@ def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, 
     return d_z
 
 
+def _is_channels_last_3d(t):
+    """(SB,C,S0,S1,S2) tensor whose memory is (SB,S0,S1,S2,C): what a conv3d stack run in torch.channels_last_3d
+    hands over.  The kernels read exactly that layout, so no re-layout pass is needed."""
+    return t.dim() == 5 and t.shape[1] > 1 and not t.is_contiguous() and \
+        t.is_contiguous(memory_format=torch.channels_last_3d)
+
+
 def _zero_grads(mlp: ops.FieldMLP):
     """Zeroed gradient buffers for every MLP parameter: ONE flat allocation / fill, views per parameter."""
     names = mlp.names()
@@ -360,7 +367,14 @@ class _ForwardNerfFn(torch.autograd.Function):
         mlp_c = ren.nerf_model.mlp_coarse.handle(ren._prec)
         mlp_f = ren.nerf_model.mlp_fine.handle(ren._prec)
         held = getattr(ren, "_vol_cl_held", None)          # rendering(): one re-layout for all ray chunks
-        vol_cl = held[1] if held is not None and held[0] is voxel_feat else ops.volume_to_channels_last(voxel_feat)
+        cl3d = _is_channels_last_3d(voxel_feat)
+        if cl3d:                                           # producer ran in torch.channels_last_3d: zero-copy view
+            vol_cl = voxel_feat.permute(0, 2, 3, 4, 1)
+        elif held is not None and held[0] is voxel_feat:
+            vol_cl = held[1]
+        else:
+            vol_cl = ops.volume_to_channels_last(voxel_feat)
+        ctx.cl3d = cl3d
         Kc, Kf, Kfd = ren.n_coarse, ren.n_fine, ren.n_fine_depth
         z_c = ops.sample_coarse(rays, Kc, noise.get("coarse"), ren.lindisp)
         st_c, (cw, crgb, cemb, cdep) = _pass_forward(ren, mlp_c, vol_cl, rays, z_c, rps, keep)
@@ -429,7 +443,9 @@ class _ForwardNerfFn(torch.autograd.Function):
                 d_cdep = d_cdep + (d_cat[:, K - Kfd:] * ctx.depth_mask).sum(-1)
         _pass_backward(ren, st_c, _zeros_like_or(d_crgb, (R, 3), dev), _zeros_like_or(d_cemb, (R, D), dev),
                        d_cdep, d_cw, grads_c, grad_cl, first=st_f is None)
-        d_vol = ops.volume_to_channels_first(grad_cl) if ctx.needs_input_grad[1] else None
+        d_vol = None
+        if ctx.needs_input_grad[1]:                        # channels_last_3d in -> channels_last_3d gradient out
+            d_vol = grad_cl.permute(0, 4, 1, 2, 3) if ctx.cl3d else ops.volume_to_channels_first(grad_cl)
         pg = [grads_c[n] for n in names_c]
         if not shared and st_f is not None:
             pg += [grads_f[n] for n in st_f.mlp.names()]
@@ -605,7 +621,8 @@ class NeuralRenderer(nn.Module):
         rays = rays.reshape(B * H * W, 8)
         rgbs, embeds, depths = [], [], []
         # the volume is re-laid out channels-last once for all ray chunks (the tensor is held, so identity is safe)
-        self._vol_cl_held = (voxel_feat, ops.volume_to_channels_last(voxel_feat))
+        self._vol_cl_held = None if _is_channels_last_3d(voxel_feat) else \
+            (voxel_feat, ops.volume_to_channels_last(voxel_feat))
         try:
             for i in range(0, rays.shape[0], self.render_chunk_rays):
                 out = self.forward_nerf(rays[i:i + self.render_chunk_rays].unsqueeze(0))
@@ -695,9 +712,10 @@ class _CompositeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ren, h, voxel_feat, rays, z, sb, *params):
-        vol_cl = ops.volume_to_channels_last(voxel_feat)
+        cl3d = _is_channels_last_3d(voxel_feat)
+        vol_cl = voxel_feat.permute(0, 2, 3, 4, 1) if cl3d else ops.volume_to_channels_last(voxel_feat)
         st, outs = _pass_forward(ren, h, vol_cl, rays, z, rays.shape[0] // sb)
-        ctx.ren, ctx.st, ctx.vol_shape = ren, st, tuple(vol_cl.shape)
+        ctx.ren, ctx.st, ctx.vol_shape, ctx.cl3d = ren, st, tuple(vol_cl.shape), cl3d
         return outs
 
     @staticmethod
@@ -711,5 +729,7 @@ class _CompositeFn(torch.autograd.Function):
         grad_cl = alloc(ctx.vol_shape, device=dev, dtype=torch.float32)
         d_z = _pass_backward(ren, st, _zeros_like_or(d_rgb, (R, 3), dev), _zeros_like_or(d_emb, (R, D), dev),
                              d_dep, d_w, grads, grad_cl, want_dz=ctx.needs_input_grad[4])
-        d_vol = ops.volume_to_channels_first(grad_cl) if ctx.needs_input_grad[2] else None
+        d_vol = None
+        if ctx.needs_input_grad[2]:
+            d_vol = grad_cl.permute(0, 4, 1, 2, 3) if ctx.cl3d else ops.volume_to_channels_first(grad_cl)
         return (None, None, d_vol, None, d_z, None, *[grads[n] for n in names])

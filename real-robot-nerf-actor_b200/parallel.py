@@ -85,7 +85,9 @@ def render_sharded(renderer, voxel_feat, focal, tgt_pose, c=None, group=None, ga
     renderer.encode(None, None, None, voxel_feat, None, focal, c)
     rgbs, embs, deps = [], [], []
     from . import ops
-    renderer._vol_cl_held = (voxel_feat, ops.volume_to_channels_last(voxel_feat))   # one re-layout for all chunks
+    from .neural_rendering import _is_channels_last_3d
+    renderer._vol_cl_held = None if _is_channels_last_3d(voxel_feat) else \
+        (voxel_feat, ops.volume_to_channels_last(voxel_feat))                       # one re-layout for all chunks
     try:
         for i in range(lo, hi, renderer.render_chunk_rays):
             out = renderer.forward_nerf(flat[i:min(i + renderer.render_chunk_rays, hi)].unsqueeze(0)).fine

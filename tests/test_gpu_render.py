@@ -349,3 +349,31 @@ def test_bf16_training_step_is_reproducible_when_asked(ops, NR):
     assert torch.equal(runs[0][0], runs[1][0])
     for k in runs[0][1]:
         assert torch.equal(runs[0][1][k], runs[1][1][k]), k
+
+
+def test_channels_last_3d_volume_is_taken_without_relayout(ops, NR):
+    """A voxel volume in torch.channels_last_3d memory format (what a conv3d producer run in that format hands
+    over) gives bit-identical outputs and gradients; its gradient comes back in the same format."""
+    fx = golden("small_kfd0")
+    ci = _case_inputs(fx)
+    ren = make_renderer(NR, [int(v) for v in fx["meta"]], ci["params"], "fp32")
+    rays, idx = T(fx["rays"]), T(fx["idx"])
+    gt_rgb = T(fx["gt_rgb_img"]).reshape(ci["SB"], -1, 3)[:, idx]
+    gt_emb = T(fx["gt_embed_img"]).reshape(ci["SB"], -1, ci["D"])[:, idx]
+    noise = {k: v.cuda() for k, v in ci["noise"].items()}
+    res = []
+    for fmt in (torch.contiguous_format, torch.channels_last_3d):
+        for p in ren.parameters():
+            p.grad = None
+        vol = T(fx["vol"]).cuda().contiguous(memory_format=fmt).requires_grad_(True)
+        ren.encode(None, None, None, vol, None, None, None)
+        out = ren.forward_nerf(rays.cuda(), noise=noise)
+        loss = O.rendering_loss({l: {k: out[l][k] for k in ("rgb", "embed", "depth")} for l in ("coarse", "fine")},
+                                gt_rgb.cuda(), gt_emb.cuda())["loss"]
+        loss.backward()
+        res.append((out, vol.grad))
+    assert res[1][1].is_contiguous(memory_format=torch.channels_last_3d) and not res[1][1].is_contiguous()
+    assert torch.equal(res[0][1], res[1][1])
+    for l in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth"):
+            assert torch.equal(res[0][0][l][k], res[1][0][l][k])
