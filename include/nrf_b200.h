@@ -99,6 +99,19 @@ int nrf_scatter_volume_grad_sorted(const float* rays, const float* z, int R, int
                                    int S1, int S2, const float* bounds_host, int accumulate,
                                    void* workspace, void* stream);
 
+/* Both render passes of a step in ONE counting sort, gradient written once and (channels_first != 0) directly
+ * in the caller's (SB,C,S0,S1,S2) layout -- the autograd of F.grid_sample at models_embed.py:275 for the coarse
+ * and the fine pass together (neural_rendering.py:446,466), without the reference's zero volume per 4096-point
+ * chunk and without a re-layout pass.  Pass a: z_a (R,K_a), dlat_a (R*K_a, ld_a); pass b likewise or z_b = NULL
+ * for a single pass.  A voxel's entries are added in a fixed order (pass a by sample, then pass b): bit-
+ * reproducible, no float atomics; voxels without entries are written as zeros (grad needs no memset).
+ * C must be 64 or 128.  workspace (16 B aligned): nrf_scatter_sorted_workspace_bytes(R*(K_a+K_b), SB, V). */
+int nrf_scatter_volume_grad_merged(const float* rays, int R, int rays_per_scene, const float* z_a, int K_a,
+                                   const float* dlat_a, int ld_a, const float* z_b, int K_b,
+                                   const float* dlat_b, int ld_b, float* grad, int channels_first, int SB,
+                                   int C, int S0, int S1, int S2, const float* bounds_host, void* workspace,
+                                   void* stream);
+
 /* ---- alpha compositing (neural_rendering.py:239-243,316-359) ---------------------------------
  * field_out (N, ldo) raw; heads sigmoid(rgb), relu(sigma) (models_embed.py:444-466) applied here.
  * weights (R,K), rgb (R,3), embed (R,D), depth (R). */

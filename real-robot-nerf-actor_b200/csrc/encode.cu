@@ -143,6 +143,126 @@ __global__ void __launch_bounds__(256) encode_points_kernel(EncodeArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 32 samples per warp iteration (num_freqs == 6, ld_out == C + 64: the BASELINE / nerfact.conf shapes).
+// The one-warp-per-sample kernel above is issue-bound (ncu: 643 warp instructions per sample, 72 % issue slots, 6 %
+// DRAM): every lane repeats the sample's geometry and the 42 tail values are produced 32 at a time behind integer
+// div/mod and a local-memory array.  Here a LANE owns a sample for everything scalar (geometry, trilinear setup, the
+// 36 sines with compile-time element indices, its 128 B / 256 B tail written as 16 B vectors), and the warp then walks
+// its 32 samples for the channel vectors: an out-of-grid sample costs one 256 B zero store, a sample that touches the
+// grid gets its setup by shuffle and the same 8 coalesced corner reads and rounding order as above (bit-identical).
+constexpr int kTailW = 64;
+constexpr int kTailFreqs = 6;
+
+__device__ __forceinline__ float tail_value(int e, const float c[3], const float d[3], float freq_factor) {
+  constexpr int n_pe = 3 + 6 * kTailFreqs;
+  if (e < 3) return c[e];
+  if (e < n_pe) {
+    const int q = e - 3, f = q / 6, w = q % 6;
+    const float freq = freq_factor * (float)(1 << f);
+    const float phase = (w >= 3) ? 1.57079637050628662109375f : 0.0f;   // fp32(pi/2), utils.py:542
+    return sinf(__fmaf_rn(c[w % 3], freq, phase));
+  }
+  if (e < n_pe + 3) return d[e - n_pe];
+  return 0.0f;
+}
+
+template <typename T> struct TailVec;
+template <> struct TailVec<float> {
+  static constexpr int kPer = 4;
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct TailVec<__nv_bfloat16> {
+  static constexpr int kPer = 8;
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&q0); u.y = *reinterpret_cast<uint32_t*>(&q1);
+    u.z = *reinterpret_cast<uint32_t*>(&q2); u.w = *reinterpret_cast<uint32_t*>(&q3);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) encode_points_w32_kernel(EncodeArgs a) {
+  const int lane = threadIdx.x % kWarp;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) / kWarp;
+  const int64_t N = (int64_t)a.R * a.K;
+  const int64_t groups = (N + kWarp - 1) / kWarp;
+  T* out = reinterpret_cast<T*>(a.out);
+  const int C = a.C;
+  const int64_t scene_stride = (int64_t)a.S0 * a.S1 * a.S2 * C;
+  for (int64_t grp = warp; grp < groups; grp += nwarps) {
+    const int64_t n = grp * kWarp + lane;
+    const bool valid = n < N;
+    const int64_t nn = valid ? n : N - 1;
+    const int r = (int)(nn / a.K);
+    const float4 ra = __ldg(reinterpret_cast<const float4*>(a.rays + (int64_t)r * 8));
+    const float4 rb = __ldg(reinterpret_cast<const float4*>(a.rays + (int64_t)r * 8) + 1);
+    const float ray[6] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y};
+    const SampleGeom g = sample_geometry(ray, __ldg(a.z + nn), a.bmin, a.bext);
+    const TriSetup ts = trilinear_setup(g.cx, g.cy, g.cz, a.S0, a.S1, a.S2);
+    if (valid) {
+      const float c[3] = {g.cx, g.cy, g.cz}, d[3] = {ra.w, rb.x, rb.y};
+      T* tail = out + n * a.ld_out + C;
+      constexpr int kPer = TailVec<T>::kPer;
+#pragma unroll
+      for (int j = 0; j < kTailW / kPer; ++j) {
+        float v[kPer];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) v[i] = tail_value(j * kPer + i, c, d, a.freq_factor);
+        TailVec<T>::store(tail + j * kPer, v);
+      }
+      if (a.points) {
+        a.points[n * 3 + 0] = g.px; a.points[n * 3 + 1] = g.py; a.points[n * 3 + 2] = g.pz;
+      }
+    }
+    const unsigned touch = __ballot_sync(0xffffffffu, valid && trilinear_touches(ts, a.S0, a.S1, a.S2));
+    const int scene_l = r / a.rays_per_scene;
+    const int cnt = (int)((N - grp * kWarp) < kWarp ? (N - grp * kWarp) : kWarp);
+    for (int s = 0; s < cnt; ++s) {
+      T* row = out + (grp * kWarp + s) * a.ld_out;
+      if (!((touch >> s) & 1u)) {
+        for (int c0 = lane * 4; c0 < C; c0 += kWarp * 4) store4<T>(row + c0, make_float4(0.f, 0.f, 0.f, 0.f));
+        continue;
+      }
+      TriSetup t;
+      t.x0 = __shfl_sync(0xffffffffu, ts.x0, s); t.y0 = __shfl_sync(0xffffffffu, ts.y0, s);
+      t.z0 = __shfl_sync(0xffffffffu, ts.z0, s);
+      t.wx0 = __shfl_sync(0xffffffffu, ts.wx0, s); t.wx1 = __shfl_sync(0xffffffffu, ts.wx1, s);
+      t.wy0 = __shfl_sync(0xffffffffu, ts.wy0, s); t.wy1 = __shfl_sync(0xffffffffu, ts.wy1, s);
+      t.wz0 = __shfl_sync(0xffffffffu, ts.wz0, s); t.wz1 = __shfl_sync(0xffffffffu, ts.wz1, s);
+      t.finite = true;
+      const int scene = __shfl_sync(0xffffffffu, scene_l, s);
+      Corner8 c8;
+      corners_from_setup(t, a.S0, a.S1, a.S2, C, c8);
+      const float* vol = a.vol + (int64_t)scene * scene_stride;
+      for (int c0 = lane * 4; c0 < C; c0 += kWarp * 4) {
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          v[k] = c8.off[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(vol + c8.off[k] + c0))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (c8.off[k] >= 0) {
+            acc.x = __fadd_rn(acc.x, __fmul_rn(v[k].x, c8.w[k]));
+            acc.y = __fadd_rn(acc.y, __fmul_rn(v[k].y, c8.w[k]));
+            acc.z = __fadd_rn(acc.z, __fmul_rn(v[k].z, c8.w[k]));
+            acc.w = __fadd_rn(acc.w, __fmul_rn(v[k].w, c8.w[k]));
+          }
+        }
+        store4<T>(row + c0, acc);
+      }
+    }
+  }
+}
+
 struct ScatterArgs {
   const float* rays;
   const float* z;
@@ -243,17 +363,23 @@ extern "C" int nrf_encode_points(const float* rays, const float* z, int R, int K
   a.out = out; a.ld_out = ld_out; a.points = points_out;
   int64_t N = (int64_t)R * K;
   int threads = 256;
-  int64_t want = (N + 7) / 8;
-  int max_blocks = sm_count() * 16;
-  int blocks = (int)(want < max_blocks ? want : max_blocks);
-  if (out_bf16)
-    { LaunchScope ls_(NRF_CAT_ENCODE, as_stream(stream));
-    encode_points_kernel<__nv_bfloat16><<<blocks, threads, 0, as_stream(stream)>>>(a);
-    }
-  else
-    { LaunchScope ls_(NRF_CAT_ENCODE, as_stream(stream));
-    encode_points_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(a);
-    }
+  const bool w32 = num_freqs == kTailFreqs && ld_out == C + kTailW &&
+                   (reinterpret_cast<uintptr_t>(rays) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (w32) {                                   // 32 samples per warp iteration
+    int64_t want = ((N + 31) / 32 + 7) / 8;
+    int max_blocks = sm_count() * 8;
+    int blocks = (int)(want < max_blocks ? want : max_blocks);
+    LaunchScope ls_(NRF_CAT_ENCODE, as_stream(stream));
+    if (out_bf16) encode_points_w32_kernel<__nv_bfloat16><<<blocks, threads, 0, as_stream(stream)>>>(a);
+    else encode_points_w32_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(a);
+  } else {                                     // any other shape: one warp per sample
+    int64_t want = (N + 7) / 8;
+    int max_blocks = sm_count() * 16;
+    int blocks = (int)(want < max_blocks ? want : max_blocks);
+    LaunchScope ls_(NRF_CAT_ENCODE, as_stream(stream));
+    if (out_bf16) encode_points_kernel<__nv_bfloat16><<<blocks, threads, 0, as_stream(stream)>>>(a);
+    else encode_points_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(a);
+  }
   NRF_LAUNCH_OK();
   return NRF_OK;
 }
@@ -447,6 +573,220 @@ __global__ void __launch_bounds__(256) scatter_reduce_kernel(const int32_t* __re
 }
 
 }  // namespace nrf
+
+// ---------------------------------------------------------------------------------------------------------------
+// Both render passes in ONE counting sort, and (optionally) the gradient written straight in the caller's
+// channel-first layout.  Entry e = 8 n + corner with n < N_a: sample n of pass a, else sample n - N_a of pass b;
+// a voxel's entries are summed in ascending e (all of pass a, then pass b): fixed order, no float atomics.
+// Replaces {sorted scatter a, sorted scatter b with read-modify-write, (V,C) -> (C,V) transpose of the whole
+// gradient volume}: the dense gradient is written exactly once.
+namespace nrf {
+
+struct ScatterPass {
+  const float* z;
+  const float* dlat;
+  int K, ld;
+};
+
+__global__ void __launch_bounds__(256) scatter_count2_kernel(const float* __restrict__ rays, int R, int rays_per_scene,
+                                                             ScatterPass pa, ScatterPass pb, int64_t Na, int64_t Nb,
+                                                             ScatterArgs g0, int64_t V, int32_t* __restrict__ key,
+                                                             float* __restrict__ wts, int32_t* __restrict__ count) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Na + Nb) return;
+  const bool second = n >= Na;
+  const int64_t nl = second ? n - Na : n;
+  const int K = second ? pb.K : pa.K;
+  const float* z = second ? pb.z : pa.z;
+  int r = (int)(nl / K);
+  int scene = r / rays_per_scene;
+  SampleGeom g = sample_geometry(rays + (int64_t)r * 8, z[nl], g0.bmin, g0.bext);
+  Corner8 c8;
+  trilinear_corners(g.cx, g.cy, g.cz, g0.S0, g0.S1, g0.S2, 1, c8);      // C = 1: off = voxel index
+  int4 kk[2];
+  int32_t* kp = reinterpret_cast<int32_t*>(kk);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int32_t q = -1;
+    if (c8.off[k] >= 0) {
+      q = (int32_t)((int64_t)scene * V + c8.off[k]);
+      atomicAdd(count + q, 1);
+    }
+    kp[k] = q;
+  }
+  reinterpret_cast<int4*>(key + n * 8)[0] = kk[0];
+  reinterpret_cast<int4*>(key + n * 8)[1] = kk[1];
+  reinterpret_cast<float4*>(wts + n * 8)[0] = make_float4(c8.w[0], c8.w[1], c8.w[2], c8.w[3]);
+  reinterpret_cast<float4*>(wts + n * 8)[1] = make_float4(c8.w[4], c8.w[5], c8.w[6], c8.w[7]);
+}
+
+// Sum of one voxel's entries for the channels lane, lane+32, ... (CJ of them), in ascending entry order.
+template <int CJ>
+__device__ __forceinline__ void voxel_sum(const int32_t* __restrict__ lst, int cnt, const float* __restrict__ wts,
+                                          ScatterPass pa, ScatterPass pb, int64_t Ea, int lane, float acc[CJ]) {
+#pragma unroll
+  for (int j = 0; j < CJ; ++j) acc[j] = 0.f;
+  int32_t last = -1;
+  for (int step = 0; step < cnt; ++step) {
+    int32_t best = 0x7fffffff;
+    for (int i = lane; i < cnt; i += kWarp) {
+      int32_t e = lst[i];
+      if (e > last && e < best) best = e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    last = best;
+    const float w = wts[best];
+    const float* d = best < Ea ? pa.dlat + (int64_t)(best >> 3) * pa.ld
+                               : pb.dlat + (int64_t)((best - Ea) >> 3) * pb.ld;
+#pragma unroll
+    for (int j = 0; j < CJ; ++j) acc[j] = fmaf(w, d[lane + j * kWarp], acc[j]);
+  }
+}
+
+// Channel-first output: a CTA owns 32 consecutive voxels; warp w sums voxels 4w..4w+3 into a (C x 32) tile
+// (row stride 33: conflict-free both ways), then every channel row leaves as one coalesced 128 B store.
+// A tile without any entry (most of the volume) is zero-filled without touching shared memory.
+template <int CJ>
+__global__ void __launch_bounds__(256) scatter_reduce_cf_kernel(const int32_t* __restrict__ offset,
+                                                                const int32_t* __restrict__ count,
+                                                                const int32_t* __restrict__ list,
+                                                                const float* __restrict__ wts, ScatterPass pa,
+                                                                ScatterPass pb, int64_t Ea, float* __restrict__ grad,
+                                                                int64_t V, int64_t T) {
+  constexpr int C = CJ * kWarp;
+  __shared__ float tile[C][33];
+  const int lane = threadIdx.x % kWarp, wid = threadIdx.x / kWarp;
+  const int64_t ntiles = (T + 31) / 32;
+  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int64_t t = tl * 32 + lane;
+    const bool valid = t < T;
+    const int cnt_l = valid ? count[t] : 0;
+    const int64_t scene = valid ? t / V : 0, v = valid ? t - scene * V : 0;
+    float* gcol = grad + (scene * C) * V + v;                   // + c * V per channel
+    const unsigned any = __ballot_sync(0xffffffffu, cnt_l > 0);
+    if (any == 0u) {                                            // uniform over the CTA (same counts in every warp)
+      if (valid)
+        for (int c = wid; c < C; c += 8) gcol[(int64_t)c * V] = 0.f;
+      continue;
+    }
+    const int off_l = valid ? offset[t] : 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int vi = wid * 4 + q;
+      const int cnt = __shfl_sync(0xffffffffu, cnt_l, vi);
+      const int off = __shfl_sync(0xffffffffu, off_l, vi);
+      float acc[CJ];
+      voxel_sum<CJ>(list + off, cnt, wts, pa, pb, Ea, lane, acc);
+#pragma unroll
+      for (int j = 0; j < CJ; ++j) tile[lane + j * kWarp][vi] = acc[j];
+    }
+    __syncthreads();
+    if (valid)
+      for (int c = wid; c < C; c += 8) gcol[(int64_t)c * V] = tile[c][lane];
+    __syncthreads();
+  }
+}
+
+// Channels-last output (the producer works in torch.channels_last_3d): one warp per voxel row.
+template <int CJ>
+__global__ void __launch_bounds__(256) scatter_reduce_cl_kernel(const int32_t* __restrict__ offset,
+                                                                const int32_t* __restrict__ count,
+                                                                const int32_t* __restrict__ list,
+                                                                const float* __restrict__ wts, ScatterPass pa,
+                                                                ScatterPass pb, int64_t Ea, float* __restrict__ grad,
+                                                                int64_t T) {
+  constexpr int C = CJ * kWarp;
+  const int lane = threadIdx.x % kWarp;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) / kWarp;
+  for (int64_t t = warp; t < T; t += nwarps) {
+    const int cnt = count[t];
+    float acc[CJ];
+    if (cnt > 0) {
+      voxel_sum<CJ>(list + offset[t], cnt, wts, pa, pb, Ea, lane, acc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CJ; ++j) acc[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < CJ; ++j) grad[t * C + lane + j * kWarp] = acc[j];
+  }
+}
+
+}  // namespace nrf
+
+extern "C" int nrf_scatter_volume_grad_merged(const float* rays, int R, int rays_per_scene, const float* z_a, int K_a,
+                                              const float* dlat_a, int ld_a, const float* z_b, int K_b,
+                                              const float* dlat_b, int ld_b, float* grad, int channels_first, int SB,
+                                              int C, int S0, int S1, int S2, const float* bounds_host,
+                                              void* workspace, void* stream) {
+  NRF_REQUIRE(rays && z_a && dlat_a && grad && bounds_host && workspace, NRF_EINVAL,
+              "nrf_scatter_volume_grad_merged: null pointer");
+  NRF_REQUIRE(R > 0 && K_a > 0 && R == SB * rays_per_scene, NRF_EINVAL,
+              "nrf_scatter_volume_grad_merged: R != SB*rays_per_scene");
+  const bool two = z_b != nullptr;
+  NRF_REQUIRE(!two || (dlat_b && K_b > 0 && ld_b >= C), NRF_EINVAL, "nrf_scatter_volume_grad_merged: pass b");
+  NRF_REQUIRE((C == 64 || C == 128) && ld_a >= C, NRF_ENOSUP,
+              "nrf_scatter_volume_grad_merged: C=%d (64 or 128 channels; use nrf_scatter_volume_grad_sorted)", C);
+  int64_t V = (int64_t)S0 * S1 * S2, T = (int64_t)SB * V;
+  int64_t Na = (int64_t)R * K_a, Nb = two ? (int64_t)R * K_b : 0, N = Na + Nb, E = N * 8;
+  NRF_REQUIRE(T < ((int64_t)1 << 31) && E < ((int64_t)1 << 31), NRF_ENOSUP,
+              "nrf_scatter_volume_grad_merged: more than 2^31 voxels or entries");
+  NRF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, NRF_EINVAL,
+              "nrf_scatter_volume_grad_merged: workspace must be 16 B aligned");
+  cudaStream_t s = as_stream(stream);
+  int64_t nb = (T + 1023) / 1024;
+  // count[T] cursor[T] offset[T] block_sums[nb+1] | 16 B aligned: key[E] wts[E] list[E]
+  int32_t* count = reinterpret_cast<int32_t*>(workspace);
+  int32_t* cursor = count + T;
+  int32_t* offset = cursor + T;
+  int32_t* block_sums = offset + T;
+  int64_t head = (3 * T + nb + 1 + 3) & ~(int64_t)3;
+  int32_t* key = count + head;
+  float* wts = reinterpret_cast<float*>(key + E);
+  int32_t* list = reinterpret_cast<int32_t*>(wts + E);
+  NRF_CUDA_OK(cudaMemsetAsync(count, 0, (size_t)(2 * T) * 4, s));       // count and cursor
+  ScatterArgs g0;
+  g0.S0 = S0; g0.S1 = S1; g0.S2 = S2; g0.C = C; g0.SB = SB;
+  fill_bounds(bounds_host, g0.bmin, g0.bext);
+  ScatterPass pa{z_a, dlat_a, K_a, ld_a};
+  ScatterPass pb{two ? z_b : z_a, two ? dlat_b : dlat_a, two ? K_b : K_a, two ? ld_b : ld_a};
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scatter_count2_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(rays, R, rays_per_scene, pa, pb, Na, Nb, g0, V,
+                                                                      key, wts, count); }
+  NRF_LAUNCH_OK();
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scan_block_kernel<<<(unsigned)nb, 256, 0, s>>>(count, offset, block_sums, T); }
+  NRF_LAUNCH_OK();
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scan_sums_kernel<<<1, 1024, 0, s>>>(block_sums, (int)nb, nullptr); }
+  NRF_LAUNCH_OK();
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scan_add_kernel<<<(unsigned)nb, 256, 0, s>>>(offset, block_sums, T); }
+  NRF_LAUNCH_OK();
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    scatter_fill_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(key, E, offset, cursor, list); }
+  NRF_LAUNCH_OK();
+  const int64_t Ea = Na * 8;
+  { LaunchScope ls_(NRF_CAT_SCATTER, s);
+    if (channels_first) {
+      int64_t ntiles = (T + 31) / 32;
+      int max_blocks = sm_count() * 8;
+      int blocks = (int)(ntiles < max_blocks ? ntiles : max_blocks);
+      if (C == 128) scatter_reduce_cf_kernel<4><<<blocks, 256, 0, s>>>(offset, count, list, wts, pa, pb, Ea, grad, V, T);
+      else scatter_reduce_cf_kernel<2><<<blocks, 256, 0, s>>>(offset, count, list, wts, pa, pb, Ea, grad, V, T);
+    } else {
+      int64_t want = (T + 7) / 8;
+      int max_blocks = sm_count() * 32;
+      int blocks = (int)(want < max_blocks ? want : max_blocks);
+      if (C == 128) scatter_reduce_cl_kernel<4><<<blocks, 256, 0, s>>>(offset, count, list, wts, pa, pb, Ea, grad, T);
+      else scatter_reduce_cl_kernel<2><<<blocks, 256, 0, s>>>(offset, count, list, wts, pa, pb, Ea, grad, T);
+    }
+  }
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
 
 extern "C" int64_t nrf_scatter_sorted_workspace_bytes(int64_t N, int SB, int64_t V) {
   int64_t T = (int64_t)SB * V, E = N * 8;

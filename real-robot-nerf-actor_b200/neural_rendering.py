@@ -316,17 +316,37 @@ def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps, keep_acts=True):
     return st, outs
 
 
-def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, want_dz=False, first=True):
+def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, want_dz=False, first=True,
+                   defer=None):
     res = ops.composite_bwd(st.field_out, st.z, st.rays, ren._d_embed, d_rgb, d_embed, d_depth, d_weights,
                             ldg=st.mlp.sizes.dout_pad, precision=st.mlp.precision,
                             white_bkgd=ren.white_bkgd, want_dz=want_dz)
     d_field, d_z = res if want_dz else (res, None)
     dlat = st.mlp.backward(st.field_in, st.acts, d_field, grads, deterministic=ren.deterministic)
-    if ren.scatter == "sorted":       # atomics-free, bit-reproducible; the first pass writes every voxel row
+    if defer is not None:             # one merged scatter for all passes once the last one is through
+        defer.append((st.z, dlat))
+    elif ren.scatter == "sorted":     # atomics-free, bit-reproducible; the first pass writes every voxel row
         ops.scatter_volume_grad_sorted(st.rays, st.z, st.rps, dlat, grad_cl, ren._bounds, accumulate=not first)
     else:                             # fp32 vector reductions into a zeroed volume
         ops.scatter_volume_grad(st.rays, st.z, st.rps, dlat, grad_cl, ren._bounds)
     return d_z
+
+
+def _merged_scatter_ok(ren, vol_shape_cl):
+    """The merged scatter (all passes in one counting sort, gradient written once in the caller's layout) is
+    built for 64 / 128 latent channels; other widths take the per-pass kernels + re-layout."""
+    return ren.scatter == "sorted" and vol_shape_cl[-1] in (64, 128)
+
+
+def _finish_volume_grad(ren, rays, rps, defer, vol_shape_cl, cl3d):
+    """dL/dvoxel_feat in the caller's memory format from the deferred (z, dlatent) of every pass."""
+    SB, S0, S1, S2, C = vol_shape_cl
+    if cl3d:                                               # channels_last_3d in -> channels_last_3d gradient out
+        g = torch.empty(vol_shape_cl, device=rays.device, dtype=torch.float32)
+        ops.scatter_volume_grad_merged(rays, rps, defer, g, False, ren._bounds)
+        return g.permute(0, 4, 1, 2, 3)
+    g = torch.empty((SB, C, S0, S1, S2), device=rays.device, dtype=torch.float32)
+    return ops.scatter_volume_grad_merged(rays, rps, defer, g, True, ren._bounds)
 
 
 def _is_channels_last_3d(t):
@@ -425,8 +445,13 @@ class _ForwardNerfFn(torch.autograd.Function):
         names_c = st_c.mlp.names()
         grads_c = _zero_grads(st_c.mlp)
         grads_f = grads_c if shared or st_f is None else _zero_grads(st_f.mlp)
-        alloc = torch.empty if ren.scatter == "sorted" else torch.zeros
-        grad_cl = alloc(ctx.vol_shape, device=dev, dtype=torch.float32)
+        want_vol = ctx.needs_input_grad[1]
+        merged = _merged_scatter_ok(ren, ctx.vol_shape)
+        defer = [] if merged else None
+        grad_cl = None
+        if not merged:
+            alloc = torch.empty if ren.scatter == "sorted" else torch.zeros
+            grad_cl = alloc(ctx.vol_shape, device=dev, dtype=torch.float32)
         _, d_cw, d_crgb, d_cemb, d_cdep = g[:5]
         d_cdep = _zeros_like_or(d_cdep, (R,), dev)
         if st_f is not None:
@@ -434,7 +459,7 @@ class _ForwardNerfFn(torch.autograd.Function):
             Kfd = ren.n_fine_depth
             d_z = _pass_backward(ren, st_f, _zeros_like_or(d_frgb, (R, 3), dev),
                                  _zeros_like_or(d_femb, (R, D), dev), d_fdep, d_fw, grads_f, grad_cl,
-                                 want_dz=Kfd > 0)
+                                 want_dz=Kfd > 0, defer=defer)
             if Kfd > 0:
                 # route dL/dz of the depth-guided samples back through sort and clamp to coarse depth
                 K = st_f.z.shape[1]
@@ -442,10 +467,13 @@ class _ForwardNerfFn(torch.autograd.Function):
                 d_cat.scatter_(1, st_f.perm.long(), d_z)
                 d_cdep = d_cdep + (d_cat[:, K - Kfd:] * ctx.depth_mask).sum(-1)
         _pass_backward(ren, st_c, _zeros_like_or(d_crgb, (R, 3), dev), _zeros_like_or(d_cemb, (R, D), dev),
-                       d_cdep, d_cw, grads_c, grad_cl, first=st_f is None)
+                       d_cdep, d_cw, grads_c, grad_cl, first=st_f is None, defer=defer)
         d_vol = None
-        if ctx.needs_input_grad[1]:                        # channels_last_3d in -> channels_last_3d gradient out
-            d_vol = grad_cl.permute(0, 4, 1, 2, 3) if ctx.cl3d else ops.volume_to_channels_first(grad_cl)
+        if want_vol:
+            if merged:
+                d_vol = _finish_volume_grad(ren, st_c.rays, st_c.rps, defer, ctx.vol_shape, ctx.cl3d)
+            else:
+                d_vol = grad_cl.permute(0, 4, 1, 2, 3) if ctx.cl3d else ops.volume_to_channels_first(grad_cl)
         pg = [grads_c[n] for n in names_c]
         if not shared and st_f is not None:
             pg += [grads_f[n] for n in st_f.mlp.names()]
@@ -725,11 +753,18 @@ class _CompositeFn(torch.autograd.Function):
         R, D = st.rays.shape[0], ren._d_embed
         names = st.mlp.names()
         grads = _zero_grads(st.mlp)
-        alloc = torch.empty if ren.scatter == "sorted" else torch.zeros
-        grad_cl = alloc(ctx.vol_shape, device=dev, dtype=torch.float32)
+        merged = _merged_scatter_ok(ren, ctx.vol_shape)
+        defer = [] if merged else None
+        grad_cl = None
+        if not merged:
+            alloc = torch.empty if ren.scatter == "sorted" else torch.zeros
+            grad_cl = alloc(ctx.vol_shape, device=dev, dtype=torch.float32)
         d_z = _pass_backward(ren, st, _zeros_like_or(d_rgb, (R, 3), dev), _zeros_like_or(d_emb, (R, D), dev),
-                             d_dep, d_w, grads, grad_cl, want_dz=ctx.needs_input_grad[4])
+                             d_dep, d_w, grads, grad_cl, want_dz=ctx.needs_input_grad[4], defer=defer)
         d_vol = None
         if ctx.needs_input_grad[2]:
-            d_vol = grad_cl.permute(0, 4, 1, 2, 3) if ctx.cl3d else ops.volume_to_channels_first(grad_cl)
+            if merged:
+                d_vol = _finish_volume_grad(ren, st.rays, st.rps, defer, ctx.vol_shape, ctx.cl3d)
+            else:
+                d_vol = grad_cl.permute(0, 4, 1, 2, 3) if ctx.cl3d else ops.volume_to_channels_first(grad_cl)
         return (None, None, d_vol, None, d_z, None, *[grads[n] for n in names])

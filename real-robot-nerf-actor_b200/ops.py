@@ -174,6 +174,34 @@ def scatter_volume_grad_sorted(rays, z, rays_per_scene, dlatent, grad_cl, bounds
     return grad_cl
 
 
+def scatter_volume_grad_merged(rays, rays_per_scene, passes, grad, channels_first, bounds):
+    """ONE atomics-free scatter for all render passes of a step (see nrf_scatter_volume_grad_merged).
+
+    passes: [(z (R,K), dlatent (R*K, >=C) fp32), ...] (one or two); grad: (SB,C,S0,S1,S2) if channels_first
+    else (SB,S0,S1,S2,C), fully overwritten (no memset needed)."""
+    rays = _f32(rays, "rays")
+    assert 1 <= len(passes) <= 2
+    assert grad.is_cuda and grad.dtype == torch.float32 and grad.is_contiguous()
+    if channels_first:
+        SB, Cc, S0, S1, S2 = grad.shape
+    else:
+        SB, S0, S1, S2, Cc = grad.shape
+    R = rays.shape[0]
+    za, da = _f32(passes[0][0], "z"), _f32(passes[0][1], "dlatent")
+    zb, db = (_f32(passes[1][0], "z"), _f32(passes[1][1], "dlatent")) if len(passes) == 2 else (None, None)
+    n_tot = R * (za.shape[1] + (zb.shape[1] if zb is not None else 0))
+    lib = _lib.load()
+    ws = torch.empty(lib.nrf_scatter_sorted_workspace_bytes(n_tot, SB, S0 * S1 * S2), device=rays.device,
+                     dtype=torch.uint8)
+    bh = _bounds_host(bounds)
+    check(lib.nrf_scatter_volume_grad_merged(ptr(rays), R, rays_per_scene, ptr(za), za.shape[1], ptr(da),
+                                             da.shape[1], ptr(zb), zb.shape[1] if zb is not None else 0, ptr(db),
+                                             db.shape[1] if db is not None else 0, ptr(grad), int(channels_first),
+                                             SB, Cc, S0, S1, S2, C.cast(bh, C.c_void_p), ptr(ws), stream_ptr()),
+          "nrf_scatter_volume_grad_merged")
+    return grad
+
+
 # ------------------------------------------------------------------------------- compositing
 def composite_fwd(field_out, z, rays, D, white_bkgd=False):
     """neural_rendering.py:339-359 on RAW MLP outputs (N, 4+D).  -> weights, rgb, embed, depth."""

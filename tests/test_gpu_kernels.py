@@ -151,9 +151,10 @@ def test_encode_points_fp32_matches_oracle(ops, C, S):
     assert torch.equal(out16.cpu(), out.to(torch.bfloat16))
 
 
-def test_encode_points_outside_box_and_edges(ops):
+@pytest.mark.parametrize("C", [8, 64, 128])       # 8: one warp per sample; 64 / 128: 32 samples per warp iteration
+def test_encode_points_outside_box_and_edges(ops, C):
     """Zero padding outside the grid, exact hits on the faces, far-away points."""
-    C, S = 8, 5
+    S = 5
     g = torch.Generator().manual_seed(1)
     vol = torch.randn(1, C, S, S, S, generator=g)
     b = torch.tensor(syn.BOUNDS)
@@ -359,6 +360,40 @@ def test_scatter_sorted_is_atomics_free_and_reproducible(ops):
     ga = torch.zeros(SB, S, S, S, C, device="cuda")
     ops.scatter_volume_grad(rays.cuda(), z.cuda(), R_per, dlc, ga, syn.BOUNDS)
     assert rel(ga, outs[0]) < 1e-6
+
+
+@pytest.mark.parametrize("C,channels_first", [(128, True), (64, True), (128, False)])
+def test_scatter_merged_two_passes_one_sort(ops, C, channels_first):
+    """nrf_scatter_volume_grad_merged: coarse + fine pass in one counting sort, gradient written once in the caller's
+    layout; equals the autograd of both gathers, every element rewritten, bit-identical run to run."""
+    SB, S, R_per, Ka, Kb = 2, 11, 150, 16, 40
+    vol, rays, za = _scene_inputs(SB, C, S, R_per, Ka, seed=21)
+    zb = O.sample_coarse(rays, Kb, torch.rand(SB * R_per, Kb, generator=torch.Generator().manual_seed(3)))
+    vol.requires_grad_(True)
+    dls = []
+    for i, z in enumerate((za, zb)):
+        pts = (rays[:, None, :3] + z.unsqueeze(2) * rays[:, None, 3:6]).reshape(SB, -1, 3)
+        lat = O.trilinear_gather(vol, O.world_to_canonical(pts, syn.BOUNDS))
+        dl = torch.randn(lat.shape, generator=torch.Generator().manual_seed(30 + i))
+        lat.backward(dl)
+        dls.append(dl.reshape(-1, C).cuda())
+    shape = (SB, C, S, S, S) if channels_first else (SB, S, S, S, C)
+    outs = []
+    for _ in range(2):
+        g = torch.full(shape, 7.0, device="cuda")
+        ops.scatter_volume_grad_merged(rays.cuda(), R_per, [(za.cuda(), dls[0]), (zb.cuda(), dls[1])], g,
+                                       channels_first, syn.BOUNDS)
+        outs.append(g)
+    assert torch.equal(outs[0], outs[1]), "must be bit-reproducible"
+    got = outs[0] if channels_first else outs[0].permute(0, 4, 1, 2, 3)
+    assert rel(got.cpu(), vol.grad) < 1e-6
+    # single pass = the per-pass sorted scatter, bit for bit in channels-last (same entry order)
+    g1 = torch.full(shape, 7.0, device="cuda")
+    ops.scatter_volume_grad_merged(rays.cuda(), R_per, [(za.cuda(), dls[0])], g1, channels_first, syn.BOUNDS)
+    gs = torch.empty(SB, S, S, S, C, device="cuda")
+    ops.scatter_volume_grad_sorted(rays.cuda(), za.cuda(), R_per, dls[0], gs, syn.BOUNDS)
+    g1_cl = g1.permute(0, 2, 3, 4, 1) if channels_first else g1
+    assert torch.equal(g1_cl, gs)
 
 
 # ------------------------------------------------------------------ whole-MLP fused forward kernel
