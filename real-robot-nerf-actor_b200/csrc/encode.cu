@@ -620,70 +620,174 @@ __global__ void __launch_bounds__(256) scatter_count2_kernel(const float* __rest
   reinterpret_cast<float4*>(wts + n * 8)[1] = make_float4(c8.w[4], c8.w[5], c8.w[6], c8.w[7]);
 }
 
+// list + its weights side by side (the reduce reads both with independent loads)
+__global__ void __launch_bounds__(256) scatter_fill2_kernel(const int32_t* __restrict__ key, const float* __restrict__ wts,
+                                                            int64_t E, const int32_t* __restrict__ offset,
+                                                            int32_t* __restrict__ cursor, int32_t* __restrict__ list,
+                                                            float* __restrict__ wlist) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int32_t k = key[e];
+  if (k < 0) return;
+  int32_t pos = offset[k] + atomicAdd(cursor + k, 1);
+  list[pos] = (int32_t)e;
+  wlist[pos] = wts[e];
+}
+
 // Sum of one voxel's entries for the channels lane, lane+32, ... (CJ of them), in ascending entry order.
+// Up to 32 entries (the usual case): one entry per lane, ranked with shuffles, then the dlatent rows are read four
+// at a time -- three dependent memory round trips per VOXEL; the selection loop below pays them per ENTRY.
 template <int CJ>
-__device__ __forceinline__ void voxel_sum(const int32_t* __restrict__ lst, int cnt, const float* __restrict__ wts,
+__device__ __forceinline__ void voxel_sum(const int32_t* __restrict__ lst, const float* __restrict__ wl, int cnt,
                                           ScatterPass pa, ScatterPass pb, int64_t Ea, int lane, float acc[CJ]) {
 #pragma unroll
   for (int j = 0; j < CJ; ++j) acc[j] = 0.f;
+  auto row_of = [&](int32_t e) {
+    return e < Ea ? pa.dlat + (int64_t)(e >> 3) * pa.ld : pb.dlat + (int64_t)((e - Ea) >> 3) * pb.ld;
+  };
+  if (cnt == 1) {
+    const float w = wl[0];
+    const float* r = row_of(lst[0]);
+#pragma unroll
+    for (int j = 0; j < CJ; ++j) acc[j] = fmaf(w, r[lane + j * kWarp], acc[j]);
+    return;
+  }
+  if (cnt <= kWarp) {
+    const int32_t e_l = lane < cnt ? lst[lane] : 0x7fffffff;
+    const float w_l = lane < cnt ? wl[lane] : 0.f;
+    int rank = 0;                                             // entries are distinct: ranks are a permutation
+    for (int j = 0; j < cnt; ++j) rank += (__shfl_sync(0xffffffffu, e_l, j) < e_l) ? 1 : 0;
+    int k = 0;
+    for (; k + 4 <= cnt; k += 4) {
+      int32_t e[4]; float w[4]; float d[4][CJ];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int src = __ffs(__ballot_sync(0xffffffffu, rank == k + q)) - 1;
+        e[q] = __shfl_sync(0xffffffffu, e_l, src);
+        w[q] = __shfl_sync(0xffffffffu, w_l, src);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float* r = row_of(e[q]);
+#pragma unroll
+        for (int j = 0; j < CJ; ++j) d[q][j] = r[lane + j * kWarp];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < CJ; ++j) acc[j] = fmaf(w[q], d[q][j], acc[j]);
+    }
+    for (; k < cnt; ++k) {
+      const int src = __ffs(__ballot_sync(0xffffffffu, rank == k)) - 1;
+      const int32_t e = __shfl_sync(0xffffffffu, e_l, src);
+      const float w = __shfl_sync(0xffffffffu, w_l, src);
+      const float* r = row_of(e);
+#pragma unroll
+      for (int j = 0; j < CJ; ++j) acc[j] = fmaf(w, r[lane + j * kWarp], acc[j]);
+    }
+    return;
+  }
   int32_t last = -1;
   for (int step = 0; step < cnt; ++step) {
-    int32_t best = 0x7fffffff;
+    int32_t best = 0x7fffffff; float wb = 0.f;
     for (int i = lane; i < cnt; i += kWarp) {
       int32_t e = lst[i];
-      if (e > last && e < best) best = e;
+      if (e > last && e < best) { best = e; wb = wl[i]; }
     }
+    int32_t mine = best;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    const int src = __ffs(__ballot_sync(0xffffffffu, mine == best)) - 1;
+    const float w = __shfl_sync(0xffffffffu, wb, src);
     last = best;
-    const float w = wts[best];
-    const float* d = best < Ea ? pa.dlat + (int64_t)(best >> 3) * pa.ld
-                               : pb.dlat + (int64_t)((best - Ea) >> 3) * pb.ld;
+    const float* d = row_of(best);
 #pragma unroll
     for (int j = 0; j < CJ; ++j) acc[j] = fmaf(w, d[lane + j * kWarp], acc[j]);
   }
 }
 
-// Channel-first output: a CTA owns 32 consecutive voxels; warp w sums voxels 4w..4w+3 into a (C x 32) tile
-// (row stride 33: conflict-free both ways), then every channel row leaves as one coalesced 128 B store.
-// A tile without any entry (most of the volume) is zero-filled without touching shared memory.
-template <int CJ>
-__global__ void __launch_bounds__(256) scatter_reduce_cf_kernel(const int32_t* __restrict__ offset,
+// Channel-first output: a CTA owns 32 consecutive voxels; its warps share the voxels that have entries (round-robin
+// over the set bits), sum each into a (C x 32) shared tile, then every channel row leaves coalesced.  kVec (V % 32
+// == 0: tiles never straddle scenes, rows are 16 B aligned): row stride 36, LDS.128 + STG.128, a warp writes four
+// channel rows per instruction.  A tile without any entry is zero-filled without touching shared memory.
+// The kernel is latency-bound (count/offset -> list -> dlatent rows -> barrier -> stores, one tile per CTA at a time):
+// small CTAs (4 warps, up to 10 resident per SM) and the next tile's count / offset prefetched during the current one.
+constexpr int kRcfWarps = 4;
+template <int CJ, bool kVec>
+__global__ void __launch_bounds__(kRcfWarps * 32, 10) scatter_reduce_cf_kernel(const int32_t* __restrict__ offset,
                                                                 const int32_t* __restrict__ count,
                                                                 const int32_t* __restrict__ list,
-                                                                const float* __restrict__ wts, ScatterPass pa,
+                                                                const float* __restrict__ wlist, ScatterPass pa,
                                                                 ScatterPass pb, int64_t Ea, float* __restrict__ grad,
                                                                 int64_t V, int64_t T) {
   constexpr int C = CJ * kWarp;
-  __shared__ float tile[C][33];
+  constexpr int LD = kVec ? 36 : 33;
+  constexpr int NW = kRcfWarps;
+  __shared__ __align__(16) float tile[C][LD];
   const int lane = threadIdx.x % kWarp, wid = threadIdx.x / kWarp;
+  const int r4 = lane >> 3, l8 = lane & 7;
   const int64_t ntiles = (T + 31) / 32;
+  int cnt_n = 0, off_n = 0;
+  if ((int64_t)blockIdx.x < ntiles) {
+    const int64_t t = (int64_t)blockIdx.x * 32 + lane;
+    if (t < T) { cnt_n = count[t]; off_n = offset[t]; }
+  }
   for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
     const int64_t t = tl * 32 + lane;
     const bool valid = t < T;
-    const int cnt_l = valid ? count[t] : 0;
-    const int64_t scene = valid ? t / V : 0, v = valid ? t - scene * V : 0;
-    float* gcol = grad + (scene * C) * V + v;                   // + c * V per channel
-    const unsigned any = __ballot_sync(0xffffffffu, cnt_l > 0);
-    if (any == 0u) {                                            // uniform over the CTA (same counts in every warp)
-      if (valid)
-        for (int c = wid; c < C; c += 8) gcol[(int64_t)c * V] = 0.f;
+    const int cnt_l = cnt_n, off_l = off_n;
+    {
+      const int64_t tn = (tl + gridDim.x) * 32 + lane;
+      cnt_n = 0; off_n = 0;
+      if (tn < T) { cnt_n = count[tn]; off_n = offset[tn]; }
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, cnt_l > 0);   // uniform over the CTA (same counts in every warp)
+    float* gcol;                                                  // scalar path: this lane's voxel, + c * V per channel
+    float* gvec;                                                  // vector path: this lane's voxel quad
+    {
+      const int64_t scene = valid ? t / V : 0, v = valid ? t - scene * V : 0;
+      gcol = grad + (scene * C) * V + v;
+      const int64_t t0 = tl * 32, scene0 = t0 / V;
+      gvec = grad + (scene0 * C) * V + (t0 - scene0 * V) + 4 * l8;
+    }
+    if (any == 0u) {
+      if (kVec) {
+#pragma unroll
+        for (int i = 0; i < C / (4 * NW); ++i)
+          *reinterpret_cast<float4*>(gvec + (int64_t)(wid * 4 + r4 + 4 * NW * i) * V) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (valid) {
+        for (int c = wid; c < C; c += NW) gcol[(int64_t)c * V] = 0.f;
+      }
       continue;
     }
-    const int off_l = valid ? offset[t] : 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int vi = wid * 4 + q;
+    unsigned m = any;
+    int idx = 0;
+    while (m) {
+      const int vi = __ffs(m) - 1;
+      m &= m - 1;
+      if ((idx++ % NW) != wid) continue;
       const int cnt = __shfl_sync(0xffffffffu, cnt_l, vi);
       const int off = __shfl_sync(0xffffffffu, off_l, vi);
       float acc[CJ];
-      voxel_sum<CJ>(list + off, cnt, wts, pa, pb, Ea, lane, acc);
+      voxel_sum<CJ>(list + off, wlist + off, cnt, pa, pb, Ea, lane, acc);
 #pragma unroll
       for (int j = 0; j < CJ; ++j) tile[lane + j * kWarp][vi] = acc[j];
     }
     __syncthreads();
-    if (valid)
-      for (int c = wid; c < C; c += 8) gcol[(int64_t)c * V] = tile[c][lane];
+    if (kVec) {
+      const unsigned sel = (any >> (4 * l8)) & 0xFu;
+#pragma unroll
+      for (int i = 0; i < C / (4 * NW); ++i) {
+        const int c = wid * 4 + r4 + 4 * NW * i;
+        float4 x = *reinterpret_cast<const float4*>(&tile[c][4 * l8]);
+        x.x = (sel & 1u) ? x.x : 0.f; x.y = (sel & 2u) ? x.y : 0.f;
+        x.z = (sel & 4u) ? x.z : 0.f; x.w = (sel & 8u) ? x.w : 0.f;
+        *reinterpret_cast<float4*>(gvec + (int64_t)c * V) = x;
+      }
+    } else if (valid) {
+      const bool has = cnt_l > 0;
+      for (int c = wid; c < C; c += NW) gcol[(int64_t)c * V] = has ? tile[c][lane] : 0.f;
+    }
     __syncthreads();
   }
 }
@@ -693,7 +797,7 @@ template <int CJ>
 __global__ void __launch_bounds__(256) scatter_reduce_cl_kernel(const int32_t* __restrict__ offset,
                                                                 const int32_t* __restrict__ count,
                                                                 const int32_t* __restrict__ list,
-                                                                const float* __restrict__ wts, ScatterPass pa,
+                                                                const float* __restrict__ wlist, ScatterPass pa,
                                                                 ScatterPass pb, int64_t Ea, float* __restrict__ grad,
                                                                 int64_t T) {
   constexpr int C = CJ * kWarp;
@@ -704,7 +808,7 @@ __global__ void __launch_bounds__(256) scatter_reduce_cl_kernel(const int32_t* _
     const int cnt = count[t];
     float acc[CJ];
     if (cnt > 0) {
-      voxel_sum<CJ>(list + offset[t], cnt, wts, pa, pb, Ea, lane, acc);
+      { const int off = offset[t]; voxel_sum<CJ>(list + off, wlist + off, cnt, pa, pb, Ea, lane, acc); }
     } else {
 #pragma unroll
       for (int j = 0; j < CJ; ++j) acc[j] = 0.f;
@@ -737,7 +841,7 @@ extern "C" int nrf_scatter_volume_grad_merged(const float* rays, int R, int rays
               "nrf_scatter_volume_grad_merged: workspace must be 16 B aligned");
   cudaStream_t s = as_stream(stream);
   int64_t nb = (T + 1023) / 1024;
-  // count[T] cursor[T] offset[T] block_sums[nb+1] | 16 B aligned: key[E] wts[E] list[E]
+  // count[T] cursor[T] offset[T] block_sums[nb+1] | 16 B aligned: key[E] wts[E] list[E] wlist[E]
   int32_t* count = reinterpret_cast<int32_t*>(workspace);
   int32_t* cursor = count + T;
   int32_t* offset = cursor + T;
@@ -746,6 +850,7 @@ extern "C" int nrf_scatter_volume_grad_merged(const float* rays, int R, int rays
   int32_t* key = count + head;
   float* wts = reinterpret_cast<float*>(key + E);
   int32_t* list = reinterpret_cast<int32_t*>(wts + E);
+  float* wlist = reinterpret_cast<float*>(list + E);
   NRF_CUDA_OK(cudaMemsetAsync(count, 0, (size_t)(2 * T) * 4, s));       // count and cursor
   ScatterArgs g0;
   g0.S0 = S0; g0.S1 = S1; g0.S2 = S2; g0.C = C; g0.SB = SB;
@@ -766,22 +871,25 @@ extern "C" int nrf_scatter_volume_grad_merged(const float* rays, int R, int rays
     scan_add_kernel<<<(unsigned)nb, 256, 0, s>>>(offset, block_sums, T); }
   NRF_LAUNCH_OK();
   { LaunchScope ls_(NRF_CAT_SCATTER, s);
-    scatter_fill_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(key, E, offset, cursor, list); }
+    scatter_fill2_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(key, wts, E, offset, cursor, list, wlist); }
   NRF_LAUNCH_OK();
   const int64_t Ea = Na * 8;
   { LaunchScope ls_(NRF_CAT_SCATTER, s);
     if (channels_first) {
       int64_t ntiles = (T + 31) / 32;
-      int max_blocks = sm_count() * 8;
+      int max_blocks = sm_count() * 10;
       int blocks = (int)(ntiles < max_blocks ? ntiles : max_blocks);
-      if (C == 128) scatter_reduce_cf_kernel<4><<<blocks, 256, 0, s>>>(offset, count, list, wts, pa, pb, Ea, grad, V, T);
-      else scatter_reduce_cf_kernel<2><<<blocks, 256, 0, s>>>(offset, count, list, wts, pa, pb, Ea, grad, V, T);
+      const bool vec = V % 32 == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0;
+#define NRF_RCF(CJ, VEC) scatter_reduce_cf_kernel<CJ, VEC><<<blocks, kRcfWarps * 32, 0, s>>>(offset, count, list, wlist, pa, pb, Ea, grad, V, T)
+      if (C == 128) { if (vec) NRF_RCF(4, true); else NRF_RCF(4, false); }
+      else { if (vec) NRF_RCF(2, true); else NRF_RCF(2, false); }
+#undef NRF_RCF
     } else {
       int64_t want = (T + 7) / 8;
       int max_blocks = sm_count() * 32;
       int blocks = (int)(want < max_blocks ? want : max_blocks);
-      if (C == 128) scatter_reduce_cl_kernel<4><<<blocks, 256, 0, s>>>(offset, count, list, wts, pa, pb, Ea, grad, T);
-      else scatter_reduce_cl_kernel<2><<<blocks, 256, 0, s>>>(offset, count, list, wts, pa, pb, Ea, grad, T);
+      if (C == 128) scatter_reduce_cl_kernel<4><<<blocks, 256, 0, s>>>(offset, count, list, wlist, pa, pb, Ea, grad, T);
+      else scatter_reduce_cl_kernel<2><<<blocks, 256, 0, s>>>(offset, count, list, wlist, pa, pb, Ea, grad, T);
     }
   }
   NRF_LAUNCH_OK();
@@ -791,8 +899,8 @@ extern "C" int nrf_scatter_volume_grad_merged(const float* rays, int R, int rays
 extern "C" int64_t nrf_scatter_sorted_workspace_bytes(int64_t N, int SB, int64_t V) {
   int64_t T = (int64_t)SB * V, E = N * 8;
   int64_t nb = (T + 1023) / 1024;
-  // count[T] cursor[T] offset[T] block_sums[nb+1] key[E] list[E] wts[E]
-  return (3 * T + nb + 1 + 2 * E) * 4 + E * 4 + 1024;
+  // count[T] cursor[T] offset[T] block_sums[nb+1] key[E] list[E] wts[E] (+ wlist[E] for the merged variant)
+  return (3 * T + nb + 1 + 2 * E) * 4 + 2 * E * 4 + 1024;
 }
 
 extern "C" int nrf_scatter_volume_grad_sorted(const float* rays, const float* z, int R, int K, int rays_per_scene,

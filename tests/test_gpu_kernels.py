@@ -362,11 +362,12 @@ def test_scatter_sorted_is_atomics_free_and_reproducible(ops):
     assert rel(ga, outs[0]) < 1e-6
 
 
-@pytest.mark.parametrize("C,channels_first", [(128, True), (64, True), (128, False)])
-def test_scatter_merged_two_passes_one_sort(ops, C, channels_first):
+@pytest.mark.parametrize("C,channels_first,S", [(128, True, 11), (128, True, 12), (64, True, 12), (64, True, 9),
+                                                 (128, False, 11)])      # S = 12: V % 32 == 0, vector write-out
+def test_scatter_merged_two_passes_one_sort(ops, C, channels_first, S):
     """nrf_scatter_volume_grad_merged: coarse + fine pass in one counting sort, gradient written once in the caller's
     layout; equals the autograd of both gathers, every element rewritten, bit-identical run to run."""
-    SB, S, R_per, Ka, Kb = 2, 11, 150, 16, 40
+    SB, R_per, Ka, Kb = 2, 150, 16, 40
     vol, rays, za = _scene_inputs(SB, C, S, R_per, Ka, seed=21)
     zb = O.sample_coarse(rays, Kb, torch.rand(SB * R_per, Kb, generator=torch.Generator().manual_seed(3)))
     vol.requires_grad_(True)
