@@ -114,10 +114,12 @@ int nrf_scatter_volume_grad_merged(const float* rays, int R, int rays_per_scene,
 
 /* ---- alpha compositing (neural_rendering.py:239-243,316-359) ---------------------------------
  * field_out (N, ldo) raw; heads sigmoid(rgb), relu(sigma) (models_embed.py:444-466) applied here.
- * weights (R,K), rgb (R,3), embed (R,D), depth (R). */
+ * weights (R,K), rgb (R,3), embed (R,D), depth (R).
+ * sigma_noise (R,K) or NULL: the training-time density noise of neural_rendering.py:336-337, already scaled
+ * by noise_std: alpha = 1 - exp(-delta * relu(relu(raw) + sigma_noise)). */
 int nrf_composite_fwd(const float* field_out, int ldo, const float* z, const float* rays, int R, int K,
                       int D, int white_bkgd, float* weights, float* rgb, float* embed, float* depth,
-                      void* stream);
+                      const float* sigma_noise, void* stream);
 
 /* Backward of the above (closed form).  d_weights and d_z may be NULL.
  * d_field (N, ldg): gradient w.r.t. the RAW MLP outputs, bf16 if out_bf16 else fp32; columns
@@ -125,7 +127,7 @@ int nrf_composite_fwd(const float* field_out, int ldo, const float* z, const flo
 int nrf_composite_bwd(const float* field_out, int ldo, const float* z, const float* rays, int R, int K,
                       int D, int white_bkgd, const float* d_rgb, const float* d_embed,
                       const float* d_depth, const float* d_weights, void* d_field, int ldg,
-                      int out_bf16, float* d_z, void* stream);
+                      int out_bf16, float* d_z, const float* sigma_noise, void* stream);
 
 /* ---- GEMM building block of the field MLP ----------------------------------------------------
  * v = resid + mask( [A0 | A1 | A2] . B^T + bias ),   B (N,K) row-major (nn.Linear layout)

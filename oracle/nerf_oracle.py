@@ -231,18 +231,21 @@ def field(p: Params, voxel_feat, xyz, viewdirs, bounds, code=(6, 1.5, True),
 
 
 # ------------------------------------------------------------------- compositing
-def composite_weights(sigmas, z_samp, far):
-    """neural_rendering.py:239-243,339-346. sigmas, z (R,K); far (R,1) -> weights (R,K)."""
+def composite_weights(sigmas, z_samp, far, sigma_noise=None):
+    """neural_rendering.py:239-243,336-346. sigmas, z (R,K); far (R,1) -> weights (R,K).
+    sigma_noise: the training-time `randn_like(sigmas) * noise_std` of :336-337 (already scaled), or None."""
     deltas = torch.cat([z_samp[:, 1:] - z_samp[:, :-1], far - z_samp[:, -1:]], -1)
+    if sigma_noise is not None:
+        sigmas = sigmas + sigma_noise
     alphas = 1 - torch.exp(-deltas * torch.relu(sigmas))
     shifted = torch.cat([torch.ones_like(alphas[:, :1]), 1 - alphas + 1e-10], -1)
     T = torch.cumprod(shifted, -1)
     return alphas * T[:, :-1]
 
 
-def composite_from_field(out, z_samp, far, white_bkgd=False):
+def composite_from_field(out, z_samp, far, white_bkgd=False, sigma_noise=None):
     """neural_rendering.py:316-359,383-389. out (R,K,4+D) -> weights, rgb, embed, depth."""
-    w = composite_weights(out[..., 3], z_samp, far)
+    w = composite_weights(out[..., 3], z_samp, far, sigma_noise)
     rgb = torch.sum(w.unsqueeze(-1) * out[..., :3], -2)
     embed = torch.sum(w.unsqueeze(-1) * out[..., 4:], -2)
     depth = torch.sum(w * z_samp, -1)
@@ -251,7 +254,8 @@ def composite_from_field(out, z_samp, far, white_bkgd=False):
     return w, rgb, embed, depth
 
 
-def composite(p, voxel_feat, rays, z_samp, sb, bounds, eval_batch_size=4096, **fkw):
+def composite(p, voxel_feat, rays, z_samp, sb, bounds, eval_batch_size=4096, white_bkgd=False, sigma_noise=None,
+              **fkw):
     """neural_rendering.py:224-395. rays (R,8), z (R,K), sb scenes -> weights, rgb, embed, depth.
 
     Points o + z*d (:246), viewdirs = d broadcast (:276); the field is evaluated in chunks of
@@ -265,22 +269,25 @@ def composite(p, voxel_feat, rays, z_samp, sb, bounds, eval_batch_size=4096, **f
     vals = [field(p, voxel_feat, a, b, bounds, **fkw)
             for a, b in zip(torch.split(pts, chunk, dim=1), torch.split(dirs, chunk, dim=1))]
     out = torch.cat(vals, dim=1).reshape(R, K, -1)
-    return composite_from_field(out, z_samp, rays[:, -1:])
+    return composite_from_field(out, z_samp, rays[:, -1:], white_bkgd, sigma_noise)
 
 
 def forward_nerf(p, voxel_feat, rays, bounds, n_coarse, n_fine, n_fine_depth=0, noise=None,
-                 lindisp=False, depth_std=0.001, eval_batch_size=4096, **fkw):
+                 lindisp=False, depth_std=0.001, eval_batch_size=4096, white_bkgd=False, noise_std=0.0, **fkw):
     """neural_rendering.py:435-471. rays (SB,B,8) -> dict(coarse=..., fine=..., z_coarse, z_fine).
 
     noise: dict with optional 'coarse' (R,Kc), 'u' (R,Kf-Kfd), 'fine' (R,Kf-Kfd), 'depth' (R,Kfd);
-    missing entries mean zeros (perturb off).
+    missing entries mean zeros (perturb off).  noise_std > 0 (training mode of :336-337): 'sigma_c' (R,Kc) and
+    'sigma_f' (R,Kc+Kf) are the standard-normal draws added, times noise_std, to the densities of each pass.
     """
     noise = noise or {}
     SB = rays.shape[0]
     r = rays.reshape(-1, 8)
     R = r.shape[0]
     z_c = sample_coarse(r, n_coarse, noise.get("coarse"), lindisp)
-    wc, rgb_c, emb_c, dep_c = composite(p, voxel_feat, r, z_c, SB, bounds, eval_batch_size, **fkw)
+    sn = lambda k: noise[k] * noise_std if noise_std > 0 and k in noise else None
+    wc, rgb_c, emb_c, dep_c = composite(p, voxel_feat, r, z_c, SB, bounds, eval_batch_size, white_bkgd,
+                                        sn("sigma_c"), **fkw)
     fmt = lambda w, a, b, c: dict(rgb=a.reshape(SB, -1, 3), embed=b.reshape(SB, -1, b.shape[-1]),
                                   depth=c.reshape(SB, -1), weights=w.reshape(SB, -1, w.shape[-1]))
     res = dict(coarse=fmt(wc, rgb_c, emb_c, dep_c), z_coarse=z_c)
@@ -295,8 +302,8 @@ def forward_nerf(p, voxel_feat, rays, bounds, n_coarse, n_fine, n_fine_depth=0, 
             nz = noise.get("depth", torch.zeros(R, n_fine_depth, device=r.device))
             samps.append(sample_fine_depth(r, dep_c, n_fine_depth, nz, depth_std))
         z_all, _ = torch.sort(torch.cat(samps, dim=-1), dim=-1)
-        wf, rgb_f, emb_f, dep_f = composite(p, voxel_feat, r, z_all, SB, bounds, eval_batch_size,
-                                            **fkw)
+        wf, rgb_f, emb_f, dep_f = composite(p, voxel_feat, r, z_all, SB, bounds, eval_batch_size, white_bkgd,
+                                            sn("sigma_f"), **fkw)
         res["fine"] = fmt(wf, rgb_f, emb_f, dep_f)
         res["z_fine"] = z_all
     return res

@@ -64,8 +64,8 @@ _SIGNATURES = {
     "nrf_volume_to_channels_first": [_p, _p, _i, _i, _i64, _p],
     "nrf_encode_points": [_p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _f, _p, _i, _i, _p, _p],
     "nrf_scatter_volume_grad": [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p],
-    "nrf_composite_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
-    "nrf_composite_bwd": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p],
+    "nrf_composite_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "nrf_composite_bwd": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p],
     "nrf_gemm": [C.POINTER(NrfGemm), _i, _p],
     "nrf_wgrad": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p],
     "nrf_mlp_sizes": [C.POINTER(NrfMlpParams), _i, C.POINTER(NrfMlpSizes)],

@@ -34,14 +34,16 @@ template <bool kBackward>
 __device__ __forceinline__ void ray_weights(const float* __restrict__ field, int ldo,
                                             const float* __restrict__ zrow, float far, int K, int lane,
                                             float* __restrict__ s_w, float* __restrict__ s_alpha,
-                                            float* __restrict__ s_T, float* __restrict__ s_delta) {
+                                            float* __restrict__ s_T, float* __restrict__ s_delta,
+                                            const float* __restrict__ nz) {
   int chunk = (K + kWarp - 1) / kWarp;
   int k0 = lane * chunk, k1 = min(K, k0 + chunk);
   float local = 1.0f;
   for (int k = k0; k < k1; ++k) {
     float zk = zrow[k];
     float delta = (k + 1 < K ? zrow[k + 1] : far) - zk;
-    float sigma = fmaxf(field[(int64_t)k * ldo + 3], 0.0f);
+    float sigma = fmaxf(field[(int64_t)k * ldo + 3], 0.0f);            // models_embed.py:464
+    if (nz) sigma = fmaxf(sigma + nz[k], 0.0f);                        // neural_rendering.py:336-339 (training noise)
     float alpha = 1.0f - expf(-delta * sigma);
     s_alpha[k] = alpha;
     if (kBackward) s_delta[k] = delta;
@@ -64,17 +66,18 @@ constexpr int kRayWarps = 4;
 __global__ void __launch_bounds__(128) composite_fwd_kernel(
     const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
     int R, int K, int D, int white_bkgd, float* __restrict__ weights, float* __restrict__ rgb,
-    float* __restrict__ embed, float* __restrict__ depth) {
+    float* __restrict__ embed, float* __restrict__ depth, const float* __restrict__ sig_noise) {
   extern __shared__ float smem[];
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
   const int r = blockIdx.x;
+  const float* nz = sig_noise ? sig_noise + (int64_t)r * K : nullptr;
   float* s_w = smem;
   float* s_alpha = s_w + K;
   float* s_part = smem + ((2 * K + 3) & ~3);   // kRayWarps x (4 + D + 4) partial sums, 16 B aligned
   const float* f = field + (int64_t)r * K * ldo;
   const float* zrow = z + (int64_t)r * K;
   float far = rays[(int64_t)r * 8 + 7];
-  if (wid == 0) ray_weights<false>(f, ldo, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr);
+  if (wid == 0) ray_weights<false>(f, ldo, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr, nz);
   __syncthreads();
 
   const int nvec = (4 + D) / 4;             // float4 per row
@@ -156,11 +159,13 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
     const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
     int R, int K, int D, int white_bkgd, const float* __restrict__ d_rgb,
     const float* __restrict__ d_embed, const float* __restrict__ d_depth,
-    const float* __restrict__ d_weights, T* __restrict__ d_field, int ldg, float* __restrict__ d_z) {
+    const float* __restrict__ d_weights, T* __restrict__ d_field, int ldg, float* __restrict__ d_z,
+    const float* __restrict__ sig_noise) {
   // One CTA of 4 warps per ray: scans on warp 0, the per-sample row work split over the 4 warps.
   extern __shared__ float smem[];
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
   const int r = blockIdx.x;
+  const float* nz = sig_noise ? sig_noise + (int64_t)r * K : nullptr;
   float* s_w = smem;
   float* s_alpha = s_w + K;
   float* s_T = s_alpha + K;
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
   const float* f = field + (int64_t)r * K * ldo;
   const float* zrow = z + (int64_t)r * K;
   float far = rays[(int64_t)r * 8 + 7];
-  if (wid == 0) ray_weights<true>(f, ldo, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta);
+  if (wid == 0) ray_weights<true>(f, ldo, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta, nz);
   __syncthreads();
 
   const int nvec = (4 + D) / 4;
@@ -256,7 +261,8 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
           gq.x = w * dout[i].x * sr * (1.0f - sr);
           gq.y = w * dout[i].y * sg * (1.0f - sg);
           gq.z = w * dout[i].z * sb * (1.0f - sb);
-          gq.w = x.w > 0.0f ? s_delta[k] * s_ds[k] : 0.0f;
+          const bool open = x.w > 0.0f && (!nz || x.w + nz[k] > 0.0f);   // both ReLUs pass
+          gq.w = open ? s_delta[k] * s_ds[k] : 0.0f;
         } else {
           gq = make_float4(w * dout[i].x, w * dout[i].y, w * dout[i].z, w * dout[i].w);
         }
@@ -267,10 +273,13 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
   }
   if (d_z) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
-      float sig_k = fmaxf(f[(int64_t)k * ldo + 3], 0.0f);
-      float dl_k = sig_k * s_ds[k];
+      auto sig_at = [&](int q) {
+        float sg = fmaxf(f[(int64_t)q * ldo + 3], 0.0f);
+        return nz ? fmaxf(sg + nz[q], 0.0f) : sg;
+      };
+      float dl_k = sig_at(k) * s_ds[k];
       float dl_km1 = 0.f;
-      if (k > 0) dl_km1 = fmaxf(f[(int64_t)(k - 1) * ldo + 3], 0.0f) * s_ds[k - 1];
+      if (k > 0) dl_km1 = sig_at(k - 1) * s_ds[k - 1];
       d_z[(int64_t)r * K + k] = dd * s_w[k] + dl_km1 - dl_k;
     }
   }
@@ -286,18 +295,19 @@ template <int DV>
 __global__ void __launch_bounds__(128) composite_fwd_fast_kernel(
     const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
     int K, int white_bkgd, float* __restrict__ weights, float* __restrict__ rgb, float* __restrict__ embed,
-    float* __restrict__ depth) {
+    float* __restrict__ depth, const float* __restrict__ sig_noise) {
   constexpr int D = 128 * DV;
   extern __shared__ float smem[];
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
   const int r = blockIdx.x;
+  const float* nz = sig_noise ? sig_noise + (int64_t)r * K : nullptr;
   float* s_w = smem;
   float* s_alpha = s_w + K;
   float* s_part = smem + ((2 * K + 3) & ~3);   // kRayWarps x (D + 8): embed sums, then rgb(3), depth, wsum
   const float* f = field + (int64_t)r * K * ldo;
   const float* zrow = z + (int64_t)r * K;
   const float far = rays[(int64_t)r * 8 + 7];
-  if (wid == 0) ray_weights<false>(f, ldo, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr);
+  if (wid == 0) ray_weights<false>(f, ldo, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr, nz);
   __syncthreads();
   float4 acc[DV];
 #pragma unroll
@@ -355,23 +365,25 @@ __global__ void __launch_bounds__(128) composite_bwd_fast_kernel(
     const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
     int K, int white_bkgd, const float* __restrict__ d_rgb, const float* __restrict__ d_embed,
     const float* __restrict__ d_depth, const float* __restrict__ d_weights, T* __restrict__ d_field, int ldg,
-    float* __restrict__ d_z) {
+    float* __restrict__ d_z, const float* __restrict__ sig_noise) {
   constexpr int D = 128 * DV;
   extern __shared__ float smem[];
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
   const int r = blockIdx.x;
+  const float* nz = sig_noise ? sig_noise + (int64_t)r * K : nullptr;
   float* s_w = smem;
   float* s_alpha = s_w + K;
   float* s_T = s_alpha + K;
   float* s_delta = s_T + K;
   float* s_g = s_delta + K;
   float* s_ds = s_g + K;       // (1 - alpha) * bracket
-  float* s_sig = s_ds + K;     // relu(sigma_k) (0 where the raw output is <= 0)
+  float* s_sig = s_ds + K;     // the density that went into alpha_k: relu(raw) (+ noise, relu again)
   float* s_h = s_sig + K;      // 3 per sample: d_rgb_c * s(1-s), the sigmoid-head factors
+  float* s_open = s_h + 3 * K; // 1 where the gradient reaches the raw density output (every ReLU on the way passes)
   const float* f = field + (int64_t)r * K * ldo;
   const float* zrow = z + (int64_t)r * K;
   const float far = rays[(int64_t)r * 8 + 7];
-  if (wid == 0) ray_weights<true>(f, ldo, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta);
+  if (wid == 0) ray_weights<true>(f, ldo, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta, nz);
   // this lane's slice of dL/d(embed of the ray) and the ray's scalar upstream gradients
   float4 de[DV];
 #pragma unroll
@@ -398,7 +410,9 @@ __global__ void __launch_bounds__(128) composite_bwd_fast_kernel(
       float g = part + sr * dr + sg * dg + sb * db + dd * zrow[k] + bk;
       if (d_weights) g += d_weights[(int64_t)r * K + k];
       s_g[k] = g;
-      s_sig[k] = fmaxf(h.w, 0.0f);
+      const float sden = nz ? fmaxf(fmaxf(h.w, 0.0f) + nz[k], 0.0f) : fmaxf(h.w, 0.0f);
+      s_sig[k] = sden;
+      s_open[k] = (h.w > 0.0f && sden > 0.0f) ? 1.0f : 0.0f;
       s_h[3 * k + 0] = dr * sr * (1.0f - sr);
       s_h[3 * k + 1] = dg * sg * (1.0f - sg);
       s_h[3 * k + 2] = db * sb * (1.0f - sb);
@@ -437,9 +451,8 @@ __global__ void __launch_bounds__(128) composite_bwd_fast_kernel(
     for (int i = 0; i < DV; ++i)
       store_grad4<T>(grow + 4 + (lane + i * kWarp) * 4, make_float4(w * de[i].x, w * de[i].y, w * de[i].z, w * de[i].w));
     if (lane == 0) {
-      const float sig = s_sig[k];
       store_grad4<T>(grow, make_float4(w * s_h[3 * k], w * s_h[3 * k + 1], w * s_h[3 * k + 2],
-                                       sig > 0.0f ? s_delta[k] * s_ds[k] : 0.0f));
+                                       s_open[k] != 0.0f ? s_delta[k] * s_ds[k] : 0.0f));
     } else if (lane <= pad4) {
       store_grad4<T>(grow + 4 + D + (lane - 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
     }
@@ -468,7 +481,7 @@ static int check_composite(const char* who, int R, int K, int D, int ldo) {
 
 extern "C" int nrf_composite_fwd(const float* field_out, int ldo, const float* z, const float* rays,
                                  int R, int K, int D, int white_bkgd, float* weights, float* rgb,
-                                 float* embed, float* depth, void* stream) {
+                                 float* embed, float* depth, const float* sigma_noise, void* stream) {
   NRF_REQUIRE(field_out && z && rays && weights && rgb && embed && depth, NRF_EINVAL,
               "nrf_composite_fwd: null pointer");
   int rc = check_composite("nrf_composite_fwd", R, K, D, ldo);
@@ -478,13 +491,13 @@ extern "C" int nrf_composite_fwd(const float* field_out, int ldo, const float* z
   { LaunchScope ls_(NRF_CAT_COMPOSITE_FWD, as_stream(stream));
   if (D == 384 && aligned && smem <= 48 * 1024)
     composite_fwd_fast_kernel<3><<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
-        field_out, ldo, z, rays, K, white_bkgd, weights, rgb, embed, depth);
+        field_out, ldo, z, rays, K, white_bkgd, weights, rgb, embed, depth, sigma_noise);
   else if (D == 512 && aligned && smem <= 48 * 1024)
     composite_fwd_fast_kernel<4><<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
-        field_out, ldo, z, rays, K, white_bkgd, weights, rgb, embed, depth);
+        field_out, ldo, z, rays, K, white_bkgd, weights, rgb, embed, depth, sigma_noise);
   else
     composite_fwd_kernel<<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
-        field_out, ldo, z, rays, R, K, D, white_bkgd, weights, rgb, embed, depth);
+        field_out, ldo, z, rays, R, K, D, white_bkgd, weights, rgb, embed, depth, sigma_noise);
   }
   NRF_LAUNCH_OK();
   return NRF_OK;
@@ -493,7 +506,8 @@ extern "C" int nrf_composite_fwd(const float* field_out, int ldo, const float* z
 extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z, const float* rays,
                                  int R, int K, int D, int white_bkgd, const float* d_rgb,
                                  const float* d_embed, const float* d_depth, const float* d_weights,
-                                 void* d_field, int ldg, int out_bf16, float* d_z, void* stream) {
+                                 void* d_field, int ldg, int out_bf16, float* d_z, const float* sigma_noise,
+                                 void* stream) {
   NRF_REQUIRE(field_out && z && rays && d_rgb && d_embed && d_field, NRF_EINVAL,
               "nrf_composite_bwd: null pointer");
   int rc = check_composite("nrf_composite_bwd", R, K, D, ldo);
@@ -502,7 +516,7 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
   size_t smem = (size_t)6 * K * sizeof(float);
   dim3 grid(R), block(kRayWarps * kWarp);
   // fast path (D = 384 / 512): every field row read once, nothing predicated
-  const size_t smem_fast = (size_t)10 * K * sizeof(float);
+  const size_t smem_fast = (size_t)11 * K * sizeof(float);
   const bool aligned = (reinterpret_cast<uintptr_t>(field_out) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(d_embed) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_field) & 15) == 0;
   const int pad4 = (ldg - (4 + D)) / 4;
@@ -511,7 +525,7 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
 #define NRF_CBWD_FAST(DV, T)                                                                                   \
     composite_bwd_fast_kernel<DV, T><<<grid, block, smem_fast, as_stream(stream)>>>(                          \
         field_out, ldo, z, rays, K, white_bkgd, d_rgb, d_embed, d_depth, d_weights, reinterpret_cast<T*>(d_field), \
-        ldg, d_z)
+        ldg, d_z, sigma_noise)
     if (D == 384) { if (out_bf16) NRF_CBWD_FAST(3, __nv_bfloat16); else NRF_CBWD_FAST(3, float); }
     else { if (out_bf16) NRF_CBWD_FAST(4, __nv_bfloat16); else NRF_CBWD_FAST(4, float); }
 #undef NRF_CBWD_FAST
@@ -522,7 +536,7 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
     { LaunchScope ls_(NRF_CAT_COMPOSITE_BWD, as_stream(stream));
     composite_bwd_kernel<__nv_bfloat16><<<grid, block, smem, as_stream(stream)>>>(
         field_out, ldo, z, rays, R, K, D, white_bkgd, d_rgb, d_embed, d_depth, d_weights,
-        reinterpret_cast<__nv_bfloat16*>(d_field), ldg, d_z);
+        reinterpret_cast<__nv_bfloat16*>(d_field), ldg, d_z, sigma_noise);
     }
   } else {
     if (smem > 48 * 1024)
@@ -531,7 +545,7 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
     { LaunchScope ls_(NRF_CAT_COMPOSITE_BWD, as_stream(stream));
     composite_bwd_kernel<float><<<grid, block, smem, as_stream(stream)>>>(
         field_out, ldo, z, rays, R, K, D, white_bkgd, d_rgb, d_embed, d_depth, d_weights,
-        reinterpret_cast<float*>(d_field), ldg, d_z);
+        reinterpret_cast<float*>(d_field), ldg, d_z, sigma_noise);
     }
   }
   NRF_LAUNCH_OK();

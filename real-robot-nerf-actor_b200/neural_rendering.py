@@ -13,7 +13,7 @@ Differences from the reference, all opt-in or invisible to its callers:
   * `forward_nerf(rays, want_weights=False, noise=None)`: `noise` injects pre-drawn tensors
     (keys coarse / u / fine / depth), used by the parity tests;
   * branches that are off in nerfact.conf (multi-scale voxels, depth-supervision volume, coord /
-    attention heads, ret_last_feat, softplus, spade, noise_std) raise NotImplementedError.
+    attention heads, ret_last_feat, softplus, spade) raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -301,18 +301,29 @@ class PixelNeRFEmbedNet(nn.Module):
 
 # -------------------------------------------------------------------------- render passes
 class _PassState:
-    __slots__ = ("rays", "z", "field_in", "acts", "field_out", "rps", "mlp", "perm")
+    __slots__ = ("rays", "z", "field_in", "acts", "field_out", "rps", "mlp", "perm", "sig_noise")
 
 
-def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps, keep_acts=True):
+def _sigma_noise(ren, noise, key, R, K, device):
+    """neural_rendering.py:336-337: sigmas + randn_like(sigmas) * noise_std, in training only.  `noise[key]` injects
+    the standard-normal draw (parity tests); returns the scaled tensor the compositing kernels take, or None."""
+    if not (ren.training and ren.noise_std and ren.noise_std > 0.0):
+        return None
+    nz = noise.get(key)
+    if nz is None:
+        nz = torch.randn(R, K, device=device)
+    return (nz.to(torch.float32) * float(ren.noise_std)).contiguous()
+
+
+def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps, keep_acts=True, sig_noise=None):
     """One composite pass (neural_rendering.py:224-395) over all samples of `z`.  keep_acts=False (no gradient
     will be asked for): the fused MLP kernel keeps nothing but the raw field outputs."""
     st = _PassState()
-    st.rays, st.z, st.rps, st.mlp, st.perm = rays, z, rps, mlp, None
+    st.rays, st.z, st.rps, st.mlp, st.perm, st.sig_noise = rays, z, rps, mlp, None, sig_noise
     st.field_in = ops.encode_points(rays, z, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
                                     ld_out=mlp.sizes.kin_pad, precision=mlp.precision)
     st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts)
-    outs = ops.composite_fwd(st.field_out, z, rays, ren._d_embed, ren.white_bkgd)
+    outs = ops.composite_fwd(st.field_out, z, rays, ren._d_embed, ren.white_bkgd, sigma_noise=sig_noise)
     return st, outs
 
 
@@ -320,7 +331,7 @@ def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, 
                    defer=None):
     res = ops.composite_bwd(st.field_out, st.z, st.rays, ren._d_embed, d_rgb, d_embed, d_depth, d_weights,
                             ldg=st.mlp.sizes.dout_pad, precision=st.mlp.precision,
-                            white_bkgd=ren.white_bkgd, want_dz=want_dz)
+                            white_bkgd=ren.white_bkgd, want_dz=want_dz, sigma_noise=st.sig_noise)
     d_field, d_z = res if want_dz else (res, None)
     dlat = st.mlp.backward(st.field_in, st.acts, d_field, grads, deterministic=ren.deterministic)
     if defer is not None:             # one merged scatter for all passes once the last one is through
@@ -397,7 +408,8 @@ class _ForwardNerfFn(torch.autograd.Function):
         ctx.cl3d = cl3d
         Kc, Kf, Kfd = ren.n_coarse, ren.n_fine, ren.n_fine_depth
         z_c = ops.sample_coarse(rays, Kc, noise.get("coarse"), ren.lindisp)
-        st_c, (cw, crgb, cemb, cdep) = _pass_forward(ren, mlp_c, vol_cl, rays, z_c, rps, keep)
+        st_c, (cw, crgb, cemb, cdep) = _pass_forward(ren, mlp_c, vol_cl, rays, z_c, rps, keep,
+                                                     _sigma_noise(ren, noise, "sigma_c", R, Kc, rays.device))
         outs = [z_c, cw, crgb, cemb, cdep]
         st_f = None
         depth_mask = None
@@ -419,7 +431,8 @@ class _ForwardNerfFn(torch.autograd.Function):
                 depth_mask = ((z0 <= far) & (z0 >= near)).to(torch.float32)
                 z_all[:, Kc + kf:] = torch.max(torch.min(z0, far), near)
             z_all, perm = ops.sort_rows(z_all, want_perm=True)
-            st_f, (fw, frgb, femb, fdep) = _pass_forward(ren, mlp_f, vol_cl, rays, z_all, rps, keep)
+            st_f, (fw, frgb, femb, fdep) = _pass_forward(ren, mlp_f, vol_cl, rays, z_all, rps, keep,
+                                                         _sigma_noise(ren, noise, "sigma_f", R, K, rays.device))
             st_f.perm = perm
             outs += [z_all, fw, frgb, femb, fdep]
         ctx.ren, ctx.st_c, ctx.st_f, ctx.sb, ctx.n_pc = ren, st_c, st_f, sb, n_pc
@@ -501,8 +514,6 @@ class NeuralRenderer(nn.Module):
         self.noise_std, self.white_bkgd, self.depth_std = g("noise_std", 0.0), g("white_bkgd", False), g("depth_std", 0.001)
         if self.ret_last_feat:
             raise NotImplementedError("ret_last_feat=True is off in nerfact.conf and not built")
-        if self.noise_std and self.noise_std > 0.0:
-            raise NotImplementedError("noise_std > 0 is off in nerfact.conf and not built")
         self.nerf_model = PixelNeRFEmbedNet(cfg, coordinate_bounds)
         self.model_name = g("foundation_model_name", None)
         if self.model_name not in ("odise", "diffusion", "dinov2", "deepfloyd", None):
@@ -539,13 +550,18 @@ class NeuralRenderer(nn.Module):
         """Noise in the reference's draw order (SURVEY 8b 'RNG'); zeros / a fixed grid if not perturb."""
         Kc, kf, Kfd = self.n_coarse, self.n_fine - self.n_fine_depth, self.n_fine_depth
         n = {}
+        sig = self.training and self.noise_std and self.noise_std > 0.0
         if self.perturb:
             n["coarse"] = torch.rand(R, Kc, device=device)
+            if sig:                                        # drawn inside the coarse composite (:336-337)
+                n["sigma_c"] = torch.randn(R, Kc, device=device)
             if self.using_fine and kf > 0:
                 n["u"] = torch.rand(R, kf, dtype=torch.float32, device=device)
                 n["fine"] = torch.rand(R, kf, device=device)
             if self.using_fine and Kfd > 0:
                 n["depth"] = torch.randn(R, Kfd, device=device)
+            if sig and self.using_fine:
+                n["sigma_f"] = torch.randn(R, Kc + self.n_fine, device=device)
         elif self.using_fine and kf > 0:
             n["u"] = ((torch.arange(kf, device=device, dtype=torch.float32) + 0.5) / kf).repeat(R, 1)
         return n
@@ -742,7 +758,8 @@ class _CompositeFn(torch.autograd.Function):
     def forward(ctx, ren, h, voxel_feat, rays, z, sb, *params):
         cl3d = _is_channels_last_3d(voxel_feat)
         vol_cl = voxel_feat.permute(0, 2, 3, 4, 1) if cl3d else ops.volume_to_channels_last(voxel_feat)
-        st, outs = _pass_forward(ren, h, vol_cl, rays, z, rays.shape[0] // sb)
+        st, outs = _pass_forward(ren, h, vol_cl, rays, z, rays.shape[0] // sb,
+                                 sig_noise=_sigma_noise(ren, {}, None, z.shape[0], z.shape[1], z.device))
         ctx.ren, ctx.st, ctx.vol_shape, ctx.cl3d = ren, st, tuple(vol_cl.shape), cl3d
         return outs
 

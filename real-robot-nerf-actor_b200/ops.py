@@ -203,8 +203,12 @@ def scatter_volume_grad_merged(rays, rays_per_scene, passes, grad, channels_firs
 
 
 # ------------------------------------------------------------------------------- compositing
-def composite_fwd(field_out, z, rays, D, white_bkgd=False):
-    """neural_rendering.py:339-359 on RAW MLP outputs (N, 4+D).  -> weights, rgb, embed, depth."""
+def composite_fwd(field_out, z, rays, D, white_bkgd=False, sigma_noise=None):
+    """neural_rendering.py:339-359 on RAW MLP outputs (N, 4+D).  -> weights, rgb, embed, depth.
+    sigma_noise (R,K): training-time density noise, already scaled by noise_std (neural_rendering.py:336-337)."""
+    if sigma_noise is not None:
+        sigma_noise = _f32(sigma_noise, "sigma_noise")
+        assert sigma_noise.shape == z.shape
     field_out = _f32(field_out, "field_out")
     z = _f32(z, "z")
     rays = _f32(rays, "rays")
@@ -215,13 +219,14 @@ def composite_fwd(field_out, z, rays, D, white_bkgd=False):
     emb = torch.empty(R, D, device=dev, dtype=torch.float32)
     dep = torch.empty(R, device=dev, dtype=torch.float32)
     check(_lib.load().nrf_composite_fwd(ptr(field_out), field_out.shape[1], ptr(z), ptr(rays), R, K, D,
-                                        int(white_bkgd), ptr(w), ptr(rgb), ptr(emb), ptr(dep), stream_ptr()),
+                                        int(white_bkgd), ptr(w), ptr(rgb), ptr(emb), ptr(dep), ptr(sigma_noise),
+                                        stream_ptr()),
           "nrf_composite_fwd")
     return w, rgb, emb, dep
 
 
 def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights=None, ldg=None,
-                  precision=NRF_PREC_BF16, white_bkgd=False, want_dz=False, out=None):
+                  precision=NRF_PREC_BF16, white_bkgd=False, want_dz=False, out=None, sigma_noise=None):
     """Closed-form backward; returns d_field (N, ldg) (operand-typed) and optionally d_z (R,K)."""
     field_out = _f32(field_out, "field_out")
     z = _f32(z, "z")
@@ -230,6 +235,7 @@ def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights
     d_embed = _f32(d_embed, "d_embed")
     d_depth = _f32(d_depth, "d_depth") if d_depth is not None else None
     d_weights = _f32(d_weights, "d_weights") if d_weights is not None else None
+    sigma_noise = _f32(sigma_noise, "sigma_noise") if sigma_noise is not None else None
     R, K = z.shape
     if ldg is None:
         ldg = (4 + D + 63) // 64 * 64
@@ -239,7 +245,7 @@ def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights
     check(_lib.load().nrf_composite_bwd(ptr(field_out), field_out.shape[1], ptr(z), ptr(rays), R, K, D,
                                         int(white_bkgd), ptr(d_rgb), ptr(d_embed), ptr(d_depth),
                                         ptr(d_weights), ptr(out), ldg, int(precision == NRF_PREC_BF16),
-                                        ptr(dz), stream_ptr()), "nrf_composite_bwd")
+                                        ptr(dz), ptr(sigma_noise), stream_ptr()), "nrf_composite_bwd")
     return (out, dz) if want_dz else out
 
 

@@ -9,6 +9,8 @@ tests check the CUDA path against the same files on the B200 box (where /root/re
 
 Cases
   small_kfd0 / small_kfd4 : tiny dims (S=12, C=16, D=24, hidden 64); every input is stored.
+  small_noise_wb          : same dims with the optional branches noise_std=0.5 (training-time density noise,
+                            neural_rendering.py:336-337), white_bkgd (:383-386) and lindisp (:175-176,205-206).
   full_s32                : BASELINE dims (C=128, D=384, hidden 512, Kc=Kf=64), 32^3 volume;
                             inputs are regenerated from seeds (synthetic.py / init_params), only
                             outputs and gradient projections are stored.
@@ -39,11 +41,12 @@ def load_params_into(renderer, params):
 
 
 def run_case(name, S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, focal, store_inputs, seed=0,
-             perturb=True):
+             perturb=True, noise_std=0.0, white_bkgd=False, lindisp=False):
     torch.manual_seed(seed)
     cfg = L.default_cfg(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H,
                         n_coarse=Kc, n_fine=Kf, n_fine_depth=Kfd, ray_chunk_size=n_rays,
-                        mlp=dict(d_hidden=hidden), eval_batch_size=1024)
+                        mlp=dict(d_hidden=hidden), eval_batch_size=1024, noise_std=noise_std,
+                        white_bkgd=white_bkgd, lindisp=lindisp)
     bounds = torch.tensor(syn.BOUNDS)
     ren = L.build_reference_renderer(cfg, bounds)
     params = O.init_params(d_in=42, d_latent=C, d_hidden=hidden, d_out=4 + D, seed=seed)
@@ -64,11 +67,18 @@ def run_case(name, S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, focal, store_
     gt_rgb_img = torch.rand(SB, H, W, 3, generator=gd)
     gt_embed_img = torch.randn(SB, H, W, D, generator=gd)
 
+    if noise_std > 0:          # the reference draws randn_like(sigmas) inside each composite (training mode)
+        noise["sigma_c"] = torch.randn(R, Kc, generator=gd)
+        noise["sigma_f"] = torch.randn(R, Kc + Kf, generator=gd)
     draws = [noise.get("coarse")]
+    if noise_std > 0:
+        draws += [noise["sigma_c"]]
     if Kf - Kfd > 0:
         draws += [noise["u"], noise.get("fine")]
     if Kfd > 0:
         draws += [noise_depth]
+    if noise_std > 0:
+        draws += [noise["sigma_f"]]
     ren.train()
     with L.inject_noise(draws), \
             mock.patch.object(torch, "randint", lambda *a, **k: idx.clone()):
@@ -79,7 +89,7 @@ def run_case(name, S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, focal, store_
     grads = {k: p.grad.clone() for k, p in ren.nerf_model.mlp_coarse.named_parameters()}
     vgrad = vol.grad.clone()
 
-    # second, no-grad pass for the intermediate tensors (same noise)
+    # second, no-grad pass for the intermediate tensors (same noise; still in training mode: noise_std applies)
     rays_full = ren_rays = None
     with torch.no_grad():
         U = sys.modules["_nrf_reference_utils"]
@@ -94,6 +104,7 @@ def run_case(name, S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, focal, store_
             z_c = ren.sample_coarse(r)
 
     fx = {"meta": np.array([S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed]),
+          "opts": np.array([noise_std, float(white_bkgd), float(lindisp)], dtype=np.float32),
           "focal": np.float32(focal), "idx": idx.numpy(), "rays": rays.numpy(), "z_coarse": z_c.numpy(),
           "loss": np.float32(out["loss"].item()),
           "loss_items": np.array([out[k] for k in ("loss_rgb_coarse", "loss_rgb_fine", "loss_embed_coarse",
@@ -161,5 +172,7 @@ if __name__ == "__main__":
              H=16, W=16, focal=19.0, store_inputs=True, seed=1)
     run_case("small_noperturb", S=12, C=16, D=24, hidden=64, SB=1, n_rays=40, Kc=16, Kf=8, Kfd=0,
              H=16, W=16, focal=19.0, store_inputs=True, seed=2, perturb=False)
+    run_case("small_noise_wb", S=12, C=16, D=24, hidden=64, SB=2, n_rays=48, Kc=16, Kf=16, Kfd=0,
+             H=16, W=16, focal=19.0, store_inputs=True, seed=4, noise_std=0.5, white_bkgd=True, lindisp=True)
     run_case("full_s32", S=32, C=128, D=384, hidden=512, SB=2, n_rays=64, Kc=64, Kf=64, Kfd=0,
              H=128, W=128, focal=153.0, store_inputs=False, seed=3)

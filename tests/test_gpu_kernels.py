@@ -191,9 +191,11 @@ def test_scatter_volume_grad_matches_autograd(ops):
 
 
 # ------------------------------------------------------------------------------ compositing
-@pytest.mark.parametrize("K,D,white", [(64, 384, False), (128, 384, False), (96, 24, True), (40, 8, False),
-                                       (128, 384, True), (80, 512, False), (256, 384, False)])
-def test_composite_fwd_bwd_matches_oracle(ops, K, D, white):
+@pytest.mark.parametrize("K,D,white,noise_std", [(64, 384, False, 0.0), (128, 384, False, 0.0), (96, 24, True, 0.0),
+                                                 (40, 8, False, 0.0), (128, 384, True, 0.0), (80, 512, False, 0.0),
+                                                 (256, 384, False, 0.0), (128, 384, True, 1.5), (48, 24, False, 1.5)])
+def test_composite_fwd_bwd_matches_oracle(ops, K, D, white, noise_std):
+    """noise_std > 0: the training-time density noise of neural_rendering.py:336-337 (both ReLUs gate the gradient)."""
     g = torch.Generator().manual_seed(K + D)
     R = 37
     raw = torch.randn(R, K, 4 + D, generator=g)
@@ -203,24 +205,27 @@ def test_composite_fwd_bwd_matches_oracle(ops, K, D, white):
     rays[:, 6], rays[:, 7] = 1.2, 4.0
     z = O.sample_coarse(rays, K, torch.rand(R, K, generator=g)).requires_grad_(True)
     act = torch.cat([torch.sigmoid(raw[..., :3]), torch.relu(raw[..., 3:4]), raw[..., 4:]], -1)
-    w, rgb, emb, dep = O.composite_from_field(act, z, rays[:, -1:], white_bkgd=white)
+    sn = torch.randn(R, K, generator=g) * noise_std if noise_std > 0 else None
+    snc = sn.cuda() if sn is not None else None
+    w, rgb, emb, dep = O.composite_from_field(act, z, rays[:, -1:], white_bkgd=white, sigma_noise=sn)
     d_rgb, d_emb = torch.randn(R, 3, generator=g), torch.randn(R, D, generator=g)
     d_dep, d_w = torch.randn(R, generator=g), torch.randn(R, K, generator=g) * 0.1
     (rgb * d_rgb).sum().add((emb * d_emb).sum()).add((dep * d_dep).sum()).add((w * d_w).sum()).backward()
 
     raw_c = raw.detach().reshape(R * K, 4 + D).cuda()
-    w2, rgb2, emb2, dep2 = ops.composite_fwd(raw_c, z.detach().cuda(), rays.cuda(), D, white)
+    w2, rgb2, emb2, dep2 = ops.composite_fwd(raw_c, z.detach().cuda(), rays.cuda(), D, white, sigma_noise=snc)
     assert rel(w2, w.detach()) < 2e-6 and rel(rgb2, rgb.detach()) < 2e-6
     assert rel(emb2, emb.detach()) < 2e-6 and rel(dep2, dep.detach()) < 2e-6
     dfield, dz = ops.composite_bwd(raw_c, z.detach().cuda(), rays.cuda(), D, d_rgb.cuda(), d_emb.cuda(),
                                    d_dep.cuda(), d_w.cuda(), precision=ops.NRF_PREC_FP32, white_bkgd=white,
-                                   want_dz=True)
+                                   want_dz=True, sigma_noise=snc)
     ldg = dfield.shape[1]
     assert ldg % 64 == 0 and (dfield[:, 4 + D:] == 0).all()
     assert rel(dfield[:, :4 + D].reshape(R, K, -1), raw.grad) < 1e-5
     assert rel(dz, z.grad) < 1e-5
     df16 = ops.composite_bwd(raw_c, z.detach().cuda(), rays.cuda(), D, d_rgb.cuda(), d_emb.cuda(),
-                             d_dep.cuda(), d_w.cuda(), precision=ops.NRF_PREC_BF16, white_bkgd=white)
+                             d_dep.cuda(), d_w.cuda(), precision=ops.NRF_PREC_BF16, white_bkgd=white,
+                             sigma_noise=snc)
     assert torch.equal(df16.cpu(), dfield.cpu().to(torch.bfloat16))
 
 

@@ -42,11 +42,11 @@ def cosine(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-30))
 
 
-def make_renderer(NR, meta, params, precision):
+def make_renderer(NR, meta, params, precision, **opts):
     U = load_pkg("utils")
     S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
     cfg = U.default_config(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H, n_coarse=Kc,
-                           n_fine=Kf, n_fine_depth=Kfd, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden))
+                           n_fine=Kf, n_fine_depth=Kfd, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden), **opts)
     ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS), precision=precision)
     sd = ren.state_dict()
     for k, v in params.items():
@@ -121,13 +121,17 @@ def _run_cuda(ren, vol, rays, noise, gt_rgb, gt_embed):
     return out, loss, vol.grad, grads
 
 
-@pytest.mark.parametrize("name", ["small_kfd0", "small_noperturb", "small_kfd4"])
+@pytest.mark.parametrize("name", ["small_kfd0", "small_noperturb", "small_kfd4", "small_noise_wb"])
 def test_small_golden_fp32(ops, NR, name):
-    """Tiny-dims cases against the reference's own outputs and gradients (fp32 parity mode)."""
+    """Tiny-dims cases against the reference's own outputs and gradients (fp32 parity mode); small_noise_wb runs the
+    optional branches noise_std > 0 (training-time density noise), white_bkgd and lindisp."""
     fx = golden(name)
     ci = _case_inputs(fx)
     meta = [int(v) for v in fx["meta"]]
-    ren = make_renderer(NR, meta, ci["params"], "fp32")
+    opts = {}
+    if "opts" in fx.files:
+        opts = dict(noise_std=float(fx["opts"][0]), white_bkgd=bool(fx["opts"][1]), lindisp=bool(fx["opts"][2]))
+    ren = make_renderer(NR, meta, ci["params"], "fp32", **opts)
     rays = T(fx["rays"])
     idx = T(fx["idx"])
     gt_rgb = T(fx["gt_rgb_img"]).reshape(ci["SB"], -1, 3)[:, idx]

@@ -55,7 +55,15 @@ def _case_inputs(fx):
                 seed=seed, params=params, noise=noise)
 
 
-@pytest.mark.parametrize("name", ["small_kfd0", "small_kfd4", "small_noperturb"])
+def _opts(fx):
+    """noise_std, white_bkgd, lindisp of a case (absent in the first fixtures: all off)."""
+    if "opts" not in fx.files:
+        return dict(noise_std=0.0, white_bkgd=False, lindisp=False)
+    o = fx["opts"]
+    return dict(noise_std=float(o[0]), white_bkgd=bool(o[1]), lindisp=bool(o[2]))
+
+
+@pytest.mark.parametrize("name", ["small_kfd0", "small_kfd4", "small_noperturb", "small_noise_wb"])
 def test_small_cases_forward_backward(name):
     fx = golden(name)
     ci = _case_inputs(fx)
@@ -67,7 +75,7 @@ def test_small_cases_forward_backward(name):
     rays = rays_full.reshape(ci["SB"], -1, 8)[:, idx]
     assert torch.equal(rays, T(fx["rays"]))
     out = O.forward_nerf(params, vol, rays, syn.BOUNDS, ci["Kc"], ci["Kf"], ci["Kfd"],
-                         noise=ci["noise"], eval_batch_size=1024)
+                         noise=ci["noise"], eval_batch_size=1024, **_opts(fx))
     assert torch.equal(out["z_coarse"], T(fx["z_coarse"]))
     for lvl in ("coarse", "fine"):
         for k in ("rgb", "embed", "depth", "weights"):
