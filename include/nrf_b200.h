@@ -129,6 +129,17 @@ int nrf_composite_bwd(const float* field_out, int ldo, const float* z, const flo
                       const float* d_depth, const float* d_weights, void* d_field, int ldg,
                       int out_bf16, float* d_z, const float* sigma_noise, void* stream);
 
+/* ---- rendering losses (neural_rendering.py:653-677 and their autograd) ---------------------------
+ * terms[0..3] = mean((rgb_c - t)^2), mean((rgb_f - t)^2), mean((emb_c - e)^2), mean((emb_f - e)^2)   (F.mse_loss)
+ * with t = gt_rgb[scene, idx[j]] (:676), e = gt_embed[scene, idx[j]] (:683) for ray r = scene*rays_per_scene + j;
+ * idx == NULL: gt_rgb (R,3) / gt_embed (R,D) are already per ray.  rgb_* (R,3), emb_* (R,D), gt_rgb (SB,n_pix,3),
+ * gt_embed (SB,n_pix,D), idx int64 (rays_per_scene).  d_* (same shapes as rgb_* / emb_*, any may be NULL) receive
+ * d terms[i] / d input = 2 (x - t) / numel.  partial: (R,4) fp32 scratch, 16 B aligned.  Fixed summation order. */
+int nrf_render_loss(const float* rgb_c, const float* rgb_f, const float* emb_c, const float* emb_f, int R, int D,
+                    int rays_per_scene, const float* gt_rgb, const float* gt_embed, int64_t n_pix,
+                    const int64_t* idx, float* partial, float* terms, float* d_rgb_c, float* d_rgb_f,
+                    float* d_emb_c, float* d_emb_f, void* stream);
+
 /* ---- GEMM building block of the field MLP ----------------------------------------------------
  * v = resid + mask( [A0 | A1 | A2] . B^T + bias ),   B (N,K) row-major (nn.Linear layout)
  *   A[i] (M,K[i]) lda[i]: up to three operand matrices concatenated along K (K[i] = 0: unused)

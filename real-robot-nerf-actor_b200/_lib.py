@@ -77,6 +77,7 @@ _SIGNATURES = {
     "nrf_mlp_bwd_layered": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, C.POINTER(NrfMlpGrads), _p, _p, _p],
 }
 _SIGNATURES["nrf_scatter_volume_grad_sorted"] = [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p]
+_SIGNATURES["nrf_render_loss"] = [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p]
 _SIGNATURES["nrf_scatter_volume_grad_merged"] = [_p, _i, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i,
                                                  _p, _p, _p]
 _SIGNATURES["nrf_timing_begin"] = []

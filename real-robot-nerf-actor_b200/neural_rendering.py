@@ -493,6 +493,28 @@ class _ForwardNerfFn(torch.autograd.Function):
         return (None, d_vol, None, None, None, None, None, *pg)
 
 
+class _RenderLossFn(torch.autograd.Function):
+    """The rgb / embed mean-squared errors of both passes (neural_rendering.py:664-685) as one autograd node:
+    one kernel produces the four terms and, in the same read, their gradients; backward only scales them."""
+
+    @staticmethod
+    def forward(ctx, rgb_c, rgb_f, emb_c, emb_f, gt_rgb, gt_embed, idx, rps):
+        need = any(ctx.needs_input_grad[:4])
+        terms, grads = ops.render_loss(rgb_c, rgb_f, emb_c, emb_f, rps, gt_rgb, gt_embed, idx, want_grads=need)
+        ctx.grads = grads
+        return terms
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.grads
+        out = [None] * 8
+        if d is not None:
+            for i in range(4):
+                if ctx.needs_input_grad[i]:
+                    out[i] = d[i] * g[i]                       # terms: rgb_c, rgb_f, emb_c, emb_f
+        return tuple(out)
+
+
 # ------------------------------------------------------------------------------ the renderer
 class NeuralRenderer(nn.Module):
     """take a voxel, camera pose, and camera intrinsics as input, and output a rendered image
@@ -530,6 +552,7 @@ class NeuralRenderer(nn.Module):
         self.target_ready_event = None         # optional torch.cuda.Event: gt_rgb / gt_embed were copied on a side
                                                # stream; awaited right before the losses read them
         self.perturb = True
+        self.fused_loss = True                 # rgb / embed losses + their gradients in one kernel (nrf_render_loss)
         self.render_chunk_rays = 4096          # neural_rendering.py:482
         self._num_freqs = self.nerf_model.code.num_freqs
         self._freq_factor = float(self.nerf_model.code.freq_factor)
@@ -717,16 +740,26 @@ class NeuralRenderer(nn.Module):
                     gt_embed = torch.from_numpy(flat).reshape(Bq, Hq, Wq, embed_dim).permute(0, 3, 1, 2)
                     gt_embed = gt_embed.to(gt_rgb.device)
                 gt_embed = gt_embed.permute(0, 2, 3, 1)
-        gt_rgb = gt_rgb.reshape(B, H * W, 3)[:, idx, :]
-        loss_rgb_coarse = F.mse_loss(outputs.coarse.rgb, gt_rgb)
-        loss_rgb_fine = F.mse_loss(outputs.fine.rgb, gt_rgb)
+        D = gt_embed.shape[-1]
+        if self.fused_loss and gt_rgb.is_cuda and gt_rgb.dtype == torch.float32 and gt_embed.dtype == torch.float32:
+            # one kernel: target gather [:, idx], the four mse terms and their gradients (nrf_render_loss)
+            t = _RenderLossFn.apply(outputs.coarse.rgb.reshape(-1, 3), outputs.fine.rgb.reshape(-1, 3),
+                                    outputs.coarse.embed.reshape(-1, D), outputs.fine.embed.reshape(-1, D),
+                                    gt_rgb.reshape(B, H * W, 3), gt_embed.reshape(B, H * W, D), idx, chunk_size)
+            loss_rgb_coarse, loss_rgb_fine = t[0], t[1]
+            loss_embed_coarse, loss_embed_fine = self.lambda_embed * t[2], self.lambda_embed * t[3]
+            mse_fine = t[1].detach()
+        else:
+            gt_rgb = gt_rgb.reshape(B, H * W, 3)[:, idx, :]
+            loss_rgb_coarse = F.mse_loss(outputs.coarse.rgb, gt_rgb)
+            loss_rgb_fine = F.mse_loss(outputs.fine.rgb, gt_rgb)
+            mse_fine = torch.mean((outputs.fine.rgb.detach() - gt_rgb) ** 2)
+            gt_embed = gt_embed.reshape(B, H * W, -1)[:, idx, :]
+            loss_embed_coarse = self.lambda_embed * F.mse_loss(outputs.coarse.embed, gt_embed)
+            loss_embed_fine = self.lambda_embed * F.mse_loss(outputs.fine.embed, gt_embed)
         loss = loss_rgb_coarse + loss_rgb_fine
-        mse_fine = torch.mean((outputs.fine.rgb.detach() - gt_rgb) ** 2)       # PSNR_torch without its host-side branch
-        psnr = torch.where(mse_fine == 0, torch.full_like(mse_fine, 100.0),
+        psnr = torch.where(mse_fine == 0, torch.full_like(mse_fine, 100.0),          # PSNR_torch without its host-side branch
                            20 * torch.log10(1.0 / torch.sqrt(mse_fine.clamp_min(1e-45))))
-        gt_embed = gt_embed.reshape(B, H * W, -1)[:, idx, :]
-        loss_embed_coarse = self.lambda_embed * F.mse_loss(outputs.coarse.embed, gt_embed)
-        loss_embed_fine = self.lambda_embed * F.mse_loss(outputs.fine.embed, gt_embed)
         loss = loss + loss_embed_coarse + loss_embed_fine
         if gt_depth is not None:
             gt_depth = gt_depth.reshape(B, H * W)[:, idx]

@@ -249,6 +249,37 @@ def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights
     return (out, dz) if want_dz else out
 
 
+def render_loss(rgb_c, rgb_f, emb_c, emb_f, rays_per_scene, gt_rgb, gt_embed, idx=None, want_grads=True):
+    """The four F.mse_loss terms of neural_rendering.py:653-677 and their gradients in one pass (nrf_render_loss).
+
+    rgb_* (R,3), emb_* (R,D); gt_rgb (SB,n_pix,3), gt_embed (SB,n_pix,D) with idx int64 (rays_per_scene) pixel per
+    ray, or idx=None and per-ray targets (R,3) / (R,D).  -> terms (4,), (d_rgb_c, d_rgb_f, d_emb_c, d_emb_f) or None."""
+    rgb_c, rgb_f = _f32(rgb_c, "rgb_c"), _f32(rgb_f, "rgb_f")
+    emb_c, emb_f = _f32(emb_c, "emb_c"), _f32(emb_f, "emb_f")
+    gt_rgb, gt_embed = _f32(gt_rgb, "gt_rgb"), _f32(gt_embed, "gt_embed")
+    R, D = emb_c.shape
+    assert rgb_c.shape == (R, 3) and rgb_f.shape == (R, 3) and emb_f.shape == (R, D) and gt_embed.shape[-1] == D
+    if idx is not None:
+        assert idx.is_cuda and idx.dtype == torch.int64 and idx.numel() == rays_per_scene
+        idx = idx.contiguous()
+        n_pix = gt_rgb.shape[-2]
+        assert gt_rgb.numel() == (R // rays_per_scene) * n_pix * 3 and gt_embed.numel() == (R // rays_per_scene) * n_pix * D
+    else:
+        n_pix = 0
+        assert gt_rgb.numel() == R * 3 and gt_embed.numel() == R * D
+    dev = rgb_c.device
+    partial = torch.empty(R, 4, device=dev, dtype=torch.float32)
+    terms = torch.empty(4, device=dev, dtype=torch.float32)
+    grads = None
+    if want_grads:
+        grads = (torch.empty_like(rgb_c), torch.empty_like(rgb_f), torch.empty_like(emb_c), torch.empty_like(emb_f))
+    gp = [ptr(g) for g in grads] if grads is not None else [None] * 4
+    check(_lib.load().nrf_render_loss(ptr(rgb_c), ptr(rgb_f), ptr(emb_c), ptr(emb_f), R, D, rays_per_scene,
+                                      ptr(gt_rgb), ptr(gt_embed), n_pix, ptr(idx), ptr(partial), ptr(terms), *gp,
+                                      stream_ptr()), "nrf_render_loss")
+    return terms, grads
+
+
 # ------------------------------------------------------------------------------------- GEMMs
 def gemm(A1, B, *, A2=None, A3=None, bias=None, mask_src=None, resid=None, out_f32=None, out_act=None,
          relu_act=False, out_act2=None, relu_act2=False, n_store=None, precision=NRF_PREC_BF16):

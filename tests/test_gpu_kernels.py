@@ -493,3 +493,39 @@ def test_acts_of_the_layered_forward_take_the_layered_backward(ops):
     db = h.backward(fin, acts_f, dfield, gb, deterministic=True)      # fused
     assert torch.equal(da, db)
     assert all(torch.equal(ga[n], gb[n]) for n in h.names())
+
+
+# ------------------------------------------------------------------------------ fused rendering losses
+@pytest.mark.parametrize("D,with_idx", [(384, True), (24, True), (512, False)])
+def test_render_loss_matches_mse_loss_and_its_autograd(ops, D, with_idx):
+    """nrf_render_loss = the four F.mse_loss terms of neural_rendering.py:664-685 with the [:, idx] target gather,
+    plus their gradients, bit-reproducible."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(D)
+    SB, rps, n_pix = 2, 150, 400
+    R = SB * rps
+    xs = [torch.randn(R, 3, generator=g), torch.randn(R, 3, generator=g), torch.randn(R, D, generator=g),
+          torch.randn(R, D, generator=g)]
+    xs = [x.requires_grad_(True) for x in xs]
+    gt_rgb, gt_emb = torch.rand(SB, n_pix, 3, generator=g), torch.randn(SB, n_pix, D, generator=g)
+    idx = torch.randint(n_pix, (rps,), generator=g)
+    t_rgb, t_emb = gt_rgb[:, idx].reshape(R, 3), gt_emb[:, idx].reshape(R, D)
+    ref = torch.stack([F.mse_loss(xs[0], t_rgb), F.mse_loss(xs[1], t_rgb), F.mse_loss(xs[2], t_emb),
+                       F.mse_loss(xs[3], t_emb)])
+    coef = torch.tensor([1.0, 0.5, 0.01, 0.02])
+    (ref * coef).sum().backward()
+    xc = [x.detach().cuda() for x in xs]
+    if with_idx:
+        terms, grads = ops.render_loss(*xc, rps, gt_rgb.cuda(), gt_emb.cuda(), idx.cuda())
+    else:
+        terms, grads = ops.render_loss(*xc, rps, t_rgb.cuda(), t_emb.cuda(), None)
+    assert rel(terms, ref.detach()) < 1e-6
+    for i in range(4):
+        assert rel(grads[i] * float(coef[i]), xs[i].grad) < 1e-6
+    terms2, grads2 = ops.render_loss(*xc, rps, gt_rgb.cuda() if with_idx else t_rgb.cuda(),
+                                     gt_emb.cuda() if with_idx else t_emb.cuda(), idx.cuda() if with_idx else None)
+    assert torch.equal(terms, terms2) and all(torch.equal(a, b) for a, b in zip(grads, grads2))
+    terms3, none = ops.render_loss(*xc, rps, gt_rgb.cuda() if with_idx else t_rgb.cuda(),
+                                   gt_emb.cuda() if with_idx else t_emb.cuda(), idx.cuda() if with_idx else None,
+                                   want_grads=False)
+    assert none is None and torch.equal(terms, terms3)

@@ -232,6 +232,35 @@ def test_forward_loss_dict_and_rendering(ops, NR):
                       voxel_pose=None, focal=focal, tgt_pose=poses, c=None)
 
 
+def test_fused_loss_equals_the_torch_losses(ops, NR):
+    """compute_rendering_loss with the one-kernel losses (default) against the same step with F.mse_loss + autograd."""
+    fx = golden("small_kfd0")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    poses = T(fx["poses"]).cuda()
+    focal = torch.tensor(float(fx["focal"])).cuda()
+    idx = T(fx["idx"]).cuda()
+    noise = {k: v.cuda() for k, v in ci["noise"].items()}
+    res = {}
+    for fused in (True, False):
+        ren = make_renderer(NR, meta, ci["params"], "fp32")
+        ren.fused_loss = fused
+        vol = T(fx["vol"]).cuda().requires_grad_(True)
+        with mock.patch.object(torch, "randint", lambda *a, **k: idx.clone()), \
+                mock.patch.object(ren, "_draw_noise", lambda R_, dev: noise):
+            out = ren(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=vol,
+                      voxel_poses=poses, focal=focal, gt_rgb=T(fx["gt_rgb_img"]).cuda(), gt_depth=None,
+                      gt_pose=poses, c=None, lang_goal=None, gt_embed=T(fx["gt_embed_img"]).cuda())
+        out["loss"].backward()
+        res[fused] = (out, vol.grad, {k: p.grad for k, p in ren.named_parameters()})
+    a, b = res[True], res[False]
+    for k in list(a[0].keys()):
+        assert abs(float(a[0][k]) - float(b[0][k])) <= 2e-6 * max(1.0, abs(float(b[0][k]))), k
+    assert rel(a[1], b[1]) < 1e-5
+    for k in a[2]:
+        assert rel(a[2][k], b[2][k]) < 1e-5, k
+
+
 def test_sorted_scatter_end_to_end_and_separate_fine_mlp(ops, NR):
     """scatter="sorted" gives the same volume gradient (bit-reproducible run to run); share_mlp=False trains
     two MLPs (models_embed.py:115-120)."""
