@@ -117,17 +117,32 @@ int nrf_scatter_volume_grad_merged(const float* rays, int R, int rays_per_scene,
  * weights (R,K), rgb (R,3), embed (R,D), depth (R).
  * sigma_noise (R,K) or NULL: the training-time density noise of neural_rendering.py:336-337, already scaled
  * by noise_std: alpha = 1 - exp(-delta * relu(relu(raw) + sigma_noise)). */
+/* reuse (or NULL): the fine pass composites the ray's K = n_first + n_new sorted samples without re-evaluating the
+ * first n_first of them (the coarse samples: same point, same view direction, same MLP when share_mlp,
+ * models_embed.py:113-114 -> the same field output).  perm (R,K) int32 from nrf_sort_rows: sorted position k of ray r
+ * is sample p = perm[r][k] of [coarse | new]; p < n_first -> row r*n_first + p of field_out (the coarse pass's
+ * buffer), else row r*n_new + (p - n_first) of field_new.  Backward: gradient rows go to d_field (R*n_first rows) /
+ * d_field_new by the same rule (every row written once); the coarse pass's own nrf_composite_bwd then runs with
+ * accumulate = 1 on the same d_field, so a reused sample goes through the MLP backward once with the sum. */
+typedef struct {
+  const float* field_new;   /* (R*n_new, ldo) raw field outputs of the newly sampled points */
+  const int32_t* perm;      /* (R, K) */
+  int n_first;
+  void* d_field_new;        /* backward only: (R*n_new, ldg), bf16 or fp32 like d_field */
+} NrfCompositeReuse;
+
 int nrf_composite_fwd(const float* field_out, int ldo, const float* z, const float* rays, int R, int K,
                       int D, int white_bkgd, float* weights, float* rgb, float* embed, float* depth,
-                      const float* sigma_noise, void* stream);
+                      const float* sigma_noise, const NrfCompositeReuse* reuse, void* stream);
 
 /* Backward of the above (closed form).  d_weights and d_z may be NULL.
  * d_field (N, ldg): gradient w.r.t. the RAW MLP outputs, bf16 if out_bf16 else fp32; columns
- * [4+D, ldg) are zero-filled. */
+ * [4+D, ldg) are zero-filled.  accumulate != 0: added to what d_field holds (rounded once more in bf16). */
 int nrf_composite_bwd(const float* field_out, int ldo, const float* z, const float* rays, int R, int K,
                       int D, int white_bkgd, const float* d_rgb, const float* d_embed,
                       const float* d_depth, const float* d_weights, void* d_field, int ldg,
-                      int out_bf16, float* d_z, const float* sigma_noise, void* stream);
+                      int out_bf16, float* d_z, const float* sigma_noise, const NrfCompositeReuse* reuse,
+                      int accumulate, void* stream);
 
 /* ---- rendering losses (neural_rendering.py:653-677 and their autograd) ---------------------------
  * terms[0..3] = mean((rgb_c - t)^2), mean((rgb_f - t)^2), mean((emb_c - e)^2), mean((emb_f - e)^2)   (F.mse_loss)

@@ -30,6 +30,10 @@ class NrfGemm(C.Structure):
                 ("out_f32", c_ptr), ("ldo", C.c_int)]
 
 
+class NrfCompositeReuse(C.Structure):
+    _fields_ = [("field_new", c_ptr), ("perm", c_ptr), ("n_first", C.c_int), ("d_field_new", c_ptr)]
+
+
 _PA = c_ptr * NRF_MAX_BLOCKS
 
 
@@ -64,8 +68,9 @@ _SIGNATURES = {
     "nrf_volume_to_channels_first": [_p, _p, _i, _i, _i64, _p],
     "nrf_encode_points": [_p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _f, _p, _i, _i, _p, _p],
     "nrf_scatter_volume_grad": [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p],
-    "nrf_composite_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
-    "nrf_composite_bwd": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p],
+    "nrf_composite_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, C.POINTER(NrfCompositeReuse), _p],
+    "nrf_composite_bwd": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p,
+                          C.POINTER(NrfCompositeReuse), _i, _p],
     "nrf_gemm": [C.POINTER(NrfGemm), _i, _p],
     "nrf_wgrad": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p],
     "nrf_mlp_sizes": [C.POINTER(NrfMlpParams), _i, C.POINTER(NrfMlpSizes)],

@@ -11,6 +11,45 @@ constexpr int kMaxPerLane = 32;   // K <= 1024
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// Where the field-output row (and the gradient row) of sorted sample k of ray r lives.  Plain pass: row r*K + k of one
+// buffer.  Fine pass that reuses the coarse pass's evaluations (perm != NULL): perm[r][k] = p indexes the ray's
+// [Ka coarse | Kb new] samples before the sort: p < Ka -> row r*Ka + p of buffer a (the coarse pass's outputs),
+// else row r*Kb + (p - Ka) of buffer b (the newly evaluated samples).
+struct Rows {
+  const float* fa;
+  const float* fb;
+  const int* perm;     // this ray's row of the permutation, or nullptr
+  int Ka, Kb, ld;
+  int64_t r;
+  __device__ __forceinline__ int64_t row(int k, bool& first) const {
+    if (!perm) { first = true; return r * Ka + k; }
+    const int p = perm[k];
+    first = p < Ka;
+    return first ? r * Ka + p : r * Kb + (p - Ka);
+  }
+  __device__ __forceinline__ const float* at(int k) const {
+    bool first;
+    const int64_t i = row(k, first);
+    return (first ? fa : fb) + i * ld;
+  }
+};
+
+struct NrfReuseDev {       // device copy of NrfCompositeReuse (+ the accumulate flag of nrf_composite_bwd)
+  const float* field_new;
+  const int* perm;
+  int n_first;
+  void* d_field_new;
+  int accumulate;
+};
+
+__device__ __forceinline__ Rows make_rows(const float* field, int ldo, int r, int K, const NrfReuseDev& ru) {
+  Rows q;
+  q.fa = field; q.fb = ru.field_new; q.ld = ldo; q.r = r;
+  if (ru.perm) { q.perm = ru.perm + (int64_t)r * K; q.Ka = ru.n_first; q.Kb = K - ru.n_first; }
+  else { q.perm = nullptr; q.Ka = K; q.Kb = 0; }
+  return q;
+}
+
 // Computes, for the warp's ray, alpha_k / T_k / w_k for the lane's contiguous chunk of samples.
 // chunk = ceil(K/32); lane owns k in [lane*chunk, min(K,(lane+1)*chunk)).
 struct RayScan {
@@ -31,7 +70,7 @@ __device__ __forceinline__ float warp_exclusive_prod(float local, int lane) {
 
 // smem per warp: w[K], aux[K]
 template <bool kBackward>
-__device__ __forceinline__ void ray_weights(const float* __restrict__ field, int ldo,
+__device__ __forceinline__ void ray_weights(const Rows& rows,
                                             const float* __restrict__ zrow, float far, int K, int lane,
                                             float* __restrict__ s_w, float* __restrict__ s_alpha,
                                             float* __restrict__ s_T, float* __restrict__ s_delta,
@@ -42,7 +81,7 @@ __device__ __forceinline__ void ray_weights(const float* __restrict__ field, int
   for (int k = k0; k < k1; ++k) {
     float zk = zrow[k];
     float delta = (k + 1 < K ? zrow[k + 1] : far) - zk;
-    float sigma = fmaxf(field[(int64_t)k * ldo + 3], 0.0f);            // models_embed.py:464
+    float sigma = fmaxf(rows.at(k)[3], 0.0f);                          // models_embed.py:464
     if (nz) sigma = fmaxf(sigma + nz[k], 0.0f);                        // neural_rendering.py:336-339 (training noise)
     float alpha = 1.0f - expf(-delta * sigma);
     s_alpha[k] = alpha;
@@ -66,7 +105,7 @@ constexpr int kRayWarps = 4;
 __global__ void __launch_bounds__(128) composite_fwd_kernel(
     const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
     int R, int K, int D, int white_bkgd, float* __restrict__ weights, float* __restrict__ rgb,
-    float* __restrict__ embed, float* __restrict__ depth, const float* __restrict__ sig_noise) {
+    float* __restrict__ embed, float* __restrict__ depth, const float* __restrict__ sig_noise, NrfReuseDev ru) {
   extern __shared__ float smem[];
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
   const int r = blockIdx.x;
@@ -74,10 +113,10 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(
   float* s_w = smem;
   float* s_alpha = s_w + K;
   float* s_part = smem + ((2 * K + 3) & ~3);   // kRayWarps x (4 + D + 4) partial sums, 16 B aligned
-  const float* f = field + (int64_t)r * K * ldo;
+  const Rows rows = make_rows(field, ldo, r, K, ru);
   const float* zrow = z + (int64_t)r * K;
   float far = rays[(int64_t)r * 8 + 7];
-  if (wid == 0) ray_weights<false>(f, ldo, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr, nz);
+  if (wid == 0) ray_weights<false>(rows, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr, nz);
   __syncthreads();
 
   const int nvec = (4 + D) / 4;             // float4 per row
@@ -88,7 +127,7 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(
   float dsum = 0.f, wsum = 0.f;
   for (int k = wid; k < K; k += kRayWarps) {
     float w = s_w[k];
-    const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
+    const float4* row = reinterpret_cast<const float4*>(rows.at(k));
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
       int v = lane + i * kWarp;
@@ -136,6 +175,16 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(
   }
 }
 
+template <typename T> __device__ __forceinline__ float4 load_grad4(const T* p);
+template <> __device__ __forceinline__ float4 load_grad4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <> __device__ __forceinline__ float4 load_grad4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
 template <typename T> __device__ __forceinline__ void store_grad4(T* p, float4 v);
 template <> __device__ __forceinline__ void store_grad4<float>(float* p, float4 v) {
   *reinterpret_cast<float4*>(p) = v;
@@ -146,6 +195,23 @@ template <> __device__ __forceinline__ void store_grad4<__nv_bfloat16>(__nv_bflo
   u.x = *reinterpret_cast<uint32_t*>(&a);
   u.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = u;
+}
+
+// acc: the row already holds this sample's gradient from the fine pass that reused it: add to it.
+template <typename T> __device__ __forceinline__ void put_grad4(T* p, float4 v, bool acc) {
+  if (acc) {
+    const float4 o = load_grad4<T>(p);
+    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+  }
+  store_grad4<T>(p, v);
+}
+
+// The gradient row of sorted sample k (see Rows).
+template <typename T>
+__device__ __forceinline__ T* grad_row(const Rows& rows, T* d_a, void* d_b, int ldg, int k) {
+  bool first;
+  const int64_t i = rows.row(k, first);
+  return (first ? d_a : reinterpret_cast<T*>(d_b)) + i * ldg;
 }
 
 // Backward.  With g_k = <d_rgb, rgb_k> + <d_embed, e_k> + d_depth z_k (+ d_w_k):
@@ -160,7 +226,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
     int R, int K, int D, int white_bkgd, const float* __restrict__ d_rgb,
     const float* __restrict__ d_embed, const float* __restrict__ d_depth,
     const float* __restrict__ d_weights, T* __restrict__ d_field, int ldg, float* __restrict__ d_z,
-    const float* __restrict__ sig_noise) {
+    const float* __restrict__ sig_noise, NrfReuseDev ru) {
   // One CTA of 4 warps per ray: scans on warp 0, the per-sample row work split over the 4 warps.
   extern __shared__ float smem[];
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -172,10 +238,10 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
   float* s_delta = s_T + K;
   float* s_g = s_delta + K;
   float* s_ds = s_g + K;   // dL/dsigma (pre relu-gate) then reused
-  const float* f = field + (int64_t)r * K * ldo;
+  const Rows rows = make_rows(field, ldo, r, K, ru);
   const float* zrow = z + (int64_t)r * K;
   float far = rays[(int64_t)r * 8 + 7];
-  if (wid == 0) ray_weights<true>(f, ldo, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta, nz);
+  if (wid == 0) ray_weights<true>(rows, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta, nz);
   __syncthreads();
 
   const int nvec = (4 + D) / 4;
@@ -201,7 +267,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
 
   // pass A: g_k
   for (int k = wid; k < K; k += kRayWarps) {
-    const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
+    const float4* row = reinterpret_cast<const float4*>(rows.at(k));
     float part = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
@@ -248,8 +314,9 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
   // pass B: write d_field rows
   for (int k = wid; k < K; k += kRayWarps) {
     float w = s_w[k];
-    const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
-    T* grow = d_field + ((int64_t)r * K + k) * ldg;
+    const float4* row = reinterpret_cast<const float4*>(rows.at(k));
+    const bool acc = ru.accumulate != 0;
+    T* grow = grad_row<T>(rows, d_field, ru.d_field_new, ldg, k);
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
       int v = lane + i * kWarp;
@@ -266,15 +333,16 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(
         } else {
           gq = make_float4(w * dout[i].x, w * dout[i].y, w * dout[i].z, w * dout[i].w);
         }
-        store_grad4<T>(grow + v * 4, gq);
+        put_grad4<T>(grow + v * 4, gq, acc);
       }
     }
-    for (int c = 4 + D + lane; c < ldg; c += kWarp) grow[c] = T(0.0f);
+    if (!acc)
+      for (int c = 4 + D + lane; c < ldg; c += kWarp) grow[c] = T(0.0f);
   }
   if (d_z) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       auto sig_at = [&](int q) {
-        float sg = fmaxf(f[(int64_t)q * ldo + 3], 0.0f);
+        float sg = fmaxf(rows.at(q)[3], 0.0f);
         return nz ? fmaxf(sg + nz[q], 0.0f) : sg;
       };
       float dl_k = sig_at(k) * s_ds[k];
@@ -295,7 +363,7 @@ template <int DV>
 __global__ void __launch_bounds__(128) composite_fwd_fast_kernel(
     const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
     int K, int white_bkgd, float* __restrict__ weights, float* __restrict__ rgb, float* __restrict__ embed,
-    float* __restrict__ depth, const float* __restrict__ sig_noise) {
+    float* __restrict__ depth, const float* __restrict__ sig_noise, NrfReuseDev ru) {
   constexpr int D = 128 * DV;
   extern __shared__ float smem[];
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -304,10 +372,10 @@ __global__ void __launch_bounds__(128) composite_fwd_fast_kernel(
   float* s_w = smem;
   float* s_alpha = s_w + K;
   float* s_part = smem + ((2 * K + 3) & ~3);   // kRayWarps x (D + 8): embed sums, then rgb(3), depth, wsum
-  const float* f = field + (int64_t)r * K * ldo;
+  const Rows rows = make_rows(field, ldo, r, K, ru);
   const float* zrow = z + (int64_t)r * K;
   const float far = rays[(int64_t)r * 8 + 7];
-  if (wid == 0) ray_weights<false>(f, ldo, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr, nz);
+  if (wid == 0) ray_weights<false>(rows, zrow, far, K, lane, s_w, s_alpha, nullptr, nullptr, nz);
   __syncthreads();
   float4 acc[DV];
 #pragma unroll
@@ -316,7 +384,7 @@ __global__ void __launch_bounds__(128) composite_fwd_fast_kernel(
 #pragma unroll 2
   for (int k = wid; k < K; k += kRayWarps) {
     const float w = s_w[k];
-    const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
+    const float4* row = reinterpret_cast<const float4*>(rows.at(k));
     float4 x[DV];
 #pragma unroll
     for (int i = 0; i < DV; ++i) x[i] = __ldg(row + 1 + lane + i * kWarp);
@@ -365,7 +433,7 @@ __global__ void __launch_bounds__(128) composite_bwd_fast_kernel(
     const float* __restrict__ field, int ldo, const float* __restrict__ z, const float* __restrict__ rays,
     int K, int white_bkgd, const float* __restrict__ d_rgb, const float* __restrict__ d_embed,
     const float* __restrict__ d_depth, const float* __restrict__ d_weights, T* __restrict__ d_field, int ldg,
-    float* __restrict__ d_z, const float* __restrict__ sig_noise) {
+    float* __restrict__ d_z, const float* __restrict__ sig_noise, NrfReuseDev ru) {
   constexpr int D = 128 * DV;
   extern __shared__ float smem[];
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -380,10 +448,10 @@ __global__ void __launch_bounds__(128) composite_bwd_fast_kernel(
   float* s_sig = s_ds + K;     // the density that went into alpha_k: relu(raw) (+ noise, relu again)
   float* s_h = s_sig + K;      // 3 per sample: d_rgb_c * s(1-s), the sigmoid-head factors
   float* s_open = s_h + 3 * K; // 1 where the gradient reaches the raw density output (every ReLU on the way passes)
-  const float* f = field + (int64_t)r * K * ldo;
+  const Rows rows = make_rows(field, ldo, r, K, ru);
   const float* zrow = z + (int64_t)r * K;
   const float far = rays[(int64_t)r * 8 + 7];
-  if (wid == 0) ray_weights<true>(f, ldo, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta, nz);
+  if (wid == 0) ray_weights<true>(rows, zrow, far, K, lane, s_w, s_alpha, s_T, s_delta, nz);
   // this lane's slice of dL/d(embed of the ray) and the ray's scalar upstream gradients
   float4 de[DV];
 #pragma unroll
@@ -396,7 +464,7 @@ __global__ void __launch_bounds__(128) composite_bwd_fast_kernel(
   // pass A: g_k = <d_rgb, rgb_k> + <d_embed, e_k> + d_depth z_k (+ d_w_k); every field row is read here, once
 #pragma unroll 2
   for (int k = wid; k < K; k += kRayWarps) {
-    const float4* row = reinterpret_cast<const float4*>(f + (int64_t)k * ldo);
+    const float4* row = reinterpret_cast<const float4*>(rows.at(k));
     float4 x[DV];
 #pragma unroll
     for (int i = 0; i < DV; ++i) x[i] = __ldg(row + 1 + lane + i * kWarp);
@@ -446,14 +514,15 @@ __global__ void __launch_bounds__(128) composite_bwd_fast_kernel(
 #pragma unroll 2
   for (int k = wid; k < K; k += kRayWarps) {
     const float w = s_w[k];
-    T* grow = d_field + ((int64_t)r * K + k) * ldg;
+    const bool acc = ru.accumulate != 0;
+    T* grow = grad_row<T>(rows, d_field, ru.d_field_new, ldg, k);
 #pragma unroll
     for (int i = 0; i < DV; ++i)
-      store_grad4<T>(grow + 4 + (lane + i * kWarp) * 4, make_float4(w * de[i].x, w * de[i].y, w * de[i].z, w * de[i].w));
+      put_grad4<T>(grow + 4 + (lane + i * kWarp) * 4, make_float4(w * de[i].x, w * de[i].y, w * de[i].z, w * de[i].w), acc);
     if (lane == 0) {
-      store_grad4<T>(grow, make_float4(w * s_h[3 * k], w * s_h[3 * k + 1], w * s_h[3 * k + 2],
-                                       s_open[k] != 0.0f ? s_delta[k] * s_ds[k] : 0.0f));
-    } else if (lane <= pad4) {
+      put_grad4<T>(grow, make_float4(w * s_h[3 * k], w * s_h[3 * k + 1], w * s_h[3 * k + 2],
+                                     s_open[k] != 0.0f ? s_delta[k] * s_ds[k] : 0.0f), acc);
+    } else if (lane <= pad4 && !acc) {
       store_grad4<T>(grow + 4 + D + (lane - 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
     }
   }
@@ -481,23 +550,30 @@ static int check_composite(const char* who, int R, int K, int D, int ldo) {
 
 extern "C" int nrf_composite_fwd(const float* field_out, int ldo, const float* z, const float* rays,
                                  int R, int K, int D, int white_bkgd, float* weights, float* rgb,
-                                 float* embed, float* depth, const float* sigma_noise, void* stream) {
+                                 float* embed, float* depth, const float* sigma_noise,
+                                 const NrfCompositeReuse* reuse, void* stream) {
   NRF_REQUIRE(field_out && z && rays && weights && rgb && embed && depth, NRF_EINVAL,
               "nrf_composite_fwd: null pointer");
   int rc = check_composite("nrf_composite_fwd", R, K, D, ldo);
   if (rc) return rc;
+  NrfReuseDev ru{nullptr, nullptr, 0, nullptr, 0};
+  if (reuse) {
+    NRF_REQUIRE(reuse->field_new && reuse->perm && reuse->n_first > 0 && reuse->n_first < K, NRF_EINVAL,
+                "nrf_composite_fwd: reuse needs field_new, perm and 0 < n_first < K");
+    ru = NrfReuseDev{reuse->field_new, reuse->perm, reuse->n_first, nullptr, 0};
+  }
   size_t smem = ((size_t)((2 * K + 3) & ~3) + (size_t)kRayWarps * (4 + D + 4)) * sizeof(float);
   const bool aligned = (reinterpret_cast<uintptr_t>(field_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(embed) & 15) == 0;
   { LaunchScope ls_(NRF_CAT_COMPOSITE_FWD, as_stream(stream));
   if (D == 384 && aligned && smem <= 48 * 1024)
     composite_fwd_fast_kernel<3><<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
-        field_out, ldo, z, rays, K, white_bkgd, weights, rgb, embed, depth, sigma_noise);
+        field_out, ldo, z, rays, K, white_bkgd, weights, rgb, embed, depth, sigma_noise, ru);
   else if (D == 512 && aligned && smem <= 48 * 1024)
     composite_fwd_fast_kernel<4><<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
-        field_out, ldo, z, rays, K, white_bkgd, weights, rgb, embed, depth, sigma_noise);
+        field_out, ldo, z, rays, K, white_bkgd, weights, rgb, embed, depth, sigma_noise, ru);
   else
     composite_fwd_kernel<<<R, kRayWarps * kWarp, smem, as_stream(stream)>>>(
-        field_out, ldo, z, rays, R, K, D, white_bkgd, weights, rgb, embed, depth, sigma_noise);
+        field_out, ldo, z, rays, R, K, D, white_bkgd, weights, rgb, embed, depth, sigma_noise, ru);
   }
   NRF_LAUNCH_OK();
   return NRF_OK;
@@ -507,11 +583,19 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
                                  int R, int K, int D, int white_bkgd, const float* d_rgb,
                                  const float* d_embed, const float* d_depth, const float* d_weights,
                                  void* d_field, int ldg, int out_bf16, float* d_z, const float* sigma_noise,
-                                 void* stream) {
+                                 const NrfCompositeReuse* reuse, int accumulate, void* stream) {
   NRF_REQUIRE(field_out && z && rays && d_rgb && d_embed && d_field, NRF_EINVAL,
               "nrf_composite_bwd: null pointer");
   int rc = check_composite("nrf_composite_bwd", R, K, D, ldo);
   if (rc) return rc;
+  NrfReuseDev ru{nullptr, nullptr, 0, nullptr, 0};
+  if (reuse) {
+    NRF_REQUIRE(reuse->field_new && reuse->perm && reuse->d_field_new && reuse->n_first > 0 && reuse->n_first < K,
+                NRF_EINVAL, "nrf_composite_bwd: reuse needs field_new, perm, d_field_new and 0 < n_first < K");
+    NRF_REQUIRE(!accumulate, NRF_EINVAL, "nrf_composite_bwd: accumulate and reuse are exclusive");
+    ru = NrfReuseDev{reuse->field_new, reuse->perm, reuse->n_first, reuse->d_field_new, 0};
+  }
+  ru.accumulate = accumulate ? 1 : 0;
   NRF_REQUIRE(ldg >= 4 + D && ldg % 4 == 0, NRF_EINVAL, "nrf_composite_bwd: ldg=%d", ldg);
   size_t smem = (size_t)6 * K * sizeof(float);
   dim3 grid(R), block(kRayWarps * kWarp);
@@ -525,7 +609,7 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
 #define NRF_CBWD_FAST(DV, T)                                                                                   \
     composite_bwd_fast_kernel<DV, T><<<grid, block, smem_fast, as_stream(stream)>>>(                          \
         field_out, ldo, z, rays, K, white_bkgd, d_rgb, d_embed, d_depth, d_weights, reinterpret_cast<T*>(d_field), \
-        ldg, d_z, sigma_noise)
+        ldg, d_z, sigma_noise, ru)
     if (D == 384) { if (out_bf16) NRF_CBWD_FAST(3, __nv_bfloat16); else NRF_CBWD_FAST(3, float); }
     else { if (out_bf16) NRF_CBWD_FAST(4, __nv_bfloat16); else NRF_CBWD_FAST(4, float); }
 #undef NRF_CBWD_FAST
@@ -536,7 +620,7 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
     { LaunchScope ls_(NRF_CAT_COMPOSITE_BWD, as_stream(stream));
     composite_bwd_kernel<__nv_bfloat16><<<grid, block, smem, as_stream(stream)>>>(
         field_out, ldo, z, rays, R, K, D, white_bkgd, d_rgb, d_embed, d_depth, d_weights,
-        reinterpret_cast<__nv_bfloat16*>(d_field), ldg, d_z, sigma_noise);
+        reinterpret_cast<__nv_bfloat16*>(d_field), ldg, d_z, sigma_noise, ru);
     }
   } else {
     if (smem > 48 * 1024)
@@ -545,7 +629,7 @@ extern "C" int nrf_composite_bwd(const float* field_out, int ldo, const float* z
     { LaunchScope ls_(NRF_CAT_COMPOSITE_BWD, as_stream(stream));
     composite_bwd_kernel<float><<<grid, block, smem, as_stream(stream)>>>(
         field_out, ldo, z, rays, R, K, D, white_bkgd, d_rgb, d_embed, d_depth, d_weights,
-        reinterpret_cast<float*>(d_field), ldg, d_z, sigma_noise);
+        reinterpret_cast<float*>(d_field), ldg, d_z, sigma_noise, ru);
     }
   }
   NRF_LAUNCH_OK();

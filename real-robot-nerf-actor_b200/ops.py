@@ -203,7 +203,21 @@ def scatter_volume_grad_merged(rays, rays_per_scene, passes, grad, channels_firs
 
 
 # ------------------------------------------------------------------------------- compositing
-def composite_fwd(field_out, z, rays, D, white_bkgd=False, sigma_noise=None):
+def _reuse_struct(reuse, K, ld, d_field_new=None):
+    """reuse = (field_new (R*n_new, ld) fp32, perm (R,K) int32, n_first) -> NrfCompositeReuse (kept alive by the caller)."""
+    if reuse is None:
+        return None
+    field_new, perm, n_first = reuse
+    field_new = _f32(field_new, "field_new")
+    assert perm.is_cuda and perm.dtype == torch.int32 and perm.is_contiguous() and perm.shape[1] == K
+    assert field_new.shape[1] == ld and 0 < n_first < K
+    st = _lib.NrfCompositeReuse()
+    st.field_new, st.perm, st.n_first = field_new.data_ptr(), perm.data_ptr(), int(n_first)
+    st.d_field_new = d_field_new.data_ptr() if d_field_new is not None else None
+    return st
+
+
+def composite_fwd(field_out, z, rays, D, white_bkgd=False, sigma_noise=None, reuse=None):
     """neural_rendering.py:339-359 on RAW MLP outputs (N, 4+D).  -> weights, rgb, embed, depth.
     sigma_noise (R,K): training-time density noise, already scaled by noise_std (neural_rendering.py:336-337)."""
     if sigma_noise is not None:
@@ -214,20 +228,24 @@ def composite_fwd(field_out, z, rays, D, white_bkgd=False, sigma_noise=None):
     rays = _f32(rays, "rays")
     R, K = z.shape
     dev = z.device
+    ru = _reuse_struct(reuse, K, field_out.shape[1])
     w = torch.empty(R, K, device=dev, dtype=torch.float32)
     rgb = torch.empty(R, 3, device=dev, dtype=torch.float32)
     emb = torch.empty(R, D, device=dev, dtype=torch.float32)
     dep = torch.empty(R, device=dev, dtype=torch.float32)
     check(_lib.load().nrf_composite_fwd(ptr(field_out), field_out.shape[1], ptr(z), ptr(rays), R, K, D,
                                         int(white_bkgd), ptr(w), ptr(rgb), ptr(emb), ptr(dep), ptr(sigma_noise),
-                                        stream_ptr()),
+                                        C.byref(ru) if ru is not None else None, stream_ptr()),
           "nrf_composite_fwd")
     return w, rgb, emb, dep
 
 
 def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights=None, ldg=None,
-                  precision=NRF_PREC_BF16, white_bkgd=False, want_dz=False, out=None, sigma_noise=None):
-    """Closed-form backward; returns d_field (N, ldg) (operand-typed) and optionally d_z (R,K)."""
+                  precision=NRF_PREC_BF16, white_bkgd=False, want_dz=False, out=None, sigma_noise=None,
+                  reuse=None, out_new=None, accumulate=False):
+    """Closed-form backward; returns d_field (N, ldg) (operand-typed) and optionally d_z (R,K).
+    reuse = (field_new, perm, n_first): the reused samples' gradient rows are written to `out` (R*n_first, ldg), the
+    new samples' rows to `out_new` (R*(K-n_first), ldg); both returned.  accumulate: add to what `out` holds."""
     field_out = _f32(field_out, "field_out")
     z = _f32(z, "z")
     rays = _f32(rays, "rays")
@@ -239,13 +257,25 @@ def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights
     R, K = z.shape
     if ldg is None:
         ldg = (4 + D + 63) // 64 * 64
-    if out is None:
+    ru = None
+    if reuse is not None:
+        n_first = reuse[2]
+        if out is None:
+            out = torch.empty(R * n_first, ldg, device=z.device, dtype=act_dtype(precision))
+        assert out.shape == (R * n_first, ldg) and out.dtype == act_dtype(precision) and not accumulate
+        if out_new is None:
+            out_new = torch.empty(R * (K - n_first), ldg, device=z.device, dtype=act_dtype(precision))
+        ru = _reuse_struct(reuse, K, field_out.shape[1], out_new)
+    elif out is None:
         out = torch.empty(R * K, ldg, device=z.device, dtype=act_dtype(precision))
     dz = torch.empty(R, K, device=z.device, dtype=torch.float32) if want_dz else None
     check(_lib.load().nrf_composite_bwd(ptr(field_out), field_out.shape[1], ptr(z), ptr(rays), R, K, D,
                                         int(white_bkgd), ptr(d_rgb), ptr(d_embed), ptr(d_depth),
                                         ptr(d_weights), ptr(out), ldg, int(precision == NRF_PREC_BF16),
-                                        ptr(dz), ptr(sigma_noise), stream_ptr()), "nrf_composite_bwd")
+                                        ptr(dz), ptr(sigma_noise), C.byref(ru) if ru is not None else None,
+                                        int(accumulate), stream_ptr()), "nrf_composite_bwd")
+    if reuse is not None:
+        return (out, out_new, dz) if want_dz else (out, out_new)
     return (out, dz) if want_dz else out
 
 

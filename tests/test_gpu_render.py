@@ -261,6 +261,48 @@ def test_fused_loss_equals_the_torch_losses(ops, NR):
         assert rel(a[2][k], b[2][k]) < 1e-5, k
 
 
+@pytest.mark.parametrize("name,precision", [("small_kfd0", "fp32"), ("small_kfd4", "fp32"), ("small_noise_wb", "fp32"),
+                                            ("full_s32", "fp32"), ("full_s32", "bf16")])
+def test_reuse_coarse_evals_is_bit_identical_forward_and_equal_backward(ops, NR, name, precision):
+    """reuse_coarse_evals: the fine pass evaluates only its new samples and composites the coarse ones from the coarse
+    pass's outputs.  Same point, view direction and MLP -> every rendered output is BIT-identical to the reference
+    schedule (all Kc+Kf samples evaluated again); gradients agree to rounding (a reused sample goes through the MLP
+    backward once with the summed upstream gradient instead of twice)."""
+    fx = golden(name)
+    meta = [int(v) for v in fx["meta"]]
+    if name == "full_s32":
+        inp = syn_case_inputs(fx)
+        params, vol0, rays, noise = inp["params"], inp["vol"], inp["rays"], inp["noise"]
+        gt_rgb, gt_emb = inp["gt_rgb"], inp["gt_embed"]
+        opts = {}
+    else:
+        ci = _case_inputs(fx)
+        params, vol0, rays, noise = ci["params"], T(fx["vol"]), T(fx["rays"]), ci["noise"]
+        idx = T(fx["idx"])
+        gt_rgb = T(fx["gt_rgb_img"]).reshape(ci["SB"], -1, 3)[:, idx]
+        gt_emb = T(fx["gt_embed_img"]).reshape(ci["SB"], -1, ci["D"])[:, idx]
+        opts = {}
+        if "opts" in fx.files:
+            opts = dict(noise_std=float(fx["opts"][0]), white_bkgd=bool(fx["opts"][1]), lindisp=bool(fx["opts"][2]))
+    res = {}
+    for reuse in (False, True):
+        ren = make_renderer(NR, meta, params, precision, **opts)
+        ren.reuse_coarse_evals = reuse
+        ren.deterministic = True
+        res[reuse] = _run_cuda(ren, vol0, rays, noise, gt_rgb, gt_emb)
+    (o0, l0, v0, g0), (o1, l1, v1, g1) = res[False], res[True]
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "weights", "z"):
+            assert torch.equal(o0[lvl][k], o1[lvl][k]), (lvl, k)
+    assert torch.equal(l0, l1)
+    tol = 2e-5 if precision == "fp32" else 3e-2       # bf16: d_field of a reused sample is rounded after the sum
+    assert rel(v1, v0) < tol, rel(v1, v0)
+    for k in g0:
+        assert rel(g1[k], g0[k]) < tol, (k, rel(g1[k], g0[k]))
+    if name == "small_kfd4":                      # and against the reference's own gradients
+        assert rel(v1, T(fx["vgrad"])) < 2e-4
+
+
 def test_sorted_scatter_end_to_end_and_separate_fine_mlp(ops, NR):
     """scatter="sorted" gives the same volume gradient (bit-reproducible run to run); share_mlp=False trains
     two MLPs (models_embed.py:115-120)."""
