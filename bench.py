@@ -203,6 +203,15 @@ def run_ours(args):
     # end-to-end: host (pinned) inputs copied in, loss read back, every step
     step(True)
     ms_e2e = timed(args.steps, True)
+    # optional mode, reported beside the headline and never mixed into it: the fine pass reuses the coarse pass's
+    # field evaluations (bit-identical rendering; the MLP runs on Kc + Kf instead of Kc + (Kc + Kf) samples per ray)
+    ms_reuse = None
+    if not args.no_reuse_line:
+        ren.reuse_coarse_evals = True
+        for _ in range(2):
+            step(False)
+        ms_reuse = timed(args.steps, False)
+        ren.reuse_coarse_evals = False
 
     evals_step = wl.evals * world
     ms_step = ms_total / args.steps
@@ -254,6 +263,12 @@ def run_ours(args):
                     "note": "poses, focal, gt_rgb, gt_embed copied from pinned host memory each step (side stream; the targets "
                             "are awaited right before the losses); loss read back; the voxel volume is device-resident "
                             "as in the reference (PerAct encoder output)"},
+            "reuse_coarse_evals": None if ms_reuse is None else {
+                "ms_per_step": round(ms_reuse / args.steps, 3),
+                "value": round(evals_step / (ms_reuse / args.steps * 1e-3), 1), "unit": "ray-samples/s",
+                "mlp_evals_per_step": world * SB * n_rays * (wl.n_coarse + wl.n_fine),
+                "note": "opt-in NeuralRenderer.reuse_coarse_evals=True: same rendered samples per step (value counts "
+                        "them as the headline does), the MLP evaluates each distinct sample once; NOT the headline"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_ms_per_step": kernel_ms,
             "ms_per_step_with_kernel_events": round(ms_total_ev / args.steps, 3)}
     if rank == 0:
@@ -341,6 +356,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=128, dest="cpu_rays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reuse-line", action="store_true", dest="no_reuse_line")
     ap.add_argument("--scatter", default="sorted", choices=["atomic", "sorted"])
     ap.add_argument("--volume-layout", default="contiguous", choices=["contiguous", "channels_last_3d"],
                     dest="volume_layout", help="memory format of the voxel volume handed to the renderer (default: "
