@@ -155,6 +155,16 @@ int nrf_render_loss(const float* rgb_c, const float* rgb_f, const float* emb_c, 
                     const int64_t* idx, float* partial, float* terms, float* d_rgb_c, float* d_rgb_f,
                     float* d_emb_c, float* d_emb_f, void* stream);
 
+/* ---- voxelizer: the producer of the grid the volume is encoded from (voxel_grid_real.py:175-233) -----------
+ * VoxelGrid.coords_to_bounding_voxel_grid: coords (B,N,3), feats (B,N,F) or NULL (F = 0), geom (B,6) device =
+ * [bb_min - res | res + 1e-12] per scene (res = (bb_max - bb_min) / S, computed by the caller in fp32 as the
+ * reference does, :176-186) -> out (B,S,S,S,3+F+3+1) = [mean xyz, mean feats, voxel index / S, occupancy].
+ * Points of a voxel are added in ascending point index (the CPU reference's order); no float atomics.  F <= 13.
+ * workspace: nrf_voxelize_workspace_bytes(B, N, S). */
+int64_t nrf_voxelize_workspace_bytes(int B, int N, int S);
+int nrf_voxelize(const float* coords, const float* feats, int B, int N, int F, const float* geom, int S,
+                 float* out, void* workspace, void* stream);
+
 /* ---- GEMM building block of the field MLP ----------------------------------------------------
  * v = resid + mask( [A0 | A1 | A2] . B^T + bias ),   B (N,K) row-major (nn.Linear layout)
  *   A[i] (M,K[i]) lda[i]: up to three operand matrices concatenated along K (K[i] = 0: unused)

@@ -83,12 +83,14 @@ _SIGNATURES = {
 }
 _SIGNATURES["nrf_scatter_volume_grad_sorted"] = [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p]
 _SIGNATURES["nrf_render_loss"] = [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p]
+_SIGNATURES["nrf_voxelize"] = [_p, _p, _i, _i, _i, _p, _i, _p, _p, _p]
 _SIGNATURES["nrf_scatter_volume_grad_merged"] = [_p, _i, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i,
                                                  _p, _p, _p]
 _SIGNATURES["nrf_timing_begin"] = []
 _SIGNATURES["nrf_timing_end"] = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
 EXPORTS = sorted(list(_SIGNATURES) + ["nrf_version", "nrf_last_error", "nrf_wgrad_workspace_bytes",
-                                      "nrf_launch_count", "nrf_scatter_sorted_workspace_bytes"])
+                                      "nrf_launch_count", "nrf_scatter_sorted_workspace_bytes",
+                                      "nrf_voxelize_workspace_bytes"])
 TIMING_CATEGORIES = ["gemm_tc", "wgrad_tc", "encode", "composite_fwd", "composite_bwd", "scatter", "transpose",
                      "colsum", "sampling", "simt", "misc", "fused_fwd", "fused_bwd"]
 
@@ -118,6 +120,8 @@ def load():
     lib.nrf_wgrad_workspace_bytes.restype = C.c_int64
     lib.nrf_scatter_sorted_workspace_bytes.argtypes = [_i64, _i, _i64]
     lib.nrf_scatter_sorted_workspace_bytes.restype = C.c_int64
+    lib.nrf_voxelize_workspace_bytes.argtypes = [_i, _i, _i]
+    lib.nrf_voxelize_workspace_bytes.restype = C.c_int64
     lib.nrf_launch_count.argtypes = []
     lib.nrf_launch_count.restype = C.c_int64
     _lib = lib

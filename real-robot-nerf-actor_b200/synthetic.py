@@ -118,3 +118,17 @@ def init_mlp_(mlp, seed=0):
                 fan_in = p.shape[1]
                 p.copy_((torch.randn(p.shape, generator=g) * math.sqrt(2.0 / fan_in)).to(p.device))
     return mlp
+
+
+def voxelizer_points(B, N, F, seed):
+    """Clustered synthetic point cloud (several points per voxel, some outside the bounds, exact face hits)."""
+    g = torch.Generator().manual_seed(seed)
+    b = torch.tensor(BOUNDS)
+    centres = torch.rand(B, 12, 3, generator=g) * (b[3:] - b[:3]) + b[:3]
+    which = torch.randint(12, (B, N), generator=g)
+    coords = torch.gather(centres, 1, which.unsqueeze(-1).expand(-1, -1, 3)) + 0.03 * torch.randn(B, N, 3, generator=g)
+    coords[:, :8] = torch.rand(B, 8, 3, generator=g) * 3.0 - 1.0            # far outside
+    coords[:, 8] = b[:3]                                                    # exactly on the lower corner
+    coords[:, 9] = b[3:]                                                    # exactly on the upper corner
+    feats = torch.rand(B, N, F, generator=g)
+    return coords, feats

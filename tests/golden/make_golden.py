@@ -15,6 +15,8 @@ Cases
                             inputs are regenerated from seeds (synthetic.py / init_params), only
                             outputs and gradient projections are stored.
   raygen                  : gen_rays for 60x80 (focal 76.18187) and rows of 128x128 (focal 153).
+  voxelize_small          : the reference's VoxelGrid.coords_to_bounding_voxel_grid (voxel_grid_real.py) on a seeded
+                            clustered point cloud (inputs regenerated from the seed by synthetic.voxelizer_points).
 """
 import importlib
 import os
@@ -164,8 +166,25 @@ def run_raygen():
     print("raygen_pe done")
 
 
+def run_voxelizer():
+    """voxelize_small.npz: the reference's VoxelGrid (voxel_grid_real.py, imports torch + numpy only) on CPU."""
+    sys.path.insert(0, "/root/reference")
+    import voxel_grid_real as V
+    B, N, F, S = 2, 6000, 3, 10
+    coords, feats = syn.voxelizer_points(B, N, F, seed=11)
+    vg = V.VoxelGrid(coord_bounds=syn.BOUNDS, voxel_size=S, device="cpu", batch_size=B, feature_size=F,
+                     max_num_coords=N)
+    out = vg.coords_to_bounding_voxel_grid(coords, coord_features=feats, coord_bounds=torch.tensor(syn.BOUNDS)[None])
+    out_default_bounds = vg.coords_to_bounding_voxel_grid(coords, coord_features=feats)
+    assert torch.equal(out, out_default_bounds)
+    np.savez_compressed(os.path.join(HERE, "voxelize_small.npz"), meta=np.array([B, N, F, S, 11]),
+                        out=out.numpy())
+    print("voxelize_small done", tuple(out.shape), "occupied", int(out[..., -1].sum()))
+
+
 if __name__ == "__main__":
     run_raygen()
+    run_voxelizer()
     run_case("small_kfd0", S=12, C=16, D=24, hidden=64, SB=2, n_rays=48, Kc=16, Kf=16, Kfd=0,
              H=16, W=16, focal=19.0, store_inputs=True)
     run_case("small_kfd4", S=12, C=16, D=24, hidden=64, SB=2, n_rays=48, Kc=16, Kf=16, Kfd=4,

@@ -529,3 +529,39 @@ def test_render_loss_matches_mse_loss_and_its_autograd(ops, D, with_idx):
                                    gt_emb.cuda() if with_idx else t_emb.cuda(), idx.cuda() if with_idx else None,
                                    want_grads=False)
     assert none is None and torch.equal(terms, terms3)
+
+
+# ------------------------------------------------------------------------------ voxelizer
+def test_voxelizer_matches_the_reference_fixture_bitwise(ops):
+    """VoxelGrid.coords_to_bounding_voxel_grid on the GPU == the reference's own output (CPU), bit for bit."""
+    VG = load_pkg("voxel_grid")
+    fx = golden("voxelize_small")
+    B, N, F, S, seed = [int(v) for v in fx["meta"]]
+    coords, feats = syn.voxelizer_points(B, N, F, seed)
+    vg = VG.VoxelGrid(coord_bounds=syn.BOUNDS, voxel_size=S, device="cuda", batch_size=B, feature_size=F,
+                      max_num_coords=N).cuda()
+    out = vg.coords_to_bounding_voxel_grid(coords.cuda(), coord_features=feats.cuda())
+    assert torch.equal(out.cpu(), torch.from_numpy(fx["out"]))
+    only = vg.coords_to_bounding_voxel_grid(coords.cuda(), coord_features=feats.cuda(), only_features=True)
+    assert only.shape[-1] == 3 + F - 3 and torch.equal(only, out[..., :-7])
+    with pytest.raises(Exception):
+        vg.coords_to_bounding_voxel_grid(coords, coord_features=feats)          # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("B,N,F,S", [(2, 220000, 3, 100), (1, 5000, 0, 16), (3, 40000, 7, 33)])
+def test_voxelizer_matches_oracle_at_real_sizes(ops, B, N, F, S):
+    """PerAct sizes (<= 220 k points into 100^3, voxel_grid_real.py / train_nerfact_multi_kitchen.py:1131), per-scene
+    bounds, no features; bit-identical to the CPU oracle and run to run."""
+    from oracle import voxel_oracle as VO
+    VG = load_pkg("voxel_grid")
+    coords, feats = syn.voxelizer_points(B, N, max(F, 1), seed=N % 97)
+    feats = feats[..., :F] if F > 0 else None
+    bounds = torch.tensor(syn.BOUNDS).repeat(B, 1)
+    bounds[:, 3:] += 0.05 * torch.arange(B).view(B, 1)                           # different box per scene
+    ref = VO.voxelize(coords, feats, bounds, S)
+    vg = VG.VoxelGrid(coord_bounds=syn.BOUNDS, voxel_size=S, device="cuda", batch_size=B, feature_size=F,
+                      max_num_coords=N).cuda()
+    args = (coords.cuda(), feats.cuda() if feats is not None else None, bounds.cuda())
+    out = vg.coords_to_bounding_voxel_grid(*args)
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(out, vg.coords_to_bounding_voxel_grid(*args))

@@ -146,3 +146,16 @@ def syn_case_inputs(fx):
                 gt_rgb=gt_rgb_img.reshape(SB, -1, 3)[:, idx],
                 gt_embed=gt_embed_img.reshape(SB, -1, D)[:, idx], sign=sign,
                 gt_rgb_img=gt_rgb_img, gt_embed_img=gt_embed_img)
+
+
+def test_voxelizer_oracle_matches_the_reference_bitwise():
+    """oracle/voxel_oracle.py against the output of the reference's own VoxelGrid (tests/golden/voxelize_small.npz)."""
+    from oracle import voxel_oracle as VO
+    fx = golden("voxelize_small")
+    B, N, F, S, seed = [int(v) for v in fx["meta"]]
+    coords, feats = syn.voxelizer_points(B, N, F, seed)
+    out = VO.voxelize(coords, feats, syn.BOUNDS, S)
+    ref = T(fx["out"])
+    assert out.shape == ref.shape == (B, S, S, S, 3 + F + 4)
+    assert torch.equal(out, ref)
+    assert int(ref[..., -1].sum()) > 100                       # the case is not degenerate
