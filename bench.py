@@ -34,8 +34,8 @@ FLOP_FWD = 6_076_416          # per field evaluation
 FLOP_DGRAD = 6_033_408        # fwd minus the 42->512 input layer (no dgrad into PE / viewdirs)
 FLOP_WGRAD = 6_076_416
 FLOP_STEP = FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD     # 18 186 240
-# measured DRAM traffic of mlp_fused_kernel per launch at config 2 (ncu, profiles/r01b_fused_ncu.md):
-# (3.609 + 7.261 + 6.692 + 3.319) GB over the 4 launches of a step
+# measured DRAM traffic of mlp_fused_kernel per launch at config 2 (ncu, profiles/r01c_fused_ncu.md):
+# (3.607 + 7.263 + 6.700 + 3.326) GB over the 4 launches of a step
 FUSED_DRAM_BYTES_PER_LAUNCH = 5.22e9
 
 
@@ -240,7 +240,7 @@ def run_ours(args):
     roof = {"bound": "tensor", "kernel": dom_name, "achieved": round(achieved, 1),
             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4),
             "traffic": FUSED_DRAM_BYTES_PER_LAUNCH if fused_n > 0 and args.workload == "config2" else None,
-            "traffic_source": "profiles/r01b_fused_ncu.md: dram__bytes_read.sum + dram__bytes_write.sum of the 4 "
+            "traffic_source": "profiles/r01c_fused_ncu.md: dram__bytes_read.sum + dram__bytes_write.sum of the 4 "
                               "mlp_fused_kernel launches of one config-2 step (ncu --set full), averaged per launch; "
                               "algorithmic bytes per launch = 5.13e9 (13.5 KB/eval forward, 12.7 KB/eval backward)",
             "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",

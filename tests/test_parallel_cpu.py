@@ -119,3 +119,28 @@ def test_renderer_keeps_reference_surface():
     with pytest.raises(Exception):                # CPU tensors are rejected: there is no CPU fallback
         ren.encode(None, None, None, torch.zeros(1, 128, 4, 4, 4), None, None)
         ren.forward_nerf(torch.zeros(1, 4, 8))
+
+
+def test_dropin_modules_resolve_under_the_reference_names():
+    """With dropin/ first on sys.path the reference scripts' own import lines (`from neural_rendering import
+    NeuralRenderer`, `from voxel_grid_real import VoxelGrid`) get the B200 classes; CPU tensors are refused."""
+    import importlib
+    import sys
+    d = os.path.join(ROOT, "real-robot-nerf-actor_b200", "dropin")
+    saved = {k: sys.modules.pop(k, None) for k in ("neural_rendering", "voxel_grid_real")}
+    sys.path.insert(0, d)
+    try:
+        nr = importlib.import_module("neural_rendering")
+        vg = importlib.import_module("voxel_grid_real")
+        assert nr.NeuralRenderer is load_pkg("neural_rendering").NeuralRenderer
+        assert vg.VoxelGrid is load_pkg("voxel_grid").VoxelGrid
+        grid = vg.VoxelGrid(coord_bounds=[-0.1, -0.3, -0.2, 0.8, 0.7, 0.7], voxel_size=10, device="cpu", batch_size=1,
+                            feature_size=3, max_num_coords=100)
+        with pytest.raises(Exception, match="CUDA"):
+            grid.coords_to_bounding_voxel_grid(torch.zeros(1, 100, 3), coord_features=torch.zeros(1, 100, 3))
+    finally:
+        sys.path.remove(d)
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
