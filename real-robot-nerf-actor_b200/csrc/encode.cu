@@ -50,6 +50,35 @@ __global__ void volume_transpose_kernel(const float* __restrict__ src, float* __
   }
 }
 
+// (SB, C, V) -> (SB, V, C) for C % 128 == 0: a CTA moves 128 channels x 32 voxels.  Every thread has 16 independent
+// 128 B-coalesced row loads in flight before the first shared-memory store (the 32x32 kernel above has 4), tile row
+// stride 129 floats: conflict-free in both directions; the voxel rows leave as four 128 B segments per warp store.
+__global__ void __launch_bounds__(256) volume_to_last_c128_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                  int C, int64_t V) {
+  __shared__ float tile[32][129];
+  const int lane = threadIdx.x % kWarp, wid = threadIdx.x / kWarp;
+  const int b = blockIdx.z;
+  const int64_t v0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 128;
+  const float* s = src + ((int64_t)b * C + c0) * V + v0;
+  float* d = dst + ((int64_t)b * V + v0) * C + c0;
+  const bool vok = v0 + lane < V;
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = vok ? __ldg(s + (int64_t)(wid + 8 * i) * V + lane) : 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tile[lane][wid + 8 * i] = x[i];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int v = wid * 4 + q;
+    if (v0 + v < V) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[(int64_t)v * C + lane + 32 * i] = tile[v][lane + 32 * i];
+    }
+  }
+}
+
 struct EncodeArgs {
   const float* rays;
   const float* z;
@@ -323,6 +352,13 @@ static int volume_transpose(const float* src, float* dst, int SB, int C, int64_t
                             void* stream) {
   NRF_REQUIRE(src && dst && SB > 0 && C > 0 && V > 0, NRF_EINVAL, "volume transpose: bad args");
   NRF_REQUIRE(SB <= 65535 && (C + 31) / 32 <= 65535, NRF_ENOSUP, "volume transpose: grid too large");
+  if (to_last && C % 128 == 0) {
+    dim3 grid128((unsigned)((V + 31) / 32), (unsigned)(C / 128), (unsigned)SB);
+    LaunchScope ls_(NRF_CAT_TRANSPOSE, as_stream(stream));
+    volume_to_last_c128_kernel<<<grid128, 256, 0, as_stream(stream)>>>(src, dst, C, V);
+    NRF_LAUNCH_OK();
+    return NRF_OK;
+  }
   dim3 block(32, 8);
   dim3 grid((unsigned)((V + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)SB);
   if (to_last)

@@ -106,9 +106,11 @@ def test_sort_rows(ops, K):
 
 
 # ---------------------------------------------------------------------------------- volume
-def test_volume_transpose_roundtrip(ops):
+@pytest.mark.parametrize("C,dims", [(20, (7, 9, 11)), (128, (7, 9, 11)), (256, (8, 8, 8)), (128, (5, 3, 2))])
+def test_volume_transpose_roundtrip(ops, C, dims):
+    """C % 128 == 0 takes the 128-channel x 32-voxel kernel (ragged voxel tails included), other widths the 32x32 one."""
     g = torch.Generator().manual_seed(0)
-    v = torch.randn(2, 20, 7, 9, 11, generator=g).cuda()
+    v = torch.randn(2, C, *dims, generator=g).cuda()
     cl = ops.volume_to_channels_last(v)
     assert torch.equal(cl, v.permute(0, 2, 3, 4, 1).contiguous())
     assert torch.equal(ops.volume_to_channels_first(cl), v)
