@@ -274,9 +274,58 @@ def run_ours(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(rays=args.cpu_rays, reps=1)
+            if wl.train:
+                line["eager_gpu_baseline"] = eager_gpu_baseline(dev, wl)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def eager_gpu_baseline(dev, wl, steps=2):
+    """The reference's algorithm as eager PyTorch on the SAME GPU: the oracle restatement (oracle/nerf_oracle.py --
+    the reference's own ATen ops: F.grid_sample, F.linear, cumprod, sort, searchsorted, in the reference's chunks of
+    eval_batch_size points) at the FULL config-2 step, fp32 (TF32 off, as in the reference).  Reported only; the
+    reference itself cannot travel to the GPU box (/root/reference is absent there)."""
+    import torch
+    from oracle import nerf_oracle as O
+    syn = importlib.import_module(PKG + ".synthetic")
+    try:
+        SB, n_rays = wl.SB, wl.rays_per_scene
+        params = {k: v.requires_grad_(True) for k, v in
+                  O.init_params(d_in=42, d_latent=wl.C, d_hidden=512, d_out=4 + wl.D, seed=0, device=dev).items()}
+        g = torch.Generator(device=dev).manual_seed(7)
+        vol = (torch.randn(SB, wl.C, wl.S, wl.S, wl.S, device=dev, generator=g) * 0.1).requires_grad_(True)
+        rays_all = O.gen_rays(syn.arc_poses(SB).to(dev), wl.W, wl.H, torch.tensor(wl.focal), 1.2, 4.0).reshape(SB, -1, 8)
+        gt_rgb, gt_emb = (t.to(dev) for t in syn.make_targets(SB, n_rays, wl.D))
+
+        def step(i):
+            vol.grad = None
+            for p in params.values():
+                p.grad = None
+            idx = syn.pick_ray_indices(wl.H * wl.W, n_rays, seed=i).to(dev)
+            noise = {k: v.to(dev) for k, v in syn.make_noise(SB * n_rays, wl.n_coarse, wl.n_fine, seed=i).items()}
+            out = O.forward_nerf(params, vol, rays_all[:, idx], syn.BOUNDS, wl.n_coarse, wl.n_fine, noise=noise)
+            O.rendering_loss(out, gt_rgb, gt_emb)["loss"].backward()
+
+        step(0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            step(i + 1)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+        del params, vol
+        torch.cuda.empty_cache()
+        return {"value": round(wl.evals / (ms * 1e-3), 1), "unit": "ray-samples/s", "ms_per_step": round(ms, 1),
+                "kind": "port", "peak_mem_gib": round(peak, 1),
+                "sample": f"oracle port in eager PyTorch (fp32, reference chunking) on the same B200: the full "
+                          f"{wl.name} step, {SB} x {n_rays} rays x ({wl.n_coarse} + {wl.n_coarse + wl.n_fine}) samples, "
+                          f"mean of {steps} steps"}
+    except Exception as e:                      # reported, never fatal for the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
 # ------------------------------------------------------------------ CPU baseline / reference arm
