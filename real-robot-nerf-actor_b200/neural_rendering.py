@@ -298,6 +298,77 @@ class PixelNeRFEmbedNet(nn.Module):
                 c = c.unsqueeze(-1).repeat((1, 2))
         self.c = c
 
+    def forward(self, xyz, coarse=True, viewdirs=None, far=False, ret_last_feat=False, precision="bf16"):
+        """models_embed.py:295-471: the field at world points.  xyz, viewdirs (SB, B, 3) ->
+        (output (SB, B, 4 + d_embed) = [sigmoid(rgb), relu(sigma), embed], point_density = None).  Call encode() first.
+        Differentiable w.r.t. the encoded volume and the MLP parameters."""
+        if ret_last_feat:
+            raise NotImplementedError("ret_last_feat=True is off in nerfact.conf and not built")
+        if viewdirs is None:
+            raise NotImplementedError("use_viewdirs=False (neural_rendering.py:294-295 raises too)")
+        if self.voxel_feat is None:
+            raise RuntimeError("call encode() before forward()")
+        SB, B, _ = xyz.shape
+        if self.voxel_feat.shape[0] != SB:
+            raise RuntimeError("grid_sampler(): expected grid and input to have same batch size, "
+                               f"but got input with sizes {list(self.voxel_feat.shape)} and {SB} point batches")
+        prec = ops.PRECISIONS[precision] if isinstance(precision, str) else precision
+        mlp = self.mlp_coarse if coarse or self.mlp_fine is None else self.mlp_fine
+        h = mlp.handle(prec)
+        rays = torch.zeros(SB * B, 8, device=xyz.device, dtype=torch.float32)
+        rays[:, 0:3] = xyz.reshape(-1, 3)
+        rays[:, 3:6] = viewdirs.reshape(-1, 3)
+        ps = [dict(mlp.named_parameters())[n] for n in h.names()]
+        keep = torch.is_grad_enabled() and (self.voxel_feat.requires_grad or any(p.requires_grad for p in ps))
+        bounds = torch.as_tensor(self.coordinate_bounds, dtype=torch.float32).reshape(-1).cpu()
+        raw = _FieldFn.apply(self, h, bounds, self.voxel_feat, rays, SB, keep, *ps)
+        out = torch.cat([torch.sigmoid(raw[:, :3]), torch.relu(raw[:, 3:4]), raw[:, 4:]], -1)     # :444-466
+        return out.reshape(SB, B, -1), None
+
+
+class _FieldFn(torch.autograd.Function):
+    """The field at explicit points (PixelNeRFEmbedNet.forward, models_embed.py:295-471): points are handed to the
+    encode kernel as zero-length rays (origin = point, direction = view direction, z = 0: o + 0 * d is exact), so
+    gather, positional encoding, MLP and the volume-gradient scatter are the kernels of the render path.
+    -> raw MLP outputs (SB*n, 4+D); no gradient w.r.t. the points (world_to_canonical is @no_grad, :185)."""
+
+    @staticmethod
+    def forward(ctx, model, h, bounds, voxel_feat, rays, sb, keep, *params):
+        cl3d = _is_channels_last_3d(voxel_feat)
+        vol_cl = voxel_feat.permute(0, 2, 3, 4, 1) if cl3d else ops.volume_to_channels_last(voxel_feat)
+        n = rays.shape[0]
+        z = torch.zeros(n, 1, device=rays.device, dtype=torch.float32)
+        field_in = ops.encode_points(rays, z, n // sb, vol_cl, bounds, model.code.num_freqs,
+                                     float(model.code.freq_factor), ld_out=h.sizes.kin_pad, precision=h.precision)
+        out, acts = h.forward(field_in, keep_acts=keep)
+        if keep:
+            ctx.h, ctx.field_in, ctx.acts, ctx.rays, ctx.z = h, field_in, acts, rays, z
+            ctx.vol_shape, ctx.cl3d, ctx.sb, ctx.bounds = tuple(vol_cl.shape), cl3d, sb, bounds
+        return out[:, :model.d_out]
+
+    @staticmethod
+    def backward(ctx, d_out):
+        h = ctx.h
+        n = ctx.rays.shape[0]
+        d_field = torch.zeros(n, h.sizes.dout_pad, device=d_out.device, dtype=ops.act_dtype(h.precision))
+        d_field[:, :d_out.shape[1]] = d_out.to(d_field.dtype)
+        names = h.names()
+        grads = _zero_grads(h)
+        dlat = h.backward(ctx.field_in, ctx.acts, d_field, grads)
+        d_vol = None
+        if ctx.needs_input_grad[3]:
+            SB, S0, S1, S2, C = ctx.vol_shape
+            if C in (64, 128):
+                g = torch.empty(ctx.vol_shape if ctx.cl3d else (SB, C, S0, S1, S2), device=d_out.device,
+                                dtype=torch.float32)
+                ops.scatter_volume_grad_merged(ctx.rays, n // ctx.sb, [(ctx.z, dlat)], g, not ctx.cl3d, ctx.bounds)
+                d_vol = g.permute(0, 4, 1, 2, 3) if ctx.cl3d else g
+            else:
+                g = torch.empty(ctx.vol_shape, device=d_out.device, dtype=torch.float32)
+                ops.scatter_volume_grad_sorted(ctx.rays, ctx.z, n // ctx.sb, dlat, g, ctx.bounds)
+                d_vol = g.permute(0, 4, 1, 2, 3) if ctx.cl3d else ops.volume_to_channels_first(g)
+        return (None, None, None, d_vol, None, None, None, *[grads[k] for k in names])
+
 
 # -------------------------------------------------------------------------- render passes
 class _PassState:

@@ -261,6 +261,45 @@ def test_ragged_shapes_forward_backward(ops, NR, SB, n_rays, Kc, Kf):
     assert rel(out16.coarse.rgb, out.coarse.rgb) < 3e-2 and rel(out16.coarse.embed, out.coarse.embed) < 3e-2
 
 
+@pytest.mark.parametrize("precision,C", [("fp32", 128), ("fp32", 16), ("bf16", 128)])
+def test_model_forward_at_explicit_points(ops, NR, precision, C):
+    """PixelNeRFEmbedNet.forward(xyz, viewdirs=...) (models_embed.py:295-471) against the oracle's field(), forward and
+    the gradients into the volume and the MLP; points inside, on the faces of and outside the box."""
+    D, hidden, S, SB, n = (384, 512, 14, 2, 333) if C == 128 else (24, 64, 9, 2, 100)
+    meta = [S, C, D, hidden, SB, 8, 8, 8, 0, 16, 16, 3]
+    params = O.init_params(d_in=42, d_latent=C, d_hidden=hidden, d_out=4 + D, seed=3)
+    ren = make_renderer(NR, meta, params, precision)
+    g = torch.Generator().manual_seed(12)
+    b = torch.tensor(syn.BOUNDS)
+    xyz = (torch.rand(SB, n, 3, generator=g) * 1.3 - 0.15) * (b[3:] - b[:3]) + b[:3]
+    xyz[:, 0] = b[:3]
+    xyz[:, 1] = b[3:]
+    dirs = torch.nn.functional.normalize(torch.randn(SB, n, 3, generator=g), dim=-1)
+    vol = syn.make_volume(SB, C, S, seed=3)
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    vr = vol.clone().requires_grad_(True)
+    ref = O.field(pr, vr, xyz, dirs, syn.BOUNDS)
+    w = torch.randn(ref.shape, generator=g)
+    (ref * w).sum().backward()
+    volc = vol.clone().cuda().requires_grad_(True)
+    ren.encode(None, None, None, volc, None, None, None)
+    out, dens = ren.nerf_model(xyz.cuda(), coarse=True, viewdirs=dirs.cuda(), precision=precision)
+    assert dens is None and out.shape == ref.shape
+    (out * w.cuda()).sum().backward()
+    grads = {k[len("nerf_model.mlp_coarse."):]: v.grad for k, v in ren.named_parameters()
+             if k.startswith("nerf_model.mlp_coarse.")}
+    if precision == "fp32":
+        assert rel(out, ref) < 1e-5
+        assert rel(volc.grad, vr.grad) < 1e-4
+        for k in pr:
+            assert rel(grads[k], pr[k].grad) < 2e-3, k          # a ReLU gate on the fence moves these, see the ragged test
+    else:
+        assert rel(out, ref) < 3e-2 and cosine(volc.grad, vr.grad) > 0.98
+    with torch.no_grad():
+        out2, _ = ren.nerf_model(xyz.cuda(), coarse=True, viewdirs=dirs.cuda(), precision=precision)
+    assert torch.equal(out2, out)
+
+
 def test_forward_loss_dict_and_rendering(ops, NR):
     """forward() returns the reference's keys/values; rendering() returns full images."""
     fx = golden("small_kfd0")
