@@ -274,15 +274,17 @@ def run_ours(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(rays=args.cpu_rays, reps=1)
-            if wl.train:
-                line["eager_gpu_baseline"] = eager_gpu_baseline(dev, wl)
+            if wl.train:                     # second half of the baseline leg: the same oracle port on the same GPU
+                line["cpu_baseline"]["eager_pytorch_same_gpu"] = eager_gpu_baseline(dev, wl)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def eager_gpu_baseline(dev, wl, steps=2):
-    """The reference's algorithm as eager PyTorch on the SAME GPU: the oracle restatement (oracle/nerf_oracle.py --
+    """Part of the baseline leg (`cpu_baseline.eager_pytorch_same_gpu`), the only other place besides cpu_baseline()
+    where bench.py executes oracle/ -- as the thing compared against, never on the product path.
+    The reference's algorithm as eager PyTorch on the SAME GPU: the oracle restatement (oracle/nerf_oracle.py --
     the reference's own ATen ops: F.grid_sample, F.linear, cumprod, sort, searchsorted, in the reference's chunks of
     eval_batch_size points) at the FULL config-2 step, fp32 (TF32 off, as in the reference).  Reported only; the
     reference itself cannot travel to the GPU box (/root/reference is absent there)."""
