@@ -20,7 +20,7 @@ it, neural_rendering.py:172,194,200,218; "perturb off" = zeros).
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 import torch.nn.functional as F

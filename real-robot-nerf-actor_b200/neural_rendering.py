@@ -17,7 +17,6 @@ Differences from the reference, all opt-in or invisible to its callers:
 """
 from __future__ import annotations
 
-import math
 
 import torch
 import torch.nn as nn

@@ -7,7 +7,7 @@ is an error.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+
 
 import torch
 

@@ -11,7 +11,7 @@ The reference's hot path is single-GPU; its ancestor shards the ray axis with nn
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Tuple
+from typing import List, Tuple
 
 import torch
 import torch.distributed as dist

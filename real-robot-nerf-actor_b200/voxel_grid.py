@@ -9,7 +9,6 @@ There is no CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
-import ctypes as C
 
 import torch
 from torch import nn

@@ -1,6 +1,6 @@
 """BASELINE config 3: novel-view full-image render, 5 cameras x 128x128 px, 64 + 64 samples, inference only,
 rays sharded over the ranks.  python scripts/run_config3.py   (or under torchrun for N > 1)"""
-import importlib, json, os, sys, time
+import importlib, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch

@@ -2,7 +2,6 @@
 CPU fp32) on the same seeded inputs.  Run on the B200 box: `pytest -m gpu`."""
 import math
 
-import numpy as np
 import pytest
 import torch
 

@@ -416,6 +416,37 @@ def test_reuse_coarse_evals_is_bit_identical_forward_and_equal_backward(ops, NR,
         assert rel(v1, T(fx["vgrad"])) < 2e-4
 
 
+@pytest.mark.parametrize("reuse", [False, True])
+def test_training_steps_do_not_grow_memory(ops, NR, reuse):
+    """Six full forward() + backward() steps (fused losses, LossDict read, both schedules): allocated memory after
+    step 6 equals that after step 3 -- no autograd cycle keeps a step's activations alive."""
+    import gc
+    fx = golden("full_s32")
+    meta = [int(v) for v in fx["meta"]]
+    S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
+    inp = syn_case_inputs(fx)
+    ren = make_renderer(NR, meta, inp["params"], "bf16")
+    ren.reuse_coarse_evals = reuse
+    vol = inp["vol"].cuda().requires_grad_(True)
+    poses = inp["poses"].cuda()
+    focal = torch.tensor(float(fx["focal"])).cuda()
+    gt_rgb, gt_emb = inp["gt_rgb_img"].cuda(), inp["gt_embed_img"].cuda()
+    marks = []
+    for i in range(6):
+        vol.grad = None
+        for p in ren.parameters():
+            p.grad = None
+        out = ren(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=vol, voxel_poses=poses,
+                  focal=focal, gt_rgb=gt_rgb, gt_depth=None, gt_pose=poses, c=None, lang_goal=None, gt_embed=gt_emb)
+        out["loss"].backward()
+        assert out["psnr"] == out["psnr"] and torch.isfinite(vol.grad).all()
+        del out
+        gc.collect()
+        torch.cuda.synchronize()
+        marks.append(torch.cuda.memory_allocated())
+    assert marks[5] == marks[2], marks
+
+
 def test_sorted_scatter_end_to_end_and_separate_fine_mlp(ops, NR):
     """scatter="sorted" gives the same volume gradient (bit-reproducible run to run); share_mlp=False trains
     two MLPs (models_embed.py:115-120)."""
