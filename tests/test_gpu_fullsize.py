@@ -122,6 +122,20 @@ def test_scatter_is_the_adjoint_of_the_gather_at_full_size(env):
         assert abs(lhs - rhs) <= 2e-6 * scale, (variant, lhs, rhs)
     # a sample inside the box really gathers something: the test is not vacuous
     assert float(lat.abs().sum()) > 0
+    # the merged scatter (the default of the training step): coarse + fine-sized pass in ONE sort, channel-first out
+    u = torch.rand(R, wl.n_fine, device="cuda", generator=g)
+    z2 = ops.sample_fine(rays, torch.rand(R, wl.n_coarse, device="cuda", generator=g), wl.n_coarse, u)
+    fin2 = ops.encode_points(rays, z2, wl.rays_per_scene, vol_cl, torch.tensor(syn.BOUNDS), precision=ops.NRF_PREC_FP32)
+    Y2 = torch.randn(R * wl.n_fine, wl.C, device="cuda", generator=g)
+    lhs2 = lhs + float((fin2[:, :wl.C].double() * Y2.double()).sum())
+    grad_cf = torch.full_like(env["vol"], 7.0)                               # garbage: every element must be rewritten
+    ops.scatter_volume_grad_merged(rays, wl.rays_per_scene, [(z, Y), (z2, Y2)], grad_cf, True, torch.tensor(syn.BOUNDS))
+    rhs2 = float((grad_cf.double() * env["vol"].double()).sum())
+    scale2 = scale + float((fin2[:, :wl.C].double().abs() * Y2.double().abs()).sum())
+    assert abs(lhs2 - rhs2) <= 2e-6 * scale2, (lhs2, rhs2)
+    again = torch.empty_like(grad_cf)
+    ops.scatter_volume_grad_merged(rays, wl.rays_per_scene, [(z, Y), (z2, Y2)], again, True, torch.tensor(syn.BOUNDS))
+    assert torch.equal(again, grad_cf), "bit-reproducible at full size"
 
 
 def test_backward_is_exactly_linear_in_the_upstream_gradient(env):
