@@ -135,6 +135,8 @@ def run_ours(args):
     poses_d, focal_d = poses_h.to(dev), focal_h.to(dev)
     gt_rgb_d, gt_emb_d = gt_rgb_h.to(dev), gt_emb_h.to(dev)
     params = [p for p in ren.parameters()]
+    if world > 1 and args.allreduce == "overlap":     # ONE NCCL all-reduce of the flat MLP gradient, started inside the
+        par.overlap_mlp_grad_allreduce(ren)           # backward: it runs under the volume-gradient scatter
 
     copy_stream = torch.cuda.Stream(device=dev)
 
@@ -164,7 +166,7 @@ def run_ours(args):
                   voxel_poses=poses, focal=focal, gt_rgb=gt_rgb, gt_depth=None, gt_pose=poses, c=None,
                   lang_goal=None, gt_embed=gt_emb)
         out["loss"].backward()
-        if world > 1:
+        if world > 1 and args.allreduce == "post":
             par.allreduce_mlp_grads(ren)
         return float(out["loss"].item()) if host_inputs else out["loss"]
 
@@ -257,7 +259,7 @@ def run_ours(args):
                                    f"{wl.S}^3 x {wl.C}ch volume, ResnetFC 512x5, RGB+{wl.D}d heads, fwd+bwd",
                        "evals_per_step": evals_step, "precision": args.precision, "scatter": args.scatter, "volume_layout": args.volume_layout,
                        "l2": "working set (1 GiB volume + ~20 GiB activations per step) >> 126 MB L2; no flush needed",
-                       "parallelism": f"dp{world} over scenes; NCCL all-reduce of MLP grads" if world > 1 else "single GPU"},
+                       "parallelism": f"dp{world} over scenes; one NCCL all-reduce of the MLP grads ({args.allreduce})" if world > 1 else "single GPU"},
             "e2e": {"value": round(e2e_value, 1), "unit": "ray-samples/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 * 8,
                     "note": "poses, focal, gt_rgb, gt_embed copied from pinned host memory each step (side stream; the targets "
@@ -408,6 +410,8 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=128, dest="cpu_rays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reuse-line", action="store_true", dest="no_reuse_line")
+    ap.add_argument("--allreduce", default="overlap", choices=["overlap", "post"],
+                    help="N > 1: MLP-gradient all-reduce started inside the backward (default) or after it")
     ap.add_argument("--scatter", default="sorted", choices=["atomic", "sorted"])
     ap.add_argument("--volume-layout", default="contiguous", choices=["contiguous", "channels_last_3d"],
                     dest="volume_layout", help="memory format of the voxel volume handed to the renderer (default: "

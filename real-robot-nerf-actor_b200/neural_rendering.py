@@ -489,17 +489,38 @@ def _is_channels_last_3d(t):
         t.is_contiguous(memory_format=torch.channels_last_3d)
 
 
+class _GradViews(dict):
+    """name -> gradient view; `.flat` is the one buffer behind all of them (what the all-reduce takes)."""
+    flat = None
+
+
 def _zero_grads(mlp: ops.FieldMLP):
     """Zeroed gradient buffers for every MLP parameter: ONE flat allocation / fill, views per parameter."""
     names = mlp.names()
     sizes = [mlp.params[n].numel() for n in names]
     dev = mlp.params[names[0]].device
     flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
-    out, off = {}, 0
+    out, off = _GradViews(), 0
+    out.flat = flat
     for n, sz in zip(names, sizes):
         out[n] = flat[off:off + sz].view_as(mlp.params[n])
         off += sz
     return out
+
+
+def _start_grad_allreduce(ren, grads_c, grads_f):
+    """If the data-parallel wrapper installed a hook (parallel.overlap_mlp_grad_allreduce), hand it the flat MLP
+    gradient buffer(s) of this step; it starts the (asynchronous) all-reduce and returns what to wait for."""
+    hook = getattr(ren, "_grad_allreduce", None)
+    if hook is None:
+        return None
+    flats = [grads_c.flat] + ([grads_f.flat] if grads_f is not grads_c else [])
+    return hook(flats)
+
+
+def _finish_grad_allreduce(pending):
+    if pending is not None:
+        pending()
 
 
 def _zeros_like_or(t, ref_shape, device):
@@ -597,11 +618,13 @@ class _ForwardNerfFn(torch.autograd.Function):
         if st_f is not None and st_f.base is not None:        # the fine pass reused the coarse evaluations
             _backward_reuse(ren, st_c, st_f, (d_cw, d_crgb, d_cemb, d_cdep), g[6:10], grads_c, defer, ctx.depth_mask,
                             grad_cl)
+            pending = _start_grad_allreduce(ren, grads_c, grads_c)
             d_vol = None
             if want_vol and merged:
                 d_vol = _finish_volume_grad(ren, st_c.rays, st_c.rps, defer, ctx.vol_shape, ctx.cl3d)
             elif want_vol:
                 d_vol = grad_cl.permute(0, 4, 1, 2, 3) if ctx.cl3d else ops.volume_to_channels_first(grad_cl)
+            _finish_grad_allreduce(pending)
             return (None, d_vol, None, None, None, None, None, *[grads_c[n] for n in names_c])
         d_cdep = _zeros_like_or(d_cdep, (R,), dev)
         if st_f is not None:
@@ -618,12 +641,15 @@ class _ForwardNerfFn(torch.autograd.Function):
                 d_cdep = d_cdep + (d_cat[:, K - Kfd:] * ctx.depth_mask).sum(-1)
         _pass_backward(ren, st_c, _zeros_like_or(d_crgb, (R, 3), dev), _zeros_like_or(d_cemb, (R, D), dev),
                        d_cdep, d_cw, grads_c, grad_cl, first=st_f is None, defer=defer)
+        # every MLP gradient of this step is final: start their all-reduce now, it overlaps the volume scatter
+        pending = _start_grad_allreduce(ren, grads_c, grads_f)
         d_vol = None
         if want_vol:
             if merged:
                 d_vol = _finish_volume_grad(ren, st_c.rays, st_c.rps, defer, ctx.vol_shape, ctx.cl3d)
             else:
                 d_vol = grad_cl.permute(0, 4, 1, 2, 3) if ctx.cl3d else ops.volume_to_channels_first(grad_cl)
+        _finish_grad_allreduce(pending)
         pg = [grads_c[n] for n in names_c]
         if not shared and st_f is not None:
             pg += [grads_f[n] for n in st_f.mlp.names()]

@@ -4,9 +4,10 @@ The reference's hot path is single-GPU; its ancestor shards the ray axis with nn
 (featurenerf_robo/featurenerf/src/render/nerf_embed.py:412-429).  Here:
   * inference (`render_sharded`): each rank renders a contiguous slice of the flattened ray list;
     the only exchange is the optional all_gather of the finished image rows;
-  * training (`allreduce_mlp_grads`): scenes (or ray slices) are data-parallel; the field MLP is
-    replicated, so its gradients are summed with ONE all_reduce over a flat fp32 buffer (12.2 MB at
-    the BASELINE dims).  The volume gradient stays local when each rank owns whole scenes;
+  * training (`overlap_mlp_grad_allreduce`, or `allreduce_mlp_grads` after the backward): scenes (or ray
+    slices) are data-parallel; the field MLP is replicated, so its gradients are summed with ONE all_reduce
+    over a flat fp32 buffer (12.2 MB at the BASELINE dims), started inside the backward so that it runs
+    under the volume-gradient scatter.  The volume gradient stays local when each rank owns whole scenes;
     `allreduce_volume_grad` covers the case of one scene split over ranks.
 """
 from __future__ import annotations
@@ -58,6 +59,32 @@ def allreduce_mlp_grads(module: torch.nn.Module, group=None, average: bool = Fal
             p.grad.copy_(flat[off:off + n].view_as(p))
         off += n
     return flat.numel() * flat.element_size()
+
+
+def overlap_mlp_grad_allreduce(renderer, group=None, average: bool = False, enabled: bool = True) -> None:
+    """Data-parallel training without a separate reduction step: the renderer's backward all-reduces the flat MLP
+    gradient buffer (ONE collective, 12.2 MB at the BASELINE dims) as soon as the last weight-gradient kernel of the
+    step is enqueued, so the collective runs under the volume-gradient scatter instead of after the backward
+    (SURVEY 8e).  The `.grad`s autograd hands out are already summed (or averaged) over the ranks: do NOT call
+    `allreduce_mlp_grads` as well.  Only the gradients produced by `forward_nerf` / `forward` are covered."""
+    if not enabled:
+        renderer._grad_allreduce = None
+        return
+
+    def start(flats):
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        works = [dist.all_reduce(f, op=dist.ReduceOp.SUM, group=group, async_op=True) for f in flats]
+
+        def finish():
+            for w in works:
+                w.wait()                       # the current stream waits; the host does not
+            if average:
+                for f in flats:
+                    f /= dist.get_world_size(group)
+        return finish
+
+    renderer._grad_allreduce = start
 
 
 def allreduce_volume_grad(grad: torch.Tensor, group=None) -> torch.Tensor:

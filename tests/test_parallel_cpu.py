@@ -52,6 +52,19 @@ def _worker(rank, world, port, out):
         for p, parts in zip((lin.weight, lin.bias, shared.weight, shared.bias), gathered):
             assert torch.allclose(p.grad, sum(parts))
         assert torch.equal(model["nograd"].weight.grad, torch.zeros(2, 2))
+        # the hook the renderer's backward calls with its flat gradient buffer(s)
+        class _R:
+            pass
+        r = _R()
+        par.overlap_mlp_grad_allreduce(r, average=True)
+        flats = [torch.full((5,), float(rank + 1)), torch.arange(3, dtype=torch.float32) * (rank + 1)]
+        finish = r._grad_allreduce(flats)
+        finish()
+        tot = float(sum(range(1, world + 1)))
+        assert torch.allclose(flats[0], torch.full((5,), tot / world))
+        assert torch.allclose(flats[1], torch.arange(3, dtype=torch.float32) * tot / world)
+        par.overlap_mlp_grad_allreduce(r, enabled=False)
+        assert r._grad_allreduce is None
         vol = torch.full((2, 3), float(rank + 1))
         par.allreduce_volume_grad(vol)
         assert torch.equal(vol, torch.full((2, 3), float(sum(range(1, world + 1)))))
