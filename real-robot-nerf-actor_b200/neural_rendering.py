@@ -718,6 +718,8 @@ class NeuralRenderer(nn.Module):
         self.reuse_coarse_evals = False        # True: the fine pass evaluates only its Kf new samples and composites
                                                # the Kc coarse ones from the coarse pass's outputs (bit-identical
                                                # rendering, 1/3 fewer MLP evaluations at Kc = Kf; needs share_mlp)
+        self._grad_allreduce = None            # set by parallel.overlap_mlp_grad_allreduce(): the backward all-reduces
+                                               # the flat MLP gradient buffer itself, under the volume scatter
         self.fused_loss = True                 # rgb / embed losses + their gradients in one kernel (nrf_render_loss)
         self.render_chunk_rays = 4096          # neural_rendering.py:482
         self._num_freqs = self.nerf_model.code.num_freqs
