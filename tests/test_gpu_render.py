@@ -187,23 +187,27 @@ def test_full_dims_golden(ops, NR, precision):
         assert e_vsum < 0.3 and worst_par < 0.3
 
 
-def _oracle_vs_cuda(NR, S, C, D, hidden, SB, n_rays, Kc, Kf, precision, seed, perturb=True, train=True):
+def _oracle_vs_cuda(NR, S, C, D, hidden, SB, n_rays, Kc, Kf, precision, seed, perturb=True, train=True, Kfd=0,
+                    reuse=False):
     """Seeded synthetic case through the oracle (CPU) and the CUDA renderer; returns both results."""
-    meta = [S, C, D, hidden, SB, n_rays, Kc, Kf, 0, 64, 64, seed]
+    meta = [S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, 64, 64, seed]
     params = O.init_params(d_in=42, d_latent=C, d_hidden=hidden, d_out=4 + D, seed=seed)
     vol = syn.make_volume(SB, C, S, seed=seed)
     poses = syn.arc_poses(SB)
     rays = O.gen_rays(poses, 64, 64, torch.tensor(76.5), 1.2, 4.0).reshape(SB, -1, 8)
     rays = rays[:, syn.pick_ray_indices(64 * 64, n_rays, seed=seed)]
-    noise = syn.make_noise(SB * n_rays, Kc, Kf, seed=seed, perturb=perturb) if Kf > 0 else \
+    noise = syn.make_noise(SB * n_rays, Kc, Kf - Kfd, seed=seed, perturb=perturb) if Kf > 0 else \
         ({"coarse": torch.rand(SB * n_rays, Kc, generator=torch.Generator().manual_seed(seed))} if perturb else {})
+    if Kfd > 0:
+        noise["depth"] = torch.randn(SB * n_rays, Kfd, generator=torch.Generator().manual_seed(seed + 1))
     gt_rgb, gt_emb = syn.make_targets(SB, n_rays, D)
     ren = make_renderer(NR, meta, params, precision)
+    ren.reuse_coarse_evals = reuse
     lv = ("coarse", "fine") if Kf > 0 else ("coarse",)
     if train:
         pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
         vr = vol.clone().requires_grad_(True)
-        ref = O.forward_nerf(pr, vr, rays, syn.BOUNDS, Kc, Kf, noise=noise)
+        ref = O.forward_nerf(pr, vr, rays, syn.BOUNDS, Kc, Kf, Kfd, noise=noise)
         loss_r = sum(((ref[l]["rgb"] - gt_rgb) ** 2).mean() + 0.01 * ((ref[l]["embed"] - gt_emb) ** 2).mean() for l in lv)
         loss_r.backward()
         volc = vol.clone().cuda().requires_grad_(True)
@@ -216,7 +220,7 @@ def _oracle_vs_cuda(NR, S, C, D, hidden, SB, n_rays, Kc, Kf, precision, seed, pe
                  if k.startswith("nerf_model.mlp_coarse.")}
         return ref, out, (vr.grad, {k: v.grad for k, v in pr.items()}), (volc.grad, grads)
     with torch.no_grad():
-        ref = O.forward_nerf(params, vol, rays, syn.BOUNDS, Kc, Kf, noise=noise)
+        ref = O.forward_nerf(params, vol, rays, syn.BOUNDS, Kc, Kf, Kfd, noise=noise)
         ren.eval()
         ren.encode(None, None, None, vol.cuda(), None, None, None)
         out = ren.forward_nerf(rays.cuda(), want_weights=True, noise={k: v.cuda() for k, v in noise.items()})
@@ -234,6 +238,28 @@ def test_config1_coarse_only_forward(ops, NR, precision):
     tol = 1e-4 if precision == "fp32" else 3e-2
     for k in ("rgb", "embed", "depth", "weights"):
         assert rel(out.coarse[k], ref["coarse"][k]) < tol, k
+
+
+@pytest.mark.parametrize("reuse", [False, True])
+def test_nerfact_conf_dims_forward_backward(ops, NR, reuse):
+    """The dims of the reference's own nerfact.conf (:22-28,:76: d_latent 64, d_embed 512, 64 coarse + 64 fine samples of
+    which 16 depth-guided, 512-ray chunks) through the full step: fused MLP kernel at 64 latent channels, compositing
+    fast path at D = 512, depth-guided samples, merged scatter at C = 64 -- fp32 parity mode against the oracle, then
+    bf16 against its own fp32 result; both schedules."""
+    kw = dict(S=20, C=64, D=512, hidden=512, SB=1, n_rays=512, Kc=64, Kf=64, Kfd=16, seed=21, reuse=reuse)
+    ref, out, (vg_r, pg_r), (vg, pg) = _oracle_vs_cuda(NR, precision="fp32", **kw)
+    assert torch.equal(out.coarse.z.cpu(), ref["z_coarse"])
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "weights"):
+            assert rel(out[lvl][k], ref[lvl][k]) < 1e-4, (lvl, k)
+    assert rel(vg, vg_r) < 3e-4
+    for k in pg_r:
+        assert rel(pg[k], pg_r[k]) < 1e-3, k
+    _, out16, _, (vg16, pg16) = _oracle_vs_cuda(NR, precision="bf16", **kw)
+    assert torch.equal(out16.coarse.z.cpu(), ref["z_coarse"])
+    assert rel(out16.coarse.rgb, out.coarse.rgb) < 3e-2 and rel(out16.coarse.embed, out.coarse.embed) < 3e-2
+    assert rel(out16.fine.embed, out.fine.embed) < 6e-2
+    assert cosine(vg16, vg) > 0.97 and all(cosine(pg16[k], pg[k]) > 0.97 for k in pg)
 
 
 @pytest.mark.parametrize("SB,n_rays,Kc,Kf", [(1, 37, 17, 5), (3, 1, 64, 64), (2, 50, 1, 3)])
