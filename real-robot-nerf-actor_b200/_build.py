@@ -12,6 +12,7 @@ LIB = os.path.join(HERE, "libnrf_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("NRF_NVCC_EXTRA", "").split()      # e.g. -DNRF_DEBUG_SPIN: fail-fast mbarrier waits
 
 
 def sources():

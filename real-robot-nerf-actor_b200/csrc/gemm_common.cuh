@@ -48,6 +48,8 @@ struct FusedLayerDesc {
   int act_slot;        // slot of `saves` this layer's output operand is written to, -1: none
   int mask_slot;       // backward: slot of the forward's saved operand whose ReLU gate applies to this layer's output
   const float* bias;   // forward
+  int n_chunks;        // 128-wide output chunks of this layer; 0 = 4 (the 512 hidden units).  lin_out: nout_pad / 128
+  int ext_col;         // first column of `in` the kb_z trailing k-panels are read from
 };
 struct FusedDesc {
   int n_layers;

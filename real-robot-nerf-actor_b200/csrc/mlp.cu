@@ -200,7 +200,7 @@ extern "C" int nrf_mlp_pack(const NrfMlpParams* p, int precision, void* packed, 
 static bool fused_supported(const MlpLayout& L) {
   // (2 nb + 1) slots x 64 B of gate bits per sample must fit the spare activation layer (H * es bytes per sample)
   return (2 * L.nb + 1) * 64 <= L.H * (int)L.es && L.H == 512 && L.es == 2 && (L.C == 64 || L.C == 128) && L.kin_pad == L.C + 64 && L.nz >= 1 &&
-         L.nout_pad <= 512 && 2 * L.nb + 2 <= kFusedMaxLayers;
+         L.nout_pad <= 640 && 2 * L.nb + 2 <= kFusedMaxLayers;
 }
 
 // diagnostics: device buffer (148 x 32 int64) that the next fused launches fill with per-role cycle counters
@@ -227,6 +227,7 @@ static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* 
         reinterpret_cast<const float*>(W + L.bias1[b]));
   }
   add(W + L.Wout, L.H, kbH, 0, 2, 1, 0, -1, reinterpret_cast<const float*>(W + L.bias_out));
+  d.L[l - 1].n_chunks = L.nout_pad / 128;          // 4 at d_embed = 384 (388 outputs), 5 at d_embed = 512 (516)
   d.n_layers = l;
   d.in = field_in; d.in_cols = L.kin_pad;
   d.N = N;
@@ -253,7 +254,13 @@ static int mlp_bwd_fused(const MlpLayout& L, const char* W, const void* d_field,
     f.act_slot = slot; f.mask_slot = mask_slot; f.bias = nullptr;
   };
   // dL/dx_nb = (d_field . W_out) gated by relu(x_nb) > 0
-  add(W + L.WoutT, L.dout_pad, L.dout_pad / 64, 0, 0, 1, L.nb, L.nb);
+  // d_field has dout_pad / 64 k-panels: up to 7 of them are loaded into P; if there are more, an EVEN number stays
+  // in P (producer and issuer walk the k-blocks in pairs that must not straddle the two sources) and the rest arrive
+  // through the ring (d_embed = 512: 576 columns = 6 + 3 panels)
+  const int kb_df = L.dout_pad / 64, kb_p = kb_df <= 7 ? kb_df : 6;
+  add(W + L.WoutT, L.dout_pad, kb_p, 0, 0, 1, L.nb, L.nb);
+  d.L[0].kb_z = kb_df - kb_p;
+  d.L[0].ext_col = kb_p * 64;
   for (int b = L.nb - 1; b >= 0; --b) {
     // dL/dnet_b = (dL/dx_{b+1} . W_fc1[b]) gated by relu(net_b) > 0
     add(W + L.Wfc1T[b], L.H, kbH, 1, 1, 0, L.nb + 1 + b, L.nb + 1 + b);

@@ -64,6 +64,8 @@ enum { kSrcIn = 0, kSrcQ = 1, kSrcP = 2 };
 
 struct FLayer {
   int kind, a_src, kb_main, kb_z, first, act_slot;
+  int n_chunks;            // 128-wide accumulator chunks of this layer (4 for the hidden layers, up to 5 for lin_out)
+  int ext_col;             // first column of the global input the kb_z trailing k-panels come from
   int mask_slot;           // backward: slot of the forward's saved operand whose sign gates this layer's output
   int publish;             // the epilogue hands its output to the next layer's MMAs (a_ready)
   const float* bias;       // forward only
@@ -174,7 +176,15 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+#ifdef NRF_DEBUG_SPIN
+    if (spin > (1u << 18)) {
+      printf("mbar_wait_u32 timeout: block %d warp %d barrier smem 0x%x parity %u\n", (int)blockIdx.x,
+             (int)(threadIdx.x >> 5), addr, parity);
+      __trap();
+    }
+#else
     if (spin > (1u << 26)) __trap();
+#endif
   }
 }
 __device__ __forceinline__ void mbar_arrive_leader_u32(uint32_t addr) {
@@ -430,7 +440,8 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
         const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
         for (int l = 0; l < nl; ++l) {
           const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
-          for (int c = 0; c < kFChunks; ++c)
+          const int nc = a.L[l].n_chunks, ext_col = a.L[l].ext_col;
+          for (int c = 0; c < nc; ++c)
             for (int kb = 0; kb < kb_tot; kb += 2) {
               if (kProf && (a.dbg & 1)) continue;
               const int nk = kb_tot - kb < 2 ? 1 : 2;
@@ -441,7 +452,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
                     if (cta_leader) mbar_expect_tx(full + st.stage, 2 * kFPanel);
                     else mbar_arrive_leader(full + st.stage);
                     tma_load_2d_pair(sRing + st.stage * kFStageB, &maps.in, full + st.stage,
-                                     (kb + h - kb_main) * 64, row0);
+                                     ext_col + (kb + h - kb_main) * 64, row0);
                   }
                   __syncwarp();
                   st.advance(kStages);
@@ -495,7 +506,8 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
           const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
           const int a_src = a.L[l].a_src;
           const uint32_t a_par = (uint32_t)(it * a.n_prod + l - 1) & 1;   // phase of the epilogue that produced A
-          for (int c = 0; c < kFChunks; ++c, ++n) {
+          const int nc = a.L[l].n_chunks;
+          for (int c = 0; c < nc; ++c, ++n) {
             const uint32_t buf = n & 1;
             if (!(kProf && (a.dbg & 8))) FUSED_TIMED(t_acc, mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1));
             const uint32_t tmem_d = tmem_base + buf * 128;
@@ -563,7 +575,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
             }
             if (elect_one()) {
               umma_commit_pair(acc_full + buf);
-              if (l == a.l_p_free && c == kFChunks - 1) umma_commit_pair(in_free);
+              if (l == a.l_p_free && c == nc - 1) umma_commit_pair(in_free);
             }
             __syncwarp();
           }
@@ -604,8 +616,8 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
     uint32_t n = 0;
     // what the next chunk (c of layer l of this CTA's tile `it`) needs prefetched: its bias values / its gate row
     // what a later chunk (c of layer l of this CTA's tile `it`; c may run past the layer) needs prefetched
-    auto norm = [&](int& it, int& l, int& c) {
-      if (c >= kFChunks) { c -= kFChunks; ++l; }
+    auto norm = [&](int& it, int& l, int& c) {          // c runs at most two chunks past its layer
+      if (c >= a.L[l].n_chunks) { c -= a.L[l].n_chunks; ++l; }
       if (l == nl) { l = 0; ++it; }
     };
     auto pre_bias = [&](int it, int l, int c) -> const void* {
@@ -650,7 +662,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
                                               pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         } else if (!kBwd) {
 #pragma unroll 1
-          for (int c = 0; c < kFChunks; ++c, ++n)
+          for (int c = 0; c < L.n_chunks; ++c, ++n)
             epi_chunk<kLayerOut, kSave, kBwd, kProf>(e, maps, a, L, c, n, row0, false, xres[0], gate[0],
                                               pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         }
@@ -699,12 +711,16 @@ int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
   for (int l = 0; l < d.n_layers; ++l) {
     const FusedLayerDesc& L = d.L[l];
     const int ktot = (L.kb_main + L.kb_z) * 64;
-    if ((rc = make_map(&maps.w[l], L.W, ktot, 512, L.ldw, 64, 64))) return rc;   // box = one k-block of a CTA's 64 rows
+    const int nchunks = L.n_chunks > 0 ? L.n_chunks : kFChunks;
+    NRF_REQUIRE(nchunks == kFChunks || (L.kind == 2 && nchunks >= 1 && nchunks <= 8), NRF_ENOSUP,
+                "mlp_fused: layer %d has %d output chunks (only lin_out may differ from %d)", l, nchunks, kFChunks);
+    if ((rc = make_map(&maps.w[l], L.W, ktot, nchunks * 128, L.ldw, 64, 64))) return rc;   // box = one k-block of a CTA's 64 rows
     NRF_REQUIRE(d.backward || ((reinterpret_cast<uintptr_t>(L.bias) & 15) == 0 && L.bias), NRF_EINVAL,
                 "mlp_fused: bias alignment");
     a.L[l].kind = L.kind; a.L[l].a_src = L.a_src; a.L[l].kb_main = L.kb_main; a.L[l].kb_z = L.kb_z;
     a.L[l].first = L.first; a.L[l].act_slot = d.saves ? L.act_slot : -1; a.L[l].bias = L.bias;
     a.L[l].mask_slot = L.mask_slot;
+    a.L[l].n_chunks = nchunks; a.L[l].ext_col = L.ext_col;
     a.L[l].publish = l + 1 < d.n_layers && L.kind != 2;
     n_prod += a.L[l].publish;
   }
@@ -719,9 +735,10 @@ int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
   a.n_layers = d.n_layers;
   a.n_tiles = (int)((d.N + 255) / 256);
   a.n_prod = n_prod;
-  NRF_REQUIRE(d.L[0].a_src == 0 && d.L[0].kb_z == 0 && d.L[0].kb_main <= kFMaxIn && d.L[0].kb_main * 64 == d.in_cols,
-              NRF_ENOSUP, "mlp_fused: the first layer reads all %d input columns from P (at most %d k-panels)",
-              d.in_cols, kFMaxIn);
+  NRF_REQUIRE(d.L[0].a_src == 0 && d.L[0].kb_main <= kFMaxIn && (d.L[0].kb_main + d.L[0].kb_z) * 64 == d.in_cols &&
+                  (d.L[0].kb_z == 0 || (d.L[0].ext_col == d.L[0].kb_main * 64 && d.L[0].kb_main % 2 == 0)),
+              NRF_ENOSUP, "mlp_fused: the first layer reads %d input columns: at most %d k-panels in P, the rest "
+              "through the ring", d.in_cols, kFMaxIn);
   a.l_p_free = 0;
   for (int l = 0; l < d.n_layers; ++l)
     if (d.L[l].a_src == 2 || (l == 0)) a.l_p_free = l;

@@ -52,7 +52,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+#ifdef NRF_DEBUG_SPIN      // debugging builds (NRF_NVCC_EXTRA=-DNRF_DEBUG_SPIN): fail fast and say who waited for what
+    if (spin > (1u << 18)) {
+      printf("mbar_wait timeout: block %d warp %d barrier smem 0x%x parity %u\n", (int)blockIdx.x,
+             (int)(threadIdx.x >> 5), addr, parity);
+      __trap();
+    }
+#else
     if (spin > (1u << 26)) __trap();
+#endif
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {

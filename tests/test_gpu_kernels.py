@@ -416,12 +416,14 @@ def _bf16_mlp(C=128, D=384, seed=0):
     return mlp.cuda()
 
 
-@pytest.mark.parametrize("C,N", [(128, 256), (128, 1000), (128, 40000), (64, 777), (128, 1)])
-def test_fused_mlp_forward_is_bit_identical_to_the_layered_chain(ops, C, N):
+@pytest.mark.parametrize("C,N,D", [(128, 256, 384), (128, 1000, 384), (128, 40000, 384), (64, 777, 384), (128, 1, 384),
+                                   (64, 1000, 512), (128, 40000, 512), (64, 3, 512)])
+def test_fused_mlp_forward_is_bit_identical_to_the_layered_chain(ops, C, N, D):
     """csrc/mlp_fused.cu (one persistent tcgen05 kernel, activations on chip) against the layer-by-layer GEMM chain
     on the same packed weights: raw outputs and every operand saved for the backward, ragged N included; the
-    inference variant (nothing saved) gives the same outputs."""
-    mlp = _bf16_mlp(C=C)
+    inference variant (nothing saved) gives the same outputs.  D = 512 (nerfact.conf:22): lin_out has 516 outputs =
+    five 128-wide chunks instead of four."""
+    mlp = _bf16_mlp(C=C, D=D)
     h = mlp.handle(ops.NRF_PREC_BF16)
     assert h.fused, "the BASELINE shape must take the fused kernel"
     g = torch.Generator().manual_seed(N)
@@ -442,19 +444,21 @@ def test_fused_mlp_forward_is_bit_identical_to_the_layered_chain(ops, C, N):
     assert rel(out_f, ref) < 3e-2
 
 
-@pytest.mark.parametrize("C,N", [(128, 256), (128, 1000), (128, 33000), (64, 777), (128, 3)])
-def test_fused_mlp_backward_is_bit_identical_to_the_layered_chain(ops, C, N):
+@pytest.mark.parametrize("C,N,D", [(128, 256, 384), (128, 1000, 384), (128, 33000, 384), (64, 777, 384), (128, 3, 384),
+                                   (64, 1000, 512), (128, 33000, 512), (64, 5, 512)])
+def test_fused_mlp_backward_is_bit_identical_to_the_layered_chain(ops, C, N, D):
     """The fused data-gradient kernel (residual gradient in registers, bit-packed ReLU gates written by the fused
     forward) + weight-gradient GEMMs against the per-layer backward on the same saved operands: dL/dlatent and, with
-    the ordered split reduction, every parameter gradient."""
+    the ordered split reduction, every parameter gradient.  D = 512: d_field has 576 columns = 9 k-panels, six of them
+    in the shared-memory operand panel and three through the weight ring."""
     NR = load_pkg("neural_rendering")
-    mlp = _bf16_mlp(C=C, seed=1)
+    mlp = _bf16_mlp(C=C, D=D, seed=1)
     h = mlp.handle(ops.NRF_PREC_BF16)
     g = torch.Generator().manual_seed(N + 1)
     fin = torch.zeros(N, h.sizes.kin_pad, dtype=torch.bfloat16)
     fin[:, :C + 42] = (torch.randn(N, C + 42, generator=g) * 0.5).to(torch.bfloat16)
     dfield = torch.zeros(N, h.sizes.dout_pad, dtype=torch.bfloat16)
-    dfield[:, :388] = (torch.randn(N, 388, generator=g) * 0.1).to(torch.bfloat16)
+    dfield[:, :4 + D] = (torch.randn(N, 4 + D, generator=g) * 0.1).to(torch.bfloat16)
     fin, dfield = fin.cuda(), dfield.cuda()
     out, acts = h.forward(fin)
     res = {}
@@ -470,7 +474,7 @@ def test_fused_mlp_backward_is_bit_identical_to_the_layered_chain(ops, C, N):
     x = fin[:, :C + 42].float().cpu().requires_grad_(True)
     ref = O.resnetfc(p, x, d_latent=C, operand_dtype=torch.bfloat16)
     ref = ref[0] if isinstance(ref, tuple) else ref
-    ref.backward(dfield[:, :388].float().cpu())
+    ref.backward(dfield[:, :4 + D].float().cpu())
     # bf16 gradient operands against fp32 autograd: SURVEY section 10 measured ~1e-1 on dL/dlatent (ReLU-gate flips)
     cos = torch.nn.functional.cosine_similarity(res[False][0].cpu().flatten(), x.grad[:, :C].flatten(), dim=0)
     assert rel(res[False][0], x.grad[:, :C]) < 2e-1 and cos > 0.98
