@@ -45,9 +45,11 @@ const char* nrf_version(void);
 const char* nrf_last_error(void);   /* text of the last failure on this thread */
 
 /* ---- rays (utils.py:444-506 unproj_map + gen_rays) ------------------------------------------
- * poses (n_img,4,4) cam->world fp32; rays_out (n_img,H,W,8). */
+ * poses (n_img,4,4) cam->world fp32; rays_out (n_img,H,W,8).
+ * intrinsics_dev: NULL, or 4 floats [fx, fy, cx, cy] in device memory that replace the by-value arguments (the
+ * reference's callers keep `focal` on the GPU, utils.py:485: it is then never read back by the host). */
 int nrf_raygen(const float* poses, int n_img, int W, int H, float fx, float fy, float cx, float cy,
-               float z_near, float z_far, float* rays_out, void* stream);
+               float z_near, float z_far, float* rays_out, const float* intrinsics_dev, void* stream);
 
 /* ---- stratified sampling (neural_rendering.py:159-176 sample_coarse) ------------------------
  * base (Kc) = linspace(0, 1-1/Kc, Kc); jitter (R,Kc) in [0,1) or NULL (perturb off). */

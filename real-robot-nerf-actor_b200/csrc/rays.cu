@@ -10,12 +10,15 @@ namespace nrf {
 
 // One thread per pixel.  CPU-ATen bit pattern: norm = sqrt(fma(z,z,fma(y,y,x*x))),
 // direction = (r0*x + r1*y) + r2*z with separately rounded products and sums.
+// intr (device, [fx, fy, cx, cy]) overrides the by-value intrinsics: a focal length that lives on the GPU (as in the
+// reference's callers) is then never read back by the host -- no stream sync at the start of every step.
 __global__ void raygen_kernel(const float* __restrict__ poses, int n_img, int W, int H, float fx,
                               float fy, float cx, float cy, float z_near, float z_far,
-                              float* __restrict__ rays) {
+                              float* __restrict__ rays, const float* __restrict__ intr) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)n_img * H * W;
   if (t >= total) return;
+  if (intr) { fx = intr[0]; fy = intr[1]; cx = intr[2]; cy = intr[3]; }
   int j = (int)(t % W);
   int i = (int)((t / W) % H);
   int b = (int)(t / ((int64_t)W * H));
@@ -167,13 +170,14 @@ __global__ void sort_rows_kernel(float* __restrict__ z, int R, int K, int P, int
 using namespace nrf;
 
 extern "C" int nrf_raygen(const float* poses, int n_img, int W, int H, float fx, float fy, float cx,
-                          float cy, float z_near, float z_far, float* rays_out, void* stream) {
+                          float cy, float z_near, float z_far, float* rays_out, const float* intrinsics_dev,
+                          void* stream) {
   NRF_REQUIRE(poses && rays_out && n_img > 0 && W > 0 && H > 0, NRF_EINVAL, "nrf_raygen: bad args");
   int64_t total = (int64_t)n_img * H * W;
   int threads = 256;
   { LaunchScope ls_(NRF_CAT_SAMPLING, as_stream(stream));
   raygen_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
-      poses, n_img, W, H, fx, fy, cx, cy, z_near, z_far, rays_out);
+      poses, n_img, W, H, fx, fy, cx, cy, z_near, z_far, rays_out, intrinsics_dev);
   }
   NRF_LAUNCH_OK();
   return NRF_OK;

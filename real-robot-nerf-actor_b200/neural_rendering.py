@@ -171,9 +171,23 @@ class ResnetFC(nn.Module):
     def n_lin_z(self):
         return len(self.lin_z) if self.d_latent != 0 else 0
 
+    def param_dict(self):
+        """name -> Parameter, cached: walking the module tree costs ~0.1 ms and is needed several times per step
+        (the step at the reference's own training shape is host-bound).  Dropped whenever the module is converted
+        (`_apply`: .to() / .cuda() / .float())."""
+        d = self.__dict__.get("_param_dict_cache")
+        if d is None:
+            d = dict(self.named_parameters())
+            self.__dict__["_param_dict_cache"] = d
+        return d
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_param_dict_cache", None)
+        return super()._apply(fn, *args, **kwargs)
+
     def handle(self, precision) -> ops.FieldMLP:
         """C-ABI handle for the given precision; rebuilt if parameters moved (e.g. after .to())."""
-        params = dict(self.named_parameters())
+        params = self.param_dict()
         key = (precision, tuple(p.data_ptr() for p in params.values()))
         h = self._handles.get(precision)
         if h is None or h[0] != key:
@@ -189,7 +203,7 @@ class ResnetFC(nn.Module):
         lead = zx.shape[:-1]
         flat = zx.reshape(-1, zx.shape[-1])
         names = h.names()
-        out = _MlpFn.apply(h, flat, *[dict(self.named_parameters())[n] for n in names])
+        out = _MlpFn.apply(h, flat, *[self.param_dict()[n] for n in names])
         return out.reshape(*lead, self.d_out), None
 
 
@@ -317,7 +331,7 @@ class PixelNeRFEmbedNet(nn.Module):
         rays = torch.zeros(SB * B, 8, device=xyz.device, dtype=torch.float32)
         rays[:, 0:3] = xyz.reshape(-1, 3)
         rays[:, 3:6] = viewdirs.reshape(-1, 3)
-        ps = [dict(mlp.named_parameters())[n] for n in h.names()]
+        ps = [mlp.param_dict()[n] for n in h.names()]
         keep = torch.is_grad_enabled() and (self.voxel_feat.requires_grad or any(p.requires_grad for p in ps))
         bounds = torch.as_tensor(self.coordinate_bounds, dtype=torch.float32).reshape(-1).cpu()
         raw = _FieldFn.apply(self, h, bounds, self.voxel_feat, rays, SB, keep, *ps)
@@ -735,7 +749,14 @@ class NeuralRenderer(nn.Module):
 
     @property
     def _bounds(self):
-        return torch.as_tensor(self.coordinate_bounds, dtype=torch.float32).reshape(-1).cpu()
+        """Host copy of the 6 bounds, read back once per `coordinate_bounds` object (callers pass a CUDA tensor: a
+        `.cpu()` per kernel call would stall the host on the stream several times a step)."""
+        cached = getattr(self, "_bounds_cache", None)
+        if cached is None or cached[0] is not self.coordinate_bounds:
+            cached = (self.coordinate_bounds,
+                      torch.as_tensor(self.coordinate_bounds, dtype=torch.float32).reshape(-1).cpu())
+            self._bounds_cache = cached
+        return cached[1]
 
     def _draw_noise(self, R, device):
         """Noise in the reference's draw order (SURVEY 8b 'RNG'); zeros / a fixed grid if not perturb."""
@@ -759,12 +780,12 @@ class NeuralRenderer(nn.Module):
 
     def _params_flat(self):
         m = self.nerf_model
-        pc = dict(m.mlp_coarse.named_parameters())
+        pc = m.mlp_coarse.param_dict()
         names = m.mlp_coarse.handle(self._prec).names()
         ps = [pc[n] for n in names]
         n_pc = len(ps)
         if m.mlp_fine is not m.mlp_coarse:
-            pf = dict(m.mlp_fine.named_parameters())
+            pf = m.mlp_fine.param_dict()
             ps += [pf[n] for n in m.mlp_fine.handle(self._prec).names()]
         return n_pc, ps
 
@@ -805,7 +826,7 @@ class NeuralRenderer(nn.Module):
         mlp = (model.mlp_coarse if coarse or model.mlp_fine is None else model.mlp_fine)
         h = mlp.handle(self._prec)
         names = h.names()
-        ps = [dict(mlp.named_parameters())[n] for n in names]
+        ps = [mlp.param_dict()[n] for n in names]
         return _CompositeFn.apply(self, h, model.voxel_feat, rays.contiguous(), z_samp.contiguous(), sb, *ps)
 
     def _format_outputs(self, rendered_outputs, superbatch_size, want_weights=False):

@@ -30,20 +30,51 @@ def act_dtype(precision: int):
 
 
 # ------------------------------------------------------------------------------------- rays
+_INTR_CACHE = {}
+
+
+def _device_intrinsics(focal, c, width, height, device):
+    """[fx, fy, cx, cy] as a 4-float device tensor, built with device ops only (no read-back).  The last result is kept
+    per (focal, c) tensor object + version: a training loop passes the same tensors every step."""
+    ver = lambda t: (id(t), t._version) if torch.is_tensor(t) else t
+    key = (ver(focal), ver(c), width, height, str(device))
+    hit = _INTR_CACHE.get("last")
+    if hit is not None and hit[0] == key and hit[1] is focal and hit[2] is c:
+        return hit[3]
+    f = torch.as_tensor(focal, dtype=torch.float32, device=device).reshape(-1)
+    intr = torch.empty(4, device=device, dtype=torch.float32)
+    intr[0:2] = f[0:2] if f.numel() >= 2 else f[0]
+    if c is None:
+        intr[2], intr[3] = width * 0.5, height * 0.5
+    else:
+        cc = torch.as_tensor(c, dtype=torch.float32, device=device).reshape(-1)
+        intr[2:4] = cc[0:2] if cc.numel() >= 2 else cc[0]
+    _INTR_CACHE["last"] = (key, focal, c, intr)          # holding focal / c keeps their ids from being reused
+    return intr
+
+
 def raygen(poses, width, height, focal, z_near, z_far, c=None):
-    """utils.py:477-506 gen_rays.  poses (B,4,4) -> rays (B,H,W,8)."""
+    """utils.py:477-506 gen_rays.  poses (B,4,4) -> rays (B,H,W,8).
+    A `focal` / `c` that lives on the GPU stays there (4 floats handed to the kernel by pointer): reading it back would
+    stall the host on everything queued before, once per step."""
     poses = _f32(poses, "poses")
-    f = torch.as_tensor(focal, dtype=torch.float32).reshape(-1).cpu()
+    B = poses.shape[0]
+    rays = torch.empty(B, height, width, 8, device=poses.device, dtype=torch.float32)
+    on_dev = (torch.is_tensor(focal) and focal.is_cuda) or (torch.is_tensor(c) and c.is_cuda)
+    if on_dev:
+        intr = _device_intrinsics(focal, c, width, height, poses.device)
+        check(_lib.load().nrf_raygen(ptr(poses), B, width, height, 0.0, 0.0, 0.0, 0.0, float(z_near), float(z_far),
+                                     ptr(rays), ptr(intr), stream_ptr()), "nrf_raygen")
+        return rays
+    f = torch.as_tensor(focal, dtype=torch.float32).reshape(-1)
     fx, fy = (float(f[0]), float(f[0])) if f.numel() == 1 else (float(f[0]), float(f[1]))
     if c is None:
         cx, cy = width * 0.5, height * 0.5
     else:
-        cc = torch.as_tensor(c, dtype=torch.float32).reshape(-1).cpu()
-        cx, cy = float(cc[0]), float(cc[1])
-    B = poses.shape[0]
-    rays = torch.empty(B, height, width, 8, device=poses.device, dtype=torch.float32)
+        cc = torch.as_tensor(c, dtype=torch.float32).reshape(-1)
+        cx, cy = (float(cc[0]), float(cc[0])) if cc.numel() == 1 else (float(cc[0]), float(cc[1]))
     check(_lib.load().nrf_raygen(ptr(poses), B, width, height, fx, fy, cx, cy, float(z_near),
-                                 float(z_far), ptr(rays), stream_ptr()), "nrf_raygen")
+                                 float(z_far), ptr(rays), None, stream_ptr()), "nrf_raygen")
     return rays
 
 

@@ -44,6 +44,9 @@ CONFIGS = {
     "config3": Workload("config3", 100, 128, 384, 1, 5 * 128 * 128, 64, 64, n_cams=5, train=False),
     "config4": Workload("config4", 100, 128, 384, 8, 4096, 64, 64),
     "config5": Workload("config5", 200, 128, 384, 1, 16384, 128, 128),
+    # the reference's own training shape (nerfact.conf:22-28,:606): one scene, 512-ray chunks, 64 latent channels,
+    # 512-d features -- a launch-bound step, kept for host-overhead work (scripts/profile_step.py nerfact)
+    "nerfact": Workload("nerfact", 100, 64, 512, 1, 512, 64, 64),
 }
 
 

@@ -17,7 +17,8 @@ syn = importlib.import_module(PKG + ".synthetic")
 
 wl = syn.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "config2"]
 dev = torch.device("cuda", 0)
-cfg = U.default_config(voxel_shape=wl.S, n_coarse=wl.n_coarse, n_fine=wl.n_fine, ray_chunk_size=wl.rays_per_scene)
+cfg = U.default_config(voxel_shape=wl.S, d_latent=wl.C, d_embed=wl.D, n_coarse=wl.n_coarse, n_fine=wl.n_fine,
+                       ray_chunk_size=wl.rays_per_scene)
 ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS))
 syn.init_mlp_(ren.nerf_model.mlp_coarse)
 ren = ren.to(dev).train()
@@ -66,4 +67,4 @@ for _ in range(3):
 torch.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
-st.sort_stats("tottime").print_stats(18)
+st.sort_stats("tottime").print_stats(28)

@@ -47,6 +47,12 @@ def test_raygen_matches_reference(ops):
                    c=torch.tensor([70.5, 61.25])).cpu()
     assert (r[:, ::32] - T(fx["rays_128_c_rows"])).abs().max() <= 2.5e-7
     assert frac > 0.99
+    # intrinsics that live on the GPU are handed over by pointer (no host read-back): same bits as by value
+    for f_, c_ in ((torch.tensor(153.0), None), (torch.tensor([150.0, 151.0]), torch.tensor([70.5, 61.25])),
+                   (torch.tensor([76.18187]), None)):
+        host = ops.raygen(poses[:2], 128, 96, f_, 1.2, 4.0, c=c_)
+        dev = ops.raygen(poses[:2], 128, 96, f_.cuda(), 1.2, 4.0, c=None if c_ is None else c_.cuda())
+        assert torch.equal(host, dev)
 
 
 @pytest.mark.parametrize("Kc,lindisp,jit", [(64, False, False), (64, False, True), (128, False, True),
