@@ -140,7 +140,13 @@ def ptr(t):
 
 
 def stream_ptr():
+    """The current CUDA stream of the current device as a void* (what every C-ABI call is enqueued on).  The raw-handle
+    query is ~30 x cheaper than building a torch.cuda.Stream object, and this runs once per kernel launch (55 times in
+    a step at the reference's training shape, which is host-bound)."""
     import torch
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return C.c_void_p(raw(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -142,10 +142,20 @@ def volume_to_channels_first(vol_cl):
     return out
 
 
+_BOUNDS_CACHE = {}
+
+
 def _bounds_host(bounds):
+    """6 floats as a ctypes array; the last conversion is kept per tensor object (the renderer hands over the same
+    cached host tensor several times a step)."""
+    hit = _BOUNDS_CACHE.get("last")
+    if hit is not None and hit[0] is bounds and (not torch.is_tensor(bounds) or hit[1] == bounds._version):
+        return hit[2]
     b = torch.as_tensor(bounds, dtype=torch.float32).reshape(-1).cpu()
     assert b.numel() == 6
-    return (C.c_float * 6)(*[float(v) for v in b])
+    arr = (C.c_float * 6)(*[float(v) for v in b])
+    _BOUNDS_CACHE["last"] = (bounds, bounds._version if torch.is_tensor(bounds) else None, arr)
+    return arr
 
 
 def encode_points(rays, z, rays_per_scene, vol_cl, bounds, num_freqs=6, freq_factor=1.5, ld_out=None,
