@@ -173,12 +173,19 @@ class ResnetFC(nn.Module):
 
     def param_dict(self):
         """name -> Parameter, cached: walking the module tree costs ~0.1 ms and is needed several times per step
-        (the step at the reference's own training shape is host-bound).  Dropped whenever the module is converted
-        (`_apply`: .to() / .cuda() / .float())."""
-        d = self.__dict__.get("_param_dict_cache")
-        if d is None:
-            d = dict(self.named_parameters())
-            self.__dict__["_param_dict_cache"] = d
+        (the step at the reference's own training shape is host-bound).  The cache remembers where every parameter
+        hangs and is re-checked by identity (30 dictionary look-ups), so replacing a parameter object rebuilds it; it
+        is also dropped whenever the module is converted (`_apply`: .to() / .cuda() / .float())."""
+        c = self.__dict__.get("_param_dict_cache")
+        if c is not None and all(m._parameters.get(n) is p for m, n, p in c[1]):
+            return c[0]
+        d, where = {}, []
+        for mod_name, mod in self.named_modules():
+            for n, p in mod._parameters.items():
+                if p is not None:
+                    d[(mod_name + "." if mod_name else "") + n] = p
+                    where.append((mod, n, p))
+        self.__dict__["_param_dict_cache"] = (d, where)
         return d
 
     def _apply(self, fn, *args, **kwargs):

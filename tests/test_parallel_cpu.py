@@ -157,3 +157,18 @@ def test_dropin_modules_resolve_under_the_reference_names():
             sys.modules.pop(k, None)
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_param_dict_cache_follows_the_module():
+    """ResnetFC.param_dict(): same names / order / objects as named_parameters(), cached, rebuilt when a parameter
+    object is replaced or the module is converted."""
+    NR = load_pkg("neural_rendering")
+    m = NR.ResnetFC(d_in=42, d_out=388, n_blocks=5, d_latent=128, d_hidden=512, combine_layer=3)
+    d, ref = m.param_dict(), dict(m.named_parameters())
+    assert list(d) == list(ref) and all(d[k] is ref[k] for k in ref) and len(d) == 30
+    assert m.param_dict() is d
+    m.lin_in.weight = torch.nn.Parameter(torch.zeros_like(m.lin_in.weight))
+    d2 = m.param_dict()
+    assert d2 is not d and d2["lin_in.weight"] is m.lin_in.weight
+    m.double()
+    assert m.param_dict() is not d2 and m.param_dict()["lin_out.bias"].dtype == torch.float64
