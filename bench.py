@@ -265,7 +265,7 @@ def run_ours(args):
     line = {"metric": "render fwd+bwd ray-samples/s", "value": round(value, 1), "unit": "ray-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
+            "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"{wl.name}: per GPU {SB} scenes x {n_rays} rays, {wl.n_coarse}+{wl.n_fine} samples, "
                                    f"{wl.S}^3 x {wl.C}ch volume, ResnetFC 512x5, RGB+{wl.D}d heads, fwd+bwd",
                        "evals_per_step": evals_step, "precision": args.precision, "scatter": args.scatter, "volume_layout": args.volume_layout,
@@ -419,7 +419,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=128, dest="cpu_rays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reuse-line", action="store_true", dest="no_reuse_line")

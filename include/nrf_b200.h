@@ -40,6 +40,18 @@ extern "C" {
 /* precision of the field MLP */
 #define NRF_PREC_BF16 0   /* bf16 operands, fp32 accumulate, tcgen05 tensor cores */
 #define NRF_PREC_FP32 1   /* fp32 SIMT FFMA: parity-grade mode                    */
+#define NRF_PREC_FP16 2   /* fp16 FORWARD operands (weights, field input, activations, residual stream: 11 significant
+                             bits, same tcgen05 kind::f16 rate as bf16, 6-8 x smaller output error: SURVEY.md section 10)
+                             with bf16 GRADIENTS (d_field, dL/dx', dL/dnet: their range needs no loss scaling; the
+                             gradient error of either mode is set by ReLU-gate flips of the forward, not by gradient
+                             rounding).  "Operand-typed" below then means fp16 for forward tensors (field_in, acts, packed
+                             weights) and bf16 for gradient tensors (d_field, the backward's scratch). */
+
+#define NRF_PREC_BF16X3 3 /* split-bf16 operands (a = hi + lo, 16 significant bits), every product as hi.hi + lo.hi + hi.lo
+                             on the tensor cores with fp32 accumulation: fp32-grade results (1.5e-5 on
+                             rgb) at a third of the bf16 rate, layer by layer (csrc/mlp_x3.cu).  The caller-facing tensors
+                             are those of NRF_PREC_FP32: fp32 field input, fp32 d_field.  nrf_mlp_* only (nrf_gemm /
+                             nrf_wgrad take the three 16-bit / fp32 modes). */
 
 const char* nrf_version(void);
 const char* nrf_last_error(void);   /* text of the last failure on this thread */
@@ -78,7 +90,7 @@ int nrf_volume_to_channels_first(const float* src, float* dst, int SB, int C, in
  * Replaces neural_rendering.py:246-283 (points, viewdirs), models_embed.py:185-203
  * (world_to_canonical), :259-277 (grid_sample), utils.py:545-557 (PositionalEncoding) and the
  * concatenations at models_embed.py:366,405.  vol_cl is channels-last.  bounds = 6 floats (HOST).
- * out: (N, ld_out) bf16 if out_bf16 else fp32; columns >= C+42 are zero-filled up to ld_out.
+ * out: (N, ld_out) fp32 (out_bf16 == 0), bf16 (1) or fp16 (2); columns >= C+42 are zero-filled up to ld_out.
  * rays_per_scene = R / SB. points_out (N,3) fp32 optional (debug / parity), may be NULL. */
 int nrf_encode_points(const float* rays, const float* z, int R, int K, int rays_per_scene,
                       const float* vol_cl, int SB, int C, int S0, int S1, int S2,
@@ -170,8 +182,8 @@ int nrf_voxelize(const float* coords, const float* feats, int B, int N, int F, c
 /* ---- GEMM building block of the field MLP ----------------------------------------------------
  * v = resid + mask( [A0 | A1 | A2] . B^T + bias ),   B (N,K) row-major (nn.Linear layout)
  *   A[i] (M,K[i]) lda[i]: up to three operand matrices concatenated along K (K[i] = 0: unused)
- *   operand type: bf16 (NRF_PREC_BF16) or fp32 (NRF_PREC_FP32); applies to A, B, mask_src, resid,
- *   out_act and out_act2
+ *   operand type: bf16 (NRF_PREC_BF16), fp16 (NRF_PREC_FP16) or fp32 (NRF_PREC_FP32); applies to A, B, mask_src,
+ *   resid, out_act and out_act2
  *   bias (N) fp32 or NULL; mask_src (M,N) or NULL: v is zeroed where mask_src <= 0 (ReLU gate)
  *   resid (M,N) or NULL (may alias out_act: the update is element-wise in place)
  *   out_act / out_act2 (M,n_store) or NULL: v, ReLU'd when the matching relu flag is set
@@ -194,7 +206,7 @@ int nrf_gemm(const NrfGemm* g, int precision, void* stream);
 /* Weight gradient dW (N,K) += G^T . A with G (M,N) ldg, A (M,K) lda operand-typed; dW fp32 ldw.
  * workspace: fp32, >= nrf_wgrad_workspace_bytes(N,K) (bf16 mode; split-K partials), may be NULL
  * in fp32 mode.  Only rows < n_valid and columns < k_valid of dW are touched.
- * dbias (n_valid) += column sums of G when non-NULL. */
+ * dbias (n_valid) += column sums of G when non-NULL.  NRF_PREC_FP16: G is bf16 (a gradient), A fp16 (an activation). */
 int64_t nrf_wgrad_workspace_bytes(int N, int K);
 int nrf_wgrad(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
               int k_valid, float* dW, int ldw, float* dbias, void* workspace, int precision,

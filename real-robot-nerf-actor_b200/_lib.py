@@ -12,6 +12,8 @@ LIB_PATH = os.environ.get("NRF_LIB_PATH") or os.path.join(HERE, "libnrf_b200.so"
 
 NRF_PREC_BF16 = 0
 NRF_PREC_FP32 = 1
+NRF_PREC_FP16 = 2
+NRF_PREC_BF16X3 = 3
 NRF_MAX_BLOCKS = 8
 
 c_f32p = C.c_void_p

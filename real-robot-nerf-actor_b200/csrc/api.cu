@@ -94,7 +94,8 @@ extern "C" int nrf_gemm(const NrfGemm* g, int precision, void* stream) {
   NRF_REQUIRE((g->K[1] == 0 || g->A[1]) && (g->K[2] == 0 || g->A[2]), NRF_EINVAL, "nrf_gemm: K[i] > 0 needs A[i]");
   NRF_REQUIRE(g->n_store > 0 && g->n_store <= g->N, NRF_EINVAL, "nrf_gemm: n_store out of range");
   NRF_REQUIRE(g->out_f32 || g->out_act, NRF_EINVAL, "nrf_gemm: no output");
-  if (precision == NRF_PREC_BF16) return gemm_tc_launch(*g, as_stream(stream));
+  if (precision == NRF_PREC_BF16 || precision == NRF_PREC_FP16)
+    return gemm_tc_launch(*g, op_fmt(precision), as_stream(stream));
   if (precision == NRF_PREC_FP32) return gemm_simt_launch(*g, as_stream(stream));
   set_error("nrf_gemm: unknown precision %d", precision);
   return NRF_EINVAL;
@@ -112,9 +113,9 @@ extern "C" int nrf_wgrad(const void* G, int ldg, const void* A, int lda, int M, 
   NRF_REQUIRE(G && A && dW && M > 0 && N > 0 && K > 0, NRF_EINVAL, "nrf_wgrad: bad arguments");
   NRF_REQUIRE(n_valid > 0 && n_valid <= N && k_valid > 0 && k_valid <= K, NRF_EINVAL,
               "nrf_wgrad: n_valid/k_valid out of range");
-  if (precision == NRF_PREC_BF16)
+  if (precision == NRF_PREC_BF16 || precision == NRF_PREC_FP16)
     return wgrad_tc_launch(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace,
-                           as_stream(stream));
+                           op_fmt(precision), as_stream(stream));
   if (precision == NRF_PREC_FP32)
     return wgrad_simt_launch(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, as_stream(stream));
   set_error("nrf_wgrad: unknown precision %d", precision);

@@ -98,6 +98,7 @@ template <> __device__ __forceinline__ float to_out<float>(float v) { return v; 
 template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) {
   return __float2bfloat16_rn(v);
 }
+template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
 
 template <typename T>
 __device__ __forceinline__ void store4(T* p, float4 v);
@@ -106,6 +107,13 @@ template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) {
 }
 template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* p, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
   uint2 u;
   u.x = *reinterpret_cast<uint32_t*>(&a);
   u.y = *reinterpret_cast<uint32_t*>(&b);
@@ -209,6 +217,17 @@ template <> struct TailVec<__nv_bfloat16> {
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
     __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
     __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&q0); u.y = *reinterpret_cast<uint32_t*>(&q1);
+    u.z = *reinterpret_cast<uint32_t*>(&q2); u.w = *reinterpret_cast<uint32_t*>(&q3);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct TailVec<__half> {
+  static constexpr int kPer = 8;
+  static __device__ __forceinline__ void store(__half* p, const float* v) {
+    __half2 q0 = __floats2half2_rn(v[0], v[1]), q1 = __floats2half2_rn(v[2], v[3]);
+    __half2 q2 = __floats2half2_rn(v[4], v[5]), q3 = __floats2half2_rn(v[6], v[7]);
     uint4 u;
     u.x = *reinterpret_cast<uint32_t*>(&q0); u.y = *reinterpret_cast<uint32_t*>(&q1);
     u.z = *reinterpret_cast<uint32_t*>(&q2); u.w = *reinterpret_cast<uint32_t*>(&q3);
@@ -407,14 +426,16 @@ extern "C" int nrf_encode_points(const float* rays, const float* z, int R, int K
     int max_blocks = sm_count() * 8;
     int blocks = (int)(want < max_blocks ? want : max_blocks);
     LaunchScope ls_(NRF_CAT_ENCODE, as_stream(stream));
-    if (out_bf16) encode_points_w32_kernel<__nv_bfloat16><<<blocks, threads, 0, as_stream(stream)>>>(a);
+    if (out_bf16 == 2) encode_points_w32_kernel<__half><<<blocks, threads, 0, as_stream(stream)>>>(a);
+    else if (out_bf16) encode_points_w32_kernel<__nv_bfloat16><<<blocks, threads, 0, as_stream(stream)>>>(a);
     else encode_points_w32_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(a);
   } else {                                     // any other shape: one warp per sample
     int64_t want = (N + 7) / 8;
     int max_blocks = sm_count() * 16;
     int blocks = (int)(want < max_blocks ? want : max_blocks);
     LaunchScope ls_(NRF_CAT_ENCODE, as_stream(stream));
-    if (out_bf16) encode_points_kernel<__nv_bfloat16><<<blocks, threads, 0, as_stream(stream)>>>(a);
+    if (out_bf16 == 2) encode_points_kernel<__half><<<blocks, threads, 0, as_stream(stream)>>>(a);
+    else if (out_bf16) encode_points_kernel<__nv_bfloat16><<<blocks, threads, 0, as_stream(stream)>>>(a);
     else encode_points_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(a);
   }
   NRF_LAUNCH_OK();

@@ -62,13 +62,34 @@ struct FusedDesc {
                                      // by the backward (same slot numbering as `saves` of the forward)
   float* out; int d_out; int ldo;    // forward: raw field outputs
   void* prof;                        // optional: 32 int64 cycle counters per CTA (diagnostics), NULL otherwise
+  int half;                          // forward only: fp16 operands (weights, field input, activations, residual stream;
+                                     // NRF_PREC_FP16); what it SAVES for the backward is bf16 either way
 };
 int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream);
 
-int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream);
+// Operand formats of a tcgen05 GEMM (0 bf16, 1 fp16: the same kind::f16 rate).  A and B must agree: the instruction
+// descriptor has a format field per operand, but fp16 x bf16 faults with "illegal instruction" on B200 (measured,
+// scripts/fp16_probe.py) - which is why the NRF_PREC_FP16 mode keeps a bf16 copy of everything its backward multiplies.
+//   gemm_tc : a = [A0|A1|A2], b = B, io = resid / out_act / out_act2 (mask_src is read by its bits: any 16-bit float)
+//   wgrad_tc: a = G, b = A
+struct OpFmt { int a_half, b_half, io_half; };
+static inline OpFmt op_fmt(int precision) {
+  const int h = precision == NRF_PREC_FP16;
+  OpFmt f = {h, h, h};
+  return f;
+}
+constexpr OpFmt kFmtBf16 = {0, 0, 0};
+int gemm_tc_launch(const NrfGemm& g, OpFmt fmt, cudaStream_t stream);
 int gemm_simt_launch(const NrfGemm& g, cudaStream_t stream);
 int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
-                    int k_valid, float* dW, int ldw, float* dbias, void* workspace, cudaStream_t stream);
+                    int k_valid, float* dW, int ldw, float* dbias, void* workspace, OpFmt fmt, cudaStream_t stream);
+// NRF_PREC_BF16X3 (mlp_x3.cu): split-bf16 operands, three MMAs per product, fp32-grade accuracy on the tensor cores
+int mlp_x3_sizes(const NrfMlpParams* p, NrfMlpSizes* out);
+int mlp_x3_pack(const NrfMlpParams* p, void* packed, cudaStream_t s);
+int mlp_x3_fwd(const NrfMlpParams* p, const void* packed, const float* field_in, int64_t N, void* acts,
+               float* field_out, cudaStream_t s);
+int mlp_x3_bwd(const NrfMlpParams* p, const void* packed, int64_t N, const void* acts, const float* d_field,
+               const NrfMlpGrads* gr, float* dlatent, void* scratch, cudaStream_t s);
 int wgrad_simt_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
                       int k_valid, float* dW, int ldw, float* dbias, cudaStream_t stream);
 

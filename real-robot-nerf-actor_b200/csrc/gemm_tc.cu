@@ -41,7 +41,20 @@ struct FwdArgs {
   const float* bias;
   int has_mask, has_resid, has_outA, relu_a, has_outB, relu_b, f32_out;
   int dbg;                   // NRF_DBG experiments: 1 = no TMA stores, 2 = no epilogue at all (timing only!)
+  uint32_t idesc;            // tcgen05 instruction descriptor (tile shape + the operand formats, OpFmt)
+  int io_half;               // resid / out_act / out_act2 are fp16 (1) or bf16 (0)
 };
+// 16-bit operand <-> fp32 in either format (warp-uniform run-time choice: this is the layer-by-layer chain, not the
+// fused kernel's hot loop)
+__device__ __forceinline__ uint32_t pack_op16(float lo, float hi, bool half) {
+  uint32_t r;
+  if (half) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float op16_to_f32(uint16_t h, bool half) {
+  return half ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);
+}
 // compile-time epilogue kinds (EPI < 0: decided at run time from FwdArgs)
 constexpr int kEpiMask = 1, kEpiResid = 2, kEpiOutB = 4, kEpiF32 = 8;
 
@@ -139,7 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp == 1) {
     if (cta_leader) {
-      constexpr uint32_t idesc = make_idesc(kTileM * CG, BN, 0, 0);
+      const uint32_t idesc = a.idesc;
       PipeState st;
       for (int it = 0; it < n_iter; ++it) {
         int as = it & 1;
@@ -186,6 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool has_outB = EPI < 0 ? a.has_outB != 0 : (EPI & kEpiOutB) != 0;
     const bool f32_out = EPI < 0 ? a.f32_out != 0 : (EPI & kEpiF32) != 0;
     const bool has_in = has_mask || has_resid;
+    const bool io_half = a.io_half != 0;
     const uint32_t in_bytes = (uint32_t)((has_mask ? 1 : 0) + (has_resid ? 1 : 0)) * Cfg::kEpiBuf;
     // per group: [outA x2 | outB-or-mask x2 | resid x2] 8 KB buffers; an fp32 output chunk (16 KB) uses the
     // first four.  A second output and a ReLU-gate input never occur in the same GEMM.
@@ -280,10 +294,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 mk = *reinterpret_cast<const uint4*>(mrow + ((j ^ sw64) << 4));
-              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&mk);
+              const uint16_t* h = reinterpret_cast<const uint16_t*>(&mk);
 #pragma unroll
-              for (int t = 0; t < 8; ++t)
-                if (!(__bfloat162float(h[t]) > 0.0f)) x[j * 8 + t] = 0.0f;
+              for (int t = 0; t < 8; ++t)      // "> 0" read off the bits: sign clear and non-zero, in bf16 and fp16 alike
+                if (!((int16_t)h[t] > 0)) x[j * 8 + t] = 0.0f;
             }
           }
           if (has_resid) {
@@ -291,9 +305,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 rk = *reinterpret_cast<const uint4*>(rrow + ((j ^ sw64) << 4));
-              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&rk);
+              const uint16_t* h = reinterpret_cast<const uint16_t*>(&rk);
 #pragma unroll
-              for (int t = 0; t < 8; ++t) x[j * 8 + t] += __bfloat162float(h[t]);
+              for (int t = 0; t < 8; ++t) x[j * 8 + t] += op16_to_f32(h[t], io_half);
             }
           }
         }
@@ -314,8 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int t = 0; t < 4; ++t) {
                 float p = x[j * 8 + 2 * t], r = x[j * 8 + 2 * t + 1];
                 if (a.relu_a) { p = fmaxf(p, 0.0f); r = fmaxf(r, 0.0f); }
-                __nv_bfloat162 h = __floats2bfloat162_rn(p, r);
-                w[t] = *reinterpret_cast<uint32_t*>(&h);
+                w[t] = pack_op16(p, r, io_half);
               }
               *reinterpret_cast<uint4*>(orow + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
@@ -329,8 +342,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int t = 0; t < 4; ++t) {
                 float p = x[j * 8 + 2 * t], r = x[j * 8 + 2 * t + 1];
                 if (a.relu_b) { p = fmaxf(p, 0.0f); r = fmaxf(r, 0.0f); }
-                __nv_bfloat162 h = __floats2bfloat162_rn(p, r);
-                w[t] = *reinterpret_cast<uint32_t*>(&h);
+                w[t] = pack_op16(p, r, io_half);
               }
               *reinterpret_cast<uint4*>(orow + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
@@ -388,7 +400,8 @@ template <int BK_, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA, int M,
                 int k_tiles, int m_per_split, int n_valid, int k_valid, float* __restrict__ dW, int ldw,
-                float* __restrict__ dbias, float* __restrict__ ws, int n_pad, int k_pad) {
+                float* __restrict__ dbias, float* __restrict__ ws, int n_pad, int k_pad, uint32_t idesc,
+                uint32_t idesc_bias, uint32_t ones_word) {
   using Cfg = WgCfg<BK_, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -416,7 +429,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
   const int bias_mask = (k_tiles & (k_tiles - 1)) == 0 ? k_tiles - 1 : 0;
   if (warp >= kEpiWarp0) {
     for (int i = threadIdx.x - kEpiWarp0 * 32; i < Cfg::kOnes / 4; i += 128)
-      reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;      // two bf16 1.0
+      reinterpret_cast<uint32_t*>(ones)[i] = ones_word;        // two 1.0 in the B operand's format
     fence_proxy_async();
   }
 
@@ -468,8 +481,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
     }
   } else if (warp == 1) {
     if (cta_leader) {
-      constexpr uint32_t idesc = make_idesc(kTileM * CG, BK_, 1, 1);
-      constexpr uint32_t idesc_bias = make_idesc(kTileM * CG, 16, 1, 1);
       const uint64_t odesc = make_sdesc(smem_u32(ones), kTileK * 128, 1024);
       PipeState st;
       uint32_t bias_acc = 0;                       // the first bias MMA of this CTA overwrites its accumulator columns
@@ -591,7 +602,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 
 // ----------------------------------------------------------------------------------- host side
 template <int BN, int CG, int EPI>
-static int launch_fwd(const NrfGemm& g, cudaStream_t stream) {
+static int launch_fwd(const NrfGemm& g, OpFmt fmt, cudaStream_t stream) {
   using Cfg = FwdCfg<BN, CG>;
   const int a_rows = kTileM, b_rows = BN / CG;   // TMA box heights
   CUtensorMap tmA[3], tmB, tmMask, tmResid, tmOutA, tmOutB, tmOutF;
@@ -630,11 +641,10 @@ static int launch_fwd(const NrfGemm& g, cudaStream_t stream) {
   a.has_outB = g.out_act2 != nullptr; a.relu_b = g.relu_act2;
   a.f32_out = g.out_f32 != nullptr;
   { const char* e = getenv("NRF_DBG"); a.dbg = e ? atoi(e) : 0; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    NRF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    attr_set = true;
-  }
+  a.idesc = make_idesc(kTileM * CG, BN, 0, 0, fmt.a_half, fmt.b_half);
+  a.io_half = fmt.io_half;
+  // per launch: the attribute is per (function, device), see mlp_fused_launch
+  NRF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   int m_tiles = (g.M + kTileM - 1) / kTileM, n_tiles = g.N / BN;
   int tiles = m_tiles * n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
@@ -658,7 +668,8 @@ static int launch_fwd(const NrfGemm& g, cudaStream_t stream) {
   return NRF_OK;
 }
 
-int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream) {
+int gemm_tc_launch(const NrfGemm& g, OpFmt fmt, cudaStream_t stream) {
+  NRF_REQUIRE(fmt.a_half == fmt.b_half, NRF_ENOSUP, "gemm_tc: mixed fp16 / bf16 operands are not executable");
   NRF_REQUIRE(g.K[0] > 0 && g.K[0] % kTileK == 0 && g.K[1] % kTileK == 0 && g.K[2] % kTileK == 0, NRF_ENOSUP,
               "gemm_tc: K = %d,%d,%d must be multiples of 64", g.K[0], g.K[1], g.K[2]);
   NRF_REQUIRE(g.K[2] == 0 || g.K[1] > 0, NRF_EINVAL, "gemm_tc: A[2] needs A[1]");
@@ -677,34 +688,35 @@ int gemm_tc_launch(const NrfGemm& g, cudaStream_t stream) {
     int epi = (g.mask_src ? kEpiMask : 0) | (g.resid ? kEpiResid : 0) | (g.out_act2 ? kEpiOutB : 0) |
               (g.out_f32 ? kEpiF32 : 0);
     switch (epi) {
-      case 0: return launch_fwd<256, 2, 0>(g, stream);
-      case kEpiOutB: return launch_fwd<256, 2, kEpiOutB>(g, stream);
-      case kEpiResid: return launch_fwd<256, 2, kEpiResid>(g, stream);
-      case kEpiResid | kEpiOutB: return launch_fwd<256, 2, kEpiResid | kEpiOutB>(g, stream);
-      case kEpiMask: return launch_fwd<256, 2, kEpiMask>(g, stream);
-      case kEpiMask | kEpiResid: return launch_fwd<256, 2, kEpiMask | kEpiResid>(g, stream);
-      case kEpiF32: return launch_fwd<256, 2, kEpiF32>(g, stream);
-      default: return launch_fwd<256, 2, -1>(g, stream);
+      case 0: return launch_fwd<256, 2, 0>(g, fmt, stream);
+      case kEpiOutB: return launch_fwd<256, 2, kEpiOutB>(g, fmt, stream);
+      case kEpiResid: return launch_fwd<256, 2, kEpiResid>(g, fmt, stream);
+      case kEpiResid | kEpiOutB: return launch_fwd<256, 2, kEpiResid | kEpiOutB>(g, fmt, stream);
+      case kEpiMask: return launch_fwd<256, 2, kEpiMask>(g, fmt, stream);
+      case kEpiMask | kEpiResid: return launch_fwd<256, 2, kEpiMask | kEpiResid>(g, fmt, stream);
+      case kEpiF32: return launch_fwd<256, 2, kEpiF32>(g, fmt, stream);
+      default: return launch_fwd<256, 2, -1>(g, fmt, stream);
     }
   }
-  if (BN == 256) return launch_fwd<256, 1, -1>(g, stream);
-  return launch_fwd<128, 1, -1>(g, stream);
+  if (BN == 256) return launch_fwd<256, 1, -1>(g, fmt, stream);
+  return launch_fwd<128, 1, -1>(g, fmt, stream);
 }
 
 template <int BK_, int CG>
 static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
-                        int k_valid, float* dW, int ldw, float* dbias, void* workspace, cudaStream_t stream) {
+                        int k_valid, float* dW, int ldw, float* dbias, void* workspace, OpFmt fmt,
+                        cudaStream_t stream) {
   using Cfg = WgCfg<BK_, CG>;
   CUtensorMap tmG, tmA;
   int rc = make_map(&tmG, G, N, M, ldg, 64, kTileK);
   if (rc) return rc;
   rc = make_map(&tmA, A, K, M, lda, 64, kTileK);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NRF_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<BK_, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    attr_set = true;
-  }
+  NRF_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<BK_, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  // UMMA A operand = G^T (fmt.a_half), B operand = A^T and the ones tile of the bias sums (fmt.b_half)
+  const uint32_t idesc = make_idesc(kTileM * CG, BK_, 1, 1, fmt.a_half, fmt.b_half);
+  const uint32_t idesc_bias = make_idesc(kTileM * CG, 16, 1, 1, fmt.a_half, fmt.b_half);
+  const uint32_t ones_word = fmt.b_half ? 0x3C003C00u : 0x3F803F80u;
   int n_tiles = (n_valid + kTileM - 1) / kTileM;
   if (CG == 2) n_tiles = (n_tiles + 1) / 2 * 2;      // whole CTA pairs
   int k_tiles = (k_valid + BK_ - 1) / BK_;
@@ -729,7 +741,7 @@ static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, i
   cfg.stream = stream;
   { LaunchScope ls_(NRF_CAT_WGRAD, stream);
   NRF_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<BK_, CG>, tmG, tmA, M, k_tiles, m_per, n_valid, k_valid, dW, ldw,
-                                 dbias, ws, n_pad, k_pad));
+                                 dbias, ws, n_pad, k_pad, idesc, idesc_bias, ones_word));
   }
   NRF_LAUNCH_OK();
   if (ws) {
@@ -744,15 +756,17 @@ static int launch_wgrad(const void* G, int ldg, const void* A, int lda, int M, i
 }
 
 int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
-                    int k_valid, float* dW, int ldw, float* dbias, void* workspace, cudaStream_t stream) {
+                    int k_valid, float* dW, int ldw, float* dbias, void* workspace, OpFmt fmt, cudaStream_t stream) {
   NRF_REQUIRE(N % 64 == 0 && K % 64 == 0, NRF_ENOSUP, "wgrad_tc: N=%d, K=%d must be multiples of 64", N, K);
   int rc;
+  // measured on B200: kind::f16 with DIFFERENT A / B formats (fp16 x bf16) faults with "illegal instruction"
+  NRF_REQUIRE(fmt.a_half == fmt.b_half, NRF_ENOSUP, "wgrad_tc: mixed fp16 / bf16 operands are not executable");
   static const bool one_cta = getenv("NRF_WGRAD_1CTA") != nullptr;
   if (k_valid > 128 && n_valid > kTileM && !one_cta)
-    rc = launch_wgrad<256, 2>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
-  else if (k_valid > 128) rc = launch_wgrad<256, 1>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
-  else if (k_valid > 64) rc = launch_wgrad<128, 1>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
-  else rc = launch_wgrad<64, 1>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, stream);
+    rc = launch_wgrad<256, 2>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, fmt, stream);
+  else if (k_valid > 128) rc = launch_wgrad<256, 1>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, fmt, stream);
+  else if (k_valid > 64) rc = launch_wgrad<128, 1>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, fmt, stream);
+  else rc = launch_wgrad<64, 1>(G, ldg, A, lda, M, N, K, n_valid, k_valid, dW, ldw, dbias, workspace, fmt, stream);
   return rc;
 }
 

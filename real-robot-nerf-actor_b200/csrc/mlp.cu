@@ -17,11 +17,14 @@
 //   dL/dz = [g'_0 | g'_1 | g'_2] . [W_z0 ; W_z1 ; W_z2]                       one GEMM, K = 3 H
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include "gemm_common.cuh"
 
 namespace nrf {
 
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+// tensor-core modes: 16-bit operands (bf16, or fp16 forward operands with bf16 gradients), fp32 accumulate
+static inline bool is_tc(int precision) { return precision == NRF_PREC_BF16 || precision == NRF_PREC_FP16; }
 
 struct MlpLayout {
   int H, C, Din, Dout, nb, nz;
@@ -40,14 +43,14 @@ static int make_layout(const NrfMlpParams* p, int precision, MlpLayout* L) {
   NRF_REQUIRE(p->n_blocks >= 1 && p->n_blocks <= NRF_MAX_BLOCKS && p->n_lin_z >= 0 &&
                   p->n_lin_z <= p->n_blocks, NRF_EINVAL, "mlp: n_blocks=%d n_lin_z=%d", p->n_blocks, p->n_lin_z);
   NRF_REQUIRE(p->d_in > 0 && p->d_hidden > 0 && p->d_out > 0 && p->d_latent >= 0, NRF_EINVAL, "mlp: bad dims");
-  NRF_REQUIRE(precision == NRF_PREC_BF16 || precision == NRF_PREC_FP32, NRF_EINVAL, "mlp: precision %d", precision);
+  NRF_REQUIRE(is_tc(precision) || precision == NRF_PREC_FP32, NRF_EINVAL, "mlp: precision %d", precision);
   L->H = p->d_hidden; L->C = p->d_latent; L->Din = p->d_in; L->Dout = p->d_out;
   L->nb = p->n_blocks; L->nz = p->d_latent > 0 ? p->n_lin_z : 0;
-  L->es = precision == NRF_PREC_BF16 ? 2 : 4;
+  L->es = is_tc(precision) ? 2 : 4;
   L->kin_pad = (int)round_up(L->C + L->Din, 64);
   L->dout_pad = (int)round_up(L->Dout, 64);
   L->nout_pad = (int)round_up(L->Dout, 128);
-  if (precision == NRF_PREC_BF16) {
+  if (is_tc(precision)) {
     NRF_REQUIRE(L->H % 128 == 0, NRF_ENOSUP, "mlp(bf16): d_hidden=%d must be a multiple of 128", L->H);
     NRF_REQUIRE(L->C % 64 == 0 && L->C > 0, NRF_ENOSUP,
                 "mlp(bf16): d_latent=%d must be a multiple of 64", L->C);
@@ -74,33 +77,68 @@ static int make_layout(const NrfMlpParams* p, int precision, MlpLayout* L) {
   return NRF_OK;
 }
 
-// dst[r*ld_dst + c] = T(src[...]) for r < rows, c < cols;  src element (r,c) is src[r*ld_src + c]
-// or, transposed, src[c*ld_src + r].
-template <typename T>
-__global__ void pack_matrix_kernel(T* __restrict__ dst, int ld_dst, int rows, int cols,
-                                   const float* __restrict__ src, int ld_src, int transpose) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)rows * cols) return;
-  int r = (int)(t / cols), c = (int)(t % cols);
-  float v = transpose ? src[(int64_t)c * ld_src + r] : src[(int64_t)r * ld_src + c];
-  if constexpr (sizeof(T) == 2) dst[(int64_t)r * ld_dst + c] = __float2bfloat16_rn(v);
-  else dst[(int64_t)r * ld_dst + c] = v;
-}
-
-__global__ void add_bias_kernel(float* __restrict__ dst, const float* __restrict__ a,
-                                const float* __restrict__ b, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = (a ? a[i] : 0.0f) + (b ? b[i] : 0.0f);
-}
+// Packing = ONE kernel launch over a table of segments (it is re-run every training step: an optimizer writing through
+// `p.data` leaves no trace a cached copy could be keyed on).
+//   mode 0: dst[r*ld_dst + c] = T(src[r*ld_src + c])      mode 1: dst[r*ld_dst + c] = T(src[c*ld_src + r])
+//   mode 2: fp32 dst[c] = src[c] + src2[c]  (merged biases; either source may be NULL)
+struct PackSeg {
+  const float* src; const float* src2;
+  int64_t dst_off;            // bytes from the packed base
+  int ld_dst, rows, cols, ld_src, mode, pad_;
+};
+constexpr int kMaxPackSegs = 72;
+struct PackTable { int n; PackSeg seg[kMaxPackSegs]; };
 
 template <typename T>
-static int pack(void* base, int64_t off, int ld_dst, int rows, int cols, const float* src, int ld_src,
-                int transpose, int col0, cudaStream_t s) {
-  if (!src) return NRF_OK;
-  T* dst = reinterpret_cast<T*>(reinterpret_cast<char*>(base) + off) + col0;
-  int64_t n = (int64_t)rows * cols;
+__global__ void __launch_bounds__(256) pack_table_kernel(const __grid_constant__ PackTable tab, char* __restrict__ base) {
+  const PackSeg& sg = tab.seg[blockIdx.y];
+  const int64_t n = (int64_t)sg.rows * sg.cols;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(t / sg.cols), c = (int)(t % sg.cols);
+    if (sg.mode == 2) {
+      reinterpret_cast<float*>(base + sg.dst_off)[c] = (sg.src ? sg.src[c] : 0.0f) + (sg.src2 ? sg.src2[c] : 0.0f);
+      continue;
+    }
+    const float v = sg.mode == 1 ? sg.src[(int64_t)c * sg.ld_src + r] : sg.src[(int64_t)r * sg.ld_src + c];
+    T* dst = reinterpret_cast<T*>(base + sg.dst_off) + (int64_t)r * sg.ld_dst + c;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) *dst = __float2bfloat16_rn(v);
+    else if constexpr (std::is_same<T, __half>::value) {
+      // NRF_PREC_FP16: the forward's matrices are fp16; the transposed ones belong to the backward, which is bf16
+      if (sg.mode == 1) *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(v);
+      else *dst = __float2half_rn(v);
+    } else *dst = v;
+  }
+}
+
+// fp16 -> bf16 copy of a forward operand the (bf16) backward multiplies with: (rows, cols) with cols % 8 == 0
+__global__ void __launch_bounds__(256) half_to_bf16_kernel(const __half* __restrict__ src, int ld_src,
+                                                           __nv_bfloat16* __restrict__ dst, int ld_dst, int64_t rows,
+                                                           int cols) {
+  const int c8 = cols / 8;
+  const int64_t n = rows * c8;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / c8;
+    const int c = (int)(t % c8) * 8;
+    const uint4 u = *reinterpret_cast<const uint4*>(src + r * ld_src + c);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+    uint4 o;
+    __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      q[i] = __floats2bfloat162_rn(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(dst + r * ld_dst + c) = o;
+  }
+}
+static int half_to_bf16(const void* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, cudaStream_t s) {
+  const int64_t n = rows * (cols / 8);
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
   { LaunchScope ls_(NRF_CAT_MISC, s);
-  pack_matrix_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, ld_dst, rows, cols, src, ld_src, transpose);
+  half_to_bf16_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const __half*>(src), ld_src,
+                                                       reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols);
   }
   NRF_LAUNCH_OK();
   return NRF_OK;
@@ -108,38 +146,42 @@ static int pack(void* base, int64_t off, int ld_dst, int rows, int cols, const f
 
 template <typename T>
 static int pack_all(const NrfMlpParams* p, const MlpLayout& L, void* packed, cudaStream_t s) {
-  NRF_CUDA_OK(cudaMemsetAsync(packed, 0, (size_t)L.total, s));
-  char* base = reinterpret_cast<char*>(packed);
-  auto f32 = [&](int64_t off) { return reinterpret_cast<float*>(base + off); };
-  int rc = 0;
-#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  NRF_CUDA_OK(cudaMemsetAsync(packed, 0, (size_t)L.total, s));        // the zero padding between / inside the matrices
+  PackTable tab;
+  tab.n = 0;
+  auto mat = [&](int64_t off, int ld_dst, int rows, int cols, const float* src, int ld_src, int transpose, int col0) {
+    if (!src || tab.n >= kMaxPackSegs) return;
+    PackSeg& g = tab.seg[tab.n++];
+    g.src = src; g.src2 = nullptr; g.dst_off = off + (int64_t)col0 * (int64_t)sizeof(T);
+    g.ld_dst = ld_dst; g.rows = rows; g.cols = cols; g.ld_src = ld_src; g.mode = transpose ? 1 : 0; g.pad_ = 0;
+  };
+  auto bias = [&](int64_t off, const float* a, const float* b, int n) {
+    if (tab.n >= kMaxPackSegs) return;
+    PackSeg& g = tab.seg[tab.n++];
+    g.src = a; g.src2 = b; g.dst_off = off; g.ld_dst = n; g.rows = 1; g.cols = n; g.ld_src = n; g.mode = 2; g.pad_ = 0;
+  };
   // W0 = [W_z0 | W_in | 0]
-  if (L.nz > 0) TRY(pack<T>(packed, L.W0, L.kin_pad, L.H, L.C, p->lin_z_w[0], L.C, 0, 0, s));
-  TRY(pack<T>(packed, L.W0, L.kin_pad, L.H, L.Din, p->lin_in_w, L.Din, 0, L.C, s));
-  { LaunchScope ls_(NRF_CAT_MISC, s);
-  add_bias_kernel<<<(L.H + 255) / 256, 256, 0, s>>>(f32(L.bias0), p->lin_in_b, L.nz > 0 ? p->lin_z_b[0] : nullptr, L.H);
-  }
-  NRF_LAUNCH_OK();
+  if (L.nz > 0) mat(L.W0, L.kin_pad, L.H, L.C, p->lin_z_w[0], L.C, 0, 0);
+  mat(L.W0, L.kin_pad, L.H, L.Din, p->lin_in_w, L.Din, 0, L.C);
+  bias(L.bias0, p->lin_in_b, L.nz > 0 ? p->lin_z_b[0] : nullptr, L.H);
   for (int b = 0; b < L.nb; ++b) {
-    TRY(pack<T>(packed, L.Wfc0[b], L.H, L.H, L.H, p->fc0_w[b], L.H, 0, 0, s));
-    TRY(pack<T>(packed, L.Wfc1[b], L.k1cat[b], L.H, L.H, p->fc1_w[b], L.H, 0, 0, s));
-    bool cat = b + 1 < L.nz;
-    if (cat) TRY(pack<T>(packed, L.Wfc1[b], L.k1cat[b], L.H, L.C, p->lin_z_w[b + 1], L.C, 0, L.H, s));
-    { LaunchScope ls_(NRF_CAT_MISC, s);
-    add_bias_kernel<<<(L.H + 255) / 256, 256, 0, s>>>(f32(L.bias1[b]), p->fc1_b[b], cat ? p->lin_z_b[b + 1] : nullptr, L.H);
-    }
-    NRF_LAUNCH_OK();
-    TRY(pack<T>(packed, L.Wfc0T[b], L.H, L.H, L.H, p->fc0_w[b], L.H, 1, 0, s));
-    TRY(pack<T>(packed, L.Wfc1T[b], L.H, L.H, L.H, p->fc1_w[b], L.H, 1, 0, s));
+    mat(L.Wfc0[b], L.H, L.H, L.H, p->fc0_w[b], L.H, 0, 0);
+    mat(L.Wfc1[b], L.k1cat[b], L.H, L.H, p->fc1_w[b], L.H, 0, 0);
+    const bool cat = b + 1 < L.nz;
+    if (cat) mat(L.Wfc1[b], L.k1cat[b], L.H, L.C, p->lin_z_w[b + 1], L.C, 0, L.H);
+    bias(L.bias1[b], p->fc1_b[b], cat ? p->lin_z_b[b + 1] : nullptr, L.H);
+    mat(L.Wfc0T[b], L.H, L.H, L.H, p->fc0_w[b], L.H, 1, 0);
+    mat(L.Wfc1T[b], L.H, L.H, L.H, p->fc1_w[b], L.H, 1, 0);
   }
-  for (int b = 0; b < L.nz; ++b) TRY(pack<T>(packed, L.WzcatT, L.nz * L.H, L.C, L.H, p->lin_z_w[b], L.C, 1, b * L.H, s));
-  TRY(pack<T>(packed, L.Wout, L.H, L.Dout, L.H, p->lin_out_w, L.H, 0, 0, s));
+  for (int b = 0; b < L.nz; ++b) mat(L.WzcatT, L.nz * L.H, L.C, L.H, p->lin_z_w[b], L.C, 1, b * L.H);
+  mat(L.Wout, L.H, L.Dout, L.H, p->lin_out_w, L.H, 0, 0);
+  bias(L.bias_out, p->lin_out_b, nullptr, L.Dout);
+  mat(L.WoutT, L.dout_pad, L.H, L.Dout, p->lin_out_w, L.H, 1, 0);
+  NRF_REQUIRE(tab.n < kMaxPackSegs, NRF_ENOSUP, "nrf_mlp_pack: segment table overflow");
   { LaunchScope ls_(NRF_CAT_MISC, s);
-  add_bias_kernel<<<(L.Dout + 255) / 256, 256, 0, s>>>(f32(L.bias_out), p->lin_out_b, nullptr, L.Dout);
+  pack_table_kernel<T><<<dim3(64, tab.n), 256, 0, s>>>(tab, reinterpret_cast<char*>(packed));
   }
   NRF_LAUNCH_OK();
-  TRY(pack<T>(packed, L.WoutT, L.dout_pad, L.H, L.Dout, p->lin_out_w, L.H, 1, 0, s));
-#undef TRY
   return NRF_OK;
 }
 
@@ -153,8 +195,9 @@ static inline void set_a(NrfGemm& g, int i, const void* A, int K, int lda) {
   g.A[i] = A; g.K[i] = K; g.lda[i] = lda;
 }
 
-static int run_gemm(const NrfGemm& g, int precision, cudaStream_t s) {
-  return precision == NRF_PREC_BF16 ? gemm_tc_launch(g, s) : gemm_simt_launch(g, s);
+// grad: a GEMM of the backward: bf16 operands in both tensor-core modes (see NRF_PREC_FP16)
+static int run_gemm(const NrfGemm& g, int precision, bool grad, cudaStream_t s) {
+  return is_tc(precision) ? gemm_tc_launch(g, grad ? kFmtBf16 : op_fmt(precision), s) : gemm_simt_launch(g, s);
 }
 
 // dW += G^T A and (fused, from the same G tiles) dbias += column sums of G.
@@ -162,8 +205,8 @@ static int run_gemm(const NrfGemm& g, int precision, cudaStream_t s) {
 static int run_wgrad(const void* G, int ldg, const void* A, int lda, int64_t M, int N, int K, int n_valid,
                      int k_valid, float* dW, int ldw, float* dbias, void* ws, int precision, cudaStream_t s) {
   if (!dW) return NRF_OK;
-  return precision == NRF_PREC_BF16
-             ? wgrad_tc_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, dbias, ws, s)
+  return is_tc(precision)
+             ? wgrad_tc_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, dbias, ws, kFmtBf16, s)
              : wgrad_simt_launch(G, ldg, A, lda, (int)M, N, K, n_valid, k_valid, dW, ldw, dbias, s);
 }
 
@@ -173,6 +216,7 @@ using namespace nrf;
 
 extern "C" int nrf_mlp_sizes(const NrfMlpParams* p, int precision, NrfMlpSizes* out) {
   NRF_REQUIRE(out, NRF_EINVAL, "nrf_mlp_sizes: null out");
+  if (precision == NRF_PREC_BF16X3) return mlp_x3_sizes(p, out);
   MlpLayout L;
   int rc = make_layout(p, precision, &L);
   if (rc) return rc;
@@ -182,17 +226,21 @@ extern "C" int nrf_mlp_sizes(const NrfMlpParams* p, int precision, NrfMlpSizes* 
   out->fwd_bytes_per_sample = (int64_t)(2 * L.nb + 2) * L.H * L.es;
   // layer-by-layer chain: dL/dx, dL/dnet and the n_lin_z kept gradients; fused chain: every dL/dx'_b and dL/dnet_b
   out->bwd_bytes_per_sample = (int64_t)(2 * L.nb + 1 > 2 + L.nz ? 2 * L.nb + 1 : 2 + L.nz) * L.H * L.es;
-  out->bwd_fixed_bytes = (int64_t)round_up(nrf_wgrad_workspace_bytes(L.H, L.H), 1024);
+  if (precision == NRF_PREC_FP16)       // bf16 copies for the backward: field_in, and (layer-by-layer chain) one layer
+    out->bwd_bytes_per_sample += (int64_t)(L.kin_pad + L.H) * 2;
+  out->bwd_fixed_bytes = (int64_t)round_up(nrf_wgrad_workspace_bytes(L.H, L.H), 1024) + 4096;   // + alignment slack
   return NRF_OK;
 }
 
 extern "C" int nrf_mlp_pack(const NrfMlpParams* p, int precision, void* packed, void* stream) {
   NRF_REQUIRE(packed, NRF_EINVAL, "nrf_mlp_pack: null buffer");
+  if (precision == NRF_PREC_BF16X3) return mlp_x3_pack(p, packed, as_stream(stream));
   MlpLayout L;
   int rc = make_layout(p, precision, &L);
   if (rc) return rc;
-  return precision == NRF_PREC_BF16 ? pack_all<__nv_bfloat16>(p, L, packed, as_stream(stream))
-                                    : pack_all<float>(p, L, packed, as_stream(stream));
+  if (precision == NRF_PREC_BF16) return pack_all<__nv_bfloat16>(p, L, packed, as_stream(stream));
+  if (precision == NRF_PREC_FP16) return pack_all<__half>(p, L, packed, as_stream(stream));
+  return pack_all<float>(p, L, packed, as_stream(stream));
 }
 
 // The fused kernel is built for the reference's field MLP: 512 hidden units, a latent of 64 or 128 channels that
@@ -208,9 +256,10 @@ static void* g_fused_prof = nullptr;
 extern "C" void nrf_debug_set_fused_profile(void* device_buffer) { g_fused_prof = device_buffer; }
 
 static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* W, const void* field_in, int64_t N,
-                         void* acts, float* field_out, cudaStream_t s) {
+                         void* acts, float* field_out, int precision, cudaStream_t s) {
   FusedDesc d;
   memset(&d, 0, sizeof(d));
+  d.half = precision == NRF_PREC_FP16;
   const int kbH = L.H / 64, kbC = L.C / 64;
   int l = 0;
   auto add = [&](const void* Wl, int ldw, int kb_main, int kb_z, int kind, int a_src, int first, int slot,
@@ -243,9 +292,10 @@ static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* 
 // dL/dnet_b at slot nb + 1 + b: the same slot numbering as the forward's `acts`, so that every weight gradient is
 // G[slot]^T . acts[slot'] (see nrf_mlp_bwd).
 static int mlp_bwd_fused(const MlpLayout& L, const char* W, const void* d_field, int64_t N, const void* acts,
-                         void* G, cudaStream_t s) {
+                         void* G, int precision, cudaStream_t s) {
   FusedDesc d;
   memset(&d, 0, sizeof(d));
+  (void)precision;                                 // the backward is bf16 in both tensor-core modes
   const int kbH = L.H / 64;
   int l = 0;
   auto add = [&](const void* Wl, int ldw, int kb_main, int kind, int a_src, int first, int slot, int mask_slot) {
@@ -280,21 +330,23 @@ static int mlp_bwd_fused(const MlpLayout& L, const char* W, const void* d_field,
 extern "C" int nrf_mlp_fused_supported(const NrfMlpParams* p, int precision) {
   MlpLayout L;
   if (make_layout(p, precision, &L)) return 0;
-  return precision == NRF_PREC_BF16 && fused_supported(L) ? 1 : 0;
+  return is_tc(precision) && fused_supported(L) ? 1 : 0;
 }
 
 static int mlp_fwd_impl(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
                         int64_t N, void* acts, float* field_out, void* stream, bool allow_fused) {
   NRF_REQUIRE(packed && field_in && field_out && N > 0, NRF_EINVAL, "nrf_mlp_fwd: bad arguments");
   NRF_REQUIRE(N < (int64_t)1 << 31, NRF_ENOSUP, "nrf_mlp_fwd: N too large for one call");
+  if (precision == NRF_PREC_BF16X3)
+    return mlp_x3_fwd(p, packed, reinterpret_cast<const float*>(field_in), N, acts, field_out, as_stream(stream));
   MlpLayout L;
   int rc = make_layout(p, precision, &L);
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
   const char* W = reinterpret_cast<const char*>(packed);
   static const bool layered = getenv("NRF_MLP_LAYERED") != nullptr;
-  if (allow_fused && precision == NRF_PREC_BF16 && fused_supported(L) && !layered)
-    return mlp_fwd_fused(p, L, W, field_in, N, acts, field_out, s);
+  if (allow_fused && is_tc(precision) && fused_supported(L) && !layered)
+    return mlp_fwd_fused(p, L, W, field_in, N, acts, field_out, precision, s);
   NRF_REQUIRE(acts, NRF_EINVAL, "nrf_mlp_fwd: the layer-by-layer chain needs the activation buffer");
   char* act = reinterpret_cast<char*>(acts);
   const int64_t layer = N * L.H * (int64_t)L.es;
@@ -308,7 +360,7 @@ static int mlp_fwd_impl(const NrfMlpParams* p, const void* packed, int precision
   g.bias = reinterpret_cast<const float*>(W + L.bias0);
   g.out_act = xcur; g.ldact = L.H;
   g.out_act2 = ax(0); g.ldact2 = L.H; g.relu_act2 = 1;
-  rc = run_gemm(g, precision, s);
+  rc = run_gemm(g, precision, false, s);
   if (rc) return rc;
   for (int b = 0; b < L.nb; ++b) {
     g = gemm_init(N, L.H, L.H);
@@ -316,7 +368,7 @@ static int mlp_fwd_impl(const NrfMlpParams* p, const void* packed, int precision
     g.B = W + L.Wfc0[b]; g.ldb = L.H;
     g.bias = p->fc0_b[b];
     g.out_act = an(b); g.ldact = L.H; g.relu_act = 1;
-    rc = run_gemm(g, precision, s);
+    rc = run_gemm(g, precision, false, s);
     if (rc) return rc;
     g = gemm_init(N, L.H, L.H);
     set_a(g, 0, an(b), L.H, L.H);
@@ -330,7 +382,7 @@ static int mlp_fwd_impl(const NrfMlpParams* p, const void* packed, int precision
     } else {
       g.out_act = ax(b + 1); g.ldact = L.H; g.relu_act = 1;  // only relu(x_nb) is needed after the last block
     }
-    rc = run_gemm(g, precision, s);
+    rc = run_gemm(g, precision, false, s);
     if (rc) return rc;
   }
   g = gemm_init(N, L.nout_pad, L.Dout);
@@ -338,7 +390,7 @@ static int mlp_fwd_impl(const NrfMlpParams* p, const void* packed, int precision
   g.B = W + L.Wout; g.ldb = L.H;
   g.bias = reinterpret_cast<const float*>(W + L.bias_out);
   g.out_f32 = field_out; g.ldo = L.Dout;
-  return run_gemm(g, precision, s);
+  return run_gemm(g, precision, false, s);
 }
 
 extern "C" int nrf_mlp_fwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
@@ -357,6 +409,9 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
   NRF_REQUIRE(packed && field_in && acts && d_field && gr && scratch && N > 0, NRF_EINVAL,
               "nrf_mlp_bwd: bad arguments");
   NRF_REQUIRE(N < (int64_t)1 << 31, NRF_ENOSUP, "nrf_mlp_bwd: N too large for one call");
+  if (precision == NRF_PREC_BF16X3)
+    return mlp_x3_bwd(p, packed, N, acts, reinterpret_cast<const float*>(d_field), gr, dlatent, scratch,
+                      as_stream(stream));
   MlpLayout L;
   int rc = make_layout(p, precision, &L);
   if (rc) return rc;
@@ -364,25 +419,39 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
   cudaStream_t s = as_stream(stream);
   const char* W = reinterpret_cast<const char*>(packed);
   const char* act = reinterpret_cast<const char*>(acts);
-  const char* fin = reinterpret_cast<const char*>(field_in);
   const int64_t layer = N * L.H * (int64_t)L.es;
   auto ax = [&](int b) { return act + (int64_t)b * layer; };
   auto an = [&](int b) { return act + (int64_t)(L.nb + 1 + b) * layer; };
   char* sc = reinterpret_cast<char*>(scratch);
   int64_t fixed = round_up(nrf_wgrad_workspace_bytes(L.H, L.H), 1024);
   void* wws = gr->deterministic ? sc : nullptr;   // per-split partial tiles of the weight gradients (ordered reduce)
-  char* gbuf = sc + fixed;                    // dL/dx, updated in place while b >= n_lin_z
-  char* dnet = gbuf + layer;
-  auto gz = [&](int b) { return dnet + (int64_t)(1 + b) * layer; };   // dL/dx'_b kept for dL/dz, b < n_lin_z
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
-
   static const bool layered = getenv("NRF_MLP_LAYERED") != nullptr;
-  if (precision == NRF_PREC_BF16 && fused_supported(L) && !layered && !force_layered) {
+  const bool fused = is_tc(precision) && fused_supported(L) && !layered && !force_layered;
+  const int64_t n_grad_layers = fused ? 2 * L.nb + 1 : 2 + L.nz;
+  // NRF_PREC_FP16: the backward is bf16 (A and B of an MMA must share a format, gradients are bf16), so every forward
+  // operand a weight gradient multiplies with must be bf16: the fused forward saved its activations that way; field_in
+  // (and, in the layer-by-layer chain, each saved fp16 activation layer right before its use) is converted here
+  const bool half = precision == NRF_PREC_FP16;
+  char* fin_bf = sc + fixed + n_grad_layers * layer;
+  char* act_bf = fin_bf + round_up(N * L.kin_pad * 2, 1024);
+  const char* fin = reinterpret_cast<const char*>(field_in);
+  if (half) {
+    TRY(half_to_bf16(field_in, L.kin_pad, fin_bf, L.kin_pad, N, L.kin_pad, s));
+    fin = fin_bf;
+  }
+  auto act16 = [&](const char* a) -> const char* {   // a saved activation layer as the wgrad's bf16 A operand
+    if (!half || fused) return a;
+    rc = half_to_bf16(a, L.H, act_bf, L.H, N, L.H, s);
+    return act_bf;
+  };
+
+  if (fused) {
     // one fused kernel for the whole data-gradient chain, then the weight gradients and dL/dz from its outputs
     char* G = sc + fixed;
     auto gx = [&](int b) { return G + (int64_t)b * layer; };                 // dL/dx'_b, b = 0..nb
     auto gn = [&](int b) { return G + (int64_t)(L.nb + 1 + b) * layer; };    // dL/dnet_b
-    TRY(mlp_bwd_fused(L, W, d_field, N, acts, G, s));
+    TRY(mlp_bwd_fused(L, W, d_field, N, acts, G, precision, s));
     TRY(run_wgrad(d_field, L.dout_pad, ax(L.nb), L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H,
                   gr->lin_out_b, wws, precision, s));
     for (int b = L.nb - 1; b >= 0; --b) {
@@ -397,7 +466,7 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
     for (int b = 0; b < L.nz; ++b) set_a(g, b, gx(b), L.H, L.H);
     g.B = W + L.WzcatT; g.ldb = L.nz * L.H;
     g.out_f32 = dlatent; g.ldo = L.C;
-    TRY(run_gemm(g, precision, s));
+    TRY(run_gemm(g, precision, true, s));
     TRY(run_wgrad(gx(0), L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[0], L.C,
                   gr->lin_z_b[0], wws, precision, s));
     TRY(run_wgrad(gx(0), L.H, fin + (int64_t)L.C * L.es, L.kin_pad, N, L.H, L.kin_pad - L.C, L.H, L.Din, gr->lin_in_w,
@@ -405,20 +474,31 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
     return NRF_OK;
   }
 
+  char* gbuf = sc + fixed;                    // dL/dx, updated in place while b >= n_lin_z
+  char* dnet = gbuf + layer;
+  auto gz = [&](int b) { return dnet + (int64_t)(1 + b) * layer; };   // dL/dx'_b kept for dL/dz, b < n_lin_z
   // lin_out: parameter gradients, then the gradient of x_nb (ReLU-gated by relu(x_nb) > 0)
-  TRY(run_wgrad(d_field, L.dout_pad, ax(L.nb), L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H,
-                gr->lin_out_b, wws, precision, s));
+  {
+    const char* a16 = act16(ax(L.nb));
+    if (rc) return rc;
+    TRY(run_wgrad(d_field, L.dout_pad, a16, L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H,
+                  gr->lin_out_b, wws, precision, s));
+  }
   NrfGemm g = gemm_init(N, L.H, L.H);
   set_a(g, 0, d_field, L.dout_pad, L.dout_pad);
   g.B = W + L.WoutT; g.ldb = L.dout_pad;
   g.mask_src = ax(L.nb); g.ldmask = L.H;
   g.out_act = gbuf; g.ldact = L.H;
-  TRY(run_gemm(g, precision, s));
+  TRY(run_gemm(g, precision, true, s));
 
   const char* gcur = gbuf;                    // dL/dx_{b+1}
   for (int b = L.nb - 1; b >= 0; --b) {
     bool cat = b + 1 < L.nz;
-    TRY(run_wgrad(gcur, L.H, an(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc1_w[b], L.H, gr->fc1_b[b], wws, precision, s));
+    {
+      const char* a16 = act16(an(b));
+      if (rc) return rc;
+      TRY(run_wgrad(gcur, L.H, a16, L.H, N, L.H, L.H, L.H, L.H, gr->fc1_w[b], L.H, gr->fc1_b[b], wws, precision, s));
+    }
     if (cat)
       TRY(run_wgrad(gcur, L.H, fin, L.kin_pad, N, L.H, (int)round_up(L.C, 64), L.H, L.C, gr->lin_z_w[b + 1], L.C,
                     gr->lin_z_b[b + 1], wws, precision, s));
@@ -428,8 +508,12 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
     g.B = W + L.Wfc1T[b]; g.ldb = L.H;
     g.mask_src = an(b); g.ldmask = L.H;
     g.out_act = dnet; g.ldact = L.H;
-    TRY(run_gemm(g, precision, s));
-    TRY(run_wgrad(dnet, L.H, ax(b), L.H, N, L.H, L.H, L.H, L.H, gr->fc0_w[b], L.H, gr->fc0_b[b], wws, precision, s));
+    TRY(run_gemm(g, precision, true, s));
+    {
+      const char* a16 = act16(ax(b));
+      if (rc) return rc;
+      TRY(run_wgrad(dnet, L.H, a16, L.H, N, L.H, L.H, L.H, L.H, gr->fc0_w[b], L.H, gr->fc0_b[b], wws, precision, s));
+    }
     // dL/dx'_b = dL/dx_{b+1} + (dnet_b . W_fc0[b]) gated by relu(x'_b) > 0
     char* target = b < L.nz ? gz(b) : gbuf;
     g = gemm_init(N, L.H, L.H);
@@ -438,18 +522,18 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
     g.mask_src = ax(b); g.ldmask = L.H;
     g.resid = gcur; g.ldr = L.H;
     g.out_act = target; g.ldact = L.H;
-    TRY(run_gemm(g, precision, s));
+    TRY(run_gemm(g, precision, true, s));
     gcur = target;
   }
   // dL/dz = [g'_0 | g'_1 | ...] . [W_z0 ; W_z1 ; ...]
   if (L.nz > 0) {
     int cpad = (int)round_up(L.C, 128);
-    if (precision == NRF_PREC_BF16 || L.nz <= 3) {
-      g = gemm_init(N, precision == NRF_PREC_BF16 ? cpad : L.C, L.C);
+    if (is_tc(precision) || L.nz <= 3) {
+      g = gemm_init(N, is_tc(precision) ? cpad : L.C, L.C);
       for (int b = 0; b < L.nz; ++b) set_a(g, b, gz(b), L.H, L.H);
       g.B = W + L.WzcatT; g.ldb = L.nz * L.H;
       g.out_f32 = dlatent; g.ldo = L.C;
-      TRY(run_gemm(g, precision, s));
+      TRY(run_gemm(g, precision, true, s));
     } else {
       set_error("nrf_mlp_bwd: n_lin_z=%d > 3 is not supported", L.nz);
       return NRF_ENOSUP;

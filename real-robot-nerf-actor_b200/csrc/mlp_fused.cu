@@ -28,6 +28,14 @@
 // registers, and every intermediate gradient (dL/dx'_b, dL/dnet_b: the G operands of the weight-gradient GEMMs)
 // streamed out by TMA stores.  Forward and backward are two "layer programs" for one executor.
 //
+// Operand formats (kind::f16 takes bf16 or fp16 at the same tensor rate): NRF_PREC_BF16 runs everything in bf16;
+// NRF_PREC_FP16 (kHalf) runs the FORWARD with fp16 weights / activations / residual stream (11 significant bits: 6-8 x
+// smaller output error).  Its backward is the bf16 backward unchanged - bf16 gradients need no
+// loss scaling, and gradient error is set by the forward's ReLU-gate flips, not by gradient rounding - so the kHalf
+// forward SAVES its operands as bf16 (converted on their way to the TMA-store staging slot): A and B of one MMA must
+// share a format (fp16 x bf16 is an illegal instruction on B200), and the weight-gradient GEMMs multiply the saved
+// operands with bf16 gradients.
+//
 // Warp roles: 0 TMA producer | 1 MMA issuer (leader CTA only) | 2 TMEM allocator | 3 first-layer input loader |
 // 4-11 epilogue: warp (g, q4) owns
 // rows [32 q4, 32 q4 + 32) x columns [64g, 64g+64) of every 128-column chunk (= its rows of k-block 2c+g of the next
@@ -74,6 +82,7 @@ struct FArgs {
   int n_layers, n_tiles, n_prod;   // n_prod: layers per tile whose epilogue publishes an A operand
   int l_p_free;                    // last layer of a tile whose MMAs read P: after it the next tile's input may land
   int N, d_out, ldo;
+  uint32_t idesc;   // tcgen05 instruction descriptor (M 256, N 128, K-major; operand formats per precision mode)
   int dbg;      // NRF_DBG timing experiments (wrong results!; only in the profiling instantiations, i.e. with a
                 // profile buffer set): 1 no weight TMA, 2 epilogue protocol only, 4 no MMAs, 8 MMA issuer ignores
                 // acc_empty / a_ready
@@ -124,16 +133,50 @@ __device__ __forceinline__ uint64_t add2(uint64_t x, uint64_t y) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
   return r;
 }
-__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {     // {lo, hi} fp32 -> packed bf16 (lo in bits 0-15)
+template <bool kHalf>
+__device__ __forceinline__ uint32_t cvt_op16x2(uint64_t v) {     // {lo, hi} fp32 -> packed bf16 / fp16 (lo in bits 0-15)
   uint32_t lo, hi, r;
   asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  if (kHalf) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
   return r;
 }
-__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t w) {    // bf16(relu(x)) == relu(bf16(x))
+template <bool kHalf>
+__device__ __forceinline__ uint32_t relu_op16x2(uint32_t w) {    // op16(relu(x)) == relu(op16(x))
   uint32_t r;
-  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(w), "r"(0u));
+  if (kHalf) asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(w), "r"(0u));
+  else asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(w), "r"(0u));
   return r;
+}
+__device__ __forceinline__ uint32_t f16x2_to_bf16x2(uint32_t w) {   // the saved copy of an fp16 operand pair
+  uint32_t r;
+  asm("{\n"
+      ".reg .f16 l, h;\n"
+      ".reg .f32 a, b;\n"
+      "mov.b32 {l, h}, %1;\n"
+      "cvt.f32.f16 a, l;\n"
+      "cvt.f32.f16 b, h;\n"
+      "cvt.rn.bf16x2.f32 %0, b, a;\n"
+      "}\n"
+      : "=r"(r)
+      : "r"(w));
+  return r;
+}
+template <bool kHalf>
+__device__ __forceinline__ uint64_t unpack_op16x2(uint32_t r) {  // packed bf16 / fp16 pair -> {lo, hi} fp32 (exact)
+  if (!kHalf) return pair_u32(r << 16, r & 0xffff0000u);
+  uint64_t o;
+  asm("{\n"
+      ".reg .f16 l, h;\n"
+      ".reg .f32 a, b;\n"
+      "mov.b32 {l, h}, %1;\n"
+      "cvt.f32.f16 a, l;\n"
+      "cvt.f32.f16 b, h;\n"
+      "mov.b64 %0, {a, b};\n"
+      "}\n"
+      : "=l"(o)
+      : "r"(r));
+  return o;
 }
 
 // Bit-packed ReLU gates.  A gate word covers one 32-column sub-chunk of one row: bit j / bit 16+j = element 2j /
@@ -238,7 +281,7 @@ struct EpiCtx {            // per-thread constants of the epilogue
 //   backward: v = gate(acc) (+ g for kLayerX), gate = sign of the forward's saved operand; next operand = bf16(v)
 // Prefetched here and parked until needed: the next chunk's bias values (`nxt`, forward: into the warp's smem slot) or
 // the gate row of the chunk after next (`nxt2`, backward: into mk, which the caller double-buffers by chunk parity).
-template <int KIND, bool kSave, bool kBwd, bool kProf>
+template <int KIND, bool kSave, bool kBwd, bool kProf, bool kHalf>
 __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FArgs& a, const FLayer& L, int c,
                                           uint32_t n, int row0, bool first, uint32_t (&xr)[32], uint2& gate,
                                           const void* nxt, const uint2* gate2) {
@@ -302,14 +345,14 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
       for (int j = 0; j < 16; ++j) {
         uint64_t t = x2[j];
         const uint32_t r = xr[s * 16 + j];
-        if (!first) t = add2(t, pair_u32(r << 16, r & 0xffff0000u));
-        uint32_t xb = cvt_bf16x2(t);
+        if (!first) t = add2(t, unpack_op16x2<kHalf>(r));
+        uint32_t xb = cvt_op16x2<kHalf>(t);
         if (kBwd) {                            // ReLU gate: closed -> the residual gradient passes unchanged
           const uint32_t m = gate_mask(gw, j);
           xb = first ? (xb & m) : ((xb & m) | (r & ~m));
         }
         xr[s * 16 + j] = xb;
-        w[s * 16 + j] = kBwd ? xb : relu_bf16x2(xb);
+        w[s * 16 + j] = kBwd ? xb : relu_op16x2<kHalf>(xb);
       }
       if (L.publish)
         tmem_st16(e.tmem_base + kFColQ + e.lane_off + (uint32_t)(col0 / 2 + s * 16),
@@ -317,7 +360,8 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        w[s * 16 + j] = kBwd ? (cvt_bf16x2(x2[j]) & gate_mask(gw, j)) : relu_bf16x2(cvt_bf16x2(x2[j]));
+        w[s * 16 + j] = kBwd ? (cvt_op16x2<kHalf>(x2[j]) & gate_mask(gw, j))
+                             : relu_op16x2<kHalf>(cvt_op16x2<kHalf>(x2[j]));
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         sts128(prow + (((uint32_t)(s * 4 + j) ^ e.sw128) << 4), w[s * 16 + 4 * j], w[s * 16 + 4 * j + 1],
@@ -336,13 +380,18 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
     }
     // 2. the copies kept for the other pass: operand values by TMA store, ReLU gates bit-packed
     if (save) {
-      if (KIND == kLayerX) {
+      if (KIND == kLayerX || kHalf) {          // (kHalf: relu(net) is saved as bf16 too, so not from its fp16 P panel)
         if (e.lane == 0) bulk_wait_read0();    // the slot's previous TMA store (a whole chunk ago) has read it
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts128(e.slot + e.lane * 128 + (((uint32_t)j ^ e.sw128) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2],
-                 w[4 * j + 3]);
+        for (int j = 0; j < 8; ++j) {
+          if (kHalf)
+            sts128(e.slot + e.lane * 128 + (((uint32_t)j ^ e.sw128) << 4), f16x2_to_bf16x2(w[4 * j]),
+                   f16x2_to_bf16x2(w[4 * j + 1]), f16x2_to_bf16x2(w[4 * j + 2]), f16x2_to_bf16x2(w[4 * j + 3]));
+          else
+            sts128(e.slot + e.lane * 128 + (((uint32_t)j ^ e.sw128) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2],
+                   w[4 * j + 3]);
+        }
         fence_proxy_async();
         __syncwarp();
       } else if (!L.publish) {
@@ -350,7 +399,8 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
         __syncwarp();
       }
       if (e.lane == 0) {
-        tma_store_3d_u32(&maps.acts, KIND == kLayerNet ? e.sP + (2 * c + e.g) * kFPanel + e.q4 * 32 * 128 : e.slot,
+        tma_store_3d_u32(&maps.acts,
+                         KIND == kLayerNet && !kHalf ? e.sP + (2 * c + e.g) * kFPanel + e.q4 * 32 * 128 : e.slot,
                          col0, row0 + e.q4 * 32, L.act_slot);
         bulk_commit();
       }
@@ -375,7 +425,7 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
   }
 }
 
-template <bool kSave, bool kBwd, bool kProf>
+template <bool kSave, bool kBwd, bool kProf, bool kHalf>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FArgs a) {
   using Cfg = FCfg<kSave>;
@@ -495,7 +545,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
       }
     } else if (warp == 1 && cta_leader) {
       // ---- MMA issuer for the pair: the whole warp runs the loop (uniform control flow), one elected lane issues
-      constexpr uint32_t idesc = make_idesc(256, 128, 0, 0);
+      const uint32_t idesc = a.idesc;
       const uint32_t sP_u = smem_u32(sP), sRing_u = smem_u32(sRing);
       PipeState st;
       uint32_t n = 0;                              // running chunk counter -> accumulator buffer / phase
@@ -653,17 +703,17 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
         if (kind == kLayerX) {
 #pragma unroll
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerX, kSave, kBwd, kProf>(e, maps, a, L, c, n, row0, first, xres[c], gate[c & 1],
+            epi_chunk<kLayerX, kSave, kBwd, kProf, kHalf>(e, maps, a, L, c, n, row0, first, xres[c], gate[c & 1],
                                             pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         } else if (kind == kLayerNet) {
 #pragma unroll 2
           for (int c = 0; c < kFChunks; ++c, ++n)
-            epi_chunk<kLayerNet, kSave, kBwd, kProf>(e, maps, a, L, c, n, row0, false, xres[0], gate[c & 1],
+            epi_chunk<kLayerNet, kSave, kBwd, kProf, kHalf>(e, maps, a, L, c, n, row0, false, xres[0], gate[c & 1],
                                               pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         } else if (!kBwd) {
 #pragma unroll 1
           for (int c = 0; c < L.n_chunks; ++c, ++n)
-            epi_chunk<kLayerOut, kSave, kBwd, kProf>(e, maps, a, L, c, n, row0, false, xres[0], gate[0],
+            epi_chunk<kLayerOut, kSave, kBwd, kProf, kHalf>(e, maps, a, L, c, n, row0, false, xres[0], gate[0],
                                               pre_bias(it, l, c + 1), pre_gate(it, l, c + 2));
         }
       }
@@ -752,16 +802,23 @@ int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
   int grid = sm_count() / 2 * 2;
   if (grid > 2 * a.n_tiles) grid = 2 * a.n_tiles;
   const bool prof = a.prof != nullptr;
-  auto kern = d.backward ? (prof ? mlp_fused_kernel<true, true, true> : mlp_fused_kernel<true, true, false>)
-              : save     ? (prof ? mlp_fused_kernel<true, false, true> : mlp_fused_kernel<true, false, false>)
-                         : (prof ? mlp_fused_kernel<false, false, true> : mlp_fused_kernel<false, false, false>);
-  const int which = (d.backward ? 2 : (save ? 1 : 0)) + (prof ? 3 : 0);
+  // the backward is bf16 in every mode; the forward's operands are bf16 or fp16 (kHalf); the cycle-counter
+  // instantiations exist for bf16 only
+  NRF_REQUIRE(!(d.backward && d.half), NRF_EINVAL, "mlp_fused: the backward runs in bf16");
+  const bool half = d.half != 0;
+  NRF_REQUIRE(!(prof && half), NRF_ENOSUP, "mlp_fused: the profiling build covers the bf16 kernels only");
+  a.idesc = make_idesc(256, 128, 0, 0, half, half);
+  auto kern = d.backward ? (prof ? mlp_fused_kernel<true, true, true, false> : mlp_fused_kernel<true, true, false, false>)
+              : save     ? (prof   ? mlp_fused_kernel<true, false, true, false>
+                            : half ? mlp_fused_kernel<true, false, false, true>
+                                   : mlp_fused_kernel<true, false, false, false>)
+                         : (prof   ? mlp_fused_kernel<false, false, true, false>
+                            : half ? mlp_fused_kernel<false, false, false, true>
+                                   : mlp_fused_kernel<false, false, false, false>);
   const int smem_bytes = save ? FCfg<true>::kSmem : FCfg<false>::kSmem;
-  static bool attr_set[6] = {false, false, false, false, false, false};
-  if (!attr_set[which]) {
-    NRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set[which] = true;
-  }
+  // per launch: the attribute is per (function, device); a process-wide "already set" flag breaks the second GPU of a
+  // process, and the call costs well under a microsecond
+  NRF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];

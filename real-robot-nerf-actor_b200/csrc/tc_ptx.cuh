@@ -167,11 +167,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // ---------------------------------------------------------------------------------- descriptors
-// Instruction descriptor, kind::f16: D=f32 (bits 4-5 =1), A=B=bf16 (bits 7-9, 10-12 =1),
+// Instruction descriptor, kind::f16: D=f32 (bits 4-5 =1), A format at bits 7-9, B format at bits 10-12 (0 = fp16,
+// 1 = bf16; the two operands may differ: fp16 activations x bf16 gradients in the NRF_PREC_FP16 weight gradients),
 // a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at 17, M>>4 at 24.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn, int a_half = 0, int b_half = 0) {
+  return (1u << 4) | ((a_half ? 0u : 1u) << 7) | ((b_half ? 0u : 1u) << 10) | ((uint32_t)a_mn << 15) |
+         ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // Shared-memory matrix descriptor, SWIZZLE_128B (layout type 2 at bits 61-63), version 1 (bit 46).
 //   K-major : rows of 64 bf16 (128 B); 8-row atoms 1024 B apart (SBO); LBO unused (1)

@@ -18,6 +18,9 @@ Differences from the reference, all opt-in or invisible to its callers:
 from __future__ import annotations
 
 
+import threading
+import weakref
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -47,32 +50,38 @@ class LossDict(dict):
     """What compute_rendering_loss returns (neural_rendering.py:697-707): 'loss' is the tensor to back-propagate, the
     other ten entries are Python floats.  The reference produces them with 13 `.item()` calls - host syncs between the
     forward and the backward of every step.  Here the seven scalars behind them are copied to pinned host memory
-    asynchronously and become floats the first time any of them is read (or the dict is iterated / printed), so a
-    loop that calls `out['loss'].backward()` before it logs never stalls the GPU."""
+    asynchronously and become floats the first time any of them is read (or the dict is iterated / printed / copied /
+    merged), so a loop that calls `out['loss'].backward()` before it logs never stalls the GPU.
+
+    It IS a dict (isinstance, json.dumps, pickling work).  CPython's C fast paths for exact-dict layouts (`dict(d)`,
+    `{**d}`, `other.update(d)`) are taken only while `__iter__` is dict's own, so overriding `__iter__` / `keys` routes
+    them through `keys()` + `__getitem__`, which resolve first; `|`, `pop`, `setdefault`, ... are overridden too."""
 
     _KEYS = ("loss_rgb_coarse", "loss_rgb_fine", "loss_rgb", "loss_embed_coarse", "loss_embed_fine", "loss_embed",
              "loss_depth_coarse", "loss_depth_fine", "loss_depth", "psnr")
-    _ring, _owners, _next = [], [], 0          # pinned staging buffers, reused round-robin
+    _rings = {}                                # device index -> [pinned staging buffers, weak owners, next slot]
+    _lock = threading.Lock()
 
     def __init__(self, loss, scalars):
         super().__init__(loss=loss)
         for k in self._KEYS:
             dict.__setitem__(self, k, None)
         cls = LossDict
-        if not cls._ring:
-            cls._ring = [torch.empty(7, dtype=torch.float32).pin_memory() for _ in range(8)]
-            cls._owners = [None] * 8
-        i = cls._next
-        cls._next = (i + 1) % len(cls._ring)
-        prev = cls._owners[i]() if cls._owners[i] is not None else None
+        with cls._lock:
+            ring = cls._rings.get(scalars.device.index)
+            if ring is None:
+                ring = cls._rings[scalars.device.index] = [
+                    [torch.empty(7, dtype=torch.float32).pin_memory() for _ in range(8)], [None] * 8, 0]
+            i = ring[2]
+            ring[2] = (i + 1) % len(ring[0])
+            prev = ring[1][i]() if ring[1][i] is not None else None
+            ring[1][i] = weakref.ref(self)
         if prev is not None:
             prev._resolve()                    # its values leave the staging buffer before it is reused
-        self._host = cls._ring[i]
+        self._host = ring[0][i]
         self._host.copy_(scalars, non_blocking=True)
         self._event = torch.cuda.Event()
-        self._event.record()
-        import weakref
-        cls._owners[i] = weakref.ref(self)
+        self._event.record(torch.cuda.current_stream(scalars.device))
 
     def _resolve(self):
         if getattr(self, "_host", None) is None:
@@ -93,6 +102,12 @@ class LossDict(dict):
             self._resolve()
         return dict.get(self, k, default)
 
+    def __iter__(self):
+        return dict.__iter__(self)
+
+    def keys(self):
+        return dict.keys(self)
+
     def items(self):
         self._resolve()
         return dict.items(self)
@@ -104,6 +119,24 @@ class LossDict(dict):
     def copy(self):
         self._resolve()
         return dict(self)
+
+    def pop(self, k, *default):
+        self._resolve()
+        return dict.pop(self, k, *default)
+
+    def popitem(self):
+        self._resolve()
+        return dict.popitem(self)
+
+    def setdefault(self, k, default=None):
+        self._resolve()
+        return dict.setdefault(self, k, default)
+
+    def __or__(self, other):
+        return dict(self) | dict(other)
+
+    def __ror__(self, other):
+        return dict(other) | dict(self)
 
     def __repr__(self):
         self._resolve()
@@ -232,7 +265,7 @@ class _MlpFn(torch.autograd.Function):
         h = ctx.h
         N = ctx.fin.shape[0]
         dpad = h.sizes.dout_pad
-        dfield = torch.zeros(N, dpad, device=d_out.device, dtype=ops.act_dtype(h.precision))
+        dfield = torch.zeros(N, dpad, device=d_out.device, dtype=ops.grad_dtype(h.precision))
         dfield[:, :d_out.shape[1]] = d_out.to(dfield.dtype)
         names = h.names()
         grads = _zero_grads(h)
@@ -370,7 +403,7 @@ class _FieldFn(torch.autograd.Function):
     def backward(ctx, d_out):
         h = ctx.h
         n = ctx.rays.shape[0]
-        d_field = torch.zeros(n, h.sizes.dout_pad, device=d_out.device, dtype=ops.act_dtype(h.precision))
+        d_field = torch.zeros(n, h.sizes.dout_pad, device=d_out.device, dtype=ops.grad_dtype(h.precision))
         d_field[:, :d_out.shape[1]] = d_out.to(d_field.dtype)
         names = h.names()
         grads = _zero_grads(h)
@@ -406,7 +439,7 @@ def _sigma_noise(ren, noise, key, R, K, device):
     return (nz.to(torch.float32) * float(ren.noise_std)).contiguous()
 
 
-def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps, keep_acts=True, sig_noise=None):
+def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps, keep_acts=True, sig_noise=None, repack=None):
     """One composite pass (neural_rendering.py:224-395) over all samples of `z`.  keep_acts=False (no gradient
     will be asked for): the fused MLP kernel keeps nothing but the raw field outputs."""
     st = _PassState()
@@ -414,7 +447,7 @@ def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps, keep_acts=True, 
     st.z_sorted = st.base = None
     st.field_in = ops.encode_points(rays, z, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
                                     ld_out=mlp.sizes.kin_pad, precision=mlp.precision)
-    st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts)
+    st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=repack)
     outs = ops.composite_fwd(st.field_out, z, rays, ren._d_embed, ren.white_bkgd, sigma_noise=sig_noise)
     return st, outs
 
@@ -429,7 +462,7 @@ def _pass_forward_reuse(ren, mlp, vol_cl, rays, z_new, z_sorted, perm, base, rps
     st.z_sorted, st.base = z_sorted, base
     st.field_in = ops.encode_points(rays, z_new, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
                                     ld_out=mlp.sizes.kin_pad, precision=mlp.precision)
-    st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts)
+    st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=False)
     outs = ops.composite_fwd(base.field_out, z_sorted, rays, ren._d_embed, ren.white_bkgd, sigma_noise=sig_noise,
                              reuse=(st.field_out, perm, base.z.shape[1]))
     return st, outs
@@ -561,6 +594,9 @@ class _ForwardNerfFn(torch.autograd.Function):
         rps = R // sb
         mlp_c = ren.nerf_model.mlp_coarse.handle(ren._prec)
         mlp_f = ren.nerf_model.mlp_fine.handle(ren._prec)
+        mlp_c.pack(force=keep)                             # once per step (see FieldMLP.pack); the passes reuse it
+        if mlp_f is not mlp_c:
+            mlp_f.pack(force=keep)
         held = getattr(ren, "_vol_cl_held", None)          # rendering(): one re-layout for all ray chunks
         cl3d = _is_channels_last_3d(voxel_feat)
         if cl3d:                                           # producer ran in torch.channels_last_3d: zero-copy view
@@ -573,7 +609,8 @@ class _ForwardNerfFn(torch.autograd.Function):
         Kc, Kf, Kfd = ren.n_coarse, ren.n_fine, ren.n_fine_depth
         z_c = ops.sample_coarse(rays, Kc, noise.get("coarse"), ren.lindisp)
         st_c, (cw, crgb, cemb, cdep) = _pass_forward(ren, mlp_c, vol_cl, rays, z_c, rps, keep,
-                                                     _sigma_noise(ren, noise, "sigma_c", R, Kc, rays.device))
+                                                     _sigma_noise(ren, noise, "sigma_c", R, Kc, rays.device),
+                                                     repack=False)
         outs = [z_c, cw, crgb, cemb, cdep]
         st_f = None
         depth_mask = None
@@ -602,7 +639,8 @@ class _ForwardNerfFn(torch.autograd.Function):
                 st_f, (fw, frgb, femb, fdep) = _pass_forward_reuse(ren, mlp_f, vol_cl, rays, z_new, z_all, perm,
                                                                    st_c, rps, keep, sn_f)
             else:
-                st_f, (fw, frgb, femb, fdep) = _pass_forward(ren, mlp_f, vol_cl, rays, z_all, rps, keep, sn_f)
+                st_f, (fw, frgb, femb, fdep) = _pass_forward(ren, mlp_f, vol_cl, rays, z_all, rps, keep, sn_f,
+                                                             repack=False)
                 st_f.perm = perm
             outs += [z_all, fw, frgb, femb, fdep]
         ctx.ren, ctx.st_c, ctx.st_f, ctx.sb, ctx.n_pc = ren, st_c, st_f, sb, n_pc

@@ -7,14 +7,37 @@ is an error.
 from __future__ import annotations
 
 import ctypes as C
-
+import functools
 
 import torch
 
 from . import _lib
-from ._lib import NRF_PREC_BF16, NRF_PREC_FP32, check, ptr, stream_ptr
+from ._lib import NRF_PREC_BF16, NRF_PREC_BF16X3, NRF_PREC_FP16, NRF_PREC_FP32, check, ptr, stream_ptr
 
-PRECISIONS = {"bf16": NRF_PREC_BF16, "fp32": NRF_PREC_FP32}
+PRECISIONS = {"bf16": NRF_PREC_BF16, "fp32": NRF_PREC_FP32, "fp16": NRF_PREC_FP16, "bf16x3": NRF_PREC_BF16X3}
+
+
+def _on_tensor_device(fn):
+    """Runs `fn` with the CUDA device of its tensor arguments current (kernels are launched on the current device's
+    current stream: without this a renderer on cuda:1 called while cuda:0 is current would launch on GPU 0 with GPU 1
+    pointers).  Tensors on different devices raise.  One integer comparison per call when the device is already
+    current (the one-process-per-GPU layout)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = None
+        for a in args:
+            if isinstance(a, FieldMLP):
+                a = a.params["lin_in.weight"]
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise _lib.NrfError(f"{fn.__name__}: tensors on different devices ({dev} and {a.device})")
+        if dev is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                return fn(*args, **kw)
+        return fn(*args, **kw)
+    return wrapper
 
 
 def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -26,7 +49,16 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def act_dtype(precision: int):
-    return torch.bfloat16 if precision == NRF_PREC_BF16 else torch.float32
+    """dtype of the forward operands (field input, saved activations) of a precision mode."""
+    return {NRF_PREC_BF16: torch.bfloat16, NRF_PREC_FP16: torch.float16}.get(precision, torch.float32)
+
+
+def grad_dtype(precision: int):
+    """dtype of the gradient operands (d_field ...): bf16 in both tensor-core modes (see NRF_PREC_FP16)."""
+    return torch.bfloat16 if precision in (NRF_PREC_BF16, NRF_PREC_FP16) else torch.float32
+
+
+_OUT_KIND = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 
 # ------------------------------------------------------------------------------------- rays
@@ -53,6 +85,7 @@ def _device_intrinsics(focal, c, width, height, device):
     return intr
 
 
+@_on_tensor_device
 def raygen(poses, width, height, focal, z_near, z_far, c=None):
     """utils.py:477-506 gen_rays.  poses (B,4,4) -> rays (B,H,W,8).
     A `focal` / `c` that lives on the GPU stays there (4 floats handed to the kernel by pointer): reading it back would
@@ -78,6 +111,7 @@ def raygen(poses, width, height, focal, z_near, z_far, c=None):
     return rays
 
 
+@_on_tensor_device
 def sample_coarse(rays, n_coarse, jitter=None, lindisp=False):
     """neural_rendering.py:159-176.  rays (R,8) -> z (R,Kc)."""
     rays = _f32(rays, "rays")
@@ -93,6 +127,7 @@ def sample_coarse(rays, n_coarse, jitter=None, lindisp=False):
     return z
 
 
+@_on_tensor_device
 def sample_fine(rays, weights, n_coarse, u, jitter=None, lindisp=False, cdf=None, out=None,
                 want_ind=False):
     """neural_rendering.py:179-207.  Returns z (R,Kf) (written into out[:, :Kf] when given)."""
@@ -112,6 +147,7 @@ def sample_fine(rays, weights, n_coarse, u, jitter=None, lindisp=False, cdf=None
     return (out, ind) if want_ind else out
 
 
+@_on_tensor_device
 def sort_rows(z, want_perm=False):
     """neural_rendering.py:463.  In-place ascending sort of each row; optional int32 permutation."""
     assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous()
@@ -122,6 +158,7 @@ def sort_rows(z, want_perm=False):
 
 
 # ----------------------------------------------------------------------------------- volume
+@_on_tensor_device
 def volume_to_channels_last(vol):
     """(SB,C,S0,S1,S2) -> (SB,S0,S1,S2,C)."""
     vol = _f32(vol, "voxel_feat")
@@ -132,6 +169,7 @@ def volume_to_channels_last(vol):
     return out
 
 
+@_on_tensor_device
 def volume_to_channels_first(vol_cl):
     """(SB,S0,S1,S2,C) -> (SB,C,S0,S1,S2)."""
     vol_cl = _f32(vol_cl, "volume")
@@ -158,6 +196,7 @@ def _bounds_host(bounds):
     return arr
 
 
+@_on_tensor_device
 def encode_points(rays, z, rays_per_scene, vol_cl, bounds, num_freqs=6, freq_factor=1.5, ld_out=None,
                   precision=NRF_PREC_BF16, want_points=False, out=None):
     """Field-input rows [latent | PE | viewdir | 0] for every sample (see nrf_encode_points)."""
@@ -175,11 +214,12 @@ def encode_points(rays, z, rays_per_scene, vol_cl, bounds, num_freqs=6, freq_fac
     bh = _bounds_host(bounds)
     check(_lib.load().nrf_encode_points(ptr(rays), ptr(z), R, K, rays_per_scene, ptr(vol_cl), SB, Cc, S0, S1,
                                         S2, C.cast(bh, C.c_void_p), num_freqs, float(freq_factor), ptr(out),
-                                        ld_out, int(precision == NRF_PREC_BF16), ptr(pts), stream_ptr()),
+                                        ld_out, _OUT_KIND[out.dtype], ptr(pts), stream_ptr()),
           "nrf_encode_points")
     return (out, pts) if want_points else out
 
 
+@_on_tensor_device
 def scatter_volume_grad(rays, z, rays_per_scene, dlatent, grad_cl, bounds):
     """grad_cl (SB,S0,S1,S2,C) += transpose-of-gather(dlatent (N,C))."""
     rays = _f32(rays, "rays")
@@ -196,6 +236,7 @@ def scatter_volume_grad(rays, z, rays_per_scene, dlatent, grad_cl, bounds):
     return grad_cl
 
 
+@_on_tensor_device
 def scatter_volume_grad_sorted(rays, z, rays_per_scene, dlatent, grad_cl, bounds, accumulate=False):
     """Atomics-free, bit-reproducible scatter (counting sort by voxel + one warp per voxel)."""
     rays = _f32(rays, "rays")
@@ -215,6 +256,7 @@ def scatter_volume_grad_sorted(rays, z, rays_per_scene, dlatent, grad_cl, bounds
     return grad_cl
 
 
+@_on_tensor_device
 def scatter_volume_grad_merged(rays, rays_per_scene, passes, grad, channels_first, bounds):
     """ONE atomics-free scatter for all render passes of a step (see nrf_scatter_volume_grad_merged).
 
@@ -258,6 +300,7 @@ def _reuse_struct(reuse, K, ld, d_field_new=None):
     return st
 
 
+@_on_tensor_device
 def composite_fwd(field_out, z, rays, D, white_bkgd=False, sigma_noise=None, reuse=None):
     """neural_rendering.py:339-359 on RAW MLP outputs (N, 4+D).  -> weights, rgb, embed, depth.
     sigma_noise (R,K): training-time density noise, already scaled by noise_std (neural_rendering.py:336-337)."""
@@ -281,6 +324,7 @@ def composite_fwd(field_out, z, rays, D, white_bkgd=False, sigma_noise=None, reu
     return w, rgb, emb, dep
 
 
+@_on_tensor_device
 def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights=None, ldg=None,
                   precision=NRF_PREC_BF16, white_bkgd=False, want_dz=False, out=None, sigma_noise=None,
                   reuse=None, out_new=None, accumulate=False):
@@ -302,17 +346,17 @@ def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights
     if reuse is not None:
         n_first = reuse[2]
         if out is None:
-            out = torch.empty(R * n_first, ldg, device=z.device, dtype=act_dtype(precision))
-        assert out.shape == (R * n_first, ldg) and out.dtype == act_dtype(precision) and not accumulate
+            out = torch.empty(R * n_first, ldg, device=z.device, dtype=grad_dtype(precision))
+        assert out.shape == (R * n_first, ldg) and out.dtype == grad_dtype(precision) and not accumulate
         if out_new is None:
-            out_new = torch.empty(R * (K - n_first), ldg, device=z.device, dtype=act_dtype(precision))
+            out_new = torch.empty(R * (K - n_first), ldg, device=z.device, dtype=grad_dtype(precision))
         ru = _reuse_struct(reuse, K, field_out.shape[1], out_new)
     elif out is None:
-        out = torch.empty(R * K, ldg, device=z.device, dtype=act_dtype(precision))
+        out = torch.empty(R * K, ldg, device=z.device, dtype=grad_dtype(precision))
     dz = torch.empty(R, K, device=z.device, dtype=torch.float32) if want_dz else None
     check(_lib.load().nrf_composite_bwd(ptr(field_out), field_out.shape[1], ptr(z), ptr(rays), R, K, D,
                                         int(white_bkgd), ptr(d_rgb), ptr(d_embed), ptr(d_depth),
-                                        ptr(d_weights), ptr(out), ldg, int(precision == NRF_PREC_BF16),
+                                        ptr(d_weights), ptr(out), ldg, int(out.dtype == torch.bfloat16),
                                         ptr(dz), ptr(sigma_noise), C.byref(ru) if ru is not None else None,
                                         int(accumulate), stream_ptr()), "nrf_composite_bwd")
     if reuse is not None:
@@ -320,6 +364,7 @@ def composite_bwd(field_out, z, rays, D, d_rgb, d_embed, d_depth=None, d_weights
     return (out, dz) if want_dz else out
 
 
+@_on_tensor_device
 def render_loss(rgb_c, rgb_f, emb_c, emb_f, rays_per_scene, gt_rgb, gt_embed, idx=None, want_grads=True):
     """The four F.mse_loss terms of neural_rendering.py:653-677 and their gradients in one pass (nrf_render_loss).
 
@@ -352,6 +397,7 @@ def render_loss(rgb_c, rgb_f, emb_c, emb_f, rays_per_scene, gt_rgb, gt_embed, id
 
 
 # ------------------------------------------------------------------------------------- GEMMs
+@_on_tensor_device
 def gemm(A1, B, *, A2=None, A3=None, bias=None, mask_src=None, resid=None, out_f32=None, out_act=None,
          relu_act=False, out_act2=None, relu_act2=False, n_store=None, precision=NRF_PREC_BF16):
     """v = resid + mask([A1|A2|A3].B^T + bias) -> out_act / out_act2 / out_f32; test hook over nrf_gemm."""
@@ -376,6 +422,7 @@ def gemm(A1, B, *, A2=None, A3=None, bias=None, mask_src=None, resid=None, out_f
     check(_lib.load().nrf_gemm(C.byref(g), precision, stream_ptr()), "nrf_gemm")
 
 
+@_on_tensor_device
 def wgrad(G, A, dW, dbias=None, n_valid=None, k_valid=None, precision=NRF_PREC_BF16, deterministic=False):
     """dW (n_valid,k_valid) += G^T.A ; dbias += colsum(G).  deterministic: ordered reduction of the sample splits
     through a workspace instead of fp32 atomics."""
@@ -447,9 +494,14 @@ class FieldMLP:
             return t.data_ptr()
         return self._fill(st, get)
 
-    def pack(self):
+    @_on_tensor_device
+    def pack(self, force=False):
+        """The packed operand cache.  Refreshed when a parameter's (data_ptr, version) changes, and ALWAYS when
+        `force` (every training forward passes it: in-place writes through `p.data` - apex / DeepSpeed fused optimizers,
+        EMA swaps, manual clipping - do not bump the Parameter's version counter, and a stale cache would silently
+        disagree with the biases read live from the parameters.  The pack is one 12 MB kernel launch)."""
         key = tuple((self.params[n].data_ptr(), self.params[n]._version) for n in self.names())
-        if self._packed is None or key != self._packed_key:
+        if force or self._packed is None or key != self._packed_key:
             dev = self.params["lin_in.weight"].device
             if self._packed is None or self._packed.device != dev:
                 self._packed = torch.empty(self.sizes.packed_bytes, device=dev, dtype=torch.uint8)
@@ -463,14 +515,17 @@ class FieldMLP:
         """True when nrf_mlp_fwd runs the whole MLP as one persistent tcgen05 kernel (csrc/mlp_fused.cu)."""
         return bool(_lib.load().nrf_mlp_fused_supported(C.byref(self._cparams()), self.precision))
 
-    def forward(self, field_in, acts=None, keep_acts=True, layered=False):
+    @_on_tensor_device
+    def forward(self, field_in, acts=None, keep_acts=True, layered=False, repack=None):
         """field_in (N,kin_pad) -> (field_out (N,d_out) fp32 raw, acts buffer).
 
         keep_acts=False (inference): the fused kernel keeps nothing (acts is None); the layer-by-layer chain
-        still needs its buffer.  layered=True forces the chain (A/B timing, parity tests)."""
+        still needs its buffer.  layered=True forces the chain (A/B timing, parity tests).
+        repack: re-derive the packed weights first (default: whenever activations are kept, i.e. in training; the
+        renderer packs once per forward_nerf and passes False for its passes)."""
         N = field_in.shape[0]
         dev = field_in.device
-        packed = self.pack()
+        packed = self.pack(force=keep_acts if repack is None else repack)
         lib = _lib.load()
         if acts is None and (keep_acts or layered or not self.fused):
             acts = torch.empty(self.sizes.fwd_bytes_per_sample * N, device=dev, dtype=torch.uint8)
@@ -483,6 +538,7 @@ class FieldMLP:
             acts._nrf_layered = bool(layered or not self.fused)
         return out, acts
 
+    @_on_tensor_device
     def backward(self, field_in, acts, d_field, grads: dict, scratch=None, deterministic=False, layered=False):
         """Accumulates parameter grads into `grads` (same keys as params); returns dlatent (N,C).
         deterministic: ordered (bit-reproducible) reduction of the weight-gradient sample splits."""

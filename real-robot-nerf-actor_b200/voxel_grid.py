@@ -62,8 +62,9 @@ class VoxelGrid(nn.Module):
         out = torch.empty(B, S, S, S, 3 + F + 4, device=coords.device, dtype=torch.float32)
         lib = _lib.load()
         ws = torch.empty(lib.nrf_voxelize_workspace_bytes(B, N, S), device=coords.device, dtype=torch.uint8)
-        check(lib.nrf_voxelize(ptr(coords), ptr(coord_features), B, N, F, ptr(geom), S, ptr(out), ptr(ws),
-                               stream_ptr()), "nrf_voxelize")
+        with torch.cuda.device(coords.device):          # launched on the tensors' device, whatever is current
+            check(lib.nrf_voxelize(ptr(coords), ptr(coord_features), B, N, F, ptr(geom), S, ptr(out), ptr(ws),
+                                   stream_ptr()), "nrf_voxelize")
         return out if not only_features else out[..., :-7]
 
     forward = coords_to_bounding_voxel_grid

@@ -56,7 +56,9 @@ def make_renderer(NR, meta, params, precision, **opts):
 
 # --------------------------------------------------------------------------------- field MLP
 @pytest.mark.parametrize("precision,C,H,D,N", [("fp32", 16, 64, 24, 300), ("fp32", 128, 512, 384, 700),
-                                               ("bf16", 128, 512, 384, 1500), ("bf16", 64, 256, 60, 517)])
+                                               ("bf16", 128, 512, 384, 1500), ("bf16", 64, 256, 60, 517),
+                                               ("fp16", 128, 512, 384, 1500), ("fp16", 64, 256, 60, 517),
+                                               ("bf16x3", 128, 512, 384, 700), ("bf16x3", 64, 256, 60, 517)])
 def test_field_mlp_forward_backward(ops, NR, precision, C, H, D, N):
     g = torch.Generator().manual_seed(N)
     p = O.init_params(d_in=42, d_latent=C, d_hidden=H, d_out=4 + D, seed=1)
@@ -69,9 +71,10 @@ def test_field_mlp_forward_backward(ops, NR, precision, C, H, D, N):
     zx = torch.randn(N, C + 42, generator=g)
     zx[:, :C] *= 0.1
     d_out = torch.randn(N, 4 + D, generator=g)
-    if precision == "bf16":
-        zx = zx.to(torch.bfloat16).float()
-        d_out = d_out.to(torch.bfloat16).float()
+    op_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(precision)
+    if op_dtype is not None:
+        zx = zx.to(op_dtype).float()
+        d_out = d_out.to(torch.bfloat16).float()        # gradients are bf16 in both tensor-core modes
     # oracle (fp32, and bf16-operand emulation for the tensor-core mode)
     def run_oracle(operand_dtype):
         pp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
@@ -84,6 +87,18 @@ def test_field_mlp_forward_backward(ops, NR, precision, C, H, D, N):
     out, _ = mlp(x, precision=precision)
     (out * d_out.cuda()).sum().backward()
     got = {k: v.grad for k, v in mlp.named_parameters()}
+    if precision == "bf16x3":
+        # split-bf16 operands, three MMAs per product: fp32-grade on the tensor cores (1.5e-5 forward,
+        # gradients limited by the same ReLU-gate flips as two fp32 accumulation orders)
+        print(f"bf16x3 MLP vs fp32 oracle: out {rel(out, out32):.2e}  dlatent {rel(x.grad[:, :C], dz32):.2e}; worst dparam "
+              f"{max(rel(got[k], gp32[k]) for k in gp32):.2e}")
+        assert rel(out, out32) < 1e-4
+        row_err = ((x.grad[:, :C].cpu() - dz32).norm(dim=1) / (dz32.norm(dim=1) + 1e-30))
+        assert float(row_err.quantile(0.9)) < 2e-4 and rel(x.grad[:, :C], dz32) < 2e-2
+        assert float(x.grad[:, C:].abs().max()) == 0.0
+        for k in gp32:
+            assert rel(got[k], gp32[k]) < 1e-2, k
+        return
     if precision == "fp32":
         assert rel(out, out32) < 2e-5
         # A pre-activation within rounding distance of 0 flips its ReLU gate between two fp32
@@ -94,10 +109,19 @@ def test_field_mlp_forward_backward(ops, NR, precision, C, H, D, N):
         for k in gp32:
             assert rel(got[k], gp32[k]) < 2e-3, k
     else:
-        out16, dz16, gp16 = run_oracle(torch.bfloat16)
+        out16, dz16, gp16 = run_oracle(op_dtype)
         e_out, e_dz = rel(out, out16), rel(x.grad[:, :C], dz16)
-        print(f"bf16 MLP vs bf16-emulated oracle: out {e_out:.2e}  dlatent {e_dz:.2e}; "
-              f"vs fp32 oracle: out {rel(out, out32):.2e}  dlatent {rel(x.grad[:, :C], dz32):.2e}")
+        print(f"{precision} MLP vs {precision}-emulated oracle: out {e_out:.2e}  dlatent {e_dz:.2e}; "
+              f"vs fp32 oracle: out {rel(out, out32):.2e}  dlatent {rel(x.grad[:, :C], dz32):.2e}; worst dparam "
+              f"{max(rel(got[k], gp32[k]) for k in gp32):.2e}")
+        if precision == "fp16":
+            # fp16 forward operands (11 significant bits) + bf16 gradients: SURVEY.md section 10 measured 1.4e-3 / 5e-4
+            # forward and 3.5e-2 gradients (ReLU-gate flips) for fp16 operands
+            assert rel(out, out32) < 2e-3 and e_out < 2e-3
+            assert rel(x.grad[:, :C], dz32) < 8e-2 and cosine(x.grad[:, :C], dz32) > 0.997
+            for k in gp32:
+                assert rel(got[k], gp32[k]) < 6e-2 and cosine(got[k], gp32[k]) > 0.997, k
+            return
         # Operands, the residual stream x' and the gradient stream are all bf16 in HBM; the emulated oracle
         # rounds GEMM operands only, so the binding comparison is against the fp32 oracle with the bounds
         # SURVEY.md section 10 measured for bf16 operands (forward ~6e-3, gradients ~1e-1, cosine > 0.99).
@@ -148,7 +172,7 @@ def test_small_golden_fp32(ops, NR, name):
         assert rel(gk, T(fx["grad." + k])) < 2e-4, k
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16", "bf16x3"])
 def test_full_dims_golden(ops, NR, precision):
     """BASELINE dims (C=128, D=384, hidden 512, 64+64 samples) against the reference's outputs."""
     fx = golden("full_s32")
@@ -178,13 +202,29 @@ def test_full_dims_golden(ops, NR, precision):
         assert max(errs.values()) < 1e-4
         assert abs(float(loss) - float(fx["loss"])) < 1e-5
         assert e_vsum < 3e-4 and e_vsign < 3e-4 and worst_par < 3e-4
+    elif precision == "bf16x3":
+        # the tensor-core mode that meets north_star's <= 1e-3 on every output and gradient
+        # measured: outputs <= 1.9e-5 (weights 7.4e-5), volume gradient 4.2e-4, worst parameter gradient 7.0e-4
+        assert max(errs.values()) < 1e-3
+        assert abs(float(loss) - float(fx["loss"])) < 5e-5
+        assert e_vsum < 1e-3 and e_vsign < 1e-3 and worst_par < 1e-3
+    elif precision == "fp16":
+        # fp16 forward operands vs the fp32 reference: rgb <= 2e-3, embed / depth <= 1e-3
+        # measured: coarse 3.7e-4 / 5.6e-4 / 1.5e-4, fine 1.0e-3 / 1.3e-3 / 6.2e-4 (the fine pass also sees the coarse
+        # pass's error through its importance samples); gradients 5e-2 (gate flips), 8 x / 3 x below bf16
+        assert errs[("coarse", "rgb")] < 1e-3 and errs[("coarse", "embed")] < 1e-3 and errs[("coarse", "depth")] < 1e-3, errs
+        assert errs[("fine", "rgb")] < 2e-3 and errs[("fine", "embed")] < 2e-3 and errs[("fine", "depth")] < 1e-3, errs
+        assert abs(float(loss) - float(fx["loss"])) < 2e-4
+        assert e_vsum < 8e-2 and e_vsign < 8e-2 and worst_par < 6e-2
     else:
         # bf16 operands vs the fp32 reference: SURVEY section 10 measured 4-8e-3 forward, ~1e-1 gradients
-        assert errs[("coarse", "rgb")] < 3e-2 and errs[("coarse", "embed")] < 3e-2
-        assert errs[("fine", "rgb")] < 5e-2 and errs[("fine", "embed")] < 5e-2
-        assert errs[("coarse", "depth")] < 1e-2
-        assert abs(float(loss) - float(fx["loss"])) < 5e-3
-        assert e_vsum < 0.3 and worst_par < 0.3
+        for lvl in ("coarse", "fine"):
+            assert errs[(lvl, "rgb")] < 1e-2 and errs[(lvl, "embed")] < 1e-2 and errs[(lvl, "depth")] < 1e-2, errs
+        assert abs(float(loss) - float(fx["loss"])) < 2e-3
+        # gradients: ReLU-gate flips of a bf16 forward (~1e-1 relative-L2, cosine > 0.99); the two
+        # volume-gradient statistics are channel sums of the gradient, the signed one cancels most of its norm
+        cos_v = cosine(vgrad.sum(1), T(fx["vgrad_sum"]))
+        assert e_vsum < 0.2 and e_vsign < 0.3 and cos_v > 0.98 and worst_par < 0.15, (e_vsum, e_vsign, cos_v, worst_par)
 
 
 def _oracle_vs_cuda(NR, S, C, D, hidden, SB, n_rays, Kc, Kf, precision, seed, perturb=True, train=True, Kfd=0,
@@ -574,6 +614,36 @@ def test_loss_dict_is_lazy_and_matches_the_reference_keys(ops, NR):
     assert abs(vals["loss_rgb"] - (vals["loss_rgb_coarse"] + vals["loss_rgb_fine"])) < 1e-7
     assert 0.0 < vals["psnr"] < 100.0
     assert out["psnr"] == vals["psnr"] and out.get("loss_depth") == 0.0
+    # CPython's exact-dict fast paths must not hand out the unresolved placeholders
+    import json
+    for how in (dict, lambda d: {**d}, lambda d: d | {}, lambda d: {} | d, lambda d: json.loads(json.dumps(
+            {k: v for k, v in d.items() if k != "loss"})), lambda d: (lambda t: (t.update(d), t)[1])({})):
+        fresh = ren(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=vol, voxel_poses=poses,
+                    focal=torch.tensor(float(fx["focal"])).cuda(), gt_rgb=gt_rgb, gt_depth=None, gt_pose=poses, c=None,
+                    lang_goal=None, gt_embed=gt_emb)
+        assert fresh._host is not None
+        got = how(fresh)
+        assert all(isinstance(got[k], float) for k in NR.LossDict._KEYS), got
+
+
+def test_weights_written_through_data_are_seen_by_the_next_step(ops, NR):
+    """An optimizer that writes through `p.data` (apex / DeepSpeed fused optimizers, EMA swaps) does not bump the
+    Parameter's version counter; the packed tensor-core copies must follow anyway: every training forward
+    repacks."""
+    fx = golden("full_s32")
+    meta = [int(v) for v in fx["meta"]]
+    inp = syn_case_inputs(fx)
+    ren = make_renderer(NR, meta, inp["params"], "bf16")
+    out0, _, _, _ = _run_cuda(ren, inp["vol"], inp["rays"], inp["noise"], inp["gt_rgb"], inp["gt_embed"])
+    w = ren.nerf_model.mlp_coarse.lin_out.weight
+    v0 = w._version
+    w.data[4:].mul_(0.5)                                      # the embed rows only: rgb / density stay as they were
+    assert w._version == v0                                   # invisible to a version-keyed cache
+    out1, _, _, _ = _run_cuda(ren, inp["vol"], inp["rays"], inp["noise"], inp["gt_rgb"], inp["gt_embed"])
+    # raw embed outputs are linear in those rows (bias 0) and a power of two commutes with every rounding on the way
+    assert torch.equal(out1.coarse.rgb, out0.coarse.rgb)
+    assert rel(out1.coarse.embed, 0.5 * out0.coarse.embed) < 1e-6
+    assert rel(out1.coarse.embed, out0.coarse.embed) > 0.3
 
 
 def test_bf16_training_step_is_reproducible_when_asked(ops, NR):
