@@ -94,14 +94,166 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------- our arm
+class Case:
+    """One workload on this rank: renderer + device-resident volume + the host (pinned) and device copies of a training
+    step's inputs."""
+
+    def __init__(self, mods, wl, precision, dev, rank, world, args, SB=None, n_rays=None, focal=None, near_far=None,
+                 vol_seed=None, share_from=None):
+        import torch
+        NR, U, syn = mods["NR"], mods["U"], mods["syn"]
+        self.wl, self.dev, self.world, self.rank = wl, dev, world, rank
+        self.SB = SB = wl.SB if SB is None else SB
+        self.n_rays = n_rays = wl.rays_per_scene if n_rays is None else n_rays
+        near, far = near_far if near_far is not None else (1.2, 4.0)
+        cfg = U.default_config(voxel_shape=wl.S, d_latent=wl.C, d_embed=wl.D, n_coarse=wl.n_coarse, n_fine=wl.n_fine,
+                               ray_chunk_size=n_rays, image_width=wl.W, image_height=wl.H, z_near=near, z_far=far)
+        ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS), precision=precision)
+        syn.init_mlp_(ren.nerf_model.mlp_coarse, seed=0)
+        self.ren = ren = ren.to(dev).train()
+        ren.scatter = args.scatter
+        self.params = [p for p in ren.parameters()]
+        if share_from is not None:                       # same volume / inputs, another precision mode
+            for k in ("vol", "poses_h", "focal_h", "gt_rgb_h", "gt_emb_h", "poses_d", "focal_d", "gt_rgb_d", "gt_emb_d",
+                      "h2d_bytes"):
+                setattr(self, k, getattr(share_from, k))
+            self.copy_stream = share_from.copy_stream
+            return
+        g = torch.Generator(device=dev).manual_seed(1234 + (rank if vol_seed is None else vol_seed))
+        vol = torch.randn(SB, wl.C, wl.S, wl.S, wl.S, device=dev, generator=g) * 0.1
+        if args.volume_layout == "channels_last_3d":     # what a conv3d producer run in that memory format hands over
+            vol = vol.contiguous(memory_format=torch.channels_last_3d)
+        self.vol = vol.requires_grad_(True)
+        # host-side inputs of a training step (what the data loader hands over), pinned
+        self.poses_h = syn.arc_poses(SB).pin_memory()
+        self.focal_h = torch.tensor(wl.focal if focal is None else focal, dtype=torch.float32).pin_memory()
+        gh = torch.Generator().manual_seed(99 + rank)
+        self.gt_rgb_h = torch.rand(SB, wl.H, wl.W, 3, generator=gh).pin_memory()
+        self.gt_emb_h = torch.randn(SB, wl.H, wl.W, wl.D, generator=gh).pin_memory()
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.poses_h, self.focal_h, self.gt_rgb_h, self.gt_emb_h))
+        self.poses_d, self.focal_d = self.poses_h.to(dev), self.focal_h.to(dev)
+        self.gt_rgb_d, self.gt_emb_d = self.gt_rgb_h.to(dev), self.gt_emb_h.to(dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+
+    @property
+    def evals(self):
+        fine = (self.wl.n_coarse + self.wl.n_fine) if self.wl.n_fine > 0 else 0
+        return self.SB * self.n_rays * (self.wl.n_coarse + fine)
+
+    def step(self, host_inputs=False, post_allreduce=None, volume_allreduce=None):
+        import torch
+        ren, dev = self.ren, self.dev
+        self.vol.grad = None
+        for p in self.params:
+            p.grad = None
+        if host_inputs:
+            # what a training loop does: the step's inputs come from pinned host memory; the copies run on a side
+            # stream so that the 50 MB of target features (needed only by the losses) overlap the coarse pass
+            main = torch.cuda.current_stream(dev)
+            with torch.cuda.stream(self.copy_stream):
+                poses, focal = self.poses_h.to(dev, non_blocking=True), self.focal_h.to(dev, non_blocking=True)
+                ev_small = torch.cuda.Event()
+                ev_small.record(self.copy_stream)
+                gt_rgb, gt_emb = self.gt_rgb_h.to(dev, non_blocking=True), self.gt_emb_h.to(dev, non_blocking=True)
+                ev_big = torch.cuda.Event()
+                ev_big.record(self.copy_stream)
+            main.wait_event(ev_small)
+            for t in (poses, focal, gt_rgb, gt_emb):
+                t.record_stream(main)
+            ren.target_ready_event = ev_big          # compute_rendering_loss waits for it right before the losses
+        else:
+            poses, focal, gt_rgb, gt_emb = self.poses_d, self.focal_d, self.gt_rgb_d, self.gt_emb_d
+            ren.target_ready_event = None
+        out = ren(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=self.vol,
+                  voxel_poses=poses, focal=focal, gt_rgb=gt_rgb, gt_depth=None, gt_pose=poses, c=None,
+                  lang_goal=None, gt_embed=gt_emb)
+        out["loss"].backward()
+        if post_allreduce is not None:
+            post_allreduce(ren)
+        if volume_allreduce is not None:
+            volume_allreduce(self.vol.grad)
+        return out
+
+
+def release():
+    """Between cases: the last step's buffers hang off autograd nodes that are only reclaimed by the cycle collector."""
+    import gc
+    import torch
+    gc.collect()
+    torch.cuda.empty_cache()
+    if os.environ.get("NRF_BENCH_DEBUG"):
+        sys.stderr.write(f"[bench] live after release: {torch.cuda.memory_allocated() / 2 ** 30:.2f} GiB\n")
+
+
+def timed_region(fn, n_steps, dev, world, read_losses=False):
+    """EXACTLY n_steps calls of fn() between a barrier + synchronize on both sides, CUDA events on the current stream.
+    -> (max over ranks, [per-rank ms])."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    prev, seen, out = None, 0.0, None
+    for _ in range(n_steps):
+        out = None
+        out = fn()
+        if read_losses:
+            # the step's result is read on the host EVERY step: the loss dictionary copies its scalars to pinned
+            # memory asynchronously (LossDict), so a training loop logs step i while step i+1 is queued; the last
+            # step's values are read before the timed region closes
+            if prev is not None:
+                seen += prev["loss_rgb"] + prev["loss_embed"] + prev["loss_depth"]
+            prev = out
+    if read_losses and prev is not None:
+        seen += prev["loss_rgb"] + prev["loss_embed"] + prev["loss_depth"]
+        assert seen == seen, "loss is NaN"
+    b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    per_rank = [float(ms.item())]
+    if world > 1:
+        parts = [torch.empty_like(ms) for _ in range(world)]
+        dist.all_gather(parts, ms)
+        per_rank = [float(p.item()) for p in parts]
+    return max(per_rank), per_rank
+
+
+def mode_rel_err(mods, base: Case, args, precisions, n_rays=256):
+    """Relative-L2 error of every tensor-core precision mode against this repo's fp32 parity mode (itself held to the
+    reference's outputs at 1e-4 by the tests) on the SAME inputs: n_rays rays per scene of the workload, identical
+    injected sampling noise, forward_nerf outputs of the fine pass."""
+    import torch
+    syn = mods["syn"]
+    dev, wl = base.dev, base.wl
+    R = base.SB * n_rays
+    from_cpu = lambda d: {k: v.to(dev) for k, v in d.items()}
+    noise = from_cpu(syn.make_noise(R, wl.n_coarse, wl.n_fine, seed=17))
+    rays_all = mods["U"].gen_rays(base.poses_d, wl.W, wl.H, base.focal_d, base.ren.z_near, base.ren.z_far).reshape(base.SB, -1, 8)
+    rays = rays_all[:, syn.pick_ray_indices(wl.W * wl.H, n_rays, seed=3).to(dev)].contiguous()
+    outs = {}
+    with torch.no_grad():
+        for prec in ["fp32"] + list(precisions):
+            c = Case(mods, wl, prec, dev, base.rank, base.world, args, SB=base.SB, n_rays=n_rays, share_from=base)
+            c.ren.eval()
+            c.ren.encode(None, None, None, base.vol.detach(), None, None, None)
+            o = c.ren.forward_nerf(rays, noise=noise)
+            outs[prec] = {k: o.fine[k].double() for k in ("rgb", "embed", "depth")}
+            del c
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    return {p: {k: float(f"{rel(outs[p][k], outs['fp32'][k]):.3e}") for k in ("rgb", "embed", "depth")} for p in precisions}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    NR = importlib.import_module(PKG + ".neural_rendering")
-    U = importlib.import_module(PKG + ".utils")
-    syn = importlib.import_module(PKG + ".synthetic")
-    par = importlib.import_module(PKG + ".parallel")
-    lib = importlib.import_module(PKG + "._lib")
+    mods = {"NR": importlib.import_module(PKG + ".neural_rendering"), "U": importlib.import_module(PKG + ".utils"),
+            "syn": importlib.import_module(PKG + ".synthetic"), "par": importlib.import_module(PKG + ".parallel"),
+            "lib": importlib.import_module(PKG + "._lib")}
+    syn, par, lib = mods["syn"], mods["par"], mods["lib"]
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -112,130 +264,62 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     wl = syn.CONFIGS[args.workload]
-    SB, n_rays = wl.SB, wl.rays_per_scene
+    K, W = args.steps, args.warmup
+    pk = peaks()
 
-    cfg = U.default_config(voxel_shape=wl.S, d_latent=wl.C, d_embed=wl.D, n_coarse=wl.n_coarse, n_fine=wl.n_fine,
-                           ray_chunk_size=n_rays, image_width=wl.W, image_height=wl.H)
-    ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS), precision=args.precision)
-    syn.init_mlp_(ren.nerf_model.mlp_coarse, seed=0)
-    ren = ren.to(dev).train()
-    ren.scatter = args.scatter
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    vol = torch.randn(SB, wl.C, wl.S, wl.S, wl.S, device=dev, generator=g) * 0.1
-    if args.volume_layout == "channels_last_3d":       # what a conv3d producer run in that memory format hands over
-        vol = vol.contiguous(memory_format=torch.channels_last_3d)
-    vol.requires_grad_(True)
-    # host-side inputs of a training step (what the data loader hands over), pinned
-    poses_h = syn.arc_poses(SB).pin_memory()
-    focal_h = torch.tensor(wl.focal, dtype=torch.float32).pin_memory()
-    gh = torch.Generator().manual_seed(99 + rank)
-    gt_rgb_h = torch.rand(SB, wl.H, wl.W, 3, generator=gh).pin_memory()
-    gt_emb_h = torch.randn(SB, wl.H, wl.W, wl.D, generator=gh).pin_memory()
-    h2d_bytes = sum(t.numel() * t.element_size() for t in (poses_h, focal_h, gt_rgb_h, gt_emb_h))
-    poses_d, focal_d = poses_h.to(dev), focal_h.to(dev)
-    gt_rgb_d, gt_emb_d = gt_rgb_h.to(dev), gt_emb_h.to(dev)
-    params = [p for p in ren.parameters()]
+    main = Case(mods, wl, args.precision, dev, rank, world, args)
+    ren = main.ren
+    post = (lambda r: par.allreduce_mlp_grads(r)) if world > 1 and args.allreduce == "post" else None
     if world > 1 and args.allreduce == "overlap":     # ONE NCCL all-reduce of the flat MLP gradient, started inside the
         par.overlap_mlp_grad_allreduce(ren)           # backward: it runs under the volume-gradient scatter
+    multi_gpu_check = multi_gpu_numerical_check(mods, main, world) if world > 1 else None
 
-    copy_stream = torch.cuda.Stream(device=dev)
-
-    def step(host_inputs: bool):
-        vol.grad = None
-        for p in params:
-            p.grad = None
-        if host_inputs:
-            # what a training loop does: the step's inputs come from pinned host memory; the copies run on a side
-            # stream so that the 50 MB of target features (needed only by the losses) overlap the coarse pass
-            main = torch.cuda.current_stream(dev)
-            with torch.cuda.stream(copy_stream):
-                poses, focal = poses_h.to(dev, non_blocking=True), focal_h.to(dev, non_blocking=True)
-                ev_small = torch.cuda.Event()
-                ev_small.record(copy_stream)
-                gt_rgb, gt_emb = gt_rgb_h.to(dev, non_blocking=True), gt_emb_h.to(dev, non_blocking=True)
-                ev_big = torch.cuda.Event()
-                ev_big.record(copy_stream)
-            main.wait_event(ev_small)
-            for t in (poses, focal, gt_rgb, gt_emb):
-                t.record_stream(main)
-            ren.target_ready_event = ev_big          # compute_rendering_loss waits for it right before the losses
-        else:
-            poses, focal, gt_rgb, gt_emb = poses_d, focal_d, gt_rgb_d, gt_emb_d
-            ren.target_ready_event = None
-        out = ren(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=vol,
-                  voxel_poses=poses, focal=focal, gt_rgb=gt_rgb, gt_depth=None, gt_pose=poses, c=None,
-                  lang_goal=None, gt_embed=gt_emb)
-        out["loss"].backward()
-        if world > 1 and args.allreduce == "post":
-            par.allreduce_mlp_grads(ren)
-        return out
-
-    def timed(n_steps, host_inputs):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        prev, seen = None, 0.0
-        for _ in range(n_steps):
-            out = step(host_inputs)
-            if host_inputs:
-                # the step's result is read on the host EVERY step: the loss dictionary copies its scalars to pinned
-                # memory asynchronously (LossDict), so a training loop logs step i while step i+1 is queued; the
-                # last step's values are read before the timed region closes
-                if prev is not None:
-                    seen += prev["loss_rgb"] + prev["loss_embed"] + prev["loss_depth"]
-                prev = out
-        if host_inputs and prev is not None:
-            seen += prev["loss_rgb"] + prev["loss_embed"] + prev["loss_depth"]
-            assert seen == seen, "loss is NaN"
-        b.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    for _ in range(args.warmup):
-        step(False)
+    for _ in range(W):
+        main.step(post_allreduce=post)
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3)
     launches0 = lib.launch_count()
-    ms_total = timed(args.steps, False)                 # the timed region behind `value`
+    ms_total, ms_rank = timed_region(lambda: main.step(post_allreduce=post), K, dev, world)   # behind `value`
     launches = lib.launch_count() - launches0
     # same K steps again with a CUDA-event pair around every kernel launch (recorded by the library on the
     # launching stream): per-kernel durations for the roofline; kept out of `value` because ~500 event
     # records per step add launch gaps
     lib.timing_begin()
-    ms_total_ev = timed(args.steps, False)
+    ms_total_ev, _ = timed_region(lambda: main.step(post_allreduce=post), K, dev, world)
     kern = lib.timing_end()
-    clocks = sampler.stop() if sampler else None
     # end-to-end: host (pinned) inputs copied in, loss read back, every step
-    step(True)
-    ms_e2e = timed(args.steps, True)
+    main.step(host_inputs=True, post_allreduce=post)
+    ms_e2e, _ = timed_region(lambda: main.step(host_inputs=True, post_allreduce=post), K, dev, world, read_losses=True)
+    # a long timed region as well (20 steps are 0.3 s): >= 200 steps and >= 3 s, same step, same clock
+    n_sus = 0 if args.sustain_steps <= 0 else max(args.sustain_steps, int(3000.0 / (ms_total / K)) + 1)
+    sustained = None
+    if n_sus:
+        ms_sus, ms_sus_rank = timed_region(lambda: main.step(post_allreduce=post), n_sus, dev, world)
+        sustained = {"steps": n_sus, "seconds": round(ms_sus / 1e3, 2), "ms_per_step": round(ms_sus / n_sus, 3),
+                     "value": round(main.evals * world / (ms_sus / n_sus * 1e-3), 1), "unit": "ray-samples/s",
+                     "ms_per_step_per_rank": [round(m / n_sus, 3) for m in ms_sus_rank]}
+    clocks = sampler.stop() if sampler else None
     # optional mode, reported beside the headline and never mixed into it: the fine pass reuses the coarse pass's
     # field evaluations (bit-identical rendering; the MLP runs on Kc + Kf instead of Kc + (Kc + Kf) samples per ray)
     ms_reuse = None
     if not args.no_reuse_line:
         ren.reuse_coarse_evals = True
         for _ in range(2):
-            step(False)
-        ms_reuse = timed(args.steps, False)
+            main.step(post_allreduce=post)
+        ms_reuse, _ = timed_region(lambda: main.step(post_allreduce=post), K, dev, world)
         ren.reuse_coarse_evals = False
 
-    evals_step = wl.evals * world
-    ms_step = ms_total / args.steps
+    SB, n_rays = main.SB, main.n_rays
+    evals_step = main.evals * world
+    ms_step = ms_total / K
     value = evals_step / (ms_step * 1e-3)
-    e2e_value = evals_step / (ms_e2e / args.steps * 1e-3)
-    pk = peaks()
+    e2e_value = evals_step / (ms_e2e / K * 1e-3)
     # dominant kernel: mlp_fused_kernel (csrc/mlp_fused.cu), the whole forward MLP and the whole data-gradient chain
     # as one persistent tcgen05 kernel each (2 + 2 launches per step: coarse and fine pass).  Algorithmic FLOPs it
     # executes per step = (forward + dgrad) FLOP per evaluation x this rank's evaluations, minus the small dL/dz GEMM
     # that stays a separate launch; duration = sum over its launches (CUDA events on the launching stream).
-    # (--precision fp32 or NRF_MLP_LAYERED=1: the per-layer gemm kernels are the dominant ones instead.)
+    # (--precision fp32 / bf16x3 or NRF_MLP_LAYERED=1: the per-layer gemm kernels are the dominant ones instead.)
     wg_ms, wg_n = kern["wgrad_tc"]
     fused_ms = kern["fused_fwd"][0] + kern["fused_bwd"][0]
     fused_n = kern["fused_fwd"][1] + kern["fused_bwd"][1]
@@ -243,12 +327,12 @@ def run_ours(args):
     if fused_n > 0:
         dom_name = "mlp_fused_kernel (whole-MLP forward + whole data-gradient chain, 4 launches/step)"
         dom_ms, dom_n = fused_ms, fused_n
-        dom_flops = (FLOP_FWD + FLOP_DGRAD - flop_dz) * wl.evals * args.steps
+        dom_flops = (FLOP_FWD + FLOP_DGRAD - flop_dz) * main.evals * K
     else:
         dom_name = "gemm_tc_kernel / gemm_simt_kernel (per-layer forward + dgrad GEMMs)"
         dom_ms = kern["gemm_tc"][0] + kern["simt"][0]
         dom_n = kern["gemm_tc"][1] + kern["simt"][1]
-        dom_flops = (FLOP_FWD + FLOP_DGRAD) * wl.evals * args.steps
+        dom_flops = (FLOP_FWD + FLOP_DGRAD) * main.evals * K
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     roof = {"bound": "tensor", "kernel": dom_name, "achieved": round(achieved, 1),
             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4),
@@ -259,11 +343,11 @@ def run_ours(args):
             "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
             "launches": dom_n, "avg_launch_ms": round(dom_ms / max(dom_n, 1), 4),
             "algorithmic_flop_per_eval": {"fwd": FLOP_FWD, "dgrad": FLOP_DGRAD, "wgrad": FLOP_WGRAD},
-            "wgrad_tc_tflops": round(FLOP_WGRAD * wl.evals * args.steps / (wg_ms * 1e-3) / 1e12, 1) if wg_ms > 0 else None,
-            "step_frac_of_tensor_peak": round(FLOP_STEP * wl.evals / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], 4)}
-    kernel_ms = {k: round(v[0] / args.steps, 3) for k, v in kern.items() if v[1] > 0}
+            "wgrad_tc_tflops": round(FLOP_WGRAD * main.evals * K / (wg_ms * 1e-3) / 1e12, 1) if wg_ms > 0 else None,
+            "step_frac_of_tensor_peak": round(FLOP_STEP * main.evals / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], 4)}
+    kernel_ms = {k: round(v[0] / K, 3) for k, v in kern.items() if v[1] > 0}
     line = {"metric": "render fwd+bwd ray-samples/s", "value": round(value, 1), "unit": "ray-samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"{wl.name}: per GPU {SB} scenes x {n_rays} rays, {wl.n_coarse}+{wl.n_fine} samples, "
@@ -271,21 +355,79 @@ def run_ours(args):
                        "evals_per_step": evals_step, "precision": args.precision, "scatter": args.scatter, "volume_layout": args.volume_layout,
                        "l2": "working set (1 GiB volume + ~20 GiB activations per step) >> 126 MB L2; no flush needed",
                        "parallelism": f"dp{world} over scenes; one NCCL all-reduce of the MLP grads ({args.allreduce})" if world > 1 else "single GPU"},
-            "e2e": {"value": round(e2e_value, 1), "unit": "ray-samples/s", "ms_per_step": round(ms_e2e / args.steps, 3),
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 * 7,
+            "ms_per_step_per_rank": [round(m / K, 3) for m in ms_rank],
+            "e2e": {"value": round(e2e_value, 1), "unit": "ray-samples/s", "ms_per_step": round(ms_e2e / K, 3),
+                    "h2d_bytes_per_step": main.h2d_bytes, "d2h_bytes_per_step": 4 * 7,
                     "note": "poses, focal, gt_rgb, gt_embed copied from pinned host memory each step (side stream; the targets "
                             "are awaited right before the losses); the 7 loss scalars of every step are copied to pinned host memory "
                             "and read by the host one step later (LossDict), the last step's inside the timed region; "
                             "the voxel volume is device-resident "
                             "as in the reference (PerAct encoder output)"},
+            "sustained": sustained,
             "reuse_coarse_evals": None if ms_reuse is None else {
-                "ms_per_step": round(ms_reuse / args.steps, 3),
-                "value": round(evals_step / (ms_reuse / args.steps * 1e-3), 1), "unit": "ray-samples/s",
+                "ms_per_step": round(ms_reuse / K, 3),
+                "value": round(evals_step / (ms_reuse / K * 1e-3), 1), "unit": "ray-samples/s",
                 "mlp_evals_per_step": world * SB * n_rays * (wl.n_coarse + wl.n_fine),
                 "note": "opt-in NeuralRenderer.reuse_coarse_evals=True: same rendered samples per step (value counts "
                         "them as the headline does), the MLP evaluates each distinct sample once; NOT the headline"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_ms_per_step": kernel_ms,
-            "ms_per_step_with_kernel_events": round(ms_total_ev / args.steps, 3)}
+            "ms_per_step_with_kernel_events": round(ms_total_ev / K, 3)}
+    if multi_gpu_check is not None:
+        line["multi_gpu_check"] = multi_gpu_check
+
+    # ---- the precision modes on the same step: ms per step + error against the fp32 parity mode
+    if not args.no_modes and wl.train:
+        modes = {args.precision: {"ms_per_step": round(ms_step, 3)}}
+        for prec in [p for p in ("bf16", "fp16", "bf16x3") if p != args.precision]:
+            c = Case(mods, wl, prec, dev, rank, world, args, share_from=main)
+            if world > 1 and args.allreduce == "overlap":
+                par.overlap_mlp_grad_allreduce(c.ren)
+            n = K if prec != "bf16x3" else max(3, K // 4)
+            for _ in range(2):
+                c.step(post_allreduce=post)
+            ms_m, _ = timed_region(lambda: c.step(post_allreduce=post), n, dev, world)
+            modes[prec] = {"ms_per_step": round(ms_m / n, 3), "steps": n}
+            del c
+            release()
+        errs = mode_rel_err(mods, main, args, list(modes))
+        for prec in modes:
+            modes[prec]["rel_err_vs_fp32_mode"] = errs[prec]
+        line["modes"] = modes
+        line["modes_note"] = ("same config-2 step per mode; rel_err = relative L2 of the fine pass's rgb / embed / depth "
+                              "against this repo's fp32 parity mode (held to the reference at 1e-4 by tests/) on 256 "
+                              "rays per scene with identical injected sampling noise; fp16 = fp16 forward operands + bf16 "
+                              "backward; bf16x3 = split-bf16 operands, three MMAs per product, layer by layer")
+
+    # ---- in-box variant: near / far clipped to the volume and a longer lens, so that ~95 % of the samples gather
+    # (in the BASELINE camera set-up only ~5 % of the samples fall inside the 1 m box): the HBM-side kernels under load
+    if not args.no_extra and wl.train:
+        ib = Case(mods, wl, args.precision, dev, rank, world, args, focal=500.0, near_far=(2.4, 3.2))
+        if world > 1 and args.allreduce == "overlap":
+            par.overlap_mlp_grad_allreduce(ib.ren)
+        for _ in range(2):
+            ib.step(post_allreduce=post)
+        ms_ib, _ = timed_region(lambda: ib.step(post_allreduce=post), K, dev, world)
+        lib.timing_begin()
+        timed_region(lambda: ib.step(post_allreduce=post), K, dev, world)
+        kib = lib.timing_end()
+        gbs = lambda ms, bytes_per_eval: round(ib.evals * K * bytes_per_eval / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
+        enc, sca = gbs(kib["encode"][0], 4096), gbs(kib["scatter"][0], 4096)
+        line["in_box"] = {"ms_per_step": round(ms_ib / K, 3), "value": round(ib.evals * world / (ms_ib / K * 1e-3), 1),
+                          "camera": "focal 500, z_near 2.4, z_far 3.2: ~95 % of the samples inside the volume",
+                          "kernel_ms_per_step": {k: round(v[0] / K, 3) for k, v in kib.items() if v[1] > 0},
+                          "encode_gbs": enc, "encode_frac_of_hbm": round(enc / pk["hbm_gbs"], 3) if enc else None,
+                          "scatter_gbs": sca, "scatter_frac_of_hbm": round(sca / pk["hbm_gbs"], 3) if sca else None,
+                          "note": "algorithmic bytes: gather 8 corners x 128 ch x 4 B = 4096 B per evaluation (SURVEY 8d); "
+                                  "scatter 4096 B per evaluation (the dense 0.97 GB gradient volume it also writes is not counted)"}
+        del ib
+        release()
+
+    # ---- the other BASELINE configs (each a short run; N > 1: strong scaling - total work fixed)
+    if not args.no_extra and args.workload == "config2":
+        del main, ren
+        release()
+        line["configs"] = other_configs(mods, args, dev, rank, world)
+
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(rays=args.cpu_rays, reps=1)
@@ -294,6 +436,109 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_numerical_check(mods, case, world):
+    """N > 1, before anything is timed: (a) the all-reduce started inside the backward gives bit-identical MLP gradients
+    to the separate all-reduce after it; (b) the reduced gradient is the sum of the ranks' local gradients (gathered
+    and added in rank order).  Asserted; the numbers go into the bench line."""
+    import torch
+    import torch.distributed as dist
+    par = mods["par"]
+    ren = case.ren
+    det0, hook0 = ren.deterministic, ren._grad_allreduce
+    ren.deterministic = True                         # ordered split reductions: run-to-run identical local gradients
+    flat = lambda: torch.cat([p.grad.reshape(-1) for p in case.params])
+
+    def run(mode):
+        par.overlap_mlp_grad_allreduce(ren, enabled=(mode == "overlap"))
+        torch.manual_seed(4321 + case.rank)
+        case.step(post_allreduce=(lambda r: par.allreduce_mlp_grads(r)) if mode == "post" else None)
+        return flat().clone()
+    g_local, g_post, g_over = run("local"), run("post"), run("overlap")
+    parts = [torch.empty_like(g_local) for _ in range(world)]
+    dist.all_gather(parts, g_local)
+    total = parts[0].double()
+    for p in parts[1:]:
+        total += p.double()
+    rel = float((g_over.double() - total).norm() / total.norm())
+    same = bool(torch.equal(g_post, g_over))
+    ren.deterministic, ren._grad_allreduce = det0, hook0
+    assert same, "overlapped MLP-gradient all-reduce differs from the separate one"
+    assert rel < 1e-5, f"all-reduced MLP gradient is not the sum over ranks (rel {rel:.2e})"
+    return {"overlap_equals_post_bitwise": same, "allreduce_vs_sum_of_local_grads_rel": float(f"{rel:.3e}"),
+            "ranks": world, "mlp_grad_bytes": int(g_local.numel() * 4)}
+
+
+def other_configs(mods, args, dev, rank, world):
+    """BASELINE configs 3, 4, 5.  N > 1 is STRONG scaling here: config 3 shards the rays of the 5
+    images, config 4 its 8 scenes, config 5 the rays of its one scene (MLP-gradient all-reduce + a dense all-reduce of
+    the 4.1 GB volume gradient).  Short runs: 2 warm-up + a few timed iterations each."""
+    import torch
+    syn, par = mods["syn"], mods["par"]
+    out = {}
+    # config 3: inference, 5 cameras x 128 x 128 px, rays sharded contiguously, image rows all-gathered
+    wl = syn.CONFIGS["config3"]
+    c = Case(mods, wl, args.precision, dev, rank, world, args, SB=1, n_rays=4096, vol_seed=0)
+    c.ren.eval()
+    poses = syn.arc_poses(wl.n_cams).to(dev)
+    vol = c.vol.detach()
+    render = lambda: par.render_sharded(c.ren, vol, c.focal_d, poses, gather=world > 1)
+    for _ in range(2):
+        render()
+    n = 5
+    ms, per_rank = timed_region(render, n, dev, world)
+    evals3 = wl.n_cams * wl.H * wl.W * (wl.n_coarse + wl.n_coarse + wl.n_fine)
+    out["config3"] = {"workload": "inference: 5 cameras x 128x128 px, 64 + 128 samples/ray, 100^3 x 128ch volume; rays "
+                                  f"sharded over {world} GPU(s), images all-gathered", "scaling": "strong",
+                      "ms_per_render": round(ms / n, 3), "value": round(evals3 / (ms / n * 1e-3), 1), "unit": "ray-samples/s",
+                      "evals_per_render": evals3, "ms_per_rank": [round(m / n, 3) for m in per_rank],
+                      "frac_of_tensor_peak_fwd": round(FLOP_FWD * evals3 / world / (ms / n * 1e-3) / 1e12 / peaks()["bf16_tflops_sustained"], 4)}
+    del c, vol, render
+    release()
+    # config 4: training, 8 scenes x 4096 rays, scenes data-parallel
+    wl = syn.CONFIGS["config4"]
+    if wl.SB % world == 0:
+        c = Case(mods, wl, args.precision, dev, rank, world, args, SB=wl.SB // world)
+        if world > 1:
+            par.overlap_mlp_grad_allreduce(c.ren)
+        for _ in range(2):
+            c.step()
+        n = 5
+        ms, per_rank = timed_region(c.step, n, dev, world)
+        out["config4"] = {"workload": f"training: 8 scenes x 4096 rays, 64+64 samples, {wl.SB // world} scene(s) per GPU, "
+                                      "one NCCL all-reduce of the MLP grads", "scaling": "strong",
+                          "ms_per_step": round(ms / n, 3), "value": round(c.evals * world / (ms / n * 1e-3), 1),
+                          "unit": "ray-samples/s", "evals_per_step": c.evals * world,
+                          "ms_per_rank": [round(m / n, 3) for m in per_rank]}
+        del c
+        release()
+    # config 5: stress shape, one scene; N > 1: its rays split over the ranks, the volume gradient summed
+    wl = syn.CONFIGS["config5"]
+    if wl.rays_per_scene % world == 0:
+        c = Case(mods, wl, args.precision, dev, rank, world, args, n_rays=wl.rays_per_scene // world, vol_seed=0)
+        vred = None
+        if world > 1:
+            par.overlap_mlp_grad_allreduce(c.ren)
+            vred = par.allreduce_volume_grad
+        for _ in range(2):
+            c.step(volume_allreduce=vred)
+        n = 5
+        ms, per_rank = timed_region(lambda: c.step(volume_allreduce=vred), n, dev, world)
+        rec = {"workload": f"training: 200^3 x 128ch volume (4.1 GB), 16384 rays x (128 + 256) samples, "
+                           f"{wl.rays_per_scene // world} rays per GPU" +
+                           ("; MLP-grad all-reduce + dense all-reduce of the 4.1 GB volume gradient" if world > 1 else ""),
+               "scaling": "strong", "ms_per_step": round(ms / n, 3), "value": round(c.evals * world / (ms / n * 1e-3), 1),
+               "unit": "ray-samples/s", "evals_per_step": c.evals * world, "ms_per_rank": [round(m / n, 3) for m in per_rank]}
+        if world > 1:                               # the collective alone, for the efficiency statement
+            g = torch.zeros_like(c.vol)
+            ms_c, _ = timed_region(lambda: par.allreduce_volume_grad(g), 3, dev, world)
+            rec["volume_grad_allreduce"] = {"bytes": int(g.numel() * 4), "ms": round(ms_c / 3, 3)}
+            del g
+        out["config5"] = rec
+        del c
+        release()
+    return out
 
 
 def eager_gpu_baseline(dev, wl, steps=2):
@@ -419,10 +664,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "bf16x3", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=128, dest="cpu_rays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reuse-line", action="store_true", dest="no_reuse_line")
+    ap.add_argument("--no-modes", action="store_true", dest="no_modes", help="skip the per-precision-mode lines")
+    ap.add_argument("--no-extra", action="store_true", dest="no_extra",
+                    help="skip the in-box variant and BASELINE configs 3 / 4 / 5")
+    ap.add_argument("--sustain-steps", type=int, default=200, dest="sustain_steps",
+                    help="length of the additional long timed region (0: skip)")
     ap.add_argument("--allreduce", default="overlap", choices=["overlap", "post"],
                     help="N > 1: MLP-gradient all-reduce started inside the backward (default) or after it")
     ap.add_argument("--scatter", default="sorted", choices=["atomic", "sorted"])

@@ -263,13 +263,17 @@ class _MlpFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         h = ctx.h
-        N = ctx.fin.shape[0]
+        if ctx.acts is None:
+            raise RuntimeError("ResnetFC.forward: backward a second time (retain_graph is not supported)")
+        fin, acts = ctx.fin, ctx.acts
+        ctx.acts = ctx.fin = None
+        N = fin.shape[0]
         dpad = h.sizes.dout_pad
         dfield = torch.zeros(N, dpad, device=d_out.device, dtype=ops.grad_dtype(h.precision))
         dfield[:, :d_out.shape[1]] = d_out.to(dfield.dtype)
         names = h.names()
         grads = _zero_grads(h)
-        dlat = h.backward(ctx.fin, ctx.acts, dfield, grads)
+        dlat = h.backward(fin, acts, dfield, grads)
         dzx = torch.zeros(N, ctx.width, device=d_out.device, dtype=torch.float32)
         dzx[:, :dlat.shape[1]] = dlat
         return (None, dzx, *[grads[n] for n in names])
@@ -402,12 +406,16 @@ class _FieldFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         h = ctx.h
+        if ctx.acts is None:
+            raise RuntimeError("nerf_model.forward: backward a second time (retain_graph is not supported)")
+        acts, field_in = ctx.acts, ctx.field_in
+        ctx.acts = ctx.field_in = None
         n = ctx.rays.shape[0]
         d_field = torch.zeros(n, h.sizes.dout_pad, device=d_out.device, dtype=ops.grad_dtype(h.precision))
         d_field[:, :d_out.shape[1]] = d_out.to(d_field.dtype)
         names = h.names()
         grads = _zero_grads(h)
-        dlat = h.backward(ctx.field_in, ctx.acts, d_field, grads)
+        dlat = h.backward(field_in, acts, d_field, grads)
         d_vol = None
         if ctx.needs_input_grad[3]:
             SB, S0, S1, S2, C = ctx.vol_shape
@@ -659,6 +667,13 @@ class _ForwardNerfFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *g):
         ren, st_c, st_f = ctx.ren, ctx.st_c, ctx.st_f
+        if st_c is None:
+            raise RuntimeError("forward_nerf: backward a second time (its buffers are released by the first backward; "
+                               "retain_graph is not supported)")
+        # this node lives as long as any output tensor does (a training loop keeps the loss dict for logging): drop the
+        # activations now rather than when `out['loss']` goes away - the next step's forward would otherwise coexist
+        # with them (2 x 70 GB at config 4)
+        ctx.st_c = ctx.st_f = None
         dev = st_c.rays.device
         R = st_c.rays.shape[0]
         D = ren._d_embed
@@ -1033,6 +1048,9 @@ class _CompositeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_w, d_rgb, d_emb, d_dep):
         ren, st = ctx.ren, ctx.st
+        if st is None:
+            raise RuntimeError("composite: backward a second time (retain_graph is not supported)")
+        ctx.st = None
         dev = st.rays.device
         R, D = st.rays.shape[0], ren._d_embed
         names = st.mlp.names()
