@@ -239,6 +239,10 @@ typedef struct {
   float* lin_z_w[NRF_MAX_BLOCKS]; float* lin_z_b[NRF_MAX_BLOCKS];
   int deterministic;   /* bf16 mode: reduce the sample splits of every weight gradient in a fixed order through the
                           scratch workspace (bit-reproducible, ~10 % slower wgrads) instead of fp32 atomics */
+  const void* d_last;  /* NULL, or (N,d_hidden) gradient-typed: dL/dx_nb that reaches the last residual stream directly
+                          (the MLP's second return value, resnetfc.py:192-195, composited instead of the embedding when
+                          ret_last_feat: neural_rendering.py:332-334); nrf_mlp_bwd_layered only.  After
+                          nrf_mlp_fwd_layered the last layer of `acts` holds x_nb itself, (N,d_hidden) operand-typed. */
 } NrfMlpGrads;
 
 /* Sizes (bytes) of the caller-provided buffers for a given shape / precision. */
@@ -255,7 +259,8 @@ int nrf_mlp_sizes(const NrfMlpParams* p, int precision, NrfMlpSizes* out);
 /* Packs the fp32 parameters into the operand layout the GEMMs read ([W_z0 | W_in] etc.). */
 int nrf_mlp_pack(const NrfMlpParams* p, int precision, void* packed, void* stream);
 
-/* Forward over N samples.  field_in (N,kin_pad) operand-typed; field_out (N,d_out) fp32 raw outputs.
+/* Forward over N samples.  field_in (N,kin_pad) operand-typed; field_out (N, ldo) fp32 raw outputs with
+ * ldo = d_out rounded up to a multiple of 4 (pad columns are written as zeros; ldo == d_out for the reference's 388 / 516).
  * acts: fwd_bytes_per_sample*N bytes, the operands kept for the backward: relu(x'_b) (b = 0..n_blocks), then
  * relu(net_b) (b < n_blocks), each (N,d_hidden) operand-typed, then one layer of scratch.
  * bf16 mode, when nrf_mlp_fused_supported(): ONE persistent tcgen05 kernel runs all layers per 256-sample tile

@@ -190,7 +190,7 @@ def _linear(x, w, b, operand_dtype=None):
     return F.linear(x, w, b)
 
 
-def resnetfc(p: Params, zx, d_latent, n_blocks=5, combine_layer=3, operand_dtype=None):
+def resnetfc(p: Params, zx, d_latent, n_blocks=5, combine_layer=3, operand_dtype=None, ret_last=False):
     """resnetfc.py:146-195 with ResnetBlockFC.forward :55-64 (ReLU, no shortcut, no spade).
 
     zx (n, d_latent + d_in) -> (n, d_out).  combine_interleaved (utils.py:509-519) at
@@ -205,11 +205,13 @@ def resnetfc(p: Params, zx, d_latent, n_blocks=5, combine_layer=3, operand_dtype
         net = lin(f"blocks.{b}.fc_0", torch.relu(x))
         dx = lin(f"blocks.{b}.fc_1", torch.relu(net))
         x = x + dx
-    return lin("lin_out", torch.relu(x))
+    out = lin("lin_out", torch.relu(x))
+    return (out, x) if ret_last else out            # resnetfc.py:192-195: (out, x); ret_last_feat concatenates them
 
 
 def field(p: Params, voxel_feat, xyz, viewdirs, bounds, code=(6, 1.5, True),
-          n_blocks=5, combine_layer=3, operand_dtype=None, return_mlp_input=False):
+          n_blocks=5, combine_layer=3, operand_dtype=None, return_mlp_input=False, regress_coord=False,
+          regress_attention=False, multi_scale_voxel_list=None, ret_last_feat=False):
     """models_embed.py:295-471 default branch. xyz, viewdirs (SB,n,3) -> (SB,n,4+D).
 
     mlp_input = [latent(C) | PE(xyz)(39) | viewdir(3)] (:366,:405); heads sigmoid(rgb),
@@ -220,14 +222,29 @@ def field(p: Params, voxel_feat, xyz, viewdirs, bounds, code=(6, 1.5, True),
     zf = positional_encoding(canon.reshape(-1, 3), *code)
     zf = torch.cat((zf, viewdirs.reshape(-1, 3)), dim=1)
     latent = trilinear_gather(voxel_feat, canon)
+    if multi_scale_voxel_list:                       # models_embed.py:279-286: [*multi-scale, main]
+        latent = torch.cat([trilinear_gather(v, canon) for v in multi_scale_voxel_list] + [latent], dim=-1)
     C = latent.shape[-1]
     mlp_input = torch.cat((latent.reshape(-1, C), zf), dim=-1)
     if return_mlp_input:
         return mlp_input
-    out = resnetfc(p, mlp_input, C, n_blocks, combine_layer, operand_dtype)
+    out = resnetfc(p, mlp_input, C, n_blocks, combine_layer, operand_dtype, ret_last=ret_last_feat)
+    last = None
+    if ret_last_feat:
+        out, last = out
+        last = last.reshape(SB, n, -1)
     out = out.reshape(-1, n, out.shape[-1])
-    out = torch.cat([torch.sigmoid(out[..., :3]), torch.relu(out[..., 3:4]), out[..., 4:]], -1)
-    return out.reshape(SB, n, -1)
+    # models_embed.py:444-466: optional coordinate head (last 3, or [-9:-6] with attention: the RESIDUAL to the
+    # canonical point is returned) and attention head (last 6)
+    n_att = 6 if regress_attention else 0
+    n_tail = n_att + (3 if regress_coord else 0)
+    parts = [torch.sigmoid(out[..., :3]), torch.relu(out[..., 3:4]), out[..., 4:out.shape[-1] - n_tail]]
+    if regress_coord:
+        parts.append(out[..., out.shape[-1] - n_tail:out.shape[-1] - n_att] - canon)
+    if regress_attention:
+        parts.append(out[..., out.shape[-1] - 6:])
+    out = torch.cat(parts, -1)
+    return (out.reshape(SB, n, -1), last) if ret_last_feat else out.reshape(SB, n, -1)
 
 
 # ------------------------------------------------------------------- compositing
@@ -243,15 +260,27 @@ def composite_weights(sigmas, z_samp, far, sigma_noise=None):
     return alphas * T[:, :-1]
 
 
-def composite_from_field(out, z_samp, far, white_bkgd=False, sigma_noise=None):
-    """neural_rendering.py:316-359,383-389. out (R,K,4+D) -> weights, rgb, embed, depth."""
+def composite_from_field(out, z_samp, far, white_bkgd=False, sigma_noise=None, regress_coord=False,
+                         regress_attention=False, last_feat=None):
+    """neural_rendering.py:316-359,383-395. out (R,K,4+D[+3][+6]) -> weights, rgb, embed, [coord], [attention], depth.
+    The attention head is alpha-composited like the embedding (:353-354), the coordinate head is the plain MEAN over
+    the samples (:356-357)."""
+    n_att = 6 if regress_attention else 0
+    n_tail = n_att + (3 if regress_coord else 0)
+    last = out.shape[-1]
     w = composite_weights(out[..., 3], z_samp, far, sigma_noise)
     rgb = torch.sum(w.unsqueeze(-1) * out[..., :3], -2)
-    embed = torch.sum(w.unsqueeze(-1) * out[..., 4:], -2)
+    embeds = out[..., 4:last - n_tail] if last_feat is None else last_feat      # neural_rendering.py:332-334
+    embed = torch.sum(w.unsqueeze(-1) * embeds, -2)
     depth = torch.sum(w * z_samp, -1)
     if white_bkgd:
         rgb = rgb + 1 - w.sum(dim=1).unsqueeze(-1)
-    return w, rgb, embed, depth
+    res = [w, rgb, embed]
+    if regress_coord:
+        res.append(torch.mean(out[..., last - n_tail:last - n_att], -2))
+    if regress_attention:
+        res.append(torch.sum(w.unsqueeze(-1) * out[..., last - 6:], -2))
+    return (*res, depth)
 
 
 def composite(p, voxel_feat, rays, z_samp, sb, bounds, eval_batch_size=4096, white_bkgd=False, sigma_noise=None,
@@ -268,8 +297,14 @@ def composite(p, voxel_feat, rays, z_samp, sb, bounds, eval_batch_size=4096, whi
     chunk = (eval_batch_size - 1) // sb + 1
     vals = [field(p, voxel_feat, a, b, bounds, **fkw)
             for a, b in zip(torch.split(pts, chunk, dim=1), torch.split(dirs, chunk, dim=1))]
+    last = None
+    if fkw.get("ret_last_feat", False):
+        last = torch.cat([v[1] for v in vals], dim=1)
+        last = last.reshape(R, K, -1)
+        vals = [v[0] for v in vals]
     out = torch.cat(vals, dim=1).reshape(R, K, -1)
-    return composite_from_field(out, z_samp, rays[:, -1:], white_bkgd, sigma_noise)
+    return composite_from_field(out, z_samp, rays[:, -1:], white_bkgd, sigma_noise, fkw.get("regress_coord", False),
+                                fkw.get("regress_attention", False), last)
 
 
 def forward_nerf(p, voxel_feat, rays, bounds, n_coarse, n_fine, n_fine_depth=0, noise=None,
@@ -286,11 +321,21 @@ def forward_nerf(p, voxel_feat, rays, bounds, n_coarse, n_fine, n_fine_depth=0, 
     R = r.shape[0]
     z_c = sample_coarse(r, n_coarse, noise.get("coarse"), lindisp)
     sn = lambda k: noise[k] * noise_std if noise_std > 0 and k in noise else None
-    wc, rgb_c, emb_c, dep_c = composite(p, voxel_feat, r, z_c, SB, bounds, eval_batch_size, white_bkgd,
-                                        sn("sigma_c"), **fkw)
-    fmt = lambda w, a, b, c: dict(rgb=a.reshape(SB, -1, 3), embed=b.reshape(SB, -1, b.shape[-1]),
-                                  depth=c.reshape(SB, -1), weights=w.reshape(SB, -1, w.shape[-1]))
-    res = dict(coarse=fmt(wc, rgb_c, emb_c, dep_c), z_coarse=z_c)
+    has_c, has_a = fkw.get("regress_coord", False), fkw.get("regress_attention", False)
+
+    def fmt(t):                                   # neural_rendering.py:398-426
+        t = list(t)
+        d = dict(rgb=t[1].reshape(SB, -1, 3), embed=t[2].reshape(SB, -1, t[2].shape[-1]),
+                 depth=t[-1].reshape(SB, -1), weights=t[0].reshape(SB, -1, t[0].shape[-1]))
+        rest = t[3:-1]
+        if has_c:
+            d["coord"] = rest.pop(0).reshape(SB, -1, 3)
+        if has_a:
+            d["attention"] = rest.pop(0).reshape(SB, -1, 6)
+        return d
+    comp_c = composite(p, voxel_feat, r, z_c, SB, bounds, eval_batch_size, white_bkgd, sn("sigma_c"), **fkw)
+    wc, dep_c = comp_c[0], comp_c[-1]
+    res = dict(coarse=fmt(comp_c), z_coarse=z_c)
     if n_fine > 0:
         samps = [z_c]
         kf = n_fine - n_fine_depth
@@ -302,9 +347,8 @@ def forward_nerf(p, voxel_feat, rays, bounds, n_coarse, n_fine, n_fine_depth=0, 
             nz = noise.get("depth", torch.zeros(R, n_fine_depth, device=r.device))
             samps.append(sample_fine_depth(r, dep_c, n_fine_depth, nz, depth_std))
         z_all, _ = torch.sort(torch.cat(samps, dim=-1), dim=-1)
-        wf, rgb_f, emb_f, dep_f = composite(p, voxel_feat, r, z_all, SB, bounds, eval_batch_size, white_bkgd,
-                                            sn("sigma_f"), **fkw)
-        res["fine"] = fmt(wf, rgb_f, emb_f, dep_f)
+        res["fine"] = fmt(composite(p, voxel_feat, r, z_all, SB, bounds, eval_batch_size, white_bkgd, sn("sigma_f"),
+                                    **fkw))
         res["z_fine"] = z_all
     return res
 

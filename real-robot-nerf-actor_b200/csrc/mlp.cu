@@ -54,7 +54,6 @@ static int make_layout(const NrfMlpParams* p, int precision, MlpLayout* L) {
     NRF_REQUIRE(L->H % 128 == 0, NRF_ENOSUP, "mlp(bf16): d_hidden=%d must be a multiple of 128", L->H);
     NRF_REQUIRE(L->C % 64 == 0 && L->C > 0, NRF_ENOSUP,
                 "mlp(bf16): d_latent=%d must be a multiple of 64", L->C);
-    NRF_REQUIRE(L->Dout % 4 == 0, NRF_ENOSUP, "mlp(bf16): d_out=%d must be a multiple of 4", L->Dout);
     NRF_REQUIRE(L->nz <= 3, NRF_ENOSUP, "mlp(bf16): n_lin_z=%d > 3", L->nz);
   }
   int64_t off = 0;
@@ -283,7 +282,7 @@ static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* 
   d.saves = acts; d.n_slots = 2 * L.nb + 1;
   // the layer-by-layer chain keeps the residual stream in the last layer of `acts`; here it holds the gate bits
   d.gate_bits = acts ? reinterpret_cast<char*>(acts) + (int64_t)(2 * L.nb + 1) * N * L.H * (int64_t)L.es : nullptr;
-  d.out = field_out; d.d_out = L.Dout; d.ldo = L.Dout;
+  d.out = field_out; d.d_out = L.Dout; d.ldo = (int)round_up(L.Dout, 4);   // pad columns receive exact zeros
   d.prof = g_fused_prof;
   return mlp_fused_launch(d, s);
 }
@@ -376,20 +375,16 @@ static int mlp_fwd_impl(const NrfMlpParams* p, const void* packed, int precision
     g.B = W + L.Wfc1[b]; g.ldb = L.k1cat[b];
     g.bias = reinterpret_cast<const float*>(W + L.bias1[b]);
     g.resid = xcur; g.ldr = L.H;
-    if (b + 1 < L.nb) {
-      g.out_act = xcur; g.ldact = L.H;                       // x' updated in place
-      g.out_act2 = ax(b + 1); g.ldact2 = L.H; g.relu_act2 = 1;
-    } else {
-      g.out_act = ax(b + 1); g.ldact = L.H; g.relu_act = 1;  // only relu(x_nb) is needed after the last block
-    }
+    g.out_act = xcur; g.ldact = L.H;                         // x' updated in place; after the last block it is x_nb, the
+    g.out_act2 = ax(b + 1); g.ldact2 = L.H; g.relu_act2 = 1; // MLP's second return value (resnetfc.py:192-195: last_feat)
     rc = run_gemm(g, precision, false, s);
     if (rc) return rc;
   }
-  g = gemm_init(N, L.nout_pad, L.Dout);
-  set_a(g, 0, ax(L.nb), L.H, L.H);
+  g = gemm_init(N, L.nout_pad, (int)round_up(L.Dout, 4));     // rows of field_out are round_up(d_out, 4) floats long;
+  set_a(g, 0, ax(L.nb), L.H, L.H);                            // the pad columns come out as exact zeros (zero weight rows)
   g.B = W + L.Wout; g.ldb = L.H;
   g.bias = reinterpret_cast<const float*>(W + L.bias_out);
-  g.out_f32 = field_out; g.ldo = L.Dout;
+  g.out_f32 = field_out; g.ldo = (int)round_up(L.Dout, 4);
   return run_gemm(g, precision, false, s);
 }
 
@@ -409,6 +404,7 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
   NRF_REQUIRE(packed && field_in && acts && d_field && gr && scratch && N > 0, NRF_EINVAL,
               "nrf_mlp_bwd: bad arguments");
   NRF_REQUIRE(N < (int64_t)1 << 31, NRF_ENOSUP, "nrf_mlp_bwd: N too large for one call");
+  NRF_REQUIRE(!(gr->d_last && precision == NRF_PREC_BF16X3), NRF_ENOSUP, "nrf_mlp_bwd: d_last in the bf16x3 mode");
   if (precision == NRF_PREC_BF16X3)
     return mlp_x3_bwd(p, packed, N, acts, reinterpret_cast<const float*>(d_field), gr, dlatent, scratch,
                       as_stream(stream));
@@ -416,6 +412,8 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
   int rc = make_layout(p, precision, &L);
   if (rc) return rc;
   NRF_REQUIRE(L.nz == 0 || dlatent, NRF_EINVAL, "nrf_mlp_bwd: dlatent is required when d_latent > 0");
+  NRF_REQUIRE(!gr->d_last || force_layered, NRF_ENOSUP,
+              "nrf_mlp_bwd: d_last (gradient of the last residual stream) needs nrf_mlp_bwd_layered");
   cudaStream_t s = as_stream(stream);
   const char* W = reinterpret_cast<const char*>(packed);
   const char* act = reinterpret_cast<const char*>(acts);
@@ -488,6 +486,7 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
   set_a(g, 0, d_field, L.dout_pad, L.dout_pad);
   g.B = W + L.WoutT; g.ldb = L.dout_pad;
   g.mask_src = ax(L.nb); g.ldmask = L.H;
+  if (gr->d_last) { g.resid = gr->d_last; g.ldr = L.H; }      // + the gradient that reaches x_nb directly (ret_last_feat)
   g.out_act = gbuf; g.ldact = L.H;
   TRY(run_gemm(g, precision, true, s));
 

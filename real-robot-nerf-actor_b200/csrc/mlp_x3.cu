@@ -43,7 +43,6 @@ int x3_layout(const NrfMlpParams* p, X3Layout* L) {
   L->nb = p->n_blocks; L->nz = p->d_latent > 0 ? p->n_lin_z : 0;
   NRF_REQUIRE(L->H % 128 == 0, NRF_ENOSUP, "mlp(bf16x3): d_hidden=%d must be a multiple of 128", L->H);
   NRF_REQUIRE(L->C % 64 == 0 && L->C > 0, NRF_ENOSUP, "mlp(bf16x3): d_latent=%d must be a multiple of 64", L->C);
-  NRF_REQUIRE(L->Dout % 4 == 0, NRF_ENOSUP, "mlp(bf16x3): d_out=%d must be a multiple of 4", L->Dout);
   L->kin_pad = (int)rup(L->C + L->Din, 64);
   L->dout_pad = (int)rup(L->Dout, 64);
   L->nout_pad = (int)rup(L->Dout, 128);
@@ -343,7 +342,8 @@ int mlp_x3_fwd(const NrfMlpParams* p, const void* packed, const float* field_in,
     x.acc2 = cat ? acc2 : nullptr; x.has_resid = 1; x.write_stream = b + 1 < L.nb; x.out = bf(a.ax0 + (b + 1) * a.layer);
     TRY(x3_epi(x, s));
   }
-  TRY(x3_gemm(bf(a.ax0 + L.nb * a.layer), L.H, W + L.Wout, L.nout_pad, L.Dout, bias(L.bias_out), field_out, L.Dout, N, s));
+  TRY(x3_gemm(bf(a.ax0 + L.nb * a.layer), L.H, W + L.Wout, L.nout_pad, (int)rup(L.Dout, 4), bias(L.bias_out), field_out,
+              (int)rup(L.Dout, 4), N, s));
 #undef TRY
   return NRF_OK;
 }

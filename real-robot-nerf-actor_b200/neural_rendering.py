@@ -12,8 +12,9 @@ Differences from the reference, all opt-in or invisible to its callers:
     gradients too: ordered reduction instead of fp32 atomics) attributes;
   * `forward_nerf(rays, want_weights=False, noise=None)`: `noise` injects pre-drawn tensors
     (keys coarse / u / fine / depth), used by the parity tests;
-  * branches that are off in nerfact.conf (multi-scale voxels, depth-supervision volume, coord /
-    attention heads, ret_last_feat, softplus, spade) raise NotImplementedError.
+  * the optional branches of nerfact.conf: coord / attention heads run on the default (fused) path; multi-scale voxels
+    and ret_last_feat run composed.py (same kernels, three autograd nodes per pass, fp32 MLP); softplus, spade and
+    the depth-supervision volume (which the reference itself cannot run) raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -26,9 +27,40 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .utils import AttrDict, PositionalEncoding, gen_rays
+from .utils import AttrDict, PositionalEncoding, gen_rays, pca_fit_transform
 
 __all__ = ["NeuralRenderer", "PixelNeRFEmbedNet", "ResnetFC", "ResnetBlockFC", "PSNR_torch", "LossDict"]
+
+
+class _trace:
+    """The reference's profiler labels (torch.autograd.profiler.record_function: neural_rendering.py:236
+    "renderer_composite", models_embed.py:306 "model_inference", resnetfc.py:153 "resnetfc_infer", resnetfc.py:56
+    "resblock", utils.py:551 "positional_enc") around the stages that replace that code, as record_function ranges AND
+    NVTX ranges (nsys / ncu --nvtx).  The five residual blocks run inside one fused kernel, so "resblock" brackets the
+    same launch as "resnetfc_infer"; "positional_enc" brackets the fused gather + encoding kernel.
+    `NeuralRenderer.trace_ranges = False` turns them off (each costs ~2 us of host time)."""
+    enabled = True
+    __slots__ = ("names", "rf")
+
+    def __init__(self, *names):
+        self.names = names
+
+    def __enter__(self):
+        if not _trace.enabled:
+            return self
+        self.rf = [torch.autograd.profiler.record_function(n) for n in self.names]
+        for n, r in zip(self.names, self.rf):
+            r.__enter__()
+            torch.cuda.nvtx.range_push(n)
+        return self
+
+    def __exit__(self, *exc):
+        if not _trace.enabled:
+            return False
+        for r in reversed(self.rf):
+            torch.cuda.nvtx.range_pop()
+            r.__exit__(*exc)
+        return False
 
 
 def _cfg_get(cfg, key, default=None):
@@ -287,10 +319,9 @@ class PixelNeRFEmbedNet(nn.Module):
         self.conf = conf
         self.coordinate_bounds = coordinate_bounds
         g = lambda k, d=None: _cfg_get(conf, k, d)
-        unsupported = dict(use_multi_scale_voxel=g("use_multi_scale_voxel", False),
-                           use_depth_supervision=g("use_depth_supervision", False),
-                           regress_coord=g("regress_coord", False),
-                           regress_attention=g("regress_attention", False),
+        unsupported = dict(use_depth_supervision=g("use_depth_supervision", False),   # cannot run in the reference either
+                                                                                      # (models_embed.py:151-154 never
+                                                                                      # stores voxel_density, :289 samples None)
                            use_code_viewdirs=g("use_code_viewdirs", False),
                            use_freenerf=g("use_freenerf", False), normalize_z=g("normalize_z", False))
         for k, v in unsupported.items():
@@ -308,13 +339,15 @@ class PixelNeRFEmbedNet(nn.Module):
         self.stop_encoder_grad = stop_encoder_grad
         self.use_code, self.use_code_viewdirs, self.use_viewdirs, self.use_xyz = True, False, True, True
         self.use_freenerf = False
-        self.regress_coord = self.regress_attention = False
-        self.use_multi_scale_voxel = self.use_depth_supervision = False
-        self.d_latent = d_latent = g("d_latent")
+        self.regress_coord = bool(g("regress_coord", False))            # models_embed.py:63-68: 3 / 6 more outputs
+        self.regress_attention = bool(g("regress_attention", False))
+        self.use_depth_supervision = False
+        self.use_multi_scale_voxel = bool(g("use_multi_scale_voxel", False))        # models_embed.py:69-72
+        self.d_latent = d_latent = g("d_multi_scale_latent") if self.use_multi_scale_voxel else g("d_latent")
         self.d_lang = g("d_lang", 0)
         self.code = PositionalEncoding.from_conf(conf["code"], d_in=3)
         d_in = self.code.d_out + 3
-        d_out = 4 + conf["d_embed"]
+        d_out = 4 + conf["d_embed"] + (3 if self.regress_coord else 0) + (6 if self.regress_attention else 0)
         self.share_mlp = g("share_mlp", True)
         mlp = conf["mlp"] if not hasattr(conf, "mlp") else conf.mlp
         mk = lambda: ResnetFC(d_in=d_in, d_latent=d_latent, d_lang=self.d_lang, d_out=d_out,
@@ -334,7 +367,7 @@ class PixelNeRFEmbedNet(nn.Module):
     def encode(self, voxel_feat, lang, multi_scale_voxel_list, voxel_density, poses, focal, c=None):
         """models_embed.py:136-183: stores a reference to the volume; focal / c bookkeeping only."""
         self.voxel_feat = voxel_feat
-        self.multi_scale_voxel_list = None
+        self.multi_scale_voxel_list = multi_scale_voxel_list if self.use_multi_scale_voxel else None   # :147-149
         self.voxel_density = None
         self.language = lang
         if focal is not None:
@@ -359,8 +392,6 @@ class PixelNeRFEmbedNet(nn.Module):
         """models_embed.py:295-471: the field at world points.  xyz, viewdirs (SB, B, 3) ->
         (output (SB, B, 4 + d_embed) = [sigmoid(rgb), relu(sigma), embed], point_density = None).  Call encode() first.
         Differentiable w.r.t. the encoded volume and the MLP parameters."""
-        if ret_last_feat:
-            raise NotImplementedError("ret_last_feat=True is off in nerfact.conf and not built")
         if viewdirs is None:
             raise NotImplementedError("use_viewdirs=False (neural_rendering.py:294-295 raises too)")
         if self.voxel_feat is None:
@@ -371,15 +402,34 @@ class PixelNeRFEmbedNet(nn.Module):
                                f"but got input with sizes {list(self.voxel_feat.shape)} and {SB} point batches")
         prec = ops.PRECISIONS[precision] if isinstance(precision, str) else precision
         mlp = self.mlp_coarse if coarse or self.mlp_fine is None else self.mlp_fine
-        h = mlp.handle(prec)
         rays = torch.zeros(SB * B, 8, device=xyz.device, dtype=torch.float32)
         rays[:, 0:3] = xyz.reshape(-1, 3)
         rays[:, 3:6] = viewdirs.reshape(-1, 3)
-        ps = [mlp.param_dict()[n] for n in h.names()]
-        keep = torch.is_grad_enabled() and (self.voxel_feat.requires_grad or any(p.requires_grad for p in ps))
         bounds = torch.as_tensor(self.coordinate_bounds, dtype=torch.float32).reshape(-1).cpu()
-        raw = _FieldFn.apply(self, h, bounds, self.voxel_feat, rays, SB, keep, *ps)
-        out = torch.cat([torch.sigmoid(raw[:, :3]), torch.relu(raw[:, 3:4]), raw[:, 4:]], -1)     # :444-466
+        last_feat = None
+        if ret_last_feat or self.use_multi_scale_voxel:          # composed branch (composed.py): fp32 MLP, layer by layer
+            from . import composed
+            z0 = torch.zeros(SB * B, 1, device=xyz.device, dtype=torch.float32)
+            vols = list(self.multi_scale_voxel_list or []) + [self.voxel_feat]
+            shim = AttrDict(_bounds=bounds)
+            raw, last_feat = composed.field_rows(shim, self, mlp, vols, rays, z0, B)
+        else:
+            h = mlp.handle(prec)
+            ps = [mlp.param_dict()[n] for n in h.names()]
+            keep = torch.is_grad_enabled() and (self.voxel_feat.requires_grad or any(p.requires_grad for p in ps))
+            raw = _FieldFn.apply(self, h, bounds, self.voxel_feat, rays, SB, keep, *ps)
+        parts = [torch.sigmoid(raw[:, :3]), torch.relu(raw[:, 3:4]), raw[:, 4:4 + self.d_embed]]   # :444-466
+        o = 4 + self.d_embed
+        if self.regress_coord:                                  # coord - canon_xyz (:449,:455); canon is @no_grad (:185)
+            b6 = bounds.to(xyz.device)
+            canon = (xyz.reshape(-1, 3).detach() - b6[:3]) / (b6[3:] - b6[:3])
+            parts.append(raw[:, o:o + 3] - canon)
+            o += 3
+        if self.regress_attention:
+            parts.append(raw[:, o:o + 6])
+        out = torch.cat(parts, -1)
+        if ret_last_feat:                                        # models_embed.py:468-471
+            return out.reshape(SB, B, -1), last_feat.reshape(SB, B, -1), None
         return out.reshape(SB, B, -1), None
 
 
@@ -401,7 +451,7 @@ class _FieldFn(torch.autograd.Function):
         if keep:
             ctx.h, ctx.field_in, ctx.acts, ctx.rays, ctx.z = h, field_in, acts, rays, z
             ctx.vol_shape, ctx.cl3d, ctx.sb, ctx.bounds = tuple(vol_cl.shape), cl3d, sb, bounds
-        return out[:, :model.d_out]
+        return out[:, :model.d_out].contiguous() if out.shape[1] != model.d_out else out
 
     @staticmethod
     def backward(ctx, d_out):
@@ -453,10 +503,14 @@ def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps, keep_acts=True, 
     st = _PassState()
     st.rays, st.z, st.rps, st.mlp, st.perm, st.sig_noise = rays, z, rps, mlp, None, sig_noise
     st.z_sorted = st.base = None
-    st.field_in = ops.encode_points(rays, z, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
-                                    ld_out=mlp.sizes.kin_pad, precision=mlp.precision)
-    st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=repack)
-    outs = ops.composite_fwd(st.field_out, z, rays, ren._d_embed, ren.white_bkgd, sigma_noise=sig_noise)
+    with _trace("renderer_composite"):
+        with _trace("model_inference"):
+            with _trace("positional_enc"):
+                st.field_in = ops.encode_points(rays, z, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
+                                                ld_out=mlp.sizes.kin_pad, precision=mlp.precision)
+            with _trace("resnetfc_infer", "resblock"):
+                st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=repack)
+        outs = ops.composite_fwd(st.field_out, z, rays, ren._d_comp, ren.white_bkgd, sigma_noise=sig_noise)
     return st, outs
 
 
@@ -468,11 +522,15 @@ def _pass_forward_reuse(ren, mlp, vol_cl, rays, z_new, z_sorted, perm, base, rps
     st = _PassState()
     st.rays, st.z, st.rps, st.mlp, st.perm, st.sig_noise = rays, z_new, rps, mlp, perm, sig_noise
     st.z_sorted, st.base = z_sorted, base
-    st.field_in = ops.encode_points(rays, z_new, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
-                                    ld_out=mlp.sizes.kin_pad, precision=mlp.precision)
-    st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=False)
-    outs = ops.composite_fwd(base.field_out, z_sorted, rays, ren._d_embed, ren.white_bkgd, sigma_noise=sig_noise,
-                             reuse=(st.field_out, perm, base.z.shape[1]))
+    with _trace("renderer_composite"):
+        with _trace("model_inference"):
+            with _trace("positional_enc"):
+                st.field_in = ops.encode_points(rays, z_new, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
+                                                ld_out=mlp.sizes.kin_pad, precision=mlp.precision)
+            with _trace("resnetfc_infer", "resblock"):
+                st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=False)
+        outs = ops.composite_fwd(base.field_out, z_sorted, rays, ren._d_comp, ren.white_bkgd, sigma_noise=sig_noise,
+                                 reuse=(st.field_out, perm, base.z.shape[1]))
     return st, outs
 
 
@@ -481,7 +539,7 @@ def _backward_reuse(ren, st_c, st_f, gc, gf, grads, defer, depth_mask, grad_cl):
     gradient rows of all Kc + Kf samples (coarse ones into the coarse buffer), the coarse compositing backward adds
     its own, and every sample goes through the MLP backward exactly once."""
     dev = st_c.rays.device
-    R, D = st_c.rays.shape[0], ren._d_embed
+    R, D = st_c.rays.shape[0], ren._d_comp
     Kc, Kfd = st_c.z.shape[1], ren.n_fine_depth
     d_cw, d_crgb, d_cemb, d_cdep = gc
     d_fw, d_frgb, d_femb, d_fdep = gf
@@ -511,12 +569,24 @@ def _backward_reuse(ren, st_c, st_f, gc, gf, grads, defer, depth_mask, grad_cl):
             ops.scatter_volume_grad(st.rays, st.z, st.rps, dlat, grad_cl, ren._bounds)
 
 
+def _coord_raw(ren, st):
+    """regress_coord: the raw coordinate outputs of every sample (R, K, 3): they are averaged over the samples, not
+    alpha-composited (neural_rendering.py:356-357), which forward_nerf does with plain torch ops."""
+    R, K = st.z.shape
+    o = 4 + ren._d_embed
+    return st.field_out.view(R, K, -1)[:, :, o:o + 3].clone()
+
+
 def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, want_dz=False, first=True,
-                   defer=None):
-    res = ops.composite_bwd(st.field_out, st.z, st.rays, ren._d_embed, d_rgb, d_embed, d_depth, d_weights,
+                   defer=None, d_coord_raw=None):
+    res = ops.composite_bwd(st.field_out, st.z, st.rays, ren._d_comp, d_rgb, d_embed, d_depth, d_weights,
                             ldg=st.mlp.sizes.dout_pad, precision=st.mlp.precision,
                             white_bkgd=ren.white_bkgd, want_dz=want_dz, sigma_noise=st.sig_noise)
     d_field, d_z = res if want_dz else (res, None)
+    if d_coord_raw is not None:           # gradient of the (uncomposited) coordinate outputs, straight into d_field
+        R, K = st.z.shape
+        o = 4 + ren._d_embed
+        d_field.view(R, K, -1)[:, :, o:o + 3] += d_coord_raw.to(d_field.dtype)
     dlat = st.mlp.backward(st.field_in, st.acts, d_field, grads, deterministic=ren.deterministic)
     if defer is not None:             # one merged scatter for all passes once the last one is through
         defer.append((st.z, dlat))
@@ -639,7 +709,7 @@ class _ForwardNerfFn(torch.autograd.Function):
                 near, far = rays[:, 6:7], rays[:, 7:8]
                 depth_mask = ((z0 <= far) & (z0 >= near)).to(torch.float32)
                 z_all[:, Kc + kf:] = torch.max(torch.min(z0, far), near)
-            reuse = ren.reuse_coarse_evals and mlp_f is mlp_c
+            reuse = ren.reuse_coarse_evals and mlp_f is mlp_c and not ren.regress_coord
             z_new = z_all[:, Kc:].contiguous() if reuse else None
             z_all, perm = ops.sort_rows(z_all, want_perm=True)
             sn_f = _sigma_noise(ren, noise, "sigma_f", R, K, rays.device)
@@ -651,6 +721,10 @@ class _ForwardNerfFn(torch.autograd.Function):
                                                              repack=False)
                 st_f.perm = perm
             outs += [z_all, fw, frgb, femb, fdep]
+        if ren.regress_coord:                              # appended: the raw coordinate outputs of each pass
+            outs.append(_coord_raw(ren, st_c))
+            if st_f is not None:
+                outs.append(_coord_raw(ren, st_f))
         ctx.ren, ctx.st_c, ctx.st_f, ctx.sb, ctx.n_pc = ren, st_c, st_f, sb, n_pc
         ctx.vol_shape = tuple(vol_cl.shape)
         ctx.depth_mask = depth_mask
@@ -676,7 +750,10 @@ class _ForwardNerfFn(torch.autograd.Function):
         ctx.st_c = ctx.st_f = None
         dev = st_c.rays.device
         R = st_c.rays.shape[0]
-        D = ren._d_embed
+        D = ren._d_comp
+        n_base = 5 if st_f is None else 10
+        d_ccoord = g[n_base] if ren.regress_coord else None
+        d_fcoord = g[n_base + 1] if ren.regress_coord and st_f is not None else None
         shared = ren.nerf_model.mlp_fine is ren.nerf_model.mlp_coarse
         names_c = st_c.mlp.names()
         grads_c = _zero_grads(st_c.mlp)
@@ -706,7 +783,7 @@ class _ForwardNerfFn(torch.autograd.Function):
             Kfd = ren.n_fine_depth
             d_z = _pass_backward(ren, st_f, _zeros_like_or(d_frgb, (R, 3), dev),
                                  _zeros_like_or(d_femb, (R, D), dev), d_fdep, d_fw, grads_f, grad_cl,
-                                 want_dz=Kfd > 0, defer=defer)
+                                 want_dz=Kfd > 0, defer=defer, d_coord_raw=d_fcoord)
             if Kfd > 0:
                 # route dL/dz of the depth-guided samples back through sort and clamp to coarse depth
                 K = st_f.z.shape[1]
@@ -714,7 +791,7 @@ class _ForwardNerfFn(torch.autograd.Function):
                 d_cat.scatter_(1, st_f.perm.long(), d_z)
                 d_cdep = d_cdep + (d_cat[:, K - Kfd:] * ctx.depth_mask).sum(-1)
         _pass_backward(ren, st_c, _zeros_like_or(d_crgb, (R, 3), dev), _zeros_like_or(d_cemb, (R, D), dev),
-                       d_cdep, d_cw, grads_c, grad_cl, first=st_f is None, defer=defer)
+                       d_cdep, d_cw, grads_c, grad_cl, first=st_f is None, defer=defer, d_coord_raw=d_ccoord)
         # every MLP gradient of this step is final: start their all-reduce now, it overlaps the volume scatter
         pending = _start_grad_allreduce(ren, grads_c, grads_f)
         d_vol = None
@@ -764,16 +841,16 @@ class NeuralRenderer(nn.Module):
         g = lambda k, d=None: _cfg_get(cfg, k, d)
         self.W, self.H = g("image_width"), g("image_height")
         self.z_near, self.z_far = g("z_near"), g("z_far")
-        self.regress_coord, self.regress_attention = g("regress_coord", False), g("regress_attention", False)
+        self.regress_coord, self.regress_attention = bool(g("regress_coord", False)), bool(g("regress_attention", False))
         self.n_coarse, self.n_fine, self.n_fine_depth = g("n_coarse"), g("n_fine"), g("n_fine_depth", 0)
         self.lindisp = g("lindisp", False)
         self.using_fine = self.n_fine > 0
         self.eval_batch_size = g("eval_batch_size", 4096)
         self.ret_last_feat = g("ret_last_feat", False)
         self.noise_std, self.white_bkgd, self.depth_std = g("noise_std", 0.0), g("white_bkgd", False), g("depth_std", 0.001)
-        if self.ret_last_feat:
-            raise NotImplementedError("ret_last_feat=True is off in nerfact.conf and not built")
         self.nerf_model = PixelNeRFEmbedNet(cfg, coordinate_bounds)
+        # multi-scale voxels / ret_last_feat change the MLP's input / what is composited: composed.py
+        self._composed = bool(self.ret_last_feat) or self.nerf_model.use_multi_scale_voxel
         self.model_name = g("foundation_model_name", None)
         if self.model_name not in ("odise", "diffusion", "dinov2", "deepfloyd", None):
             raise NotImplementedError(f"foundation model {self.model_name} is not implemented")
@@ -796,9 +873,14 @@ class NeuralRenderer(nn.Module):
                                                # the flat MLP gradient buffer itself, under the volume scatter
         self.fused_loss = True                 # rgb / embed losses + their gradients in one kernel (nrf_render_loss)
         self.render_chunk_rays = 4096          # neural_rendering.py:482
+        self.trace_ranges = True               # the reference's five profiler labels as record_function + NVTX ranges
         self._num_freqs = self.nerf_model.code.num_freqs
         self._freq_factor = float(self.nerf_model.code.freq_factor)
         self._d_embed = self.nerf_model.d_embed
+        # channels the compositing kernels weight-sum after [rgb, sigma]: embed (+ coord, which is then ignored) + attention,
+        # rounded up to whole float4s (the field-output rows are padded with exact zeros)
+        n_heads = (3 if self.regress_coord else 0) + (6 if self.regress_attention else 0)
+        self._d_comp = (self._d_embed + n_heads + 3) // 4 * 4
         if not self.nerf_model.code.include_input:
             raise NotImplementedError("code.include_input=False is not built")
 
@@ -883,24 +965,61 @@ class NeuralRenderer(nn.Module):
         """neural_rendering.py:224-395 for externally supplied samples -> weights, rgb, embed, depth."""
         model = model if model is not None else self.nerf_model
         sb = max(int(sb), 1)
+        if self._composed:
+            from . import composed
+            return composed.composite_pass(self, model, rays.contiguous(), z_samp.contiguous(), coarse, sb,
+                                           _sigma_noise(self, {}, None, z_samp.shape[0], z_samp.shape[1], z_samp.device))
         mlp = (model.mlp_coarse if coarse or model.mlp_fine is None else model.mlp_fine)
         h = mlp.handle(self._prec)
         names = h.names()
         ps = [mlp.param_dict()[n] for n in names]
-        return _CompositeFn.apply(self, h, model.voxel_feat, rays.contiguous(), z_samp.contiguous(), sb, *ps)
+        rays, z_samp = rays.contiguous(), z_samp.contiguous()
+        res = _CompositeFn.apply(self, h, model.voxel_feat, rays, z_samp, sb, *ps)
+        return self._split_heads(*res[:4], res[4] if self.regress_coord else None, rays, z_samp)
 
     def _format_outputs(self, rendered_outputs, superbatch_size, want_weights=False):
-        """neural_rendering.py:398-426."""
-        weights, rgb, embed, depth = rendered_outputs
+        """neural_rendering.py:398-426: (weights, rgb, embed, [coord], [attention], depth) -> AttrDict."""
+        rendered_outputs = list(rendered_outputs)
+        weights, rgb, embed = rendered_outputs[:3]
+        depth = rendered_outputs[-1]
+        rest = rendered_outputs[3:-1]
+        coord = rest.pop(0) if self.regress_coord else None
+        attention = rest.pop(0) if self.regress_attention else None
         if superbatch_size > 0:
             rgb = rgb.reshape(superbatch_size, -1, 3)
             embed = embed.reshape(superbatch_size, -1, embed.shape[-1])
             depth = depth.reshape(superbatch_size, -1)
             weights = weights.reshape(superbatch_size, -1, weights.shape[-1])
+            if coord is not None:
+                coord = coord.reshape(superbatch_size, -1, 3)
+            if attention is not None:
+                attention = attention.reshape(superbatch_size, -1, attention.shape[-1])
         ret = AttrDict(rgb=rgb, embed=embed, depth=depth)
         if want_weights:
             ret.weights = weights
+        if coord is not None:
+            ret.coord = coord
+        if attention is not None:
+            ret.attention = attention
         return ret
+
+    def _split_heads(self, w, rgb, emb_all, dep, coord_raw, rays, z, d_embed=None):
+        """(weights, rgb, embed', depth) of a compositing pass + the raw coordinate outputs -> the reference's tuple
+        (weights, rgb, embed, [coord], [attention], depth) (neural_rendering.py:388-395)."""
+        D = self._d_embed if d_embed is None else d_embed
+        out = [w, rgb, emb_all[:, :D] if emb_all.shape[1] != D else emb_all]
+        o = D
+        if self.regress_coord:
+            # coord_final = mean over the samples of (coord - canon_xyz) (models_embed.py:449, neural_rendering.py:356-357)
+            b6 = torch.as_tensor(self._bounds, dtype=torch.float32).to(rays.device, non_blocking=True)
+            pts = rays[:, None, :3] + z.unsqueeze(2) * rays[:, None, 3:6]
+            canon = (pts - b6[:3]) / (b6[3:] - b6[:3])
+            out.append(torch.mean(coord_raw - canon, -2))
+            o += 3
+        if self.regress_attention:
+            out.append(emb_all[:, o:o + 6])
+        out.append(dep)
+        return tuple(out)
 
     def forward_nerf(self, rays, want_weights=False, noise=None):
         """neural_rendering.py:435-471.  rays (SB,B,8) -> AttrDict(coarse=..., fine=...)."""
@@ -913,16 +1032,23 @@ class NeuralRenderer(nn.Module):
             raise RuntimeError("grid_sampler(): expected grid and input to have same batch size, "
                                f"but got input with sizes {list(vol.shape)} and {sb} ray batches")
         flat = rays.reshape(-1, 8).contiguous()
+        _trace.enabled = bool(self.trace_ranges)
         if noise is None:
             noise = self._draw_noise(flat.shape[0], flat.device)
+        if self._composed:
+            from . import composed
+            return composed.forward_nerf(self, flat, sb, noise, want_weights)
         n_pc, ps = self._params_flat()
         # decided here: inside Function.forward grad mode is always off and needs_input_grad ignores no_grad()
         keep = torch.is_grad_enabled() and (vol.requires_grad or any(p.requires_grad for p in ps))
         outs = _ForwardNerfFn.apply(self, vol, flat, sb, noise, n_pc, keep, *ps)
-        outputs = AttrDict(coarse=self._format_outputs(outs[1:5], sb, want_weights))
+        n_base = 10 if self.using_fine else 5
+        craw = outs[n_base] if self.regress_coord else None
+        outputs = AttrDict(coarse=self._format_outputs(self._split_heads(*outs[1:5], craw, flat, outs[0]), sb, want_weights))
         outputs.coarse.z = outs[0]
         if self.using_fine:
-            outputs.fine = self._format_outputs(outs[6:10], sb, want_weights)
+            fraw = outs[n_base + 1] if self.regress_coord else None
+            outputs.fine = self._format_outputs(self._split_heads(*outs[6:10], fraw, flat, outs[5]), sb, want_weights)
             outputs.fine.z = outs[5]
         return outputs
 
@@ -982,12 +1108,11 @@ class NeuralRenderer(nn.Module):
                 gt_embed = self.extract_foundation_model_feature(gt_rgb, lang_goal)
                 embed_dim = _cfg_get(self.cfg, "d_embed")
                 if embed_dim < 512 and gt_embed.shape[1] != embed_dim:
-                    from sklearn.decomposition import PCA        # neural_rendering.py:640-646
+                    # neural_rendering.py:640-646 (sklearn PCA on the CPU) on the device: no host round trip / stall
                     Bq, Dq, Hq, Wq = gt_embed.shape
-                    flat = gt_embed.permute(0, 2, 3, 1).reshape(Bq * Hq * Wq, Dq).cpu().numpy()
-                    flat = PCA(n_components=embed_dim).fit_transform(flat)
-                    gt_embed = torch.from_numpy(flat).reshape(Bq, Hq, Wq, embed_dim).permute(0, 3, 1, 2)
-                    gt_embed = gt_embed.to(gt_rgb.device)
+                    flat = gt_embed.permute(0, 2, 3, 1).reshape(Bq * Hq * Wq, Dq)
+                    flat = pca_fit_transform(flat.float(), embed_dim)
+                    gt_embed = flat.reshape(Bq, Hq, Wq, embed_dim).permute(0, 3, 1, 2)
                 gt_embed = gt_embed.permute(0, 2, 3, 1)
         D = gt_embed.shape[-1]
         if self.fused_loss and gt_rgb.is_cuda and gt_rgb.dtype == torch.float32 and gt_embed.dtype == torch.float32:
@@ -1043,16 +1168,16 @@ class _CompositeFn(torch.autograd.Function):
         st, outs = _pass_forward(ren, h, vol_cl, rays, z, rays.shape[0] // sb,
                                  sig_noise=_sigma_noise(ren, {}, None, z.shape[0], z.shape[1], z.device))
         ctx.ren, ctx.st, ctx.vol_shape, ctx.cl3d = ren, st, tuple(vol_cl.shape), cl3d
-        return outs
+        return (*outs, _coord_raw(ren, st)) if ren.regress_coord else outs
 
     @staticmethod
-    def backward(ctx, d_w, d_rgb, d_emb, d_dep):
+    def backward(ctx, d_w, d_rgb, d_emb, d_dep, d_coord_raw=None):
         ren, st = ctx.ren, ctx.st
         if st is None:
             raise RuntimeError("composite: backward a second time (retain_graph is not supported)")
         ctx.st = None
         dev = st.rays.device
-        R, D = st.rays.shape[0], ren._d_embed
+        R, D = st.rays.shape[0], ren._d_comp
         names = st.mlp.names()
         grads = _zero_grads(st.mlp)
         merged = _merged_scatter_ok(ren, ctx.vol_shape)
@@ -1062,7 +1187,8 @@ class _CompositeFn(torch.autograd.Function):
             alloc = torch.empty if ren.scatter == "sorted" else torch.zeros
             grad_cl = alloc(ctx.vol_shape, device=dev, dtype=torch.float32)
         d_z = _pass_backward(ren, st, _zeros_like_or(d_rgb, (R, 3), dev), _zeros_like_or(d_emb, (R, D), dev),
-                             d_dep, d_w, grads, grad_cl, want_dz=ctx.needs_input_grad[4], defer=defer)
+                             d_dep, d_w, grads, grad_cl, want_dz=ctx.needs_input_grad[4], defer=defer,
+                             d_coord_raw=d_coord_raw)
         d_vol = None
         if ctx.needs_input_grad[2]:
             if merged:

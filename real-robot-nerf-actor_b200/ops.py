@@ -529,7 +529,8 @@ class FieldMLP:
         lib = _lib.load()
         if acts is None and (keep_acts or layered or not self.fused):
             acts = torch.empty(self.sizes.fwd_bytes_per_sample * N, device=dev, dtype=torch.uint8)
-        out = torch.empty(N, self.dims[3], device=dev, dtype=torch.float32)
+        # rows are d_out rounded up to whole float4s; the pad columns come back as exact zeros
+        out = torch.empty(N, (self.dims[3] + 3) // 4 * 4, device=dev, dtype=torch.float32)
         fn = lib.nrf_mlp_fwd_layered if layered else lib.nrf_mlp_fwd
         check(fn(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
                  ptr(acts), ptr(out), stream_ptr()), "nrf_mlp_fwd")
@@ -539,9 +540,20 @@ class FieldMLP:
         return out, acts
 
     @_on_tensor_device
-    def backward(self, field_in, acts, d_field, grads: dict, scratch=None, deterministic=False, layered=False):
+    def last_feat(self, acts, N):
+        """x_nb (N, d_hidden), the MLP's second return value (resnetfc.py:192-195), after a layered forward: a view of
+        the last layer of `acts`."""
+        H, nb = self.dims[2], self.dims[4]
+        dt = act_dtype(self.precision)
+        es = torch.empty(0, dtype=dt).element_size()
+        off = (2 * nb + 1) * N * H * es
+        return acts[off:off + N * H * es].view(dt).view(N, H)
+
+    def backward(self, field_in, acts, d_field, grads: dict, scratch=None, deterministic=False, layered=False,
+                 d_last=None):
         """Accumulates parameter grads into `grads` (same keys as params); returns dlatent (N,C).
-        deterministic: ordered (bit-reproducible) reduction of the weight-gradient sample splits."""
+        deterministic: ordered (bit-reproducible) reduction of the weight-gradient sample splits.
+        d_last (N, d_hidden): gradient w.r.t. the last residual stream (layered chain only)."""
         N = field_in.shape[0]
         dev = field_in.device
         d_latent = self.dims[1]
@@ -552,6 +564,9 @@ class FieldMLP:
         dlatent = torch.empty(N, d_latent, device=dev, dtype=torch.float32)
         g = self._fill(_lib.NrfMlpGrads(), lambda n: grads[n].data_ptr() if grads.get(n) is not None else None)
         g.deterministic = int(bool(deterministic))
+        if d_last is not None:
+            assert d_last.shape == (N, self.dims[2]) and d_last.dtype == grad_dtype(self.precision) and d_last.is_contiguous()
+            g.d_last = d_last.data_ptr()
         lib = _lib.load()
         layered = layered or getattr(acts, "_nrf_layered", False)
         fn = lib.nrf_mlp_bwd_layered if layered else lib.nrf_mlp_bwd

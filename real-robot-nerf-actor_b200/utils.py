@@ -121,3 +121,29 @@ class PositionalEncoding(torch.nn.Module):
     def from_conf(cls, conf, d_in=3):
         g = lambda k: conf[k] if isinstance(conf, dict) else getattr(conf, k)
         return cls(g("num_freqs"), d_in, g("freq_factor"), g("include_input"))
+
+
+def pca_fit_transform(x: torch.Tensor, n_components: int) -> torch.Tensor:
+    """sklearn.decomposition.PCA(n_components).fit_transform(x) on the device x lives on (neural_rendering.py:640-646
+    runs it on the CPU through numpy: a device -> host -> device round trip of the whole target feature map and a host
+    stall in every training step).
+
+    x (N, D) -> scores (N, n_components) = (x - mean) . V_k, V_k the top principal axes.  Exact PCA through the (D, D)
+    covariance eigen-decomposition in fp64 (N >> D here: N = B*H*W pixels); signs follow sklearn's svd_flip
+    (u_based_decision=False: the largest-magnitude entry of every axis is positive), so the result equals sklearn's
+    `svd_solver="full"` / "covariance_eigh" output up to rounding.  (sklearn's "auto" may pick the randomized solver,
+    whose output is itself only approximate and seed-dependent.)"""
+    if x.dim() != 2:
+        raise ValueError("pca_fit_transform expects (N, D)")
+    n, d = x.shape
+    if not 0 < n_components <= min(n, d):
+        raise ValueError(f"n_components={n_components} must be in (0, min(N, D)={min(n, d)}]")
+    xd = x.to(torch.float64)
+    xc = xd - xd.mean(0, keepdim=True)
+    cov = xc.t() @ xc                                   # (D, D); the 1/(N-1) factor does not change the axes
+    evals, evecs = torch.linalg.eigh(cov)               # ascending
+    v = evecs[:, -n_components:].flip(1)                # (D, k), descending variance
+    idx = v.abs().argmax(0)
+    signs = torch.sign(v[idx, torch.arange(n_components, device=v.device)])
+    signs = torch.where(signs == 0, torch.ones_like(signs), signs)
+    return (xc @ (v * signs)).to(x.dtype)

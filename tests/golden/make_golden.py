@@ -14,6 +14,10 @@ Cases
   full_s32                : BASELINE dims (C=128, D=384, hidden 512, Kc=Kf=64), 32^3 volume;
                             inputs are regenerated from seeds (synthetic.py / init_params), only
                             outputs and gradient projections are stored.
+  small_heads             : regress_coord + regress_attention (3 + 6 extra outputs, d_out = 37): all outputs of
+                            forward_nerf incl. coord / attention and the gradients of a probe loss over all of them.
+  small_multiscale        : use_multi_scale_voxel (three volumes of 10 / 8 / 16 channels at 12^3 / 6^3 / 12^3) with
+                            ret_last_feat (the MLP's last residual stream composited) and depth-guided samples.
   raygen                  : gen_rays for 60x80 (focal 76.18187) and rows of 128x128 (focal 153).
   voxelize_small          : the reference's VoxelGrid.coords_to_bounding_voxel_grid (voxel_grid_real.py) on a seeded
                             clustered point cloud (inputs regenerated from the seed by synthetic.voxelizer_points).
@@ -146,6 +150,128 @@ def run_case(name, S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, focal, store_
     print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "loss", float(out["loss"]))
 
 
+def run_heads_case(name="small_heads", S=12, C=16, D=24, hidden=64, SB=2, n_rays=40, Kc=16, Kf=16, H=16, W=16,
+                   focal=19.0, seed=6):
+    """regress_coord + regress_attention (models_embed.py:63-68,447-461, neural_rendering.py:318-329,353-357,388-395):
+    d_out = 4 + D + 3 + 6 = 37 outputs; forward_nerf of the reference + a loss over ALL of its outputs (the reference's
+    own loss ignores coord / attention), gradients into the volume and the MLP."""
+    torch.manual_seed(seed)
+    cfg = L.default_cfg(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H, n_coarse=Kc, n_fine=Kf,
+                        n_fine_depth=0, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden), eval_batch_size=1024,
+                        regress_coord=True, regress_attention=True)
+    ren = L.build_reference_renderer(cfg, torch.tensor(syn.BOUNDS))
+    d_out = 4 + D + 9
+    params = O.init_params(d_in=42, d_latent=C, d_hidden=hidden, d_out=d_out, seed=seed)
+    g = torch.Generator().manual_seed(77 + seed)
+    for k in params:
+        if k.endswith(".bias"):
+            params[k] = 0.05 * torch.randn(params[k].shape, generator=g)
+    load_params_into(ren, params)
+    vol = syn.make_volume(SB, C, S, seed=seed).requires_grad_(True)
+    poses = syn.arc_poses(SB)
+    focal_t = torch.tensor(focal, dtype=torch.float32)
+    idx = syn.pick_ray_indices(H * W, n_rays, seed=seed)
+    R = SB * n_rays
+    noise = syn.make_noise(R, Kc, Kf, seed=seed)
+    U = sys.modules["_nrf_reference_utils"]
+    rays = U.gen_rays(poses, W, H, focal_t, cfg.z_near, cfg.z_far, c=None).reshape(SB, H * W, 8)[:, idx]
+    ren.train()
+    ren.encode(None, None, None, vol, poses, focal_t, None)
+    with L.inject_noise([noise["coarse"], noise["u"], noise["fine"]]):
+        o = ren.forward_nerf(rays, want_weights=True)
+    gw = torch.Generator().manual_seed(900 + seed)
+    loss = 0.0
+    probes = {}
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "coord", "attention"):
+            t = o[lvl][k]
+            probes[f"{lvl}_{k}"] = torch.randn(t.shape, generator=gw)
+            loss = loss + (t * probes[f"{lvl}_{k}"]).sum()
+    loss.backward()
+    fx = {"meta": np.array([S, C, D, hidden, SB, n_rays, Kc, Kf, 0, H, W, seed]), "focal": np.float32(focal),
+          "idx": idx.numpy(), "rays": rays.numpy(), "loss": np.float32(loss.item()), "vol": vol.detach().numpy(),
+          "vgrad": vol.grad.numpy(), "poses": poses.numpy()}
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "coord", "attention", "weights"):
+            fx[f"{lvl}_{k}"] = o[lvl][k].detach().numpy()
+    for k, v in probes.items():
+        fx["probe_" + k] = v.numpy()
+    for k, v in params.items():
+        fx["param." + k] = v.numpy()
+    for k, p in ren.nerf_model.mlp_coarse.named_parameters():
+        fx["grad." + k] = p.grad.numpy()
+    for k, v in noise.items():
+        fx["noise_" + k] = v.numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **fx)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "loss", float(loss))
+
+
+def run_multiscale_case(name="small_multiscale", S=12, C=16, D=24, hidden=64, SB=2, n_rays=40, Kc=16, Kf=16, Kfd=2,
+                        H=16, W=16, focal=19.0, seed=8):
+    """use_multi_scale_voxel (models_embed.py:279-286: latent = [10-ch 12^3 | 8-ch 6^3 | main 16-ch 12^3] = 34 channels)
+    together with ret_last_feat (neural_rendering.py:285-293,332-334: the 64-d last residual stream is composited in
+    place of the embedding head) and 2 depth-guided samples; forward_nerf of the reference + a probe loss over its
+    outputs, gradients into all three volumes and the MLP."""
+    torch.manual_seed(seed)
+    ms_shapes = [(10, S), (8, S // 2)]
+    cfg = L.default_cfg(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H, n_coarse=Kc, n_fine=Kf,
+                        n_fine_depth=Kfd, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden), eval_batch_size=1024,
+                        use_multi_scale_voxel=True, d_multi_scale_latent=C + sum(c for c, _ in ms_shapes),
+                        ret_last_feat=True)
+    ren = L.build_reference_renderer(cfg, torch.tensor(syn.BOUNDS))
+    params = O.init_params(d_in=42, d_latent=cfg.d_multi_scale_latent, d_hidden=hidden, d_out=4 + D, seed=seed)
+    g = torch.Generator().manual_seed(77 + seed)
+    for k in params:
+        if k.endswith(".bias"):
+            params[k] = 0.05 * torch.randn(params[k].shape, generator=g)
+    load_params_into(ren, params)
+    vol = syn.make_volume(SB, C, S, seed=seed).requires_grad_(True)
+    ms = [(torch.randn(SB, c, s_, s_, s_, generator=g) * 0.1).requires_grad_(True) for c, s_ in ms_shapes]
+    poses = syn.arc_poses(SB)
+    focal_t = torch.tensor(focal, dtype=torch.float32)
+    idx = syn.pick_ray_indices(H * W, n_rays, seed=seed)
+    R = SB * n_rays
+    noise = syn.make_noise(R, Kc, Kf - Kfd, seed=seed)
+    noise["depth"] = torch.randn(R, Kfd, generator=g)
+    U = sys.modules["_nrf_reference_utils"]
+    rays = U.gen_rays(poses, W, H, focal_t, cfg.z_near, cfg.z_far, c=None).reshape(SB, H * W, 8)[:, idx]
+    ren.train()
+    ren.encode(ms, None, None, vol, poses, focal_t, None)
+    with L.inject_noise([noise["coarse"], noise["u"], noise["fine"], noise["depth"]]):
+        o = ren.forward_nerf(rays, want_weights=True)
+    gw = torch.Generator().manual_seed(900 + seed)
+    loss = 0.0
+    probes = {}
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth"):
+            t = o[lvl][k]
+            probes[f"{lvl}_{k}"] = torch.randn(t.shape, generator=gw)
+            loss = loss + (t * probes[f"{lvl}_{k}"]).sum()
+    loss.backward()
+    assert o["coarse"]["embed"].shape[-1] == hidden
+    fx = {"meta": np.array([S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed]), "focal": np.float32(focal),
+          "idx": idx.numpy(), "rays": rays.numpy(), "loss": np.float32(loss.item()), "vol": vol.detach().numpy(),
+          "vgrad": vol.grad.numpy(), "poses": poses.numpy(), "n_ms": np.int64(len(ms))}
+    for i, v in enumerate(ms):
+        fx[f"ms{i}"] = v.detach().numpy()
+        fx[f"ms{i}_grad"] = v.grad.numpy()
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "weights"):
+            fx[f"{lvl}_{k}"] = o[lvl][k].detach().numpy()
+    for k, v in probes.items():
+        fx["probe_" + k] = v.numpy()
+    for k, v in params.items():
+        fx["param." + k] = v.numpy()
+    for k, p in ren.nerf_model.mlp_coarse.named_parameters():
+        fx["grad." + k] = p.grad.numpy()
+    for k, v in noise.items():
+        fx["noise_" + k] = v.numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **fx)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "loss", float(loss))
+
+
 def run_raygen():
     L.load_reference()
     U = sys.modules["_nrf_reference_utils"]
@@ -183,7 +309,15 @@ def run_voxelizer():
 
 
 if __name__ == "__main__":
+    if "--heads-only" in sys.argv:
+        run_heads_case()
+        sys.exit(0)
+    if "--multiscale-only" in sys.argv:
+        run_multiscale_case()
+        sys.exit(0)
     run_raygen()
+    run_heads_case()
+    run_multiscale_case()
     run_voxelizer()
     run_case("small_kfd0", S=12, C=16, D=24, hidden=64, SB=2, n_rays=48, Kc=16, Kf=16, Kfd=0,
              H=16, W=16, focal=19.0, store_inputs=True)

@@ -638,9 +638,10 @@ def test_weights_written_through_data_are_seen_by_the_next_step(ops, NR):
     w = ren.nerf_model.mlp_coarse.lin_out.weight
     v0 = w._version
     w.data[4:].mul_(0.5)                                      # the embed rows only: rgb / density stay as they were
+    ren.nerf_model.mlp_coarse.lin_out.bias.data[4:].mul_(0.5)
     assert w._version == v0                                   # invisible to a version-keyed cache
     out1, _, _, _ = _run_cuda(ren, inp["vol"], inp["rays"], inp["noise"], inp["gt_rgb"], inp["gt_embed"])
-    # raw embed outputs are linear in those rows (bias 0) and a power of two commutes with every rounding on the way
+    # raw embed outputs are linear in those rows and a power of two commutes with every rounding on the way
     assert torch.equal(out1.coarse.rgb, out0.coarse.rgb)
     assert rel(out1.coarse.embed, 0.5 * out0.coarse.embed) < 1e-6
     assert rel(out1.coarse.embed, out0.coarse.embed) > 0.3
@@ -692,3 +693,171 @@ def test_channels_last_3d_volume_is_taken_without_relayout(ops, NR):
     for l in ("coarse", "fine"):
         for k in ("rgb", "embed", "depth"):
             assert torch.equal(res[0][0][l][k], res[1][0][l][k])
+
+
+def test_depth_loss_branch_matches_the_oracle(ops, NR):
+    """gt_depth given (neural_rendering.py:684-692): masked depth MSE of both passes, lambda_depth > 0, through forward()
+    with the ray subsample mocked to the fixture's indices; loss terms and gradients against the oracle."""
+    fx = golden("small_kfd0")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
+    ren = make_renderer(NR, meta, ci["params"], "fp32", lambda_depth=0.5)
+    idx = T(fx["idx"])
+    g = torch.Generator().manual_seed(3)
+    gt_depth = 1.2 + 3.2 * torch.rand(SB, H, W, generator=g)            # some pixels beyond z_far = 4.0: masked out
+    gt_rgb, gt_emb = T(fx["gt_rgb_img"]), T(fx["gt_embed_img"])
+    noise = ci["noise"]
+    # oracle
+    pr = {k: v.clone().requires_grad_(True) for k, v in ci["params"].items()}
+    vr = T(fx["vol"]).clone().requires_grad_(True)
+    ref = O.forward_nerf(pr, vr, T(fx["rays"]), syn.BOUNDS, Kc, Kf, Kfd, noise=noise)
+    L = O.rendering_loss(ref, gt_rgb.reshape(SB, -1, 3)[:, idx], gt_emb.reshape(SB, -1, D)[:, idx],
+                         gt_depth.reshape(SB, -1)[:, idx], lambda_depth=0.5)
+    L["loss"].backward()
+    # CUDA path through the public forward(): same ray indices and the same noise
+    vol = T(fx["vol"]).cuda().requires_grad_(True)
+    poses = T(fx["poses"]).cuda() if "poses" in fx.files else syn.arc_poses(SB).cuda()
+    with mock.patch.object(torch, "randint", lambda *a, **k: idx.cuda()), \
+            mock.patch.object(ren, "_draw_noise", lambda R, dev: {k: v.cuda() for k, v in noise.items()}):
+        out = ren(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=vol, voxel_poses=poses,
+                  focal=torch.tensor(float(fx["focal"])).cuda(), gt_rgb=gt_rgb.cuda(), gt_depth=gt_depth.cuda(),
+                  gt_pose=poses, c=None, lang_goal=None, gt_embed=gt_emb.cuda())
+    out["loss"].backward()
+    assert abs(float(out["loss"]) - float(L["loss"])) < 1e-5 * max(1.0, abs(float(L["loss"])))
+    assert abs(out["loss_depth_coarse"] - float(L["loss_depth_coarse"])) < 1e-5
+    assert abs(out["loss_depth_fine"] - float(L["loss_depth_fine"])) < 1e-5
+    assert out["loss_depth"] > 0.0
+    assert rel(vol.grad, vr.grad) < 3e-4
+    for k, v in pr.items():
+        assert rel(ren.state_dict(keep_vars=True)["nerf_model.mlp_coarse." + k].grad, v.grad) < 1e-3, k
+
+
+def test_target_features_are_extracted_and_reduced_on_the_device(ops, NR):
+    """gt_embed=None: the target feature map comes from `feature_extractor` and is reduced to d_embed channels by PCA
+    (neural_rendering.py:631-650); here the PCA runs on the GPU - same loss as handing over the reduced map."""
+    U = load_pkg("utils")
+    fx = golden("small_kfd0")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(SB, 3 * D, H, W, generator=g).cuda()             # what a foundation model would return
+    ren = make_renderer(NR, meta, ci["params"], "fp32")
+    ren.feature_extractor = lambda rgb, lang: feat
+    reduced = U.pca_fit_transform(feat.permute(0, 2, 3, 1).reshape(-1, 3 * D), D).reshape(SB, H, W, D)
+    vol = T(fx["vol"]).cuda()
+    poses = syn.arc_poses(SB).cuda()
+    kw = dict(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=vol, voxel_poses=poses,
+              focal=torch.tensor(float(fx["focal"])).cuda(), gt_rgb=T(fx["gt_rgb_img"]).cuda(), gt_depth=None,
+              gt_pose=poses, c=None, lang_goal=None)
+    torch.manual_seed(11)
+    a = ren(gt_embed=None, **kw)
+    torch.manual_seed(11)
+    b = ren(gt_embed=reduced, **kw)
+    assert abs(a["loss_embed"] - b["loss_embed"]) < 1e-6 * max(1.0, abs(b["loss_embed"]))
+    assert float(a["loss"]) == pytest.approx(float(b["loss"]), rel=1e-6)
+
+
+def test_coord_and_attention_heads_on_the_fused_path(ops, NR):
+    """The heads at the BASELINE dims (d_out = 4 + 384 + 3 + 6 = 397: lin_out runs 4 chunks, rows padded to 400 floats)
+    through the fused tcgen05 kernels, bf16 and fp16, against this repo's fp32 mode (itself held to the reference's
+    outputs by the next test)."""
+    S, C, D, hidden, SB, n_rays, Kc, Kf = 16, 128, 384, 512, 2, 48, 64, 64
+    meta = [S, C, D, hidden, SB, n_rays, Kc, Kf, 0, 64, 64, 3]
+    params = O.init_params(d_in=42, d_latent=C, d_hidden=hidden, d_out=4 + D + 9, seed=3)
+    vol = syn.make_volume(SB, C, S, seed=3)
+    rays = O.gen_rays(syn.arc_poses(SB), 64, 64, torch.tensor(76.5), 1.2, 4.0).reshape(SB, -1, 8)
+    rays = rays[:, syn.pick_ray_indices(64 * 64, n_rays, seed=3)]
+    noise = {k: v.cuda() for k, v in syn.make_noise(SB * n_rays, Kc, Kf, seed=3).items()}
+    res = {}
+    for precision in ("fp32", "bf16", "fp16"):
+        ren = make_renderer(NR, meta, params, precision, regress_coord=True, regress_attention=True)
+        if precision != "fp32":
+            assert ren.nerf_model.mlp_coarse.handle(ops.PRECISIONS[precision]).fused
+        v = vol.clone().cuda().requires_grad_(True)
+        ren.encode(None, None, None, v, None, None, None)
+        out = ren.forward_nerf(rays.cuda(), noise=noise)
+        sum(out[l][k].square().sum() for l in ("coarse", "fine") for k in ("rgb", "embed", "coord", "attention")).backward()
+        res[precision] = (out, v.grad)
+    for precision, tol in (("bf16", 3e-2), ("fp16", 5e-3)):
+        for k in ("rgb", "embed", "coord", "attention", "depth"):
+            e = rel(res[precision][0].coarse[k], res["fp32"][0].coarse[k])
+            assert e < tol, (precision, k, e)
+        assert cosine(res[precision][1], res["fp32"][1]) > 0.98
+
+
+@pytest.mark.parametrize("precision", ["fp32"])
+def test_coord_and_attention_heads_match_the_reference(ops, NR, precision):
+    """regress_coord + regress_attention: 4 + D + 3 + 6 = 37 outputs (rows padded to 40 floats), the
+    attention head alpha-composited with the embedding, the coordinate head averaged over the samples as the residual
+    to the canonical point; outputs and the gradients of a probe loss over ALL outputs against the reference's."""
+    fx = golden("small_heads")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    ren = make_renderer(NR, meta, ci["params"], precision, regress_coord=True, regress_attention=True)
+    assert ren.nerf_model.d_out == 37
+    vol = T(fx["vol"]).cuda().requires_grad_(True)
+    ren.encode(None, None, None, vol, None, None, None)
+    out = ren.forward_nerf(T(fx["rays"]).cuda(), want_weights=True, noise={k: v.cuda() for k, v in ci["noise"].items()})
+    tol = 1e-4 if precision == "fp32" else 5e-2
+    loss = 0.0
+    for lvl in ("coarse", "fine"):
+        assert set(out[lvl].keys()) >= {"rgb", "embed", "depth", "weights", "coord", "attention"}
+        for k in ("rgb", "embed", "depth", "coord", "attention"):
+            assert out[lvl][k].shape == T(fx[f"{lvl}_{k}"]).shape, (lvl, k)
+            assert rel(out[lvl][k], T(fx[f"{lvl}_{k}"])) < tol, (lvl, k, rel(out[lvl][k], T(fx[f"{lvl}_{k}"])))
+            loss = loss + (out[lvl][k] * T(fx[f"probe_{lvl}_{k}"]).cuda()).sum()
+    loss.backward()
+    if precision == "fp32":
+        assert abs(float(loss) - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+        assert rel(vol.grad, T(fx["vgrad"])) < 3e-4
+        for k, p in ren.nerf_model.mlp_coarse.named_parameters():
+            assert rel(p.grad, T(fx["grad." + k])) < 1e-3, k
+        # the field at explicit points carries the heads as well (models_embed.py:447-461)
+        pts = torch.rand(2, 50, 3, generator=torch.Generator().manual_seed(1)) * 0.8
+        dirs = torch.nn.functional.normalize(torch.randn(2, 50, 3, generator=torch.Generator().manual_seed(2)), dim=-1)
+        got, _ = ren.nerf_model(pts.cuda(), viewdirs=dirs.cuda(), precision="fp32")
+        ref = O.field(ci["params"], T(fx["vol"]), pts, dirs, syn.BOUNDS, regress_coord=True, regress_attention=True)
+        assert got.shape == ref.shape == (2, 50, 37) and rel(got, ref) < 1e-4
+    else:
+        assert cosine(vol.grad, T(fx["vgrad"])) > 0.98
+
+
+def test_multiscale_voxels_and_last_feat_match_the_reference(ops, NR):
+    """use_multi_scale_voxel (latent = gathers from three volumes of 10 / 8 / 16 channels at two resolutions: 34
+    channels) + ret_last_feat (the MLP's last residual stream composited in place of the embedding) + depth-guided
+    samples, through composed.py: outputs and the gradients into every volume and the MLP against the reference."""
+    fx = golden("small_multiscale")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    ren = make_renderer(NR, meta, ci["params"], "bf16", use_multi_scale_voxel=True, d_multi_scale_latent=34,
+                        ret_last_feat=True)                   # the composed branch runs its MLP in fp32 regardless
+    assert ren._composed and ren.nerf_model.d_latent == 34
+    vol = T(fx["vol"]).cuda().requires_grad_(True)
+    ms = [T(fx[f"ms{i}"]).cuda().requires_grad_(True) for i in range(int(fx["n_ms"]))]
+    ren.encode(ms, None, None, vol, None, None, None)
+    out = ren.forward_nerf(T(fx["rays"]).cuda(), want_weights=True, noise={k: v.cuda() for k, v in ci["noise"].items()})
+    loss = 0.0
+    for lvl in ("coarse", "fine"):
+        assert out[lvl].embed.shape[-1] == ci["hidden"]
+        for k in ("rgb", "embed", "depth", "weights"):
+            e = rel(out[lvl][k], T(fx[f"{lvl}_{k}"]))
+            assert e < 1e-4, (lvl, k, e)
+        for k in ("rgb", "embed", "depth"):
+            loss = loss + (out[lvl][k] * T(fx[f"probe_{lvl}_{k}"]).cuda()).sum()
+    assert abs(float(loss) - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+    loss.backward()
+    assert rel(vol.grad, T(fx["vgrad"])) < 3e-4
+    for i, v in enumerate(ms):
+        assert rel(v.grad, T(fx[f"ms{i}_grad"])) < 3e-4, i
+    for k, p in ren.nerf_model.mlp_coarse.named_parameters():
+        assert rel(p.grad, T(fx["grad." + k])) < 1e-3, k
+    # the field at explicit points: (output, last_feat, point_density) (models_embed.py:468-471)
+    pts = torch.rand(2, 30, 3, generator=torch.Generator().manual_seed(1)) * 0.8
+    dirs = torch.nn.functional.normalize(torch.randn(2, 30, 3, generator=torch.Generator().manual_seed(2)), dim=-1)
+    with torch.no_grad():
+        got, last, dens = ren.nerf_model(pts.cuda(), viewdirs=dirs.cuda(), ret_last_feat=True)
+        ref, ref_last = O.field(ci["params"], T(fx["vol"]), pts, dirs, syn.BOUNDS, ret_last_feat=True,
+                                multi_scale_voxel_list=[T(fx[f"ms{i}"]) for i in range(int(fx["n_ms"]))])
+    assert dens is None and rel(got, ref) < 1e-4 and rel(last, ref_last) < 1e-4

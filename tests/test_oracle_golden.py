@@ -159,3 +159,47 @@ def test_voxelizer_oracle_matches_the_reference_bitwise():
     assert out.shape == ref.shape == (B, S, S, S, 3 + F + 4)
     assert torch.equal(out, ref)
     assert int(ref[..., -1].sum()) > 100                       # the case is not degenerate
+
+
+def test_oracle_heads_match_reference():
+    """regress_coord + regress_attention (models_embed.py:447-461, neural_rendering.py:318-329,353-357) against the
+    reference's own outputs and the gradients of the probe loss over all of them (small_heads.npz)."""
+    fx = golden("small_heads")
+    ci = _case_inputs(fx)
+    pr = {k: v.clone().requires_grad_(True) for k, v in ci["params"].items()}
+    vol = T(fx["vol"]).clone().requires_grad_(True)
+    out = O.forward_nerf(pr, vol, T(fx["rays"]), syn.BOUNDS, ci["Kc"], ci["Kf"], noise=ci["noise"],
+                         eval_batch_size=1024, regress_coord=True, regress_attention=True)
+    loss = 0.0
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "coord", "attention"):
+            assert _rel(out[lvl][k], T(fx[f"{lvl}_{k}"])) < 2e-6, (lvl, k)
+            loss = loss + (out[lvl][k] * T(fx[f"probe_{lvl}_{k}"])).sum()
+    assert abs(float(loss) - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+    loss.backward()
+    assert _rel(vol.grad, T(fx["vgrad"])) < 1e-5
+    for k, v in pr.items():
+        assert _rel(v.grad, T(fx["grad." + k])) < 1e-4, k
+
+
+def test_oracle_multiscale_and_last_feat_match_reference():
+    """use_multi_scale_voxel + ret_last_feat + depth-guided samples against the reference (small_multiscale.npz)."""
+    fx = golden("small_multiscale")
+    ci = _case_inputs(fx)
+    pr = {k: v.clone().requires_grad_(True) for k, v in ci["params"].items()}
+    vol = T(fx["vol"]).clone().requires_grad_(True)
+    ms = [T(fx[f"ms{i}"]).clone().requires_grad_(True) for i in range(int(fx["n_ms"]))]
+    out = O.forward_nerf(pr, vol, T(fx["rays"]), syn.BOUNDS, ci["Kc"], ci["Kf"], ci["Kfd"], noise=ci["noise"],
+                         eval_batch_size=1024, multi_scale_voxel_list=ms, ret_last_feat=True)
+    loss = 0.0
+    for lvl in ("coarse", "fine"):
+        assert out[lvl]["embed"].shape[-1] == ci["hidden"]
+        for k in ("rgb", "embed", "depth"):
+            assert _rel(out[lvl][k], T(fx[f"{lvl}_{k}"])) < 2e-6, (lvl, k)
+            loss = loss + (out[lvl][k] * T(fx[f"probe_{lvl}_{k}"])).sum()
+    loss.backward()
+    assert _rel(vol.grad, T(fx["vgrad"])) < 1e-5
+    for i, v in enumerate(ms):
+        assert _rel(v.grad, T(fx[f"ms{i}_grad"])) < 1e-5, i
+    for k, v in pr.items():
+        assert _rel(v.grad, T(fx["grad." + k])) < 1e-4, k

@@ -124,9 +124,13 @@ def test_renderer_keeps_reference_surface():
     for name in ("forward", "rendering", "encode", "forward_nerf", "sample_coarse", "sample_fine",
                  "sample_fine_depth", "composite", "compute_rendering_loss"):
         assert callable(getattr(ren, name))
-    for key, bad in (("use_multi_scale_voxel", True), ("regress_coord", True), ("ret_last_feat", True)):
-        with pytest.raises(NotImplementedError):
-            NR.NeuralRenderer(U.default_config(**{key: bad}), torch.zeros(6))
+    with pytest.raises(NotImplementedError):      # the reference cannot run it either (models_embed.py:151-154,:289)
+        NR.NeuralRenderer(U.default_config(use_depth_supervision=True), torch.zeros(6))
+    ms = NR.NeuralRenderer(U.default_config(use_multi_scale_voxel=True, ret_last_feat=True), torch.zeros(6))
+    assert ms._composed and ms.nerf_model.d_latent == 266 and ms.nerf_model.mlp_coarse.lin_z[0].weight.shape == (512, 266)
+    heads = NR.NeuralRenderer(U.default_config(regress_coord=True, regress_attention=True), torch.zeros(6))
+    assert heads.nerf_model.d_out == 4 + 384 + 3 + 6 and heads._d_comp == 396          # models_embed.py:96-103
+    assert heads.nerf_model.mlp_coarse.lin_out.weight.shape == (397, 512)
     with pytest.raises(NotImplementedError):
         NR.NeuralRenderer(U.default_config(foundation_model_name="nope"), torch.zeros(6))
     with pytest.raises(Exception):                # CPU tensors are rejected: there is no CPU fallback
