@@ -57,11 +57,19 @@ constexpr int kFSmemBar = 320;
 constexpr int kFMaxIn = 7;                   // k-panels of the first layer's global A operand (they live in P)
 constexpr int kFSmemBias = 8 * 256;          // per epilogue warp: the 64 bias values of its current chunk
 constexpr int kFAlignSlack = 704;            // dynamic shared memory starts 1024-aligned in practice (checked)
+#ifndef NRF_FUSED_INFER_STAGES
+#define NRF_FUSED_INFER_STAGES 6
+#endif
+#ifdef NRF_FUSED_DIRECT_SAVE          // A/B experiment: the saved copies of relu(x') leave with st.global from registers
+constexpr bool kDirectSave = true;
+#else
+constexpr bool kDirectSave = false;
+#endif
 template <bool kSave>
 struct FCfg {
-  static constexpr int kStages = kSave ? 4 : 6;      // saving gives 32 KB up for the staging slots
+  static constexpr int kStages = kSave ? (kDirectSave ? 6 : 4) : NRF_FUSED_INFER_STAGES;   // saving gives 32 KB up for the staging slots
   static constexpr int kRing = kStages * kFStageB;
-  static constexpr int kStaging = kSave ? 8 * kFSlot : 0;
+  static constexpr int kStaging = kSave && !kDirectSave ? 8 * kFSlot : 0;
   static constexpr int kSmem = kFSmemP + kRing + kStaging + kFSmemBar + kFSmemBias + kFAlignSlack;
   static_assert(kSmem <= 232448, "fused MLP kernel exceeds the 227 KB shared-memory limit");
 };
@@ -87,6 +95,7 @@ struct FArgs {
                 // profile buffer set): 1 no weight TMA, 2 epilogue protocol only, 4 no MMAs, 8 MMA issuer ignores
                 // acc_empty / a_ready
   float* out;
+  uint32_t* saves;                 // kDirectSave: base of the (slots, N, 512) saved-operand tensor
   uint2* gate_bits;                // slots x (N, 8) x 64 bits: bit-packed ReLU gates, written by the training forward
                                    // (one bit per saved operand element: non-zero) and read by the backward
   long long* prof;                 // NRF_FUSED_PROF=1: per-CTA cycle counters of the warp roles (see mlp_fused_launch)
@@ -379,7 +388,25 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
       if (e.lane == 0) mbar_arrive_leader_u32(e.a_ready + (2 * c + e.g) * 8);
     }
     // 2. the copies kept for the other pass: operand values by TMA store, ReLU gates bit-packed
-    if (save) {
+    if (save && kDirectSave && (KIND == kLayerX || kHalf)) {
+      if (row0 + e.row < a.N) {
+        uint4* dst = reinterpret_cast<uint4*>(a.saves + (((int64_t)L.act_slot * a.N + row0 + e.row) * 512 + col0) / 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = kHalf ? make_uint4(f16x2_to_bf16x2(w[4 * j]), f16x2_to_bf16x2(w[4 * j + 1]),
+                                      f16x2_to_bf16x2(w[4 * j + 2]), f16x2_to_bf16x2(w[4 * j + 3]))
+                         : make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      }
+      if (!kBwd && row0 + e.row < a.N) {
+        uint32_t g0 = 0u, g1 = 0u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          g0 = gate_push(g0, w[j]);
+          g1 = gate_push(g1, w[16 + j]);
+        }
+        a.gate_bits[((int64_t)L.act_slot * a.N + row0 + e.row) * 8 + c * 2 + e.g] = make_uint2(g0, g1);
+      }
+    } else if (save) {
       if (KIND == kLayerX || kHalf) {          // (kHalf: relu(net) is saved as bf16 too, so not from its fp16 P panel)
         if (e.lane == 0) bulk_wait_read0();    // the slot's previous TMA store (a whole chunk ago) has read it
         __syncwarp();
@@ -796,6 +823,7 @@ int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
   NRF_REQUIRE(n_prod == d.n_layers - 1, NRF_EINVAL, "mlp_fused: every layer but the last must feed the next");
   a.N = (int)d.N; a.d_out = d.d_out; a.ldo = d.ldo; a.out = d.out;
   a.gate_bits = reinterpret_cast<uint2*>(d.gate_bits);
+  a.saves = reinterpret_cast<uint32_t*>(d.saves);
   NRF_REQUIRE(!d.saves || d.gate_bits, NRF_EINVAL, "mlp_fused: saving needs the gate-bit buffer");
   { const char* e = getenv("NRF_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.prof = reinterpret_cast<long long*>(d.prof);

@@ -8,7 +8,8 @@ The reference's hot path is single-GPU; its ancestor shards the ray axis with nn
     slices) are data-parallel; the field MLP is replicated, so its gradients are summed with ONE all_reduce
     over a flat fp32 buffer (12.2 MB at the BASELINE dims), started inside the backward so that it runs
     under the volume-gradient scatter.  The volume gradient stays local when each rank owns whole scenes;
-    `allreduce_volume_grad` covers the case of one scene split over ranks.
+    one scene split over ranks (config 5) sums it with `sparse_allreduce_volume_grad` (touched voxel rows only) or the
+    dense `allreduce_volume_grad`.
 """
 from __future__ import annotations
 
@@ -92,6 +93,73 @@ def allreduce_volume_grad(grad: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
     return grad
+
+
+@torch.no_grad()
+def sparse_allreduce_volume_grad(grad: torch.Tensor, group=None) -> dict:
+    """Sum of a volume gradient across ranks by exchanging only the voxels a rank's rays touched (SURVEY 8e, config 5:
+    ONE scene whose rays are split over the GPUs).  grad: (SB,C,S0,S1,S2), contiguous or channels_last_3d, summed IN
+    PLACE; every rank ends with bit-identical values (the contributions are added in rank order on every rank).
+
+    A rank's rays touch a small part of the grid (the 200^3 x 128-channel gradient is 4.1 GB, the rows written by
+    16 384 / N rays a few hundred MB), so instead of a dense all-reduce each rank all-gathers (voxel index, C-vector)
+    rows: bytes on the wire = sum of the touched rows x (4 C + 8) instead of 2 (N-1)/N x the whole volume.
+    Costs one host synchronisation (the row counts size the exchange buffers).  Returns the exchange statistics."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return {"rows": 0, "bytes": 0}
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    SB, C = grad.shape[:2]
+    V = grad[0, 0].numel()
+    # per scene a 2-D view with the voxel axis `vdim`: (C, V) for a contiguous gradient, (V, C) for channels_last_3d; every
+    # gather / scatter below then moves along the unit-stride axis of the neighbouring (ascending) voxel indices
+    if grad.is_contiguous():
+        views, vdim = [grad[b].reshape(C, V) for b in range(SB)], 1
+    elif grad.is_contiguous(memory_format=torch.channels_last_3d):
+        views, vdim = [grad[b].permute(1, 2, 3, 0).reshape(V, C) for b in range(SB)], 0
+    else:
+        raise ValueError("sparse_allreduce_volume_grad: gradient must be contiguous or channels_last_3d")
+    assert all(v.data_ptr() == grad[b].data_ptr() for b, v in enumerate(views)), "expected views, got copies"
+    touched = torch.stack([(v != 0).any(1 - vdim) for v in views])               # (SB, V)
+    idx = touched.reshape(-1).nonzero().squeeze(1)                               # flat (scene * V + voxel), ascending
+    counts = torch.zeros(world, device=grad.device, dtype=torch.int64)
+    counts[rank] = idx.numel()
+    dist.all_reduce(counts, group=group)
+    counts = counts.tolist()                                                     # the one host sync
+    cap = max(max(counts), 1)
+    shape = (C, cap) if vdim == 1 else (cap, C)
+    my_rows = torch.zeros(shape, device=grad.device, dtype=grad.dtype)
+    my_idx = torch.zeros(cap, device=grad.device, dtype=torch.int64)
+    n = idx.numel()
+    my_idx[:n] = idx
+    bounds = torch.searchsorted(idx, torch.arange(SB + 1, device=idx.device) * V).tolist() if SB > 1 else [0, n]
+
+    def rows_of(buf, lo, hi):
+        return buf[:, lo:hi] if vdim == 1 else buf[lo:hi]
+    for b in range(SB):
+        lo, hi = bounds[b], bounds[b + 1]
+        if hi > lo:
+            rows_of(my_rows, lo, hi).copy_(views[b].index_select(vdim, idx[lo:hi] - b * V))
+    all_rows = [torch.empty_like(my_rows) for _ in range(world)]
+    all_idx = [torch.empty_like(my_idx) for _ in range(world)]
+    dist.all_gather(all_rows, my_rows, group=group)
+    dist.all_gather(all_idx, my_idx, group=group)
+    # own touched rows are cleared, then every rank's rows (own included) are added in rank order: identical bits on
+    # every rank; within one rank's list the voxel indices are unique, so index_add_ has no collisions
+    for b in range(SB):
+        lo, hi = bounds[b], bounds[b + 1]
+        if hi > lo:
+            views[b].index_fill_(vdim, idx[lo:hi] - b * V, 0.0)
+    for r in range(world):
+        k = counts[r]
+        if k == 0:
+            continue
+        i_r = all_idx[r][:k]
+        bnd = torch.searchsorted(i_r, torch.arange(SB + 1, device=i_r.device) * V).tolist() if SB > 1 else [0, k]
+        for b in range(SB):
+            lo, hi = bnd[b], bnd[b + 1]
+            if hi > lo:
+                views[b].index_add_(vdim, i_r[lo:hi] - b * V, rows_of(all_rows[r], lo, hi))
+    return {"rows": counts, "bytes": int(cap * world * (C * grad.element_size() + 8))}
 
 
 @torch.no_grad()

@@ -77,3 +77,71 @@ def test_overlapped_grad_allreduce_equals_the_separate_one():
     for p in procs:
         p.join(timeout=60)
     assert all(msg == "ok" for _, msg in results), results
+
+
+def _worker_split(rank, world, port, out):
+    """Config-5 partition: ONE scene, its rays split over the ranks; MLP gradients all-reduced, the volume gradient summed
+    by the sparse exchange of touched voxel rows.  Against the single-GPU gradient over ALL rays (computed on every rank)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        NR, U, syn, par = (load_pkg(m) for m in ("neural_rendering", "utils", "synthetic", "parallel"))
+        from oracle import nerf_oracle as O
+        S, n_rays, Kc, Kf, D = 24, 96, 64, 64, 384
+        cfg = U.default_config(voxel_shape=S, ray_chunk_size=n_rays, image_width=64, image_height=64)
+        vol0 = syn.make_volume(1, 128, S, seed=7).cuda()
+        rays = O.gen_rays(syn.arc_poses(1), 64, 64, torch.tensor(76.5), 1.2, 4.0).reshape(1, -1, 8)
+        rays = rays[:, syn.pick_ray_indices(64 * 64, n_rays, seed=7)].cuda()
+        noise = {k: v.cuda() for k, v in syn.make_noise(n_rays, Kc, Kf, seed=7).items()}
+        gt_rgb, gt_emb = (t.cuda() for t in syn.make_targets(1, n_rays, D))
+
+        def run(sl):
+            ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS), precision="fp32")
+            syn.init_mlp_(ren.nerf_model.mlp_coarse, seed=0)
+            ren = ren.cuda().train()
+            vol = vol0.clone().requires_grad_(True)
+            ren.encode(None, None, None, vol, None, None, None)
+            o = ren.forward_nerf(rays[:, sl], noise={k: v[sl] for k, v in noise.items()})
+            # sums (not means) so that the split losses add up to the full one
+            loss = sum(((o[l].rgb - gt_rgb[:, sl]) ** 2).sum() + 0.01 * ((o[l].embed - gt_emb[:, sl]) ** 2).sum()
+                       for l in ("coarse", "fine"))
+            loss.backward()
+            return ren, vol.grad
+        ren_full, vg_full = run(slice(0, n_rays))
+        lo, hi = par.shard_bounds(n_rays, world, rank)
+        ren, vg = run(slice(lo, hi))
+        dense = vg.clone()
+        par.allreduce_volume_grad(dense)
+        stats = par.sparse_allreduce_volume_grad(vg)
+        par.allreduce_mlp_grads(ren)
+        torch.cuda.synchronize()
+        rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+        assert torch.equal(vg, dense), "sparse exchange != dense all-reduce (2 ranks: a + b is order-free)"
+        assert rel(vg, vg_full) < 1e-5, rel(vg, vg_full)
+        for (k, p), (_, q) in zip(ren.named_parameters(), ren_full.named_parameters()):
+            assert rel(p.grad, q.grad) < 2e-4, (k, rel(p.grad, q.grad))
+        assert stats["bytes"] < vg.numel() * 4
+        both = [torch.empty_like(vg) for _ in range(world)]
+        dist.all_gather(both, vg)
+        assert torch.equal(both[0], both[1])
+        out.put((rank, "ok"))
+    except Exception:                                                   # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_one_scene_split_over_two_gpus_equals_the_single_gpu_gradient():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_split, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(msg == "ok" for _, msg in results), results

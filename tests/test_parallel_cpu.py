@@ -68,9 +68,31 @@ def _worker(rank, world, port, out):
         vol = torch.full((2, 3), float(rank + 1))
         par.allreduce_volume_grad(vol)
         assert torch.equal(vol, torch.full((2, 3), float(sum(range(1, world + 1)))))
+        # one scene's rays split over the ranks: the sparse exchange of touched voxel rows equals the dense sum, for a
+        # contiguous and a channels_last_3d gradient, with overlapping and disjoint footprints, and two scenes
+        for SB, fmt in ((1, torch.contiguous_format), (2, torch.channels_last_3d)):
+            g = torch.Generator().manual_seed(100 + rank)
+            C_, S_ = 8, 6
+            local = torch.zeros(SB, C_, S_, S_, S_)
+            hit = torch.randint(0, S_ ** 3, (40,), generator=g)
+            hit[:5] = torch.arange(5)                            # five voxels every rank touches
+            for b in range(SB):
+                local[b].reshape(C_, -1)[:, hit] = torch.randn(C_, 40, generator=g)
+            local = local.contiguous(memory_format=fmt)
+            dense = local.clone()
+            dist.all_reduce(dense)
+            sparse = local.clone()
+            stats = par.sparse_allreduce_volume_grad(sparse)
+            assert sparse.is_contiguous(memory_format=fmt)
+            assert torch.allclose(sparse, dense, atol=1e-6) and len(stats["rows"]) == world
+            assert stats["bytes"] < dense.numel() * 4
+            both = [torch.empty_like(sparse) for _ in range(world)]
+            dist.all_gather(both, sparse.contiguous())
+            assert torch.equal(both[0], both[1])                 # bit-identical replicas
         out.put((rank, "ok"))
     except Exception as e:                                        # pragma: no cover
-        out.put((rank, repr(e)))
+        import traceback
+        out.put((rank, traceback.format_exc()[-800:]))
     finally:
         dist.destroy_process_group()
 
