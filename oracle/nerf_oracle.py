@@ -398,3 +398,35 @@ def init_params(d_in=42, d_latent=128, d_hidden=512, d_out=388, n_blocks=5, comb
 
 def params_from_state_dict(sd, prefix="nerf_model.mlp_coarse.") -> Params:
     return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+# ------------------------------------------------------------------- extraction
+def extract_radience(p, voxel_feat, rays, z_samp, sb, bounds, **fkw):
+    """featurenerf_robo/featurenerf/src/render/nerf_embed.py:432-516: the field at every sample, not composited.
+    rays (R,8), z (R,K) -> points (sb, R'K, 3), rgbs (sb, R'K, 3), sigmas (sb, R'K), embeds (sb, R'K, D)."""
+    R, K = z_samp.shape
+    pts = (rays[:, None, :3] + z_samp.unsqueeze(2) * rays[:, None, 3:6]).reshape(sb, -1, 3)
+    dirs = rays[:, None, 3:6].expand(-1, K, -1).reshape(sb, -1, 3)
+    out = field(p, voxel_feat, pts, dirs, bounds, **fkw)
+    return pts, out[..., :3], out[..., 3], out[..., 4:]
+
+
+def point_cloud_masks(rgbs, sigmas, lower_bound=50000, upper_bound=70000, max_iters=1000):
+    """train_nerfact_multi_kitchen.py:985-1013: brighter-than-average AND sigma > step * max, `step` walked from 0.1 by
+    -0.01 / +0.02 until the survivor count is inside [lower_bound, upper_bound]."""
+    mask2 = rgbs.sum(-1) > rgbs.sum(-1).mean()
+    step, num, it = 0.1, 0, 0
+    mask1 = sigmas > sigmas.max() * step
+    while num < lower_bound or num > upper_bound:
+        mask1 = sigmas > (sigmas.max() * step)
+        num = int((mask1 & mask2).sum())
+        if num < lower_bound:
+            step -= 0.01
+        elif num > upper_bound:
+            step += 0.02
+        else:
+            break
+        it += 1
+        if it >= max_iters:
+            break
+    return mask1 & mask2, step

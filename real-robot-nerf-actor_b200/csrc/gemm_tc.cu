@@ -536,7 +536,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         } else if (n < n_valid) {
           float* dst = dW + (int64_t)n * ldw + k0;
-          if ((ldw & 3) == 0 && k0 + 32 <= k_valid) {      // 16 B aligned rows: vector reductions (red.global.add.v4.f32)
+          if ((ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0 && k0 + 32 <= k_valid) {
+            // 16 B aligned rows: vector reductions (red.global.add.v4.f32)
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               atomicAdd(reinterpret_cast<float4*>(dst + j),

@@ -631,12 +631,15 @@ def _zero_grads(mlp: ops.FieldMLP):
     names = mlp.names()
     sizes = [mlp.params[n].numel() for n in names]
     dev = mlp.params[names[0]].device
-    flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+    # every view starts on a 16 B boundary (the weight-gradient kernels add float4s): sizes that are not multiples of 4
+    # occur with the coord / attention heads (d_out = 397)
+    padded = [(sz + 3) // 4 * 4 for sz in sizes]
+    flat = torch.zeros(sum(padded), device=dev, dtype=torch.float32)
     out, off = _GradViews(), 0
     out.flat = flat
-    for n, sz in zip(names, sizes):
+    for n, sz, psz in zip(names, sizes, padded):
         out[n] = flat[off:off + sz].view_as(mlp.params[n])
-        off += sz
+        off += psz
     return out
 
 
@@ -1021,8 +1024,21 @@ class NeuralRenderer(nn.Module):
         out.append(dep)
         return tuple(out)
 
-    def forward_nerf(self, rays, want_weights=False, noise=None):
-        """neural_rendering.py:435-471.  rays (SB,B,8) -> AttrDict(coarse=..., fine=...)."""
+    def extract_radience(self, model, rays, z_samp, coarse=True, sb=0, ret_last_feat=False):
+        """The ancestor renderer's per-sample field values (nerf_embed.py:432-516): points, rgbs, sigmas, embeds."""
+        from . import extract
+        return extract.extract_radience(self, model, rays, z_samp, coarse, sb, ret_last_feat)
+
+    def forward_nerf(self, rays, want_weights=False, noise=None, extract_radience=False, ret_last_feat=False):
+        """neural_rendering.py:435-471.  rays (SB,B,8) -> AttrDict(coarse=..., fine=...).
+        extract_radience (the ancestor's switch, nerf_embed.py:338-342): run the coarse pass, draw the fine samples and
+        return the field values (points, rgbs, sigmas, embeds) at the sorted sample set instead of compositing them."""
+        if extract_radience:
+            with torch.no_grad():
+                out = self.forward_nerf(rays, want_weights=True, noise=noise)
+                z = out.fine.z if self.using_fine else out.coarse.z
+                return self.extract_radience(self.nerf_model, rays.reshape(-1, 8), z, coarse=not self.using_fine,
+                                             sb=rays.shape[0], ret_last_feat=ret_last_feat)
         assert len(rays.shape) == 3
         sb = rays.shape[0]
         vol = self.nerf_model.voxel_feat
@@ -1091,6 +1107,14 @@ class NeuralRenderer(nn.Module):
     def compute_rendering_loss(self, multi_scale_voxel_list, voxel_density, language, voxel_feat, voxel_poses,
                                focal, gt_rgb, gt_depth, gt_pose, c=None, lang_goal=None, gt_embed=None):
         """neural_rendering.py:595-707."""
+        loss, scalars = self._loss_tensors(multi_scale_voxel_list, voxel_density, language, voxel_feat, voxel_poses,
+                                           focal, gt_rgb, gt_depth, gt_pose, c, lang_goal, gt_embed)
+        return LossDict(loss, scalars)
+
+    def _loss_tensors(self, multi_scale_voxel_list, voxel_density, language, voxel_feat, voxel_poses,
+                      focal, gt_rgb, gt_depth, gt_pose, c=None, lang_goal=None, gt_embed=None):
+        """The body of compute_rendering_loss on device tensors only: -> (loss, the 7 scalars behind the float entries
+        of the loss dict).  No host interaction at all, so the whole step can be captured into a CUDA graph (graphed.py)."""
         rays = gen_rays(gt_pose, self.W, self.H, focal, self.z_near, self.z_far, c=c)
         self.encode(multi_scale_voxel_list=multi_scale_voxel_list, voxel_density=voxel_density, lang=language,
                     voxel_feat=voxel_feat, poses=voxel_poses, focal=focal, c=c)
@@ -1149,7 +1173,7 @@ class NeuralRenderer(nn.Module):
         scalars = torch.stack([v.detach().float().reshape(()) for v in
                                (loss_rgb_coarse, loss_rgb_fine, loss_embed_coarse, loss_embed_fine,
                                 loss_depth_coarse, loss_depth_fine, psnr_t)])
-        return LossDict(loss, scalars)
+        return loss, scalars
 
     def forward(self, multi_scale_voxel_list, voxel_density, language, voxel_feat, voxel_poses, focal, gt_rgb,
                 gt_depth, gt_pose, c=None, lang_goal=None, gt_embed=None):

@@ -861,3 +861,86 @@ def test_multiscale_voxels_and_last_feat_match_the_reference(ops, NR):
         ref, ref_last = O.field(ci["params"], T(fx["vol"]), pts, dirs, syn.BOUNDS, ret_last_feat=True,
                                 multi_scale_voxel_list=[T(fx[f"ms{i}"]) for i in range(int(fx["n_ms"]))])
     assert dens is None and rel(got, ref) < 1e-4 and rel(last, ref_last) < 1e-4
+
+
+def test_radiance_and_point_cloud_extraction(ops, NR):
+    """The ancestor's `extract_radience` switch (nerf_embed.py:338-342,432-516) and the point-cloud masks of
+    `extract_nerf_feat` (train_nerfact_multi_kitchen.py:985-1040): field values at the sorted coarse + fine samples
+    against the oracle, then the density / brightness selection on the same values."""
+    ext = load_pkg("extract")
+    fx = golden("small_kfd0")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
+    ren = make_renderer(NR, meta, ci["params"], "fp32").eval()
+    vol = T(fx["vol"])
+    ren.encode(None, None, None, vol.cuda(), None, None, None)
+    rays = T(fx["rays"])
+    noise = {k: v.cuda() for k, v in ci["noise"].items()}
+    pts, rgbs, sigmas, embeds = ren.forward_nerf(rays.cuda(), noise=noise, extract_radience=True)
+    assert pts.shape == (SB, n_rays * (Kc + Kf), 3) and embeds.shape == (SB, n_rays * (Kc + Kf), D)
+    with torch.no_grad():
+        ref = O.forward_nerf(ci["params"], vol, rays, syn.BOUNDS, Kc, Kf, noise=ci["noise"])
+        r_pts, r_rgb, r_sig, r_emb = O.extract_radience(ci["params"], vol, rays.reshape(-1, 8), ref["z_fine"], SB, syn.BOUNDS)
+    assert rel(pts, r_pts) < 1e-6 and rel(rgbs, r_rgb) < 1e-4 and rel(sigmas, r_sig) < 1e-4 and rel(embeds, r_emb) < 1e-4
+    # last-feature variant (ret_last_feat=True in the script, :962): (B, K, d_hidden)
+    _, _, _, last = ren.forward_nerf(rays.cuda(), noise=noise, extract_radience=True, ret_last_feat=True)
+    assert last.shape == (SB * n_rays, Kc + Kf, hidden)
+    # masks on identical inputs: same survivors, same step
+    lo, hi = 300, 600
+    mask_ref, step_ref = O.point_cloud_masks(r_rgb, r_sig, lo, hi)
+    w2b = torch.eye(4)
+    w2b[:3, 3] = torch.tensor([0.1, -0.2, 0.3])
+    p, c, e, step = ext.extract_point_cloud(r_pts.cuda(), r_rgb.cuda(), r_sig.cuda(), r_emb.cuda(), lo, hi, world_to_base=w2b)
+    assert step == pytest.approx(step_ref) and p.shape[0] == int(mask_ref.sum()) and lo <= p.shape[0] <= hi
+    assert torch.allclose(p.cpu(), r_pts[mask_ref] + w2b[:3, 3]) and torch.equal(c.cpu(), r_rgb[mask_ref])
+    assert torch.equal(e.cpu(), r_emb[mask_ref])
+
+
+def test_training_script_call_sites_run_unchanged(ops, NR):
+    """The call sites of train_nerfact_multi_kitchen.py, with the script's own keywords and nerfact.conf's shapes
+    (:1100-1103 60 x 80 images, focal 76.18; nerfact.conf:22-28,:74-76 d_embed 512, d_latent 64, 64 + 64 samples of which
+    16 depth-guided, 512-ray chunks): NeuralRenderer(conf['neural_renderer'], coordinate_bounds=bounds).to(device)
+    (:1248), the voxelizer feeding a 3-D encoder (:1336-1340), neural_renderer(voxel_feat=..., gt_embed=None, ...)
+    (:1390-1397) with the loss dict read the way the script reads it (:1407-1412), total_loss.backward() through the
+    encoder, an optimizer step, and neural_renderer.rendering(...) (:1417-1422)."""
+    U, VG = load_pkg("utils"), load_pkg("voxel_grid")
+    dev = torch.device("cuda")
+    H, W, S = 60, 80, 20
+    bounds = torch.tensor(syn.BOUNDS)
+    conf = U.default_config(image_width=W, image_height=H, d_embed=512, d_latent=64, voxel_shape=S, n_fine_depth=16,
+                            ray_chunk_size=512)
+    feats = torch.randn(1, 512, 15, 20, generator=torch.Generator().manual_seed(0)).to(dev)
+    neural_renderer = NR.NeuralRenderer(conf, coordinate_bounds=bounds, feature_extractor=lambda rgb, lang: feats).to(dev)
+    syn.init_mlp_(neural_renderer.nerf_model.mlp_coarse, seed=0)
+    voxelizer = VG.VoxelGrid(coord_bounds=syn.BOUNDS, voxel_size=S, device=dev, batch_size=1, feature_size=3,
+                             max_num_coords=5000)
+    qnet = torch.nn.Conv3d(10, 64, 3, padding=1).to(dev)                  # stand-in for the PerceiverIO encoder
+    optimizer = torch.optim.Adam(list(qnet.parameters()) + list(neural_renderer.parameters()), lr=1e-4)
+    coords, rgb = syn.voxelizer_points(1, 5000, 3, seed=2)
+    gt_pose = syn.arc_poses(1).to(dev)
+    focal = torch.tensor(76.18187).to(dev)
+    gt_rgb = torch.rand(1, H, W, 3, device=dev)
+    losses = []
+    for it in range(3):
+        voxel_grid = voxelizer.coords_to_bounding_voxel_grid(coords.to(dev), coord_features=rgb.to(dev), coord_bounds=bounds.to(dev))
+        voxel_grid = voxel_grid.permute(0, 4, 1, 2, 3).detach().to(dev)
+        voxel_grid_feature = qnet(voxel_grid)
+        total_loss = voxel_grid_feature.square().mean()                   # stand-in for the BC losses
+        rendering_loss_dict = neural_renderer(voxel_feat=voxel_grid_feature, language=None, multi_scale_voxel_list=None,
+                                              voxel_density=None, voxel_poses=gt_pose, gt_depth=None, focal=focal, c=None,
+                                              gt_rgb=gt_rgb, gt_pose=gt_pose, lang_goal="open the drawer", gt_embed=None)
+        total_loss = 1.0 * total_loss + 10.0 * rendering_loss_dict["loss"]
+        optimizer.zero_grad()
+        total_loss.backward()
+        optimizer.step()
+        items = [rendering_loss_dict[k] for k in ("loss_rgb", "loss_embed", "loss_depth", "psnr")]
+        assert all(isinstance(v, float) and v == v for v in items)
+        assert qnet.weight.grad is not None and torch.isfinite(qnet.weight.grad).all() and float(qnet.weight.grad.abs().sum()) > 0
+        losses.append(float(total_loss))
+    assert all(l == l for l in losses)
+    rgb_render, embed_render, depth = neural_renderer.rendering(voxel_feat=voxel_grid_feature.detach(), language=None,
+                                                                multi_scale_voxel_list=None, voxel_density=None,
+                                                                voxel_pose=None, tgt_pose=gt_pose, focal=focal, c=None)
+    assert rgb_render.shape == (1, H, W, 3) and embed_render.shape == (1, H, W, 512) and depth.shape == (1, H, W)
+    assert torch.isfinite(rgb_render).all() and float(rgb_render.min()) >= 0.0 and float(rgb_render.max()) <= 1.0
