@@ -90,7 +90,10 @@ int nrf_volume_to_channels_first(const float* src, float* dst, int SB, int C, in
  * Replaces neural_rendering.py:246-283 (points, viewdirs), models_embed.py:185-203
  * (world_to_canonical), :259-277 (grid_sample), utils.py:545-557 (PositionalEncoding) and the
  * concatenations at models_embed.py:366,405.  vol_cl is channels-last.  bounds = 6 floats (HOST).
- * out: (N, ld_out) fp32 (out_bf16 == 0), bf16 (1) or fp16 (2); columns >= C+42 are zero-filled up to ld_out.
+ * out: (N, ld_out) fp32 (out_bf16 & 0xff == 0), bf16 (1) or fp16 (2); columns >= C+42 are zero-filled up to ld_out.
+ * out_bf16 | 0x100: the eight corners are accumulated with FMAs, which is what ATen's CUDA grid_sampler_3d compiles to
+ * (bit-identical to the reference run on a GPU); default: separately rounded multiply and add, ATen's CPU kernel
+ * (bit-identical to the reference run on the CPU, which is what the golden fixtures were produced by).
  * rays_per_scene = R / SB. points_out (N,3) fp32 optional (debug / parity), may be NULL. */
 int nrf_encode_points(const float* rays, const float* z, int R, int K, int rays_per_scene,
                       const float* vol_cl, int SB, int C, int S0, int S1, int S2,

@@ -91,7 +91,23 @@ struct EncodeArgs {
   void* out;
   int ld_out;
   float* points;
+  int fma;          // corner accumulation out = fma(v, w, out) (ATen's CUDA grid_sampler_3d) instead of the separately
+                    // rounded multiply and add of ATen's CPU kernel (the default)
 };
+
+// One trilinear corner: out += v * w in ATen's rounding.  The CPU kernel rounds the product and the sum separately;
+// nvcc contracts the same source line of the CUDA kernel into an FMA.  Measured on B200 (tests/test_gpu_bench_sizes.py):
+// the default is bit-identical to CPU ATen, the FMA form to CUDA-eager ATen.
+__device__ __forceinline__ float4 corner_acc(float4 acc, float4 v, float w, int fma) {
+  if (fma) {
+    acc.x = __fmaf_rn(v.x, w, acc.x); acc.y = __fmaf_rn(v.y, w, acc.y);
+    acc.z = __fmaf_rn(v.z, w, acc.z); acc.w = __fmaf_rn(v.w, w, acc.w);
+  } else {
+    acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, w)); acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, w));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, w)); acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, w));
+  }
+  return acc;
+}
 
 template <typename T> __device__ __forceinline__ T to_out(float v);
 template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
@@ -152,10 +168,7 @@ __global__ void __launch_bounds__(256) encode_points_kernel(EncodeArgs a) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         if (c8.off[k] >= 0) {
-          acc.x = __fadd_rn(acc.x, __fmul_rn(v[k].x, c8.w[k]));
-          acc.y = __fadd_rn(acc.y, __fmul_rn(v[k].y, c8.w[k]));
-          acc.z = __fadd_rn(acc.z, __fmul_rn(v[k].z, c8.w[k]));
-          acc.w = __fadd_rn(acc.w, __fmul_rn(v[k].w, c8.w[k]));
+          acc = corner_acc(acc, v[k], c8.w[k], a.fma);
         }
       }
       store4<T>(row + c0, acc);
@@ -300,10 +313,7 @@ __global__ void __launch_bounds__(256) encode_points_w32_kernel(EncodeArgs a) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           if (c8.off[k] >= 0) {
-            acc.x = __fadd_rn(acc.x, __fmul_rn(v[k].x, c8.w[k]));
-            acc.y = __fadd_rn(acc.y, __fmul_rn(v[k].y, c8.w[k]));
-            acc.z = __fadd_rn(acc.z, __fmul_rn(v[k].z, c8.w[k]));
-            acc.w = __fadd_rn(acc.w, __fmul_rn(v[k].w, c8.w[k]));
+            acc = corner_acc(acc, v[k], c8.w[k], a.fma);
           }
         }
         store4<T>(row + c0, acc);
@@ -417,6 +427,8 @@ extern "C" int nrf_encode_points(const float* rays, const float* z, int R, int K
   fill_bounds(bounds_host, a.bmin, a.bext);
   a.num_freqs = num_freqs; a.freq_factor = freq_factor;
   a.out = out; a.ld_out = ld_out; a.points = points_out;
+  a.fma = (out_bf16 >> 8) & 1;
+  out_bf16 &= 0xff;
   int64_t N = (int64_t)R * K;
   int threads = 256;
   const bool w32 = num_freqs == kTailFreqs && ld_out == C + kTailW &&
@@ -669,20 +681,37 @@ __device__ __forceinline__ void voxel_sum(const int32_t* __restrict__ lst, const
     }
     return;
   }
-  int32_t last = -1;
-  for (int step = 0; step < cnt; ++step) {
-    int32_t best = 0x7fffffff; float wb = 0.f;
-    for (int i = lane; i < cnt; i += kWarp) {
-      int32_t e = lst[i];
-      if (e > last && e < best) { best = e; wb = wl[i]; }
+  // more than a warp's worth of entries in one voxel (coarse grids under many samples; degenerate inputs): the voxel's
+  // segment of the entry / weight lists belongs to this warp alone, so it is sorted IN PLACE by a bitonic network whose
+  // comparators all point the same way (any length: the virtual padding behind `cnt` never moves) -
+  // O(cnt log^2 cnt / 32) steps instead of the cnt^2 / 32 of a selection loop - and then summed in order
+  int32_t* se = const_cast<int32_t*>(lst);
+  float* sw = const_cast<float*>(wl);
+  auto cmpxchg = [&](int i, int p) {
+    const int32_t a = se[i], b = se[p];
+    if (a > b) {
+      se[i] = b; se[p] = a;
+      const float wa = sw[i], wb = sw[p];
+      sw[i] = wb; sw[p] = wa;
     }
-    int32_t mine = best;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-    const int src = __ffs(__ballot_sync(0xffffffffu, mine == best)) - 1;
-    const float w = __shfl_sync(0xffffffffu, wb, src);
-    last = best;
-    const float* d = row_of(best);
+  };
+  for (int k = 2; (k >> 1) < cnt; k <<= 1) {
+    for (int i = lane; i < cnt; i += kWarp) {
+      const int p = i ^ (k - 1);
+      if (p > i && p < cnt) cmpxchg(i, p);
+    }
+    __syncwarp();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int i = lane; i < cnt; i += kWarp) {
+        const int p = i ^ j;
+        if (p > i && p < cnt) cmpxchg(i, p);
+      }
+      __syncwarp();
+    }
+  }
+  for (int k = 0; k < cnt; ++k) {
+    const float w = sw[k];
+    const float* d = row_of(se[k]);
 #pragma unroll
     for (int j = 0; j < CJ; ++j) acc[j] = fmaf(w, d[lane + j * kWarp], acc[j]);
   }

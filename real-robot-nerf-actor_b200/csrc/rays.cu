@@ -150,7 +150,12 @@ __global__ void sort_rows_kernel(float* __restrict__ z, int R, int K, int P, int
         bool up = ((lo & size) == 0);
         float a = key[lo], b = key[hi];
         int ia = idx[lo], ib = idx[hi];
-        bool gt = (a > b) || (a == b && ia > ib);
+        // a TOTAL order: NaN sorts last among the real entries (as torch.sort does) and the padding behind K stays
+        // behind every real entry - a NaN depth can no longer pull a padding slot (index >= K) into the first K
+        auto ord = [](float x) { int i = __float_as_int(x); return x != x ? 0x7fffffff : i ^ ((i >> 31) & 0x7fffffff); };
+        const int ka = ord(a), kb = ord(b);
+        const bool pa = ia >= K, pb = ib >= K;
+        bool gt = pa != pb ? pa : (ka > kb) || (ka == kb && ia > ib);
         if (gt == up) {
           key[lo] = b; key[hi] = a;
           idx[lo] = ib; idx[hi] = ia;

@@ -56,13 +56,38 @@ __global__ void __launch_bounds__(256) voxel_reduce_kernel(const float* __restri
 #pragma unroll
   for (int c = 0; c < kVoxMaxCh; ++c) acc[c] = 0.f;
   if (cnt > 0) {
-    const int32_t* lst = list + offset[t];
+    int32_t* lst = const_cast<int32_t*>(list) + offset[t];      // this voxel's own segment of the list
+    if (cnt > 16) {
+      // long lists (a cloud collapsed onto few voxels): heap sort of the segment in place, O(cnt log cnt), instead of
+      // the cnt^2 selection loop below (1e4 points in one voxel were 1e8 iterations of one thread)
+      auto sift = [&](int root, int end) {
+        const int32_t v = lst[root];
+        for (int child = 2 * root + 1; child < end; child = 2 * root + 1) {
+          if (child + 1 < end && lst[child + 1] > lst[child]) ++child;
+          if (lst[child] <= v) break;
+          lst[root] = lst[child];
+          root = child;
+        }
+        lst[root] = v;
+      };
+      for (int i = cnt / 2 - 1; i >= 0; --i) sift(i, cnt);
+      for (int end = cnt - 1; end > 0; --end) {
+        const int32_t top = lst[0];
+        lst[0] = lst[end];
+        lst[end] = top;
+        sift(0, end);
+      }
+    }
     int32_t last = -1;
-    for (int step = 0; step < cnt; ++step) {          // ascending point index (lists are short)
+    for (int step = 0; step < cnt; ++step) {          // ascending point index
       int32_t best = 0x7fffffff;
-      for (int i = 0; i < cnt; ++i) {
-        const int32_t e = lst[i];
-        if (e > last && e < best) best = e;
+      if (cnt > 16) {
+        best = lst[step];
+      } else {
+        for (int i = 0; i < cnt; ++i) {
+          const int32_t e = lst[i];
+          if (e > last && e < best) best = e;
+        }
       }
       last = best;
       const float* p = coords + (int64_t)best * 3;

@@ -77,7 +77,8 @@ def _device_intrinsics(focal, c, width, height, device):
     intr = torch.empty(4, device=device, dtype=torch.float32)
     intr[0:2] = f[0:2] if f.numel() >= 2 else f[0]
     if c is None:
-        intr[2], intr[3] = width * 0.5, height * 0.5
+        intr[2].fill_(width * 0.5)            # fill kernels, not host -> device copies (CUDA-graph capturable)
+        intr[3].fill_(height * 0.5)
     else:
         cc = torch.as_tensor(c, dtype=torch.float32, device=device).reshape(-1)
         intr[2:4] = cc[0:2] if cc.numel() >= 2 else cc[0]
@@ -196,9 +197,13 @@ def _bounds_host(bounds):
     return arr
 
 
+GATHER_FMA = False      # True: accumulate the trilinear corners with FMAs (ATen's CUDA grid_sampler_3d rounding, i.e.
+                        # bit-identical latents to the reference run on a GPU); default: ATen's CPU rounding
+
+
 @_on_tensor_device
 def encode_points(rays, z, rays_per_scene, vol_cl, bounds, num_freqs=6, freq_factor=1.5, ld_out=None,
-                  precision=NRF_PREC_BF16, want_points=False, out=None):
+                  precision=NRF_PREC_BF16, want_points=False, out=None, fma=None):
     """Field-input rows [latent | PE | viewdir | 0] for every sample (see nrf_encode_points)."""
     rays = _f32(rays, "rays")
     z = _f32(z, "z")
@@ -214,7 +219,8 @@ def encode_points(rays, z, rays_per_scene, vol_cl, bounds, num_freqs=6, freq_fac
     bh = _bounds_host(bounds)
     check(_lib.load().nrf_encode_points(ptr(rays), ptr(z), R, K, rays_per_scene, ptr(vol_cl), SB, Cc, S0, S1,
                                         S2, C.cast(bh, C.c_void_p), num_freqs, float(freq_factor), ptr(out),
-                                        ld_out, _OUT_KIND[out.dtype], ptr(pts), stream_ptr()),
+                                        ld_out, _OUT_KIND[out.dtype] | (0x100 if (GATHER_FMA if fma is None else fma) else 0),
+                                        ptr(pts), stream_ptr()),
           "nrf_encode_points")
     return (out, pts) if want_points else out
 

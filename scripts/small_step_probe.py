@@ -41,4 +41,24 @@ for reuse in (False, True):
         "kernel_ms_sum": round(sum(v[0] for v in kern.values()), 3),
         "kernel_ms": {k: [round(v[0], 3), v[1]] for k, v in kern.items() if v[1] > 0},
         "evals_per_step": SB * 512 * 192}
+# the same step captured into CUDA graphs (graphed.py): the host enqueues 2 graph launches instead of ~56 kernels + ~40 torch ops
+G = importlib.import_module(PKG + ".graphed")
+ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS))
+syn.init_mlp_(ren.nerf_model.mlp_coarse, seed=0)
+ren = ren.to(dev).train()
+vol = (torch.randn(SB, 64, 100, 100, 100, device=dev) * 0.1).requires_grad_(True)
+graphed = G.GraphedRenderLoss(ren, vol, poses, focal, gt_rgb, gt_emb)
+def gstep():
+    vol.grad = None
+    for p in ren.parameters(): p.grad = None
+    graphed(vol, poses, focal, gt_rgb, gt_emb)["loss"].backward()
+for _ in range(5): gstep()
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter(); a.record()
+for _ in range(50): gstep()
+b.record(); torch.cuda.synchronize()
+res["cuda graph (reference schedule)"] = {"ms_per_step": round(a.elapsed_time(b) / 50, 3),
+                                          "wall_ms_per_step": round((time.perf_counter() - t0) / 50 * 1e3, 3),
+                                          "evals_per_step": SB * 512 * 192}
 print(json.dumps({"nerfact.conf shape, SB=%d" % SB: res}))

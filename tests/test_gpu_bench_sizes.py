@@ -234,6 +234,10 @@ def test_stages_against_the_oracle_run_on_the_device(mods):
     report["grid_sample_latent_max_abs"] = float((field_in[:, :C] - lat_ref).abs().max())
     report["samples_inside_box"] = float(inside.float().mean())
     assert report["grid_sample_latent_max_abs"] <= 2e-7 and torch.equal(field_in[:, :C][~inside], lat_ref[~inside])
+    # the FMA form of the corner accumulation is what nvcc makes of ATen's CUDA kernel: bit-identical to CUDA-eager
+    field_fma = ops.encode_points(rays, z, R // 2, ops.volume_to_channels_last(vol), torch.tensor(syn.BOUNDS),
+                                  precision=ops.NRF_PREC_FP32, fma=True)
+    report["grid_sample_latent_fma_mode"] = bits_equal_frac(field_fma[:, :C][inside], lat_ref[inside])
     report["positional_encoding_xyz"] = bits_equal_frac(field_in[:, C:C + 3], pe_ref[:, :3])
     assert report["positional_encoding_xyz"] == 1.0                             # canonical coordinates: IEEE sub / div
     report["positional_encoding_sin"] = bits_equal_frac(field_in[:, C + 3:C + 39], pe_ref[:, 3:])

@@ -944,3 +944,55 @@ def test_training_script_call_sites_run_unchanged(ops, NR):
                                                                 voxel_pose=None, tgt_pose=gt_pose, focal=focal, c=None)
     assert rgb_render.shape == (1, H, W, 3) and embed_render.shape == (1, H, W, 512) and depth.shape == (1, H, W)
     assert torch.isfinite(rgb_render).all() and float(rgb_render.min()) >= 0.0 and float(rgb_render.max()) <= 1.0
+
+
+def test_cuda_graph_step_matches_the_eager_step(ops, NR):
+    """GraphedRenderLoss (graphed.py): the training step captured into two CUDA graphs behind one autograd node.  With the
+    ray subsample pinned at capture time and perturb off, a replay is the same arithmetic as the eager step: bit-identical
+    loss and gradients in the reproducible mode; new inputs and updated weights are picked up by the next replay."""
+    G = load_pkg("graphed")
+    fx = golden("full_s32")
+    meta = [int(v) for v in fx["meta"]]
+    S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
+    inp = syn_case_inputs(fx)
+    ren = make_renderer(NR, meta, inp["params"], "bf16").train()
+    ren.perturb = False
+    ren.deterministic = True
+    dev = torch.device("cuda")
+    vol = inp["vol"].cuda().requires_grad_(True)
+    poses = syn.arc_poses(SB).cuda()
+    focal = torch.tensor(153.0, device=dev)
+    g = torch.Generator().manual_seed(1)
+    gt_rgb = torch.rand(SB, H, W, 3, generator=g).cuda()
+    gt_emb = torch.randn(SB, H, W, D, generator=g).cuda()
+    idx = syn.pick_ray_indices(H * W, n_rays, seed=2).cuda()
+    params = [p for p in ren.parameters()]
+
+    def eager(rgb):
+        with mock.patch.object(torch, "randint", lambda *a, **k: idx):
+            return ren(multi_scale_voxel_list=None, voxel_density=None, language=None, voxel_feat=vol, voxel_poses=poses,
+                       focal=focal, gt_rgb=rgb, gt_depth=None, gt_pose=poses, c=None, lang_goal=None, gt_embed=gt_emb)
+
+    def grads_of(out):
+        vol.grad = None
+        for p in params:
+            p.grad = None
+        out["loss"].backward()
+        return vol.grad.clone(), [p.grad.clone() for p in params]
+    with mock.patch.object(torch, "randint", lambda *a, **k: idx):      # the subsample becomes a constant of the graph
+        step = G.GraphedRenderLoss(ren, vol, poses, focal, gt_rgb, gt_emb)
+    for rgb in (gt_rgb, 1.0 - gt_rgb):                                    # second round: new targets through the static buffers
+        ref = eager(rgb)
+        vg_ref, pg_ref = grads_of(ref)
+        out = step(vol, poses, focal, rgb, gt_emb)
+        assert isinstance(out, NR.LossDict)
+        vg, pg = grads_of(out)
+        assert float(out["loss"]) == float(ref["loss"]) and out["psnr"] == ref["psnr"]
+        assert torch.equal(vg, vg_ref)
+        for a, b in zip(pg, pg_ref):
+            assert torch.equal(a, b)
+    # weights written by an optimizer are read by the next replay (the pack kernel is part of the graph)
+    with torch.no_grad():
+        ren.nerf_model.mlp_coarse.lin_out.weight.mul_(0.5)
+    a, b = step(vol, poses, focal, gt_rgb, gt_emb), eager(gt_rgb)
+    assert float(a["loss"]) == float(b["loss"]) and float(a["loss"]) != float(ref["loss"])
