@@ -238,6 +238,7 @@ def test_stages_against_the_oracle_run_on_the_device(mods):
     field_fma = ops.encode_points(rays, z, R // 2, ops.volume_to_channels_last(vol), torch.tensor(syn.BOUNDS),
                                   precision=ops.NRF_PREC_FP32, fma=True)
     report["grid_sample_latent_fma_mode"] = bits_equal_frac(field_fma[:, :C][inside], lat_ref[inside])
+    assert report["grid_sample_latent_fma_mode"] == 1.0 and torch.equal(field_fma[:, :C], lat_ref)
     report["positional_encoding_xyz"] = bits_equal_frac(field_in[:, C:C + 3], pe_ref[:, :3])
     assert report["positional_encoding_xyz"] == 1.0                             # canonical coordinates: IEEE sub / div
     report["positional_encoding_sin"] = bits_equal_frac(field_in[:, C + 3:C + 39], pe_ref[:, 3:])
