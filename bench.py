@@ -520,7 +520,8 @@ def other_configs(mods, args, dev, rank, world):
         vred = None
         if world > 1:
             par.overlap_mlp_grad_allreduce(c.ren)
-            vred = par.sparse_allreduce_volume_grad       # touched voxel rows only (the dense form is timed below)
+            c.ren.keep_voxel_counts = True                # the scatter's own per-voxel counts name the touched rows
+            vred = lambda g: par.sparse_allreduce_volume_grad(g, counts=c.ren.last_voxel_counts)   # (dense form: below)
         for _ in range(2):
             c.step(volume_allreduce=vred)
         n = 5
@@ -533,12 +534,13 @@ def other_configs(mods, args, dev, rank, world):
         if world > 1:                               # the exchange alone, both forms, for the efficiency statement
             g0 = c.vol.grad.detach().clone()        # this rank's reduced gradient has the union footprint: an upper bound
             g = g0.clone()
+            stats = par.sparse_allreduce_volume_grad(g0.clone(), counts=c.ren.last_voxel_counts)
             ms_s, _ = timed_region(lambda: par.sparse_allreduce_volume_grad(g), 3, dev, world)
-            stats = par.sparse_allreduce_volume_grad(g)
             ms_c, _ = timed_region(lambda: par.allreduce_volume_grad(g), 3, dev, world)
             ms_dense_step, _ = timed_region(lambda: c.step(volume_allreduce=par.allreduce_volume_grad), 3, dev, world)
             rec["volume_grad_exchange"] = {
-                "sparse_ms_union_footprint": round(ms_s / 3, 3), "sparse_bytes_union_footprint": stats["bytes"],
+                "sparse_bytes_per_rank_received": stats["bytes"], "sparse_rows_per_rank": stats["rows"],
+                "sparse_ms_dense_scan_union_footprint": round(ms_s / 3, 3),
                 "dense_allreduce_ms": round(ms_c / 3, 3), "dense_bytes": int(g.numel() * 4),
                 "ms_per_step_with_dense_allreduce": round(ms_dense_step / 3, 3)}
             rec["workload"] = rec["workload"].replace("dense all-reduce of the 4.1 GB volume gradient",

@@ -606,12 +606,12 @@ def _merged_scatter_ok(ren, vol_shape_cl):
 def _finish_volume_grad(ren, rays, rps, defer, vol_shape_cl, cl3d):
     """dL/dvoxel_feat in the caller's memory format from the deferred (z, dlatent) of every pass."""
     SB, S0, S1, S2, C = vol_shape_cl
-    if cl3d:                                               # channels_last_3d in -> channels_last_3d gradient out
-        g = torch.empty(vol_shape_cl, device=rays.device, dtype=torch.float32)
-        ops.scatter_volume_grad_merged(rays, rps, defer, g, False, ren._bounds)
-        return g.permute(0, 4, 1, 2, 3)
-    g = torch.empty((SB, C, S0, S1, S2), device=rays.device, dtype=torch.float32)
-    return ops.scatter_volume_grad_merged(rays, rps, defer, g, True, ren._bounds)
+    keep = bool(getattr(ren, "keep_voxel_counts", False))  # for parallel.sparse_allreduce_volume_grad (config 5)
+    g = torch.empty(vol_shape_cl if cl3d else (SB, C, S0, S1, S2), device=rays.device, dtype=torch.float32)
+    res = ops.scatter_volume_grad_merged(rays, rps, defer, g, not cl3d, ren._bounds, want_counts=keep)
+    if keep:
+        ren.last_voxel_counts = res[1]
+    return g.permute(0, 4, 1, 2, 3) if cl3d else g
 
 
 def _is_channels_last_3d(t):
@@ -877,6 +877,8 @@ class NeuralRenderer(nn.Module):
         self.fused_loss = True                 # rgb / embed losses + their gradients in one kernel (nrf_render_loss)
         self.render_chunk_rays = 4096          # neural_rendering.py:482
         self.trace_ranges = True               # the reference's five profiler labels as record_function + NVTX ranges
+        self.keep_voxel_counts = False         # True: the backward leaves the per-voxel entry counts of its scatter in
+        self.last_voxel_counts = None          # `last_voxel_counts` (what the sparse volume-gradient exchange sends)
         self._num_freqs = self.nerf_model.code.num_freqs
         self._freq_factor = float(self.nerf_model.code.freq_factor)
         self._d_embed = self.nerf_model.d_embed

@@ -263,11 +263,14 @@ def scatter_volume_grad_sorted(rays, z, rays_per_scene, dlatent, grad_cl, bounds
 
 
 @_on_tensor_device
-def scatter_volume_grad_merged(rays, rays_per_scene, passes, grad, channels_first, bounds):
+def scatter_volume_grad_merged(rays, rays_per_scene, passes, grad, channels_first, bounds, want_counts=False):
     """ONE atomics-free scatter for all render passes of a step (see nrf_scatter_volume_grad_merged).
 
     passes: [(z (R,K), dlatent (R*K, >=C) fp32), ...] (one or two); grad: (SB,C,S0,S1,S2) if channels_first
-    else (SB,S0,S1,S2,C), fully overwritten (no memset needed)."""
+    else (SB,S0,S1,S2,C), fully overwritten (no memset needed).
+    want_counts: also return the per-voxel entry counts (SB*V,) int32 the counting sort produced (the first array of the
+    workspace): `counts > 0` marks exactly the voxels whose gradient row was computed rather than zero-filled - what
+    parallel.sparse_allreduce_volume_grad needs, without a pass over the dense gradient."""
     rays = _f32(rays, "rays")
     assert 1 <= len(passes) <= 2
     assert grad.is_cuda and grad.dtype == torch.float32 and grad.is_contiguous()
@@ -288,6 +291,8 @@ def scatter_volume_grad_merged(rays, rays_per_scene, passes, grad, channels_firs
                                              db.shape[1] if db is not None else 0, ptr(grad), int(channels_first),
                                              SB, Cc, S0, S1, S2, C.cast(bh, C.c_void_p), ptr(ws), stream_ptr()),
           "nrf_scatter_volume_grad_merged")
+    if want_counts:
+        return grad, ws[:4 * SB * S0 * S1 * S2].view(torch.int32).clone()
     return grad
 
 

@@ -96,7 +96,7 @@ def allreduce_volume_grad(grad: torch.Tensor, group=None) -> torch.Tensor:
 
 
 @torch.no_grad()
-def sparse_allreduce_volume_grad(grad: torch.Tensor, group=None) -> dict:
+def sparse_allreduce_volume_grad(grad: torch.Tensor, group=None, counts: torch.Tensor = None) -> dict:
     """Sum of a volume gradient across ranks by exchanging only the voxels a rank's rays touched (SURVEY 8e, config 5:
     ONE scene whose rays are split over the GPUs).  grad: (SB,C,S0,S1,S2), contiguous or channels_last_3d, summed IN
     PLACE; every rank ends with bit-identical values (the contributions are added in rank order on every rank).
@@ -104,7 +104,10 @@ def sparse_allreduce_volume_grad(grad: torch.Tensor, group=None) -> dict:
     A rank's rays touch a small part of the grid (the 200^3 x 128-channel gradient is 4.1 GB, the rows written by
     16 384 / N rays a few hundred MB), so instead of a dense all-reduce each rank all-gathers (voxel index, C-vector)
     rows: bytes on the wire = sum of the touched rows x (4 C + 8) instead of 2 (N-1)/N x the whole volume.
-    Costs one host synchronisation (the row counts size the exchange buffers).  Returns the exchange statistics."""
+    Costs one host synchronisation (the row counts size the exchange buffers).  Returns the exchange statistics.
+    counts: optional (SB*V,) per-voxel entry counts of the scatter that produced `grad`
+    (`renderer.keep_voxel_counts = True` -> `renderer.last_voxel_counts`): the touched set is then `counts > 0`
+    (32 MB at 200^3) instead of a scan of the dense gradient (4.1 GB read + a 1 GB boolean temporary)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return {"rows": 0, "bytes": 0}
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -119,8 +122,12 @@ def sparse_allreduce_volume_grad(grad: torch.Tensor, group=None) -> dict:
     else:
         raise ValueError("sparse_allreduce_volume_grad: gradient must be contiguous or channels_last_3d")
     assert all(v.data_ptr() == grad[b].data_ptr() for b, v in enumerate(views)), "expected views, got copies"
-    touched = torch.stack([(v != 0).any(1 - vdim) for v in views])               # (SB, V)
-    idx = touched.reshape(-1).nonzero().squeeze(1)                               # flat (scene * V + voxel), ascending
+    if counts is not None:
+        assert counts.numel() == SB * V, "counts must have one entry per voxel"
+        touched = counts.reshape(-1) > 0
+    else:
+        touched = torch.stack([(v != 0).any(1 - vdim) for v in views]).reshape(-1)   # (SB * V)
+    idx = touched.nonzero().squeeze(1)                                           # flat (scene * V + voxel), ascending
     counts = torch.zeros(world, device=grad.device, dtype=torch.int64)
     counts[rank] = idx.numel()
     dist.all_reduce(counts, group=group)

@@ -101,6 +101,7 @@ def _worker_split(rank, world, port, out):
             syn.init_mlp_(ren.nerf_model.mlp_coarse, seed=0)
             ren = ren.cuda().train()
             vol = vol0.clone().requires_grad_(True)
+            ren.keep_voxel_counts = True
             ren.encode(None, None, None, vol, None, None, None)
             o = ren.forward_nerf(rays[:, sl], noise={k: v[sl] for k, v in noise.items()})
             # sums (not means) so that the split losses add up to the full one
@@ -113,7 +114,10 @@ def _worker_split(rank, world, port, out):
         ren, vg = run(slice(lo, hi))
         dense = vg.clone()
         par.allreduce_volume_grad(dense)
-        stats = par.sparse_allreduce_volume_grad(vg)
+        by_scan = vg.clone()
+        par.sparse_allreduce_volume_grad(by_scan)
+        stats = par.sparse_allreduce_volume_grad(vg, counts=ren.last_voxel_counts)     # touched set from the scatter itself
+        assert torch.equal(vg, by_scan)
         par.allreduce_mlp_grads(ren)
         torch.cuda.synchronize()
         rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
