@@ -90,6 +90,32 @@ int mlp_x3_fwd(const NrfMlpParams* p, const void* packed, const float* field_in,
                float* field_out, cudaStream_t s);
 int mlp_x3_bwd(const NrfMlpParams* p, const void* packed, int64_t N, const void* acts, const float* d_field,
                const NrfMlpGrads* gr, float* dlatent, void* scratch, cudaStream_t s);
+// All weight gradients of one backward pass in one persistent launch (wgrad_multi.cu).  Operands are (M, cols) bf16
+// matrices with row pitch ld; a problem multiplies the columns of ONE G operand with k_tiles x ns slabs of 64 columns,
+// each slab taken from any operand at any 64-aligned column and added into its own destination.
+constexpr int kWgmMaxMaps = 40, kWgmMaxProblems = 28, kWgmMaxSlabs = 8;
+struct WgmSlab {
+  float* dW; int ldw;      // destination of this slab's 64 columns: dW[n * ldw + j], j < k_valid
+  int k_valid;             // 0: padding slab, results dropped
+  int a_map, a_col;        // source operand and first column
+};
+struct WgmProblem {
+  int g_map;               // operand G
+  int n_valid;             // columns of G that count = rows of the dW's
+  int ns;                  // slabs per k tile: 2 or 4 (MMA N = 64 ns)
+  int k_tiles;
+  float* dbias;            // += column sums of G (NULL: none)
+  float* dbias2;           // a second bias with the same gradient (lin_in / lin_z[0]), or NULL
+  WgmSlab slab[kWgmMaxSlabs];
+};
+struct WgmOperand { const void* base; int cols, ld; };
+struct WgmHost {
+  int n_maps; WgmOperand op[kWgmMaxMaps];
+  int n_prob; WgmProblem prob[kWgmMaxProblems];
+  int M;
+  int* sync;               // >= kWgmMaxProblems * 128 ints of device scratch (zeroed by the launcher), or NULL
+};
+int wgrad_multi_launch(const WgmHost& h, cudaStream_t stream);
 int wgrad_simt_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
                       int k_valid, float* dW, int ldw, float* dbias, cudaStream_t stream);
 

@@ -450,6 +450,87 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
     auto gx = [&](int b) { return G + (int64_t)b * layer; };                 // dL/dx'_b, b = 0..nb
     auto gn = [&](int b) { return G + (int64_t)(L.nb + 1 + b) * layer; };    // dL/dnet_b
     TRY(mlp_bwd_fused(L, W, d_field, N, acts, G, precision, s));
+    // every weight gradient of the pass in one persistent launch (wgrad_multi.cu); the ordered-reduction mode and
+    // NRF_WGRAD_MULTI=0 keep one launch per GEMM
+    static const bool multi_off = getenv("NRF_WGRAD_MULTI") && atoi(getenv("NRF_WGRAD_MULTI")) == 0;
+    if (!gr->deterministic && !multi_off && L.H == 512) {
+      WgmHost h;
+      memset(&h, 0, sizeof(h));
+      h.M = (int)N;
+      h.sync = reinterpret_cast<int*>(sc);        // the split-reduction workspace of the ordered mode is free here
+      auto operand = [&](const void* base, int cols, int ld) {
+        h.op[h.n_maps].base = base; h.op[h.n_maps].cols = cols; h.op[h.n_maps].ld = ld;
+        return h.n_maps++;
+      };
+      // a problem over the 512 columns of a saved activation layer: two k tiles of four slabs
+      auto square = [&](int g_map, int n_valid, const void* a, float* dW, float* db, float* db2) {
+        if (!dW) return;                                       // as run_wgrad: no weight gradient wanted, none computed
+        WgmProblem& q = h.prob[h.n_prob++];
+        q.g_map = g_map; q.n_valid = n_valid; q.ns = 4; q.k_tiles = L.H / 256;
+        q.dbias = db ? db : db2; q.dbias2 = db ? db2 : nullptr;
+        const int am = operand(a, L.H, L.H);
+        for (int j = 0; j < L.H / 64; ++j) {
+          q.slab[j].dW = dW + 64 * j; q.slab[j].ldw = L.H; q.slab[j].k_valid = 64;
+          q.slab[j].a_map = am; q.slab[j].a_col = 64 * j;
+        }
+      };
+      const int fin_map = operand(fin, L.kin_pad, L.kin_pad);
+      const int cs = L.C / 64;                                 // 64-wide slabs of the latent part of the field input
+      // G = dL/dx'_b times the latent columns of the field input (lin_z[b]); b = 0 also takes the PE / viewdir columns
+      // (lin_in) in the same tile.  Biases: lin_z_b[b] has the gradient of the layer that shares its G (added there).
+      auto field_in_problem = [&](int g_map, int b) {
+        float* wz = b < L.nz ? gr->lin_z_w[b] : nullptr;
+        float* win = b == 0 ? gr->lin_in_w : nullptr;
+        if (!wz && !win) return;
+        WgmProblem& q = h.prob[h.n_prob++];
+        const int pe = b == 0 ? (L.kin_pad - L.C) / 64 : 0;
+        const int slabs = (b < L.nz ? cs : 0) + pe;
+        q.g_map = g_map; q.n_valid = L.H; q.ns = slabs <= 2 ? 2 : 4; q.k_tiles = (slabs + q.ns - 1) / q.ns;
+        int j = 0;
+        for (int c = 0; b < L.nz && c < cs; ++c, ++j) {
+          q.slab[j].dW = wz ? wz + 64 * c : nullptr; q.slab[j].ldw = L.C; q.slab[j].k_valid = wz ? 64 : 0;
+          q.slab[j].a_map = fin_map; q.slab[j].a_col = 64 * c;
+        }
+        for (int c = 0; c < pe; ++c, ++j) {
+          const int left = L.Din - 64 * c;
+          q.slab[j].dW = win ? win + 64 * c : nullptr; q.slab[j].ldw = L.Din;
+          q.slab[j].k_valid = !win || left < 0 ? 0 : (left > 64 ? 64 : left);
+          q.slab[j].a_map = fin_map; q.slab[j].a_col = L.C + 64 * c;
+        }
+        for (; j < q.k_tiles * q.ns; ++j) {                    // padding slabs: any readable columns, results dropped
+          q.slab[j].dW = nullptr; q.slab[j].ldw = 0; q.slab[j].k_valid = 0; q.slab[j].a_map = fin_map; q.slab[j].a_col = 0;
+        }
+        if (b == 0) {                                          // the per-GEMM path ties a bias to its weight's GEMM
+          float* b1 = win ? gr->lin_in_b : nullptr;
+          float* b2 = wz ? gr->lin_z_b[0] : nullptr;
+          q.dbias = b1 ? b1 : b2; q.dbias2 = b1 ? b2 : nullptr;
+        }
+      };
+      const bool fits = 2 * L.nb + 2 + L.nz <= kWgmMaxProblems && 4 * L.nb + 4 <= kWgmMaxMaps &&
+                        (L.kin_pad - L.C) / 64 + cs <= kWgmMaxSlabs;
+      if (fits) {
+        square(operand(d_field, L.dout_pad, L.dout_pad), L.Dout, ax(L.nb), gr->lin_out_w, gr->lin_out_b, nullptr);
+        for (int b = L.nb - 1; b >= 0; --b) {
+          const int gxm = operand(gx(b + 1), L.H, L.H);
+          // lin_z_b[b + 1] has fc1_b[b]'s gradient: summed once, by fc_1's problem, or by lin_z's own when fc_1 has none
+          const bool z_here = b + 1 < L.nz && gr->lin_z_w[b + 1];
+          square(gxm, L.H, an(b), gr->fc1_w[b], gr->fc1_b[b], z_here ? gr->lin_z_b[b + 1] : nullptr);
+          if (z_here) {
+            field_in_problem(gxm, b + 1);
+            if (!gr->fc1_w[b]) h.prob[h.n_prob - 1].dbias = gr->lin_z_b[b + 1];
+          }
+          square(operand(gn(b), L.H, L.H), L.H, ax(b), gr->fc0_w[b], gr->fc0_b[b], nullptr);
+        }
+        field_in_problem(operand(gx(0), L.H, L.H), 0);
+        TRY(wgrad_multi_launch(h, s));
+        NrfGemm g = gemm_init(N, (int)round_up(L.C, 128), L.C);
+        for (int b = 0; b < L.nz; ++b) set_a(g, b, gx(b), L.H, L.H);
+        g.B = W + L.WzcatT; g.ldb = L.nz * L.H;
+        g.out_f32 = dlatent; g.ldo = L.C;
+        TRY(run_gemm(g, precision, true, s));
+        return NRF_OK;
+      }
+    }
     TRY(run_wgrad(d_field, L.dout_pad, ax(L.nb), L.H, N, L.dout_pad, L.H, L.Dout, L.H, gr->lin_out_w, L.H,
                   gr->lin_out_b, wws, precision, s));
     for (int b = L.nb - 1; b >= 0; --b) {

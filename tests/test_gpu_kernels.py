@@ -487,6 +487,44 @@ def test_fused_mlp_backward_is_bit_identical_to_the_layered_chain(ops, C, N, D):
     assert rel(res[False][1]["lin_out.weight"], p["lin_out.weight"].grad) < 3e-2
 
 
+@pytest.mark.parametrize("C,N,D", [(128, 256, 384), (128, 1000, 384), (128, 33000, 384), (64, 777, 384), (128, 3, 384),
+                                   (64, 1000, 512), (128, 70001, 512), (64, 5, 512), (128, 300000, 384)])
+def test_one_launch_weight_gradients_match_the_per_gemm_kernel(ops, C, N, D):
+    """wgrad_multi_kernel (every weight / bias gradient of the pass in one persistent launch; bias sums on CUDA cores;
+    lin_in + lin_z[0] in one tile) against the per-GEMM kernel with its ordered split reduction on the same operands:
+    same bf16 products, fp32 sums in a different order.  dL/dlatent does not depend on the choice: bit-identical."""
+    NR = load_pkg("neural_rendering")
+    mlp = _bf16_mlp(C=C, D=D, seed=2)
+    h = mlp.handle(ops.NRF_PREC_BF16)
+    g = torch.Generator().manual_seed(N + 7)
+    fin = torch.zeros(N, h.sizes.kin_pad, dtype=torch.bfloat16)
+    fin[:, :C + 42] = (torch.randn(N, C + 42, generator=g) * 0.5).to(torch.bfloat16)
+    dfield = torch.zeros(N, h.sizes.dout_pad, dtype=torch.bfloat16)
+    dfield[:, :4 + D] = (torch.randn(N, 4 + D, generator=g) * 0.1).to(torch.bfloat16)
+    fin, dfield = fin.cuda(), dfield.cuda()
+    out, acts = h.forward(fin)
+    res = {}
+    for det in (True, False):
+        grads = NR._zero_grads(h)
+        n0 = load_pkg("_lib").launch_count()
+        dlat = h.backward(fin, acts, dfield, grads, deterministic=det)
+        res[det] = (dlat, grads, load_pkg("_lib").launch_count() - n0)
+    assert res[False][2] <= 4 < res[True][2], f"fused backward + ONE weight-gradient launch + dL/dz GEMM, got {res[False][2]}"
+    assert torch.equal(res[True][0], res[False][0])
+    for n in h.names():
+        a, b = res[False][1][n], res[True][1][n]
+        assert a.shape == b.shape
+        err = float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+        assert err < 2e-5, (n, err)
+    # accumulation: a second pass adds on top (the gradient buffers are not overwritten)
+    grads = res[False][1]
+    before = {n: grads[n].clone() for n in h.names()}
+    h.backward(fin, acts, dfield, grads, deterministic=False)
+    for n in h.names():
+        err = float((grads[n].double() - 2 * before[n].double()).abs().max() / (before[n].double().abs().max() + 1e-30))
+        assert err < 2e-5, (n, err)
+
+
 def test_acts_of_the_layered_forward_take_the_layered_backward(ops):
     """Only the fused forward writes the gate bits; FieldMLP routes a backward over layered activations to the chain."""
     NR = load_pkg("neural_rendering")
