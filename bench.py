@@ -282,15 +282,16 @@ def run_ours(args):
     launches0 = lib.launch_count()
     ms_total, ms_rank = timed_region(lambda: main.step(post_allreduce=post), K, dev, world)   # behind `value`
     launches = lib.launch_count() - launches0
+    # end-to-end: host (pinned) inputs copied in, loss read back, every step (right after `value`: the step slows by
+    # ~5 % over the first seconds under the power cap - see `sustained` - and the two should see the same clocks)
+    main.step(host_inputs=True, post_allreduce=post)
+    ms_e2e, _ = timed_region(lambda: main.step(host_inputs=True, post_allreduce=post), K, dev, world, read_losses=True)
     # same K steps again with a CUDA-event pair around every kernel launch (recorded by the library on the
-    # launching stream): per-kernel durations for the roofline; kept out of `value` because ~500 event
+    # launching stream): per-kernel durations for the roofline; kept out of `value` because ~300 event
     # records per step add launch gaps
     lib.timing_begin()
     ms_total_ev, _ = timed_region(lambda: main.step(post_allreduce=post), K, dev, world)
     kern = lib.timing_end()
-    # end-to-end: host (pinned) inputs copied in, loss read back, every step
-    main.step(host_inputs=True, post_allreduce=post)
-    ms_e2e, _ = timed_region(lambda: main.step(host_inputs=True, post_allreduce=post), K, dev, world, read_losses=True)
     # a long timed region as well (20 steps are 0.3 s): >= 200 steps and >= 3 s, same step, same clock
     n_sus = 0 if args.sustain_steps <= 0 else max(args.sustain_steps, int(3000.0 / (ms_total / K)) + 1)
     sustained = None

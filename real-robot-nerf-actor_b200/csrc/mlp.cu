@@ -509,18 +509,23 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
       const bool fits = 2 * L.nb + 2 + L.nz <= kWgmMaxProblems && 4 * L.nb + 4 <= kWgmMaxMaps &&
                         (L.kin_pad - L.C) / 64 + cs <= kWgmMaxSlabs;
       if (fits) {
+        int gx_map[NRF_MAX_BLOCKS + 1];
+        for (int b = 0; b <= NRF_MAX_BLOCKS; ++b) gx_map[b] = -1;
         square(operand(d_field, L.dout_pad, L.dout_pad), L.Dout, ax(L.nb), gr->lin_out_w, gr->lin_out_b, nullptr);
         for (int b = L.nb - 1; b >= 0; --b) {
           const int gxm = operand(gx(b + 1), L.H, L.H);
           // lin_z_b[b + 1] has fc1_b[b]'s gradient: summed once, by fc_1's problem, or by lin_z's own when fc_1 has none
           const bool z_here = b + 1 < L.nz && gr->lin_z_w[b + 1];
           square(gxm, L.H, an(b), gr->fc1_w[b], gr->fc1_b[b], z_here ? gr->lin_z_b[b + 1] : nullptr);
-          if (z_here) {
-            field_in_problem(gxm, b + 1);
-            if (!gr->fc1_w[b]) h.prob[h.n_prob - 1].dbias = gr->lin_z_b[b + 1];
-          }
+          if (z_here) gx_map[b + 1] = gxm;
           square(operand(gn(b), L.H, L.H), L.H, ax(b), gr->fc0_w[b], gr->fc0_b[b], nullptr);
         }
+        // the narrow problems after the 512 x 512 ones: problems of one shape in a row can share a wave (short passes)
+        for (int b = L.nz - 1; b >= 1; --b)
+          if (gx_map[b] >= 0) {
+            field_in_problem(gx_map[b], b);
+            if (!gr->fc1_w[b - 1]) h.prob[h.n_prob - 1].dbias = gr->lin_z_b[b];
+          }
         field_in_problem(operand(gx(0), L.H, L.H), 0);
         TRY(wgrad_multi_launch(h, s));
         NrfGemm g = gemm_init(N, (int)round_up(L.C, 128), L.C);

@@ -36,7 +36,7 @@ struct WgmDevProblem {
   int g_map, n_valid, ns, k_tiles;
   int tiles, splits, m_per, bias_mask;       // bias_mask < 0: k tile 0 sums every sample block
   uint32_t idesc;
-  int pad_;
+  int pair0;                                 // first CTA pair of this problem (several short problems share a wave)
   float* dbias;
   float* dbias2;
   WgmSlab slab[kWgmMaxSlabs];
@@ -55,8 +55,9 @@ constexpr int kWgmSyncStride = 128;
 // This pair's share of problem p (the same arithmetic in every warp role).
 __device__ __forceinline__ bool wgm_work(const WgmArgs& a, int p, int pair, WgmWork& w) {
   const WgmDevProblem& P = a.prob[p];
-  if (pair >= P.tiles * P.splits) return false;
-  const int tile = pair % P.tiles, split = pair / P.tiles;
+  const int rel = pair - P.pair0;
+  if (rel < 0 || rel >= P.tiles * P.splits) return false;
+  const int tile = rel % P.tiles, split = rel / P.tiles;
   w.np = tile / P.k_tiles;
   w.kt = tile - w.np * P.k_tiles;
   w.split = split;
@@ -109,7 +110,14 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_multi_kernel(const __gri
       const int c0 = sl[0].a_col, c1 = sl[half - 1].a_col;
       const uint32_t bytes = 2u * (uint32_t)(kWgmStageG + half * kWgmSlab);
       const int n0 = w.np * 256 + (int)crank * kTileM;
-      if (lane == 0) { tma_prefetch_desc(mg); tma_prefetch_desc(ma0); tma_prefetch_desc(ma1); }
+      if (lane == 0) {
+        tma_prefetch_desc(mg); tma_prefetch_desc(ma0); tma_prefetch_desc(ma1);
+        if (p + 1 < a.n_prob) {                                    // and the next problem's, a whole problem ahead
+          const WgmDevProblem& Q = a.prob[p + 1];
+          tma_prefetch_desc(&a.maps[Q.g_map]);
+          tma_prefetch_desc(&a.maps[Q.slab[0].a_map]);
+        }
+      }
       if (a.sync && P.tiles > 1 && !(a.dbg & 8)) {
         // The tiles of a sample split read the same G / A rows: started together they take them from DRAM once and
         // from L2 otherwise.  Without this the pairs drift apart over the launch (measured: +16 % DRAM reads).  A
@@ -296,14 +304,34 @@ int wgrad_multi_launch(const WgmHost& h, cudaStream_t stream) {
     const int n_pairs = (s.n_valid + 255) / 256;
     d.tiles = n_pairs * s.k_tiles;
     NRF_REQUIRE(d.tiles <= pairs, NRF_ENOSUP, "wgrad_multi: %d output tiles > %d CTA pairs", d.tiles, pairs);
-    int splits = pairs / d.tiles;                              // one wave: tiles x sample splits <= CTA pairs
+    d.bias_mask = (s.k_tiles & (s.k_tiles - 1)) == 0 ? s.k_tiles - 1 : -1;
+    d.idesc = make_idesc(2 * kTileM, 64 * s.ns, 1, 1, 0, 0);
+  }
+  // Sample splits.  Long passes: one problem at a time, its tiles x splits fill the CTA pairs.  Short passes (the
+  // reference's own 512-ray chunks): a split of fewer than ~8192 samples costs more in fp32 reductions of its
+  // accumulator (256 KB per pair and problem, whatever M is) and in pipeline restarts than it computes, so up to `g`
+  // consecutive problems of the same shape run side by side on disjoint pairs, each with 1/g of the splits.
+  const int want = (h.M + 8191) / 8192;                        // splits a problem can keep busy
+  for (int p = 0; p < h.n_prob;) {
+    const int T = args.prob[p].tiles;
+    int gmax = 1;
+    while (p + gmax < h.n_prob && args.prob[p + gmax].tiles == T && args.prob[p + gmax].ns == args.prob[p].ns) ++gmax;
+    int g = 1;
+    for (int c = 1; c <= gmax; ++c) {                          // the most problems per wave that still leave >= `want`
+      const int sp = pairs / (c * T);                          // splits each and idle <= 5 % of the pairs
+      if (sp >= 1 && sp >= (want < pairs / T ? want : pairs / T) && c * T * sp * 20 >= pairs * 19) g = c;
+    }
+    int splits = pairs / (g * T);
     const int max_splits = (h.M + 4 * kTileK - 1) / (4 * kTileK);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    d.m_per = ((h.M + splits - 1) / splits + kTileK - 1) / kTileK * kTileK;
-    d.splits = (h.M + d.m_per - 1) / d.m_per;
-    d.bias_mask = (s.k_tiles & (s.k_tiles - 1)) == 0 ? s.k_tiles - 1 : -1;
-    d.idesc = make_idesc(2 * kTileM, 64 * s.ns, 1, 1, 0, 0);
+    const int m_per = ((h.M + splits - 1) / splits + kTileK - 1) / kTileK * kTileK;
+    splits = (h.M + m_per - 1) / m_per;
+    for (int j = 0; j < g; ++j) {
+      WgmDevProblem& d = args.prob[p + j];
+      d.m_per = m_per; d.splits = splits; d.pair0 = j * T * splits;
+    }
+    p += g;
   }
   args.n_prob = h.n_prob; args.M = h.M;
   args.sync = h.sync;
