@@ -129,6 +129,25 @@ int nrf_scatter_volume_grad_merged(const float* rays, int R, int rays_per_scene,
                                    int C, int S0, int S1, int S2, const float* bounds_host, void* workspace,
                                    void* stream);
 
+/* ---- sparse exchange of a volume gradient between ranks (BASELINE config 5) --------------------
+ * ONE scene whose rays are split over the GPUs: every rank's backward produces a full-size dL/dvoxel_feat of which
+ * only the voxels its own rays crossed are non-zero.  The reference has no multi-GPU path (its ancestor shards rays
+ * and replicates the network: featurenerf_robo/featurenerf/src/render/nerf_embed.py:412-429); these two calls are the
+ * device side of summing such gradients by exchanging (voxel index, C-vector) rows instead of the whole volume.
+ * grad: (SB,C,V) if channels_first else (SB,V,C), V = S0*S1*S2.  idx: n ascending, unique int64 `scene * V + voxel`.
+ *   nrf_rows_gather: rows[i, 0:C] = grad[voxel idx[i]]                        rows (n, C) fp32, 16 B aligned
+ *   nrf_rows_update: grad[voxel idx[i]] = rows[i] (add == 0), += rows[i] (add != 0), or = 0 (rows == NULL)
+ * No atomics (unique indices): lists applied one call after the other in rank order give the same bits everywhere. */
+int nrf_rows_gather(const float* grad, int channels_first, int C, int64_t V, const int64_t* idx, int64_t n,
+                    float* rows, void* stream);
+int nrf_rows_update(float* grad, int channels_first, int C, int64_t V, const int64_t* idx, int64_t n,
+                    const float* rows, int add, void* stream);
+/* All ranks' lists at once: rows (world, cap, C), idx (world, cap), counts_host[r] valid entries of rank r (HOST array).
+ * Every voxel some rank lists is set to the sum of its rows in rank order (0.0 + r_0 + r_1 + ..: the same bits on every
+ * rank); other voxels keep their value.  One pass, the volume is written once per touched 32-voxel tile, never read. */
+int nrf_rows_merge(float* grad, int channels_first, int C, int64_t V, int SB, const float* rows, const int64_t* idx,
+                   int64_t cap, const int64_t* counts_host, int world, void* stream);
+
 /* ---- alpha compositing (neural_rendering.py:239-243,316-359) ---------------------------------
  * field_out (N, ldo) raw; heads sigmoid(rgb), relu(sigma) (models_embed.py:444-466) applied here.
  * weights (R,K), rgb (R,3), embed (R,D), depth (R).

@@ -262,6 +262,59 @@ def scatter_volume_grad_sorted(rays, z, rays_per_scene, dlatent, grad_cl, bounds
     return grad_cl
 
 
+def _rows_args(grad, idx):
+    assert grad.is_cuda and grad.dtype == torch.float32 and grad.dim() == 5
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and idx.device == grad.device
+    SB, Cc = grad.shape[:2]
+    V = grad[0, 0].numel()
+    if grad.is_contiguous():
+        cf = 1
+    elif grad.is_contiguous(memory_format=torch.channels_last_3d):
+        cf = 0
+    else:
+        raise ValueError("volume gradient must be contiguous or channels_last_3d")
+    return cf, Cc, V
+
+
+@_on_tensor_device
+def rows_gather(grad, idx, out=None):
+    """rows (n, C) fp32 = the voxel rows `idx` (ascending unique flat `scene * V + voxel`, int64) of the volume gradient
+    `grad` (SB,C,S0,S1,S2), contiguous or channels_last_3d (nrf_rows_gather)."""
+    cf, Cc, V = _rows_args(grad, idx)
+    n = idx.numel()
+    if out is None:
+        out = torch.empty((n, Cc), device=grad.device, dtype=torch.float32)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.shape[0] >= n and out.shape[1] == Cc
+    check(_lib.load().nrf_rows_gather(ptr(grad), cf, Cc, V, ptr(idx), n, ptr(out), stream_ptr()), "nrf_rows_gather")
+    return out
+
+
+@_on_tensor_device
+def rows_update(grad, idx, rows=None, add=True):
+    """grad[voxel idx[i]] += rows[i] (add), = rows[i] (not add) or = 0 (rows None), in place, no atomics (nrf_rows_update)."""
+    cf, Cc, V = _rows_args(grad, idx)
+    n = idx.numel()
+    if rows is not None:
+        assert rows.is_contiguous() and rows.dtype == torch.float32 and rows.shape[0] >= n and rows.shape[1] == Cc
+    check(_lib.load().nrf_rows_update(ptr(grad), cf, Cc, V, ptr(idx), n, ptr(rows) if rows is not None else None,
+                                      int(bool(add)), stream_ptr()), "nrf_rows_update")
+    return grad
+
+
+@_on_tensor_device
+def rows_merge(grad, all_rows, all_idx, counts):
+    """grad[voxel] = sum in rank order of the ranks' rows for every listed voxel (nrf_rows_merge).  all_rows
+    (world, cap, C) fp32, all_idx (world, cap) int64 ascending per rank, counts: list of world ints."""
+    assert all_idx.dtype == torch.int64 and all_idx.is_contiguous() and all_rows.is_contiguous()
+    cf, Cc, V = _rows_args(grad, all_idx)
+    world, cap = all_idx.shape
+    assert all_rows.shape == (world, cap, Cc) and all_rows.dtype == torch.float32 and len(counts) == world
+    cnt = (C.c_int64 * world)(*[int(c) for c in counts])
+    check(_lib.load().nrf_rows_merge(ptr(grad), cf, Cc, V, grad.shape[0], ptr(all_rows), ptr(all_idx), cap,
+                                     C.cast(cnt, C.c_void_p), world, stream_ptr()), "nrf_rows_merge")
+    return grad
+
+
 @_on_tensor_device
 def scatter_volume_grad_merged(rays, rays_per_scene, passes, grad, channels_first, bounds, want_counts=False):
     """ONE atomics-free scatter for all render passes of a step (see nrf_scatter_volume_grad_merged).

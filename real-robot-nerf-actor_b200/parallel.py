@@ -128,6 +128,8 @@ def sparse_allreduce_volume_grad(grad: torch.Tensor, group=None, counts: torch.T
     else:
         touched = torch.stack([(v != 0).any(1 - vdim) for v in views]).reshape(-1)   # (SB * V)
     idx = touched.nonzero().squeeze(1)                                           # flat (scene * V + voxel), ascending
+    if grad.is_cuda and C % 4 == 0:
+        return _sparse_allreduce_rows_cuda(grad, idx, group)
     counts = torch.zeros(world, device=grad.device, dtype=torch.int64)
     counts[rank] = idx.numel()
     dist.all_reduce(counts, group=group)
@@ -167,6 +169,72 @@ def sparse_allreduce_volume_grad(grad: torch.Tensor, group=None, counts: torch.T
             if hi > lo:
                 views[b].index_add_(vdim, i_r[lo:hi] - b * V, rows_of(all_rows[r], lo, hi))
     return {"rows": counts, "bytes": int(cap * world * (C * grad.element_size() + 8))}
+
+
+def _sparse_allreduce_rows_cuda(grad, idx, group):
+    """The device path of sparse_allreduce_volume_grad: nrf_rows_gather -> all_gather of (rows, indices) ->
+    nrf_rows_merge (every voxel some rank lists = the sum of its rows in rank order, own rows included: the same bits
+    on every rank; the volume is written once per touched tile and never read).  One host synchronisation (the row
+    counts size the buffers)."""
+    from . import ops
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    C = grad.shape[1]
+    n = idx.numel()
+    counts = torch.zeros(world, device=grad.device, dtype=torch.int64)
+    counts[rank] = n
+    dist.all_reduce(counts, group=group)
+    counts = counts.tolist()                                                     # the one host sync
+    cap = max(max(counts), 1)
+    my_rows = torch.empty((cap, C), device=grad.device, dtype=torch.float32)
+    my_idx = torch.empty(cap, device=grad.device, dtype=torch.int64)
+    my_idx[:n] = idx
+    ops.rows_gather(grad, idx, out=my_rows)
+    all_rows = torch.empty((world, cap, C), device=grad.device, dtype=torch.float32)
+    all_idx = torch.empty((world, cap), device=grad.device, dtype=torch.int64)
+    dist.all_gather_into_tensor(all_rows, my_rows, group=group)
+    dist.all_gather_into_tensor(all_idx, my_idx, group=group)
+    ops.rows_merge(grad, all_rows, all_idx, counts)       # every listed voxel = its rows summed in rank order, written once
+    return {"rows": counts, "bytes": int(cap * world * (C * 4 + 8))}
+
+
+@torch.no_grad()
+def sparse_allreduce_phases(grad, counts, group=None) -> dict:
+    """Diagnostics (scripts/exchange_probe.py): the device path of sparse_allreduce_volume_grad phase by phase, each
+    bracketed by a device synchronisation (so the sum exceeds the pipelined call).  Milliseconds."""
+    import time
+    from . import ops
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    C = grad.shape[1]
+    out = {}
+
+    def phase(name, fn):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        out[name] = round((time.perf_counter() - t) * 1e3, 3)
+        return r
+    idx = phase("nonzero", lambda: (counts.reshape(-1) > 0).nonzero().squeeze(1))
+    n = idx.numel()
+
+    def sizes():
+        c = torch.zeros(world, device=grad.device, dtype=torch.int64)
+        c[rank] = n
+        dist.all_reduce(c, group=group)
+        return c.tolist()
+    cnt = phase("counts_allreduce", sizes)
+    cap = max(max(cnt), 1)
+    my_rows = torch.empty((cap, C), device=grad.device, dtype=torch.float32)
+    my_idx = torch.empty(cap, device=grad.device, dtype=torch.int64)
+    my_idx[:n] = idx
+    phase("rows_gather", lambda: ops.rows_gather(grad, idx, out=my_rows))
+    all_rows = torch.empty((world, cap, C), device=grad.device, dtype=torch.float32)
+    all_idx = torch.empty((world, cap), device=grad.device, dtype=torch.int64)
+    phase("all_gather_rows", lambda: dist.all_gather_into_tensor(all_rows, my_rows, group=group))
+    phase("all_gather_idx", lambda: dist.all_gather_into_tensor(all_idx, my_idx, group=group))
+    phase("rows_merge", lambda: ops.rows_merge(grad, all_rows, all_idx, cnt))
+    out["rows"] = cnt
+    return out
 
 
 @torch.no_grad()

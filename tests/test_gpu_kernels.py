@@ -663,3 +663,67 @@ def test_scatter_and_voxelizer_with_long_per_voxel_lists(ops):
     got = vg.coords_to_bounding_voxel_grid(coords.cuda(), coord_features=feats.cuda())
     ref = VO.voxelize(coords, feats, syn.BOUNDS, 10)
     assert int((got[..., -1] > 0).sum()) <= 8 and torch.equal(got.cpu(), ref)
+
+
+# ------------------------------------------------------------------- voxel rows <-> compact list (sparse exchange)
+@pytest.mark.parametrize("C,dims,SB,cl3d", [(128, (9, 7, 11), 2, False), (128, (9, 7, 11), 2, True), (64, (5, 6, 7), 1, False),
+                                            (12, (4, 4, 5), 3, False), (12, (4, 4, 5), 3, True)])
+def test_voxel_rows_gather_and_update(ops, C, dims, SB, cl3d):
+    """nrf_rows_gather / nrf_rows_update against torch indexing, both memory formats: gather, clear, overwrite, add -
+    exact (no arithmetic but one add), untouched voxels untouched."""
+    g = torch.Generator().manual_seed(C + SB)
+    grad = torch.randn(SB, C, *dims, generator=g).cuda()
+    if cl3d:
+        grad = grad.contiguous(memory_format=torch.channels_last_3d)
+    V = dims[0] * dims[1] * dims[2]
+    flat = lambda t: t.permute(0, 2, 3, 4, 1).reshape(SB * V, C)        # (scene * V + voxel, C) copy
+    for n in (0, 1, 31, 32, 33, SB * V // 3, SB * V):
+        idx = torch.randperm(SB * V, generator=g)[:n].sort()[0].cuda()
+        rows = ops.rows_gather(grad, idx)
+        assert torch.equal(rows, flat(grad)[idx])
+        upd = torch.randn(n, C, generator=g).cuda()
+        ref = flat(grad).clone()
+        work = grad.clone(memory_format=torch.preserve_format)
+        ops.rows_update(work, idx, upd, add=True)
+        ref[idx] += upd
+        assert torch.equal(flat(work), ref)
+        ops.rows_update(work, idx, upd, add=False)
+        ref[idx] = upd
+        assert torch.equal(flat(work), ref)
+        ops.rows_update(work, idx, None)
+        ref[idx] = 0
+        assert torch.equal(flat(work), ref)
+        assert work.stride() == grad.stride()
+
+
+@pytest.mark.parametrize("C,dims,SB,cl3d,world", [(128, (9, 7, 11), 2, False, 3), (128, (9, 7, 11), 1, True, 8),
+                                                  (64, (5, 6, 7), 1, False, 2), (12, (4, 4, 5), 3, False, 5),
+                                                  (128, (40, 40, 40), 1, False, 8)])
+def test_voxel_rows_merge_sums_the_lists_in_rank_order(ops, C, dims, SB, cl3d, world):
+    """nrf_rows_merge: every voxel some rank lists = ((0 + r_0) + r_1) + .. in rank order (bit-exact against the same
+    order in torch), everything else untouched; ragged lists, empty ranks, voxel counts that are not multiples of 32."""
+    g = torch.Generator().manual_seed(C + world)
+    V = dims[0] * dims[1] * dims[2]
+    total = SB * V
+    grad = torch.randn(SB, C, *dims, generator=g).cuda()
+    if cl3d:
+        grad = grad.contiguous(memory_format=torch.channels_last_3d)
+    flat = lambda t: t.permute(0, 2, 3, 4, 1).reshape(total, C)
+    counts = [int(torch.randint(0, max(2, total // 4), (1,), generator=g)) for _ in range(world)]
+    counts[world // 2] = 0
+    counts[0] = min(total, max(counts[0], 40))
+    cap = max(counts) + 3
+    all_idx = torch.zeros(world, cap, dtype=torch.int64)
+    all_rows = torch.randn(world, cap, C, generator=g)
+    for r in range(world):
+        all_idx[r, :counts[r]] = torch.randperm(total, generator=g)[:counts[r]].sort()[0]
+    ref = flat(grad).cpu().clone()
+    listed = torch.zeros(total, dtype=torch.bool)
+    for r in range(world):
+        listed[all_idx[r, :counts[r]]] = True
+    ref[listed] = 0.0
+    for r in range(world):
+        ref[all_idx[r, :counts[r]]] += all_rows[r, :counts[r]]
+    work = grad.clone(memory_format=torch.preserve_format)
+    ops.rows_merge(work, all_rows.cuda(), all_idx.cuda(), counts)
+    assert torch.equal(flat(work).cpu(), ref)
