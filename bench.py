@@ -552,7 +552,7 @@ def other_configs(mods, args, dev, rank, world):
             del g_local
             rec["workload"] = rec["workload"].replace("dense all-reduce of the 4.1 GB volume gradient",
                                                       "sparse exchange of the touched voxel rows of the volume gradient")
-            del g, g0
+            del g
         out["config5"] = rec
         del c
         release()

@@ -144,9 +144,11 @@ int nrf_rows_update(float* grad, int channels_first, int C, int64_t V, const int
                     const float* rows, int add, void* stream);
 /* All ranks' lists at once: rows (world, cap, C), idx (world, cap), counts_host[r] valid entries of rank r (HOST array).
  * Every voxel some rank lists is set to the sum of its rows in rank order (0.0 + r_0 + r_1 + ..: the same bits on every
- * rank); other voxels keep their value.  One pass, the volume is written once per touched 32-voxel tile, never read. */
+ * rank); other voxels keep their value.  One pass, the volume is written once per touched 32-voxel tile, never read.
+ * unlisted_are_zero != 0: the caller knows every unlisted voxel of `grad` holds 0 (a gradient fresh from the scatter, whose
+ * untouched voxels are zero-filled): touched tiles are then written whole - full 32 B sectors instead of 4 B pieces. */
 int nrf_rows_merge(float* grad, int channels_first, int C, int64_t V, int SB, const float* rows, const int64_t* idx,
-                   int64_t cap, const int64_t* counts_host, int world, void* stream);
+                   int64_t cap, const int64_t* counts_host, int world, int unlisted_are_zero, void* stream);
 
 /* ---- alpha compositing (neural_rendering.py:239-243,316-359) ---------------------------------
  * field_out (N, ldo) raw; heads sigmoid(rgb), relu(sigma) (models_embed.py:444-466) applied here.

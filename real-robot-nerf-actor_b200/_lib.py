@@ -90,7 +90,7 @@ _SIGNATURES["nrf_scatter_volume_grad_merged"] = [_p, _i, _i, _p, _i, _p, _i, _p,
                                                  _p, _p, _p]
 _SIGNATURES["nrf_rows_gather"] = [_p, _i, _i, _i64, _p, _i64, _p, _p]
 _SIGNATURES["nrf_rows_update"] = [_p, _i, _i, _i64, _p, _i64, _p, _i, _p]
-_SIGNATURES["nrf_rows_merge"] = [_p, _i, _i, _i64, _i, _p, _p, _i64, _p, _i, _p]
+_SIGNATURES["nrf_rows_merge"] = [_p, _i, _i, _i64, _i, _p, _p, _i64, _p, _i, _i, _p]
 _SIGNATURES["nrf_timing_begin"] = []
 _SIGNATURES["nrf_timing_end"] = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
 EXPORTS = sorted(list(_SIGNATURES) + ["nrf_version", "nrf_last_error", "nrf_wgrad_workspace_bytes",

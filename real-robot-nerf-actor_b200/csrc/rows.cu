@@ -99,6 +99,7 @@ struct MergeArgs {
   const float* rows; const int64_t* idx; int64_t cap;
   int64_t cnt[kMergeMaxWorld];
   int world, C, channels_first;
+  int whole_tiles;           // unlisted voxels are known to be zero: write whole 32-voxel tiles (full 32 B sectors)
   int64_t V, total;          // voxels per scene, SB * V
 };
 
@@ -157,14 +158,14 @@ __global__ void __launch_bounds__(128) rows_merge_kernel(float* __restrict__ gra
     }
     if (a.channels_first) {
       const int64_t f = f0 + lane;
-      if (f < a.total && ((listed >> lane) & 1u)) {        // voxels nobody lists keep their value
+      if (f < a.total && (a.whole_tiles || ((listed >> lane) & 1u))) {   // voxels nobody lists keep their value
         const int64_t scene = f / a.V;
         float* g = grad + scene * C * a.V + (f - scene * a.V);
         for (int c = warp; c < C; c += 4) g[(int64_t)c * a.V] = acc[lane * ldt + c];
       }
     } else {
       for (int v = warp; v < 32 && f0 + v < a.total; v += 4)
-        if ((listed >> v) & 1u)
+        if (a.whole_tiles || ((listed >> v) & 1u))
           for (int c = lane; c < C; c += 32) grad[(f0 + v) * C + c] = acc[v * ldt + c];
     }
     __syncthreads();
@@ -212,7 +213,8 @@ extern "C" int nrf_rows_update(float* grad, int channels_first, int C, int64_t V
 }
 
 extern "C" int nrf_rows_merge(float* grad, int channels_first, int C, int64_t V, int SB, const float* rows,
-                              const int64_t* idx, int64_t cap, const int64_t* counts_host, int world, void* stream) {
+                              const int64_t* idx, int64_t cap, const int64_t* counts_host, int world,
+                              int unlisted_are_zero, void* stream) {
   NRF_REQUIRE(grad && rows && idx && counts_host && C > 0 && C % 4 == 0 && V > 0 && SB > 0 && cap > 0, NRF_EINVAL,
               "nrf_rows_merge: bad arguments");
   NRF_REQUIRE(world >= 1 && world <= kMergeMaxWorld, NRF_ENOSUP, "nrf_rows_merge: world=%d > %d", world, kMergeMaxWorld);
@@ -220,7 +222,7 @@ extern "C" int nrf_rows_merge(float* grad, int channels_first, int C, int64_t V,
   MergeArgs a;
   memset(&a, 0, sizeof(a));
   a.rows = rows; a.idx = idx; a.cap = cap; a.world = world; a.C = C; a.channels_first = channels_first;
-  a.V = V; a.total = (int64_t)SB * V;
+  a.V = V; a.total = (int64_t)SB * V; a.whole_tiles = unlisted_are_zero != 0;
   int64_t n = 0;
   for (int r = 0; r < world; ++r) {
     NRF_REQUIRE(counts_host[r] >= 0 && counts_host[r] <= cap, NRF_EINVAL, "nrf_rows_merge: counts[%d] out of range", r);

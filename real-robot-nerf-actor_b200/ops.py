@@ -302,16 +302,18 @@ def rows_update(grad, idx, rows=None, add=True):
 
 
 @_on_tensor_device
-def rows_merge(grad, all_rows, all_idx, counts):
+def rows_merge(grad, all_rows, all_idx, counts, unlisted_are_zero=False):
     """grad[voxel] = sum in rank order of the ranks' rows for every listed voxel (nrf_rows_merge).  all_rows
-    (world, cap, C) fp32, all_idx (world, cap) int64 ascending per rank, counts: list of world ints."""
+    (world, cap, C) fp32, all_idx (world, cap) int64 ascending per rank, counts: list of world ints.
+    unlisted_are_zero: every voxel of `grad` that no list names is known to hold 0 (whole-tile writes)."""
     assert all_idx.dtype == torch.int64 and all_idx.is_contiguous() and all_rows.is_contiguous()
     cf, Cc, V = _rows_args(grad, all_idx)
     world, cap = all_idx.shape
     assert all_rows.shape == (world, cap, Cc) and all_rows.dtype == torch.float32 and len(counts) == world
     cnt = (C.c_int64 * world)(*[int(c) for c in counts])
     check(_lib.load().nrf_rows_merge(ptr(grad), cf, Cc, V, grad.shape[0], ptr(all_rows), ptr(all_idx), cap,
-                                     C.cast(cnt, C.c_void_p), world, stream_ptr()), "nrf_rows_merge")
+                                     C.cast(cnt, C.c_void_p), world, int(bool(unlisted_are_zero)), stream_ptr()),
+          "nrf_rows_merge")
     return grad
 
 

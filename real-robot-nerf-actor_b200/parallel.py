@@ -129,7 +129,7 @@ def sparse_allreduce_volume_grad(grad: torch.Tensor, group=None, counts: torch.T
         touched = torch.stack([(v != 0).any(1 - vdim) for v in views]).reshape(-1)   # (SB * V)
     idx = touched.nonzero().squeeze(1)                                           # flat (scene * V + voxel), ascending
     if grad.is_cuda and C % 4 == 0:
-        return _sparse_allreduce_rows_cuda(grad, idx, group)
+        return _sparse_allreduce_rows_cuda(grad, idx, group, exact_touched=True)
     counts = torch.zeros(world, device=grad.device, dtype=torch.int64)
     counts[rank] = idx.numel()
     dist.all_reduce(counts, group=group)
@@ -171,7 +171,7 @@ def sparse_allreduce_volume_grad(grad: torch.Tensor, group=None, counts: torch.T
     return {"rows": counts, "bytes": int(cap * world * (C * grad.element_size() + 8))}
 
 
-def _sparse_allreduce_rows_cuda(grad, idx, group):
+def _sparse_allreduce_rows_cuda(grad, idx, group, exact_touched=False):
     """The device path of sparse_allreduce_volume_grad: nrf_rows_gather -> all_gather of (rows, indices) ->
     nrf_rows_merge (every voxel some rank lists = the sum of its rows in rank order, own rows included: the same bits
     on every rank; the volume is written once per touched tile and never read).  One host synchronisation (the row
@@ -193,7 +193,9 @@ def _sparse_allreduce_rows_cuda(grad, idx, group):
     all_idx = torch.empty((world, cap), device=grad.device, dtype=torch.int64)
     dist.all_gather_into_tensor(all_rows, my_rows, group=group)
     dist.all_gather_into_tensor(all_idx, my_idx, group=group)
-    ops.rows_merge(grad, all_rows, all_idx, counts)       # every listed voxel = its rows summed in rank order, written once
+    # every listed voxel = its rows summed in rank order, written once; with the touched set from the scatter's own
+    # counts every other voxel of this rank's gradient is a zero the scatter wrote: whole tiles, full sectors
+    ops.rows_merge(grad, all_rows, all_idx, counts, unlisted_are_zero=exact_touched)
     return {"rows": counts, "bytes": int(cap * world * (C * 4 + 8))}
 
 
@@ -232,7 +234,7 @@ def sparse_allreduce_phases(grad, counts, group=None) -> dict:
     all_idx = torch.empty((world, cap), device=grad.device, dtype=torch.int64)
     phase("all_gather_rows", lambda: dist.all_gather_into_tensor(all_rows, my_rows, group=group))
     phase("all_gather_idx", lambda: dist.all_gather_into_tensor(all_idx, my_idx, group=group))
-    phase("rows_merge", lambda: ops.rows_merge(grad, all_rows, all_idx, cnt))
+    phase("rows_merge", lambda: ops.rows_merge(grad, all_rows, all_idx, cnt, unlisted_are_zero=True))
     out["rows"] = cnt
     return out
 

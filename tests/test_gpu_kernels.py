@@ -727,3 +727,13 @@ def test_voxel_rows_merge_sums_the_lists_in_rank_order(ops, C, dims, SB, cl3d, w
     work = grad.clone(memory_format=torch.preserve_format)
     ops.rows_merge(work, all_rows.cuda(), all_idx.cuda(), counts)
     assert torch.equal(flat(work).cpu(), ref)
+    # whole-tile mode: the caller vouches that every unlisted voxel holds 0 (a gradient fresh from the scatter)
+    sparse = grad.clone(memory_format=torch.preserve_format)
+    fl = flat(sparse)
+    fl[~listed.cuda()] = 0.0
+    sparse = fl.reshape(SB, *dims, C).permute(0, 4, 1, 2, 3)
+    sparse = sparse.contiguous(memory_format=torch.channels_last_3d) if cl3d else sparse.contiguous()
+    ref0 = ref.clone()
+    ref0[~listed] = 0.0
+    ops.rows_merge(sparse, all_rows.cuda(), all_idx.cuda(), counts, unlisted_are_zero=True)
+    assert torch.equal(flat(sparse).cpu(), ref0)
