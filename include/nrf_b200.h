@@ -99,6 +99,15 @@ int nrf_encode_points(const float* rays, const float* z, int R, int K, int rays_
                       const float* vol_cl, int SB, int C, int S0, int S1, int S2,
                       const float* bounds_host, int num_freqs, float freq_factor,
                       void* out, int ld_out, int out_bf16, float* points_out, void* stream);
+/* The same, and touch_flags[g] = 1 if any of the samples 32 g .. 32 g + 31 has a trilinear corner inside the grid, else 0
+ * ((N + 31) / 32 bytes, every one written).  A sample without such a corner has an all-zero latent (zeros padding of
+ * F.grid_sample, models_embed.py:275) and its dL/dlatent is never used: nrf_mlp_bwd skips whole sample tiles by these
+ * flags (NrfMlpGrads.touch_flags).  In BASELINE config 2 three rays in four miss the 1 m box altogether. */
+int nrf_encode_points_touch(const float* rays, const float* z, int R, int K, int rays_per_scene,
+                            const float* vol_cl, int SB, int C, int S0, int S1, int S2,
+                            const float* bounds_host, int num_freqs, float freq_factor,
+                            void* out, int ld_out, int out_bf16, float* points_out, uint8_t* touch_flags,
+                            void* stream);
 
 /* ---- volume gradient: transpose of the trilinear gather (autograd of models_embed.py:275) ----
  * dlatent (N, ld) fp32; grad_cl channels-last (SB,S0,S1,S2,C), accumulated into (caller zeroes). */
@@ -267,6 +276,9 @@ typedef struct {
                           (the MLP's second return value, resnetfc.py:192-195, composited instead of the embedding when
                           ret_last_feat: neural_rendering.py:332-334); nrf_mlp_bwd_layered only.  After
                           nrf_mlp_fwd_layered the last layer of `acts` holds x_nb itself, (N,d_hidden) operand-typed. */
+  const void* touch_flags; /* NULL, or the (N + 31) / 32 bytes nrf_encode_points_touch wrote for these N samples: dlatent
+                          is then only computed for 128-sample tiles with a flag set; the rows of the other tiles are
+                          left unwritten (nothing reads them: the volume scatter visits in-grid corners only) */
 } NrfMlpGrads;
 
 /* Sizes (bytes) of the caller-provided buffers for a given shape / precision. */

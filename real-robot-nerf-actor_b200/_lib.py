@@ -50,7 +50,8 @@ class NrfMlpParams(C.Structure):
 class NrfMlpGrads(C.Structure):
     _fields_ = [("lin_in_w", c_ptr), ("lin_in_b", c_ptr), ("lin_out_w", c_ptr), ("lin_out_b", c_ptr),
                 ("fc0_w", _PA), ("fc0_b", _PA), ("fc1_w", _PA), ("fc1_b", _PA),
-                ("lin_z_w", _PA), ("lin_z_b", _PA), ("deterministic", C.c_int), ("d_last", c_ptr)]
+                ("lin_z_w", _PA), ("lin_z_b", _PA), ("deterministic", C.c_int), ("d_last", c_ptr),
+                ("touch_flags", c_ptr)]
 
 
 class NrfMlpSizes(C.Structure):
@@ -88,6 +89,7 @@ _SIGNATURES["nrf_render_loss"] = [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _p, 
 _SIGNATURES["nrf_voxelize"] = [_p, _p, _i, _i, _i, _p, _i, _p, _p, _p]
 _SIGNATURES["nrf_scatter_volume_grad_merged"] = [_p, _i, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i,
                                                  _p, _p, _p]
+_SIGNATURES["nrf_encode_points_touch"] = [_p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _f, _p, _i, _i, _p, _p, _p]
 _SIGNATURES["nrf_rows_gather"] = [_p, _i, _i, _i64, _p, _i64, _p, _p]
 _SIGNATURES["nrf_rows_update"] = [_p, _i, _i, _i64, _p, _i64, _p, _i, _p]
 _SIGNATURES["nrf_rows_merge"] = [_p, _i, _i, _i64, _i, _p, _p, _i64, _p, _i, _i, _p]

@@ -91,6 +91,7 @@ struct EncodeArgs {
   void* out;
   int ld_out;
   float* points;
+  uint8_t* touch;   // optional: one byte per group of 32 consecutive samples, 1 if any of them has a corner inside the grid
   int fma;          // corner accumulation out = fma(v, w, out) (ATen's CUDA grid_sampler_3d) instead of the separately
                     // rounded multiply and add of ATen's CPU kernel (the default)
 };
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(256) encode_points_w32_kernel(EncodeArgs a) {
       }
     }
     const unsigned touch = __ballot_sync(0xffffffffu, valid && trilinear_touches(ts, a.S0, a.S1, a.S2));
+    if (a.touch && lane == 0) a.touch[grp] = touch != 0u;
     const int scene_l = r / a.rays_per_scene;
     const int cnt = (int)((N - grp * kWarp) < kWarp ? (N - grp * kWarp) : kWarp);
     for (int s = 0; s < cnt; ++s) {
@@ -411,10 +413,10 @@ extern "C" int nrf_volume_to_channels_first(const float* src, float* dst, int SB
   return volume_transpose(src, dst, SB, C, V, false, stream);
 }
 
-extern "C" int nrf_encode_points(const float* rays, const float* z, int R, int K, int rays_per_scene,
-                                 const float* vol_cl, int SB, int C, int S0, int S1, int S2,
-                                 const float* bounds_host, int num_freqs, float freq_factor, void* out,
-                                 int ld_out, int out_bf16, float* points_out, void* stream) {
+static int encode_points_impl(const float* rays, const float* z, int R, int K, int rays_per_scene,
+                              const float* vol_cl, int SB, int C, int S0, int S1, int S2,
+                              const float* bounds_host, int num_freqs, float freq_factor, void* out,
+                              int ld_out, int out_bf16, float* points_out, uint8_t* touch_flags, void* stream) {
   NRF_REQUIRE(rays && z && vol_cl && bounds_host && out, NRF_EINVAL, "nrf_encode_points: null pointer");
   NRF_REQUIRE(R > 0 && K > 0 && rays_per_scene > 0 && R == SB * rays_per_scene, NRF_EINVAL,
               "nrf_encode_points: R=%d must equal SB*rays_per_scene=%d*%d", R, SB, rays_per_scene);
@@ -428,6 +430,7 @@ extern "C" int nrf_encode_points(const float* rays, const float* z, int R, int K
   a.num_freqs = num_freqs; a.freq_factor = freq_factor;
   a.out = out; a.ld_out = ld_out; a.points = points_out;
   a.fma = (out_bf16 >> 8) & 1;
+  a.touch = touch_flags;
   out_bf16 &= 0xff;
   int64_t N = (int64_t)R * K;
   int threads = 256;
@@ -442,6 +445,8 @@ extern "C" int nrf_encode_points(const float* rays, const float* z, int R, int K
     else if (out_bf16) encode_points_w32_kernel<__nv_bfloat16><<<blocks, threads, 0, as_stream(stream)>>>(a);
     else encode_points_w32_kernel<float><<<blocks, threads, 0, as_stream(stream)>>>(a);
   } else {                                     // any other shape: one warp per sample
+    if (touch_flags)                           // (this kernel does not report them: every group counts as touching)
+      NRF_CUDA_OK(cudaMemsetAsync(touch_flags, 1, (size_t)((N + 31) / 32), as_stream(stream)));
     int64_t want = (N + 7) / 8;
     int max_blocks = sm_count() * 16;
     int blocks = (int)(want < max_blocks ? want : max_blocks);
@@ -452,6 +457,23 @@ extern "C" int nrf_encode_points(const float* rays, const float* z, int R, int K
   }
   NRF_LAUNCH_OK();
   return NRF_OK;
+}
+
+extern "C" int nrf_encode_points(const float* rays, const float* z, int R, int K, int rays_per_scene,
+                                 const float* vol_cl, int SB, int C, int S0, int S1, int S2,
+                                 const float* bounds_host, int num_freqs, float freq_factor, void* out,
+                                 int ld_out, int out_bf16, float* points_out, void* stream) {
+  return encode_points_impl(rays, z, R, K, rays_per_scene, vol_cl, SB, C, S0, S1, S2, bounds_host, num_freqs, freq_factor,
+                            out, ld_out, out_bf16, points_out, nullptr, stream);
+}
+
+extern "C" int nrf_encode_points_touch(const float* rays, const float* z, int R, int K, int rays_per_scene,
+                                       const float* vol_cl, int SB, int C, int S0, int S1, int S2,
+                                       const float* bounds_host, int num_freqs, float freq_factor, void* out,
+                                       int ld_out, int out_bf16, float* points_out, uint8_t* touch_flags,
+                                       void* stream) {
+  return encode_points_impl(rays, z, R, K, rays_per_scene, vol_cl, SB, C, S0, S1, S2, bounds_host, num_freqs, freq_factor,
+                            out, ld_out, out_bf16, points_out, touch_flags, stream);
 }
 
 extern "C" int nrf_scatter_volume_grad(const float* rays, const float* z, int R, int K,

@@ -79,7 +79,10 @@ static inline OpFmt op_fmt(int precision) {
   return f;
 }
 constexpr OpFmt kFmtBf16 = {0, 0, 0};
-int gemm_tc_launch(const NrfGemm& g, OpFmt fmt, cudaStream_t stream);
+// live (optional, N = 128 GEMMs without epilogue inputs): live[0] row tiles of 128 rows to compute, indices live[1..]
+int gemm_tc_launch(const NrfGemm& g, OpFmt fmt, cudaStream_t stream, const int32_t* live = nullptr);
+// builds such a list from one flag byte per 32 rows (nrf_encode_points_touch)
+int live_tiles_launch(const void* flags, int64_t n_rows, int32_t* live, cudaStream_t stream);
 int gemm_simt_launch(const NrfGemm& g, cudaStream_t stream);
 int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
                     int k_valid, float* dW, int ldw, float* dbias, void* workspace, OpFmt fmt, cudaStream_t stream);

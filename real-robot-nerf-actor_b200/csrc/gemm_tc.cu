@@ -43,6 +43,8 @@ struct FwdArgs {
   int dbg;                   // NRF_DBG experiments: 1 = no TMA stores, 2 = no epilogue at all (timing only!)
   uint32_t idesc;            // tcgen05 instruction descriptor (tile shape + the operand formats, OpFmt)
   int io_half;               // resid / out_act / out_act2 are fp16 (1) or bf16 (0)
+  const int32_t* live;       // optional (single-CTA kernels, one n tile): live[0] = number of row tiles to compute,
+                             // live[1 + i] = their indices, ascending; the other row tiles are left unwritten
 };
 // 16-bit operand <-> fp32 in either format (warp-uniform run-time choice: this is the layer-by-layer chain, not the
 // fused kernel's hot loop)
@@ -90,10 +92,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const bool cta_leader = crank == 0;
   const int unit = CG == 2 ? blockIdx.x / 2 : blockIdx.x, n_units = CG == 2 ? gridDim.x / 2 : gridDim.x;
-  const int work = (CG == 2 ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+  const int32_t* live = CG == 1 ? a.live : nullptr;
+  const int work = live ? __ldg(live) : (CG == 2 ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
   const int n_iter = unit < work ? (work - unit + n_units - 1) / n_units : 0;
   auto tile_of = [&](int it, int& m_blk, int& n_blk) {
     int t = unit + it * n_units;
+    if (live) { m_blk = __ldg(live + 1 + t); n_blk = 0; return; }
     m_blk = CG == 2 ? 2 * (t / n_tiles) + (int)crank : t / n_tiles;
     n_blk = t % n_tiles;
   };
@@ -602,8 +606,45 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 }
 
 // ----------------------------------------------------------------------------------- host side
+// Row tiles (128 rows) that have work, from one flag byte per 32 rows: live[0] = count, live[1..] = tile indices.
+__global__ void __launch_bounds__(1024) live_tiles_kernel(const uint8_t* __restrict__ flags, int64_t n_groups, int n_tiles,
+                                                          int32_t* __restrict__ live) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x % 32, wid = threadIdx.x / 32;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < n_tiles; t0 += 1024) {
+    const int t = t0 + threadIdx.x;
+    bool on = false;
+    if (t < n_tiles)
+      for (int j = 0; j < 4; ++j) {
+        const int64_t gidx = (int64_t)t * 4 + j;
+        on = on || (gidx < n_groups && flags[gidx] != 0);
+      }
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) warp_tot[wid] = __popc(m);
+    __syncthreads();
+    int before = base_s;
+    for (int w = 0; w < wid; ++w) before += warp_tot[w];
+    if (on) live[1 + before + __popc(m & ((1u << lane) - 1u))] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 32; ++w) tot += warp_tot[w]; base_s += tot; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) live[0] = base_s;
+}
+
+int live_tiles_launch(const void* flags, int64_t n_rows, int32_t* live, cudaStream_t stream) {
+  const int n_tiles = (int)((n_rows + kTileM - 1) / kTileM);
+  LaunchScope ls_(NRF_CAT_MISC, stream);
+  live_tiles_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const uint8_t*>(flags), (n_rows + 31) / 32, n_tiles, live);
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
+
 template <int BN, int CG, int EPI>
-static int launch_fwd(const NrfGemm& g, OpFmt fmt, cudaStream_t stream) {
+static int launch_fwd(const NrfGemm& g, OpFmt fmt, cudaStream_t stream, const int32_t* live = nullptr) {
   using Cfg = FwdCfg<BN, CG>;
   const int a_rows = kTileM, b_rows = BN / CG;   // TMA box heights
   CUtensorMap tmA[3], tmB, tmMask, tmResid, tmOutA, tmOutB, tmOutF;
@@ -644,6 +685,7 @@ static int launch_fwd(const NrfGemm& g, OpFmt fmt, cudaStream_t stream) {
   { const char* e = getenv("NRF_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.idesc = make_idesc(kTileM * CG, BN, 0, 0, fmt.a_half, fmt.b_half);
   a.io_half = fmt.io_half;
+  a.live = live;
   // per launch: the attribute is per (function, device), see mlp_fused_launch
   NRF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   int m_tiles = (g.M + kTileM - 1) / kTileM, n_tiles = g.N / BN;
@@ -669,7 +711,7 @@ static int launch_fwd(const NrfGemm& g, OpFmt fmt, cudaStream_t stream) {
   return NRF_OK;
 }
 
-int gemm_tc_launch(const NrfGemm& g, OpFmt fmt, cudaStream_t stream) {
+int gemm_tc_launch(const NrfGemm& g, OpFmt fmt, cudaStream_t stream, const int32_t* live) {
   NRF_REQUIRE(fmt.a_half == fmt.b_half, NRF_ENOSUP, "gemm_tc: mixed fp16 / bf16 operands are not executable");
   NRF_REQUIRE(g.K[0] > 0 && g.K[0] % kTileK == 0 && g.K[1] % kTileK == 0 && g.K[2] % kTileK == 0, NRF_ENOSUP,
               "gemm_tc: K = %d,%d,%d must be multiples of 64", g.K[0], g.K[1], g.K[2]);
@@ -699,8 +741,10 @@ int gemm_tc_launch(const NrfGemm& g, OpFmt fmt, cudaStream_t stream) {
       default: return launch_fwd<256, 2, -1>(g, fmt, stream);
     }
   }
+  NRF_REQUIRE(!live || (BN == 128 && g.N == 128 && !g.mask_src && !g.resid), NRF_ENOSUP,
+              "gemm_tc: a live-tile list needs the single-CTA kernel with one n tile and no epilogue inputs");
   if (BN == 256) return launch_fwd<256, 1, -1>(g, fmt, stream);
-  return launch_fwd<128, 1, -1>(g, fmt, stream);
+  return launch_fwd<128, 1, -1>(g, fmt, stream, live);
 }
 
 template <int BK_, int CG>

@@ -532,7 +532,17 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
         for (int b = 0; b < L.nz; ++b) set_a(g, b, gx(b), L.H, L.H);
         g.B = W + L.WzcatT; g.ldb = L.nz * L.H;
         g.out_f32 = dlatent; g.ldo = L.C;
-        TRY(run_gemm(g, precision, true, s));
+        // dL/dz only for the 128-sample tiles in which some sample has a corner inside the grid (the others' rows are
+        // never read: the scatter visits in-grid corners only); the list lives in the idle split-reduction workspace
+        const int64_t n_tiles = (N + 127) / 128;
+        const int64_t live_off = 65536;
+        if (gr->touch_flags && g.N == 128 && live_off + (n_tiles + 1) * 4 <= fixed) {
+          int32_t* live = reinterpret_cast<int32_t*>(sc + live_off);
+          TRY(live_tiles_launch(gr->touch_flags, N, live, s));
+          TRY(gemm_tc_launch(g, kFmtBf16, s, live));
+        } else {
+          TRY(run_gemm(g, precision, true, s));
+        }
         return NRF_OK;
       }
     }

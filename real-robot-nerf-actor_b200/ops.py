@@ -203,8 +203,10 @@ GATHER_FMA = False      # True: accumulate the trilinear corners with FMAs (ATen
 
 @_on_tensor_device
 def encode_points(rays, z, rays_per_scene, vol_cl, bounds, num_freqs=6, freq_factor=1.5, ld_out=None,
-                  precision=NRF_PREC_BF16, want_points=False, out=None, fma=None):
-    """Field-input rows [latent | PE | viewdir | 0] for every sample (see nrf_encode_points)."""
+                  precision=NRF_PREC_BF16, want_points=False, out=None, fma=None, want_touch=False):
+    """Field-input rows [latent | PE | viewdir | 0] for every sample (see nrf_encode_points).
+    want_touch: also return one uint8 per 32 consecutive samples, 1 if any of them has a corner inside the grid
+    (nrf_encode_points_touch; what FieldMLP.backward(touch=...) skips whole dL/dlatent tiles by)."""
     rays = _f32(rays, "rays")
     z = _f32(z, "z")
     vol_cl = _f32(vol_cl, "volume")
@@ -217,10 +219,17 @@ def encode_points(rays, z, rays_per_scene, vol_cl, bounds, num_freqs=6, freq_fac
         out = torch.empty(R * K, ld_out, device=rays.device, dtype=act_dtype(precision))
     pts = torch.empty(R * K, 3, device=rays.device, dtype=torch.float32) if want_points else None
     bh = _bounds_host(bounds)
+    kind = _OUT_KIND[out.dtype] | (0x100 if (GATHER_FMA if fma is None else fma) else 0)
+    if want_touch:
+        touch = torch.empty((R * K + 31) // 32, device=rays.device, dtype=torch.uint8)
+        check(_lib.load().nrf_encode_points_touch(ptr(rays), ptr(z), R, K, rays_per_scene, ptr(vol_cl), SB, Cc, S0, S1,
+                                                  S2, C.cast(bh, C.c_void_p), num_freqs, float(freq_factor), ptr(out),
+                                                  ld_out, kind, ptr(pts), ptr(touch), stream_ptr()),
+              "nrf_encode_points_touch")
+        return (out, pts, touch) if want_points else (out, touch)
     check(_lib.load().nrf_encode_points(ptr(rays), ptr(z), R, K, rays_per_scene, ptr(vol_cl), SB, Cc, S0, S1,
                                         S2, C.cast(bh, C.c_void_p), num_freqs, float(freq_factor), ptr(out),
-                                        ld_out, _OUT_KIND[out.dtype] | (0x100 if (GATHER_FMA if fma is None else fma) else 0),
-                                        ptr(pts), stream_ptr()),
+                                        ld_out, kind, ptr(pts), stream_ptr()),
           "nrf_encode_points")
     return (out, pts) if want_points else out
 
@@ -616,10 +625,13 @@ class FieldMLP:
         return acts[off:off + N * H * es].view(dt).view(N, H)
 
     def backward(self, field_in, acts, d_field, grads: dict, scratch=None, deterministic=False, layered=False,
-                 d_last=None):
+                 d_last=None, touch=None):
         """Accumulates parameter grads into `grads` (same keys as params); returns dlatent (N,C).
         deterministic: ordered (bit-reproducible) reduction of the weight-gradient sample splits.
-        d_last (N, d_hidden): gradient w.r.t. the last residual stream (layered chain only)."""
+        d_last (N, d_hidden): gradient w.r.t. the last residual stream (layered chain only).
+        touch: the uint8 flags of encode_points(want_touch=True) for these samples: dlatent is then only computed for
+        128-sample tiles with a sample inside the grid - rows of the other tiles are UNINITIALISED (the volume scatter
+        never reads them)."""
         N = field_in.shape[0]
         dev = field_in.device
         d_latent = self.dims[1]
@@ -633,6 +645,9 @@ class FieldMLP:
         if d_last is not None:
             assert d_last.shape == (N, self.dims[2]) and d_last.dtype == grad_dtype(self.precision) and d_last.is_contiguous()
             g.d_last = d_last.data_ptr()
+        if touch is not None:
+            assert touch.dtype == torch.uint8 and touch.is_contiguous() and touch.numel() == (N + 31) // 32
+            g.touch_flags = touch.data_ptr()
         lib = _lib.load()
         layered = layered or getattr(acts, "_nrf_layered", False)
         fn = lib.nrf_mlp_bwd_layered if layered else lib.nrf_mlp_bwd

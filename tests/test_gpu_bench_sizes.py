@@ -80,7 +80,13 @@ def _cuda_step(ren, vol_cuda, rays, noise, gt_rgb, gt_emb):
 # Measured (config-2 subset): fp32 2-4e-7 / dvoxel 2e-6; bf16x3 coarse <= 1.8e-5, fine 3-5e-4 and gradients 1e-2 (an
 # importance-sampling bin that flips moves one fine sample: a discontinuity of the reference algorithm itself; the
 # config-5 subset, without a flip, shows 5e-6 / 1e-4); fp16 4-15e-4 / 5e-2; bf16 3-9e-3 / 1.4e-1.
-_BOUNDS = {"fp32": (1e-4, 1e-4, 3e-4, 1e-3), "bf16x3": (1e-3, 1e-3, 2e-2, 2e-2), "fp16": (3e-3, 1e-3, 1.2e-1, 8e-2),
+# The oracle runs LIVE on the GPU box's host CPU here (its result depends on the host: MKL partitions the GEMMs by core
+# count, 16 on some boxes of the pool and 32 on others), and the reference's gradient is discontinuous in its own
+# rounding: one ReLU gate whose pre-activation sits within fp32 noise of zero moved dvoxel / dparam from 2e-6 / 1e-4 to
+# 1.5e-3 / 1.6e-3 on one box in ten runs (outputs 6e-6), the same floor DESIGN.md section 2 records for the oracle
+# against an fp64 evaluation of itself (3.7e-3).  The fp32 gradient bounds below are therefore 5e-3; the bounds against
+# the COMMITTED fixtures (tests/test_gpu_render.py, produced once by the reference) stay at 3e-4.
+_BOUNDS = {"fp32": (1e-4, 1e-4, 5e-3, 5e-3), "bf16x3": (1e-3, 1e-3, 2e-2, 2e-2), "fp16": (3e-3, 1e-3, 1.2e-1, 8e-2),
            "bf16": (1.5e-2, 5e-3, 2.5e-1, 2e-1)}
 
 

@@ -996,3 +996,49 @@ def test_cuda_graph_step_matches_the_eager_step(ops, NR):
         ren.nerf_model.mlp_coarse.lin_out.weight.mul_(0.5)
     a, b = step(vol, poses, focal, gt_rgb, gt_emb), eager(gt_rgb)
     assert float(a["loss"]) == float(b["loss"]) and float(a["loss"]) != float(ref["loss"])
+
+
+def test_dlatent_tile_skipping_changes_no_gradient(NR):
+    """Training encodes with nrf_encode_points_touch and the backward computes dL/dlatent only for 128-sample tiles in
+    which some sample has a corner inside the grid.  Nothing may change: the volume gradient is bit-identical to the
+    run that computes all tiles (the sorted scatter is reproducible; it never reads the skipped rows), the parameter
+    gradients agree to the order of their fp32 reductions - in a camera set-up where most rays miss the box, one where
+    all hit it, and with ragged tile tails."""
+    ops, U = load_pkg("ops"), load_pkg("utils")
+    for n_rays, near_far, focal in ((96, (1.2, 4.0), 153.0), (77, (2.4, 3.2), 500.0)):
+        res = {}
+        for skip in (True, False):
+            cfg = U.default_config(voxel_shape=24, n_coarse=64, n_fine=64, ray_chunk_size=n_rays, z_near=near_far[0],
+                                   z_far=near_far[1])
+            ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS), precision="bf16")
+            syn.init_mlp_(ren.nerf_model.mlp_coarse, seed=0)
+            ren = ren.cuda().train()
+            ren.skip_empty_latent_tiles = skip
+            vol = syn.make_volume(2, 128, 24, seed=1).cuda().requires_grad_(True)
+            poses = syn.arc_poses(2).cuda()
+            rays = U.gen_rays(poses, 128, 128, torch.tensor(focal).cuda(), *near_far).reshape(2, -1, 8)
+            rays = rays[:, syn.pick_ray_indices(128 * 128, n_rays, seed=4).cuda()].contiguous()
+            noise = {k: v.cuda() for k, v in syn.make_noise(2 * n_rays, 64, 64, seed=5).items()}
+            ren.encode(None, None, None, vol, None, None, None)
+            out = ren.forward_nerf(rays, noise=noise)
+            loss = sum((out[l]["rgb"] ** 2).mean() + 0.01 * (out[l]["embed"] ** 2).mean() + 0.1 * out[l]["depth"].mean()
+                       for l in ("coarse", "fine"))
+            loss.backward()
+            res[skip] = (vol.grad.clone(), {k: p.grad.clone() for k, p in ren.named_parameters() if p.grad is not None})
+        assert float(res[True][0].abs().sum()) > 0 or near_far[0] < 2
+        assert torch.equal(res[True][0], res[False][0])
+        for k in res[True][1]:
+            a, b = res[True][1][k].double(), res[False][1][k].double()
+            assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-12, k
+    # the flags themselves: a group is flagged iff one of its 32 samples gathers a non-zero latent from an all-ones volume
+    vol1 = torch.ones(2, 10, 10, 10, 128, device="cuda")
+    poses = syn.arc_poses(2).cuda()
+    rays = U.gen_rays(poses, 128, 128, torch.tensor(153.0).cuda(), 1.2, 4.0).reshape(2, -1, 8)
+    rays = rays[:, syn.pick_ray_indices(128 * 128, 50, seed=6).cuda()].reshape(-1, 8).contiguous()
+    z = ops.sample_coarse(rays, 48, None)
+    fin, touch = ops.encode_points(rays, z, 50, vol1, torch.tensor(syn.BOUNDS), want_touch=True)
+    lat = fin[:, :128].float().abs().sum(1)
+    pad = (-lat.numel()) % 32
+    ref = torch.cat([lat, lat.new_zeros(pad)]).reshape(-1, 32).gt(0).any(1)
+    assert touch.numel() == ref.numel() and torch.equal(touch.bool(), ref)
+    assert 0 < int(ref.sum()) < ref.numel()
