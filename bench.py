@@ -338,7 +338,7 @@ def run_ours(args):
     roof = {"bound": "tensor", "kernel": dom_name, "achieved": round(achieved, 1),
             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4),
             "traffic": FUSED_DRAM_BYTES_PER_LAUNCH if fused_n > 0 and args.workload == "config2" else None,
-            "traffic_source": "profiles/r01c_fused_ncu.md: dram__bytes_read.sum + dram__bytes_write.sum of the 4 "
+            "traffic_source": "profiles/r02b_fused_ncu.md: dram__bytes_read.sum + dram__bytes_write.sum of the 4 "
                               "mlp_fused_kernel launches of one config-2 step (ncu --set full), averaged per launch; "
                               "algorithmic bytes per launch = 5.13e9 (13.5 KB/eval forward, 12.7 KB/eval backward)",
             "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
