@@ -82,7 +82,8 @@ constexpr OpFmt kFmtBf16 = {0, 0, 0};
 // live (optional, N = 128 GEMMs without epilogue inputs): live[0] row tiles of 128 rows to compute, indices live[1..]
 int gemm_tc_launch(const NrfGemm& g, OpFmt fmt, cudaStream_t stream, const int32_t* live = nullptr);
 // builds such a list from one flag byte per 32 rows (nrf_encode_points_touch)
-int live_tiles_launch(const void* flags, int64_t n_rows, int32_t* live, cudaStream_t stream);
+// (one launch: 128-row tiles into live128 and / or 64-row blocks into live64)
+int live_tiles_launch(const void* flags, int64_t n_rows, int32_t* live128, int32_t* live64, cudaStream_t stream);
 int gemm_simt_launch(const NrfGemm& g, cudaStream_t stream);
 int wgrad_tc_launch(const void* G, int ldg, const void* A, int lda, int M, int N, int K, int n_valid,
                     int k_valid, float* dW, int ldw, float* dbias, void* workspace, OpFmt fmt, cudaStream_t stream);
@@ -109,6 +110,8 @@ struct WgmProblem {
   int k_tiles;
   float* dbias;            // += column sums of G (NULL: none)
   float* dbias2;           // a second bias with the same gradient (lin_in / lin_z[0]), or NULL
+  const int32_t* blocks;   // optional (dbias == NULL only): blocks[0] 64-sample blocks to visit, indices blocks[1..] ascending
+                           // (live_tiles_launch): the others contribute nothing (their A rows are all zero)
   WgmSlab slab[kWgmMaxSlabs];
 };
 struct WgmOperand { const void* base; int cols, ld; };

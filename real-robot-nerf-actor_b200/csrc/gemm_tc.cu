@@ -606,9 +606,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 }
 
 // ----------------------------------------------------------------------------------- host side
-// Row tiles (128 rows) that have work, from one flag byte per 32 rows: live[0] = count, live[1..] = tile indices.
-__global__ void __launch_bounds__(1024) live_tiles_kernel(const uint8_t* __restrict__ flags, int64_t n_groups, int n_tiles,
-                                                          int32_t* __restrict__ live) {
+// Row tiles (64 or 128 rows) that have work, from one flag byte per 32 rows: live[0] = count, live[1..] = tile indices.
+// Block 0 builds the list of 128-row tiles into live128, block 1 (if launched) the list of 64-row blocks into live64.
+__global__ void __launch_bounds__(1024) live_tiles_kernel(const uint8_t* __restrict__ flags, int64_t n_groups, int64_t n_rows,
+                                                          int32_t* __restrict__ live128, int32_t* __restrict__ live64) {
+  const int gpt = blockIdx.x == 0 && live128 ? 4 : 2;
+  int32_t* __restrict__ live = gpt == 4 ? live128 : live64;
+  const int n_tiles = (int)((n_rows + gpt * 32 - 1) / (gpt * 32));
   __shared__ int warp_tot[32];
   __shared__ int base_s;
   const int lane = threadIdx.x % 32, wid = threadIdx.x / 32;
@@ -618,8 +622,8 @@ __global__ void __launch_bounds__(1024) live_tiles_kernel(const uint8_t* __restr
     const int t = t0 + threadIdx.x;
     bool on = false;
     if (t < n_tiles)
-      for (int j = 0; j < 4; ++j) {
-        const int64_t gidx = (int64_t)t * 4 + j;
+      for (int j = 0; j < gpt; ++j) {
+        const int64_t gidx = (int64_t)t * gpt + j;
         on = on || (gidx < n_groups && flags[gidx] != 0);
       }
     const unsigned m = __ballot_sync(0xffffffffu, on);
@@ -635,10 +639,11 @@ __global__ void __launch_bounds__(1024) live_tiles_kernel(const uint8_t* __restr
   if (threadIdx.x == 0) live[0] = base_s;
 }
 
-int live_tiles_launch(const void* flags, int64_t n_rows, int32_t* live, cudaStream_t stream) {
-  const int n_tiles = (int)((n_rows + kTileM - 1) / kTileM);
+int live_tiles_launch(const void* flags, int64_t n_rows, int32_t* live128, int32_t* live64, cudaStream_t stream) {
+  NRF_REQUIRE(flags && (live128 || live64), NRF_EINVAL, "live_tiles: null pointer");
   LaunchScope ls_(NRF_CAT_MISC, stream);
-  live_tiles_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const uint8_t*>(flags), (n_rows + 31) / 32, n_tiles, live);
+  live_tiles_kernel<<<(live128 && live64) ? 2 : 1, 1024, 0, stream>>>(reinterpret_cast<const uint8_t*>(flags),
+                                                                      (n_rows + 31) / 32, n_rows, live128, live64);
   NRF_LAUNCH_OK();
   return NRF_OK;
 }

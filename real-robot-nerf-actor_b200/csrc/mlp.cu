@@ -520,11 +520,25 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
           if (z_here) gx_map[b + 1] = gxm;
           square(operand(gn(b), L.H, L.H), L.H, ax(b), gr->fc0_w[b], gr->fc0_b[b], nullptr);
         }
-        // the narrow problems after the 512 x 512 ones: problems of one shape in a row can share a wave (short passes)
+        // the narrow problems after the 512 x 512 ones: problems of one shape in a row can share a wave (short passes).
+        // lin_z[b >= 1] multiplies with the latent columns only, which are zero for every sample without a corner inside
+        // the grid: with the encode's touch flags those problems visit the flagged 64-sample blocks only (one block in
+        // five in the BASELINE camera set-up; they are bound by streaming G otherwise)
+        const int64_t n_t128 = (N + 127) / 128, n_b64 = (N + 63) / 64;
+        const int64_t blk_off = round_up(65536 + (n_t128 + 1) * 4, 256);
+        int32_t* blocks = nullptr;
+        int32_t* live = nullptr;                               // 128-sample tiles for the dL/dz GEMM below
+        if (gr->touch_flags && blk_off + (n_b64 + 1) * 4 <= fixed) {
+          if (L.nz > 0 && round_up(L.C, 128) == 128) live = reinterpret_cast<int32_t*>(sc + 65536);
+          for (int b = 1; b < L.nz; ++b)
+            if (gx_map[b] >= 0) blocks = reinterpret_cast<int32_t*>(sc + blk_off);
+          if (live || blocks) TRY(live_tiles_launch(gr->touch_flags, N, live, blocks, s));
+        }
         for (int b = L.nz - 1; b >= 1; --b)
           if (gx_map[b] >= 0) {
             field_in_problem(gx_map[b], b);
             if (!gr->fc1_w[b - 1]) h.prob[h.n_prob - 1].dbias = gr->lin_z_b[b];
+            if (!h.prob[h.n_prob - 1].dbias) h.prob[h.n_prob - 1].blocks = blocks;
           }
         field_in_problem(operand(gx(0), L.H, L.H), 0);
         TRY(wgrad_multi_launch(h, s));
@@ -534,15 +548,8 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
         g.out_f32 = dlatent; g.ldo = L.C;
         // dL/dz only for the 128-sample tiles in which some sample has a corner inside the grid (the others' rows are
         // never read: the scatter visits in-grid corners only); the list lives in the idle split-reduction workspace
-        const int64_t n_tiles = (N + 127) / 128;
-        const int64_t live_off = 65536;
-        if (gr->touch_flags && g.N == 128 && live_off + (n_tiles + 1) * 4 <= fixed) {
-          int32_t* live = reinterpret_cast<int32_t*>(sc + live_off);
-          TRY(live_tiles_launch(gr->touch_flags, N, live, s));
-          TRY(gemm_tc_launch(g, kFmtBf16, s, live));
-        } else {
-          TRY(run_gemm(g, precision, true, s));
-        }
+        if (live && g.N == 128) TRY(gemm_tc_launch(g, kFmtBf16, s, live));
+        else TRY(run_gemm(g, precision, true, s));
         return NRF_OK;
       }
     }

@@ -39,6 +39,7 @@ struct WgmDevProblem {
   int pair0;                                 // first CTA pair of this problem (several short problems share a wave)
   float* dbias;
   float* dbias2;
+  const int32_t* blocks;                     // optional list of the 64-sample blocks to visit ([0] = count)
   WgmSlab slab[kWgmMaxSlabs];
 };
 struct WgmArgs {
@@ -50,7 +51,7 @@ struct WgmArgs {
                // warps at all), 4 no reductions of the accumulator
 };
 
-struct WgmWork { int np, kt, split, m_begin, num_mb; };
+struct WgmWork { int np, kt, split, m_begin, num_mb, first; };   // first: position of the split's first block in P.blocks
 constexpr int kWgmSyncStride = 128;
 // This pair's share of problem p (the same arithmetic in every warp role).
 __device__ __forceinline__ bool wgm_work(const WgmArgs& a, int p, int pair, WgmWork& w) {
@@ -61,6 +62,15 @@ __device__ __forceinline__ bool wgm_work(const WgmArgs& a, int p, int pair, WgmW
   w.np = tile / P.k_tiles;
   w.kt = tile - w.np * P.k_tiles;
   w.split = split;
+  if (P.blocks) {                              // the splits share the LISTED blocks evenly (every tile of a split alike)
+    const int n = __ldg(P.blocks);
+    const int per = (n + P.splits - 1) / P.splits;
+    w.first = split * per;
+    w.m_begin = 0;
+    w.num_mb = max(0, min(per, n - w.first));
+    return w.num_mb > 0;
+  }
+  w.first = 0;
   w.m_begin = split * P.m_per;
   const int m_end = min(a.M, w.m_begin + P.m_per);
   w.num_mb = (m_end - w.m_begin + kTileK - 1) / kTileK;
@@ -132,11 +142,14 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_multi_kernel(const __gri
         }
         __syncwarp();
       }
+      int blk32 = 0;                                   // listed problems: 32 block indices at a time, one per lane
       for (int mb = 0; mb < w.num_mb; ++mb) {
+        if (P.blocks && (mb & 31) == 0) blk32 = mb + lane < w.num_mb ? __ldg(P.blocks + 1 + w.first + mb + lane) : 0;
         mbar_wait(((a.dbg & 2) ? mma_done : slot_free) + st.stage, st.phase ^ 1);
         uint8_t* sg = smem + st.stage * kWgmStage;
         uint8_t* sa = sg + kWgmStageG;
-        const int m0 = w.m_begin + mb * kTileK;      // rows >= M are zero-filled by TMA; splits are 64-aligned
+        // rows >= M are zero-filled by TMA; splits are 64-aligned
+        const int m0 = P.blocks ? __shfl_sync(0xffffffffu, blk32, mb & 31) * kTileK : w.m_begin + mb * kTileK;
         if (elect_one()) {
           if (cta_leader) mbar_expect_tx(full + st.stage, bytes);
           else mbar_arrive_leader(full + st.stage);
@@ -297,6 +310,8 @@ int wgrad_multi_launch(const WgmHost& h, cudaStream_t stream) {
     NRF_REQUIRE((s.ns == 2 || s.ns == 4) && s.k_tiles >= 1 && s.k_tiles * s.ns <= kWgmMaxSlabs && s.n_valid > 0 &&
                     s.g_map >= 0 && s.g_map < h.n_maps, NRF_EINVAL, "wgrad_multi: problem %d malformed", p);
     d.g_map = s.g_map; d.n_valid = s.n_valid; d.ns = s.ns; d.k_tiles = s.k_tiles; d.dbias = s.dbias; d.dbias2 = s.dbias2;
+    NRF_REQUIRE(!s.blocks || !s.dbias, NRF_EINVAL, "wgrad_multi: a block list excludes bias sums (they need every sample)");
+    d.blocks = s.blocks;
     for (int j = 0; j < s.k_tiles * s.ns; ++j) {
       NRF_REQUIRE(s.slab[j].a_map >= 0 && s.slab[j].a_map < h.n_maps, NRF_EINVAL, "wgrad_multi: slab operand");
       d.slab[j] = s.slab[j];
