@@ -288,34 +288,43 @@ __global__ void __launch_bounds__(256) encode_points_w32_kernel(EncodeArgs a) {
     if (a.touch && lane == 0) a.touch[grp] = touch != 0u;
     const int scene_l = r / a.rays_per_scene;
     const int cnt = (int)((N - grp * kWarp) < kWarp ? (N - grp * kWarp) : kWarp);
+    // The eight corners (voxel index within the scene or -1, weight) are worked out ONCE, by the lane that owns the
+    // sample, and handed to the warp by 16 shuffles per sample: the warp used to redo the whole corner set-up (bounds
+    // tests, 64-bit offsets, weight products: ~120 instructions) for each of its 32 samples.
+    int cvox[8];
+    float cw[8];
+    {
+      Corner8 c8;
+      corners_from_setup(ts, a.S0, a.S1, a.S2, 1, c8);                  // C = 1: off = voxel index
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { cvox[k] = (int)c8.off[k]; cw[k] = c8.w[k]; }
+    }
     for (int s = 0; s < cnt; ++s) {
       T* row = out + (grp * kWarp + s) * a.ld_out;
       if (!((touch >> s) & 1u)) {
         for (int c0 = lane * 4; c0 < C; c0 += kWarp * 4) store4<T>(row + c0, make_float4(0.f, 0.f, 0.f, 0.f));
         continue;
       }
-      TriSetup t;
-      t.x0 = __shfl_sync(0xffffffffu, ts.x0, s); t.y0 = __shfl_sync(0xffffffffu, ts.y0, s);
-      t.z0 = __shfl_sync(0xffffffffu, ts.z0, s);
-      t.wx0 = __shfl_sync(0xffffffffu, ts.wx0, s); t.wx1 = __shfl_sync(0xffffffffu, ts.wx1, s);
-      t.wy0 = __shfl_sync(0xffffffffu, ts.wy0, s); t.wy1 = __shfl_sync(0xffffffffu, ts.wy1, s);
-      t.wz0 = __shfl_sync(0xffffffffu, ts.wz0, s); t.wz1 = __shfl_sync(0xffffffffu, ts.wz1, s);
-      t.finite = true;
       const int scene = __shfl_sync(0xffffffffu, scene_l, s);
-      Corner8 c8;
-      corners_from_setup(t, a.S0, a.S1, a.S2, C, c8);
+      int vx[8];
+      float w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        vx[k] = __shfl_sync(0xffffffffu, cvox[k], s);
+        w[k] = __shfl_sync(0xffffffffu, cw[k], s);
+      }
       const float* vol = a.vol + (int64_t)scene * scene_stride;
       for (int c0 = lane * 4; c0 < C; c0 += kWarp * 4) {
         float4 v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          v[k] = c8.off[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(vol + c8.off[k] + c0))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[k] = vx[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(vol + (int64_t)vx[k] * C + c0))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          if (c8.off[k] >= 0) {
-            acc = corner_acc(acc, v[k], c8.w[k], a.fma);
+          if (vx[k] >= 0) {
+            acc = corner_acc(acc, v[k], w[k], a.fma);
           }
         }
         store4<T>(row + c0, acc);
