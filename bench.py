@@ -429,7 +429,7 @@ def run_ours(args):
         release()
 
     # ---- the other BASELINE configs (each a short run; N > 1: strong scaling - total work fixed)
-    if not args.no_extra and args.workload == "config2":
+    if not args.no_extra and not args.no_configs and args.workload == "config2":
         del main, ren
         release()
         line["configs"] = other_configs(mods, args, dev, rank, world)
@@ -694,6 +694,8 @@ def main():
     ap.add_argument("--no-modes", action="store_true", dest="no_modes", help="skip the per-precision-mode lines")
     ap.add_argument("--no-extra", action="store_true", dest="no_extra",
                     help="skip the in-box variant and BASELINE configs 3 / 4 / 5")
+    ap.add_argument("--no-configs", action="store_true", dest="no_configs",
+                    help="skip BASELINE configs 3 / 4 / 5 (the in-box variant still runs)")
     ap.add_argument("--sustain-steps", type=int, default=200, dest="sustain_steps",
                     help="length of the additional long timed region (0: skip)")
     ap.add_argument("--allreduce", default="overlap", choices=["overlap", "post"],

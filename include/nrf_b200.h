@@ -63,6 +63,29 @@ const char* nrf_last_error(void);   /* text of the last failure on this thread *
 int nrf_raygen(const float* poses, int n_img, int W, int H, float fx, float fy, float cx, float cy,
                float z_near, float z_far, float* rays_out, const float* intrinsics_dev, void* stream);
 
+/* The same formulas under another ATen back end's rounding pattern (utils.py:444-506 run on a GPU executes ATen's CUDA
+ * kernels and a cuBLAS batched K = 3 product, the golden fixtures were written by the CPU kernels; nrf_raygen = flags 0).
+ * flags = direction | pixel | norm:
+ *   NRF_RAYGEN_DIR_SEPARATE (r0*x + r1*y) + r2*z, every product and sum rounded | _DIR_FMA_ASC fma(r2,z,fma(r1,y,r0*x))
+ *   | _DIR_FMA_DESC fma(r0,x,fma(r1,y,r2*z)) | _DIR_SPLIT fma(r1,y,fma(r0,x,+0)) + fma(r2,z,+0);
+ *   NRF_RAYGEN_PIXEL_RECIP: (j - cx) * (1/fx) instead of (j - cx) / fx (ATen CUDA divides by a host scalar that way);
+ *   NRF_RAYGEN_NORM_FMA sqrt(fma(z,z,fma(y,y,x*x))) | _NORM_XY_Z (xx + yy) + zz | _NORM_XZ_Y (xx + zz) + yy
+ *   | _NORM_X_YZ xx + (yy + zz).
+ * NRF_RAYGEN_CUDA_EAGER is the combination measured bit-identical - signed zeros included - to CUDA-eager PyTorch
+ * 2.11 on B200 (scripts/raygen_probe.py over all 64 combinations; asserted in tests/test_gpu_bench_sizes.py). */
+#define NRF_RAYGEN_DIR_SEPARATE 0
+#define NRF_RAYGEN_DIR_FMA_ASC 1
+#define NRF_RAYGEN_DIR_FMA_DESC 2
+#define NRF_RAYGEN_DIR_SPLIT 3
+#define NRF_RAYGEN_PIXEL_RECIP 4
+#define NRF_RAYGEN_NORM_FMA 0
+#define NRF_RAYGEN_NORM_XY_Z 8
+#define NRF_RAYGEN_NORM_XZ_Y 16
+#define NRF_RAYGEN_NORM_X_YZ 24
+#define NRF_RAYGEN_CUDA_EAGER (NRF_RAYGEN_DIR_SPLIT | NRF_RAYGEN_PIXEL_RECIP | NRF_RAYGEN_NORM_XZ_Y)
+int nrf_raygen_ex(const float* poses, int n_img, int W, int H, float fx, float fy, float cx, float cy,
+                  float z_near, float z_far, float* rays_out, const float* intrinsics_dev, int flags, void* stream);
+
 /* ---- stratified sampling (neural_rendering.py:159-176 sample_coarse) ------------------------
  * base (Kc) = linspace(0, 1-1/Kc, Kc); jitter (R,Kc) in [0,1) or NULL (perturb off). */
 int nrf_sample_coarse(const float* rays, int R, int Kc, const float* base, const float* jitter,

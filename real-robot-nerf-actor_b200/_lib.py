@@ -64,6 +64,7 @@ _i, _f, _p, _i64 = C.c_int, C.c_float, c_ptr, C.c_int64
 
 _SIGNATURES = {
     "nrf_raygen": [_p, _i, _i, _i, _f, _f, _f, _f, _f, _f, _p, _p, _p],
+    "nrf_raygen_ex": [_p, _i, _i, _i, _f, _f, _f, _f, _f, _f, _p, _p, _i, _p],
     "nrf_sample_coarse": [_p, _i, _i, _p, _p, _i, _p, _p],
     "nrf_sample_fine": [_p, _p, _p, _i, _i, _p, _p, _i, _i, _p, _i, _p, _p],
     "nrf_sort_rows": [_p, _i, _i, _p, _p],

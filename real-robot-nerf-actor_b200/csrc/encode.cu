@@ -834,6 +834,205 @@ __global__ void __launch_bounds__(kRcfWarps * 32, 10) scatter_reduce_cf_kernel(c
   }
 }
 
+// The same reduction for the kVec case, restructured for the regime where most voxels of a tile have entries (rays
+// that stay inside the volume: 6 M entries over ~1 M voxels at config 2).  scatter_reduce_cf_kernel pays a dependent
+// chain (list -> rows) and a shuffle-ranked selection PER VOXEL and reads every 512 B row as four 128 B pieces
+// (ncu, in-box: 71 warp instructions per entry, 28 % DRAM).  Here a warp owns 8 voxels of the tile (every fourth) and
+//   1. loads up to 32 entries of whole voxels with one read of the entry and the weight list,
+//   2. ranks every entry among the entries of its own voxel (shuffles over the longest voxel of the batch only) and
+//      drops {entry, weight} at its sorted position in shared memory,
+//   3. walks the sorted batch four entries at a time - one broadcast LDS.64 and ONE vector load of the lane's CJ
+//      consecutive channels per entry, the four row loads of a group in flight together - and adds in ascending entry
+//      order (the same fmaf chain per channel as voxel_sum: bit-identical results),
+//   4. puts a finished voxel's row into the (32 voxel x C) tile with one vector STS; 16 B slots are XOR-swizzled by the
+//      voxel quad so that the channel-first read-out below (4 scalar LDS -> STG.128 of four consecutive voxels, a
+//      warp instruction = four full 128 B lines) is conflict-free too.
+// Voxels with more than 32 entries take voxel_sum's in-place sort.
+template <int CJ> struct LaneVec;
+template <> struct LaneVec<4> {
+  float4 v;
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ void fma(float w, const LaneVec& d) {
+    v.x = fmaf(w, d.v.x, v.x); v.y = fmaf(w, d.v.y, v.y); v.z = fmaf(w, d.v.z, v.z); v.w = fmaf(w, d.v.w, v.w);
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct LaneVec<2> {
+  float2 v;
+  __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float2*>(p)); }
+  __device__ __forceinline__ void fma(float w, const LaneVec& d) {
+    v.x = fmaf(w, d.v.x, v.x); v.y = fmaf(w, d.v.y, v.y);
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = v; }
+};
+
+template <int CJ>
+__global__ void __launch_bounds__(kRcfWarps * 32, 8) scatter_reduce_cf2_kernel(const int32_t* __restrict__ offset,
+                                                                 const int32_t* __restrict__ count,
+                                                                 const int32_t* __restrict__ list,
+                                                                 const float* __restrict__ wlist, ScatterPass pa,
+                                                                 ScatterPass pb, int64_t Ea, float* __restrict__ grad,
+                                                                 int64_t V, int64_t T) {
+  constexpr int C = CJ * kWarp;
+  constexpr int NS = C / 4;                       // 16 B slots per tile row
+  constexpr int NW = kRcfWarps;
+  static_assert(NW == 4, "a warp owns 8 of the tile's 32 voxels");
+  __shared__ __align__(16) float tile[32 * C];
+  __shared__ __align__(8) const float* ent_row[NW][kWarp];    // sorted batch: the entry's gradient row ...
+  __shared__ float ent_w[NW][kWarp];                          // ... and its trilinear weight
+  int lane;                                       // volatile: kept in a register, never re-read with S2R in the loops
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x / kWarp), 0);      // warp-uniform to the compiler too
+  const int32_t Ea32 = (int32_t)Ea;               // E < 2^31 (checked by the caller)
+  const int r4 = lane >> 3, l8 = lane & 7;
+  const int64_t ntiles = T / 32;                  // kVec: V % 32 == 0
+  // element (voxel vi, channel c) of the tile: row vi, slot (c / 4) ^ (vi / 4), word c % 4
+  auto tile_at = [&](int vi, int c) -> float* {
+    return tile + vi * C + ((((c >> 2) ^ (vi >> 2)) & (NS - 1)) << 2) + (c & 3);
+  };
+  auto row_of = [&](int32_t e) {                  // worked out by the lane that owns the entry, once
+    return e < Ea32 ? pa.dlat + (int64_t)(e >> 3) * pa.ld : pb.dlat + (int64_t)((e - Ea32) >> 3) * pb.ld;
+  };
+  int cnt_n = 0, off_n = 0;
+  if ((int64_t)blockIdx.x < ntiles) {
+    const int64_t t = (int64_t)blockIdx.x * 32 + lane;
+    cnt_n = count[t]; off_n = offset[t];
+  }
+  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int cnt_l = cnt_n, off_l = off_n;
+    {
+      const int64_t tn = (tl + gridDim.x) * 32 + lane;
+      cnt_n = 0; off_n = 0;
+      if (tn < T) { cnt_n = count[tn]; off_n = offset[tn]; }
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, cnt_l > 0);   // uniform over the CTA (same counts in every warp)
+    const uint32_t t0 = (uint32_t)tl * 32u, scene0 = t0 / (uint32_t)V;        // T < 2^31 (checked by the caller)
+    // this lane's voxel quad, channel wid * 4 + r4; the write-out walks the channels in steps of 16
+    float* gvec = grad + ((int64_t)scene0 * C + wid * 4 + r4) * V + (t0 - scene0 * (uint32_t)V) + 4 * l8;
+    if (any == 0u) {
+#pragma unroll
+      for (int i = 0; i < C / (4 * NW); ++i)
+        *reinterpret_cast<float4*>(gvec + (int64_t)(4 * NW * i) * V) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    // lanes 0..7: count, list offset and inclusive prefix of this warp's voxels 4 j + wid (interleaved: the voxels a
+    // ray crosses are runs along x, so consecutive ownership would leave one warp with the whole tile's work)
+    const int cj = __shfl_sync(0xffffffffu, cnt_l, 4 * l8 + wid);
+    const int oj = __shfl_sync(0xffffffffu, off_l, 4 * l8 + wid);
+    int pin = cj;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, pin, d, 8);
+      if (l8 >= d) pin += o;
+    }
+    int vs = 0, pstart = 0;                       // first voxel not done yet, entries before it
+    while (vs < 8) {
+      const unsigned fit = __ballot_sync(0xffffffffu, lane < 8 && lane >= vs && pin - pstart <= kWarp);
+      const int nv = __popc(fit);
+      if (nv == 0) {                              // a voxel with more than a warp's worth of entries, on its own
+        const int cnt = __shfl_sync(0xffffffffu, cj, vs);
+        const int off = __shfl_sync(0xffffffffu, oj, vs);
+        float acc[CJ];
+        voxel_sum<CJ>(list + off, wlist + off, cnt, pa, pb, Ea, lane, acc);
+#pragma unroll
+        for (int j = 0; j < CJ; ++j) *tile_at(4 * vs + wid, lane + j * kWarp) = acc[j];
+        pstart += cnt;
+        vs += 1;
+        continue;
+      }
+      const int ve = vs + nv;
+      const int n = __shfl_sync(0xffffffffu, pin, ve - 1) - pstart;           // entries of the batch (may be 0)
+      LaneVec<CJ> acc;
+      acc.zero();
+      int v = vs;
+      if (n > 0) {
+        int vi_l = vs;                            // this entry's voxel: the first whose inclusive prefix exceeds `lane`
+        int maxc = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pj = __shfl_sync(0xffffffffu, pin, j) - pstart;
+          const int cc = __shfl_sync(0xffffffffu, cj, j);
+          if (j >= vs && j < ve) {
+            vi_l += (pj <= lane) ? 1 : 0;
+            maxc = cc > maxc ? cc : maxc;
+          }
+        }
+        if (vi_l > 7) vi_l = 7;                    // lanes past the batch: any valid source lane
+        const int seg_end = __shfl_sync(0xffffffffu, pin, vi_l) - pstart;
+        const int seg_beg = seg_end - __shfl_sync(0xffffffffu, cj, vi_l);
+        const int src_l = __shfl_sync(0xffffffffu, oj, vi_l) + lane - seg_beg;   // a voxel's entries are contiguous
+        int32_t e_l = 0x7fffffff;
+        float w_l = 0.f;
+        if (lane < n) { e_l = list[src_l]; w_l = wlist[src_l]; }
+        int rank = 0;                              // entries are distinct: ranks within a voxel are a permutation
+        for (int d = 0; d < maxc; ++d) {
+          const int src = seg_beg + d;
+          const int32_t ej = __shfl_sync(0xffffffffu, e_l, src & 31);
+          rank += (src < seg_end && ej < e_l) ? 1 : 0;
+        }
+        __syncwarp();                              // the previous batch's reads of ent_*[] are done
+        if (lane < n) {
+          ent_row[wid][seg_beg + rank] = row_of(e_l);
+          ent_w[wid][seg_beg + rank] = w_l;
+        }
+        __syncwarp();
+        int vend = __shfl_sync(0xffffffffu, pin, v) - pstart;
+        for (int k0 = 0; k0 < n; k0 += 4) {
+          const float* row[4];
+          float w[4];
+          LaneVec<CJ> d[4];
+          const float* const* er = &ent_row[wid][k0];      // k0 + q <= 31: n <= 32, k0 a multiple of 4
+          const float* ewt = &ent_w[wid][k0];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            row[q] = er[q];
+            w[q] = ewt[q];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (k0 + q < n) d[q].load(row[q] + lane * CJ);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (k0 + q < n) {
+              while (k0 + q >= vend) {             // voxel v is complete (or empty): its row goes into the tile
+                acc.store(tile_at(4 * v + wid, lane * CJ));
+                acc.zero();
+                ++v;
+                vend = __shfl_sync(0xffffffffu, pin, v & 7) - pstart;
+              }
+              acc.fma(w[q], d[q]);
+            }
+          }
+        }
+      }
+      for (; v < ve; ++v) {                        // the last voxel with entries, then trailing empty ones
+        acc.store(tile_at(4 * v + wid, lane * CJ));
+        acc.zero();
+      }
+      pstart += n;
+      vs = ve;
+    }
+    __syncthreads();
+    // channel c = wid * 4 + r4 + 16 i of voxels 4 l8 + t: slot (c / 4) ^ l8 = ((wid ^ (l8 & 3)) | ((i ^ (l8 >> 2)) << 2)),
+    // so the i-dependence is +-16 words on one of two per-thread bases (even / odd i) and every LDS has an immediate offset
+    {
+      const int h = l8 >> 2;
+      const float* rd_even = tile + (4 * l8) * C + 4 * (wid ^ (l8 & 3)) + r4 + 16 * h;
+      const float* rd_odd = rd_even - 32 * h;
+#pragma unroll
+      for (int i = 0; i < C / (4 * NW); ++i) {
+        const float* rd = ((i & 1) ? rd_odd : rd_even) + 16 * i;
+        float4 x;
+        x.x = rd[0]; x.y = rd[C]; x.z = rd[2 * C]; x.w = rd[3 * C];
+        *reinterpret_cast<float4*>(gvec + (int64_t)(4 * NW * i) * V) = x;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Channels-last output (the producer works in torch.channels_last_3d): one warp per voxel row.
 template <int CJ>
 __global__ void __launch_bounds__(256) scatter_reduce_cl_kernel(const int32_t* __restrict__ offset,
@@ -922,10 +1121,20 @@ extern "C" int nrf_scatter_volume_grad_merged(const float* rays, int R, int rays
       int max_blocks = sm_count() * 10;
       int blocks = (int)(ntiles < max_blocks ? ntiles : max_blocks);
       const bool vec = V % 32 == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0;
+      // rows read as one vector per lane: 16 B aligned gradient rows in both passes
+      const bool rowvec = vec && ld_a % 4 == 0 && (reinterpret_cast<uintptr_t>(dlat_a) & 15) == 0 &&
+                          (!two || (ld_b % 4 == 0 && (reinterpret_cast<uintptr_t>(dlat_b) & 15) == 0));
+      const char* env = getenv("NRF_SCATTER_RCF");            // "1": the one-voxel-per-warp kernel (A/B, tests)
+      const bool batched = rowvec && !(env && atoi(env) == 1);
 #define NRF_RCF(CJ, VEC) scatter_reduce_cf_kernel<CJ, VEC><<<blocks, kRcfWarps * 32, 0, s>>>(offset, count, list, wlist, pa, pb, Ea, grad, V, T)
-      if (C == 128) { if (vec) NRF_RCF(4, true); else NRF_RCF(4, false); }
+#define NRF_RCF2(CJ) scatter_reduce_cf2_kernel<CJ><<<blocks8, kRcfWarps * 32, 0, s>>>(offset, count, list, wlist, pa, pb, Ea, grad, V, T)
+      const int max8 = sm_count() * 8;
+      const int blocks8 = (int)(ntiles < max8 ? ntiles : max8);
+      if (batched) { if (C == 128) NRF_RCF2(4); else NRF_RCF2(2); }
+      else if (C == 128) { if (vec) NRF_RCF(4, true); else NRF_RCF(4, false); }
       else { if (vec) NRF_RCF(2, true); else NRF_RCF(2, false); }
 #undef NRF_RCF
+#undef NRF_RCF2
     } else {
       int64_t want = (T + 7) / 8;
       int max_blocks = sm_count() * 32;

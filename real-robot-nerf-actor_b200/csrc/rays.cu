@@ -8,13 +8,17 @@
 
 namespace nrf {
 
-// One thread per pixel.  CPU-ATen bit pattern: norm = sqrt(fma(z,z,fma(y,y,x*x))),
-// direction = (r0*x + r1*y) + r2*z with separately rounded products and sums.
+// One thread per pixel.  Default = the CPU-ATen bit pattern the golden fixtures were produced with:
+// norm = sqrt(fma(z,z,fma(y,y,x*x))), direction = (r0*x + r1*y) + r2*z with separately rounded products and sums.
+// `flags` selects the rounding pattern of the SAME formulas as other ATen back ends execute them (NRF_RAYGEN_*):
+//   pixel coordinate  true division | product with the fp32 reciprocal (ATen's CUDA div by a host scalar)
+//   norm              the four association orders of x*x + y*y + z*z a reduction kernel can produce
+//   direction         separately rounded | FMA chain over k ascending | descending | two accumulators {0, 1} + {2}
 // intr (device, [fx, fy, cx, cy]) overrides the by-value intrinsics: a focal length that lives on the GPU (as in the
 // reference's callers) is then never read back by the host -- no stream sync at the start of every step.
 __global__ void raygen_kernel(const float* __restrict__ poses, int n_img, int W, int H, float fx,
                               float fy, float cx, float cy, float z_near, float z_far,
-                              float* __restrict__ rays, const float* __restrict__ intr) {
+                              float* __restrict__ rays, const float* __restrict__ intr, int flags) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)n_img * H * W;
   if (t >= total) return;
@@ -23,10 +27,25 @@ __global__ void raygen_kernel(const float* __restrict__ poses, int n_img, int W,
   int i = (int)((t / W) % H);
   int b = (int)(t / ((int64_t)W * H));
   const float* P = poses + (int64_t)b * 16;
-  float x = __fdiv_rn(__fsub_rn((float)j, cx), fx);
-  float y = -__fdiv_rn(__fsub_rn((float)i, cy), fy);
+  const int dir_mode = flags & 3, recip = (flags >> 2) & 1, norm_mode = (flags >> 3) & 3;
+  float x, y;
+  if (recip) {
+    x = __fmul_rn(__fsub_rn((float)j, cx), __fdiv_rn(1.0f, fx));
+    y = -__fmul_rn(__fsub_rn((float)i, cy), __fdiv_rn(1.0f, fy));
+  } else {
+    x = __fdiv_rn(__fsub_rn((float)j, cx), fx);
+    y = -__fdiv_rn(__fsub_rn((float)i, cy), fy);
+  }
   float zc = -1.0f;
-  float nrm = __fsqrt_rn(__fmaf_rn(zc, zc, __fmaf_rn(y, y, __fmul_rn(x, x))));
+  float n2;
+  {
+    const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(zc, zc);
+    if (norm_mode == 0) n2 = __fmaf_rn(zc, zc, __fmaf_rn(y, y, xx));
+    else if (norm_mode == 1) n2 = __fadd_rn(__fadd_rn(xx, yy), zz);
+    else if (norm_mode == 2) n2 = __fadd_rn(__fadd_rn(xx, zz), yy);
+    else n2 = __fadd_rn(xx, __fadd_rn(yy, zz));
+  }
+  float nrm = __fsqrt_rn(n2);
   x = __fdiv_rn(x, nrm);
   y = __fdiv_rn(y, nrm);
   zc = __fdiv_rn(zc, nrm);
@@ -36,9 +55,21 @@ __global__ void raygen_kernel(const float* __restrict__ poses, int n_img, int W,
   lo.z = P[11];
   float d[3];
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
-    d[r] = __fadd_rn(__fadd_rn(__fmul_rn(P[r * 4 + 0], x), __fmul_rn(P[r * 4 + 1], y)),
-                     __fmul_rn(P[r * 4 + 2], zc));
+  for (int r = 0; r < 3; ++r) {
+    const float r0 = P[r * 4 + 0], r1 = P[r * 4 + 1], r2 = P[r * 4 + 2];
+    if (dir_mode == 0) {
+      d[r] = __fadd_rn(__fadd_rn(__fmul_rn(r0, x), __fmul_rn(r1, y)), __fmul_rn(r2, zc));
+    } else if (dir_mode == 1) {
+      d[r] = __fmaf_rn(r2, zc, __fmaf_rn(r1, y, __fmul_rn(r0, x)));
+    } else if (dir_mode == 2) {
+      d[r] = __fmaf_rn(r0, x, __fmaf_rn(r1, y, __fmul_rn(r2, zc)));
+    } else {
+      // cuBLAS' batched (3x3) x (3x1) product as torch.matmul reaches it on B200 (scripts/raygen_probe.py): two
+      // accumulators that start at +0 - k = 0, 1 chained by FMA and k = 2 on its own - then added.  The +0 start only
+      // shows in the sign of an exact zero (fma(0, x, +0) = +0 for negative x where 0 * x = -0).
+      d[r] = __fadd_rn(__fmaf_rn(r1, y, __fmaf_rn(r0, x, 0.0f)), __fmaf_rn(r2, zc, 0.0f));
+    }
+  }
   lo.w = d[0];
   hi.x = d[1];
   hi.y = d[2];
@@ -174,18 +205,25 @@ __global__ void sort_rows_kernel(float* __restrict__ z, int R, int K, int P, int
 
 using namespace nrf;
 
-extern "C" int nrf_raygen(const float* poses, int n_img, int W, int H, float fx, float fy, float cx,
-                          float cy, float z_near, float z_far, float* rays_out, const float* intrinsics_dev,
-                          void* stream) {
+extern "C" int nrf_raygen_ex(const float* poses, int n_img, int W, int H, float fx, float fy, float cx,
+                             float cy, float z_near, float z_far, float* rays_out, const float* intrinsics_dev,
+                             int flags, void* stream) {
   NRF_REQUIRE(poses && rays_out && n_img > 0 && W > 0 && H > 0, NRF_EINVAL, "nrf_raygen: bad args");
+  NRF_REQUIRE(flags >= 0 && flags < 32, NRF_EINVAL, "nrf_raygen: unknown flags %d", flags);
   int64_t total = (int64_t)n_img * H * W;
   int threads = 256;
   { LaunchScope ls_(NRF_CAT_SAMPLING, as_stream(stream));
   raygen_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
-      poses, n_img, W, H, fx, fy, cx, cy, z_near, z_far, rays_out, intrinsics_dev);
+      poses, n_img, W, H, fx, fy, cx, cy, z_near, z_far, rays_out, intrinsics_dev, flags);
   }
   NRF_LAUNCH_OK();
   return NRF_OK;
+}
+
+extern "C" int nrf_raygen(const float* poses, int n_img, int W, int H, float fx, float fy, float cx,
+                          float cy, float z_near, float z_far, float* rays_out, const float* intrinsics_dev,
+                          void* stream) {
+  return nrf_raygen_ex(poses, n_img, W, H, fx, fy, cx, cy, z_near, z_far, rays_out, intrinsics_dev, 0, stream);
 }
 
 extern "C" int nrf_sample_coarse(const float* rays, int R, int Kc, const float* base,

@@ -86,19 +86,29 @@ def _device_intrinsics(focal, c, width, height, device):
     return intr
 
 
+# nrf_raygen_ex flags (include/nrf_b200.h)
+NRF_RAYGEN_DIR_FMA_ASC, NRF_RAYGEN_DIR_FMA_DESC, NRF_RAYGEN_DIR_SPLIT, NRF_RAYGEN_PIXEL_RECIP = 1, 2, 3, 4
+NRF_RAYGEN_NORM_XY_Z, NRF_RAYGEN_NORM_XZ_Y, NRF_RAYGEN_NORM_X_YZ = 8, 16, 24
+NRF_RAYGEN_CUDA_EAGER = NRF_RAYGEN_DIR_SPLIT | NRF_RAYGEN_PIXEL_RECIP | NRF_RAYGEN_NORM_XZ_Y
+RAYGEN_FLAGS = 0        # default rounding pattern of gen_rays: 0 = ATen's CPU kernels (what the golden fixtures hold);
+                        # NRF_RAYGEN_CUDA_EAGER = bit-identical rays to the reference run on a GPU (like GATHER_FMA below)
+
+
 @_on_tensor_device
-def raygen(poses, width, height, focal, z_near, z_far, c=None):
+def raygen(poses, width, height, focal, z_near, z_far, c=None, flags=None):
     """utils.py:477-506 gen_rays.  poses (B,4,4) -> rays (B,H,W,8).
     A `focal` / `c` that lives on the GPU stays there (4 floats handed to the kernel by pointer): reading it back would
-    stall the host on everything queued before, once per step."""
+    stall the host on everything queued before, once per step.
+    flags: rounding pattern (NRF_RAYGEN_*); None = the module default RAYGEN_FLAGS."""
+    flags = RAYGEN_FLAGS if flags is None else flags
     poses = _f32(poses, "poses")
     B = poses.shape[0]
     rays = torch.empty(B, height, width, 8, device=poses.device, dtype=torch.float32)
     on_dev = (torch.is_tensor(focal) and focal.is_cuda) or (torch.is_tensor(c) and c.is_cuda)
     if on_dev:
         intr = _device_intrinsics(focal, c, width, height, poses.device)
-        check(_lib.load().nrf_raygen(ptr(poses), B, width, height, 0.0, 0.0, 0.0, 0.0, float(z_near), float(z_far),
-                                     ptr(rays), ptr(intr), stream_ptr()), "nrf_raygen")
+        check(_lib.load().nrf_raygen_ex(ptr(poses), B, width, height, 0.0, 0.0, 0.0, 0.0, float(z_near), float(z_far),
+                                        ptr(rays), ptr(intr), int(flags), stream_ptr()), "nrf_raygen")
         return rays
     f = torch.as_tensor(focal, dtype=torch.float32).reshape(-1)
     fx, fy = (float(f[0]), float(f[0])) if f.numel() == 1 else (float(f[0]), float(f[1]))
@@ -107,8 +117,8 @@ def raygen(poses, width, height, focal, z_near, z_far, c=None):
     else:
         cc = torch.as_tensor(c, dtype=torch.float32).reshape(-1)
         cx, cy = (float(cc[0]), float(cc[0])) if cc.numel() == 1 else (float(cc[0]), float(cc[1]))
-    check(_lib.load().nrf_raygen(ptr(poses), B, width, height, fx, fy, cx, cy, float(z_near),
-                                 float(z_far), ptr(rays), None, stream_ptr()), "nrf_raygen")
+    check(_lib.load().nrf_raygen_ex(ptr(poses), B, width, height, fx, fy, cx, cy, float(z_near),
+                                    float(z_far), ptr(rays), None, int(flags), stream_ptr()), "nrf_raygen")
     return rays
 
 

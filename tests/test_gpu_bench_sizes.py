@@ -214,6 +214,18 @@ def test_stages_against_the_oracle_run_on_the_device(mods):
     report["gen_rays"] = bits_equal_frac(r, r_ref)
     assert torch.equal(r[..., :3], r_ref[..., :3]) and torch.equal(r[..., 6:], r_ref[..., 6:])
     assert float((r - r_ref).abs().max()) <= 2.5e-7
+    # ... and in the rounding pattern CUDA-eager executes (pixel * (1 / f), norm as (xx + zz) + yy, cuBLAS' two-accumulator
+    # K = 3 product: scripts/raygen_probe.py tried all 64 combinations) every ray is bit-identical, signed zeros included
+    same_bits = lambda a, b: torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))
+    for P, W_, H_, f_, c_ in ((poses, wl.W, wl.H, focal, None),
+                              (torch.eye(4, device=dev)[None].repeat(2, 1, 1), wl.W, wl.H, focal, None),
+                              (syn.arc_poses(5).to(dev), 160, 120, torch.tensor([201.3, 199.1], device=dev),
+                               torch.tensor([77.2, 61.9], device=dev)),
+                              (syn.arc_poses(3).to(dev), 80, 60, torch.tensor(76.18187, device=dev), None)):
+        ref_ = O.gen_rays(P, W_, H_, f_, 1.2, 4.0, c=c_)
+        got_ = ops.raygen(P, W_, H_, f_, 1.2, 4.0, c=c_, flags=ops.NRF_RAYGEN_CUDA_EAGER)
+        assert same_bits(got_, ref_), (W_, H_)
+    report["gen_rays_cuda_eager_mode"] = 1.0
     rays = r_ref.reshape(2, -1, 8)[:, syn.pick_ray_indices(wl.W * wl.H, 512, seed=1).to(dev)].reshape(-1, 8).contiguous()
     R = rays.shape[0]
     noise = {k: v.to(dev) for k, v in syn.make_noise(R, 64, 64, seed=2).items()}

@@ -409,6 +409,34 @@ def test_scatter_merged_two_passes_one_sort(ops, C, channels_first, S):
     assert torch.equal(g1_cl, gs)
 
 
+@pytest.mark.parametrize("C,S,R,K", [(128, 16, 96, 48), (64, 16, 300, 40), (128, 8, 200, 64), (128, 32, 64, 96)])
+def test_scatter_batched_reduce_equals_the_one_voxel_per_warp_kernel(ops, monkeypatch, C, S, R, K):
+    """scatter_reduce_cf2_kernel (a warp sums 8 consecutive voxels from one batched read of their entries, rows as one
+    vector per lane) against scatter_reduce_cf_kernel (NRF_SCATTER_RCF=1), rays INSIDE the box: a few to a few hundred
+    entries per voxel, so batches of whole voxels, voxels that split a batch, empty voxels between them and the
+    more-than-a-warp fallback all occur.  Same ascending-entry fmaf chain per channel: bit for bit."""
+    g = torch.Generator().manual_seed(S * 1000 + C)
+    b = torch.tensor(syn.BOUNDS)
+    o = (b[:3] + (b[3:] - b[:3]) * (0.15 + 0.7 * torch.rand(2 * R, 3, generator=g)))
+    d = torch.nn.functional.normalize(torch.randn(2 * R, 3, generator=g), dim=-1) * 0.25
+    rays = torch.cat([o, d, torch.zeros(2 * R, 1), torch.ones(2 * R, 1)], 1).cuda()
+    za = torch.rand(2 * R, K, generator=g).sort(-1)[0].cuda()
+    zb = torch.rand(2 * R, K + 8, generator=g).sort(-1)[0].cuda()
+    dla = torch.randn(2 * R * K, C, generator=g).cuda()
+    dlb = torch.randn(2 * R * (K + 8), C, generator=g).cuda()
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NRF_SCATTER_RCF", mode)
+        grad = torch.full((2, C, S, S, S), 7.0, device="cuda")
+        _, counts = ops.scatter_volume_grad_merged(rays, R, [(za, dla), (zb, dlb)], grad, True, b, want_counts=True)
+        outs[mode] = grad
+    assert torch.equal(outs["0"], outs["1"])
+    assert float(outs["0"].abs().sum()) > 0
+    c = counts.cpu()
+    print(f"S={S} C={C}: entries per touched voxel mean {float(c[c > 0].float().mean()):.1f}, max {int(c.max())}, "
+          f"touched {float((c > 0).float().mean()):.2f} of the voxels")
+
+
 # ------------------------------------------------------------------ whole-MLP fused forward kernel
 def _bf16_mlp(C=128, D=384, seed=0):
     NR = load_pkg("neural_rendering")
