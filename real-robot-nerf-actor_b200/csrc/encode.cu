@@ -5,6 +5,7 @@
 //   nrf_volume_to_channels_* <- layout change so one trilinear corner is one contiguous C-vector
 #include "common.cuh"
 #include "sortscan.cuh"
+#include "tc_ptx.cuh"
 
 namespace nrf {
 
@@ -333,6 +334,137 @@ __global__ void __launch_bounds__(256) encode_points_w32_kernel(EncodeArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The gather staged through TMA and shared memory (BASELINE north_star, subsystem 2).  The channels-last volume is a
+// 5-D tensor (C, S2, S1, S0, SB) to the TMA unit; the 2 x 2 x 2 voxel neighbourhood of a sample is ONE tile of that
+// tensor - box (C, 2, 2, 2, 1) = 8 rows of 512 B - so the lane that owns a sample fetches all eight corners with a
+// single cp.async.bulk.tensor.5d at coordinates (0, x0, y0, z0, scene), straight from its own registers: no corner
+// offsets, no bounds tests, no shuffles of addresses.  Corners outside the grid are the TMA unit's out-of-bounds
+// zero fill, which IS F.grid_sample's zeros padding (models_embed.py:275); a zero row adds +-0 to the sum, so the
+// latents are bit-identical to the kernels that skip those corners.  The box arrives in ATen's corner order
+// (x fastest, then y, then z).  Per warp: kTmaStages boxes of 4 KB in flight (mbarrier per stage), the warp consumes
+// box i (8 x LDS.128 per lane, the eight weights by shuffle from the owner) while boxes i+1 .. are on their way.
+// 128 channels, the w32 tail layout; NRF_ENCODE_TMA=0 falls back to encode_points_w32_kernel (A/B, tests).
+constexpr int kTmaWarps = 4;
+constexpr int kTmaBox = 8 * 128 * 4;             // bytes: 8 corners x 128 channels fp32
+
+__device__ __forceinline__ void tma_load_box5(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c1, int c2,
+                                              int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+template <typename T, int kTmaStages>
+__global__ void __launch_bounds__(kTmaWarps * 32) encode_points_tma_kernel(const __grid_constant__ CUtensorMap vmap,
+                                                                          EncodeArgs a) {
+  extern __shared__ uint8_t tma_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tma_smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t bars[kTmaWarps][kTmaStages];
+  int lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  const int wid = uniform_warp_idx();
+  const int64_t warp = (int64_t)blockIdx.x * kTmaWarps + wid;
+  const int64_t nwarps = (int64_t)gridDim.x * kTmaWarps;
+  const int64_t N = (int64_t)a.R * a.K;
+  const int64_t groups = (N + kWarp - 1) / kWarp;
+  T* out = reinterpret_cast<T*>(a.out);
+  constexpr int C = 128;
+  if (lane == 0) {
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(&bars[wid][s], 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x == 0) tma_prefetch_desc(&vmap);
+  __syncthreads();
+  const uint32_t slot0 = smem_u32(smem) + wid * kTmaStages * kTmaBox;
+  const uint32_t bar0 = smem_u32(&bars[wid][0]);
+  uint32_t n_issued = 0, n_done = 0;             // boxes of this warp so far: stage = n % stages, parity = (n / stages) & 1
+  for (int64_t grp = warp; grp < groups; grp += nwarps) {
+    const int64_t n = grp * kWarp + lane;
+    const bool valid = n < N;
+    const int64_t nn = valid ? n : N - 1;
+    const int r = (int)(nn / a.K);
+    const float4 ra = __ldg(reinterpret_cast<const float4*>(a.rays + (int64_t)r * 8));
+    const float4 rb = __ldg(reinterpret_cast<const float4*>(a.rays + (int64_t)r * 8) + 1);
+    const float ray[6] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y};
+    const SampleGeom g = sample_geometry(ray, __ldg(a.z + nn), a.bmin, a.bext);
+    const TriSetup ts = trilinear_setup(g.cx, g.cy, g.cz, a.S0, a.S1, a.S2);
+    if (valid) {
+      const float c[3] = {g.cx, g.cy, g.cz}, d[3] = {ra.w, rb.x, rb.y};
+      T* tail = out + n * a.ld_out + C;
+      constexpr int kPer = TailVec<T>::kPer;
+#pragma unroll
+      for (int j = 0; j < kTailW / kPer; ++j) {
+        float v[kPer];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) v[i] = tail_value(j * kPer + i, c, d, a.freq_factor);
+        TailVec<T>::store(tail + j * kPer, v);
+      }
+      if (a.points) {
+        a.points[n * 3 + 0] = g.px; a.points[n * 3 + 1] = g.py; a.points[n * 3 + 2] = g.pz;
+      }
+    }
+    const unsigned touch = __ballot_sync(0xffffffffu, valid && trilinear_touches(ts, a.S0, a.S1, a.S2));
+    if (a.touch && lane == 0) a.touch[grp] = touch != 0u;
+    const int scene = r / a.rays_per_scene;
+    float cw[8];                                  // the corner weights, (wx * wy) * wz in ATen's rounding order
+    {
+      Corner8 c8;
+      corners_from_setup(ts, a.S0, a.S1, a.S2, 1, c8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cw[k] = c8.w[k];
+    }
+    auto issue = [&](int s) {                     // the owner of sample s fetches its 2 x 2 x 2 x C box
+      if (lane == s) {
+        const uint32_t st = n_issued % kTmaStages;
+        const uint32_t bar = bar0 + st * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kTmaBox) : "memory");
+        tma_load_box5(slot0 + st * kTmaBox, &vmap, bar, ts.x0, ts.y0, ts.z0, scene);
+      }
+      ++n_issued;
+    };
+    // samples that touch the grid, in order; up to kTmaStages - 1 boxes ahead of the one being summed
+    unsigned ahead = touch;
+    for (int i = 0; i < kTmaStages - 1 && ahead; ++i) {
+      const int s = __ffs(ahead) - 1;
+      ahead &= ahead - 1;
+      issue(s);
+    }
+    unsigned todo = touch;
+    for (int s = 0; s < kWarp; ++s) {
+      if (grp * kWarp + s >= N) break;
+      T* row = out + (grp * kWarp + s) * a.ld_out;
+      if (!((todo >> s) & 1u)) {
+        store4<T>(row + lane * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        continue;
+      }
+      __syncwarp();                               // every lane is done with the slot the next box lands in
+      if (ahead) {
+        const int sn = __ffs(ahead) - 1;
+        ahead &= ahead - 1;
+        issue(sn);
+      }
+      float w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[k] = __shfl_sync(0xffffffffu, cw[k], s);
+      const uint32_t st = n_done % kTmaStages;
+      mbar_wait(&bars[wid][st], (n_done / kTmaStages) & 1);
+      ++n_done;
+      const uint32_t src = slot0 + st * kTmaBox + lane * 16;
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "r"(src + k * 512));
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = corner_acc(acc, v[k], w[k], a.fma);
+      store4<T>(row + lane * 4, acc);
+    }
+  }
+}
+
 struct ScatterArgs {
   const float* rays;
   const float* z;
@@ -445,7 +577,48 @@ static int encode_points_impl(const float* rays, const float* z, int R, int K, i
   int threads = 256;
   const bool w32 = num_freqs == kTailFreqs && ld_out == C + kTailW &&
                    (reinterpret_cast<uintptr_t>(rays) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-  if (w32) {                                   // 32 samples per warp iteration
+  const char* tma_env = getenv("NRF_ENCODE_TMA");             // "0": encode_points_w32_kernel (A/B, tests)
+  if (w32 && C == 128 && !(tma_env && atoi(tma_env) == 0) && (reinterpret_cast<uintptr_t>(vol_cl) & 15) == 0) {
+    // the corners through TMA boxes and shared memory (encode_points_tma_kernel)
+    EncodeTiledFn fn = encode_tiled_fn();
+    NRF_REQUIRE(fn != nullptr, NRF_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    CUtensorMap vmap;
+    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)S2, (cuuint64_t)S1, (cuuint64_t)S0, (cuuint64_t)SB};
+    cuuint64_t gstr[4] = {(cuuint64_t)C * 4, (cuuint64_t)S2 * C * 4, (cuuint64_t)S1 * S2 * C * 4,
+                          (cuuint64_t)S0 * S1 * S2 * C * 4};
+    cuuint32_t box[5] = {(cuuint32_t)C, 2, 2, 2, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult cr = fn(&vmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(vol_cl), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NRF_REQUIRE(cr == CUDA_SUCCESS, NRF_ECUDA, "cuTensorMapEncodeTiled(volume) failed (%d)", (int)cr);
+    static const int stages_env = getenv("NRF_ENCODE_TMA_STAGES") ? atoi(getenv("NRF_ENCODE_TMA_STAGES")) : 3;
+    const int stages = stages_env == 2 || stages_env == 4 ? stages_env : 3;
+    const int smem_bytes = kTmaWarps * stages * kTmaBox + 128;
+    int64_t want = ((N + 31) / 32 + kTmaWarps - 1) / kTmaWarps;
+    int per_sm = (227 * 1024) / (smem_bytes + 1024);
+    if (per_sm > 8) per_sm = 8;
+    int max_blocks = sm_count() * per_sm;
+    int blocks = (int)(want < max_blocks ? want : max_blocks);
+    LaunchScope ls_(NRF_CAT_ENCODE, as_stream(stream));
+#define NRF_ENC_TMA2(TT, NS)                                                                                         \
+    do {                                                                                                             \
+      NRF_CUDA_OK(cudaFuncSetAttribute(encode_points_tma_kernel<TT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,\
+                                       smem_bytes));                                                                 \
+      encode_points_tma_kernel<TT, NS><<<blocks, kTmaWarps * 32, smem_bytes, as_stream(stream)>>>(vmap, a);          \
+    } while (0)
+#define NRF_ENC_TMA(TT)                                                                                              \
+    do {                                                                                                             \
+      if (stages == 2) NRF_ENC_TMA2(TT, 2);                                                                          \
+      else if (stages == 4) NRF_ENC_TMA2(TT, 4);                                                                     \
+      else NRF_ENC_TMA2(TT, 3);                                                                                      \
+    } while (0)
+    if (out_bf16 == 2) NRF_ENC_TMA(__half);
+    else if (out_bf16) NRF_ENC_TMA(__nv_bfloat16);
+    else NRF_ENC_TMA(float);
+#undef NRF_ENC_TMA
+#undef NRF_ENC_TMA2
+  } else if (w32) {                            // 32 samples per warp iteration
     int64_t want = ((N + 31) / 32 + 7) / 8;
     int max_blocks = sm_count() * 8;
     int blocks = (int)(want < max_blocks ? want : max_blocks);

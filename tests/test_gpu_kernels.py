@@ -132,6 +132,36 @@ def _scene_inputs(SB, C, S, R_per, K, seed=0):
     return vol, rays, z
 
 
+@pytest.mark.parametrize("S,fma", [(24, False), (100, False), (7, True)])
+def test_encode_points_tma_box_gather_is_bit_identical(ops, monkeypatch, S, fma):
+    """encode_points_tma_kernel (NRF_ENCODE_TMA=1: a sample's eight corners as one 5-D TMA box, out-of-grid corners
+    zero-filled by the TMA unit) against encode_points_w32_kernel, which computes corner offsets and skips corners
+    outside the grid: every latent, tail value and touch flag bit for bit - rays that cross the faces of the box, end
+    inside it, or miss it; all three output types."""
+    SB, R_per, K, C = 2, 70, 48, 128
+    vol, rays, z = _scene_inputs(SB, C, S, R_per, K, seed=S)
+    g = torch.Generator().manual_seed(S)
+    b = torch.tensor(syn.BOUNDS)
+    n_in = 40                                   # ... plus rays that start inside the box and run through its faces
+    o = b[:3] + (b[3:] - b[:3]) * torch.rand(SB * n_in, 3, generator=g)
+    d = torch.nn.functional.normalize(torch.randn(SB * n_in, 3, generator=g), dim=-1) * 0.9
+    inside = torch.cat([o, d, torch.zeros(SB * n_in, 1), torch.ones(SB * n_in, 1)], 1)
+    rays = torch.cat([rays.view(SB, R_per, 8), inside.view(SB, n_in, 8)], 1).reshape(-1, 8).contiguous()
+    z = torch.cat([z.view(SB, R_per, K), torch.rand(SB, n_in, K, generator=g).sort(-1)[0]], 1).reshape(-1, K).contiguous()
+    R_per += n_in
+    vol_cl = ops.volume_to_channels_last(vol.cuda())
+    for prec in (ops.NRF_PREC_FP32, ops.NRF_PREC_BF16, ops.NRF_PREC_FP16):
+        res = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("NRF_ENCODE_TMA", mode)
+            res[mode] = ops.encode_points(rays.cuda(), z.cuda(), R_per, vol_cl, syn.BOUNDS, precision=prec, fma=fma,
+                                          want_points=True, want_touch=True)
+        for x, y in zip(res["0"], res["1"]):
+            assert torch.equal(x, y)
+        lat = res["0"][0][:, :C].float()
+        assert 0.05 < float((lat.abs().sum(1) > 0).float().mean()) < 0.95      # samples inside AND outside
+
+
 @pytest.mark.parametrize("C,S", [(128, 24), (16, 12), (64, 17)])
 def test_encode_points_fp32_matches_oracle(ops, C, S):
     SB, R_per, K = 2, 50, 24
