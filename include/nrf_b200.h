@@ -331,6 +331,13 @@ int nrf_mlp_fwd(const NrfMlpParams* p, const void* packed, int precision, const 
                 int64_t N, void* acts, float* field_out, void* stream);
 int nrf_mlp_fwd_layered(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
                         int64_t N, void* acts, float* field_out, void* stream);
+/* nrf_mlp_fwd with the flags nrf_encode_points_touch wrote for these N samples ((N + 31) / 32 bytes, or NULL): in the
+ * fused kernel a 256-sample tile without any flag set has an all-zero latent (zeros padding of F.grid_sample,
+ * models_embed.py:275), so the k-panels that multiply the latent - two of the first layer's three, the lin_z tails of
+ * fc_1 (resnetfc.py:181-182) - are neither loaded nor multiplied for it: the same accumulators bit for bit (they
+ * would have added exact zeros), 6 % fewer MMAs on such a tile.  The layer-by-layer paths ignore the flags. */
+int nrf_mlp_fwd_touch(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                      int64_t N, void* acts, float* field_out, const uint8_t* touch_flags, void* stream);
 
 /* Backward: d_field (N,dout_pad) operand-typed gradient of the raw outputs (from
  * nrf_composite_bwd); accumulates parameter gradients into `grads` and writes

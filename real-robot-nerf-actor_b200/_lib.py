@@ -80,6 +80,7 @@ _SIGNATURES = {
     "nrf_mlp_sizes": [C.POINTER(NrfMlpParams), _i, C.POINTER(NrfMlpSizes)],
     "nrf_mlp_pack": [C.POINTER(NrfMlpParams), _i, _p, _p],
     "nrf_mlp_fwd": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, _p],
+    "nrf_mlp_fwd_touch": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, _p, _p],
     "nrf_mlp_fwd_layered": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, _p],
     "nrf_mlp_fused_supported": [C.POINTER(NrfMlpParams), _i],
     "nrf_mlp_bwd": [C.POINTER(NrfMlpParams), _p, _i, _p, _i64, _p, _p, C.POINTER(NrfMlpGrads), _p, _p, _p],

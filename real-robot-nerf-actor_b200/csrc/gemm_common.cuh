@@ -50,6 +50,8 @@ struct FusedLayerDesc {
   const float* bias;   // forward
   int n_chunks;        // 128-wide output chunks of this layer; 0 = 4 (the 512 hidden units).  lin_out: nout_pad / 128
   int ext_col;         // first column of `in` the kb_z trailing k-panels are read from
+  int skip_head;       // forward: the first skip_head main k-panels multiply latent columns of `in` ...
+  int skip_z;          // ... and so do the kb_z trailing panels: both are all-zero for a tile without a sample in the grid
 };
 struct FusedDesc {
   int n_layers;
@@ -62,6 +64,8 @@ struct FusedDesc {
                                      // by the backward (same slot numbering as `saves` of the forward)
   float* out; int d_out; int ldo;    // forward: raw field outputs
   void* prof;                        // optional: 32 int64 cycle counters per CTA (diagnostics), NULL otherwise
+  const uint8_t* touch;              // forward, optional: one flag per 32 rows (nrf_encode_points_touch); a 256-row tile
+                                     // whose flags are all 0 has an all-zero latent: its latent k-panels are skipped
   int half;                          // forward only: fp16 operands (weights, field input, activations, residual stream;
                                      // NRF_PREC_FP16); what it SAVES for the backward is bf16 either way
 };

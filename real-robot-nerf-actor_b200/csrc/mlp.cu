@@ -255,7 +255,7 @@ static void* g_fused_prof = nullptr;
 extern "C" void nrf_debug_set_fused_profile(void* device_buffer) { g_fused_prof = device_buffer; }
 
 static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* W, const void* field_in, int64_t N,
-                         void* acts, float* field_out, int precision, cudaStream_t s) {
+                         void* acts, float* field_out, int precision, const uint8_t* touch, cudaStream_t s) {
   FusedDesc d;
   memset(&d, 0, sizeof(d));
   d.half = precision == NRF_PREC_FP16;
@@ -269,10 +269,12 @@ static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* 
   };
   // slots of `acts`: relu(x'_b) at b, relu(net_b) at nb + 1 + b (the layout nrf_mlp_bwd reads)
   add(W + L.W0, L.kin_pad, kbC + 1, 0, 0, 0, 1, 0, reinterpret_cast<const float*>(W + L.bias0));
+  d.L[0].skip_head = kbC;                          // [latent | PE + viewdir]: the latent k-panels come first
   for (int b = 0; b < L.nb; ++b) {
     add(W + L.Wfc0[b], L.H, kbH, 0, 1, 1, 0, L.nb + 1 + b, p->fc0_b[b]);
     add(W + L.Wfc1[b], L.k1cat[b], kbH, (b + 1 < L.nz) ? kbC : 0, 0, 2, 0, b + 1,
         reinterpret_cast<const float*>(W + L.bias1[b]));
+    d.L[l - 1].skip_z = 1;                         // the lin_z[b + 1] tail of fc_1 multiplies the latent
   }
   add(W + L.Wout, L.H, kbH, 0, 2, 1, 0, -1, reinterpret_cast<const float*>(W + L.bias_out));
   d.L[l - 1].n_chunks = L.nout_pad / 128;          // 4 at d_embed = 384 (388 outputs), 5 at d_embed = 512 (516)
@@ -284,6 +286,7 @@ static int mlp_fwd_fused(const NrfMlpParams* p, const MlpLayout& L, const char* 
   d.gate_bits = acts ? reinterpret_cast<char*>(acts) + (int64_t)(2 * L.nb + 1) * N * L.H * (int64_t)L.es : nullptr;
   d.out = field_out; d.d_out = L.Dout; d.ldo = (int)round_up(L.Dout, 4);   // pad columns receive exact zeros
   d.prof = g_fused_prof;
+  d.touch = touch;
   return mlp_fused_launch(d, s);
 }
 
@@ -333,7 +336,8 @@ extern "C" int nrf_mlp_fused_supported(const NrfMlpParams* p, int precision) {
 }
 
 static int mlp_fwd_impl(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
-                        int64_t N, void* acts, float* field_out, void* stream, bool allow_fused) {
+                        int64_t N, void* acts, float* field_out, void* stream, bool allow_fused,
+                        const uint8_t* touch = nullptr) {
   NRF_REQUIRE(packed && field_in && field_out && N > 0, NRF_EINVAL, "nrf_mlp_fwd: bad arguments");
   NRF_REQUIRE(N < (int64_t)1 << 31, NRF_ENOSUP, "nrf_mlp_fwd: N too large for one call");
   if (precision == NRF_PREC_BF16X3)
@@ -345,7 +349,7 @@ static int mlp_fwd_impl(const NrfMlpParams* p, const void* packed, int precision
   const char* W = reinterpret_cast<const char*>(packed);
   static const bool layered = getenv("NRF_MLP_LAYERED") != nullptr;
   if (allow_fused && is_tc(precision) && fused_supported(L) && !layered)
-    return mlp_fwd_fused(p, L, W, field_in, N, acts, field_out, precision, s);
+    return mlp_fwd_fused(p, L, W, field_in, N, acts, field_out, precision, touch, s);
   NRF_REQUIRE(acts, NRF_EINVAL, "nrf_mlp_fwd: the layer-by-layer chain needs the activation buffer");
   char* act = reinterpret_cast<char*>(acts);
   const int64_t layer = N * L.H * (int64_t)L.es;
@@ -391,6 +395,11 @@ static int mlp_fwd_impl(const NrfMlpParams* p, const void* packed, int precision
 extern "C" int nrf_mlp_fwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
                            int64_t N, void* acts, float* field_out, void* stream) {
   return mlp_fwd_impl(p, packed, precision, field_in, N, acts, field_out, stream, true);
+}
+
+extern "C" int nrf_mlp_fwd_touch(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
+                                 int64_t N, void* acts, float* field_out, const uint8_t* touch_flags, void* stream) {
+  return mlp_fwd_impl(p, packed, precision, field_in, N, acts, field_out, stream, true, touch_flags);
 }
 
 extern "C" int nrf_mlp_fwd_layered(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,

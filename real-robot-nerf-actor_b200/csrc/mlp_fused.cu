@@ -84,6 +84,7 @@ struct FLayer {
   int ext_col;             // first column of the global input the kb_z trailing k-panels come from
   int mask_slot;           // backward: slot of the forward's saved operand whose sign gates this layer's output
   int publish;             // the epilogue hands its output to the next layer's MMAs (a_ready)
+  int skip_head, skip_z;   // k-panels that multiply the latent (see FusedLayerDesc): no MMAs, no weight loads on a dead tile
   const float* bias;       // forward only
 };
 struct FArgs {
@@ -99,6 +100,8 @@ struct FArgs {
   uint2* gate_bits;                // slots x (N, 8) x 64 bits: bit-packed ReLU gates, written by the training forward
                                    // (one bit per saved operand element: non-zero) and read by the backward
   long long* prof;                 // NRF_FUSED_PROF=1: per-CTA cycle counters of the warp roles (see mlp_fused_launch)
+  const uint8_t* touch;            // optional: one flag per 32 samples "some corner inside the grid"; NULL: every tile live
+  int n_flags;                     // (N + 31) / 32
   FLayer L[kFusedMaxLayers];
 };
 struct FMaps {
@@ -260,6 +263,19 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorM
       "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
+}
+
+// A 256-sample tile none of whose eight 32-sample groups touches the grid: its latent columns are exact zeros
+// (zeros padding of the gather), so the k-panels that multiply them add nothing to any accumulator.
+__device__ __forceinline__ bool tile_dead(const uint8_t* touch, int n_flags, int tile) {
+  if (touch == nullptr) return false;
+  uint32_t any = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = tile * 8 + j;
+    if (i < n_flags) any |= __ldg(touch + i);
+  }
+  return any == 0;
 }
 
 // cycle accounting of the waits: compiled in only for the kProf instantiations (even a dormant run-time branch
@@ -513,15 +529,21 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
       PipeState st;
       long long t_empty = 0;
       const long long t_begin = clock64();
+      bool dead_n = !kBwd && n_iter > 0 && tile_dead(a.touch, a.n_flags, pair);
       for (int it = 0; it < n_iter; ++it) {
         const int row0 = ((pair + it * n_pairs) * 2 + (int)crank) * 128;
+        const bool dead = dead_n;                      // (the next tile's flags are fetched a tile ahead)
+        dead_n = !kBwd && it + 1 < n_iter && tile_dead(a.touch, a.n_flags, pair + (it + 1) * n_pairs);
         for (int l = 0; l < nl; ++l) {
           const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
           const int nc = a.L[l].n_chunks, ext_col = a.L[l].ext_col;
+          const int skip_head = dead ? a.L[l].skip_head : 0;
+          const bool skip_z = dead && a.L[l].skip_z;
           for (int c = 0; c < nc; ++c)
             for (int kb = 0; kb < kb_tot; kb += 2) {
               if (kProf && (a.dbg & 1)) continue;
               const int nk = kb_tot - kb < 2 ? 1 : 2;
+              if (kb >= kb_main ? skip_z : kb + nk <= skip_head) continue;   // a unit of latent k-panels, dead tile
               if (kb >= kb_main) {                     // this CTA's 128 rows of the trailing global A k-panels
                 for (int h = 0; h < nk; ++h) {
                   FUSED_TIMED(t_empty, mbar_wait(empty + st.stage, st.phase ^ 1));
@@ -578,19 +600,34 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
       uint32_t n = 0;                              // running chunk counter -> accumulator buffer / phase
       long long t_acc = 0, t_ready = 0, t_full = 0;
       const long long t_begin = clock64();
+      bool dead_n = !kBwd && n_iter > 0 && tile_dead(a.touch, a.n_flags, pair);
       for (int it = 0; it < n_iter; ++it) {
+        const bool dead = dead_n;
+        dead_n = !kBwd && it + 1 < n_iter && tile_dead(a.touch, a.n_flags, pair + (it + 1) * n_pairs);
         for (int l = 0; l < nl; ++l) {
           const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
           const int a_src = a.L[l].a_src;
           const uint32_t a_par = (uint32_t)(it * a.n_prod + l - 1) & 1;   // phase of the epilogue that produced A
           const int nc = a.L[l].n_chunks;
+          const int skip_head = dead ? a.L[l].skip_head : 0;
+          const bool skip_z = dead && a.L[l].skip_z;
           for (int c = 0; c < nc; ++c, ++n) {
             const uint32_t buf = n & 1;
             if (!(kProf && (a.dbg & 8))) FUSED_TIMED(t_acc, mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1));
             const uint32_t tmem_d = tmem_base + buf * 128;
+            uint32_t fresh = 1;                                            // the chunk's first MMA overwrites the accumulator
             for (int kb0 = 0; kb0 < kb_tot; kb0 += 2) {
               const int nk = kb_tot - kb0 < 2 ? 1 : 2;
               const bool ext = kb0 >= kb_main;                             // A k-panels arrive through the ring
+              if (ext ? skip_z : kb0 + nk <= skip_head) {                  // latent k-panels of a dead tile: exact zeros
+                // (the producer skipped their ring stages too; the first-layer panels still land in P - wait for them,
+                // so that nothing is in flight towards P when the next layers' epilogues write it)
+                if (!ext && c == 0 && a_src == kSrcIn && !(kProf && (a.dbg & 8))) {
+                  FUSED_TIMED(t_ready, mbar_wait(in_full + kb0, it & 1));
+                  if (nk == 2) FUSED_TIMED(t_ready, mbar_wait(in_full + kb0 + 1, it & 1));
+                }
+                continue;
+              }
               uint32_t pa0 = 0, pa1 = 0;                                    // smem A panels of the unit's k-blocks
               int sa0 = 0, sa1 = 0;
               if (ext) {
@@ -621,22 +658,25 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
               tc_fence_after();
               const uint32_t sb = sRing_u + st.stage * kFStageB;
               if (elect_one()) {
+                uint32_t f = fresh;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   if (h < nk && !(kProf && (a.dbg & 4))) {
                     const int kb = kb0 + h;
+                    if (!ext && kb < skip_head) continue;                  // one latent panel of a mixed unit (64-channel latent)
                     const uint64_t bdesc = make_sdesc(sb + h * kFBoxB, 16, 1024);
                     if (!ext && a_src == kSrcQ) {
                       const uint32_t ta = tmem_base + kFColQ + kb * 32;
 #pragma unroll
                       for (int k = 0; k < 4; ++k)
-                        umma_bf16_pair_ts(tmem_d, ta + k * 8, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        umma_bf16_pair_ts(tmem_d, ta + k * 8, bdesc + 2 * k, idesc, k != 0 || !f);
                     } else {
                       const uint64_t adesc = make_sdesc(h == 0 ? pa0 : pa1, 16, 1024);
 #pragma unroll
                       for (int k = 0; k < 4; ++k)
-                        umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0 || !f);
                     }
+                    f = 0;
                   }
                 }
                 if (!(kProf && (a.dbg & 1))) {
@@ -648,6 +688,7 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
                 }
               }
               __syncwarp();
+              fresh = 0;
               st.advance(kStages);
             }
             if (elect_one()) {
@@ -798,6 +839,9 @@ int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
     a.L[l].first = L.first; a.L[l].act_slot = d.saves ? L.act_slot : -1; a.L[l].bias = L.bias;
     a.L[l].mask_slot = L.mask_slot;
     a.L[l].n_chunks = nchunks; a.L[l].ext_col = L.ext_col;
+    a.L[l].skip_head = d.touch && !d.backward ? L.skip_head : 0;
+    a.L[l].skip_z = d.touch && !d.backward ? L.skip_z : 0;
+    NRF_REQUIRE(a.L[l].skip_head < L.kb_main, NRF_EINVAL, "mlp_fused: layer %d would skip all of its main k-panels", l);
     a.L[l].publish = l + 1 < d.n_layers && L.kind != 2;
     n_prod += a.L[l].publish;
   }
@@ -822,6 +866,8 @@ int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
   NRF_REQUIRE(a.l_p_free < d.n_layers - 1 || d.backward, NRF_EINVAL, "mlp_fused: forward programs end on lin_out");
   NRF_REQUIRE(n_prod == d.n_layers - 1, NRF_EINVAL, "mlp_fused: every layer but the last must feed the next");
   a.N = (int)d.N; a.d_out = d.d_out; a.ldo = d.ldo; a.out = d.out;
+  a.touch = d.backward ? nullptr : d.touch;
+  a.n_flags = (int)((d.N + 31) / 32);
   a.gate_bits = reinterpret_cast<uint2*>(d.gate_bits);
   a.saves = reinterpret_cast<uint32_t*>(d.saves);
   NRF_REQUIRE(!d.saves || d.gate_bits, NRF_EINVAL, "mlp_fused: saving needs the gate-bit buffer");

@@ -513,12 +513,13 @@ def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps, keep_acts=True, 
                 # for sample tiles that have one (three rays in four miss the box in the BASELINE camera set-up)
                 st.field_in = ops.encode_points(rays, z, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
                                                 ld_out=mlp.sizes.kin_pad, precision=mlp.precision,
-                                                want_touch=keep_acts and ren.skip_empty_latent_tiles)
+                                                want_touch=ren.skip_empty_latent_tiles)
                 st.touch = None
-                if keep_acts and ren.skip_empty_latent_tiles:
+                if ren.skip_empty_latent_tiles:
                     st.field_in, st.touch = st.field_in
             with _trace("resnetfc_infer", "resblock"):
-                st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=repack)
+                # ... and the forward skips the latent k-panels of 256-sample tiles that lie outside the grid altogether
+                st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=repack, touch=st.touch)
         outs = ops.composite_fwd(st.field_out, z, rays, ren._d_comp, ren.white_bkgd, sigma_noise=sig_noise)
     return st, outs
 
@@ -536,12 +537,12 @@ def _pass_forward_reuse(ren, mlp, vol_cl, rays, z_new, z_sorted, perm, base, rps
             with _trace("positional_enc"):
                 st.field_in = ops.encode_points(rays, z_new, rps, vol_cl, ren._bounds, ren._num_freqs, ren._freq_factor,
                                                 ld_out=mlp.sizes.kin_pad, precision=mlp.precision,
-                                                want_touch=keep_acts and ren.skip_empty_latent_tiles)
+                                                want_touch=ren.skip_empty_latent_tiles)
                 st.touch = None
-                if keep_acts and ren.skip_empty_latent_tiles:
+                if ren.skip_empty_latent_tiles:
                     st.field_in, st.touch = st.field_in
             with _trace("resnetfc_infer", "resblock"):
-                st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=False)
+                st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=False, touch=st.touch)
         outs = ops.composite_fwd(base.field_out, z_sorted, rays, ren._d_comp, ren.white_bkgd, sigma_noise=sig_noise,
                                  reuse=(st.field_out, perm, base.z.shape[1]))
     return st, outs
@@ -890,7 +891,8 @@ class NeuralRenderer(nn.Module):
         self.fused_loss = True                 # rgb / embed losses + their gradients in one kernel (nrf_render_loss)
         self.render_chunk_rays = 4096          # neural_rendering.py:482
         self.trace_ranges = True               # the reference's five profiler labels as record_function + NVTX ranges
-        # backward: dL/dlatent only for 128-sample tiles with a sample inside the grid (NRF_SKIP_EMPTY_TILES=0: all tiles)
+        # sample tiles without a sample inside the grid have an all-zero latent: the forward skips their latent k-panels,
+        # the backward their dL/dlatent and lin_z weight-gradient blocks (NRF_SKIP_EMPTY_TILES=0: every tile in full)
         self.skip_empty_latent_tiles = os.environ.get("NRF_SKIP_EMPTY_TILES", "1") != "0"
         self.keep_voxel_counts = False         # True: the backward leaves the per-voxel entry counts of its scatter in
         self.last_voxel_counts = None          # `last_voxel_counts` (what the sparse volume-gradient exchange sends)

@@ -601,8 +601,11 @@ class FieldMLP:
         return bool(_lib.load().nrf_mlp_fused_supported(C.byref(self._cparams()), self.precision))
 
     @_on_tensor_device
-    def forward(self, field_in, acts=None, keep_acts=True, layered=False, repack=None):
+    def forward(self, field_in, acts=None, keep_acts=True, layered=False, repack=None, touch=None):
         """field_in (N,kin_pad) -> (field_out (N,d_out) fp32 raw, acts buffer).
+
+        touch: the flags encode_points(want_touch=True) returned for these samples; the fused kernel then skips the
+        latent k-panels of 256-sample tiles that lie outside the grid altogether (same results bit for bit).
 
         keep_acts=False (inference): the fused kernel keeps nothing (acts is None); the layer-by-layer chain
         still needs its buffer.  layered=True forces the chain (A/B timing, parity tests).
@@ -616,9 +619,14 @@ class FieldMLP:
             acts = torch.empty(self.sizes.fwd_bytes_per_sample * N, device=dev, dtype=torch.uint8)
         # rows are d_out rounded up to whole float4s; the pad columns come back as exact zeros
         out = torch.empty(N, (self.dims[3] + 3) // 4 * 4, device=dev, dtype=torch.float32)
-        fn = lib.nrf_mlp_fwd_layered if layered else lib.nrf_mlp_fwd
-        check(fn(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
-                 ptr(acts), ptr(out), stream_ptr()), "nrf_mlp_fwd")
+        if touch is not None and not layered:
+            assert touch.is_cuda and touch.dtype == torch.uint8 and touch.numel() == (N + 31) // 32
+            check(lib.nrf_mlp_fwd_touch(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
+                                        ptr(acts), ptr(out), ptr(touch), stream_ptr()), "nrf_mlp_fwd_touch")
+        else:
+            fn = lib.nrf_mlp_fwd_layered if layered else lib.nrf_mlp_fwd
+            check(fn(C.byref(self._cparams()), ptr(packed), self.precision, ptr(field_in), N,
+                     ptr(acts), ptr(out), stream_ptr()), "nrf_mlp_fwd")
         if acts is not None:
             # the fused backward reads the bit-packed ReLU gates only the fused forward writes
             acts._nrf_layered = bool(layered or not self.fused)

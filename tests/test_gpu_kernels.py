@@ -508,6 +508,47 @@ def test_fused_mlp_forward_is_bit_identical_to_the_layered_chain(ops, C, N, D):
     assert rel(out_f, ref) < 3e-2
 
 
+@pytest.mark.parametrize("C,N,D,prec", [(128, 100000, 384, "bf16"), (128, 77777, 384, "fp16"), (64, 50000, 384, "bf16"),
+                                        (128, 40001, 512, "bf16"), (64, 3000, 512, "fp16"), (128, 200, 384, "bf16")])
+def test_fused_forward_skips_latent_panels_of_tiles_outside_the_grid(ops, C, N, D, prec):
+    """nrf_mlp_fwd_touch: a 256-sample tile whose flags say "no sample has a corner inside the grid" has an all-zero
+    latent; the fused forward neither loads nor multiplies the k-panels that meet it (two of the first layer's three,
+    the lin_z tails of fc_1; with a 64-channel latent one panel of a mixed unit).  Raw outputs, every saved operand and
+    the gate bits equal the unflagged run bit for bit - tiles that are dead, live, and dead only in part (those must
+    not be skipped), training and inference variants."""
+    mlp = _bf16_mlp(C=C, D=D, seed=3)
+    precision = ops.NRF_PREC_BF16 if prec == "bf16" else ops.NRF_PREC_FP16
+    h = mlp.handle(precision)
+    assert h.fused
+    dt = torch.bfloat16 if prec == "bf16" else torch.float16
+    g = torch.Generator().manual_seed(N)
+    fin = torch.zeros(N, h.sizes.kin_pad, dtype=dt)
+    fin[:, :C + 42] = (torch.randn(N, C + 42, generator=g) * 0.5).to(dt)
+    # runs of samples without a latent, the way rays that miss the box produce them: whole 32-sample groups
+    groups = (N + 31) // 32
+    live = torch.rand(groups, generator=g) < 0.5
+    run = torch.rand(groups // 24 + 1, generator=g) < 0.6                  # long dead stretches (whole tiles) ...
+    live &= ~run.repeat_interleave(24)[:groups]
+    live[-1] = N % 256 == 200                                              # ... and a ragged last tile either way
+    rows_live = live.repeat_interleave(32)[:N]
+    fin[~rows_live, :C] = 0
+    fin = fin.cuda()
+    touch = live.to(torch.uint8).cuda()
+    tiles = (N + 255) // 256
+    pad = torch.zeros(tiles * 8, dtype=torch.bool)
+    pad[:groups] = live
+    dead_tiles = int((~pad.view(tiles, 8).any(1)).sum())
+    assert dead_tiles > 0 or N < 1000
+    out0, acts0 = h.forward(fin)
+    out1, acts1 = h.forward(fin, touch=touch)
+    outi, _ = h.forward(fin, keep_acts=False, touch=touch)
+    print(f"C={C} N={N}: {dead_tiles} of {tiles} tiles dead")
+    assert torch.equal(out0, out1) and torch.equal(out0, outi)
+    n_ops = 11 * N * 512 * 2                                               # bytes: 11 saved operands, then the gate bits
+    n_gate = 11 * N * 64
+    assert torch.equal(acts0[:n_ops + n_gate], acts1[:n_ops + n_gate])
+
+
 @pytest.mark.parametrize("C,N,D", [(128, 256, 384), (128, 1000, 384), (128, 33000, 384), (64, 777, 384), (128, 3, 384),
                                    (64, 1000, 512), (128, 33000, 512), (64, 5, 512)])
 def test_fused_mlp_backward_is_bit_identical_to_the_layered_chain(ops, C, N, D):
