@@ -34,9 +34,17 @@ FLOP_FWD = 6_076_416          # per field evaluation
 FLOP_DGRAD = 6_033_408        # fwd minus the 42->512 input layer (no dgrad into PE / viewdirs)
 FLOP_WGRAD = 6_076_416
 FLOP_STEP = FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD     # 18 186 240
-# measured DRAM traffic of mlp_fused_kernel per launch at config 2 (ncu, profiles/r01c_fused_ncu.md):
-# (3.607 + 7.263 + 6.700 + 3.326) GB over the 4 launches of a step
-FUSED_DRAM_BYTES_PER_LAUNCH = 5.22e9
+# measured DRAM traffic of mlp_fused_kernel per launch at config 2 (ncu --set full, one step, 4 launches): read from
+# profiles/fused_traffic.json (written from the committed capture by scripts/summarize_ncu.py traffic)
+def _fused_traffic():
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "fused_traffic.json")))
+        return float(d["dram_bytes_per_launch"]), d["source"]
+    except Exception:
+        return 5.22e9, "profiles/r02b_fused_ncu.md"
+
+
+FUSED_DRAM_BYTES_PER_LAUNCH, FUSED_DRAM_SOURCE = _fused_traffic()
 
 
 def peaks():
@@ -296,6 +304,20 @@ def run_ours(args):
     lib.timing_begin()
     ms_total_ev, _ = timed_region(lambda: main.step(post_allreduce=post), K, dev, world)
     kern = lib.timing_end()
+    # sample tiles (256 evaluations) that lie outside the grid altogether: the fused forward skips their latent
+    # k-panels (exact zeros), 2 * 3 * C * 512 FLOP per evaluation that `achieved` below still counts as algorithmic work
+    ren._touch_log = []
+    main.step(post_allreduce=post)
+    torch.cuda.synchronize()
+    dead_evals = tiles_total = 0
+    for t in ren._touch_log:
+        n8 = (t.numel() + 7) // 8 * 8
+        tt = torch.zeros(n8, dtype=torch.uint8, device=t.device)
+        tt[:t.numel()] = t
+        live = tt.view(-1, 8).sum(1) > 0              # (uint8 .any() stays uint8: its ~ is not a logical not)
+        dead_evals += int((~live).sum()) * 256
+        tiles_total += live.numel()
+    ren._touch_log = None
     # a long timed region as well (20 steps are 0.3 s): >= 200 steps and >= 3 s, same step, same clock
     n_sus = 0 if args.sustain_steps <= 0 else max(args.sustain_steps, int(3000.0 / (ms_total / K)) + 1)
     sustained = None
@@ -339,10 +361,17 @@ def run_ours(args):
         dom_n = kern["gemm_tc"][1] + kern["simt"][1]
         dom_flops = (FLOP_FWD + FLOP_DGRAD) * main.evals * K
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    skipped_flops = dead_evals * flop_dz * K if fused_n > 0 else 0        # (2 * 3 * C * 512 per evaluation, as flop_dz)
+    executed = (dom_flops - skipped_flops) / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     roof = {"bound": "tensor", "kernel": dom_name, "achieved": round(achieved, 1),
             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4),
+            "executed": round(executed, 1), "frac_executed": round(executed / pk["bf16_tflops_sustained"], 4),
+            "executed_note": f"`achieved` counts the algorithmic FLOPs of the reference's MLP; {dead_evals} of "
+                             f"{main.evals} evaluations per step sit in 256-sample tiles without any sample inside the "
+                             "grid, whose all-zero latent the fused forward does not multiply (bit-identical results): "
+                             "`executed` leaves those products out",
             "traffic": FUSED_DRAM_BYTES_PER_LAUNCH if fused_n > 0 and args.workload == "config2" else None,
-            "traffic_source": "profiles/r02b_fused_ncu.md: dram__bytes_read.sum + dram__bytes_write.sum of the 4 "
+            "traffic_source": FUSED_DRAM_SOURCE + ": dram__bytes_read.sum + dram__bytes_write.sum of the 4 "
                               "mlp_fused_kernel launches of one config-2 step (ncu --set full), averaged per launch; "
                               "algorithmic bytes per launch = 5.13e9 (13.5 KB/eval forward, 12.7 KB/eval backward)",
             "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
@@ -424,7 +453,10 @@ def run_ours(args):
                           "encode_gbs": enc, "encode_frac_of_hbm": round(enc / pk["hbm_gbs"], 3) if enc else None,
                           "scatter_gbs": sca, "scatter_frac_of_hbm": round(sca / pk["hbm_gbs"], 3) if sca else None,
                           "note": "algorithmic bytes: gather 8 corners x 128 ch x 4 B = 4096 B per evaluation (SURVEY 8d); "
-                                  "scatter 4096 B per evaluation (the dense 0.97 GB gradient volume it also writes is not counted)"}
+                                  "scatter 4096 B per evaluation (the dense 0.97 GB gradient volume it also writes is not counted). "
+                                  "A fraction above 1 is not a DRAM rate: neighbouring samples share corner rows, which then "
+                                  "come from L2 (ncu, profiles/r02c_encode_tma_ncu.md: 0.66 GB of DRAM reads for 2.0 GB of "
+                                  "corner rows in the fine pass; the kernel moves 9.2 TB/s from L2 to the SMs)"}
         del ib
         release()
 

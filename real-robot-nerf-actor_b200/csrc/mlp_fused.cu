@@ -537,13 +537,13 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
         for (int l = 0; l < nl; ++l) {
           const int kb_main = a.L[l].kb_main, kb_tot = kb_main + a.L[l].kb_z;
           const int nc = a.L[l].n_chunks, ext_col = a.L[l].ext_col;
-          const int skip_head = dead ? a.L[l].skip_head : 0;
-          const bool skip_z = dead && a.L[l].skip_z;
+          // a dead tile walks [skip_head, kb_main) only: the units of latent k-panels in front and behind are left out
+          const int kb_begin = dead ? a.L[l].skip_head : 0;
+          const int kb_end = dead && a.L[l].skip_z ? kb_main : kb_tot;
           for (int c = 0; c < nc; ++c)
-            for (int kb = 0; kb < kb_tot; kb += 2) {
+            for (int kb = kb_begin; kb < kb_end; kb += 2) {
               if (kProf && (a.dbg & 1)) continue;
-              const int nk = kb_tot - kb < 2 ? 1 : 2;
-              if (kb >= kb_main ? skip_z : kb + nk <= skip_head) continue;   // a unit of latent k-panels, dead tile
+              const int nk = kb_end - kb < 2 ? 1 : 2;
               if (kb >= kb_main) {                     // this CTA's 128 rows of the trailing global A k-panels
                 for (int h = 0; h < nk; ++h) {
                   FUSED_TIMED(t_empty, mbar_wait(empty + st.stage, st.phase ^ 1));
@@ -609,25 +609,21 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
           const int a_src = a.L[l].a_src;
           const uint32_t a_par = (uint32_t)(it * a.n_prod + l - 1) & 1;   // phase of the epilogue that produced A
           const int nc = a.L[l].n_chunks;
-          const int skip_head = dead ? a.L[l].skip_head : 0;
-          const bool skip_z = dead && a.L[l].skip_z;
+          // a dead tile walks [kb_begin, kb_end) = [skip_head, kb_main) only (the producer leaves the same ring stages
+          // out): the latent k-panels in front and behind would add exact zeros.  The chunk's first MMA - k-block
+          // kb_begin, step 0 - overwrites the accumulator.
+          const int kb_begin = dead ? a.L[l].skip_head : 0;
+          const int kb_end = dead && a.L[l].skip_z ? kb_main : kb_tot;
+          if (kb_begin > 0 && a_src == kSrcIn && !(kProf && (a.dbg & 8)))
+            for (int kb = 0; kb < kb_begin; ++kb)        // the skipped first-layer panels still land in P: nothing may be
+              mbar_wait(in_full + kb, it & 1);          // in flight towards P when the next layers' epilogues write it
           for (int c = 0; c < nc; ++c, ++n) {
             const uint32_t buf = n & 1;
             if (!(kProf && (a.dbg & 8))) FUSED_TIMED(t_acc, mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1));
             const uint32_t tmem_d = tmem_base + buf * 128;
-            uint32_t fresh = 1;                                            // the chunk's first MMA overwrites the accumulator
-            for (int kb0 = 0; kb0 < kb_tot; kb0 += 2) {
-              const int nk = kb_tot - kb0 < 2 ? 1 : 2;
+            for (int kb0 = kb_begin; kb0 < kb_end; kb0 += 2) {
+              const int nk = kb_end - kb0 < 2 ? 1 : 2;
               const bool ext = kb0 >= kb_main;                             // A k-panels arrive through the ring
-              if (ext ? skip_z : kb0 + nk <= skip_head) {                  // latent k-panels of a dead tile: exact zeros
-                // (the producer skipped their ring stages too; the first-layer panels still land in P - wait for them,
-                // so that nothing is in flight towards P when the next layers' epilogues write it)
-                if (!ext && c == 0 && a_src == kSrcIn && !(kProf && (a.dbg & 8))) {
-                  FUSED_TIMED(t_ready, mbar_wait(in_full + kb0, it & 1));
-                  if (nk == 2) FUSED_TIMED(t_ready, mbar_wait(in_full + kb0 + 1, it & 1));
-                }
-                continue;
-              }
               uint32_t pa0 = 0, pa1 = 0;                                    // smem A panels of the unit's k-blocks
               int sa0 = 0, sa1 = 0;
               if (ext) {
@@ -658,25 +654,22 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
               tc_fence_after();
               const uint32_t sb = sRing_u + st.stage * kFStageB;
               if (elect_one()) {
-                uint32_t f = fresh;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   if (h < nk && !(kProf && (a.dbg & 4))) {
                     const int kb = kb0 + h;
-                    if (!ext && kb < skip_head) continue;                  // one latent panel of a mixed unit (64-channel latent)
                     const uint64_t bdesc = make_sdesc(sb + h * kFBoxB, 16, 1024);
                     if (!ext && a_src == kSrcQ) {
                       const uint32_t ta = tmem_base + kFColQ + kb * 32;
 #pragma unroll
                       for (int k = 0; k < 4; ++k)
-                        umma_bf16_pair_ts(tmem_d, ta + k * 8, bdesc + 2 * k, idesc, k != 0 || !f);
+                        umma_bf16_pair_ts(tmem_d, ta + k * 8, bdesc + 2 * k, idesc, ((kb ^ kb_begin) | k) != 0);
                     } else {
                       const uint64_t adesc = make_sdesc(h == 0 ? pa0 : pa1, 16, 1024);
 #pragma unroll
                       for (int k = 0; k < 4; ++k)
-                        umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0 || !f);
+                        umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb ^ kb_begin) | k) != 0);
                     }
-                    f = 0;
                   }
                 }
                 if (!(kProf && (a.dbg & 1))) {
@@ -688,7 +681,6 @@ mlp_fused_kernel(const __grid_constant__ FMaps maps, const __grid_constant__ FAr
                 }
               }
               __syncwarp();
-              fresh = 0;
               st.advance(kStages);
             }
             if (elect_one()) {
@@ -839,7 +831,7 @@ int mlp_fused_launch(const FusedDesc& d, cudaStream_t stream) {
     a.L[l].first = L.first; a.L[l].act_slot = d.saves ? L.act_slot : -1; a.L[l].bias = L.bias;
     a.L[l].mask_slot = L.mask_slot;
     a.L[l].n_chunks = nchunks; a.L[l].ext_col = L.ext_col;
-    a.L[l].skip_head = d.touch && !d.backward ? L.skip_head : 0;
+    a.L[l].skip_head = d.touch && !d.backward && L.skip_head % 2 == 0 ? L.skip_head : 0;   // whole units of two k-panels
     a.L[l].skip_z = d.touch && !d.backward ? L.skip_z : 0;
     NRF_REQUIRE(a.L[l].skip_head < L.kb_main, NRF_EINVAL, "mlp_fused: layer %d would skip all of its main k-panels", l);
     a.L[l].publish = l + 1 < d.n_layers && L.kind != 2;

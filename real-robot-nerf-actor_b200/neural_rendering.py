@@ -517,6 +517,9 @@ def _pass_forward(ren, mlp: ops.FieldMLP, vol_cl, rays, z, rps, keep_acts=True, 
                 st.touch = None
                 if ren.skip_empty_latent_tiles:
                     st.field_in, st.touch = st.field_in
+            log = getattr(ren, "_touch_log", None)             # bench.py: which sample tiles were skipped (for its FLOP count)
+            if log is not None and st.touch is not None:
+                log.append(st.touch)
             with _trace("resnetfc_infer", "resblock"):
                 # ... and the forward skips the latent k-panels of 256-sample tiles that lie outside the grid altogether
                 st.field_out, st.acts = mlp.forward(st.field_in, keep_acts=keep_acts, repack=repack, touch=st.touch)

@@ -63,5 +63,27 @@ def report(path):
         print()
 
 
+def traffic(path):
+    """DRAM bytes per launch of the mlp_fused_kernel launches in a capture -> JSON for bench.py's roofline.traffic
+    (python scripts/summarize_ncu.py traffic gpurun_out/X.ncu-rep profiles/X.md > profiles/fused_traffic.json)."""
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    per = []
+    for vals in rows[2:]:
+        if "mlp_fused_kernel" not in vals[hdr.index("Kernel Name")]:
+            continue
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(k)
+            tot += float(vals[i].replace(",", "")) * scale[units[i]]
+        per.append(tot)
+    print(json.dumps({"dram_bytes_per_launch": round(sum(per) / len(per)), "launches": len(per),
+                      "dram_bytes": [round(x) for x in per],
+                      "source": sys.argv[3] if len(sys.argv) > 3 else path}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2])
