@@ -344,9 +344,8 @@ __global__ void __launch_bounds__(256) encode_points_w32_kernel(EncodeArgs a) {
 // latents are bit-identical to the kernels that skip those corners.  The box arrives in ATen's corner order
 // (x fastest, then y, then z).  Per warp: kTmaStages boxes of 4 KB in flight (mbarrier per stage), the warp consumes
 // box i (8 x LDS.128 per lane, the eight weights by shuffle from the owner) while boxes i+1 .. are on their way.
-// 128 channels, the w32 tail layout; NRF_ENCODE_TMA=0 falls back to encode_points_w32_kernel (A/B, tests).
+// 64 or 128 channels, the w32 tail layout; NRF_ENCODE_TMA=0 falls back to encode_points_w32_kernel (A/B, tests).
 constexpr int kTmaWarps = 4;
-constexpr int kTmaBox = 8 * 128 * 4;             // bytes: 8 corners x 128 channels fp32
 
 __device__ __forceinline__ void tma_load_box5(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c1, int c2,
                                               int c3, int c4) {
@@ -356,7 +355,7 @@ __device__ __forceinline__ void tma_load_box5(uint32_t dst, const CUtensorMap* m
       : "memory");
 }
 
-template <typename T, int kTmaStages>
+template <typename T, int kTmaStages, int C>
 __global__ void __launch_bounds__(kTmaWarps * 32) encode_points_tma_kernel(const __grid_constant__ CUtensorMap vmap,
                                                                           EncodeArgs a) {
   extern __shared__ uint8_t tma_smem_raw[];
@@ -370,14 +369,15 @@ __global__ void __launch_bounds__(kTmaWarps * 32) encode_points_tma_kernel(const
   const int64_t N = (int64_t)a.R * a.K;
   const int64_t groups = (N + kWarp - 1) / kWarp;
   T* out = reinterpret_cast<T*>(a.out);
-  constexpr int C = 128;
+  constexpr int kBox = 8 * C * 4;                  // bytes: 8 corners x C channels fp32 (a lane owns 4 channels: C = 64
+                                                   // leaves the upper half-warp idle in the sums, as in the LDG kernel)
   if (lane == 0) {
     for (int s = 0; s < kTmaStages; ++s) mbar_init(&bars[wid][s], 1);
     fence_barrier_init();
   }
   if (threadIdx.x == 0) tma_prefetch_desc(&vmap);
   __syncthreads();
-  const uint32_t slot0 = smem_u32(smem) + wid * kTmaStages * kTmaBox;
+  const uint32_t slot0 = smem_u32(smem) + wid * kTmaStages * kBox;
   const uint32_t bar0 = smem_u32(&bars[wid][0]);
   uint32_t n_issued = 0, n_done = 0;             // boxes of this warp so far: stage = n % stages, parity = (n / stages) & 1
   for (int64_t grp = warp; grp < groups; grp += nwarps) {
@@ -419,8 +419,8 @@ __global__ void __launch_bounds__(kTmaWarps * 32) encode_points_tma_kernel(const
       if (lane == s) {
         const uint32_t st = n_issued % kTmaStages;
         const uint32_t bar = bar0 + st * 8;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kTmaBox) : "memory");
-        tma_load_box5(slot0 + st * kTmaBox, &vmap, bar, ts.x0, ts.y0, ts.z0, scene);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kBox) : "memory");
+        tma_load_box5(slot0 + st * kBox, &vmap, bar, ts.x0, ts.y0, ts.z0, scene);
       }
       ++n_issued;
     };
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32) encode_points_tma_kernel(const
       if (grp * kWarp + s >= N) break;
       T* row = out + (grp * kWarp + s) * a.ld_out;
       if (!((todo >> s) & 1u)) {
-        store4<T>(row + lane * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (lane * 4 < C) store4<T>(row + lane * 4, make_float4(0.f, 0.f, 0.f, 0.f));
         continue;
       }
       __syncwarp();                               // every lane is done with the slot the next box lands in
@@ -451,16 +451,18 @@ __global__ void __launch_bounds__(kTmaWarps * 32) encode_points_tma_kernel(const
       const uint32_t st = n_done % kTmaStages;
       mbar_wait(&bars[wid][st], (n_done / kTmaStages) & 1);
       ++n_done;
-      const uint32_t src = slot0 + st * kTmaBox + lane * 16;
-      float4 v[8];
+      const uint32_t src = slot0 + st * kBox + lane * 16;
+      if (lane * 4 < C) {
+        float4 v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "r"(src + k * 512));
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 8; ++k)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "r"(src + k * (C * 4)));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc = corner_acc(acc, v[k], w[k], a.fma);
-      store4<T>(row + lane * 4, acc);
+        for (int k = 0; k < 8; ++k) acc = corner_acc(acc, v[k], w[k], a.fma);
+        store4<T>(row + lane * 4, acc);
+      }
     }
   }
 }
@@ -578,7 +580,8 @@ static int encode_points_impl(const float* rays, const float* z, int R, int K, i
   const bool w32 = num_freqs == kTailFreqs && ld_out == C + kTailW &&
                    (reinterpret_cast<uintptr_t>(rays) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   const char* tma_env = getenv("NRF_ENCODE_TMA");             // "0": encode_points_w32_kernel (A/B, tests)
-  if (w32 && C == 128 && !(tma_env && atoi(tma_env) == 0) && (reinterpret_cast<uintptr_t>(vol_cl) & 15) == 0) {
+  if (w32 && (C == 128 || C == 64) && S0 >= 2 && S1 >= 2 && S2 >= 2 && !(tma_env && atoi(tma_env) == 0) &&
+      (reinterpret_cast<uintptr_t>(vol_cl) & 15) == 0) {
     // the corners through TMA boxes and shared memory (encode_points_tma_kernel)
     EncodeTiledFn fn = encode_tiled_fn();
     NRF_REQUIRE(fn != nullptr, NRF_ECUDA, "cuTensorMapEncodeTiled entry point not found");
@@ -594,18 +597,23 @@ static int encode_points_impl(const float* rays, const float* z, int R, int K, i
     NRF_REQUIRE(cr == CUDA_SUCCESS, NRF_ECUDA, "cuTensorMapEncodeTiled(volume) failed (%d)", (int)cr);
     static const int stages_env = getenv("NRF_ENCODE_TMA_STAGES") ? atoi(getenv("NRF_ENCODE_TMA_STAGES")) : 3;
     const int stages = stages_env == 2 || stages_env == 4 ? stages_env : 3;
-    const int smem_bytes = kTmaWarps * stages * kTmaBox + 128;
+    const int smem_bytes = kTmaWarps * stages * (8 * C * 4) + 128;
     int64_t want = ((N + 31) / 32 + kTmaWarps - 1) / kTmaWarps;
     int per_sm = (227 * 1024) / (smem_bytes + 1024);
     if (per_sm > 8) per_sm = 8;
     int max_blocks = sm_count() * per_sm;
     int blocks = (int)(want < max_blocks ? want : max_blocks);
     LaunchScope ls_(NRF_CAT_ENCODE, as_stream(stream));
+#define NRF_ENC_TMA3(TT, NS, CC)                                                                                     \
+    do {                                                                                                             \
+      NRF_CUDA_OK(cudaFuncSetAttribute(encode_points_tma_kernel<TT, NS, CC>,                                         \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));                    \
+      encode_points_tma_kernel<TT, NS, CC><<<blocks, kTmaWarps * 32, smem_bytes, as_stream(stream)>>>(vmap, a);      \
+    } while (0)
 #define NRF_ENC_TMA2(TT, NS)                                                                                         \
     do {                                                                                                             \
-      NRF_CUDA_OK(cudaFuncSetAttribute(encode_points_tma_kernel<TT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,\
-                                       smem_bytes));                                                                 \
-      encode_points_tma_kernel<TT, NS><<<blocks, kTmaWarps * 32, smem_bytes, as_stream(stream)>>>(vmap, a);          \
+      if (C == 128) NRF_ENC_TMA3(TT, NS, 128);                                                                       \
+      else NRF_ENC_TMA3(TT, NS, 64);                                                                                 \
     } while (0)
 #define NRF_ENC_TMA(TT)                                                                                              \
     do {                                                                                                             \
@@ -618,6 +626,7 @@ static int encode_points_impl(const float* rays, const float* z, int R, int K, i
     else NRF_ENC_TMA(float);
 #undef NRF_ENC_TMA
 #undef NRF_ENC_TMA2
+#undef NRF_ENC_TMA3
   } else if (w32) {                            // 32 samples per warp iteration
     int64_t want = ((N + 31) / 32 + 7) / 8;
     int max_blocks = sm_count() * 8;

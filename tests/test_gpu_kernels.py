@@ -132,13 +132,13 @@ def _scene_inputs(SB, C, S, R_per, K, seed=0):
     return vol, rays, z
 
 
-@pytest.mark.parametrize("S,fma", [(24, False), (100, False), (7, True)])
-def test_encode_points_tma_box_gather_is_bit_identical(ops, monkeypatch, S, fma):
+@pytest.mark.parametrize("S,fma,C", [(24, False, 128), (100, False, 128), (7, True, 128), (17, False, 64), (12, True, 64)])
+def test_encode_points_tma_box_gather_is_bit_identical(ops, monkeypatch, S, fma, C):
     """encode_points_tma_kernel (NRF_ENCODE_TMA=1: a sample's eight corners as one 5-D TMA box, out-of-grid corners
     zero-filled by the TMA unit) against encode_points_w32_kernel, which computes corner offsets and skips corners
     outside the grid: every latent, tail value and touch flag bit for bit - rays that cross the faces of the box, end
     inside it, or miss it; all three output types."""
-    SB, R_per, K, C = 2, 70, 48, 128
+    SB, R_per, K = 2, 70, 48
     vol, rays, z = _scene_inputs(SB, C, S, R_per, K, seed=S)
     g = torch.Generator().manual_seed(S)
     b = torch.tensor(syn.BOUNDS)
