@@ -200,6 +200,19 @@ __device__ __forceinline__ uint32_t gate_push(uint32_t G, uint32_t w) {
   const uint32_t t = w + 0x7fff7fffu;
   return ((G >> 1) & 0x7fff7fffu) | (t & 0x80008000u);
 }
+// the same gate word built in place: HSET2 gives 0xffff per non-zero half of the (non-negative) pair, one LOP3 drops
+// its bits j and 16 + j into G - two instructions per pair where the shift-merge above needs three
+template <bool kHalf>
+__device__ __forceinline__ uint32_t gate_set(uint32_t G, uint32_t w, int j) {
+#ifdef NRF_GATE_PUSH                    // A/B build: the shift-merge form (the same bits)
+  (void)j;
+  return gate_push(G, w);
+#endif
+  uint32_t m;
+  if (kHalf) asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(w), "r"(0u));
+  else asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(w), "r"(0u));
+  return G | (m & (0x00010001u << j));
+}
 __device__ __forceinline__ uint32_t gate_mask(uint32_t G, int j) {
   uint32_t m;                                  // selector nibble 8+k: the MSB of byte k replicated over the byte
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(G << (15 - j)), "r"(0u), "r"(0xBB99u));
@@ -417,8 +430,8 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
         uint32_t g0 = 0u, g1 = 0u;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          g0 = gate_push(g0, w[j]);
-          g1 = gate_push(g1, w[16 + j]);
+          g0 = gate_set<kHalf>(g0, w[j], j);
+          g1 = gate_set<kHalf>(g1, w[16 + j], j);
         }
         a.gate_bits[((int64_t)L.act_slot * a.N + row0 + e.row) * 8 + c * 2 + e.g] = make_uint2(g0, g1);
       }
@@ -451,8 +464,8 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
         uint32_t g0 = 0u, g1 = 0u;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          g0 = gate_push(g0, w[j]);
-          g1 = gate_push(g1, w[16 + j]);
+          g0 = gate_set<kHalf>(g0, w[j], j);
+          g1 = gate_set<kHalf>(g1, w[16 + j], j);
         }
         a.gate_bits[((int64_t)L.act_slot * a.N + row0 + e.row) * 8 + c * 2 + e.g] = make_uint2(g0, g1);
       }
