@@ -202,6 +202,20 @@ __device__ __forceinline__ uint32_t gate_push(uint32_t G, uint32_t w) {
 }
 // the same gate word built in place: HSET2 gives 0xffff per non-zero half of the (non-negative) pair, one LOP3 drops
 // its bits j and 16 + j into G - two instructions per pair where the shift-merge above needs three
+// 0xffff per half that is > 0: ReLU is `x & mask` (what max(x, 0) gives, -0 and NaN included: both -> +0) and the gate
+// bits come from the same mask
+template <bool kHalf>
+__device__ __forceinline__ uint32_t pos_mask(uint32_t x) {
+  uint32_t m;
+  if (kHalf) asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(0u));
+  else asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(0u));
+  return m;
+}
+#ifdef NRF_RELU_MAX
+constexpr bool kReluMask = false;      // A/B build: max.bf16x2 for the ReLU, the gate bits from the result
+#else
+constexpr bool kReluMask = true;
+#endif
 template <bool kHalf>
 __device__ __forceinline__ uint32_t gate_set(uint32_t G, uint32_t w, int j) {
 #ifdef NRF_GATE_PUSH                    // A/B build: the shift-merge form (the same bits)
@@ -352,6 +366,8 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
   if (e.lane == 0) mbar_arrive_leader_u32(e.acc_empty + buf * 8);
   const uint32_t prow = e.sP + (2 * c + e.g) * kFPanel + e.row * 128;
   uint32_t w[32];                              // this thread's 64 outputs of the chunk as packed bf16 operand values
+  uint32_t gacc[2] = {0u, 0u};                 // training forward: the two gate words of these 64 outputs
+  constexpr bool kMaskRelu = kReluMask && kSave && !kBwd;
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const uint32_t gw = s == 0 ? gate.x : gate.y;    // backward: gate word of this sub-chunk
@@ -390,7 +406,13 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
           xb = first ? (xb & m) : ((xb & m) | (r & ~m));
         }
         xr[s * 16 + j] = xb;
-        w[s * 16 + j] = kBwd ? xb : relu_op16x2<kHalf>(xb);
+        if (kMaskRelu) {
+          const uint32_t m = pos_mask<kHalf>(xb);
+          w[s * 16 + j] = xb & m;
+          gacc[s] |= m & (0x00010001u << j);
+        } else {
+          w[s * 16 + j] = kBwd ? xb : relu_op16x2<kHalf>(xb);
+        }
       }
       if (L.publish)
         tmem_st16(e.tmem_base + kFColQ + e.lane_off + (uint32_t)(col0 / 2 + s * 16),
@@ -398,8 +420,15 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        w[s * 16 + j] = kBwd ? (cvt_op16x2<kHalf>(x2[j]) & gate_mask(gw, j))
-                             : relu_op16x2<kHalf>(cvt_op16x2<kHalf>(x2[j]));
+        if (kMaskRelu) {
+          const uint32_t xb = cvt_op16x2<kHalf>(x2[j]);
+          const uint32_t m = pos_mask<kHalf>(xb);
+          w[s * 16 + j] = xb & m;
+          gacc[s] |= m & (0x00010001u << j);
+        } else {
+          w[s * 16 + j] = kBwd ? (cvt_op16x2<kHalf>(x2[j]) & gate_mask(gw, j))
+                               : relu_op16x2<kHalf>(cvt_op16x2<kHalf>(x2[j]));
+        }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         sts128(prow + (((uint32_t)(s * 4 + j) ^ e.sw128) << 4), w[s * 16 + 4 * j], w[s * 16 + 4 * j + 1],
@@ -427,11 +456,13 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
                          : make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
       }
       if (!kBwd && row0 + e.row < a.N) {
-        uint32_t g0 = 0u, g1 = 0u;
+        uint32_t g0 = gacc[0], g1 = gacc[1];
+        if (!kMaskRelu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          g0 = gate_set<kHalf>(g0, w[j], j);
-          g1 = gate_set<kHalf>(g1, w[16 + j], j);
+          for (int j = 0; j < 16; ++j) {
+            g0 = gate_set<kHalf>(g0, w[j], j);
+            g1 = gate_set<kHalf>(g1, w[16 + j], j);
+          }
         }
         a.gate_bits[((int64_t)L.act_slot * a.N + row0 + e.row) * 8 + c * 2 + e.g] = make_uint2(g0, g1);
       }
@@ -461,11 +492,13 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const FMaps& maps, const FA
         bulk_commit();
       }
       if (!kBwd && row0 + e.row < a.N) {
-        uint32_t g0 = 0u, g1 = 0u;
+        uint32_t g0 = gacc[0], g1 = gacc[1];
+        if (!kMaskRelu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          g0 = gate_set<kHalf>(g0, w[j], j);
-          g1 = gate_set<kHalf>(g1, w[16 + j], j);
+          for (int j = 0; j < 16; ++j) {
+            g0 = gate_set<kHalf>(g0, w[j], j);
+            g1 = gate_set<kHalf>(g1, w[16 + j], j);
+          }
         }
         a.gate_bits[((int64_t)L.act_slot * a.N + row0 + e.row) * 8 + c * 2 + e.g] = make_uint2(g0, g1);
       }
