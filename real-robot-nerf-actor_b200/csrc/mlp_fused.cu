@@ -193,7 +193,9 @@ __device__ __forceinline__ uint64_t unpack_op16x2(uint32_t r) {  // packed bf16 
 
 // Bit-packed ReLU gates.  A gate word covers one 32-column sub-chunk of one row: bit j / bit 16+j = element 2j /
 // 2j+1 of the saved (ReLU'd, packed bf16) operand is non-zero.
-//   forward : 16 x gate_push(G, w_j)   (w + 0x7fff7fff carries "non-zero" into bits 15 / 31 of a non-negative pair)
+//   forward : G |= pos_mask(x_j) & (0x00010001 << j), the same mask that applies the ReLU (kReluMask); the first form,
+//             16 x gate_push(G, w_j)   (w + 0x7fff7fff carries "non-zero" into bits 15 / 31 of a non-negative pair),
+//             is kept for the A/B builds
 //   backward: gate_mask(G, j) = per-half 0xffff / 0 for pair j  (shift the two flags to the byte MSBs, PRMT
 //             replicates them over the halves)
 __device__ __forceinline__ uint32_t gate_push(uint32_t G, uint32_t w) {
