@@ -198,10 +198,12 @@ __device__ __forceinline__ uint64_t unpack_op16x2(uint32_t r) {  // packed bf16 
 //             is kept for the A/B builds
 //   backward: gate_mask(G, j) = per-half 0xffff / 0 for pair j  (shift the two flags to the byte MSBs, PRMT
 //             replicates them over the halves)
+#ifdef NRF_GATE_PUSH
 __device__ __forceinline__ uint32_t gate_push(uint32_t G, uint32_t w) {
   const uint32_t t = w + 0x7fff7fffu;
   return ((G >> 1) & 0x7fff7fffu) | (t & 0x80008000u);
 }
+#endif
 // the same gate word built in place: HSET2 gives 0xffff per non-zero half of the (non-negative) pair, one LOP3 drops
 // its bits j and 16 + j into G - two instructions per pair where the shift-merge above needs three
 // 0xffff per half that is > 0: ReLU is `x & mask` (what max(x, 0) gives, -0 and NaN included: both -> +0) and the gate
