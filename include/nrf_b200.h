@@ -95,6 +95,11 @@ int nrf_sample_coarse(const float* rays, int R, int Kc, const float* base, const
  * weights (R,Kc) coarse compositing weights, or cdf (R,Kc+1) when `cdf` is non-NULL (then weights
  * is ignored); u, jitter (R,Kf) (jitter NULL = 0).  Writes z_out[r*ldz + k], k<Kf, and, when
  * ind_out != NULL, the bin indices (R,Kf) as fp32 (the reference's `inds`). */
+#define NRF_FINE_CUDA_EAGER 0x100 /* OR into `lindisp`: build the cdf from the weights in the association order of ATen's CUDA
+                                    kernels (torch.sum: strided / float4 partials + shuffle-down tree; torch.cumsum: 32-element
+                                    chunks, 16-thread Sklansky network) instead of the CPU back end's (double accumulation):
+                                    bit-identical cdf, indices and depths to a GPU run of neural_rendering.py:189-207.
+                                    Kc = 64 or 128 (measured: scripts/cdf_probe.py, tests/test_gpu_bench_sizes.py). */
 int nrf_sample_fine(const float* rays, const float* weights, const float* cdf, int R, int Kc,
                     const float* u, const float* jitter, int Kf, int lindisp, float* z_out, int ldz,
                     float* ind_out, void* stream);

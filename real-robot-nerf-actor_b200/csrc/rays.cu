@@ -101,12 +101,19 @@ __global__ void sample_coarse_kernel(const float* __restrict__ rays, int R, int 
 
 // One warp per ray.  cdf is either given (bit-exact path: identical (cdf,u,jitter) -> identical
 // (ind,z)) or built here from the weights: pdf = (w+1e-5)/sum, cdf = cumsum(pdf) accumulated in
-// double and rounded to fp32 per entry (the CPU-ATen cumsum bit pattern).
+// double and rounded to fp32 per entry (the CPU-ATen cumsum bit pattern), or - flags & NRF_FINE_CUDA_EAGER,
+// Kc = 64 / 128 - in the association order ATen's CUDA kernels use (scripts/cdf_probe.py, bit for bit on B200):
+//   torch.sum     Kc = 64: lane t adds elements t and t + 32; Kc = 128: lane t adds its float4 ((e0+e1)+e2)+e3;
+//                 then a shuffle-down tree with offsets 16, 8, 4, 2, 1
+//   the division  IEEE
+//   torch.cumsum  chunks of 32 elements, the running total added to a chunk's first element, then a 16-thread
+//                 Sklansky network (5 steps: thread t adds element a - 1 to element a + t % s, a = (t / s) 2 s + s)
 __global__ void sample_fine_kernel(const float* __restrict__ rays, const float* __restrict__ weights,
                                    const float* __restrict__ cdf_in, int R, int Kc,
                                    const float* __restrict__ u, const float* __restrict__ jitter,
-                                   int Kf, int lindisp, float* __restrict__ z_out, int ldz,
+                                   int Kf, int flags, float* __restrict__ z_out, int ldz,
                                    float* __restrict__ ind_out) {
+  const int lindisp = flags & 1;
   extern __shared__ float smem[];
   int warps = blockDim.x / kWarp;
   int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -115,6 +122,37 @@ __global__ void sample_fine_kernel(const float* __restrict__ rays, const float* 
   if (r >= R) return;
   if (cdf_in) {
     for (int k = lane; k <= Kc; k += kWarp) cdf[k] = cdf_in[(int64_t)r * (Kc + 1) + k];
+  } else if (flags & NRF_FINE_CUDA_EAGER) {
+    const float* w = weights + (int64_t)r * Kc;
+    float a;
+    if (Kc == 64) {
+      a = __fadd_rn(__fadd_rn(w[lane], 1e-5f), __fadd_rn(w[lane + 32], 1e-5f));
+    } else {                                       // Kc == 128
+      const float4 v = *reinterpret_cast<const float4*>(w + 4 * lane);
+      a = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(v.x, 1e-5f), __fadd_rn(v.y, 1e-5f)), __fadd_rn(v.z, 1e-5f)),
+                    __fadd_rn(v.w, 1e-5f));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, o));
+    const float total = __shfl_sync(0xffffffffu, a, 0);
+    if (lane == 0) cdf[0] = 0.0f;
+    for (int k = lane; k < Kc; k += kWarp) cdf[k + 1] = __fdiv_rn(__fadd_rn(w[k], 1e-5f), total);
+    __syncwarp();
+    for (int c0 = 0; c0 < Kc; c0 += 32) {
+      float* buf = cdf + 1 + c0;
+      if (lane == 0 && c0 > 0) buf[0] = __fadd_rn(buf[0], cdf[c0]);     // the total of the chunks before
+      __syncwarp();
+#pragma unroll
+      for (int sft = 0; sft < 5; ++sft) {
+        const int st = 1 << sft;
+        if (lane < 16) {
+          const int base = (lane >> sft) * (2 * st) + st;
+          const int ti = base + (lane & (st - 1)), si = base - 1;
+          buf[ti] = __fadd_rn(buf[ti], buf[si]);
+        }
+        __syncwarp();
+      }
+    }
   } else {
     const float* w = weights + (int64_t)r * Kc;
     // sum of (w + 1e-5) in fp32 element order-independent double accumulation
@@ -245,6 +283,9 @@ extern "C" int nrf_sample_fine(const float* rays, const float* weights, const fl
   NRF_REQUIRE(rays && (weights || cdf) && u && z_out && R > 0 && Kc > 0 && Kf > 0 && ldz >= Kf,
               NRF_EINVAL, "nrf_sample_fine: bad args");
   NRF_REQUIRE(Kc <= 4096, NRF_ENOSUP, "nrf_sample_fine: Kc > 4096");
+  NRF_REQUIRE(!(lindisp & NRF_FINE_CUDA_EAGER) || cdf || ((Kc == 64 || Kc == 128) &&
+              (reinterpret_cast<uintptr_t>(weights) & 15) == 0), NRF_ENOSUP,
+              "nrf_sample_fine: the CUDA-eager cdf pattern is known for Kc = 64 / 128 (Kc = %d)", Kc);
   int warps = 4;
   size_t smem = (size_t)warps * (Kc + 1) * sizeof(float);
   { LaunchScope ls_(NRF_CAT_SAMPLING, as_stream(stream));

@@ -138,10 +138,16 @@ def sample_coarse(rays, n_coarse, jitter=None, lindisp=False):
     return z
 
 
+FINE_CUDA_EAGER = False  # True: the in-kernel cdf in ATen's CUDA association order (Kc = 64 / 128), like RAYGEN_FLAGS / GATHER_FMA
+NRF_FINE_CUDA_EAGER = 0x100
+
+
 @_on_tensor_device
 def sample_fine(rays, weights, n_coarse, u, jitter=None, lindisp=False, cdf=None, out=None,
-                want_ind=False):
-    """neural_rendering.py:179-207.  Returns z (R,Kf) (written into out[:, :Kf] when given)."""
+                want_ind=False, cuda_eager=None):
+    """neural_rendering.py:179-207.  Returns z (R,Kf) (written into out[:, :Kf] when given).
+    cuda_eager: build the cdf the way a GPU run of the reference does (bit-identical indices and depths to CUDA-eager
+    PyTorch for 64 / 128 coarse samples); default: the CPU back end's pattern (module default FINE_CUDA_EAGER)."""
     rays = _f32(rays, "rays")
     u = _f32(u, "u")
     R, Kf = u.shape
@@ -152,8 +158,10 @@ def sample_fine(rays, weights, n_coarse, u, jitter=None, lindisp=False, cdf=None
         out = torch.empty(R, Kf, device=rays.device, dtype=torch.float32)
     assert out.is_contiguous() and out.shape[0] == R and out.shape[1] >= Kf
     ind = torch.empty(R, Kf, device=rays.device, dtype=torch.float32) if want_ind else None
+    eager = FINE_CUDA_EAGER if cuda_eager is None else cuda_eager
+    mode = int(bool(lindisp)) | (NRF_FINE_CUDA_EAGER if eager and cdf is None and n_coarse in (64, 128) else 0)
     check(_lib.load().nrf_sample_fine(ptr(rays), ptr(weights), ptr(cdf), R, n_coarse, ptr(u), ptr(jitter),
-                                      Kf, int(lindisp), ptr(out), out.shape[1], ptr(ind), stream_ptr()),
+                                      Kf, mode, ptr(out), out.shape[1], ptr(ind), stream_ptr()),
           "nrf_sample_fine")
     return (out, ind) if want_ind else out
 

@@ -283,6 +283,16 @@ def test_stages_against_the_oracle_run_on_the_device(mods):
     zf2, ind2 = ops.sample_fine(rays, w_ref, 64, noise["u"], noise["fine"], want_ind=True)
     report["fine_ind_in_kernel_cdf"] = float((ind2 == ind_ref).float().mean())
     assert report["fine_ind_in_kernel_cdf"] > 0.997
+    # the in-kernel cdf in the association order of ATen's CUDA sum / cumsum (scripts/cdf_probe.py): every index and
+    # depth bit-identical to CUDA-eager, for both coarse sample counts of the BASELINE configs
+    for Kc_ in (64, 128):
+        w_ = w_ref if Kc_ == 64 else (torch.rand(R, Kc_, device=dev, generator=g) ** 4 * 0.2).contiguous()
+        u_ = torch.rand(R, 96, device=dev, generator=g)
+        j_ = torch.rand(R, 96, device=dev, generator=g)
+        ind_e, z_e = O.sample_fine_from_cdf(rays, O.fine_cdf(w_), Kc_, u_, j_)
+        z_k, ind_k = ops.sample_fine(rays, w_, Kc_, u_, j_, want_ind=True, cuda_eager=True)
+        assert torch.equal(ind_k, ind_e) and same_bits(z_k, z_e), Kc_
+    report["fine_in_kernel_cdf_cuda_eager_mode"] = 1.0
     # sort (neural_rendering.py:463)
     z_all = torch.cat([z, zf_ref], -1)
     report["sort"] = bits_equal_frac(ops.sort_rows(z_all.clone()), torch.sort(z_all, dim=-1)[0])
