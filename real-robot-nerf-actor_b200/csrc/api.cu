@@ -85,7 +85,7 @@ extern "C" int nrf_timing_end(double* ms, int64_t* launches) {
   return NRF_OK;
 }
 
-extern "C" const char* nrf_version(void) { return "nrf_b200 0.1 (sm_100a; tcgen05/TMEM/TMA)"; }
+extern "C" const char* nrf_version(void) { return "nrf_b200 0.2 (sm_100a; tcgen05/TMEM/TMA)"; }
 extern "C" const char* nrf_last_error(void) { return g_err; }
 
 extern "C" int nrf_gemm(const NrfGemm* g, int precision, void* stream) {
