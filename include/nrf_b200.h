@@ -137,6 +137,20 @@ int nrf_encode_points_touch(const float* rays, const float* z, int R, int K, int
                             void* out, int ld_out, int out_bf16, float* points_out, uint8_t* touch_flags,
                             void* stream);
 
+/* ---- re-layout of the touched voxels only -----------------------------------------------------------------------
+ * The gather reads the in-grid trilinear corners of its samples and nothing else.  When a step's rays cross a small part
+ * of the volume (2048 rays of one 200^3 scene: 1.5 % of the voxels) the dense nrf_volume_to_channels_last pass is almost
+ * all wasted traffic.  nrf_mark_voxels sets flags[scene * V + voxel] = 2 for every in-grid corner of the samples (R, K)
+ * whose flag is still 0; nrf_volume_to_channels_last_marked moves every 32-voxel tile that holds a 2 and sets the
+ * tile's flags to 1 (per_voxel == 0).  flags: SB * V bytes, zeroed by the caller once per volume; call the pair once per render pass.
+ * Tiles never flagged stay unwritten in vol_cl. */
+int nrf_mark_voxels(const float* rays, const float* z, int R, int K, int rays_per_scene, int SB, int S0, int S1,
+                    int S2, const float* bounds_host, uint8_t* flags, void* stream);
+int nrf_volume_to_channels_last_marked(const float* src, float* dst, int SB, int C, int64_t V, uint8_t* flags,
+                                       int per_voxel, void* stream);
+/* per_voxel != 0: only the flagged voxels themselves are moved (C strided 4 B reads each) and marked done; the rest of
+ * their tiles stays unwritten.  The sparser choice: a ray crosses a 32-voxel run in one or two voxels. */
+
 /* ---- volume gradient: transpose of the trilinear gather (autograd of models_embed.py:275) ----
  * dlatent (N, ld) fp32; grad_cl channels-last (SB,S0,S1,S2,C), accumulated into (caller zeroes). */
 int nrf_scatter_volume_grad(const float* rays, const float* z, int R, int K, int rays_per_scene,

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "nrf_sample_fine": [_p, _p, _p, _i, _i, _p, _p, _i, _i, _p, _i, _p, _p],
     "nrf_sort_rows": [_p, _i, _i, _p, _p],
     "nrf_volume_to_channels_last": [_p, _p, _i, _i, _i64, _p],
+    "nrf_mark_voxels": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "nrf_volume_to_channels_last_marked": [_p, _p, _i, _i, _i64, _p, _i, _p],
     "nrf_volume_to_channels_first": [_p, _p, _i, _i, _i64, _p],
     "nrf_encode_points": [_p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _f, _p, _i, _i, _p, _p],
     "nrf_scatter_volume_grad": [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p],

@@ -80,6 +80,69 @@ __global__ void __launch_bounds__(256) volume_to_last_c128_kernel(const float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Re-layout of the voxels the rays actually touch.  A training step of 2 x 2048 rays reads a few per cent of a 100^3
+// volume (one scene's 2048 rays of 16 384 on a 200^3 grid: 1.5 %), yet the dense (C, V) -> (V, C) pass moves all of it
+// - 8.2 GB for the 200^3 volume, every step, on every rank.  mark_voxels_kernel flags the in-grid trilinear corners of
+// a pass's samples (the same geometry code as the gather); volume_to_last_marked_kernel then moves only the 32-voxel
+// tiles that hold a newly flagged voxel and marks the whole tile as done, so that the second pass of a step adds what
+// it touches beyond the first.  Tiles without a flag stay unwritten in the channels-last buffer: the gather never
+// reads them (it reads in-grid corners of its samples only - exactly the flagged voxels).
+constexpr uint8_t kVoxWanted = 2, kVoxDone = 1;
+
+__global__ void __launch_bounds__(256) mark_voxels_kernel(const float* __restrict__ rays, const float* __restrict__ z,
+                                                          int R, int K, int rays_per_scene, int S0, int S1, int S2,
+                                                          float b0, float b1, float b2, float e0, float e1, float e2,
+                                                          uint8_t* __restrict__ flags) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (int64_t)R * K) return;
+  const int r = (int)(n / K);
+  const float bmin[3] = {b0, b1, b2}, bext[3] = {e0, e1, e2};
+  const SampleGeom g = sample_geometry(rays + (int64_t)r * 8, z[n], bmin, bext);
+  Corner8 c8;
+  trilinear_corners(g.cx, g.cy, g.cz, S0, S1, S2, 1, c8);               // C = 1: off = voxel index
+  uint8_t* f = flags + (int64_t)(r / rays_per_scene) * S0 * S1 * S2;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (c8.off[k] >= 0 && f[c8.off[k]] == 0) f[c8.off[k]] = kVoxWanted;  // (racing writers all store the same value)
+}
+
+// grid (tiles of 32 voxels, 1, SB), 256 threads; 64 channels x 32 voxels per round through shared memory
+__global__ void __launch_bounds__(256) volume_to_last_marked_kernel(const float* __restrict__ src,
+                                                                    float* __restrict__ dst, int C, int64_t V,
+                                                                    uint8_t* __restrict__ flags) {
+  __shared__ float tile[32][65];
+  const int lane = threadIdx.x % kWarp, wid = threadIdx.x / kWarp;
+  const int b = blockIdx.z;
+  const int64_t v0 = (int64_t)blockIdx.x * 32;
+  const bool vok = v0 + lane < V;
+  uint8_t* fl = flags + (int64_t)b * V + v0;
+  const uint8_t mine = vok ? fl[lane] : (uint8_t)0;
+  if (__ballot_sync(0xffffffffu, mine == kVoxWanted) == 0u) return;      // same flags in every warp: uniform exit
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const float* s = src + ((int64_t)b * C + c0) * V + v0;
+    float* d = dst + ((int64_t)b * V + v0) * C + c0;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = (vok && c0 + wid + 8 * i < C) ? __ldg(s + (int64_t)(wid + 8 * i) * V + lane) : 0.f;
+    __syncthreads();                                                     // the previous round's reads of the tile
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[lane][wid + 8 * i] = x[i];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = wid * 4 + q;
+      if (v0 + v < V) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (c0 + lane + 32 * i < C) d[(int64_t)v * C + lane + 32 * i] = tile[v][lane + 32 * i];
+      }
+    }
+  }
+  __syncthreads();                                                       // every warp has read the flags
+  if (wid == 0 && vok) fl[lane] = kVoxDone;
+}
+
 struct EncodeArgs {
   const float* rays;
   const float* z;
@@ -554,6 +617,71 @@ extern "C" int nrf_volume_to_channels_last(const float* src, float* dst, int SB,
 extern "C" int nrf_volume_to_channels_first(const float* src, float* dst, int SB, int C, int64_t V,
                                             void* stream) {
   return volume_transpose(src, dst, SB, C, V, false, stream);
+}
+
+namespace nrf {
+// The same at voxel granularity: a warp scans 32 flags and moves only the flagged voxels - C strided 4 B reads (a 32 B
+// sector each) and one coalesced row per voxel.  8 x the bytes of the tile kernel per voxel moved, so it pays when the
+// touched voxels are sparse WITHIN the tiles too: a ray crosses a 32-voxel run along x in one or two voxels, so 2048
+// rays on a 200^3 grid touch 1.5 % of the voxels but half of the tiles.
+__global__ void __launch_bounds__(256) volume_to_last_marked_voxels_kernel(const float* __restrict__ src,
+                                                                           float* __restrict__ dst, int C, int64_t V,
+                                                                           uint8_t* __restrict__ flags) {
+  const int lane = threadIdx.x % kWarp, wid = threadIdx.x / kWarp;
+  const int b = blockIdx.z;
+  const int64_t v0 = ((int64_t)blockIdx.x * 8 + wid) * 32;
+  if (v0 >= V) return;
+  const bool vok = v0 + lane < V;
+  uint8_t* fl = flags + (int64_t)b * V + v0;
+  const uint8_t mine = vok ? fl[lane] : (uint8_t)0;
+  unsigned m = __ballot_sync(0xffffffffu, mine == kVoxWanted);
+  const float* s = src + (int64_t)b * C * V + v0;
+  float* d = dst + ((int64_t)b * V + v0) * C;
+  while (m) {
+    const int vi = __ffs(m) - 1;
+    m &= m - 1;
+    for (int c = lane; c < C; c += 128) {
+      float x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = c + 32 * i < C ? __ldg(s + (int64_t)(c + 32 * i) * V + vi) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c + 32 * i < C) d[(int64_t)vi * C + c + 32 * i] = x[i];
+    }
+  }
+  if (mine == kVoxWanted) fl[lane] = kVoxDone;
+}
+}  // namespace nrf
+
+extern "C" int nrf_mark_voxels(const float* rays, const float* z, int R, int K, int rays_per_scene, int SB, int S0,
+                               int S1, int S2, const float* bounds_host, uint8_t* flags, void* stream) {
+  NRF_REQUIRE(rays && z && bounds_host && flags && R > 0 && K > 0 && rays_per_scene > 0 && R == SB * rays_per_scene,
+              NRF_EINVAL, "nrf_mark_voxels: bad arguments");
+  float bmin[3], bext[3];
+  fill_bounds(bounds_host, bmin, bext);
+  const int64_t N = (int64_t)R * K;
+  { LaunchScope ls_(NRF_CAT_TRANSPOSE, as_stream(stream));
+    mark_voxels_kernel<<<(unsigned)((N + 255) / 256), 256, 0, as_stream(stream)>>>(
+        rays, z, R, K, rays_per_scene, S0, S1, S2, bmin[0], bmin[1], bmin[2], bext[0], bext[1], bext[2], flags); }
+  NRF_LAUNCH_OK();
+  return NRF_OK;
+}
+
+extern "C" int nrf_volume_to_channels_last_marked(const float* src, float* dst, int SB, int C, int64_t V,
+                                                  uint8_t* flags, int per_voxel, void* stream) {
+  NRF_REQUIRE(src && dst && flags && SB > 0 && C > 0 && V > 0, NRF_EINVAL, "nrf_volume_to_channels_last_marked: bad args");
+  NRF_REQUIRE(SB <= 65535 && (V + 31) / 32 < ((int64_t)1 << 31), NRF_ENOSUP,
+              "nrf_volume_to_channels_last_marked: grid too large");
+  { LaunchScope ls_(NRF_CAT_TRANSPOSE, as_stream(stream));
+    if (per_voxel) {
+      dim3 grid((unsigned)((V + 255) / 256), 1, (unsigned)SB);
+      volume_to_last_marked_voxels_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, C, V, flags);
+    } else {
+      dim3 grid((unsigned)((V + 31) / 32), 1, (unsigned)SB);
+      volume_to_last_marked_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, C, V, flags);
+    } }
+  NRF_LAUNCH_OK();
+  return NRF_OK;
 }
 
 static int encode_points_impl(const float* rays, const float* z, int R, int K, int rays_per_scene,

@@ -697,15 +697,26 @@ class _ForwardNerfFn(torch.autograd.Function):
             mlp_f.pack(force=keep)
         held = getattr(ren, "_vol_cl_held", None)          # rendering(): one re-layout for all ray chunks
         cl3d = _is_channels_last_3d(voxel_feat)
+        Kc, Kf, Kfd = ren.n_coarse, ren.n_fine, ren.n_fine_depth
+        touched = None                                     # re-layout of the voxels the rays touch, pass by pass
         if cl3d:                                           # producer ran in torch.channels_last_3d: zero-copy view
             vol_cl = voxel_feat.permute(0, 2, 3, 4, 1)
         elif held is not None and held[0] is voxel_feat:
             vol_cl = held[1]
+        elif ren.sparse_relayout and voxel_feat.shape[1] in (64, 128) and \
+                R * (Kc + (Kc + Kf if ren.using_fine else 0)) < ren.sparse_relayout_ratio * voxel_feat.shape[0] * voxel_feat[0, 0].numel():
+            # far fewer samples than voxels (2048 rays of one scene on a 200^3 grid, BASELINE config 5 split over 8 GPUs:
+            # 0.1 samples per voxel, 1.5 % of the voxels touched): a dense (C, V) -> (V, C) pass would move 8.2 GB of which
+            # the gather reads 60 MB.  (At config 2, 0.4 samples per voxel, the rays already touch most 32-voxel tiles and
+            # the dense pass is the faster one: measured, profiles/r02c_summary.md.)
+            touched = ops.TouchedRelayout(voxel_feat, ren._bounds)
+            vol_cl = touched.vol_cl
         else:
             vol_cl = ops.volume_to_channels_last(voxel_feat)
         ctx.cl3d = cl3d
-        Kc, Kf, Kfd = ren.n_coarse, ren.n_fine, ren.n_fine_depth
         z_c = ops.sample_coarse(rays, Kc, noise.get("coarse"), ren.lindisp)
+        if touched is not None:
+            touched.add(rays, z_c, rps)
         st_c, (cw, crgb, cemb, cdep) = _pass_forward(ren, mlp_c, vol_cl, rays, z_c, rps, keep,
                                                      _sigma_noise(ren, noise, "sigma_c", R, Kc, rays.device),
                                                      repack=False)
@@ -731,6 +742,8 @@ class _ForwardNerfFn(torch.autograd.Function):
                 z_all[:, Kc + kf:] = torch.max(torch.min(z0, far), near)
             reuse = ren.reuse_coarse_evals and mlp_f is mlp_c and not ren.regress_coord
             z_new = z_all[:, Kc:].contiguous() if reuse else None
+            if touched is not None:                        # what the fine samples touch beyond the coarse ones
+                touched.add(rays, z_all[:, Kc:].contiguous(), rps)
             z_all, perm = ops.sort_rows(z_all, want_perm=True)
             sn_f = _sigma_noise(ren, noise, "sigma_f", R, K, rays.device)
             if reuse:
@@ -897,6 +910,10 @@ class NeuralRenderer(nn.Module):
         # sample tiles without a sample inside the grid have an all-zero latent: the forward skips their latent k-panels,
         # the backward their dL/dlatent and lin_z weight-gradient blocks (NRF_SKIP_EMPTY_TILES=0: every tile in full)
         self.skip_empty_latent_tiles = os.environ.get("NRF_SKIP_EMPTY_TILES", "1") != "0"
+        # a training step with fewer samples than voxels re-lays out only the 32-voxel tiles its rays touch
+        # (ops.TouchedRelayout; NRF_SPARSE_RELAYOUT=0: always the dense pass)
+        self.sparse_relayout = os.environ.get("NRF_SPARSE_RELAYOUT", "1") != "0"
+        self.sparse_relayout_ratio = float(os.environ.get("NRF_SPARSE_RELAYOUT_RATIO", "0.25"))   # samples per voxel below which it pays
         self.keep_voxel_counts = False         # True: the backward leaves the per-voxel entry counts of its scatter in
         self.last_voxel_counts = None          # `last_voxel_counts` (what the sparse volume-gradient exchange sends)
         self._num_freqs = self.nerf_model.code.num_freqs

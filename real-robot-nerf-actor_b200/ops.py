@@ -188,6 +188,35 @@ def volume_to_channels_last(vol):
     return out
 
 
+class TouchedRelayout:
+    """The channels-last copy of a volume, filled in only where the rays go (nrf_mark_voxels +
+    nrf_volume_to_channels_last_marked): `add(rays, z, rays_per_scene)` before a pass's gather moves the 32-voxel tiles
+    that pass touches and no earlier pass has moved.  `vol_cl` elsewhere is unwritten memory - which the gather never
+    reads (it reads the in-grid corners of its own samples only)."""
+
+    def __init__(self, vol, bounds, per_voxel=True):
+        self.per_voxel = per_voxel          # move the flagged voxels themselves (default) or their whole 32-voxel tiles
+        self.vol = _f32(vol, "voxel_feat")
+        SB, Cc, S0, S1, S2 = self.vol.shape
+        self.shape = (SB, S0, S1, S2, Cc)
+        self.vol_cl = torch.empty(self.shape, device=vol.device, dtype=torch.float32)
+        self.flags = torch.zeros(SB * S0 * S1 * S2, device=vol.device, dtype=torch.uint8)
+        self.bh = _bounds_host(bounds)
+
+    def add(self, rays, z, rays_per_scene):
+        SB, S0, S1, S2, Cc = self.shape
+        rays, z = _f32(rays, "rays"), _f32(z, "z")
+        R, K = z.shape
+        with torch.cuda.device(self.vol.device):
+            lib = _lib.load()
+            check(lib.nrf_mark_voxels(ptr(rays), ptr(z), R, K, rays_per_scene, SB, S0, S1, S2,
+                                      C.cast(self.bh, C.c_void_p), ptr(self.flags), stream_ptr()), "nrf_mark_voxels")
+            check(lib.nrf_volume_to_channels_last_marked(ptr(self.vol), ptr(self.vol_cl), SB, Cc, S0 * S1 * S2,
+                                                         ptr(self.flags), int(self.per_voxel), stream_ptr()),
+                  "nrf_volume_to_channels_last_marked")
+        return self.vol_cl
+
+
 @_on_tensor_device
 def volume_to_channels_first(vol_cl):
     """(SB,S0,S1,S2,C) -> (SB,C,S0,S1,S2)."""

@@ -1042,3 +1042,67 @@ def test_dlatent_tile_skipping_changes_no_gradient(NR):
     ref = torch.cat([lat, lat.new_zeros(pad)]).reshape(-1, 32).gt(0).any(1)
     assert touch.numel() == ref.numel() and torch.equal(touch.bool(), ref)
     assert 0 < int(ref.sum()) < ref.numel()
+
+
+@pytest.mark.parametrize("C,S,n_rays,near_far,focal", [(128, 48, 40, (1.2, 4.0), 153.0), (64, 40, 64, (2.4, 3.2), 500.0),
+                                                       (128, 33, 30, (1.2, 4.0), 90.0)])
+def test_touched_voxel_relayout_changes_nothing(NR, C, S, n_rays, near_far, focal):
+    """A step with fewer samples than voxels re-lays out only the 32-voxel tiles its rays touch (nrf_mark_voxels +
+    nrf_volume_to_channels_last_marked, once per pass; the rest of the channels-last buffer stays unwritten).  The
+    gather reads in-grid corners of its samples only, so every output and gradient is bit-identical to the dense
+    re-layout - rays that miss the box, rays inside it, a volume whose size is not a multiple of the 32-voxel tile,
+    both latent widths; and the kernels themselves: flagged tiles equal the dense transpose, the others are untouched."""
+    ops, U = load_pkg("ops"), load_pkg("utils")
+    res = {}
+    for sparse in (True, False):
+        cfg = U.default_config(voxel_shape=S, d_latent=C, n_coarse=64, n_fine=64, ray_chunk_size=n_rays,
+                               z_near=near_far[0], z_far=near_far[1])
+        ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS), precision="bf16")
+        syn.init_mlp_(ren.nerf_model.mlp_coarse, seed=0)
+        ren = ren.cuda().train()
+        ren.sparse_relayout = sparse
+        ren.sparse_relayout_ratio = 1.0
+        ren.deterministic = True
+        vol = syn.make_volume(2, C, S, seed=1).cuda().requires_grad_(True)
+        poses = syn.arc_poses(2).cuda()
+        rays = U.gen_rays(poses, 128, 128, torch.tensor(focal).cuda(), *near_far).reshape(2, -1, 8)
+        rays = rays[:, syn.pick_ray_indices(128 * 128, n_rays, seed=4).cuda()].contiguous()
+        noise = {k: v.cuda() for k, v in syn.make_noise(2 * n_rays, 64, 64, seed=5).items()}
+        n0 = load_pkg("_lib").launch_count()
+        ren.encode(None, None, None, vol, None, None, None)
+        out = ren.forward_nerf(rays, noise=noise)
+        loss = sum((out[l]["rgb"] ** 2).mean() + 0.01 * (out[l]["embed"] ** 2).mean() + 0.1 * out[l]["depth"].mean()
+                   for l in ("coarse", "fine"))
+        loss.backward()
+        res[sparse] = ({(l, k): out[l][k].detach().clone() for l in ("coarse", "fine") for k in ("rgb", "embed", "depth")},
+                       vol.grad.clone(), {k: p.grad.clone() for k, p in ren.named_parameters() if p.grad is not None})
+    assert 2 * n_rays * 192 < 2 * S ** 3, "the case must take the sparse path"
+    for key in res[True][0]:
+        assert torch.equal(res[True][0][key], res[False][0][key]), key
+    assert torch.equal(res[True][1], res[False][1])
+    for k in res[True][2]:
+        assert torch.equal(res[True][2][k], res[False][2][k]), k
+    # the two kernels against the dense transpose
+    vol = syn.make_volume(2, C, S, seed=2).cuda()
+    rays_f = rays.reshape(-1, 8).contiguous()
+    z = ops.sample_coarse(rays_f, 64, None)
+    dense = ops.volume_to_channels_last(vol)
+    V = S ** 3
+    for per_voxel in (True, False):
+        t = ops.TouchedRelayout(vol, torch.tensor(syn.BOUNDS), per_voxel=per_voxel)
+        t.vol_cl.fill_(-7.0)
+        t.add(rays_f, z, n_rays)
+        fl = t.flags.view(2, -1)
+        assert int((t.flags == 2).sum()) == 0 and 0 < int((t.flags == 1).sum()) < t.flags.numel()
+        if not per_voxel:                        # whole 32-voxel tiles (per scene; the last one may be ragged)
+            pad = (-V) % 32
+            tiles = torch.cat([fl, fl.new_zeros(2, pad)], 1).view(2, -1, 32)
+            whole = (tiles == 1).all(-1) | (tiles == 0).all(-1)
+            whole[:, -1] |= (tiles[:, -1, :32 - pad] == 1).all(-1)
+            assert bool(whole.all())
+        done = (fl == 1).view(2, S, S, S)
+        assert torch.equal(t.vol_cl[done], dense[done]) and bool((t.vol_cl[~done] == -7.0).all())
+    # every in-grid corner of every sample lies in a moved tile: gathers from the sparse and the dense copy agree
+    a = ops.encode_points(rays_f, z, n_rays, t.vol_cl, torch.tensor(syn.BOUNDS), precision=ops.NRF_PREC_FP32)
+    b = ops.encode_points(rays_f, z, n_rays, dense, torch.tensor(syn.BOUNDS), precision=ops.NRF_PREC_FP32)
+    assert torch.equal(a, b)
