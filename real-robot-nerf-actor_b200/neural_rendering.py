@@ -325,7 +325,8 @@ class PixelNeRFEmbedNet(nn.Module):
                                                                                       # (models_embed.py:151-154 never
                                                                                       # stores voxel_density, :289 samples None)
                            use_code_viewdirs=g("use_code_viewdirs", False),
-                           use_freenerf=g("use_freenerf", False), normalize_z=g("normalize_z", False))
+                           use_freenerf=g("use_freenerf", False))    # models_embed.py:350-352 is a debugger breakpoint
+                                                                     # and an invalid statement: it cannot run there either
         for k, v in unsupported.items():
             if v:
                 raise NotImplementedError(f"config option {k}=True is off in nerfact.conf and not built "
@@ -336,7 +337,9 @@ class PixelNeRFEmbedNet(nn.Module):
             raise NotImplementedError("use_xyz / use_code must be True (nerfact.conf:69-71)")
         self._voxel_shape = g("voxel_shape")
         self.image_shape = (g("image_height"), g("image_width"))
-        self.normalize_z = False
+        # models_embed.py:42 hard-codes canon_xyz = True, so xyz_rot IS xyz (:325-326) and normalize_z only picks
+        # between two names of the same tensor (:337-340): the flag is accepted and changes nothing, as in the reference
+        self.normalize_z = bool(g("normalize_z", False))
         self.canon_xyz = True
         self.stop_encoder_grad = stop_encoder_grad
         self.use_code, self.use_code_viewdirs, self.use_viewdirs, self.use_xyz = True, False, True, True

@@ -679,6 +679,7 @@ class FieldMLP:
         off = (2 * nb + 1) * N * H * es
         return acts[off:off + N * H * es].view(dt).view(N, H)
 
+    @_on_tensor_device
     def backward(self, field_in, acts, d_field, grads: dict, scratch=None, deterministic=False, layered=False,
                  d_last=None, touch=None):
         """Accumulates parameter grads into `grads` (same keys as params); returns dlatent (N,C).
