@@ -68,6 +68,141 @@ def default_config(**over) -> ConfigDict:
     return ConfigDict(d)
 
 
+def _conf_tokens(text):
+    """Tokens of the HOCON subset nerfact.conf uses: { } [ ] = : , newline, quoted / unquoted scalars; # and // comments."""
+    i, n = 0, len(text)
+    while i < n:
+        ch = text[i]
+        if ch == "#" or text.startswith("//", i):
+            while i < n and text[i] != "\n":
+                i += 1
+        elif ch == "\n":
+            yield ("nl", ch)
+            i += 1
+        elif ch.isspace():
+            i += 1
+        elif ch in "{}[]=:,":
+            yield (ch, ch)
+            i += 1
+        elif ch in "\"'":
+            j = text.find(ch, i + 1)
+            if j < 0:
+                raise ValueError("unterminated string in config")
+            yield ("str", text[i + 1:j])
+            i = j + 1
+        else:
+            j = i
+            while j < n and text[j] not in "{}[]=:,\n#" and not text.startswith("//", j):
+                j += 1
+            yield ("raw", text[i:j].strip())
+            i = j
+
+
+def _conf_scalar(raw):
+    """An unquoted value the way pyhocon reads it: int, float, true / false in any case, null; anything else - `None`
+    and `average` included (nerfact.conf:43-44,:95) - stays a string."""
+    low = raw.lower()
+    if low in ("true", "false"):
+        return low == "true"
+    if low == "null":
+        return None
+    for cast in (int, float):
+        try:
+            return cast(raw)
+        except ValueError:
+            pass
+    return raw
+
+
+def parse_conf(text: str) -> ConfigDict:
+    """Parses the HOCON subset of the reference's nerfact.conf (key = value / key : value / key { ... } blocks, dotted
+    keys, [lists], quoted and bare scalars, # and // comments) into a ConfigDict, so that the config loads without
+    pyhocon (`ConfigFactory.parse_file`, train_nerfact_multi_kitchen.py:1244-1245): the result answers both
+    `conf['neural_renderer'].image_width = W` and `conf.mlp.d_hidden` like pyhocon's ConfigTree.  Substitutions
+    (${...}), includes and multi-line strings are not part of the subset and raise."""
+    toks = list(_conf_tokens(text))
+    pos = 0
+
+    def peek():
+        return toks[pos] if pos < len(toks) else ("eof", "")
+
+    def skip_seps():
+        nonlocal pos
+        while peek()[0] in ("nl", ","):
+            pos += 1
+
+    def value():
+        nonlocal pos
+        kind, tok = peek()
+        if kind == "{":
+            pos += 1
+            return obj("}")
+        if kind == "[":
+            pos += 1
+            out = []
+            skip_seps()
+            while peek()[0] != "]":
+                if peek()[0] == "eof":
+                    raise ValueError("unterminated list in config")
+                out.append(value())
+                skip_seps()
+            pos += 1
+            return out
+        if kind == "str":
+            pos += 1
+            return tok
+        if kind == "raw":
+            if "${" in tok:
+                raise ValueError("config substitutions are not supported")
+            pos += 1
+            return _conf_scalar(tok)
+        raise ValueError(f"unexpected {tok!r} in config")
+
+    def put(d, dotted, v):
+        parts = dotted.split(".")
+        for k in parts[:-1]:
+            d = d.setdefault(k, {})
+        if isinstance(v, dict) and isinstance(d.get(parts[-1]), dict):
+            d[parts[-1]].update(v)            # HOCON merges repeated objects
+        else:
+            d[parts[-1]] = v
+
+    def obj(end):
+        nonlocal pos
+        d = {}
+        skip_seps()
+        while peek()[0] != end:
+            kind, key = peek()
+            if kind not in ("raw", "str"):
+                raise ValueError(f"expected a key, got {key!r}")
+            if key == "include":
+                raise ValueError("config includes are not supported")
+            pos += 1
+            if peek()[0] in ("=", ":"):
+                pos += 1
+            elif peek()[0] != "{":
+                raise ValueError(f"expected '=', ':' or '{{' after key {key!r}")
+            put(d, key, value())
+            skip_seps()
+        pos += 1
+        return d
+
+    toks.append(("eof", ""))
+    skip_seps()
+    if peek()[0] == "{":
+        pos += 1
+        d = obj("}")
+    else:
+        d = obj("eof")
+    return ConfigDict(d)
+
+
+def load_conf(path) -> ConfigDict:
+    """`ConfigFactory.parse_file(path)` for nerfact.conf without pyhocon (see parse_conf)."""
+    with open(path) as f:
+        return parse_conf(f.read())
+
+
 def repeat_interleave(input, repeats, dim=0):
     """utils.py:434-441."""
     output = input.unsqueeze(1).expand(-1, repeats, *input.shape[1:])
