@@ -370,7 +370,12 @@ class PixelNeRFEmbedNet(nn.Module):
         self.voxel_feat = None
 
     def encode(self, voxel_feat, lang, multi_scale_voxel_list, voxel_density, poses, focal, c=None):
-        """models_embed.py:136-183: stores a reference to the volume; focal / c bookkeeping only."""
+        """models_embed.py:136-183: stores a reference to the volume; focal / c bookkeeping only.
+        A bf16 / fp16 volume (a voxel encoder run under torch.autocast) is widened to fp32 here: what autocast itself
+        does to the reference's F.grid_sample (models_embed.py:275; grid_sampler is on autocast's fp32 list) - the
+        gather then interpolates in fp32 and autograd returns the volume gradient in the producer's dtype."""
+        if torch.is_tensor(voxel_feat) and voxel_feat.dtype in (torch.bfloat16, torch.float16):
+            voxel_feat = voxel_feat.float()       # keeps the memory format (channels_last_3d stays zero-copy below)
         self.voxel_feat = voxel_feat
         self.multi_scale_voxel_list = multi_scale_voxel_list if self.use_multi_scale_voxel else None   # :147-149
         self.voxel_density = None
@@ -1121,6 +1126,7 @@ class NeuralRenderer(nn.Module):
         rays = rays.reshape(B * H * W, 8)
         rgbs, embeds, depths = [], [], []
         # the volume is re-laid out channels-last once for all ray chunks (the tensor is held, so identity is safe)
+        voxel_feat = self.nerf_model.voxel_feat            # as encode() keeps it (fp32 also for a bf16 / fp16 hand-over)
         self._vol_cl_held = None if _is_channels_last_3d(voxel_feat) else \
             (voxel_feat, ops.volume_to_channels_last(voxel_feat))
         try:

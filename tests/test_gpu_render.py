@@ -695,6 +695,48 @@ def test_channels_last_3d_volume_is_taken_without_relayout(ops, NR):
             assert torch.equal(res[0][0][l][k], res[1][0][l][k])
 
 
+def test_reduced_precision_volume_is_widened_like_autocast(ops, NR):
+    """A bf16 / fp16 voxel volume (an encoder run under torch.autocast; SURVEY 8f rank 1's hand-off): autocast runs the
+    reference's F.grid_sample in fp32 on the widened volume (models_embed.py:275), so the result must equal the fp32
+    render of `vol.float()` bit for bit, and the gradient comes back in the producer's dtype (and memory format)."""
+    fx = golden("small_kfd0")
+    ci = _case_inputs(fx)
+    ren = make_renderer(NR, [int(v) for v in fx["meta"]], ci["params"], "fp32")
+    rays, idx = T(fx["rays"]), T(fx["idx"])
+    gt_rgb = T(fx["gt_rgb_img"]).reshape(ci["SB"], -1, 3)[:, idx]
+    gt_emb = T(fx["gt_embed_img"]).reshape(ci["SB"], -1, ci["D"])[:, idx]
+    noise = {k: v.cuda() for k, v in ci["noise"].items()}
+
+    def run(vol):
+        for p in ren.parameters():
+            p.grad = None
+        vol = vol.requires_grad_(True)
+        ren.encode(None, None, None, vol, None, None, None)
+        out = ren.forward_nerf(rays.cuda(), noise=noise)
+        loss = O.rendering_loss({l: {k: out[l][k] for k in ("rgb", "embed", "depth")} for l in ("coarse", "fine")},
+                                gt_rgb.cuda(), gt_emb.cuda())["loss"]
+        loss.backward()
+        return out, vol.grad
+
+    for dt in (torch.bfloat16, torch.float16):
+        for fmt in (torch.contiguous_format, torch.channels_last_3d):
+            low = T(fx["vol"]).cuda().to(dt).contiguous(memory_format=fmt)
+            out_l, g_l = run(low.clone())
+            out_w, g_w = run(low.float())
+            assert g_l.dtype == dt and g_l.shape == low.shape
+            assert torch.equal(g_l, g_w.to(dt)) and float(g_w.abs().max()) > 0
+            for l in ("coarse", "fine"):
+                for k in ("rgb", "embed", "depth"):
+                    assert torch.equal(out_l[l][k], out_w[l][k]), (dt, l, k)
+    # full-image inference takes the same hand-off
+    ren.perturb = False
+    focal, poses = T(fx["focal"]).cuda(), T(fx["poses"]).cuda()
+    low = T(fx["vol"]).cuda().to(torch.bfloat16)[:1]
+    a = ren.rendering(low, None, None, None, None, focal, poses)
+    b = ren.rendering(low.float(), None, None, None, None, focal, poses)
+    assert all(torch.equal(x, y) for x, y in zip(a, b)) and float(a[1].abs().max()) > 0
+
+
 def test_depth_loss_branch_matches_the_oracle(ops, NR):
     """gt_depth given (neural_rendering.py:684-692): masked depth MSE of both passes, lambda_depth > 0, through forward()
     with the ray subsample mocked to the fixture's indices; loss terms and gradients against the oracle."""
