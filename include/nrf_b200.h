@@ -122,6 +122,9 @@ int nrf_volume_to_channels_first(const float* src, float* dst, int SB, int C, in
  * out_bf16 | 0x100: the eight corners are accumulated with FMAs, which is what ATen's CUDA grid_sampler_3d compiles to
  * (bit-identical to the reference run on a GPU); default: separately rounded multiply and add, ATen's CPU kernel
  * (bit-identical to the reference run on the CPU, which is what the golden fixtures were produced by).
+ * out_bf16 | 0x200 (use_code_viewdirs, models_embed.py:370-372): the positional encoding runs over the six inputs
+ * [canonical xyz | view direction] together, tail [in(6) | per frequency sin(in), cos(in)] = 6 + 12 num_freqs columns
+ * (78), instead of [PE(xyz) (3 + 6 num_freqs) | view direction (3)] (:347-366, 42 columns).
  * rays_per_scene = R / SB. points_out (N,3) fp32 optional (debug / parity), may be NULL. */
 int nrf_encode_points(const float* rays, const float* z, int R, int K, int rays_per_scene,
                       const float* vol_cl, int SB, int C, int S0, int S1, int S2,

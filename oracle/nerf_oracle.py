@@ -211,7 +211,7 @@ def resnetfc(p: Params, zx, d_latent, n_blocks=5, combine_layer=3, operand_dtype
 
 def field(p: Params, voxel_feat, xyz, viewdirs, bounds, code=(6, 1.5, True),
           n_blocks=5, combine_layer=3, operand_dtype=None, return_mlp_input=False, regress_coord=False,
-          regress_attention=False, multi_scale_voxel_list=None, ret_last_feat=False):
+          regress_attention=False, multi_scale_voxel_list=None, ret_last_feat=False, code_viewdirs=False):
     """models_embed.py:295-471 default branch. xyz, viewdirs (SB,n,3) -> (SB,n,4+D).
 
     mlp_input = [latent(C) | PE(xyz)(39) | viewdir(3)] (:366,:405); heads sigmoid(rgb),
@@ -219,8 +219,11 @@ def field(p: Params, voxel_feat, xyz, viewdirs, bounds, code=(6, 1.5, True),
     """
     SB, n, _ = xyz.shape
     canon = world_to_canonical(xyz, bounds)
-    zf = positional_encoding(canon.reshape(-1, 3), *code)
-    zf = torch.cat((zf, viewdirs.reshape(-1, 3)), dim=1)
+    if code_viewdirs:                                # models_embed.py:355-372: [xyz | viewdir] through the encoding together
+        zf = positional_encoding(torch.cat((canon.reshape(-1, 3), viewdirs.reshape(-1, 3)), dim=1), *code)
+    else:                                            # :347-366: PE(xyz), then the raw view direction
+        zf = positional_encoding(canon.reshape(-1, 3), *code)
+        zf = torch.cat((zf, viewdirs.reshape(-1, 3)), dim=1)
     latent = trilinear_gather(voxel_feat, canon)
     if multi_scale_voxel_list:                       # models_embed.py:279-286: [*multi-scale, main]
         latent = torch.cat([trilinear_gather(v, canon) for v in multi_scale_voxel_list] + [latent], dim=-1)

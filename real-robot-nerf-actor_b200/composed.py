@@ -4,9 +4,11 @@
     concatenation of trilinear gathers from several volumes of different resolution and channel count
     ([*multi_scale_voxel_list, voxel_feat]);
   * `ret_last_feat` (neural_rendering.py:285-293,332-334; resnetfc.py:192-195): the MLP's last residual stream x_nb
-    (d_hidden channels) is alpha-composited in place of the embedding head.
+    (d_hidden channels) is alpha-composited in place of the embedding head;
+  * `use_code_viewdirs` (models_embed.py:86-95,:355-372): the view direction goes through the positional encoding
+    together with the point (nrf_encode_points with out_bf16 | 0x200: tail of 78 columns, MLP d_in = 78).
 
-Both are off in nerfact.conf.  They run on the same kernels as the default path (nrf_encode_points per volume, the
+All are off in nerfact.conf.  They run on the same kernels as the default path (nrf_encode_points per volume, the
 field MLP, nrf_composite_*, nrf_scatter_volume_grad_sorted per volume), composed at the torch level as three autograd
 nodes per pass instead of one per forward_nerf - so the general shapes (266 latent channels, volumes of 10 channels,
 an extra 512-wide output) need no kernel of their own.  The MLP runs in the fp32 parity mode here (d_latent = 266 is
@@ -26,15 +28,16 @@ class GatherFn(torch.autograd.Function):
     atomics-free sorted scatter into that volume; no gradient reaches rays / z (world_to_canonical is @no_grad)."""
 
     @staticmethod
-    def forward(ctx, vol, rays, z, rps, bounds, num_freqs, freq_factor):
+    def forward(ctx, vol, rays, z, rps, bounds, num_freqs, freq_factor, code_viewdirs=False):
         SB, C = vol.shape[:2]
         Cp = (C + 3) // 4 * 4                      # the kernels move whole float4s: pad the channels with zeros
         v = vol.detach()
         if Cp != C:
             v = torch.cat([v, v.new_zeros(SB, Cp - C, *v.shape[2:])], 1)
         vol_cl = ops.volume_to_channels_last(v.contiguous())
-        tail = 6 + 6 * num_freqs
-        rows = ops.encode_points(rays, z, rps, vol_cl, bounds, num_freqs, freq_factor, precision=NRF_PREC_FP32)
+        tail = 6 + (12 if code_viewdirs else 6) * num_freqs
+        rows = ops.encode_points(rays, z, rps, vol_cl, bounds, num_freqs, freq_factor, precision=NRF_PREC_FP32,
+                                 code_viewdirs=code_viewdirs)
         ctx.save_for_backward(rays, z)
         ctx.meta = (rps, bounds, tuple(vol_cl.shape), C, Cp)
         out = torch.cat([rows[:, :C], rows[:, Cp:Cp + tail]], 1)
@@ -45,12 +48,12 @@ class GatherFn(torch.autograd.Function):
         rays, z = ctx.saved_tensors
         rps, bounds, shape_cl, C, Cp = ctx.meta
         if not ctx.needs_input_grad[0]:
-            return (None,) * 7
+            return (None,) * 8
         d_lat = d_rows.new_zeros(d_rows.shape[0], Cp)
         d_lat[:, :C] = d_rows[:, :C]
         g = torch.empty(shape_cl, device=d_rows.device, dtype=torch.float32)
         ops.scatter_volume_grad_sorted(rays, z, rps, d_lat, g, bounds)
-        return (ops.volume_to_channels_first(g)[:, :C], None, None, None, None, None, None)
+        return (ops.volume_to_channels_first(g)[:, :C], None, None, None, None, None, None, None)
 
 
 class MlpLastFn(torch.autograd.Function):
@@ -117,8 +120,9 @@ class CompositeFieldFn(torch.autograd.Function):
 def field_rows(ren, model, mlp, vols, rays, z, rps):
     """[*multi-scale latents | main latent | PE | viewdir] -> (raw MLP outputs (N, d_out), x_nb (N, d_hidden))."""
     nf, ff = model.code.num_freqs, float(model.code.freq_factor)
-    tail = 6 + 6 * nf
-    rows = [GatherFn.apply(v, rays, z, rps, ren._bounds, nf, ff) for v in vols]
+    cv = bool(getattr(model, "use_code_viewdirs", False))
+    tail = 6 + (12 if cv else 6) * nf
+    rows = [GatherFn.apply(v, rays, z, rps, ren._bounds, nf, ff, cv) for v in vols]
     zx = torch.cat([r[:, :r.shape[1] - tail] for r in rows] + [rows[-1][:, -tail:]], 1)
     if zx.shape[1] != model.d_latent + model.d_in:
         raise RuntimeError(f"multi-scale latent has {zx.shape[1] - model.d_in} channels, the model expects d_latent = "

@@ -158,6 +158,8 @@ struct EncodeArgs {
   uint8_t* touch;   // optional: one byte per group of 32 consecutive samples, 1 if any of them has a corner inside the grid
   int fma;          // corner accumulation out = fma(v, w, out) (ATen's CUDA grid_sampler_3d) instead of the separately
                     // rounded multiply and add of ATen's CPU kernel (the default)
+  int pe_dirs;      // use_code_viewdirs (models_embed.py:370-372): the positional encoding runs over [xyz | viewdir] (6
+                    // inputs, tail 6 + 12 F) instead of over xyz with the raw view direction behind it (tail 6 + 6 F)
 };
 
 // One trilinear corner: out += v * w in ATen's rounding.  The CPU kernel rounds the product and the sum separately;
@@ -212,7 +214,8 @@ __global__ void __launch_bounds__(256) encode_points_kernel(EncodeArgs a) {
   int64_t N = (int64_t)a.R * a.K;
   T* out = reinterpret_cast<T*>(a.out);
   const int C = a.C;
-  const int n_pe = 3 + 6 * a.num_freqs;
+  const int d_pe = a.pe_dirs ? 6 : 3;
+  const int n_pe = d_pe + 2 * d_pe * a.num_freqs;
   for (int64_t n = warp; n < N; n += nwarps) {
     int r = (int)(n / a.K);
     int scene = r / a.rays_per_scene;
@@ -238,19 +241,20 @@ __global__ void __launch_bounds__(256) encode_points_kernel(EncodeArgs a) {
       }
       store4<T>(row + c0, acc);
     }
-    // positional encoding [x y z | per frequency: sin(xyz), cos(xyz)] then the view direction
-    float cxyz[3] = {g.cx, g.cy, g.cz};
+    // positional encoding [x y z | per frequency: sin(xyz), cos(xyz)] then the view direction; with pe_dirs the six
+    // inputs [x y z dx dy dz] are encoded together: [in(6) | per frequency: sin(in), cos(in)] (utils.py:545-557)
+    const float cin[6] = {g.cx, g.cy, g.cz, ray[3], ray[4], ray[5]};
     for (int e = lane; e < a.ld_out - C; e += kWarp) {
       float val = 0.f;
-      if (e < 3) {
-        val = cxyz[e];
+      if (e < d_pe) {
+        val = cin[e];
       } else if (e < n_pe) {
-        int q = e - 3;
-        int f = q / 6, w = q % 6;
+        int q = e - d_pe;
+        int f = q / (2 * d_pe), w = q % (2 * d_pe);
         float freq = a.freq_factor * (float)(1 << f);
-        float phase = (w >= 3) ? 1.57079637050628662109375f : 0.0f;   // fp32(pi/2), utils.py:542
-        val = sinf(__fmaf_rn(cxyz[w % 3], freq, phase));   // addcmul contracts to an FMA in ATen
-      } else if (e < n_pe + 3) {
+        float phase = (w >= d_pe) ? 1.57079637050628662109375f : 0.0f;   // fp32(pi/2), utils.py:542
+        val = sinf(__fmaf_rn(cin[w % d_pe], freq, phase));   // addcmul contracts to an FMA in ATen
+      } else if (!a.pe_dirs && e < n_pe + 3) {
         val = ray[3 + (e - n_pe)];
       }
       row[C + e] = to_out<T>(val);
@@ -692,7 +696,9 @@ static int encode_points_impl(const float* rays, const float* z, int R, int K, i
   NRF_REQUIRE(R > 0 && K > 0 && rays_per_scene > 0 && R == SB * rays_per_scene, NRF_EINVAL,
               "nrf_encode_points: R=%d must equal SB*rays_per_scene=%d*%d", R, SB, rays_per_scene);
   NRF_REQUIRE(C % 4 == 0 && C > 0, NRF_ENOSUP, "nrf_encode_points: C=%d must be a multiple of 4", C);
-  NRF_REQUIRE(ld_out >= C + 6 + 6 * num_freqs && ld_out % 4 == 0, NRF_EINVAL,
+  const int pe_dirs = (out_bf16 >> 9) & 1;
+  NRF_REQUIRE(num_freqs >= 0 && num_freqs <= 24, NRF_EINVAL, "nrf_encode_points: num_freqs=%d", num_freqs);
+  NRF_REQUIRE(ld_out >= C + 6 + (pe_dirs ? 12 : 6) * num_freqs && ld_out % 4 == 0, NRF_EINVAL,
               "nrf_encode_points: ld_out=%d too small / unaligned", ld_out);
   EncodeArgs a;
   a.rays = rays; a.z = z; a.R = R; a.K = K; a.rays_per_scene = rays_per_scene;
@@ -701,11 +707,12 @@ static int encode_points_impl(const float* rays, const float* z, int R, int K, i
   a.num_freqs = num_freqs; a.freq_factor = freq_factor;
   a.out = out; a.ld_out = ld_out; a.points = points_out;
   a.fma = (out_bf16 >> 8) & 1;
+  a.pe_dirs = pe_dirs;
   a.touch = touch_flags;
   out_bf16 &= 0xff;
   int64_t N = (int64_t)R * K;
   int threads = 256;
-  const bool w32 = num_freqs == kTailFreqs && ld_out == C + kTailW &&
+  const bool w32 = !pe_dirs && num_freqs == kTailFreqs && ld_out == C + kTailW &&
                    (reinterpret_cast<uintptr_t>(rays) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   const char* tma_env = getenv("NRF_ENCODE_TMA");             // "0": encode_points_w32_kernel (A/B, tests)
   if (w32 && (C == 128 || C == 64) && S0 >= 2 && S1 >= 2 && S2 >= 2 && !(tma_env && atoi(tma_env) == 0) &&

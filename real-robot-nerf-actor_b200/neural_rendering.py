@@ -12,9 +12,10 @@ Differences from the reference, all opt-in or invisible to its callers:
     gradients too: ordered reduction instead of fp32 atomics) attributes;
   * `forward_nerf(rays, want_weights=False, noise=None)`: `noise` injects pre-drawn tensors
     (keys coarse / u / fine / depth), used by the parity tests;
-  * the optional branches of nerfact.conf: coord / attention heads run on the default (fused) path; multi-scale voxels
-    and ret_last_feat run composed.py (same kernels, three autograd nodes per pass, fp32 MLP); softplus, spade and
-    the depth-supervision volume (which the reference itself cannot run) raise NotImplementedError.
+  * the optional branches of nerfact.conf: coord / attention heads run on the default (fused) path; multi-scale voxels,
+    ret_last_feat and use_code_viewdirs run composed.py (same kernels, three autograd nodes per pass, fp32 MLP);
+    normalize_z is the no-op it is in the reference; softplus, spade, and the two branches the reference itself cannot
+    run (the depth-supervision volume, use_freenerf) raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -324,7 +325,6 @@ class PixelNeRFEmbedNet(nn.Module):
         unsupported = dict(use_depth_supervision=g("use_depth_supervision", False),   # cannot run in the reference either
                                                                                       # (models_embed.py:151-154 never
                                                                                       # stores voxel_density, :289 samples None)
-                           use_code_viewdirs=g("use_code_viewdirs", False),
                            use_freenerf=g("use_freenerf", False))    # models_embed.py:350-352 is a debugger breakpoint
                                                                      # and an invalid statement: it cannot run there either
         for k, v in unsupported.items():
@@ -342,7 +342,10 @@ class PixelNeRFEmbedNet(nn.Module):
         self.normalize_z = bool(g("normalize_z", False))
         self.canon_xyz = True
         self.stop_encoder_grad = stop_encoder_grad
-        self.use_code, self.use_code_viewdirs, self.use_viewdirs, self.use_xyz = True, False, True, True
+        self.use_code, self.use_viewdirs, self.use_xyz = True, True, True
+        # models_embed.py:86-95,:370-372: the view direction goes THROUGH the positional encoding (6 inputs, d_in = 78)
+        # instead of behind it (d_in = 42); runs on the composed fp32 branch (composed.py)
+        self.use_code_viewdirs = bool(g("use_code_viewdirs", False))
         self.use_freenerf = False
         self.regress_coord = bool(g("regress_coord", False))            # models_embed.py:63-68: 3 / 6 more outputs
         self.regress_attention = bool(g("regress_attention", False))
@@ -350,8 +353,8 @@ class PixelNeRFEmbedNet(nn.Module):
         self.use_multi_scale_voxel = bool(g("use_multi_scale_voxel", False))        # models_embed.py:69-72
         self.d_latent = d_latent = g("d_multi_scale_latent") if self.use_multi_scale_voxel else g("d_latent")
         self.d_lang = g("d_lang", 0)
-        self.code = PositionalEncoding.from_conf(conf["code"], d_in=3)
-        d_in = self.code.d_out + 3
+        self.code = PositionalEncoding.from_conf(conf["code"], d_in=6 if self.use_code_viewdirs else 3)
+        d_in = self.code.d_out + (0 if self.use_code_viewdirs else 3)
         d_out = 4 + conf["d_embed"] + (3 if self.regress_coord else 0) + (6 if self.regress_attention else 0)
         self.share_mlp = g("share_mlp", True)
         mlp = conf["mlp"] if not hasattr(conf, "mlp") else conf.mlp
@@ -417,7 +420,7 @@ class PixelNeRFEmbedNet(nn.Module):
         rays[:, 3:6] = viewdirs.reshape(-1, 3)
         bounds = torch.as_tensor(self.coordinate_bounds, dtype=torch.float32).reshape(-1).cpu()
         last_feat = None
-        if ret_last_feat or self.use_multi_scale_voxel:          # composed branch (composed.py): fp32 MLP, layer by layer
+        if ret_last_feat or self.use_multi_scale_voxel or self.use_code_viewdirs:   # composed branch (composed.py): fp32 MLP, layer by layer
             from . import composed
             z0 = torch.zeros(SB * B, 1, device=xyz.device, dtype=torch.float32)
             vols = list(self.multi_scale_voxel_list or []) + [self.voxel_feat]
@@ -891,7 +894,8 @@ class NeuralRenderer(nn.Module):
         self.noise_std, self.white_bkgd, self.depth_std = g("noise_std", 0.0), g("white_bkgd", False), g("depth_std", 0.001)
         self.nerf_model = PixelNeRFEmbedNet(cfg, coordinate_bounds)
         # multi-scale voxels / ret_last_feat change the MLP's input / what is composited: composed.py
-        self._composed = bool(self.ret_last_feat) or self.nerf_model.use_multi_scale_voxel
+        self._composed = bool(self.ret_last_feat) or self.nerf_model.use_multi_scale_voxel or \
+            self.nerf_model.use_code_viewdirs
         self.model_name = g("foundation_model_name", None)
         if self.model_name not in ("odise", "diffusion", "dinov2", "deepfloyd", None):
             raise NotImplementedError(f"foundation model {self.model_name} is not implemented")

@@ -250,8 +250,10 @@ GATHER_FMA = False      # True: accumulate the trilinear corners with FMAs (ATen
 
 @_on_tensor_device
 def encode_points(rays, z, rays_per_scene, vol_cl, bounds, num_freqs=6, freq_factor=1.5, ld_out=None,
-                  precision=NRF_PREC_BF16, want_points=False, out=None, fma=None, want_touch=False):
+                  precision=NRF_PREC_BF16, want_points=False, out=None, fma=None, want_touch=False,
+                  code_viewdirs=False):
     """Field-input rows [latent | PE | viewdir | 0] for every sample (see nrf_encode_points).
+    code_viewdirs: use_code_viewdirs (models_embed.py:370-372) - rows [latent | PE([xyz | viewdir]) | 0].
     want_touch: also return one uint8 per 32 consecutive samples, 1 if any of them has a corner inside the grid
     (nrf_encode_points_touch; what FieldMLP.backward(touch=...) skips whole dL/dlatent tiles by)."""
     rays = _f32(rays, "rays")
@@ -259,14 +261,14 @@ def encode_points(rays, z, rays_per_scene, vol_cl, bounds, num_freqs=6, freq_fac
     vol_cl = _f32(vol_cl, "volume")
     R, K = z.shape
     SB, S0, S1, S2, Cc = vol_cl.shape
-    need = Cc + 6 + 6 * num_freqs
+    need = Cc + 6 + (12 if code_viewdirs else 6) * num_freqs
     if ld_out is None:
         ld_out = (need + 63) // 64 * 64
     if out is None:
         out = torch.empty(R * K, ld_out, device=rays.device, dtype=act_dtype(precision))
     pts = torch.empty(R * K, 3, device=rays.device, dtype=torch.float32) if want_points else None
     bh = _bounds_host(bounds)
-    kind = _OUT_KIND[out.dtype] | (0x100 if (GATHER_FMA if fma is None else fma) else 0)
+    kind = _OUT_KIND[out.dtype] | (0x100 if (GATHER_FMA if fma is None else fma) else 0) | (0x200 if code_viewdirs else 0)
     if want_touch:
         touch = torch.empty((R * K + 31) // 32, device=rays.device, dtype=torch.uint8)
         check(_lib.load().nrf_encode_points_touch(ptr(rays), ptr(z), R, K, rays_per_scene, ptr(vol_cl), SB, Cc, S0, S1,

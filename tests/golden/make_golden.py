@@ -18,6 +18,8 @@ Cases
                             forward_nerf incl. coord / attention and the gradients of a probe loss over all of them.
   small_multiscale        : use_multi_scale_voxel (three volumes of 10 / 8 / 16 channels at 12^3 / 6^3 / 12^3) with
                             ret_last_feat (the MLP's last residual stream composited) and depth-guided samples.
+  small_codeviewdirs      : use_code_viewdirs (view direction through the positional encoding, d_in = 78) with
+                            normalize_z = True (a no-op under the hard-coded canon_xyz) and depth-guided samples.
   raygen                  : gen_rays for 60x80 (focal 76.18187) and rows of 128x128 (focal 153).
   voxelize_small          : the reference's VoxelGrid.coords_to_bounding_voxel_grid (voxel_grid_real.py) on a seeded
                             clustered point cloud (inputs regenerated from the seed by synthetic.voxelizer_points).
@@ -272,6 +274,68 @@ def run_multiscale_case(name="small_multiscale", S=12, C=16, D=24, hidden=64, SB
     print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "loss", float(loss))
 
 
+def run_code_viewdirs_case(name="small_codeviewdirs", S=12, C=16, D=24, hidden=64, SB=2, n_rays=40, Kc=16, Kf=16, Kfd=2,
+                           H=16, W=16, focal=19.0, seed=9):
+    """use_code_viewdirs (models_embed.py:86-95,:355-372: the view direction goes through the positional encoding with
+    the point, d_in = 6 + 12 * 6 = 78) together with normalize_z = True (:337-340: a no-op under the hard-coded
+    canon_xyz, :42 - this case is what pins that claim); forward_nerf of the reference + a probe loss over its
+    outputs, gradients into the volume and the MLP.  Also the reference's PositionalEncoding on 6-d inputs."""
+    torch.manual_seed(seed)
+    cfg = L.default_cfg(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H, n_coarse=Kc, n_fine=Kf,
+                        n_fine_depth=Kfd, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden), eval_batch_size=1024,
+                        use_code_viewdirs=True, normalize_z=True)
+    ren = L.build_reference_renderer(cfg, torch.tensor(syn.BOUNDS))
+    assert ren.nerf_model.d_in == 78 and ren.nerf_model.mlp_coarse.lin_in.weight.shape == (hidden, 78)
+    params = O.init_params(d_in=78, d_latent=C, d_hidden=hidden, d_out=4 + D, seed=seed)
+    g = torch.Generator().manual_seed(77 + seed)
+    for k in params:
+        if k.endswith(".bias"):
+            params[k] = 0.05 * torch.randn(params[k].shape, generator=g)
+    load_params_into(ren, params)
+    vol = syn.make_volume(SB, C, S, seed=seed).requires_grad_(True)
+    poses = syn.arc_poses(SB)
+    focal_t = torch.tensor(focal, dtype=torch.float32)
+    idx = syn.pick_ray_indices(H * W, n_rays, seed=seed)
+    R = SB * n_rays
+    noise = syn.make_noise(R, Kc, Kf - Kfd, seed=seed)
+    noise["depth"] = torch.randn(R, Kfd, generator=g)
+    U = sys.modules["_nrf_reference_utils"]
+    rays = U.gen_rays(poses, W, H, focal_t, cfg.z_near, cfg.z_far, c=None).reshape(SB, H * W, 8)[:, idx]
+    ren.train()
+    ren.encode(None, None, None, vol, poses, focal_t, None)
+    with L.inject_noise([noise["coarse"], noise["u"], noise["fine"], noise["depth"]]):
+        o = ren.forward_nerf(rays, want_weights=True)
+    gw = torch.Generator().manual_seed(900 + seed)
+    loss = 0.0
+    probes = {}
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth"):
+            t = o[lvl][k]
+            probes[f"{lvl}_{k}"] = torch.randn(t.shape, generator=gw)
+            loss = loss + (t * probes[f"{lvl}_{k}"]).sum()
+    loss.backward()
+    fx = {"meta": np.array([S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed]), "focal": np.float32(focal),
+          "idx": idx.numpy(), "rays": rays.numpy(), "loss": np.float32(loss.item()), "vol": vol.detach().numpy(),
+          "vgrad": vol.grad.numpy(), "poses": poses.numpy()}
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "weights"):
+            fx[f"{lvl}_{k}"] = o[lvl][k].detach().numpy()
+    for k, v in probes.items():
+        fx["probe_" + k] = v.numpy()
+    for k, v in params.items():
+        fx["param." + k] = v.numpy()
+    for k, p in ren.nerf_model.mlp_coarse.named_parameters():
+        fx["grad." + k] = p.grad.numpy()
+    for k, v in noise.items():
+        fx["noise_" + k] = v.numpy()
+    x6 = torch.rand(129, 6, generator=torch.Generator().manual_seed(5)) * 2.0 - 1.0
+    fx["pe6_x"] = x6.numpy()
+    fx["pe6_out"] = ren.nerf_model.code(x6).detach().numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **fx)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "loss", float(loss))
+
+
 def run_raygen():
     L.load_reference()
     U = sys.modules["_nrf_reference_utils"]
@@ -315,9 +379,13 @@ if __name__ == "__main__":
     if "--multiscale-only" in sys.argv:
         run_multiscale_case()
         sys.exit(0)
+    if "--codeviewdirs-only" in sys.argv:
+        run_code_viewdirs_case()
+        sys.exit(0)
     run_raygen()
     run_heads_case()
     run_multiscale_case()
+    run_code_viewdirs_case()
     run_voxelizer()
     run_case("small_kfd0", S=12, C=16, D=24, hidden=64, SB=2, n_rays=48, Kc=16, Kf=16, Kfd=0,
              H=16, W=16, focal=19.0, store_inputs=True)

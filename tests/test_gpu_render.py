@@ -905,6 +905,52 @@ def test_multiscale_voxels_and_last_feat_match_the_reference(ops, NR):
     assert dens is None and rel(got, ref) < 1e-4 and rel(last, ref_last) < 1e-4
 
 
+def test_code_viewdirs_matches_the_reference(ops, NR):
+    """use_code_viewdirs (models_embed.py:86-95,:355-372: the view direction goes through the positional encoding with
+    the point, field input [latent | PE([xyz | dir]) (78)]) with normalize_z = True (the reference's own no-op), through
+    composed.py: outputs and the gradients into the volume and the MLP against the reference's fixture; the encoding
+    itself against the reference's PositionalEncoding on 6-d inputs; the field at explicit points against the oracle."""
+    fx = golden("small_codeviewdirs")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    ren = make_renderer(NR, meta, ci["params"], "bf16", use_code_viewdirs=True, normalize_z=True)
+    assert ren._composed and ren.nerf_model.d_in == 78 and ren.nerf_model.code.d_in == 6
+    assert ren.nerf_model.mlp_coarse.lin_in.weight.shape == (ci["hidden"], 78)
+    # the encoding kernel on its own: rays whose origin is the canonical point (z = 0, unit bounds) and whose direction
+    # is the other half of the 6-d input
+    x6 = T(fx["pe6_x"])
+    rays = torch.zeros(x6.shape[0], 8)
+    rays[:, 0:6] = x6
+    vol1 = torch.zeros(1, 2, 2, 2, 4).cuda()                          # (SB, S0, S1, S2, C = 4) channels-last, unused values
+    rows = ops.encode_points(rays.cuda(), torch.zeros(x6.shape[0], 1).cuda(), x6.shape[0], vol1,
+                             torch.tensor([0.0, 0, 0, 1, 1, 1]), 6, 1.5, precision=ops.NRF_PREC_FP32, code_viewdirs=True)
+    assert rows.shape[1] == 128 and float(rows[:, 4 + 78:].abs().max()) == 0.0
+    pe = rows[:, 4:4 + 78].cpu()
+    assert torch.equal(pe[:, :6], x6)
+    assert float((pe - T(fx["pe6_out"])).abs().max()) <= 5e-7          # sin ulp, as for the 3-d encoding
+    vol = T(fx["vol"]).cuda().requires_grad_(True)
+    ren.encode(None, None, None, vol, None, None, None)
+    out = ren.forward_nerf(T(fx["rays"]).cuda(), want_weights=True, noise={k: v.cuda() for k, v in ci["noise"].items()})
+    loss = 0.0
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "weights"):
+            e = rel(out[lvl][k], T(fx[f"{lvl}_{k}"]))
+            assert e < 1e-4, (lvl, k, e)
+        for k in ("rgb", "embed", "depth"):
+            loss = loss + (out[lvl][k] * T(fx[f"probe_{lvl}_{k}"]).cuda()).sum()
+    assert abs(float(loss) - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+    loss.backward()
+    assert rel(vol.grad, T(fx["vgrad"])) < 3e-4
+    for k, p in ren.nerf_model.mlp_coarse.named_parameters():
+        assert rel(p.grad, T(fx["grad." + k])) < 1e-3, k
+    pts = torch.rand(2, 30, 3, generator=torch.Generator().manual_seed(1)) * 0.8
+    dirs = torch.nn.functional.normalize(torch.randn(2, 30, 3, generator=torch.Generator().manual_seed(2)), dim=-1)
+    with torch.no_grad():
+        got, dens = ren.nerf_model(pts.cuda(), viewdirs=dirs.cuda())
+        ref = O.field(ci["params"], T(fx["vol"]), pts, dirs, syn.BOUNDS, code_viewdirs=True)
+    assert dens is None and rel(got, ref) < 1e-4
+
+
 def test_radiance_and_point_cloud_extraction(ops, NR):
     """The ancestor's `extract_radience` switch (nerf_embed.py:338-342,432-516) and the point-cloud masks of
     `extract_nerf_feat` (train_nerfact_multi_kitchen.py:985-1040): field values at the sorted coarse + fine samples

@@ -203,3 +203,27 @@ def test_oracle_multiscale_and_last_feat_match_reference():
         assert _rel(v.grad, T(fx[f"ms{i}_grad"])) < 1e-5, i
     for k, v in pr.items():
         assert _rel(v.grad, T(fx["grad." + k])) < 1e-4, k
+
+
+def test_oracle_code_viewdirs_matches_reference():
+    """use_code_viewdirs (models_embed.py:86-95,:355-372: [xyz | viewdir] through the positional encoding together, d_in =
+    78) with normalize_z = True - which the fixture shows to be the no-op models_embed.py:42,:337-340 make it: the oracle
+    has no such switch and still reproduces the reference (small_codeviewdirs.npz)."""
+    fx = golden("small_codeviewdirs")
+    ci = _case_inputs(fx)
+    assert ci["params"]["lin_in.weight"].shape[1] == 78
+    assert _rel(O.positional_encoding(T(fx["pe6_x"]), 6, 1.5, True), T(fx["pe6_out"])) < 1e-7
+    pr = {k: v.clone().requires_grad_(True) for k, v in ci["params"].items()}
+    vol = T(fx["vol"]).clone().requires_grad_(True)
+    out = O.forward_nerf(pr, vol, T(fx["rays"]), syn.BOUNDS, ci["Kc"], ci["Kf"], ci["Kfd"], noise=ci["noise"],
+                         eval_batch_size=1024, code_viewdirs=True)
+    loss = 0.0
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth"):
+            assert _rel(out[lvl][k], T(fx[f"{lvl}_{k}"])) < 2e-6, (lvl, k)
+            loss = loss + (out[lvl][k] * T(fx[f"probe_{lvl}_{k}"])).sum()
+    assert abs(float(loss) - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+    loss.backward()
+    assert _rel(vol.grad, T(fx["vgrad"])) < 1e-5
+    for k, v in pr.items():
+        assert _rel(v.grad, T(fx["grad." + k])) < 1e-4, k

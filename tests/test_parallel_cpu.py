@@ -153,6 +153,11 @@ def test_renderer_keeps_reference_surface():
     heads = NR.NeuralRenderer(U.default_config(regress_coord=True, regress_attention=True), torch.zeros(6))
     assert heads.nerf_model.d_out == 4 + 384 + 3 + 6 and heads._d_comp == 396          # models_embed.py:96-103
     assert heads.nerf_model.mlp_coarse.lin_out.weight.shape == (397, 512)
+    cv = NR.NeuralRenderer(U.default_config(use_code_viewdirs=True, normalize_z=True), torch.zeros(6))
+    assert cv._composed and cv.nerf_model.d_in == 78 and cv.nerf_model.code.d_out == 78      # models_embed.py:86-95
+    assert cv.nerf_model.mlp_coarse.lin_in.weight.shape == (512, 78) and len(cv.state_dict()) == 62
+    with pytest.raises(NotImplementedError):      # a debugger breakpoint in the reference (models_embed.py:350-352)
+        NR.NeuralRenderer(U.default_config(use_freenerf=True), torch.zeros(6))
     with pytest.raises(NotImplementedError):
         NR.NeuralRenderer(U.default_config(foundation_model_name="nope"), torch.zeros(6))
     with pytest.raises(Exception):                # CPU tensors are rejected: there is no CPU fallback
