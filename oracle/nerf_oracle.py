@@ -190,28 +190,33 @@ def _linear(x, w, b, operand_dtype=None):
     return F.linear(x, w, b)
 
 
-def resnetfc(p: Params, zx, d_latent, n_blocks=5, combine_layer=3, operand_dtype=None, ret_last=False):
-    """resnetfc.py:146-195 with ResnetBlockFC.forward :55-64 (ReLU, no shortcut, no spade).
+def resnetfc(p: Params, zx, d_latent, n_blocks=5, combine_layer=3, operand_dtype=None, ret_last=False, beta=0.0,
+             use_spade=False):
+    """resnetfc.py:146-195 with ResnetBlockFC.forward :55-64 (no shortcut: size_in == size_out).
 
     zx (n, d_latent + d_in) -> (n, d_out).  combine_interleaved (utils.py:509-519) at
     blkid == combine_layer averages over a size-1 dim (num_views_per_obj = 1): identity.
+    beta > 0: softplus activations (:43-46,:138-141); use_spade: x = scale_z(z) * x + lin_z(z) (:130-136,:184-186).
     """
     z, x = zx[..., :d_latent], zx[..., d_latent:]
     lin = lambda name, t: _linear(t, p[name + ".weight"], p[name + ".bias"], operand_dtype)
+    act = (lambda t: F.softplus(t, beta=beta)) if beta > 0 else torch.relu
     x = lin("lin_in", x)
     for b in range(n_blocks):
         if d_latent > 0 and b < combine_layer:
-            x = x + lin(f"lin_z.{b}", z)
-        net = lin(f"blocks.{b}.fc_0", torch.relu(x))
-        dx = lin(f"blocks.{b}.fc_1", torch.relu(net))
+            tz = lin(f"lin_z.{b}", z)
+            x = lin(f"scale_z.{b}", z) * x + tz if use_spade else x + tz
+        net = lin(f"blocks.{b}.fc_0", act(x))
+        dx = lin(f"blocks.{b}.fc_1", act(net))
         x = x + dx
-    out = lin("lin_out", torch.relu(x))
+    out = lin("lin_out", act(x))
     return (out, x) if ret_last else out            # resnetfc.py:192-195: (out, x); ret_last_feat concatenates them
 
 
 def field(p: Params, voxel_feat, xyz, viewdirs, bounds, code=(6, 1.5, True),
           n_blocks=5, combine_layer=3, operand_dtype=None, return_mlp_input=False, regress_coord=False,
-          regress_attention=False, multi_scale_voxel_list=None, ret_last_feat=False, code_viewdirs=False):
+          regress_attention=False, multi_scale_voxel_list=None, ret_last_feat=False, code_viewdirs=False, beta=0.0,
+          use_spade=False):
     """models_embed.py:295-471 default branch. xyz, viewdirs (SB,n,3) -> (SB,n,4+D).
 
     mlp_input = [latent(C) | PE(xyz)(39) | viewdir(3)] (:366,:405); heads sigmoid(rgb),
@@ -231,7 +236,8 @@ def field(p: Params, voxel_feat, xyz, viewdirs, bounds, code=(6, 1.5, True),
     mlp_input = torch.cat((latent.reshape(-1, C), zf), dim=-1)
     if return_mlp_input:
         return mlp_input
-    out = resnetfc(p, mlp_input, C, n_blocks, combine_layer, operand_dtype, ret_last=ret_last_feat)
+    out = resnetfc(p, mlp_input, C, n_blocks, combine_layer, operand_dtype, ret_last=ret_last_feat, beta=beta,
+                   use_spade=use_spade)
     last = None
     if ret_last_feat:
         out, last = out
@@ -378,7 +384,7 @@ def rendering_loss(outputs, gt_rgb, gt_embed, gt_depth=None, lambda_embed=0.01, 
 
 # -------------------------------------------------------------------- parameters
 def init_params(d_in=42, d_latent=128, d_hidden=512, d_out=388, n_blocks=5, combine_layer=3,
-                seed=0, randomize_fc1=True, device="cpu") -> Params:
+                seed=0, randomize_fc1=True, device="cpu", use_spade=False) -> Params:
     """Reference init (resnetfc.py:38-41,92-98,126-128): kaiming-normal fan-in, zero biases,
     fc_1.weight = 0.  `randomize_fc1` overwrites fc_1.weight ~ N(0, 2/d_hidden) so the blocks
     are not identities.  Drawn from a CPU generator: identical on every machine.
@@ -396,6 +402,10 @@ def init_params(d_in=42, d_latent=128, d_hidden=512, d_out=388, n_blocks=5, comb
     for b in range(min(combine_layer, n_blocks)):
         p[f"lin_z.{b}.weight"] = kaiming(d_hidden, d_latent)
         p[f"lin_z.{b}.bias"] = torch.zeros(d_hidden)
+    if use_spade:                                    # resnetfc.py:130-136 (drawn last: the other tensors keep their values)
+        for b in range(min(combine_layer, n_blocks)):
+            p[f"scale_z.{b}.weight"] = kaiming(d_hidden, d_latent)
+            p[f"scale_z.{b}.bias"] = torch.zeros(d_hidden)
     return {k: v.to(device) for k, v in p.items()}
 
 

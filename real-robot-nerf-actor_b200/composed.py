@@ -8,6 +8,9 @@
   * `use_code_viewdirs` (models_embed.py:86-95,:355-372): the view direction goes through the positional encoding
     together with the point (nrf_encode_points with out_bf16 | 0x200: tail of 78 columns, MLP d_in = 78).
 
+  * softplus activations (`mlp.beta > 0`) and SPADE modulation (`mlp.use_spade`), resnetfc.py:43-46,130-141,184-186:
+    the MLP layer by layer (`mlp_general`: one LinearFn node per layer on nrf_gemm / nrf_wgrad, fp32).
+
 All are off in nerfact.conf.  They run on the same kernels as the default path (nrf_encode_points per volume, the
 field MLP, nrf_composite_*, nrf_scatter_volume_grad_sorted per volume), composed at the torch level as three autograd
 nodes per pass instead of one per forward_nerf - so the general shapes (266 latent channels, volumes of 10 channels,
@@ -91,6 +94,57 @@ class MlpLastFn(torch.autograd.Function):
         return (None, dzx, *[grads[n] for n in h.names()])
 
 
+class LinearFn(torch.autograd.Function):
+    """y = x . W^T + b on the fp32 GEMM kernels: nrf_gemm forward and data gradient, nrf_wgrad for dW / db - one layer of
+    the field MLP as an autograd node of its own, for the MLP variants whose glue between the layers is not the fused
+    chain's (mlp_general)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w = x.detach().contiguous(), w.detach().contiguous()
+        out = torch.empty(x.shape[0], w.shape[0], device=x.device, dtype=torch.float32)
+        ops.gemm(x, w, bias=b.detach().contiguous(), out_f32=out, precision=NRF_PREC_FP32)
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ops.gemm(g, w.t().contiguous(), out_f32=dx, precision=NRF_PREC_FP32)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw = torch.zeros_like(w)
+            db = torch.zeros(w.shape[0], device=w.device, dtype=torch.float32)
+            ops.wgrad(g, x, dw, db, precision=NRF_PREC_FP32)
+        return dx, dw, db
+
+
+def mlp_general(mlp, zx):
+    """ResnetFC.forward (resnetfc.py:146-195) with the two options the fused chain is not built for: softplus
+    activations (beta > 0, :43-46,:138-141) and SPADE modulation of the residual stream by the latent (use_spade,
+    :130-136,:184-186: x = scale_z(z) * x + lin_z(z)).  zx (N, d_latent + d_in) fp32 -> (raw outputs (N, d_out), x_nb (N,
+    d_hidden)).  Every linear layer is a LinearFn node; the activations and the modulation are elementwise torch ops."""
+    if zx.shape[1] != mlp.d_latent + mlp.d_in:
+        raise RuntimeError(f"field MLP input has {zx.shape[1]} columns, expected d_latent + d_in = "
+                           f"{mlp.d_latent} + {mlp.d_in}")
+    act = (lambda t: torch.nn.functional.softplus(t, beta=mlp.beta)) if mlp.beta > 0 else torch.relu
+    lin = lambda layer, t: LinearFn.apply(t, layer.weight, layer.bias)
+    zx = zx.to(torch.float32)
+    z, x = zx[:, :mlp.d_latent], zx[:, mlp.d_latent:]
+    x = lin(mlp.lin_in, x)
+    for b in range(mlp.n_blocks):
+        if b < mlp.n_lin_z:                                   # resnetfc.py:181-188 (combine_interleaved is the identity
+            tz = lin(mlp.lin_z[b], z)                         # for one view, :176-179)
+            x = lin(mlp.scale_z[b], z) * x + tz if mlp.use_spade else x + tz
+        blk = mlp.blocks[b]                                   # resnetfc.py:55-64, identity shortcut
+        net = lin(blk.fc_0, act(x))
+        x = x + lin(blk.fc_1, act(net))
+    return lin(mlp.lin_out, act(x)), x
+
+
 class CompositeFieldFn(torch.autograd.Function):
     """Alpha compositing (neural_rendering.py:339-359) of given RAW field rows (N, ld) [rgb | sigma | D channels]:
     -> weights (R,K), rgb (R,3), composited channels (R,D), depth (R).  Differentiable w.r.t. the rows and z."""
@@ -127,6 +181,8 @@ def field_rows(ren, model, mlp, vols, rays, z, rps):
     if zx.shape[1] != model.d_latent + model.d_in:
         raise RuntimeError(f"multi-scale latent has {zx.shape[1] - model.d_in} channels, the model expects d_latent = "
                            f"{model.d_latent} (d_multi_scale_latent)")
+    if mlp.general:                                           # softplus / SPADE: layer by layer at the torch level
+        return mlp_general(mlp, zx)
     h = mlp.handle(NRF_PREC_FP32)
     ps = [mlp.param_dict()[n] for n in h.names()]
     return MlpLastFn.apply(h, zx, *ps)

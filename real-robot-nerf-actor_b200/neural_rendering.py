@@ -14,8 +14,9 @@ Differences from the reference, all opt-in or invisible to its callers:
     (keys coarse / u / fine / depth), used by the parity tests;
   * the optional branches of nerfact.conf: coord / attention heads run on the default (fused) path; multi-scale voxels,
     ret_last_feat and use_code_viewdirs run composed.py (same kernels, three autograd nodes per pass, fp32 MLP);
-    normalize_z is the no-op it is in the reference; softplus, spade, and the two branches the reference itself cannot
-    run (the depth-supervision volume, use_freenerf) raise NotImplementedError.
+    softplus activations (mlp.beta > 0) and SPADE modulation (mlp.use_spade) run there too, layer by layer on the fp32
+    GEMM kernels (composed.mlp_general); normalize_z is the no-op it is in the reference; the two branches the reference
+    itself cannot run (the depth-supervision volume, use_freenerf) raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -212,10 +213,10 @@ class ResnetFC(nn.Module):
     def __init__(self, d_in, d_out=4, n_blocks=5, d_latent=0, d_lang=0, d_hidden=128, beta=0.0,
                  combine_layer=1000, combine_type="average", use_spade=False, use_language=False):
         super().__init__()
-        if beta > 0:
-            raise NotImplementedError("softplus activation (beta > 0) is not built; nerfact.conf uses ReLU")
-        if use_spade:
-            raise NotImplementedError("use_spade is off in nerfact.conf and not built")
+        # resnetfc.py:43-46,138-141 softplus activations (beta > 0) and :130-136,184-186 SPADE modulation (x = sz * x + tz)
+        # are off in nerfact.conf; they run layer by layer on the fp32 GEMM kernels (composed.mlp_general)
+        self.beta = float(beta)
+        self.general = self.beta > 0 or bool(use_spade)
         self.lin_in = nn.Linear(d_in, d_hidden)
         nn.init.constant_(self.lin_in.bias, 0.0)
         nn.init.kaiming_normal_(self.lin_in.weight, a=0, mode="fan_in")
@@ -233,6 +234,11 @@ class ResnetFC(nn.Module):
             for i in range(n_lin_z):
                 nn.init.constant_(self.lin_z[i].bias, 0.0)
                 nn.init.kaiming_normal_(self.lin_z[i].weight, a=0, mode="fan_in")
+            if self.use_spade:                                        # resnetfc.py:130-136
+                self.scale_z = nn.ModuleList([nn.Linear(d_latent, d_hidden) for _ in range(n_lin_z)])
+                for i in range(n_lin_z):
+                    nn.init.constant_(self.scale_z[i].bias, 0.0)
+                    nn.init.kaiming_normal_(self.scale_z[i].weight, a=0, mode="fan_in")
         self._handles = {}
 
     @property
@@ -273,10 +279,13 @@ class ResnetFC(nn.Module):
 
     def forward(self, zx, precision="bf16", **_ignored):
         """zx (..., d_latent + d_in) -> (out (..., d_out), None).  See `_MlpFn`."""
-        prec = ops.PRECISIONS[precision] if isinstance(precision, str) else precision
-        h = self.handle(prec)
         lead = zx.shape[:-1]
         flat = zx.reshape(-1, zx.shape[-1])
+        if self.general:
+            from . import composed
+            return composed.mlp_general(self, flat)[0].reshape(*lead, self.d_out), None
+        prec = ops.PRECISIONS[precision] if isinstance(precision, str) else precision
+        h = self.handle(prec)
         names = h.names()
         out = _MlpFn.apply(h, flat, *[self.param_dict()[n] for n in names])
         return out.reshape(*lead, self.d_out), None
@@ -420,7 +429,7 @@ class PixelNeRFEmbedNet(nn.Module):
         rays[:, 3:6] = viewdirs.reshape(-1, 3)
         bounds = torch.as_tensor(self.coordinate_bounds, dtype=torch.float32).reshape(-1).cpu()
         last_feat = None
-        if ret_last_feat or self.use_multi_scale_voxel or self.use_code_viewdirs:   # composed branch (composed.py): fp32 MLP, layer by layer
+        if ret_last_feat or self.use_multi_scale_voxel or self.use_code_viewdirs or mlp.general:   # composed branch (composed.py): fp32 MLP, layer by layer
             from . import composed
             z0 = torch.zeros(SB * B, 1, device=xyz.device, dtype=torch.float32)
             vols = list(self.multi_scale_voxel_list or []) + [self.voxel_feat]
@@ -895,7 +904,7 @@ class NeuralRenderer(nn.Module):
         self.nerf_model = PixelNeRFEmbedNet(cfg, coordinate_bounds)
         # multi-scale voxels / ret_last_feat change the MLP's input / what is composited: composed.py
         self._composed = bool(self.ret_last_feat) or self.nerf_model.use_multi_scale_voxel or \
-            self.nerf_model.use_code_viewdirs
+            self.nerf_model.use_code_viewdirs or self.nerf_model.mlp_coarse.general
         self.model_name = g("foundation_model_name", None)
         if self.model_name not in ("odise", "diffusion", "dinov2", "deepfloyd", None):
             raise NotImplementedError(f"foundation model {self.model_name} is not implemented")

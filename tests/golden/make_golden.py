@@ -20,6 +20,7 @@ Cases
                             ret_last_feat (the MLP's last residual stream composited) and depth-guided samples.
   small_codeviewdirs      : use_code_viewdirs (view direction through the positional encoding, d_in = 78) with
                             normalize_z = True (a no-op under the hard-coded canon_xyz) and depth-guided samples.
+  small_softplus_spade    : mlp.beta = 10 (softplus activations) with mlp.use_spade (latent-modulated residual stream).
   raygen                  : gen_rays for 60x80 (focal 76.18187) and rows of 128x128 (focal 153).
   voxelize_small          : the reference's VoxelGrid.coords_to_bounding_voxel_grid (voxel_grid_real.py) on a seeded
                             clustered point cloud (inputs regenerated from the seed by synthetic.voxelizer_points).
@@ -336,6 +337,65 @@ def run_code_viewdirs_case(name="small_codeviewdirs", S=12, C=16, D=24, hidden=6
     print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "loss", float(loss))
 
 
+def run_softplus_spade_case(name="small_softplus_spade", S=12, C=16, D=24, hidden=64, SB=2, n_rays=40, Kc=16, Kf=16,
+                            H=16, W=16, focal=19.0, seed=10, beta=10.0):
+    """mlp.beta > 0 (softplus activations, resnetfc.py:43-46,:138-141) together with mlp.use_spade (the latent modulates
+    the residual stream: x = scale_z(z) * x + lin_z(z), :130-136,:184-186; six more parameters); forward_nerf of the
+    reference + a probe loss over its outputs, gradients into the volume and every MLP parameter."""
+    torch.manual_seed(seed)
+    cfg = L.default_cfg(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H, n_coarse=Kc, n_fine=Kf,
+                        n_fine_depth=0, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden, beta=beta, use_spade=True),
+                        eval_batch_size=1024)
+    ren = L.build_reference_renderer(cfg, torch.tensor(syn.BOUNDS))
+    assert len(ren.nerf_model.mlp_coarse.scale_z) == 3 and len(ren.state_dict()) == 74
+    params = O.init_params(d_in=42, d_latent=C, d_hidden=hidden, d_out=4 + D, seed=seed, use_spade=True)
+    g = torch.Generator().manual_seed(77 + seed)
+    for k in params:
+        if k.endswith(".bias"):
+            params[k] = 0.05 * torch.randn(params[k].shape, generator=g)
+        if k.startswith("scale_z") and k.endswith(".bias"):
+            params[k] = params[k] + 1.0                  # a scale around one keeps the stream's magnitude
+    load_params_into(ren, params)
+    vol = syn.make_volume(SB, C, S, seed=seed).requires_grad_(True)
+    poses = syn.arc_poses(SB)
+    focal_t = torch.tensor(focal, dtype=torch.float32)
+    idx = syn.pick_ray_indices(H * W, n_rays, seed=seed)
+    R = SB * n_rays
+    noise = syn.make_noise(R, Kc, Kf, seed=seed)
+    U = sys.modules["_nrf_reference_utils"]
+    rays = U.gen_rays(poses, W, H, focal_t, cfg.z_near, cfg.z_far, c=None).reshape(SB, H * W, 8)[:, idx]
+    ren.train()
+    ren.encode(None, None, None, vol, poses, focal_t, None)
+    with L.inject_noise([noise["coarse"], noise["u"], noise["fine"]]):
+        o = ren.forward_nerf(rays, want_weights=True)
+    gw = torch.Generator().manual_seed(900 + seed)
+    loss = 0.0
+    probes = {}
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth"):
+            t = o[lvl][k]
+            probes[f"{lvl}_{k}"] = torch.randn(t.shape, generator=gw)
+            loss = loss + (t * probes[f"{lvl}_{k}"]).sum()
+    loss.backward()
+    fx = {"meta": np.array([S, C, D, hidden, SB, n_rays, Kc, Kf, 0, H, W, seed]), "focal": np.float32(focal),
+          "beta": np.float32(beta), "idx": idx.numpy(), "rays": rays.numpy(), "loss": np.float32(loss.item()),
+          "vol": vol.detach().numpy(), "vgrad": vol.grad.numpy(), "poses": poses.numpy()}
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "weights"):
+            fx[f"{lvl}_{k}"] = o[lvl][k].detach().numpy()
+    for k, v in probes.items():
+        fx["probe_" + k] = v.numpy()
+    for k, v in params.items():
+        fx["param." + k] = v.numpy()
+    for k, p in ren.nerf_model.mlp_coarse.named_parameters():
+        fx["grad." + k] = p.grad.numpy()
+    for k, v in noise.items():
+        fx["noise_" + k] = v.numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **fx)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "loss", float(loss))
+
+
 def run_raygen():
     L.load_reference()
     U = sys.modules["_nrf_reference_utils"]
@@ -382,10 +442,14 @@ if __name__ == "__main__":
     if "--codeviewdirs-only" in sys.argv:
         run_code_viewdirs_case()
         sys.exit(0)
+    if "--softplus-spade-only" in sys.argv:
+        run_softplus_spade_case()
+        sys.exit(0)
     run_raygen()
     run_heads_case()
     run_multiscale_case()
     run_code_viewdirs_case()
+    run_softplus_spade_case()
     run_voxelizer()
     run_case("small_kfd0", S=12, C=16, D=24, hidden=64, SB=2, n_rays=48, Kc=16, Kf=16, Kfd=0,
              H=16, W=16, focal=19.0, store_inputs=True)

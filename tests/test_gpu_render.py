@@ -45,8 +45,10 @@ def cosine(a, b):
 def make_renderer(NR, meta, params, precision, **opts):
     U = load_pkg("utils")
     S, C, D, hidden, SB, n_rays, Kc, Kf, Kfd, H, W, seed = meta
+    mlp_opts = opts.pop("mlp", {})
     cfg = U.default_config(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H, n_coarse=Kc,
-                           n_fine=Kf, n_fine_depth=Kfd, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden), **opts)
+                           n_fine=Kf, n_fine_depth=Kfd, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden, **mlp_opts),
+                           **opts)
     ren = NR.NeuralRenderer(cfg, torch.tensor(syn.BOUNDS), precision=precision)
     sd = ren.state_dict()
     for k, v in params.items():
@@ -949,6 +951,61 @@ def test_code_viewdirs_matches_the_reference(ops, NR):
         got, dens = ren.nerf_model(pts.cuda(), viewdirs=dirs.cuda())
         ref = O.field(ci["params"], T(fx["vol"]), pts, dirs, syn.BOUNDS, code_viewdirs=True)
     assert dens is None and rel(got, ref) < 1e-4
+
+
+def test_softplus_and_spade_match_the_reference(ops, NR):
+    """mlp.beta = 10 (softplus activations, resnetfc.py:43-46,:138-141) with mlp.use_spade (x = scale_z(z) * x + lin_z(z),
+    :130-136,:184-186): the MLP layer by layer on nrf_gemm / nrf_wgrad (composed.mlp_general) inside the composed render;
+    outputs and the gradients into the volume and all 36 MLP parameters against the reference's fixture; the MLP alone
+    against the oracle; softplus alone and SPADE alone against the oracle."""
+    fx = golden("small_softplus_spade")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    beta = float(fx["beta"])
+    ren = make_renderer(NR, meta, ci["params"], "bf16", mlp=dict(beta=beta, use_spade=True))
+    mlp = ren.nerf_model.mlp_coarse
+    assert ren._composed and mlp.general and len(mlp.scale_z) == 3 and len(ren.state_dict()) == 74
+    vol = T(fx["vol"]).cuda().requires_grad_(True)
+    ren.encode(None, None, None, vol, None, None, None)
+    out = ren.forward_nerf(T(fx["rays"]).cuda(), want_weights=True, noise={k: v.cuda() for k, v in ci["noise"].items()})
+    loss = 0.0
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth", "weights"):
+            e = rel(out[lvl][k], T(fx[f"{lvl}_{k}"]))
+            assert e < 1e-4, (lvl, k, e)
+        for k in ("rgb", "embed", "depth"):
+            loss = loss + (out[lvl][k] * T(fx[f"probe_{lvl}_{k}"]).cuda()).sum()
+    assert abs(float(loss) - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+    loss.backward()
+    assert rel(vol.grad, T(fx["vgrad"])) < 3e-4
+    n = 0
+    for k, p in mlp.named_parameters():
+        assert rel(p.grad, T(fx["grad." + k])) < 1e-3, k
+        n += 1
+    assert n == 36
+    # the MLP alone (ResnetFC.forward hook), each option on its own, ragged row count
+    g = torch.Generator().manual_seed(3)
+    for kw in (dict(beta=4.0, use_spade=False), dict(beta=0.0, use_spade=True)):
+        p = O.init_params(d_in=42, d_latent=16, d_hidden=64, d_out=28, seed=5, use_spade=kw["use_spade"])
+        for k in p:
+            if k.endswith(".bias"):
+                p[k] = 0.1 * torch.randn(p[k].shape, generator=g)
+        m = NR.ResnetFC(d_in=42, d_out=28, n_blocks=5, d_latent=16, d_hidden=64, combine_layer=3, **kw)
+        m.load_state_dict(p)
+        m = m.cuda()
+        zx = torch.randn(333, 58, generator=g)
+        zc = zx.cuda().requires_grad_(True)
+        got, _ = m(zc)
+        pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        zr = zx.clone().requires_grad_(True)
+        ref = O.resnetfc(pr, zr, 16, beta=kw["beta"], use_spade=kw["use_spade"])
+        assert rel(got, ref) < 1e-5, kw
+        w = torch.randn(ref.shape, generator=g)
+        (got * w.cuda()).sum().backward()
+        (ref * w).sum().backward()
+        assert rel(zc.grad, zr.grad) < 1e-4, kw
+        for k, v in m.named_parameters():
+            assert rel(v.grad, pr[k].grad) < 1e-4, (kw, k)
 
 
 def test_radiance_and_point_cloud_extraction(ops, NR):

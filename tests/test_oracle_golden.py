@@ -227,3 +227,26 @@ def test_oracle_code_viewdirs_matches_reference():
     assert _rel(vol.grad, T(fx["vgrad"])) < 1e-5
     for k, v in pr.items():
         assert _rel(v.grad, T(fx["grad." + k])) < 1e-4, k
+
+
+def test_oracle_softplus_and_spade_match_reference():
+    """mlp.beta = 10 (softplus, resnetfc.py:43-46,:138-141) with mlp.use_spade (x = scale_z(z) * x + lin_z(z),
+    :130-136,:184-186) against the reference's outputs and gradients (small_softplus_spade.npz)."""
+    fx = golden("small_softplus_spade")
+    ci = _case_inputs(fx)
+    beta = float(fx["beta"])
+    assert "scale_z.2.weight" in ci["params"] and beta == 10.0
+    pr = {k: v.clone().requires_grad_(True) for k, v in ci["params"].items()}
+    vol = T(fx["vol"]).clone().requires_grad_(True)
+    out = O.forward_nerf(pr, vol, T(fx["rays"]), syn.BOUNDS, ci["Kc"], ci["Kf"], noise=ci["noise"],
+                         eval_batch_size=1024, beta=beta, use_spade=True)
+    loss = 0.0
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "embed", "depth"):
+            assert _rel(out[lvl][k], T(fx[f"{lvl}_{k}"])) < 2e-6, (lvl, k)
+            loss = loss + (out[lvl][k] * T(fx[f"probe_{lvl}_{k}"])).sum()
+    assert abs(float(loss) - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+    loss.backward()
+    assert _rel(vol.grad, T(fx["vgrad"])) < 1e-5
+    for k, v in pr.items():
+        assert _rel(v.grad, T(fx["grad." + k])) < 1e-4, k

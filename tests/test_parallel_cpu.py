@@ -156,6 +156,9 @@ def test_renderer_keeps_reference_surface():
     cv = NR.NeuralRenderer(U.default_config(use_code_viewdirs=True, normalize_z=True), torch.zeros(6))
     assert cv._composed and cv.nerf_model.d_in == 78 and cv.nerf_model.code.d_out == 78      # models_embed.py:86-95
     assert cv.nerf_model.mlp_coarse.lin_in.weight.shape == (512, 78) and len(cv.state_dict()) == 62
+    sp = NR.NeuralRenderer(U.default_config(mlp=dict(beta=10.0, use_spade=True)), torch.zeros(6))   # resnetfc.py:130-141
+    assert sp._composed and sp.nerf_model.mlp_coarse.general and len(sp.state_dict()) == 62 + 2 * 6
+    assert sp.nerf_model.mlp_coarse.scale_z[2].weight.shape == (512, 128)
     with pytest.raises(NotImplementedError):      # a debugger breakpoint in the reference (models_embed.py:350-352)
         NR.NeuralRenderer(U.default_config(use_freenerf=True), torch.zeros(6))
     with pytest.raises(NotImplementedError):
