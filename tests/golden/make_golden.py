@@ -21,6 +21,8 @@ Cases
   small_codeviewdirs      : use_code_viewdirs (view direction through the positional encoding, d_in = 78) with
                             normalize_z = True (a no-op under the hard-coded canon_xyz) and depth-guided samples.
   small_softplus_spade    : mlp.beta = 10 (softplus activations) with mlp.use_spade (latent-modulated residual stream).
+  extract_small           : the ancestor renderer's extract_radience (nerf_embed.py:432-516, imported unmodified) over the
+                            reference's field model: points / rgbs / sigmas / embeds at given sorted sample depths.
   raygen                  : gen_rays for 60x80 (focal 76.18187) and rows of 128x128 (focal 153).
   voxelize_small          : the reference's VoxelGrid.coords_to_bounding_voxel_grid (voxel_grid_real.py) on a seeded
                             clustered point cloud (inputs regenerated from the seed by synthetic.voxelizer_points).
@@ -396,6 +398,61 @@ def run_softplus_spade_case(name="small_softplus_spade", S=12, C=16, D=24, hidde
     print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "loss", float(loss))
 
 
+def run_extract_case(name="extract_small", S=12, C=16, D=24, hidden=64, SB=2, n_rays=24, K=20, H=16, W=16, focal=19.0,
+                     seed=12):
+    """The ancestor renderer's `extract_radience` (featurenerf_robo/featurenerf/src/render/nerf_embed.py:432-516), imported
+    unmodified (its `util` import stubbed: the method does not use it), driven with the reference's own field model
+    (PixelNeRFEmbedNet after encode(); the ancestor expects a model that returns the value tensor, this repo's returns
+    (value, point_density): the wrapper takes element 0) on sorted sample depths: points, rgbs, sigmas, embeds."""
+    import importlib.util
+    torch.manual_seed(seed)
+    cfg = L.default_cfg(d_embed=D, d_latent=C, voxel_shape=S, image_width=W, image_height=H, n_coarse=K, n_fine=0,
+                        n_fine_depth=0, ray_chunk_size=n_rays, mlp=dict(d_hidden=hidden), eval_batch_size=256)
+    ren = L.build_reference_renderer(cfg, torch.tensor(syn.BOUNDS))
+    params = O.init_params(d_in=42, d_latent=C, d_hidden=hidden, d_out=4 + D, seed=seed)
+    g = torch.Generator().manual_seed(77 + seed)
+    for k in params:
+        if k.endswith(".bias"):
+            params[k] = 0.05 * torch.randn(params[k].shape, generator=g)
+    load_params_into(ren, params)
+    sys.modules.setdefault("util", mock.MagicMock())
+    spec = importlib.util.spec_from_file_location(
+        "_nrf_ancestor_nerf_embed", "/root/reference/featurenerf_robo/featurenerf/src/render/nerf_embed.py")
+    anc_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(anc_mod)
+    anc = anc_mod.NeRFEmbedRenderer(n_coarse=K, n_fine=0, eval_batch_size=256)
+
+    class Model:
+        use_viewdirs = True
+
+        def __call__(self, pnts, coarse=True, viewdirs=None):
+            return ren.nerf_model(pnts, coarse=coarse, viewdirs=viewdirs)[0]
+
+    vol = syn.make_volume(SB, C, S, seed=seed)
+    poses = syn.arc_poses(SB)
+    focal_t = torch.tensor(focal, dtype=torch.float32)
+    idx = syn.pick_ray_indices(H * W, n_rays, seed=seed)
+    U = sys.modules["_nrf_reference_utils"]
+    rays = U.gen_rays(poses, W, H, focal_t, cfg.z_near, cfg.z_far, c=None).reshape(SB, H * W, 8)[:, idx].reshape(-1, 8)
+    R = rays.shape[0]
+    z = rays[:, 6:7] + (rays[:, 7:8] - rays[:, 6:7]) * torch.rand(R, K, generator=g)
+    z, _ = torch.sort(z, dim=-1)
+    ren.eval()
+    ren.encode(None, None, None, vol, poses, focal_t, None)
+    with torch.no_grad():
+        pts, rgbs, sigmas, embeds = anc.extract_radience(Model(), rays, z, coarse=True, sb=SB)
+    assert pts.shape == (SB, n_rays * K, 3) and embeds.shape == (SB, n_rays * K, D)   # (sb = 0 hands the model 2-D points,
+                                                                                     # which models_embed.py:307 rejects)
+    fx = {"meta": np.array([S, C, D, hidden, SB, n_rays, K, 0, 0, H, W, seed]), "rays": rays.numpy(), "z": z.numpy(),
+          "vol": vol.numpy(), "points": pts.numpy(), "rgbs": rgbs.numpy(), "sigmas": sigmas.numpy(),
+          "embeds": embeds.numpy()}
+    for k, v in params.items():
+        fx["param." + k] = v.numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **fx)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "sigma max", float(sigmas.max()))
+
+
 def run_raygen():
     L.load_reference()
     U = sys.modules["_nrf_reference_utils"]
@@ -442,6 +499,9 @@ if __name__ == "__main__":
     if "--codeviewdirs-only" in sys.argv:
         run_code_viewdirs_case()
         sys.exit(0)
+    if "--extract-only" in sys.argv:
+        run_extract_case()
+        sys.exit(0)
     if "--softplus-spade-only" in sys.argv:
         run_softplus_spade_case()
         sys.exit(0)
@@ -450,6 +510,7 @@ if __name__ == "__main__":
     run_multiscale_case()
     run_code_viewdirs_case()
     run_softplus_spade_case()
+    run_extract_case()
     run_voxelizer()
     run_case("small_kfd0", S=12, C=16, D=24, hidden=64, SB=2, n_rays=48, Kc=16, Kf=16, Kfd=0,
              H=16, W=16, focal=19.0, store_inputs=True)

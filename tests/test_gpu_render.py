@@ -1042,6 +1042,23 @@ def test_radiance_and_point_cloud_extraction(ops, NR):
     assert torch.equal(e.cpu(), r_emb[mask_ref])
 
 
+def test_extract_radience_matches_the_ancestor_fixture(ops, NR):
+    """extract.extract_radience (fp32 parity mode and the bf16 fast path) against the ancestor renderer's own output for
+    the same inputs (tests/golden/extract_small.npz: nerf_embed.py:432-516 run unmodified by make_golden.py)."""
+    ext = load_pkg("extract")
+    fx = golden("extract_small")
+    ci = _case_inputs(fx)
+    meta = [int(v) for v in fx["meta"]]
+    for precision, tol in (("fp32", 1e-4), ("bf16", 3e-2)):
+        ren = make_renderer(NR, meta, ci["params"], precision).eval()
+        ren.encode(None, None, None, T(fx["vol"]).cuda(), None, None, None)
+        pts, rgbs, sigmas, embeds = ext.extract_radience(ren, None, T(fx["rays"]).cuda(), T(fx["z"]).cuda(),
+                                                         coarse=True, sb=ci["SB"])
+        assert torch.equal(pts.cpu(), T(fx["points"]))                      # sample positions: bit-exact
+        assert rel(rgbs, T(fx["rgbs"])) < tol and rel(sigmas, T(fx["sigmas"])) < tol, precision
+        assert rel(embeds, T(fx["embeds"])) < tol, precision
+
+
 def test_training_script_call_sites_run_unchanged(ops, NR):
     """The call sites of train_nerfact_multi_kitchen.py, with the script's own keywords and nerfact.conf's shapes
     (:1100-1103 60 x 80 images, focal 76.18; nerfact.conf:22-28,:74-76 d_embed 512, d_latent 64, 64 + 64 samples of which

@@ -250,3 +250,17 @@ def test_oracle_softplus_and_spade_match_reference():
     assert _rel(vol.grad, T(fx["vgrad"])) < 1e-5
     for k, v in pr.items():
         assert _rel(v.grad, T(fx["grad." + k])) < 1e-4, k
+
+
+def test_oracle_extract_radience_matches_the_ancestor_renderer():
+    """oracle.extract_radience against the ancestor's own method (featurenerf_robo/featurenerf/src/render/nerf_embed.py:
+    432-516, run unmodified over the reference's field model by make_golden.py: extract_small.npz)."""
+    fx = golden("extract_small")
+    ci = _case_inputs(fx)
+    with torch.no_grad():
+        pts, rgbs, sigmas, embeds = O.extract_radience(ci["params"], T(fx["vol"]), T(fx["rays"]), T(fx["z"]), ci["SB"],
+                                                       syn.BOUNDS)
+    assert torch.equal(pts, T(fx["points"]))
+    assert rgbs.shape == T(fx["rgbs"]).shape and sigmas.shape == T(fx["sigmas"]).shape
+    assert _rel(rgbs, T(fx["rgbs"])) < 2e-6 and _rel(sigmas, T(fx["sigmas"])) < 2e-6
+    assert _rel(embeds, T(fx["embeds"])) < 2e-6 and float(T(fx["sigmas"]).max()) > 0
