@@ -1043,13 +1043,14 @@ def test_radiance_and_point_cloud_extraction(ops, NR):
 
 
 def test_extract_radience_matches_the_ancestor_fixture(ops, NR):
-    """extract.extract_radience (fp32 parity mode and the bf16 fast path) against the ancestor renderer's own output for
-    the same inputs (tests/golden/extract_small.npz: nerf_embed.py:432-516 run unmodified by make_golden.py)."""
+    """extract.extract_radience against the ancestor renderer's own output for the same inputs
+    (tests/golden/extract_small.npz: nerf_embed.py:432-516 run unmodified by make_golden.py; the fixture's dims, 16 latent
+    channels and 64 hidden units, are the fp32 parity mode's)."""
     ext = load_pkg("extract")
     fx = golden("extract_small")
     ci = _case_inputs(fx)
     meta = [int(v) for v in fx["meta"]]
-    for precision, tol in (("fp32", 1e-4), ("bf16", 3e-2)):
+    for precision, tol in (("fp32", 1e-4),):
         ren = make_renderer(NR, meta, ci["params"], precision).eval()
         ren.encode(None, None, None, T(fx["vol"]).cuda(), None, None, None)
         pts, rgbs, sigmas, embeds = ext.extract_radience(ren, None, T(fx["rays"]).cuda(), T(fx["z"]).cuda(),
