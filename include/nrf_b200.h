@@ -324,6 +324,10 @@ typedef struct {
   const void* touch_flags; /* NULL, or the (N + 31) / 32 bytes nrf_encode_points_touch wrote for these N samples: dlatent
                           is then only computed for 128-sample tiles with a flag set; the rows of the other tiles are
                           left unwritten (nothing reads them: the volume scatter visits in-grid corners only) */
+  void* dlatent_ready_event; /* NULL, or a cudaEvent_t the call records on `stream` as soon as `dlatent` is complete: in
+                          the default (fused, one-launch weight-gradient) path that is BEFORE the weight gradients are
+                          enqueued - the dL/dz GEMM is then issued first - so that a caller's volume scatter on a second
+                          stream runs under them; in every other path, when the whole backward is enqueued */
 } NrfMlpGrads;
 
 /* Sizes (bytes) of the caller-provided buffers for a given shape / precision. */

@@ -51,7 +51,7 @@ class NrfMlpGrads(C.Structure):
     _fields_ = [("lin_in_w", c_ptr), ("lin_in_b", c_ptr), ("lin_out_w", c_ptr), ("lin_out_b", c_ptr),
                 ("fc0_w", _PA), ("fc0_b", _PA), ("fc1_w", _PA), ("fc1_b", _PA),
                 ("lin_z_w", _PA), ("lin_z_b", _PA), ("deterministic", C.c_int), ("d_last", c_ptr),
-                ("touch_flags", c_ptr)]
+                ("touch_flags", c_ptr), ("dlatent_ready_event", c_ptr)]
 
 
 class NrfMlpSizes(C.Structure):

@@ -409,7 +409,7 @@ extern "C" int nrf_mlp_fwd_layered(const NrfMlpParams* p, const void* packed, in
 
 static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
                         int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* gr,
-                        float* dlatent, void* scratch, void* stream, bool force_layered) {
+                        float* dlatent, void* scratch, void* stream, bool force_layered, bool* event_recorded) {
   NRF_REQUIRE(packed && field_in && acts && d_field && gr && scratch && N > 0, NRF_EINVAL,
               "nrf_mlp_bwd: bad arguments");
   NRF_REQUIRE(N < (int64_t)1 << 31, NRF_ENOSUP, "nrf_mlp_bwd: N too large for one call");
@@ -550,7 +550,11 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
             if (!h.prob[h.n_prob - 1].dbias) h.prob[h.n_prob - 1].blocks = blocks;
           }
         field_in_problem(operand(gx(0), L.H, L.H), 0);
-        TRY(wgrad_multi_launch(h, s));
+        // With NrfMlpGrads.dlatent_ready_event the dL/dz GEMM goes FIRST and the event is recorded behind it: the
+        // caller's volume scatter (on a stream of its own) then runs under the weight gradients.  Same kernels, same
+        // operands: nothing changes numerically.
+        const bool dz_first = gr->dlatent_ready_event != nullptr;
+        if (!dz_first) TRY(wgrad_multi_launch(h, s));
         NrfGemm g = gemm_init(N, (int)round_up(L.C, 128), L.C);
         for (int b = 0; b < L.nz; ++b) set_a(g, b, gx(b), L.H, L.H);
         g.B = W + L.WzcatT; g.ldb = L.nz * L.H;
@@ -559,6 +563,11 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
         // never read: the scatter visits in-grid corners only); the list lives in the idle split-reduction workspace
         if (live && g.N == 128) TRY(gemm_tc_launch(g, kFmtBf16, s, live));
         else TRY(run_gemm(g, precision, true, s));
+        if (dz_first) {
+          NRF_CUDA_OK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(gr->dlatent_ready_event), s));
+          *event_recorded = true;
+          TRY(wgrad_multi_launch(h, s));
+        }
         return NRF_OK;
       }
     }
@@ -660,14 +669,28 @@ static int mlp_bwd_impl(const NrfMlpParams* p, const void* packed, int precision
   return NRF_OK;
 }
 
+// NrfMlpGrads.dlatent_ready_event: the one-launch weight-gradient path records it right behind the dL/dz GEMM, before
+// the weight gradients; every other path records it here, when the whole backward is enqueued - "dlatent is complete
+// once the event has fired" holds either way.  (Never both: a stream that waits on an event waits for its LATEST record.)
+static int mlp_bwd_entry(const NrfMlpParams* p, const void* packed, int precision, const void* field_in, int64_t N,
+                         const void* acts, const void* d_field, const NrfMlpGrads* gr, float* dlatent, void* scratch,
+                         void* stream, bool force_layered) {
+  bool recorded = false;
+  int rc = mlp_bwd_impl(p, packed, precision, field_in, N, acts, d_field, gr, dlatent, scratch, stream, force_layered,
+                        &recorded);
+  if (rc == NRF_OK && gr && gr->dlatent_ready_event && !recorded)
+    NRF_CUDA_OK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(gr->dlatent_ready_event), as_stream(stream)));
+  return rc;
+}
+
 extern "C" int nrf_mlp_bwd(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
                            int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* gr,
                            float* dlatent, void* scratch, void* stream) {
-  return mlp_bwd_impl(p, packed, precision, field_in, N, acts, d_field, gr, dlatent, scratch, stream, false);
+  return mlp_bwd_entry(p, packed, precision, field_in, N, acts, d_field, gr, dlatent, scratch, stream, false);
 }
 
 extern "C" int nrf_mlp_bwd_layered(const NrfMlpParams* p, const void* packed, int precision, const void* field_in,
                                    int64_t N, const void* acts, const void* d_field, const NrfMlpGrads* gr,
                                    float* dlatent, void* scratch, void* stream) {
-  return mlp_bwd_impl(p, packed, precision, field_in, N, acts, d_field, gr, dlatent, scratch, stream, true);
+  return mlp_bwd_entry(p, packed, precision, field_in, N, acts, d_field, gr, dlatent, scratch, stream, true);
 }

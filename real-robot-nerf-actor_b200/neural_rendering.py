@@ -615,7 +615,7 @@ def _coord_raw(ren, st):
 
 
 def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, want_dz=False, first=True,
-                   defer=None, d_coord_raw=None):
+                   defer=None, d_coord_raw=None, dlatent_event=None):
     res = ops.composite_bwd(st.field_out, st.z, st.rays, ren._d_comp, d_rgb, d_embed, d_depth, d_weights,
                             ldg=st.mlp.sizes.dout_pad, precision=st.mlp.precision,
                             white_bkgd=ren.white_bkgd, want_dz=want_dz, sigma_noise=st.sig_noise)
@@ -624,7 +624,8 @@ def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, 
         R, K = st.z.shape
         o = 4 + ren._d_embed
         d_field.view(R, K, -1)[:, :, o:o + 3] += d_coord_raw.to(d_field.dtype)
-    dlat = st.mlp.backward(st.field_in, st.acts, d_field, grads, deterministic=ren.deterministic, touch=st.touch)
+    dlat = st.mlp.backward(st.field_in, st.acts, d_field, grads, deterministic=ren.deterministic, touch=st.touch,
+                           dlatent_event=dlatent_event)
     if defer is not None:             # one merged scatter for all passes once the last one is through
         defer.append((st.z, dlat))
     elif ren.scatter == "sorted":     # atomics-free, bit-reproducible; the first pass writes every voxel row
@@ -632,6 +633,19 @@ def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, 
     else:                             # fp32 vector reductions into a zeroed volume
         ops.scatter_volume_grad(st.rays, st.z, st.rps, dlat, grad_cl, ren._bounds)
     return d_z
+
+
+def _scatter_side(ren, dev):
+    """(stream, event) of `dev` for the overlapped volume scatter, made on first use; the event is recorded once so
+    that its CUDA handle exists before the C ABI is given it."""
+    cache = ren.__dict__.setdefault("_scatter_side_cache", {})
+    hit = cache.get(dev.index)
+    if hit is None:
+        with torch.cuda.device(dev):
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            hit = cache[dev.index] = (torch.cuda.Stream(device=dev), ev)
+    return hit
 
 
 def _merged_scatter_ok(ren, vol_shape_cl):
@@ -843,13 +857,29 @@ class _ForwardNerfFn(torch.autograd.Function):
                 d_cat = torch.zeros(R, K, device=dev, dtype=torch.float32)
                 d_cat.scatter_(1, st_f.perm.long(), d_z)
                 d_cdep = d_cdep + (d_cat[:, K - Kfd:] * ctx.depth_mask).sum(-1)
+        # overlap_scatter: the last pass's backward records an event as soon as its dL/dlatent is complete - ahead of its
+        # weight gradients - and the merged volume scatter (HBM-bound, one 18 KB CTA fits beside a weight-gradient CTA)
+        # runs on a stream of its own under them
+        overlap = merged and want_vol and ren.overlap_scatter and not torch.cuda.is_current_stream_capturing()
+        ev = _scatter_side(ren, dev)[1] if overlap else None
         _pass_backward(ren, st_c, _zeros_like_or(d_crgb, (R, 3), dev), _zeros_like_or(d_cemb, (R, D), dev),
-                       d_cdep, d_cw, grads_c, grad_cl, first=st_f is None, defer=defer, d_coord_raw=d_ccoord)
+                       d_cdep, d_cw, grads_c, grad_cl, first=st_f is None, defer=defer, d_coord_raw=d_ccoord,
+                       dlatent_event=ev)
         # every MLP gradient of this step is final: start their all-reduce now, it overlaps the volume scatter
         pending = _start_grad_allreduce(ren, grads_c, grads_f)
         d_vol = None
         if want_vol:
-            if merged:
+            if overlap:
+                main = torch.cuda.current_stream(dev)
+                side = _scatter_side(ren, dev)[0]
+                side.wait_event(ev)               # both passes' dlatent (and everything enqueued before) are complete
+                with torch.cuda.stream(side):
+                    d_vol = _finish_volume_grad(ren, st_c.rays, st_c.rps, defer, ctx.vol_shape, ctx.cl3d)
+                main.wait_stream(side)
+                d_vol.record_stream(main)         # allocated on the side stream, consumed (and freed) on this one
+                if ren.last_voxel_counts is not None and getattr(ren, "keep_voxel_counts", False):
+                    ren.last_voxel_counts.record_stream(main)
+            elif merged:
                 d_vol = _finish_volume_grad(ren, st_c.rays, st_c.rps, defer, ctx.vol_shape, ctx.cl3d)
             else:
                 d_vol = grad_cl.permute(0, 4, 1, 2, 3) if ctx.cl3d else ops.volume_to_channels_first(grad_cl)
@@ -935,6 +965,9 @@ class NeuralRenderer(nn.Module):
         # (ops.TouchedRelayout; NRF_SPARSE_RELAYOUT=0: always the dense pass)
         self.sparse_relayout = os.environ.get("NRF_SPARSE_RELAYOUT", "1") != "0"
         self.sparse_relayout_ratio = float(os.environ.get("NRF_SPARSE_RELAYOUT_RATIO", "0.25"))   # samples per voxel below which it pays
+        # the volume scatter of a training step on a side stream under the last pass's weight gradients (see
+        # _ForwardNerfFn.backward); NRF_SCATTER_OVERLAP=1 switches it on
+        self.overlap_scatter = os.environ.get("NRF_SCATTER_OVERLAP", "0") == "1"
         self.keep_voxel_counts = False         # True: the backward leaves the per-voxel entry counts of its scatter in
         self.last_voxel_counts = None          # `last_voxel_counts` (what the sparse volume-gradient exchange sends)
         self._num_freqs = self.nerf_model.code.num_freqs

@@ -683,13 +683,15 @@ class FieldMLP:
 
     @_on_tensor_device
     def backward(self, field_in, acts, d_field, grads: dict, scratch=None, deterministic=False, layered=False,
-                 d_last=None, touch=None):
+                 d_last=None, touch=None, dlatent_event=None):
         """Accumulates parameter grads into `grads` (same keys as params); returns dlatent (N,C).
         deterministic: ordered (bit-reproducible) reduction of the weight-gradient sample splits.
         d_last (N, d_hidden): gradient w.r.t. the last residual stream (layered chain only).
         touch: the uint8 flags of encode_points(want_touch=True) for these samples: dlatent is then only computed for
         128-sample tiles with a sample inside the grid - rows of the other tiles are UNINITIALISED (the volume scatter
-        never reads them)."""
+        never reads them).
+        dlatent_event: a torch.cuda.Event (already recorded once, so that its handle exists) that the call records as
+        soon as dlatent is complete - ahead of the weight gradients in the default path (NrfMlpGrads.dlatent_ready_event)."""
         N = field_in.shape[0]
         dev = field_in.device
         d_latent = self.dims[1]
@@ -706,6 +708,11 @@ class FieldMLP:
         if touch is not None:
             assert touch.dtype == torch.uint8 and touch.is_contiguous() and touch.numel() == (N + 31) // 32
             g.touch_flags = touch.data_ptr()
+        if dlatent_event is not None:
+            handle = int(dlatent_event.cuda_event)
+            if not handle:
+                raise _lib.NrfError("dlatent_event has no CUDA handle yet: record it once before handing it over")
+            g.dlatent_ready_event = handle
         lib = _lib.load()
         layered = layered or getattr(acts, "_nrf_layered", False)
         fn = lib.nrf_mlp_bwd_layered if layered else lib.nrf_mlp_bwd

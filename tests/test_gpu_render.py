@@ -669,6 +669,38 @@ def test_bf16_training_step_is_reproducible_when_asked(ops, NR):
         assert torch.equal(runs[0][1][k], runs[1][1][k]), k
 
 
+def test_scatter_under_the_weight_gradients_changes_nothing(ops, NR):
+    """renderer.overlap_scatter: the last pass's backward issues its dL/dz GEMM before its weight gradients and records an
+    event (NrfMlpGrads.dlatent_ready_event); the merged volume scatter runs on a side stream behind that event, under the
+    weight gradients.  Same kernels on the same operands: outputs and the volume gradient bit for bit (both memory
+    formats of the volume), parameter gradients to the rounding of their fp32 atomics; five steps in a row, so that
+    buffers handed between the two streams are reused."""
+    fx = golden("full_s32")
+    meta = [int(v) for v in fx["meta"]]
+    inp = syn_case_inputs(fx)
+    ren = make_renderer(NR, meta, inp["params"], "bf16")
+    assert ren.nerf_model.mlp_coarse.handle(ops.NRF_PREC_BF16).fused
+    for fmt in (torch.contiguous_format, torch.channels_last_3d):
+        vol = inp["vol"].contiguous(memory_format=fmt)
+        res = {}
+        for overlap in (False, True, True, False, True):
+            ren.overlap_scatter = overlap
+            for p in ren.parameters():
+                p.grad = None
+            out, loss, vg, pg = _run_cuda(ren, vol, inp["rays"], inp["noise"], inp["gt_rgb"], inp["gt_embed"])
+            torch.cuda.synchronize()
+            cur = (out.fine.embed.clone(), float(loss), vg.clone(), {k: v.clone() for k, v in pg.items()})
+            if not res:
+                res = cur
+                assert float(vg.abs().sum()) > 0
+                continue
+            assert torch.equal(cur[0], res[0]) and cur[1] == res[1], overlap
+            assert torch.equal(cur[2], res[2]), overlap
+            for k in res[3]:
+                assert rel(cur[3][k], res[3][k]) < 1e-5, (overlap, k)
+    ren.overlap_scatter = False
+
+
 def test_channels_last_3d_volume_is_taken_without_relayout(ops, NR):
     """A voxel volume in torch.channels_last_3d memory format (what a conv3d producer run in that format hands
     over) gives bit-identical outputs and gradients; its gradient comes back in the same format."""
