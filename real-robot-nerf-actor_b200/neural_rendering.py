@@ -386,9 +386,13 @@ class PixelNeRFEmbedNet(nn.Module):
         A bf16 / fp16 volume (a voxel encoder run under torch.autocast) is widened to fp32 here: what autocast itself
         does to the reference's F.grid_sample (models_embed.py:275; grid_sampler is on autocast's fp32 list) - the
         gather then interpolates in fp32 and autograd returns the volume gradient in the producer's dtype."""
-        if torch.is_tensor(voxel_feat) and voxel_feat.dtype in (torch.bfloat16, torch.float16):
+        low = (torch.bfloat16, torch.float16)
+        if torch.is_tensor(voxel_feat) and voxel_feat.dtype in low:
             voxel_feat = voxel_feat.float()       # keeps the memory format (channels_last_3d stays zero-copy below)
         self.voxel_feat = voxel_feat
+        if self.use_multi_scale_voxel and multi_scale_voxel_list is not None:
+            multi_scale_voxel_list = [v.float() if torch.is_tensor(v) and v.dtype in low else v
+                                      for v in multi_scale_voxel_list]
         self.multi_scale_voxel_list = multi_scale_voxel_list if self.use_multi_scale_voxel else None   # :147-149
         self.voxel_density = None
         self.language = lang
@@ -635,16 +639,19 @@ def _pass_backward(ren, st, d_rgb, d_embed, d_depth, d_weights, grads, grad_cl, 
     return d_z
 
 
+_SCATTER_SIDE = {}      # device index -> (stream, event); per process, not per renderer: a backward records and waits on
+                        # the event within one host call, and keeping CUDA handles out of the module keeps it picklable
+
+
 def _scatter_side(ren, dev):
     """(stream, event) of `dev` for the overlapped volume scatter, made on first use; the event is recorded once so
     that its CUDA handle exists before the C ABI is given it."""
-    cache = ren.__dict__.setdefault("_scatter_side_cache", {})
-    hit = cache.get(dev.index)
+    hit = _SCATTER_SIDE.get(dev.index)
     if hit is None:
         with torch.cuda.device(dev):
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
-            hit = cache[dev.index] = (torch.cuda.Stream(device=dev), ev)
+            hit = _SCATTER_SIDE[dev.index] = (torch.cuda.Stream(device=dev), ev)
     return hit
 
 
